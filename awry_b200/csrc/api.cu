@@ -1,0 +1,1302 @@
+// api.cu -- host side of libawry_b200: `.awry` v1 loader, device replicas, the batched
+// count / locate pipelines and the extern "C" boundary declared in include/awry_b200.h.
+//
+// Reference host code this stands in for (paths under /root/reference/src):
+//   FmIndex::load / read_fm_index_by_version_number   fm_index_file.rs:132-160, :184-287
+//   KmerLookupTable::from_file (skipped, Q1/Q2)        kmer_lookup_table.rs:55-77
+//   SequenceIndex::from_file                           sequence_index.rs:155-183
+//   parallel_count / parallel_locate (rayon map)       fm_index.rs:455-487
+#include <algorithm>
+#include <atomic>
+#include <cerrno>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/awry_b200.h"
+#include "kernels.hpp"
+
+using namespace awry;
+
+namespace {
+
+thread_local char g_err[1024] = "";
+
+struct ApiError : std::runtime_error {
+  int code;
+  ApiError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+[[noreturn]] void fail(int code, const char* fmt, ...) {
+  char buf[900];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw ApiError(code, buf);
+}
+
+#define CU(expr)                                                                          \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess)                                                               \
+      fail(AWRY_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return AWRY_OK;
+  } catch (const ApiError& e) {
+    snprintf(g_err, sizeof g_err, "%s", e.what());
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    snprintf(g_err, sizeof g_err, "out of host memory");
+    return AWRY_ERR_NOMEM;
+  } catch (const std::exception& e) {
+    snprintf(g_err, sizeof g_err, "%s", e.what());
+    return AWRY_ERR_INVALID_ARG;
+  } catch (...) {
+    snprintf(g_err, sizeof g_err, "unknown error");
+    return AWRY_ERR_INVALID_ARG;
+  }
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    CU(cudaSetDevice(dev));
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// ------------------------------------------------------------------ profiling
+
+struct ProfState {
+  std::mutex mu;
+  bool enabled = false;
+  struct Span {
+    cudaEvent_t a, b;
+    int kind;  // 0 search, 1 walk, 2 pack
+    int device;
+  };
+  std::vector<Span> spans;
+  uint64_t n[3] = {0, 0, 0};
+  double ms[3] = {0, 0, 0};
+  std::atomic<uint64_t> h2d{0}, d2h{0};
+} g_prof;
+
+struct ProfScope {
+  bool on;
+  cudaStream_t st;
+  ProfState::Span sp{};
+  ProfScope(int kind, int device, cudaStream_t s) : st(s) {
+    on = g_prof.enabled;
+    if (!on) return;
+    sp.kind = kind;
+    sp.device = device;
+    cudaEventCreate(&sp.a);
+    cudaEventCreate(&sp.b);
+    cudaEventRecord(sp.a, st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(sp.b, st);
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    g_prof.spans.push_back(sp);
+  }
+};
+
+void prof_collect_locked() {
+  int prev = -1;
+  cudaGetDevice(&prev);
+  for (auto& s : g_prof.spans) {
+    cudaSetDevice(s.device);
+    float ms = 0;
+    if (cudaEventSynchronize(s.b) == cudaSuccess && cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+      g_prof.ms[s.kind] += ms;
+      g_prof.n[s.kind]++;
+    }
+    cudaEventDestroy(s.a);
+    cudaEventDestroy(s.b);
+  }
+  g_prof.spans.clear();
+  if (prev >= 0) cudaSetDevice(prev);
+}
+
+SearchVariant g_variant;  // experiments only (awry_set_search_variant)
+
+// ------------------------------------------------------------------ index
+
+struct Workspace {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t done = nullptr;
+  // pinned staging
+  uint8_t* h_qbytes = nullptr;
+  size_t h_qbytes_cap = 0;
+  uint64_t* h_qoff = nullptr;
+  size_t h_qoff_cap = 0;  // entries
+  uint8_t* h_out = nullptr;
+  size_t h_out_cap = 0;  // bytes
+  unsigned long long* h_flag = nullptr;
+  // device
+  uint8_t* d_qbytes = nullptr;
+  size_t d_qbytes_cap = 0;
+  uint64_t* d_qoff = nullptr;
+  size_t d_qoff_cap = 0;
+  uint64_t* d_qwords = nullptr;
+  size_t d_qwords_cap = 0;
+  uint8_t* d_out = nullptr;
+  size_t d_out_cap = 0;
+  uint64_t* d_hit_off = nullptr;
+  size_t d_hit_off_cap = 0;
+  void* d_temp = nullptr;
+  size_t d_temp_cap = 0;
+  unsigned long long* d_flag = nullptr;
+
+  template <class T>
+  static void grow_dev(T*& p, size_t& cap, size_t need) {
+    if (need <= cap) return;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = need + need / 8 + 256;
+    CU(cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T)));
+    cap = want;
+  }
+  template <class T>
+  static void grow_host(T*& p, size_t& cap, size_t need) {
+    if (need <= cap) return;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = need + need / 8 + 256;
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&p), want * sizeof(T), cudaHostAllocDefault));
+    cap = want;
+  }
+  void init(int dev) {
+    device = dev;
+    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&h_flag), sizeof(unsigned long long), cudaHostAllocDefault));
+    CU(cudaMalloc(reinterpret_cast<void**>(&d_flag), sizeof(unsigned long long)));
+  }
+  void destroy() {
+    cudaSetDevice(device);
+    if (st) cudaStreamSynchronize(st);
+    cudaFreeHost(h_qbytes);
+    cudaFreeHost(h_qoff);
+    cudaFreeHost(h_out);
+    cudaFreeHost(h_flag);
+    cudaFree(d_qbytes);
+    cudaFree(d_qoff);
+    cudaFree(d_qwords);
+    cudaFree(d_out);
+    cudaFree(d_hit_off);
+    cudaFree(d_temp);
+    cudaFree(d_flag);
+    if (done) cudaEventDestroy(done);
+    if (st) cudaStreamDestroy(st);
+  }
+};
+
+struct Replica {
+  int device = 0;
+  int sm_count = 148;
+  uint4* d_blocks = nullptr;
+  uint64_t* d_sa = nullptr;
+  uint2* d_table = nullptr;
+  uint64_t* d_seq_starts = nullptr;
+  unsigned long long* d_async_flag = nullptr;  // first bad query seen by *_device calls
+  size_t bytes_blocks = 0, bytes_sa = 0, bytes_table = 0;
+  IndexView view{};
+  std::mutex ws_mu;
+  std::vector<Workspace*> free_ws;
+  std::vector<Workspace*> all_ws;
+
+  Workspace* acquire() {
+    {
+      std::lock_guard<std::mutex> lk(ws_mu);
+      if (!free_ws.empty()) {
+        Workspace* w = free_ws.back();
+        free_ws.pop_back();
+        return w;
+      }
+    }
+    auto* w = new Workspace();
+    w->init(device);
+    std::lock_guard<std::mutex> lk(ws_mu);
+    all_ws.push_back(w);
+    return w;
+  }
+  void release(Workspace* w) {
+    std::lock_guard<std::mutex> lk(ws_mu);
+    free_ws.push_back(w);
+  }
+};
+
+}  // namespace
+
+struct awry_index {
+  uint64_t version = 1, sa_ratio = 0, bwt_len = 0;
+  int alphabet = 0;
+  int card = 6;
+  uint32_t kmer_len_file = 0, kmer_len_dev = 0;
+  uint64_t prefix_sums[23] = {0};
+  uint64_t n_sa_words = 0;
+  uint32_t sa_bits = 0;
+  std::vector<uint64_t> seq_starts;
+  std::vector<std::string> headers;
+  std::vector<std::unique_ptr<Replica>> reps;
+};
+
+namespace {
+
+uint32_t bits_per_element(uint64_t bwt_len) {  // compressed_suffix_array.rs:124-130
+  uint64_t v = bwt_len - 1;
+  return v ? 64u - uint32_t(__builtin_clzll(v)) : 0u;
+}
+uint64_t sa_word_len(uint64_t bwt_len, uint64_t ratio) {  // compressed_suffix_array.rs:113-123
+  unsigned __int128 t = (unsigned __int128)((bwt_len + ratio - 1) / ratio) * bits_per_element(bwt_len);
+  return uint64_t((t + 63) / 64);
+}
+uint64_t ipow(uint64_t b, uint32_t e) {
+  uint64_t r = 1;
+  while (e--) r *= b;
+  return r;
+}
+
+// sequential byte source: a file (FmIndex::load) or caller memory sections (FmIndex::new hand-over)
+struct Source {
+  FILE* f = nullptr;
+  std::vector<std::pair<const uint8_t*, size_t>> segs;
+  size_t cur = 0, off = 0;
+  void read(void* dst, size_t n, const char* what) {
+    if (n == 0) return;
+    if (f) {
+      if (fread(dst, 1, n, f) != n) fail(AWRY_ERR_IO, "unexpected end of file while reading %s", what);
+      return;
+    }
+    uint8_t* d = static_cast<uint8_t*>(dst);
+    while (n) {
+      if (cur >= segs.size()) fail(AWRY_ERR_INVALID_ARG, "index parts too short while reading %s", what);
+      size_t take = std::min(segs[cur].second - off, n);
+      memcpy(d, segs[cur].first + off, take);
+      off += take;
+      d += take;
+      n -= take;
+      if (off == segs[cur].second) {
+        cur++;
+        off = 0;
+      }
+    }
+  }
+};
+
+void set_view_constants(awry_index* ix, Replica& r) {
+  IndexView& v = r.view;
+  v.blocks = r.d_blocks;
+  v.sa_words = r.d_sa;
+  v.table = r.d_table;
+  v.seq_starts = r.d_seq_starts;
+  v.bwt_len = uint32_t(ix->bwt_len);
+  v.sa_ratio = uint32_t(ix->sa_ratio);
+  v.sa_pow2 = (ix->sa_ratio & (ix->sa_ratio - 1)) == 0 ? 1u : 0u;
+  v.sa_ratio_shift = v.sa_pow2 ? uint32_t(__builtin_ctzll(ix->sa_ratio)) : 0u;
+  v.sa_bits = ix->sa_bits;
+  v.kmer_len = ix->kmer_len_dev;
+  v.n_seqs = uint32_t(ix->seq_starts.size());
+  v.alphabet = uint32_t(ix->alphabet);
+  for (int i = 0; i < 24; i++) v.c_lo[i] = 1, v.c_hi[i] = 0;
+  if (ix->alphabet == AWRY_NUCLEOTIDE) {
+    static const int ref_of_dsym[6] = {1, 2, 3, 5, 4, 0};  // A C G T N $
+    for (int d = 0; d < 6; d++) {
+      int ri = ref_of_dsym[d];
+      v.c_lo[d] = uint32_t(ix->prefix_sums[ri]);
+      v.c_hi[d] = uint32_t(ix->prefix_sums[ri + 1] - 1);
+    }
+  } else {
+    for (int s = 0; s < 22; s++) {
+      v.c_lo[s] = uint32_t(ix->prefix_sums[s]);
+      v.c_hi[s] = uint32_t(ix->prefix_sums[s + 1] - 1);
+    }
+  }
+}
+
+// Streams the reference-layout blocks through a pinned double buffer and re-lays them out on
+// the device; then SA words, then the seed table.
+void build_replica0(awry_index* ix, Replica& r, Source& src_blocks_then_rest, bool skip_file_table) {
+  DeviceGuard dg(r.device);
+  CU(init_device_tables());
+  CU(cudaDeviceGetAttribute(&r.sm_count, cudaDevAttrMultiProcessorCount, r.device));
+  const uint64_t n_ref_blocks = (ix->bwt_len + 255) / 256;
+  const size_t ref_block_bytes = ix->alphabet == AWRY_NUCLEOTIDE ? 160 : 352;
+  // nucleotide: 2 x 64-B device blocks per 256-row reference block; amino: one 256-B block
+  r.bytes_blocks = size_t(n_ref_blocks) * (ix->alphabet == AWRY_NUCLEOTIDE ? 128 : 256);
+  CU(cudaMalloc(reinterpret_cast<void**>(&r.d_blocks), r.bytes_blocks + 256));
+  CU(cudaMemset(r.d_blocks, 0, r.bytes_blocks + 256));
+  unsigned int* d_dollar = nullptr;
+  CU(cudaMalloc(reinterpret_cast<void**>(&d_dollar), 4));
+  CU(cudaMemset(d_dollar, 0xff, 4));
+
+  cudaStream_t st;
+  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  const uint64_t CHUNK = 1u << 18;  // reference blocks per staging buffer (40 / 88 MiB)
+  uint8_t* h_stage[2] = {nullptr, nullptr};
+  uint64_t* d_stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2];
+  uint64_t chunk_blocks = std::min<uint64_t>(CHUNK, n_ref_blocks);
+  for (int i = 0; i < 2; i++) {
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&h_stage[i]), chunk_blocks * ref_block_bytes, cudaHostAllocDefault));
+    CU(cudaMalloc(reinterpret_cast<void**>(&d_stage[i]), chunk_blocks * ref_block_bytes));
+    CU(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+  }
+  int slot = 0;
+  for (uint64_t b0 = 0; b0 < n_ref_blocks; b0 += chunk_blocks, slot ^= 1) {
+    uint64_t nb = std::min(chunk_blocks, n_ref_blocks - b0);
+    CU(cudaEventSynchronize(ev[slot]));
+    src_blocks_then_rest.read(h_stage[slot], nb * ref_block_bytes, "bwt blocks");
+    CU(cudaMemcpyAsync(d_stage[slot], h_stage[slot], nb * ref_block_bytes, cudaMemcpyHostToDevice, st));
+    CU(launch_transpose(ix->alphabet, d_stage[slot], b0, nb, ix->bwt_len, r.d_blocks, d_dollar, st));
+    CU(cudaEventRecord(ev[slot], st));
+  }
+  CU(cudaStreamSynchronize(st));
+  unsigned int dollar = 0;
+  CU(cudaMemcpy(&dollar, d_dollar, 4, cudaMemcpyDeviceToHost));
+  cudaFree(d_dollar);
+  if (dollar == 0xffffffffu) fail(AWRY_ERR_FORMAT, "no sentinel row found in the BWT blocks");
+
+  // prefix sums (fm_index_file.rs:265-270)
+  src_blocks_then_rest.read(ix->prefix_sums, size_t(ix->card + 1) * 8, "prefix sums");
+  if (ix->prefix_sums[ix->card] != ix->bwt_len)
+    fail(AWRY_ERR_FORMAT, "prefix sums do not add up to bwt_len (%llu vs %llu)",
+         (unsigned long long)ix->prefix_sums[ix->card], (unsigned long long)ix->bwt_len);
+
+  // sampled suffix array words, verbatim (fm_index_file.rs:272-278)
+  r.bytes_sa = size_t(ix->n_sa_words + 2) * 8;
+  CU(cudaMalloc(reinterpret_cast<void**>(&r.d_sa), r.bytes_sa));
+  CU(cudaMemsetAsync(r.d_sa, 0, r.bytes_sa, st));
+  {
+    const size_t words_per_chunk = chunk_blocks * ref_block_bytes / 8;
+    slot = 0;
+    for (uint64_t w0 = 0; w0 < ix->n_sa_words; w0 += words_per_chunk, slot ^= 1) {
+      uint64_t nw = std::min<uint64_t>(words_per_chunk, ix->n_sa_words - w0);
+      CU(cudaEventSynchronize(ev[slot]));
+      src_blocks_then_rest.read(h_stage[slot], nw * 8, "sampled suffix array");
+      CU(cudaMemcpyAsync(r.d_sa + w0, h_stage[slot], nw * 8, cudaMemcpyHostToDevice, st));
+      CU(cudaEventRecord(ev[slot], st));
+    }
+    CU(cudaStreamSynchronize(st));
+  }
+  for (int i = 0; i < 2; i++) {
+    cudaFreeHost(h_stage[i]);
+    cudaFree(d_stage[i]);
+    cudaEventDestroy(ev[i]);
+  }
+
+  // k-mer table section of the file: 1 byte k, then (card-2)^k x 16 B that the reference never
+  // reads back when searching (kmer_lookup_table.rs:90-110) and that is incomplete.
+  if (skip_file_table) {
+    uint8_t k = 0;
+    src_blocks_then_rest.read(&k, 1, "kmer length");
+    ix->kmer_len_file = k;
+    uint64_t n_entries = ipow(uint64_t(ix->card - 2), k);
+    if (src_blocks_then_rest.f) {
+      if (fseeko(src_blocks_then_rest.f, off_t(n_entries * 16), SEEK_CUR) != 0)
+        fail(AWRY_ERR_IO, "cannot seek past the kmer table");
+    }
+  }
+
+  // sequence starts on the device (filled by the caller into ix->seq_starts before this returns
+  // for parts; for files they follow the table -- read by the caller after this function)
+  r.view.dollar_row = dollar;
+  CU(cudaStreamDestroy(st));
+}
+
+void finish_replica0(awry_index* ix, Replica& r) {
+  DeviceGuard dg(r.device);
+  if (ix->seq_starts.empty()) ix->seq_starts.push_back(0);
+  CU(cudaMalloc(reinterpret_cast<void**>(&r.d_seq_starts), ix->seq_starts.size() * 8));
+  CU(cudaMemcpy(r.d_seq_starts, ix->seq_starts.data(), ix->seq_starts.size() * 8, cudaMemcpyHostToDevice));
+  CU(cudaMalloc(reinterpret_cast<void**>(&r.d_async_flag), 8));
+  CU(cudaMemset(r.d_async_flag, 0xff, 8));
+
+  // device seed table: k_dev = min(k_file, cap); the table only accelerates, results are those
+  // of the plain backward search either way
+  uint32_t cap = ix->alphabet == AWRY_NUCLEOTIDE ? 14 : 6;
+  uint32_t k = std::min<uint32_t>(ix->kmer_len_file, cap);
+  size_t free_b = 0, total_b = 0;
+  CU(cudaMemGetInfo(&free_b, &total_b));
+  while (k > 0 && table_entries(ix->alphabet, k) * 8 > free_b / 4) k--;
+  ix->kmer_len_dev = k;
+  uint32_t dollar = r.view.dollar_row;
+  set_view_constants(ix, r);
+  r.view.dollar_row = dollar;
+  if (k > 0) {
+    r.bytes_table = table_entries(ix->alphabet, k) * 8;
+    CU(cudaMalloc(reinterpret_cast<void**>(&r.d_table), r.bytes_table));
+    r.view.table = r.d_table;
+    IndexView v = r.view;
+    v.kmer_len = 0;
+    CU(launch_build_table(v, r.d_table, k, nullptr));
+    CU(cudaDeviceSynchronize());
+  }
+}
+
+void clone_replica(awry_index* ix, const Replica& src, Replica& dst) {
+  DeviceGuard dg(dst.device);
+  CU(init_device_tables());
+  CU(cudaDeviceGetAttribute(&dst.sm_count, cudaDevAttrMultiProcessorCount, dst.device));
+  dst.bytes_blocks = src.bytes_blocks;
+  dst.bytes_sa = src.bytes_sa;
+  dst.bytes_table = src.bytes_table;
+  CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_blocks), src.bytes_blocks + 256));
+  CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_sa), src.bytes_sa));
+  CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_seq_starts), ix->seq_starts.size() * 8));
+  CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_async_flag), 8));
+  CU(cudaMemset(dst.d_async_flag, 0xff, 8));
+  // fan-out over NVLink instead of N PCIe uploads
+  CU(cudaMemcpyPeer(dst.d_blocks, dst.device, src.d_blocks, src.device, src.bytes_blocks + 256));
+  CU(cudaMemcpyPeer(dst.d_sa, dst.device, src.d_sa, src.device, src.bytes_sa));
+  CU(cudaMemcpyPeer(dst.d_seq_starts, dst.device, src.d_seq_starts, src.device, ix->seq_starts.size() * 8));
+  if (src.bytes_table) {
+    CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_table), src.bytes_table));
+    CU(cudaMemcpyPeer(dst.d_table, dst.device, src.d_table, src.device, src.bytes_table));
+  }
+  uint32_t dollar = src.view.dollar_row;
+  set_view_constants(ix, dst);
+  dst.view.dollar_row = dollar;
+}
+
+std::vector<int> pick_devices(const int* devices, int n_dev) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    fail(AWRY_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+         e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  std::vector<int> out;
+  if (devices == nullptr || n_dev <= 0) {
+    out.push_back(0);
+  } else {
+    for (int i = 0; i < n_dev; i++) {
+      if (devices[i] < 0 || devices[i] >= count) fail(AWRY_ERR_INVALID_ARG, "device %d out of range (0..%d)", devices[i], count - 1);
+      out.push_back(devices[i]);
+    }
+  }
+  for (int d : out) {
+    cudaDeviceProp p;
+    CU(cudaGetDeviceProperties(&p, d));
+    if (p.major < 10) fail(AWRY_ERR_CUDA, "device %d is sm_%d%d; this build targets sm_100a (B200)", d, p.major, p.minor);
+  }
+  return out;
+}
+
+void check_header(awry_index* ix) {
+  if (ix->alphabet != AWRY_NUCLEOTIDE && ix->alphabet != AWRY_AMINO)
+    fail(AWRY_ERR_FORMAT, "invalid symbol alphabet id %d", ix->alphabet);
+  if (ix->sa_ratio == 0) fail(AWRY_ERR_FORMAT, "suffix array compression ratio is 0");
+  if (ix->bwt_len < 2) fail(AWRY_ERR_FORMAT, "bwt_len %llu too small", (unsigned long long)ix->bwt_len);
+  if (ix->bwt_len >= (1ull << 32) - 256)
+    fail(AWRY_ERR_UNSUPPORTED, "bwt_len %llu >= 2^32: the device layout uses 32-bit row pointers",
+         (unsigned long long)ix->bwt_len);
+  if (ix->sa_ratio >= (1ull << 32)) fail(AWRY_ERR_UNSUPPORTED, "suffix array compression ratio too large");
+  ix->card = ix->alphabet == AWRY_NUCLEOTIDE ? 6 : 22;
+  ix->sa_bits = bits_per_element(ix->bwt_len);
+  ix->n_sa_words = sa_word_len(ix->bwt_len, ix->sa_ratio);
+}
+
+void make_replicas(awry_index* ix, const std::vector<int>& devs, Source& src, bool from_file) {
+  for (int d : devs) {
+    auto r = std::make_unique<Replica>();
+    r->device = d;
+    ix->reps.push_back(std::move(r));
+  }
+  Replica& r0 = *ix->reps[0];
+  build_replica0(ix, r0, src, from_file);
+  if (from_file) {
+    // sequence index (sequence_index.rs:155-183)
+    uint64_t n = 0;
+    src.read(&n, 8, "sequence count");
+    if (n > (1ull << 32)) fail(AWRY_ERR_FORMAT, "implausible sequence count");
+    for (uint64_t i = 0; i < n; i++) {
+      uint64_t start = 0, hl = 0;
+      src.read(&start, 8, "sequence start");
+      src.read(&hl, 8, "header length");
+      if (hl > (1ull << 30)) fail(AWRY_ERR_FORMAT, "implausible header length");
+      std::string h(hl, '\0');
+      src.read(h.data(), hl, "header");
+      ix->seq_starts.push_back(start);
+      ix->headers.push_back(std::move(h));
+    }
+  }
+  finish_replica0(ix, r0);
+  for (size_t i = 1; i < ix->reps.size(); i++) clone_replica(ix, r0, *ix->reps[i]);
+}
+
+// ------------------------------------------------------------------ batched pipelines
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+void parallel_memcpy(void* dst, const void* src, size_t n) {
+  const size_t MIN_PER_THREAD = 8u << 20;
+  unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  unsigned nt = unsigned(std::min<size_t>(std::min(hw, 16u), n / MIN_PER_THREAD));
+  if (nt <= 1) {
+    memcpy(dst, src, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; t++) {
+    size_t lo = n * t / nt, hi = n * (t + 1) / nt;
+    th.emplace_back([=] { memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, hi - lo); });
+  }
+  for (auto& x : th) x.join();
+}
+
+constexpr uint64_t CHUNK_MAX_Q = 4u << 20;        // queries per pipeline chunk
+constexpr uint64_t CHUNK_MAX_BYTES = 512u << 20;  // query bytes per pipeline chunk
+
+struct Chunk {
+  uint64_t q0, q1, b0, b1;
+};
+
+std::vector<Chunk> make_chunks(const uint64_t* qoff, uint64_t q_lo, uint64_t q_hi, uint64_t max_q,
+                               uint64_t max_bytes) {
+  std::vector<Chunk> out;
+  uint64_t q = q_lo;
+  while (q < q_hi) {
+    uint64_t hi = std::min(q_hi, q + max_q);
+    // largest hi with qoff[hi] - qoff[q] <= max_bytes (at least one query)
+    if (qoff[hi] - qoff[q] > max_bytes) {
+      uint64_t lo2 = q + 1, hi2 = hi;
+      while (lo2 < hi2) {
+        uint64_t mid = (lo2 + hi2 + 1) / 2;
+        if (qoff[mid] - qoff[q] <= max_bytes)
+          lo2 = mid;
+        else
+          hi2 = mid - 1;
+      }
+      hi = lo2;
+    }
+    out.push_back(Chunk{q, hi, qoff[q], qoff[hi]});
+    q = hi;
+  }
+  return out;
+}
+
+void validate_offsets(const uint64_t* qoff, uint64_t nq) {
+  // cheap sanity check on the ends; per-query monotonicity is checked on the device (prepass)
+  if (nq && qoff[nq] < qoff[0]) fail(AWRY_ERR_INVALID_ARG, "query offsets are not monotone");
+}
+
+// Uploads one chunk of queries and runs prepass + search on ws->st.  The search result lands
+// in ws->d_out in the requested mode.
+void enqueue_search(const awry_index* ix, Replica& r, Workspace* ws, const uint8_t* qbytes,
+                    const uint64_t* qoff, const Chunk& c, SearchOut mode, bool src_pinned) {
+  const uint64_t nq = c.q1 - c.q0, nbytes = c.b1 - c.b0;
+  const size_t out_elem = mode == OUT_COUNT_U64 ? 8 : mode == OUT_RANGE_U64 ? 16 : 8;
+  Workspace::grow_dev(ws->d_qbytes, ws->d_qbytes_cap, size_t(nbytes) + 16);
+  Workspace::grow_dev(ws->d_qoff, ws->d_qoff_cap, size_t(nq) + 1);
+  Workspace::grow_dev(ws->d_qwords, ws->d_qwords_cap, size_t(packed_words(ix->alphabet, nq, nbytes)));
+  Workspace::grow_dev(ws->d_out, ws->d_out_cap, size_t(nq) * out_elem);
+  const uint8_t* src_b = qbytes + c.b0;
+  const uint64_t* src_o = qoff + c.q0;
+  if (!src_pinned) {
+    Workspace::grow_host(ws->h_qbytes, ws->h_qbytes_cap, size_t(nbytes) + 16);
+    Workspace::grow_host(ws->h_qoff, ws->h_qoff_cap, size_t(nq) + 1);
+    parallel_memcpy(ws->h_qbytes, src_b, nbytes);
+    parallel_memcpy(ws->h_qoff, src_o, (nq + 1) * 8);
+    src_b = ws->h_qbytes;
+    src_o = ws->h_qoff;
+  }
+  if (nbytes) CU(cudaMemcpyAsync(ws->d_qbytes, src_b, nbytes, cudaMemcpyHostToDevice, ws->st));
+  CU(cudaMemcpyAsync(ws->d_qoff, src_o, (nq + 1) * 8, cudaMemcpyHostToDevice, ws->st));
+  g_prof.h2d += nbytes + (nq + 1) * 8;
+  CU(cudaMemsetAsync(ws->d_flag, 0xff, 8, ws->st));
+  // offsets stay absolute: the kernels subtract the chunk's byte base
+  {
+    ProfScope p(2, r.device, ws->st);
+    CU(launch_pack(ix->alphabet, ws->d_qbytes - c.b0, ws->d_qoff, nq, ws->d_qwords - (c.b0 >> (ix->alphabet == 0 ? 4 : 3)), ws->d_flag, ws->st));
+  }
+  {
+    ProfScope p(0, r.device, ws->st);
+    CU(launch_search(r.view, ws->d_qwords - (c.b0 >> (ix->alphabet == 0 ? 4 : 3)), ws->d_qoff, nq, mode, ws->d_out, g_variant, r.sm_count, ws->st));
+  }
+  CU(cudaMemcpyAsync(ws->h_flag, ws->d_flag, 8, cudaMemcpyDeviceToHost, ws->st));
+}
+
+void check_flag(Workspace* ws, const Chunk& c) {
+  if (*ws->h_flag != ~0ull)
+    fail(AWRY_ERR_INVALID_QUERY,
+         "query %llu is empty or contains a sentinel ('$'/'#'): the reference panics on it "
+         "(fm_index.rs:406, bwt.rs:127)",
+         (unsigned long long)(c.q0 + *ws->h_flag));
+}
+
+// count / range search over [q_lo, q_hi) on one replica, 3-deep pipeline
+void search_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, const uint64_t* qoff,
+                       uint64_t q_lo, uint64_t q_hi, SearchOut mode, void* out) {
+  if (q_lo >= q_hi) return;
+  DeviceGuard dg(r.device);
+  const size_t out_elem = mode == OUT_COUNT_U64 ? 8 : 16;
+  const bool src_pinned = is_pinned(qbytes) && is_pinned(qoff);
+  const bool dst_pinned = is_pinned(out);
+  auto chunks = make_chunks(qoff, q_lo, q_hi, CHUNK_MAX_Q, CHUNK_MAX_BYTES);
+  constexpr int DEPTH = 3;
+  Workspace* ws[DEPTH] = {nullptr, nullptr, nullptr};
+  int pending[DEPTH] = {-1, -1, -1};
+  auto finish = [&](int s) {
+    if (pending[s] < 0) return;
+    const Chunk& c = chunks[size_t(pending[s])];
+    CU(cudaEventSynchronize(ws[s]->done));
+    check_flag(ws[s], c);
+    if (!dst_pinned)
+      parallel_memcpy(static_cast<char*>(out) + c.q0 * out_elem, ws[s]->h_out, (c.q1 - c.q0) * out_elem);
+    pending[s] = -1;
+  };
+  try {
+    for (size_t i = 0; i < chunks.size(); i++) {
+      int s = int(i % DEPTH);
+      if (!ws[s]) ws[s] = r.acquire();
+      finish(s);
+      const Chunk& c = chunks[i];
+      enqueue_search(ix, r, ws[s], qbytes, qoff, c, mode, src_pinned);
+      size_t bytes = (c.q1 - c.q0) * out_elem;
+      void* dst = static_cast<char*>(out) + c.q0 * out_elem;
+      if (!dst_pinned) {
+        Workspace::grow_host(ws[s]->h_out, ws[s]->h_out_cap, bytes);
+        dst = ws[s]->h_out;
+      }
+      CU(cudaMemcpyAsync(dst, ws[s]->d_out, bytes, cudaMemcpyDeviceToHost, ws[s]->st));
+      g_prof.d2h += bytes;
+      CU(cudaEventRecord(ws[s]->done, ws[s]->st));
+      pending[s] = int(i);
+    }
+    for (int s = 0; s < DEPTH; s++) finish(s);
+  } catch (...) {
+    for (int s = 0; s < DEPTH; s++)
+      if (ws[s]) {
+        cudaStreamSynchronize(ws[s]->st);
+        r.release(ws[s]);
+      }
+    throw;
+  }
+  for (int s = 0; s < DEPTH; s++)
+    if (ws[s]) r.release(ws[s]);
+}
+
+// splits [0,nq) across replicas by query bytes; one host thread per replica
+template <class F>
+void for_each_replica_range(const awry_index* ix, const uint64_t* qoff, uint64_t nq, F&& fn) {
+  size_t nr = ix->reps.size();
+  if (nr == 1 || nq < 2 * nr) {
+    fn(0, 0, nq);
+    return;
+  }
+  std::vector<uint64_t> cut(nr + 1, 0);
+  cut[nr] = nq;
+  uint64_t total = qoff[nq] - qoff[0];
+  for (size_t i = 1; i < nr; i++) {
+    uint64_t target = qoff[0] + total * i / nr;
+    cut[i] = uint64_t(std::lower_bound(qoff, qoff + nq, target) - qoff);
+    cut[i] = std::max(cut[i], cut[i - 1]);
+  }
+  std::vector<std::thread> th;
+  std::vector<int> codes(nr, 0);
+  std::vector<std::string> msgs(nr);
+  for (size_t i = 0; i < nr; i++)
+    th.emplace_back([&, i] {
+      try {
+        fn(i, cut[i], cut[i + 1]);
+      } catch (const ApiError& e) {
+        codes[i] = e.code;
+        msgs[i] = e.what();
+      } catch (const std::exception& e) {
+        codes[i] = AWRY_ERR_INVALID_ARG;
+        msgs[i] = e.what();
+      }
+    });
+  for (auto& t : th) t.join();
+  for (size_t i = 0; i < nr; i++)
+    if (codes[i]) fail(codes[i], "%s", msgs[i].c_str());
+}
+
+struct LocatePart {
+  std::vector<uint64_t> hit_off;  // local CSR over the replica's queries, size n+1
+  awry_hit* hits = nullptr;       // malloc'd
+  uint64_t n_hits = 0;
+};
+
+// device-side two-pass locate of a chunk whose queries are already packed on the device.
+// Leaves hit offsets in ws->d_hit_off (nq+1) and returns a fresh device buffer with the hits.
+uint64_t* locate_chunk_device(const awry_index* ix, Replica& r, Workspace* ws, uint64_t nq,
+                              uint32_t flags, uint64_t* d_hit_off, uint64_t* n_hits_out,
+                              cudaStream_t st) {
+  (void)ix;
+  const uint2* d_sp_cnt = reinterpret_cast<const uint2*>(ws->d_out);
+  size_t temp = 0;
+  CU(scan_hit_offsets(d_sp_cnt, nq, d_hit_off, nullptr, temp, st));
+  Workspace::grow_dev(reinterpret_cast<uint8_t*&>(ws->d_temp), ws->d_temp_cap, temp + 16);
+  CU(scan_hit_offsets(d_sp_cnt, nq, d_hit_off, ws->d_temp, temp, st));
+  uint64_t n_hits = 0;
+  CU(cudaMemcpyAsync(&n_hits, d_hit_off + nq, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  *n_hits_out = n_hits;
+  if (n_hits == 0) return nullptr;
+  uint64_t* d_hits = nullptr;
+  CU(cudaMalloc(reinterpret_cast<void**>(&d_hits), n_hits * 16));
+  try {
+    if (flags & AWRY_LOCATE_SORTED) {
+      uint64_t *d_locs = nullptr, *d_sorted = nullptr;
+      CU(cudaMalloc(reinterpret_cast<void**>(&d_locs), n_hits * 8));
+      CU(cudaMalloc(reinterpret_cast<void**>(&d_sorted), n_hits * 8));
+      {
+        ProfScope p(1, r.device, st);
+        CU(launch_walk(r.view, d_sp_cnt, d_hit_off, nq, n_hits, nullptr, d_locs, r.sm_count, st));
+      }
+      size_t t2 = 0;
+      CU(sort_hit_segments(d_locs, d_sorted, n_hits, nq, d_hit_off, nullptr, t2, st));
+      Workspace::grow_dev(reinterpret_cast<uint8_t*&>(ws->d_temp), ws->d_temp_cap, t2 + 16);
+      CU(sort_hit_segments(d_locs, d_sorted, n_hits, nq, d_hit_off, ws->d_temp, t2, st));
+      CU(launch_map_locations(r.view, d_sorted, n_hits, d_hits, st));
+      CU(cudaStreamSynchronize(st));
+      cudaFree(d_locs);
+      cudaFree(d_sorted);
+    } else {
+      ProfScope p(1, r.device, st);
+      CU(launch_walk(r.view, d_sp_cnt, d_hit_off, nq, n_hits, d_hits, nullptr, r.sm_count, st));
+    }
+  } catch (...) {
+    cudaFree(d_hits);
+    throw;
+  }
+  return d_hits;
+}
+
+void locate_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, const uint64_t* qoff,
+                       uint64_t q_lo, uint64_t q_hi, uint32_t flags, LocatePart& part) {
+  part.hit_off.assign(q_hi - q_lo + 1, 0);
+  if (q_lo >= q_hi) return;
+  DeviceGuard dg(r.device);
+  const bool src_pinned = is_pinned(qbytes) && is_pinned(qoff);
+  auto chunks = make_chunks(qoff, q_lo, q_hi, CHUNK_MAX_Q, CHUNK_MAX_BYTES);
+  Workspace* ws = r.acquire();
+  size_t cap = 0;
+  try {
+    for (const Chunk& c : chunks) {
+      uint64_t nq = c.q1 - c.q0;
+      enqueue_search(ix, r, ws, qbytes, qoff, c, OUT_SP_CNT_U32, src_pinned);
+      Workspace::grow_dev(ws->d_hit_off, ws->d_hit_off_cap, size_t(nq) + 1);
+      uint64_t n_hits = 0;
+      uint64_t* d_hits = locate_chunk_device(ix, r, ws, nq, flags, ws->d_hit_off, &n_hits, ws->st);
+      check_flag(ws, c);
+      // offsets of this chunk, rebased onto the replica-local hit count so far
+      uint64_t* dst_off = part.hit_off.data() + (c.q0 - q_lo);
+      CU(cudaMemcpyAsync(dst_off, ws->d_hit_off, (nq + 1) * 8, cudaMemcpyDeviceToHost, ws->st));
+      if (n_hits) {
+        if (part.n_hits + n_hits > cap) {
+          cap = std::max<size_t>(size_t(part.n_hits + n_hits), cap * 2);
+          void* np = realloc(part.hits, cap * sizeof(awry_hit));
+          if (!np) {
+            cudaFree(d_hits);
+            fail(AWRY_ERR_NOMEM, "out of host memory for %llu hits", (unsigned long long)cap);
+          }
+          part.hits = static_cast<awry_hit*>(np);
+        }
+        CU(cudaMemcpyAsync(part.hits + part.n_hits, d_hits, n_hits * 16, cudaMemcpyDeviceToHost, ws->st));
+      }
+      CU(cudaStreamSynchronize(ws->st));
+      g_prof.d2h += (nq + 1) * 8 + n_hits * 16;
+      if (d_hits) cudaFree(d_hits);
+      for (uint64_t i = 0; i <= nq; i++) dst_off[i] += part.n_hits;
+      part.n_hits += n_hits;
+    }
+  } catch (...) {
+    cudaStreamSynchronize(ws->st);
+    r.release(ws);
+    free(part.hits);
+    part.hits = nullptr;
+    throw;
+  }
+  r.release(ws);
+}
+
+uint32_t ascii_to_dsym(const awry_index* ix, uint8_t ch, bool* sentinel) {
+  if (ch >= 'a' && ch <= 'z') ch = uint8_t(ch - 'a' + 'A');
+  *sentinel = (ch == '$' || ch == '#');
+  if (ix->alphabet == AWRY_NUCLEOTIDE) {
+    switch (ch) {
+      case 'A': return 0;
+      case 'C': return 1;
+      case 'G': return 2;
+      case 'T':
+      case 'U': return 3;
+      case '$':
+      case '#': return DNA_SENTINEL;
+      default: return DNA_N;
+    }
+  }
+  static const char L[23] = "$ACDEFGHIKLMNPQRSTVWXY";
+  if (*sentinel) return 0;
+  for (int i = 1; i < 22; i++)
+    if (i != 20 && L[i] == char(ch)) return uint32_t(i);
+  return 20;
+}
+
+const awry_index* need(const awry_index* ix) {
+  if (!ix || ix->reps.empty()) fail(AWRY_ERR_INVALID_ARG, "null or empty index handle");
+  return ix;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ extern "C"
+
+extern "C" {
+
+const char* awry_last_error(void) { return g_err; }
+const char* awry_version(void) { return "awry_b200 0.1.0 (sm_100a)"; }
+
+int awry_index_load(const char* path, const int* devices, int n_dev, awry_index** out) {
+  return guarded([&] {
+    if (!path || !out) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) fail(AWRY_ERR_IO, "cannot open %s: %s", path, strerror(errno));
+    std::unique_ptr<FILE, int (*)(FILE*)> closer(f, fclose);
+    // large stdio buffer: the file is read once, sequentially
+    setvbuf(f, nullptr, _IOFBF, 8u << 20);
+    char label[11];
+    if (fread(label, 1, 11, f) != 11 || memcmp(label, "AWRY-Index\n", 11) != 0)
+      fail(AWRY_ERR_FORMAT, "file did not start with the expected label; probably not an fm index file");
+    uint64_t hdr[4];
+    if (fread(hdr, 8, 4, f) != 4) fail(AWRY_ERR_FORMAT, "truncated header");
+    auto ix = std::make_unique<awry_index>();
+    ix->version = hdr[0];  // read, not validated (fm_index_file.rs:185-186)
+    ix->sa_ratio = hdr[1];
+    ix->bwt_len = hdr[2];
+    if (hdr[3] > 1) fail(AWRY_ERR_FORMAT, "invalid symbol alphabet id %llu", (unsigned long long)hdr[3]);
+    ix->alphabet = int(hdr[3]);
+    check_header(ix.get());
+    auto devs = pick_devices(devices, n_dev);
+    Source src;
+    src.f = f;
+    try {
+      make_replicas(ix.get(), devs, src, true);
+    } catch (...) {
+      awry_index_free(ix.release());
+      throw;
+    }
+    *out = ix.release();
+  });
+}
+
+int awry_index_from_parts(const awry_parts* p, const int* devices, int n_dev, awry_index** out) {
+  return guarded([&] {
+    if (!p || !out || !p->blocks || !p->prefix_sums || !p->sa_words) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    auto ix = std::make_unique<awry_index>();
+    ix->version = p->version ? p->version : 1;
+    ix->sa_ratio = p->sa_ratio;
+    ix->bwt_len = p->bwt_len;
+    if (p->alphabet > 1) fail(AWRY_ERR_INVALID_ARG, "invalid alphabet id %u", p->alphabet);
+    ix->alphabet = int(p->alphabet);
+    ix->kmer_len_file = p->kmer_len;
+    check_header(ix.get());
+    auto devs = pick_devices(devices, n_dev);
+    for (uint64_t i = 0; i < p->n_sequences; i++) {
+      ix->seq_starts.push_back(p->seq_starts ? p->seq_starts[i] : 0);
+      ix->headers.emplace_back(p->headers && p->headers[i] ? p->headers[i] : "");
+    }
+    const uint64_t n_ref_blocks = (ix->bwt_len + 255) / 256;
+    Source src;  // same read order as the file: blocks, prefix sums, SA words
+    src.segs.emplace_back(reinterpret_cast<const uint8_t*>(p->blocks),
+                          size_t(n_ref_blocks) * (ix->alphabet == AWRY_NUCLEOTIDE ? 160 : 352));
+    src.segs.emplace_back(reinterpret_cast<const uint8_t*>(p->prefix_sums), size_t(ix->card + 1) * 8);
+    src.segs.emplace_back(reinterpret_cast<const uint8_t*>(p->sa_words), size_t(ix->n_sa_words) * 8);
+    try {
+      make_replicas(ix.get(), devs, src, false);
+    } catch (...) {
+      awry_index_free(ix.release());
+      throw;
+    }
+    *out = ix.release();
+  });
+}
+
+void awry_index_free(awry_index* ix) {
+  if (!ix) return;
+  for (auto& rp : ix->reps) {
+    Replica& r = *rp;
+    cudaSetDevice(r.device);
+    for (Workspace* w : r.all_ws) {
+      w->destroy();
+      delete w;
+    }
+    cudaFree(r.d_blocks);
+    cudaFree(r.d_sa);
+    cudaFree(r.d_table);
+    cudaFree(r.d_seq_starts);
+    cudaFree(r.d_async_flag);
+  }
+  delete ix;
+}
+
+int awry_index_info(const awry_index* ix, awry_info* info) {
+  return guarded([&] {
+    need(ix);
+    if (!info) fail(AWRY_ERR_INVALID_ARG, "null info");
+    memset(info, 0, sizeof *info);
+    info->version = ix->version;
+    info->sa_ratio = ix->sa_ratio;
+    info->bwt_len = ix->bwt_len;
+    info->alphabet = uint32_t(ix->alphabet);
+    info->kmer_len = ix->kmer_len_file;
+    info->n_prefix_sums = uint32_t(ix->card + 1);
+    info->n_devices = uint32_t(ix->reps.size());
+    memcpy(info->prefix_sums, ix->prefix_sums, sizeof info->prefix_sums);
+    info->n_sequences = ix->seq_starts.size();
+    info->device_bytes_blocks = ix->reps[0]->bytes_blocks;
+    info->device_bytes_sa = ix->reps[0]->bytes_sa;
+    info->device_bytes_table = ix->reps[0]->bytes_table;
+    for (size_t i = 0; i < ix->reps.size() && i < 16; i++) info->devices[i] = ix->reps[i]->device;
+  });
+}
+
+int awry_index_sequence_header(const awry_index* ix, uint64_t seq_idx, const char** header, uint64_t* header_len) {
+  return guarded([&] {
+    need(ix);
+    if (seq_idx >= ix->headers.size()) fail(AWRY_ERR_INVALID_ARG, "sequence index %llu out of range", (unsigned long long)seq_idx);
+    if (header) *header = ix->headers[seq_idx].c_str();
+    if (header_len) *header_len = ix->headers[seq_idx].size();
+  });
+}
+
+int awry_count_batch(const awry_index* ix, const uint8_t* qbytes, const uint64_t* qoff, uint64_t nq, uint64_t* counts) {
+  return guarded([&] {
+    need(ix);
+    if (nq == 0) return;
+    if (!qbytes || !qoff || !counts) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    validate_offsets(qoff, nq);
+    for_each_replica_range(ix, qoff, nq, [&](size_t ri, uint64_t lo, uint64_t hi) {
+      search_on_replica(ix, *ix->reps[ri], qbytes, qoff, lo, hi, OUT_COUNT_U64, counts);
+    });
+  });
+}
+
+int awry_search_batch(const awry_index* ix, const uint8_t* qbytes, const uint64_t* qoff, uint64_t nq, awry_range* ranges) {
+  return guarded([&] {
+    need(ix);
+    if (nq == 0) return;
+    if (!qbytes || !qoff || !ranges) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    validate_offsets(qoff, nq);
+    for_each_replica_range(ix, qoff, nq, [&](size_t ri, uint64_t lo, uint64_t hi) {
+      search_on_replica(ix, *ix->reps[ri], qbytes, qoff, lo, hi, OUT_RANGE_U64, ranges);
+    });
+  });
+}
+
+int awry_locate_batch(const awry_index* ix, const uint8_t* qbytes, const uint64_t* qoff, uint64_t nq, uint32_t flags,
+                      uint64_t* hit_off, awry_hit** hits, uint64_t* n_hits) {
+  return guarded([&] {
+    need(ix);
+    if (!hit_off || !hits || !n_hits) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    *hits = nullptr;
+    *n_hits = 0;
+    hit_off[0] = 0;
+    if (nq == 0) return;
+    if (!qbytes || !qoff) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    validate_offsets(qoff, nq);
+    size_t nr = ix->reps.size();
+    std::vector<LocatePart> parts(nr);
+    std::vector<std::pair<uint64_t, uint64_t>> ranges(nr, {0, 0});
+    try {
+      for_each_replica_range(ix, qoff, nq, [&](size_t ri, uint64_t lo, uint64_t hi) {
+        ranges[ri] = {lo, hi};
+        locate_on_replica(ix, *ix->reps[ri], qbytes, qoff, lo, hi, flags, parts[ri]);
+      });
+    } catch (...) {
+      for (auto& p : parts) free(p.hits);
+      throw;
+    }
+    // concatenate in range order (results of the reference's order-preserving collect)
+    uint64_t total = 0;
+    for (auto& p : parts) total += p.n_hits;
+    awry_hit* all = nullptr;
+    if (nr == 1) {
+      all = parts[0].hits;
+      parts[0].hits = nullptr;
+    } else if (total) {
+      all = static_cast<awry_hit*>(malloc(total * sizeof(awry_hit)));
+      if (!all) {
+        for (auto& p : parts) free(p.hits);
+        fail(AWRY_ERR_NOMEM, "out of host memory for %llu hits", (unsigned long long)total);
+      }
+    }
+    uint64_t base = 0;
+    for (size_t ri = 0; ri < nr; ri++) {
+      auto [lo, hi] = ranges[ri];
+      if (hi > lo)
+        for (uint64_t i = 0; i <= hi - lo; i++) hit_off[lo + i] = base + parts[ri].hit_off[i];
+      if (nr > 1 && parts[ri].n_hits) memcpy(all + base, parts[ri].hits, parts[ri].n_hits * sizeof(awry_hit));
+      base += parts[ri].n_hits;
+      if (nr > 1) free(parts[ri].hits);
+    }
+    hit_off[nq] = total;
+    *hits = all;
+    *n_hits = total;
+  });
+}
+
+void awry_hits_free(awry_hit* hits) { free(hits); }
+
+int awry_initial_range(const awry_index* ix, uint8_t ascii_symbol, awry_range* out) {
+  return guarded([&] {
+    need(ix);
+    if (!out) fail(AWRY_ERR_INVALID_ARG, "null out");
+    bool sent = false;
+    uint32_t d = ascii_to_dsym(ix, ascii_symbol, &sent);
+    // SearchRange::new accepts the sentinel too: [C[0], C[1]-1] (search.rs:43-48)
+    const IndexView& v = ix->reps[0]->view;
+    if (sent) {
+      out->start_ptr = ix->prefix_sums[0];
+      out->end_ptr = ix->prefix_sums[1] - 1;
+    } else {
+      out->start_ptr = v.c_lo[d];
+      out->end_ptr = v.c_hi[d];
+    }
+  });
+}
+
+int awry_update_range(const awry_index* ix, awry_range range, uint8_t ascii_symbol, awry_range* out) {
+  return guarded([&] {
+    need(ix);
+    if (!out) fail(AWRY_ERR_INVALID_ARG, "null out");
+    bool sent = false;
+    uint32_t d = ascii_to_dsym(ix, ascii_symbol, &sent);
+    if (sent) fail(AWRY_ERR_INVALID_QUERY, "cannot extend a range with the sentinel (reference panics, bwt.rs:127)");
+    if (range.start_ptr == 0 || range.start_ptr > ix->bwt_len || range.end_ptr >= ix->bwt_len)
+      fail(AWRY_ERR_INVALID_ARG, "range [%llu,%llu] outside the BWT (reference: unchecked out-of-bounds read)",
+           (unsigned long long)range.start_ptr, (unsigned long long)range.end_ptr);
+    Replica& r = *ix->reps[0];
+    DeviceGuard dg(r.device);
+    Workspace* ws = r.acquire();
+    try {
+      Workspace::grow_dev(ws->d_out, ws->d_out_cap, 16);
+      CU(launch_single_update(r.view, uint32_t(range.start_ptr), uint32_t(range.end_ptr), d,
+                              reinterpret_cast<uint32_t*>(ws->d_out), ws->st));
+      uint32_t res[2];
+      CU(cudaMemcpyAsync(res, ws->d_out, 8, cudaMemcpyDeviceToHost, ws->st));
+      CU(cudaStreamSynchronize(ws->st));
+      out->start_ptr = res[0];
+      out->end_ptr = res[1];
+    } catch (...) {
+      r.release(ws);
+      throw;
+    }
+    r.release(ws);
+  });
+}
+
+int awry_backstep(const awry_index* ix, uint64_t row, uint64_t* out) {
+  return guarded([&] {
+    need(ix);
+    if (!out) fail(AWRY_ERR_INVALID_ARG, "null out");
+    if (row >= ix->bwt_len) fail(AWRY_ERR_INVALID_ARG, "row %llu outside the BWT", (unsigned long long)row);
+    Replica& r = *ix->reps[0];
+    DeviceGuard dg(r.device);
+    Workspace* ws = r.acquire();
+    try {
+      Workspace::grow_dev(ws->d_out, ws->d_out_cap, 16);
+      CU(launch_single_backstep(r.view, uint32_t(row), reinterpret_cast<uint32_t*>(ws->d_out), ws->st));
+      uint32_t res = 0;
+      CU(cudaMemcpyAsync(&res, ws->d_out, 4, cudaMemcpyDeviceToHost, ws->st));
+      CU(cudaStreamSynchronize(ws->st));
+      *out = res;
+    } catch (...) {
+      r.release(ws);
+      throw;
+    }
+    r.release(ws);
+  });
+}
+
+// ---- device-resident entry points ----
+
+int awry_count_device(const awry_index* ix, int replica, const uint8_t* d_qbytes, const uint64_t* d_qoff, uint64_t nq,
+                      uint64_t* d_counts, void* cuda_stream) {
+  return guarded([&] {
+    need(ix);
+    if (replica < 0 || size_t(replica) >= ix->reps.size()) fail(AWRY_ERR_INVALID_ARG, "replica out of range");
+    if (nq == 0) return;
+    if (!d_qbytes || !d_qoff || !d_counts) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    Replica& r = *ix->reps[size_t(replica)];
+    DeviceGuard dg(r.device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    // total query bytes bound the packed size; read the last offset (one 8-byte D2H)
+    uint64_t ends[2] = {0, 0};
+    CU(cudaMemcpyAsync(&ends[0], d_qoff, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&ends[1], d_qoff + nq, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (ends[1] < ends[0]) fail(AWRY_ERR_INVALID_ARG, "query offsets are not monotone");
+    const int sh = ix->alphabet == 0 ? 4 : 3;
+    uint64_t words = nq + ((ends[1] >> sh) - (ends[0] >> sh)) + 4;
+    uint64_t* d_qwords = nullptr;
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&d_qwords), words * 8, st));
+    {
+      ProfScope p(2, r.device, st);
+      CU(launch_pack(ix->alphabet, d_qbytes, d_qoff, nq, d_qwords - (ends[0] >> sh), r.d_async_flag, st));
+    }
+    {
+      ProfScope p(0, r.device, st);
+      CU(launch_search(r.view, d_qwords - (ends[0] >> sh), d_qoff, nq, OUT_COUNT_U64, d_counts, g_variant, r.sm_count, st));
+    }
+    CU(cudaFreeAsync(d_qwords, st));
+  });
+}
+
+int awry_locate_device(const awry_index* ix, int replica, const uint8_t* d_qbytes, const uint64_t* d_qoff, uint64_t nq,
+                       uint32_t flags, uint64_t* d_hit_off, awry_hit** d_hits, uint64_t* n_hits, void* cuda_stream) {
+  return guarded([&] {
+    need(ix);
+    if (replica < 0 || size_t(replica) >= ix->reps.size()) fail(AWRY_ERR_INVALID_ARG, "replica out of range");
+    if (!d_hit_off || !d_hits || !n_hits) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    *d_hits = nullptr;
+    *n_hits = 0;
+    if (nq == 0) return;
+    if (!d_qbytes || !d_qoff) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    Replica& r = *ix->reps[size_t(replica)];
+    DeviceGuard dg(r.device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    uint64_t ends[2] = {0, 0};
+    CU(cudaMemcpyAsync(&ends[0], d_qoff, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&ends[1], d_qoff + nq, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (ends[1] < ends[0]) fail(AWRY_ERR_INVALID_ARG, "query offsets are not monotone");
+    const int sh = ix->alphabet == 0 ? 4 : 3;
+    Workspace* ws = r.acquire();
+    try {
+      uint64_t words = nq + ((ends[1] >> sh) - (ends[0] >> sh)) + 4;
+      Workspace::grow_dev(ws->d_qwords, ws->d_qwords_cap, size_t(words));
+      Workspace::grow_dev(ws->d_out, ws->d_out_cap, size_t(nq) * 8);
+      {
+        ProfScope p(2, r.device, st);
+        CU(launch_pack(ix->alphabet, d_qbytes, d_qoff, nq, ws->d_qwords - (ends[0] >> sh), r.d_async_flag, st));
+      }
+      {
+        ProfScope p(0, r.device, st);
+        CU(launch_search(r.view, ws->d_qwords - (ends[0] >> sh), d_qoff, nq, OUT_SP_CNT_U32, ws->d_out, g_variant, r.sm_count, st));
+      }
+      uint64_t n = 0;
+      uint64_t* h = locate_chunk_device(ix, r, ws, nq, flags, d_hit_off, &n, st);
+      CU(cudaStreamSynchronize(st));
+      *d_hits = reinterpret_cast<awry_hit*>(h);
+      *n_hits = n;
+    } catch (...) {
+      cudaStreamSynchronize(st);
+      r.release(ws);
+      throw;
+    }
+    r.release(ws);
+  });
+}
+
+int awry_device_free(const awry_index* ix, int replica, void* d_ptr) {
+  return guarded([&] {
+    need(ix);
+    if (replica < 0 || size_t(replica) >= ix->reps.size()) fail(AWRY_ERR_INVALID_ARG, "replica out of range");
+    if (!d_ptr) return;
+    DeviceGuard dg(ix->reps[size_t(replica)]->device);
+    CU(cudaFree(d_ptr));
+  });
+}
+
+int awry_device_check(const awry_index* ix, int replica, void* cuda_stream) {
+  return guarded([&] {
+    need(ix);
+    if (replica < 0 || size_t(replica) >= ix->reps.size()) fail(AWRY_ERR_INVALID_ARG, "replica out of range");
+    Replica& r = *ix->reps[size_t(replica)];
+    DeviceGuard dg(r.device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    unsigned long long flag = ~0ull;
+    CU(cudaMemcpyAsync(&flag, r.d_async_flag, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemsetAsync(r.d_async_flag, 0xff, 8, st));
+    CU(cudaStreamSynchronize(st));
+    if (flag != ~0ull)
+      fail(AWRY_ERR_INVALID_QUERY, "query %llu of a device batch is empty or contains a sentinel", flag);
+  });
+}
+
+// ---- instrumentation ----
+
+int awry_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  g_prof.enabled = on != 0;
+  return AWRY_OK;
+}
+int awry_profile_reset(void) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  prof_collect_locked();
+  for (int i = 0; i < 3; i++) g_prof.n[i] = 0, g_prof.ms[i] = 0;
+  g_prof.h2d = 0;
+  g_prof.d2h = 0;
+  kernel_launch_count_reset();
+  return AWRY_OK;
+}
+int awry_profile_get(awry_profile* out) {
+  if (!out) return AWRY_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  prof_collect_locked();
+  out->launches = kernel_launch_count();
+  out->search_launches = g_prof.n[0];
+  out->search_ms = g_prof.ms[0];
+  out->walk_launches = g_prof.n[1];
+  out->walk_ms = g_prof.ms[1];
+  out->pack_launches = g_prof.n[2];
+  out->pack_ms = g_prof.ms[2];
+  out->h2d_bytes = g_prof.h2d;
+  out->d2h_bytes = g_prof.d2h;
+  return AWRY_OK;
+}
+
+int awry_bench_random_gather(int device, uint64_t footprint_bytes, uint32_t granule, uint32_t lanes, uint64_t n_reads,
+                             int iters, double* reads_per_s, double* gb_per_s) {
+  return guarded([&] {
+    if (!reads_per_s || !gb_per_s || footprint_bytes < granule || n_reads == 0) fail(AWRY_ERR_INVALID_ARG, "bad argument");
+    pick_devices(&device, 1);
+    DeviceGuard dg(device);
+    cudaError_t e = run_random_gather(footprint_bytes, granule, lanes, n_reads, iters, reads_per_s, gb_per_s);
+    if (e == cudaErrorInvalidValue) fail(AWRY_ERR_INVALID_ARG, "unsupported granule/lanes combination %u/%u", granule, lanes);
+    CU(e);
+  });
+}
+
+int awry_set_search_variant(int lanes_per_query, int threads_per_block, int blocks_per_sm) {
+  if (lanes_per_query != 0 && lanes_per_query != -1 && lanes_per_query != 1 && lanes_per_query != 2 && lanes_per_query != 4)
+    return AWRY_ERR_INVALID_ARG;
+  g_variant.lanes = lanes_per_query;
+  g_variant.tpb = threads_per_block;
+  g_variant.blocks_per_sm = blocks_per_sm;
+  return AWRY_OK;
+}
+
+}  // extern "C"

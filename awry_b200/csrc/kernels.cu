@@ -1,0 +1,810 @@
+// kernels.cu -- hand-written sm_100a kernels of the batched FM-index search path.
+//
+// Reference functions replaced (paths under /root/reference/src):
+//   pack_kernel           Symbol::new_ascii / index()            alphabet.rs:109-114, :169-248
+//   build_table_kernel    KmerLookupTable (a CORRECT seed table)  kmer_lookup_table.rs:17-20, :121-167
+//   search kernels        get_search_range_for_string + update_range_with_symbol + count_string
+//                                                                 fm_index.rs:402-438, :499-501, :559-582
+//   walk_kernel           locate_string + backstep + reconstruct_value + get_seq_location
+//                                                                 fm_index.rs:516-544, :585-593,
+//                                                                 compressed_suffix_array.rs:76-111,
+//                                                                 sequence_index.rs:108-141
+//   transpose kernels     load-time re-layout of bwt.rs:12-25 blocks (fm_index_file.rs:215-262)
+#include <atomic>
+#include <cstdio>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_segmented_sort.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include "kernels.hpp"
+
+namespace awry {
+
+static std::atomic<uint64_t> g_launches{0};
+uint64_t kernel_launch_count() { return g_launches.load(); }
+void kernel_launch_count_reset() { g_launches.store(0); }
+#define COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
+
+// ------------------------------------------------------------------ symbol tables
+
+__constant__ uint8_t c_ascii_to_dsym[2][256];  // ASCII -> device symbol (alphabet.rs:169-248)
+__constant__ uint8_t c_amino_code_to_idx[32];  // reference 5-bit code -> index (alphabet.rs:197-222)
+
+static uint8_t host_ascii_to_ref_index(int alphabet, uint8_t ch) {
+  if (ch >= 'a' && ch <= 'z') ch = uint8_t(ch - 'a' + 'A');
+  if (ch == '$' || ch == '#') return 0;
+  if (alphabet == 0) {
+    switch (ch) {
+      case 'A': return 1;
+      case 'C': return 2;
+      case 'G': return 3;
+      case 'T':
+      case 'U': return 5;
+      default: return 4;
+    }
+  }
+  static const char L[23] = "$ACDEFGHIKLMNPQRSTVWXY";
+  for (int i = 1; i < 22; i++)
+    if (i != 20 && L[i] == char(ch)) return uint8_t(i);
+  return 20;
+}
+
+cudaError_t init_device_tables() {
+  uint8_t lut[2][256];
+  static const uint8_t dna_ref_to_dsym[6] = {DNA_SENTINEL, 0, 1, 2, DNA_N, 3};
+  for (int c = 0; c < 256; c++) {
+    lut[0][c] = dna_ref_to_dsym[host_ascii_to_ref_index(0, uint8_t(c))];
+    lut[1][c] = host_ascii_to_ref_index(1, uint8_t(c));
+  }
+  cudaError_t e = cudaMemcpyToSymbol(c_ascii_to_dsym, lut, sizeof lut);
+  if (e != cudaSuccess) return e;
+  static const uint8_t codes[22] = {0x00, 0x0c, 0x17, 0x03, 0x06, 0x1e, 0x1a, 0x1b, 0x19, 0x15, 0x1c,
+                                    0x1d, 0x08, 0x09, 0x04, 0x13, 0x0a, 0x05, 0x16, 0x01, 0x1f, 0x02};
+  uint8_t c2i[32];
+  for (int c = 0; c < 32; c++) c2i[c] = 20;  // unknown codes decode to X
+  for (int i = 0; i < 22; i++) c2i[codes[i]] = uint8_t(i);
+  return cudaMemcpyToSymbol(c_amino_code_to_idx, c2i, sizeof c2i);
+}
+
+// ------------------------------------------------------------------ load-time re-layout
+
+// one thread per 16-B output chunk; 8 chunks per 256-row reference block (bwt.rs:12-17)
+__global__ void transpose_dna_kernel(const uint64_t* __restrict__ ref, uint64_t first_rb,
+                                     uint64_t n_rb, uint64_t bwt_len, uint4* __restrict__ out,
+                                     unsigned int* dollar_row) {
+  uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (t >= n_rb * 8) return;
+  uint64_t lrb = t >> 3;
+  uint32_t h = uint32_t(t >> 2) & 1, j = uint32_t(t) & 3;
+  const uint64_t* rb = ref + lrb * 20;
+  uint32_t w = 2 * h + (j >> 1), sh = 32 * (j & 1);
+  uint32_t r0 = uint32_t(rb[w] >> sh), r1 = uint32_t(rb[4 + w] >> sh), r2 = uint32_t(rb[8 + w] >> sh);
+  uint64_t row0 = (first_rb + lrb) * 256 + 128 * h + 32 * j;
+  uint32_t valid = row0 >= bwt_len ? 0u : (bwt_len - row0 >= 32 ? ~0u : ((1u << (bwt_len - row0)) - 1u));
+  // reference codes (alphabet.rs:237-244): $100 A110 C101 G011 T001, everything else decodes to N
+  uint32_t isS = ~r0 & ~r1 & r2, isA = ~r0 & r1 & r2, isC = r0 & ~r1 & r2, isG = r0 & r1 & ~r2,
+           isT = r0 & ~r1 & ~r2;
+  uint32_t isN = ~(isS | isA | isC | isG | isT);
+  uint32_t d0 = ((isC | isT | isS) & valid) | ~valid;  // device codes A0 C1 G2 T3 N4 $5, pad 7
+  uint32_t d1 = ((isG | isT) & valid) | ~valid;
+  uint32_t d2 = ((isN | isS) & valid) | ~valid;
+  if (isS & valid) *dollar_row = uint32_t(row0 + (__ffs(isS & valid) - 1));
+  // milestone of symbol j (A,C,G,T = reference index 1,2,3,5) at the start of this 128-row block
+  const int ref_idx = j == 3 ? 5 : int(j) + 1;
+  uint64_t cnt = rb[12 + ref_idx];
+  if (h == 1) {
+#pragma unroll
+    for (int ww = 0; ww < 2; ww++) {
+      uint64_t a = rb[ww], b = rb[4 + ww], c = rb[8 + ww];
+      uint64_t m = j == 0 ? (~a & b & c) : j == 1 ? (a & ~b & c) : j == 2 ? (a & b & ~c) : (a & ~b & ~c);
+      cnt += uint64_t(__popcll(m));
+    }
+  }
+  out[(first_rb + lrb) * 8 + h * 4 + j] = make_uint4(d0, d1, d2, uint32_t(cnt));
+}
+
+// one thread per 32-B output chunk; 8 chunks per 256-row reference block (bwt.rs:19-25)
+__global__ void transpose_amino_kernel(const uint64_t* __restrict__ ref, uint64_t first_rb,
+                                       uint64_t n_rb, uint64_t bwt_len, uint4* __restrict__ out,
+                                       unsigned int* dollar_row) {
+  uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (t >= n_rb * 8) return;
+  uint64_t lrb = t >> 3;
+  uint32_t j = uint32_t(t) & 7;
+  const uint64_t* rb = ref + lrb * 44;
+  uint32_t w = j >> 1, sh = 32 * (j & 1);
+  uint32_t r[5], d[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+  for (int p = 0; p < 5; p++) r[p] = uint32_t(rb[4 * p + w] >> sh);
+  uint64_t row0 = (first_rb + lrb) * 256 + 32 * j;
+  uint32_t valid = row0 >= bwt_len ? 0u : (bwt_len - row0 >= 32 ? ~0u : ((1u << (bwt_len - row0)) - 1u));
+  for (int bit = 0; bit < 32; bit++) {
+    uint32_t code = 0;
+#pragma unroll
+    for (int p = 0; p < 5; p++) code |= ((r[p] >> bit) & 1u) << p;
+    uint32_t idx = ((valid >> bit) & 1u) ? c_amino_code_to_idx[code] : 0u;
+    if (((valid >> bit) & 1u) && code == 0) *dollar_row = uint32_t(row0 + bit);
+#pragma unroll
+    for (int p = 0; p < 5; p++) d[p] |= ((idx >> p) & 1u) << bit;
+  }
+  uint32_t c[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    uint32_t s = 3 * j + i + 1;  // reference symbol index held by count slot 3j+i
+    c[i] = s <= 21 ? uint32_t(rb[20 + s]) : 0u;
+  }
+  uint4* o = out + (first_rb + lrb) * 16 + 2 * j;
+  o[0] = make_uint4(d[0], d[1], d[2], d[3]);
+  o[1] = make_uint4(d[4], c[0], c[1], c[2]);
+}
+
+cudaError_t launch_transpose(int alphabet, const uint64_t* d_ref_blocks, uint64_t first_ref_block,
+                             uint64_t n_ref_blocks, uint64_t bwt_len, uint4* d_blocks,
+                             unsigned int* d_dollar_row, cudaStream_t s) {
+  if (n_ref_blocks == 0) return cudaSuccess;
+  uint64_t threads = n_ref_blocks * 8;
+  unsigned grid = unsigned((threads + 255) / 256);
+  if (alphabet == 0)
+    transpose_dna_kernel<<<grid, 256, 0, s>>>(d_ref_blocks, first_ref_block, n_ref_blocks, bwt_len,
+                                              d_blocks, d_dollar_row);
+  else
+    transpose_amino_kernel<<<grid, 256, 0, s>>>(d_ref_blocks, first_ref_block, n_ref_blocks,
+                                                bwt_len, d_blocks, d_dollar_row);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ k-mer seed table
+
+uint64_t table_entries(int alphabet, uint32_t k) {
+  uint64_t b = alphabet == 0 ? 4 : 20, r = 1;
+  for (uint32_t i = 0; i < k; i++) r *= b;
+  return r;
+}
+
+__device__ __forceinline__ uint32_t amino_digit_to_sym(uint32_t d) { return d < 19 ? d + 1 : 21; }
+
+// entry idx = sum_j digit_j * B^j, digit_0 = LAST query character (search order).
+// One thread per k-mer: k-1 LF steps with early exit; absent k-mers get SearchRange::zero().
+template <int ALPHA>
+__global__ void build_table_kernel(IndexView ix, uint2* __restrict__ table, uint64_t n, uint32_t k) {
+  constexpr uint32_t B = ALPHA == 0 ? 4 : 20;
+  uint64_t idx = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (idx >= n) return;
+  uint64_t rest = idx;
+  uint32_t d = uint32_t(rest % B);
+  rest /= B;
+  uint32_t c = ALPHA == 0 ? d : amino_digit_to_sym(d);
+  uint32_t sp = ix.c_lo[c], ep = ix.c_hi[c];
+  for (uint32_t j = 1; j < k && sp <= ep; j++) {
+    d = uint32_t(rest % B);
+    rest /= B;
+    lf_update<ALPHA>(ix, sp, ep, ALPHA == 0 ? d : amino_digit_to_sym(d));
+  }
+  table[idx] = sp <= ep ? make_uint2(sp, ep) : make_uint2(1u, 0u);
+}
+
+cudaError_t launch_build_table(const IndexView& ix, uint2* d_table, uint32_t k, cudaStream_t s) {
+  uint64_t n = table_entries(int(ix.alphabet), k);
+  unsigned grid = unsigned((n + 255) / 256);
+  if (ix.alphabet == 0)
+    build_table_kernel<0><<<grid, 256, 0, s>>>(ix, d_table, n, k);
+  else
+    build_table_kernel<1><<<grid, 256, 0, s>>>(ix, d_table, n, k);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ query packing prepass
+
+// 8 lanes per query; lane t packs words t, t+8, ...  Flags the first empty / sentinel query.
+template <int ALPHA>
+__global__ void pack_kernel(const uint8_t* __restrict__ qbytes, const uint64_t* __restrict__ qoff,
+                            uint64_t nq, uint64_t* __restrict__ qwords,
+                            unsigned long long* first_bad) {
+  constexpr int BITS = ALPHA == 0 ? 4 : 8;
+  constexpr int SPW = 64 / BITS;
+  constexpr int LOG_SPW = ALPHA == 0 ? 4 : 3;
+  constexpr uint32_t SENT = ALPHA == 0 ? DNA_SENTINEL : AMINO_SENTINEL;
+  uint64_t gid = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 3;
+  uint32_t sub = threadIdx.x & 7;
+  uint64_t ngroups = (gridDim.x * uint64_t(blockDim.x)) >> 3;
+  for (uint64_t q = gid; q < nq; q += ngroups) {
+    uint64_t o0 = qoff[q], o1 = qoff[q + 1];
+    uint64_t len = o1 - o0;
+    if (len == 0 || o1 < o0) {
+      if (sub == 0) atomicMin(first_bad, (unsigned long long)q);
+      continue;
+    }
+    uint64_t nwords = (len + SPW - 1) / SPW;
+    uint64_t* dst = qwords + q + (o0 >> LOG_SPW);
+    const uint8_t* src = qbytes + o0;
+    bool bad = false;
+    for (uint64_t wi = sub; wi < nwords; wi += 8) {
+      uint64_t word = 0;
+      uint64_t first = wi * SPW;  // search-order index of this word's first symbol
+#pragma unroll
+      for (int t = 0; t < SPW; t++) {
+        uint64_t si = first + t;
+        if (si < len) {
+          uint32_t d = c_ascii_to_dsym[ALPHA][src[len - 1 - si]];
+          bad |= d == SENT;
+          word |= uint64_t(d) << (BITS * t);
+        }
+      }
+      dst[wi] = word;
+    }
+    if (bad) atomicMin(first_bad, (unsigned long long)q);
+  }
+}
+
+cudaError_t launch_pack(int alphabet, const uint8_t* d_qbytes, const uint64_t* d_qoff, uint64_t nq,
+                        uint64_t* d_qwords, unsigned long long* d_first_bad, cudaStream_t s) {
+  if (nq == 0) return cudaSuccess;
+  uint64_t threads = nq * 8;
+  unsigned grid = unsigned(std::min<uint64_t>((threads + 255) / 256, 148 * 64));
+  if (alphabet == 0)
+    pack_kernel<0><<<grid, 256, 0, s>>>(d_qbytes, d_qoff, nq, d_qwords, d_first_bad);
+  else
+    pack_kernel<1><<<grid, 256, 0, s>>>(d_qbytes, d_qoff, nq, d_qwords, d_first_bad);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ backward search
+
+template <int MODE>
+__device__ __forceinline__ void store_result(void* out, uint64_t q, uint32_t sp, uint32_t ep) {
+  bool empty = sp > ep;
+  if (MODE == OUT_COUNT_U64) {
+    reinterpret_cast<uint64_t*>(out)[q] = empty ? 0ull : uint64_t(ep - sp) + 1ull;  // search.rs:66-71
+  } else if (MODE == OUT_RANGE_U64) {
+    reinterpret_cast<ulonglong2*>(out)[q] = empty ? make_ulonglong2(1, 0) : make_ulonglong2(sp, ep);
+  } else {
+    reinterpret_cast<uint2*>(out)[q] = empty ? make_uint2(1u, 0u) : make_uint2(sp, ep - sp + 1u);
+  }
+}
+
+// Packed-symbol reader: current word in a register, the next one prefetched.
+template <int ALPHA>
+struct QueryStream {
+  static constexpr int BITS = ALPHA == 0 ? 4 : 8;
+  static constexpr int SPW = 64 / BITS;
+  static constexpr int LOG_SPW = ALPHA == 0 ? 4 : 3;
+  const uint64_t* wp;
+  uint64_t w, wnext;
+  uint32_t inword;
+  __device__ __forceinline__ void open(const uint64_t* qwords, uint64_t q, uint64_t o0) {
+    wp = qwords + q + (o0 >> LOG_SPW);
+    w = __ldg(wp);
+    wnext = __ldg(wp + 1);  // buffer is padded by 2 words
+    inword = 0;
+  }
+  __device__ __forceinline__ uint32_t next() {
+    uint32_t c = uint32_t(w) & ((1u << BITS) - 1u);
+    w >>= BITS;
+    if (++inword == SPW) {
+      w = wnext;
+      wp++;
+      wnext = __ldg(wp + 1);
+      inword = 0;
+    }
+    return c;
+  }
+};
+
+// Start of a query: seed interval from the k-mer table when the last k symbols are all
+// encoding symbols (replaces KmerLookupTable::get_range_for_kmer, kmer_lookup_table.rs:90-110,
+// which recomputes the k-1 steps), else the single-symbol range (search.rs:43-48).
+// Returns the number of symbols still to process.
+template <int ALPHA>
+__device__ __forceinline__ uint32_t begin_query(const IndexView& ix, QueryStream<ALPHA>& qs,
+                                                uint32_t len, uint32_t& sp, uint32_t& ep) {
+  const uint32_t k = ix.kmer_len;
+  if (k != 0 && len >= k) {
+    uint64_t idx = 0;
+    bool ok = true;
+    if (ALPHA == 0) {
+      uint64_t w = qs.w;  // k <= 16 symbols, all inside the first word
+      uint64_t himask = 0xCCCCCCCCCCCCCCCCull >> (4 * (16 - k));
+      ok = (w & himask) == 0;
+      for (uint32_t j = 0; j < k; j++) idx |= ((w >> (4 * j)) & 3ull) << (2 * j);
+    } else {
+      uint64_t w = qs.w, mult = 1;  // k <= 8
+      for (uint32_t j = 0; j < k; j++) {
+        uint32_t s = uint32_t(w >> (8 * j)) & 0xff;
+        ok &= (s != AMINO_X) & (s != AMINO_SENTINEL);
+        idx += uint64_t(s == 21 ? 19 : s - 1) * mult;
+        mult *= 20;
+      }
+    }
+    if (ok) {
+      uint2 r = __ldg(ix.table + idx);
+      sp = r.x;
+      ep = r.y;
+      for (uint32_t j = 0; j < k; j++) qs.next();
+      return len - k;
+    }
+  }
+  uint32_t c = qs.next();
+  if (c == (ALPHA == 0 ? uint32_t(DNA_SENTINEL) : uint32_t(AMINO_SENTINEL))) {
+    sp = 1;
+    ep = 0;
+    return 0;
+  }
+  sp = ix.c_lo[c];
+  ep = ix.c_hi[c];
+  return len - 1;
+}
+
+// ---- scalar kernel: one thread per query (any alphabet) ----
+template <int ALPHA, int MODE>
+__global__ void __launch_bounds__(256) search_scalar_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
+                                                            const uint64_t* __restrict__ qoff, uint64_t nq,
+                                                            void* __restrict__ out) {
+  uint64_t stride = gridDim.x * uint64_t(blockDim.x);
+  for (uint64_t q = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; q < nq; q += stride) {
+    uint64_t o0 = qoff[q];
+    uint32_t len = uint32_t(qoff[q + 1] - o0);
+    uint32_t sp = 1, ep = 0;
+    if (len != 0) {
+      QueryStream<ALPHA> qs;
+      qs.open(qwords, q, o0);
+      uint32_t left = begin_query<ALPHA>(ix, qs, len, sp, ep);
+      while (left != 0 && sp <= ep) {  // early break: fm_index.rs:409-416 / :425-433
+        uint32_t c = qs.next();
+        left--;
+        if (c == (ALPHA == 0 ? uint32_t(DNA_SENTINEL) : uint32_t(AMINO_SENTINEL))) {
+          sp = 1;
+          ep = 0;
+          break;
+        }
+        lf_update<ALPHA>(ix, sp, ep, c);
+      }
+    }
+    store_result<MODE>(out, q, sp, ep);
+  }
+}
+
+// ---- nucleotide kernel: LANES lanes cooperate on one query ----
+// Each lane owns CH = 4/LANES chunks of the 64-B block (LANES=4: one LDG.128, LANES=2: one
+// LDG.256, LANES=1: two LDG.256), computes its part of both inclusive ranks Occ(c,sp-1) and
+// Occ(c,ep) from ONE block load whenever both fall in the same block, and the group reduces
+// with LANES-wide xor shuffles.  Groups are persistent: when a query finishes (all symbols
+// consumed or empty interval) the group moves to query q + G, so early exits refill lanes
+// instead of idling them; all groups of a warp stay converged on the step body.
+template <int LANES>
+struct LaneChunks;
+template <>
+struct LaneChunks<4> {
+  uint4 c[1];
+  __device__ __forceinline__ void load(const uint4* blk, uint32_t sub) { c[0] = ldg128(blk + sub); }
+};
+template <>
+struct LaneChunks<2> {
+  uint4 c[2];
+  __device__ __forceinline__ void load(const uint4* blk, uint32_t sub) {
+    u32x8 v = ldg256(blk + 2 * sub);
+    c[0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+    c[1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+  }
+};
+template <>
+struct LaneChunks<1> {
+  uint4 c[4];
+  __device__ __forceinline__ void load(const uint4* blk, uint32_t) {
+    u32x8 v = ldg256(blk);
+    u32x8 u = ldg256(blk + 2);
+    c[0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+    c[1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+    c[2] = make_uint4(u.v[0], u.v[1], u.v[2], u.v[3]);
+    c[3] = make_uint4(u.v[4], u.v[5], u.v[6], u.v[7]);
+  }
+};
+
+template <int LANES>
+__device__ __forceinline__ uint32_t dna_partial_rank(const LaneChunks<LANES>& x, uint32_t sub,
+                                                     uint32_t local, uint32_t c, uint32_t m0,
+                                                     uint32_t m1) {
+  constexpr int CH = 4 / LANES;
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < CH; i++) {
+    uint32_t j = sub * CH + i;
+    uint32_t pred = ~x.c[i].z & ~(x.c[i].x ^ m0) & ~(x.c[i].y ^ m1);
+    r += __popc(pred & chunk_mask(local, j));
+    r += (j == c) ? x.c[i].w : 0u;
+  }
+  return r;
+}
+
+template <int LANES, int MODE, int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB)
+    search_dna_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
+                      const uint64_t* __restrict__ qoff, uint64_t nq, void* __restrict__ out) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t sub = lane % LANES;
+  const uint32_t gmask = LANES == 1 ? (1u << lane) : (((1u << LANES) - 1u) << (lane - sub));
+  const uint64_t G = (gridDim.x * uint64_t(blockDim.x)) / LANES;
+  uint64_t q = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) / LANES;
+  uint64_t cur = 0;
+  bool have = false;
+  uint32_t sp = 1, ep = 0, left = 0;
+  QueryStream<0> qs;
+  qs.wp = qwords;
+  qs.w = qs.wnext = 0;
+  qs.inword = 0;
+
+  for (;;) {
+    if (left == 0 || sp > ep) {
+      if (have && sub == 0) store_result<MODE>(out, cur, sp, ep);
+      have = false;
+      if (q >= nq) break;
+      cur = q;
+      q += G;
+      have = true;
+      uint64_t o0 = qoff[cur];
+      uint32_t len = uint32_t(qoff[cur + 1] - o0);
+      sp = 1;
+      ep = 0;
+      left = 0;
+      if (len != 0) {
+        qs.open(qwords, cur, o0);
+        left = begin_query<0>(ix, qs, len, sp, ep);
+      }
+      continue;
+    }
+    uint32_t c = qs.next();
+    left--;
+    uint32_t pa = sp - 1, pb = ep;
+    uint32_t ba = pa >> 7, bb = pb >> 7;
+    if (c < 4) {
+      const uint4* blk = ix.blocks + size_t(ba) * DNA_BLOCK_UINT4;
+      LaneChunks<LANES> x;
+      x.load(blk, sub);
+      uint32_t m0 = (c & 1) ? ~0u : 0u, m1 = (c & 2) ? ~0u : 0u;
+      uint32_t ra = dna_partial_rank<LANES>(x, sub, pa & 127, c, m0, m1);
+      if (bb != ba) x.load(ix.blocks + size_t(bb) * DNA_BLOCK_UINT4, sub);
+      uint32_t rb = dna_partial_rank<LANES>(x, sub, pb & 127, c, m0, m1);
+#pragma unroll
+      for (int off = LANES / 2; off > 0; off >>= 1) {
+        ra += __shfl_xor_sync(gmask, ra, off);
+        rb += __shfl_xor_sync(gmask, rb, off);
+      }
+      uint32_t base = ix.c_lo[c];
+      sp = base + ra;
+      ep = base + rb - 1;
+    } else if (c == DNA_N) {
+      lf_update<0>(ix, sp, ep, c);  // rare: every lane of the group runs the scalar step
+    } else {
+      sp = 1;  // sentinel in a query: rejected by the prepass; keep the kernel well defined
+      ep = 0;
+    }
+  }
+}
+
+template <int LANES, int MODE>
+static cudaError_t launch_search_dna(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
+                                     uint64_t nq, void* d_out, const SearchVariant& v, int sm_count,
+                                     cudaStream_t s) {
+  constexpr int TPB = 256;
+  auto kern = search_dna_kernel<LANES, MODE, TPB, 1>;
+  int per_sm = v.blocks_per_sm;
+  if (per_sm <= 0) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+  }
+  uint64_t groups_needed = nq;
+  uint64_t max_blocks = uint64_t(sm_count) * uint64_t(per_sm);
+  uint64_t need_blocks = (groups_needed * LANES + TPB - 1) / TPB;
+  unsigned grid = unsigned(std::max<uint64_t>(1, std::min(max_blocks, need_blocks)));
+  kern<<<grid, TPB, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t launch_search_mode(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
+                                      uint64_t nq, void* d_out, const SearchVariant& v, int sm_count,
+                                      cudaStream_t s) {
+  if (ix.alphabet == 0 && v.lanes != -1) {
+    switch (v.lanes) {
+      case 1: return launch_search_dna<1, MODE>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
+      case 2: return launch_search_dna<2, MODE>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
+      default: return launch_search_dna<4, MODE>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
+    }
+  }
+  // amino (and lanes == -1: the scalar nucleotide kernel, kept for cross-checking)
+  int per_sm = 8;
+  uint64_t need_blocks = (nq + 255) / 256;
+  unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * per_sm, need_blocks)));
+  if (ix.alphabet == 0)
+    search_scalar_kernel<0, MODE><<<grid, 256, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out);
+  else
+    search_scalar_kernel<1, MODE><<<grid, 256, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_search(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
+                          uint64_t nq, SearchOut mode, void* d_out, const SearchVariant& v,
+                          int sm_count, cudaStream_t s) {
+  if (nq == 0) return cudaSuccess;
+  switch (mode) {
+    case OUT_COUNT_U64: return launch_search_mode<OUT_COUNT_U64>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
+    case OUT_RANGE_U64: return launch_search_mode<OUT_RANGE_U64>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
+    default: return launch_search_mode<OUT_SP_CNT_U32>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
+  }
+}
+
+// ------------------------------------------------------------------ locate
+
+struct CountOf {
+  const uint2* r;
+  uint64_t nq;
+  __host__ __device__ uint64_t operator()(uint64_t i) const { return i < nq ? uint64_t(r[i].y) : 0ull; }
+};
+
+// exclusive scan of the per-query hit counts -> CSR offsets, d_hit_off[nq] = total
+cudaError_t scan_hit_offsets(const uint2* d_sp_cnt, uint64_t nq, uint64_t* d_hit_off, void* d_temp,
+                             size_t& temp_bytes, cudaStream_t s) {
+  cub::CountingInputIterator<uint64_t> idx(0);
+  cub::TransformInputIterator<uint64_t, CountOf, cub::CountingInputIterator<uint64_t>> in(idx, CountOf{d_sp_cnt, nq});
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, in, d_hit_off, nq + 1, s);
+  if (d_temp != nullptr) COUNT_LAUNCH();
+  return e;
+}
+
+// get_seq_location, intended semantics (sequence_index.rs:108-141)
+__device__ __forceinline__ void map_location(const IndexView& ix, uint64_t loc, uint64_t* out2) {
+  uint32_t lo = 0;
+  if (ix.n_seqs > 1) {
+    uint32_t hi = ix.n_seqs - 1;
+    while (lo < hi) {
+      uint32_t mid = (lo + hi + 1) >> 1;
+      if (__ldg(ix.seq_starts + mid) <= loc)
+        lo = mid;
+      else
+        hi = mid - 1;
+    }
+  }
+  out2[0] = lo;
+  out2[1] = loc - __ldg(ix.seq_starts + lo);
+}
+
+// One thread per hit, persistent with lane refill: a lane whose walk ends takes the next hit
+// (h += stride), so the geometric walk lengths (rows, not text positions, are sampled --
+// compressed_suffix_array.rs:109-111) do not idle the rest of the warp.
+// hit h -> query via binary search over the CSR offsets, row = sp[q] + (h - off[q]).
+template <int ALPHA, bool MAP>
+__global__ void __launch_bounds__(256)
+    walk_kernel(IndexView ix, const uint2* __restrict__ sp_cnt, const uint64_t* __restrict__ hit_off,
+                uint64_t nq, uint64_t n_hits, uint64_t* __restrict__ out) {
+  const uint64_t stride = gridDim.x * uint64_t(blockDim.x);
+  uint64_t h = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  uint64_t cur = 0;
+  uint32_t row = 0, steps = 0;
+  bool have = false;
+  for (;;) {
+    if (!have) {
+      if (h >= n_hits) break;
+      cur = h;
+      h += stride;
+      // largest q with hit_off[q] <= cur
+      uint64_t lo = 0, hi = nq - 1;
+      while (lo < hi) {
+        uint64_t mid = (lo + hi + 1) >> 1;
+        if (__ldg(hit_off + mid) <= cur)
+          lo = mid;
+        else
+          hi = mid - 1;
+      }
+      row = __ldg(&sp_cnt[lo].x) + uint32_t(cur - __ldg(hit_off + lo));
+      steps = 0;
+      have = true;
+    }
+    if (row_is_sampled(ix, row)) {
+      uint64_t loc = (sa_sample(ix, row) + steps) % ix.bwt_len;  // fm_index.rs:533-534
+      if (MAP)
+        map_location(ix, loc, out + 2 * cur);
+      else
+        out[cur] = loc;
+      have = false;
+      continue;
+    }
+    row = lf_backstep<ALPHA>(ix, row);
+    steps++;
+  }
+}
+
+cudaError_t launch_walk(const IndexView& ix, const uint2* d_sp_cnt, const uint64_t* d_hit_off,
+                        uint64_t nq, uint64_t n_hits, uint64_t* d_hits_pairs, uint64_t* d_locs,
+                        int sm_count, cudaStream_t s) {
+  if (n_hits == 0 || nq == 0) return cudaSuccess;
+  unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (n_hits + 255) / 256)));
+  bool map = d_hits_pairs != nullptr;
+  uint64_t* out = map ? d_hits_pairs : d_locs;
+  if (ix.alphabet == 0) {
+    if (map)
+      walk_kernel<0, true><<<grid, 256, 0, s>>>(ix, d_sp_cnt, d_hit_off, nq, n_hits, out);
+    else
+      walk_kernel<0, false><<<grid, 256, 0, s>>>(ix, d_sp_cnt, d_hit_off, nq, n_hits, out);
+  } else {
+    if (map)
+      walk_kernel<1, true><<<grid, 256, 0, s>>>(ix, d_sp_cnt, d_hit_off, nq, n_hits, out);
+    else
+      walk_kernel<1, false><<<grid, 256, 0, s>>>(ix, d_sp_cnt, d_hit_off, nq, n_hits, out);
+  }
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+// per-query ascending sort of global text positions (== (seq_idx, local_pos) order)
+cudaError_t sort_hit_segments(uint64_t* d_locs_in, uint64_t* d_locs_out, uint64_t n_hits,
+                              uint64_t nq, const uint64_t* d_hit_off, void* d_temp,
+                              size_t& temp_bytes, cudaStream_t s) {
+  cudaError_t e = cub::DeviceSegmentedSort::SortKeys(d_temp, temp_bytes, d_locs_in, d_locs_out,
+                                                     (long long)n_hits, (long long)nq, d_hit_off,
+                                                     d_hit_off + 1, s);
+  if (d_temp != nullptr) COUNT_LAUNCH();
+  return e;
+}
+
+__global__ void map_locations_kernel(IndexView ix, const uint64_t* __restrict__ locs, uint64_t n,
+                                     uint64_t* __restrict__ out) {
+  uint64_t stride = gridDim.x * uint64_t(blockDim.x);
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += stride)
+    map_location(ix, locs[i], out + 2 * i);
+}
+
+cudaError_t launch_map_locations(const IndexView& ix, const uint64_t* d_locs, uint64_t n_hits,
+                                 uint64_t* d_hits_pairs, cudaStream_t s) {
+  if (n_hits == 0) return cudaSuccess;
+  unsigned grid = unsigned(std::min<uint64_t>((n_hits + 255) / 256, 148 * 16));
+  map_locations_kernel<<<grid, 256, 0, s>>>(ix, d_locs, n_hits, d_hits_pairs);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ single steps
+
+template <int ALPHA>
+__global__ void single_update_kernel(IndexView ix, uint32_t sp, uint32_t ep, uint32_t c, uint32_t* out) {
+  lf_update<ALPHA>(ix, sp, ep, c);
+  out[0] = sp;
+  out[1] = ep;
+}
+template <int ALPHA>
+__global__ void single_backstep_kernel(IndexView ix, uint32_t row, uint32_t* out) {
+  out[0] = lf_backstep<ALPHA>(ix, row);
+}
+cudaError_t launch_single_update(const IndexView& ix, uint32_t sp, uint32_t ep, uint32_t dsym,
+                                 uint32_t* d_out2, cudaStream_t s) {
+  if (ix.alphabet == 0)
+    single_update_kernel<0><<<1, 1, 0, s>>>(ix, sp, ep, dsym, d_out2);
+  else
+    single_update_kernel<1><<<1, 1, 0, s>>>(ix, sp, ep, dsym, d_out2);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+cudaError_t launch_single_backstep(const IndexView& ix, uint32_t row, uint32_t* d_out, cudaStream_t s) {
+  if (ix.alphabet == 0)
+    single_backstep_kernel<0><<<1, 1, 0, s>>>(ix, row, d_out);
+  else
+    single_backstep_kernel<1><<<1, 1, 0, s>>>(ix, row, d_out);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ random-gather roofline probe
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// LANES consecutive lanes read one GRANULE-byte aligned granule at a uniformly random place;
+// UNROLL independent granules per group are in flight before any is consumed.
+template <int GRANULE, int LANES, int UNROLL>
+__global__ void __launch_bounds__(256) gather_kernel(const char* __restrict__ buf, uint64_t n_granules,
+                                                     uint64_t reads_per_group, uint64_t seed,
+                                                     uint32_t* __restrict__ sink) {
+  constexpr int BYTES = GRANULE / LANES;          // per lane
+  constexpr int NV = BYTES >= 32 ? BYTES / 32 : 1;  // vector loads per lane
+  const uint32_t lane = threadIdx.x & 31, sub = lane % LANES;
+  const uint64_t group = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) / LANES;
+  uint32_t acc = 0;
+  for (uint64_t it = 0; it < reads_per_group; it += UNROLL) {
+    uint32_t v[UNROLL][NV * (BYTES >= 32 ? 8 : BYTES / 4)];
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      uint64_t g = mix64(seed ^ (group * 0x100000001B3ull + it + u)) % n_granules;
+      const char* p = buf + g * GRANULE + sub * BYTES;
+      if (BYTES >= 32) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+          u32x8 r = ldg256(p + 32 * i);
+#pragma unroll
+          for (int k = 0; k < 8; k++) v[u][8 * i + k] = r.v[k];
+        }
+      } else if (BYTES == 16) {
+        uint4 r = ldg128(reinterpret_cast<const uint4*>(p));
+        v[u][0] = r.x, v[u][1] = r.y, v[u][2] = r.z, v[u][3] = r.w;
+      } else {
+        uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+        v[u][0] = r.x, v[u][1] = r.y;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++)
+#pragma unroll
+      for (int k = 0; k < int(sizeof(v[0]) / 4); k++) acc ^= v[u][k];
+  }
+  if (acc == 0x12345678u) sink[0] = acc;
+}
+
+template <int GRANULE, int LANES>
+static cudaError_t gather_run(const char* buf, uint64_t n_granules, uint64_t n_reads, int iters,
+                              uint32_t* sink, double* ms_out) {
+  constexpr int UNROLL = 4;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  unsigned grid = unsigned(sms) * 8;
+  uint64_t groups = uint64_t(grid) * 256 / LANES;
+  uint64_t per_group = ((n_reads + groups - 1) / groups + UNROLL - 1) / UNROLL * UNROLL;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int i = 0; i < iters + 1; i++) {
+    cudaEventRecord(e0);
+    gather_kernel<GRANULE, LANES, UNROLL><<<grid, 256>>>(buf, n_granules, per_group, 0x5eed + i, sink);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) return e;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (i > 0 && ms < best) best = ms;
+    COUNT_LAUNCH();
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_out = double(best) / (double(per_group * groups) / double(n_reads));  // normalise to n_reads
+  return cudaGetLastError();
+}
+
+cudaError_t run_random_gather(uint64_t footprint_bytes, uint32_t granule, uint32_t lanes,
+                              uint64_t n_reads, int iters, double* reads_per_s, double* gb_per_s) {
+  char* buf = nullptr;
+  uint32_t* sink = nullptr;
+  cudaError_t e = cudaMalloc(&buf, footprint_bytes);
+  if (e != cudaSuccess) return e;
+  e = cudaMalloc(&sink, 4);
+  if (e != cudaSuccess) {
+    cudaFree(buf);
+    return e;
+  }
+  cudaMemset(buf, 1, footprint_bytes);
+  uint64_t n_granules = footprint_bytes / granule;
+  double ms = 0;
+  e = cudaErrorInvalidValue;
+#define GATHER_CASE(G, L) \
+  if (granule == G && lanes == L) e = gather_run<G, L>(buf, n_granules, n_reads, iters, sink, &ms);
+  GATHER_CASE(32, 1) GATHER_CASE(32, 2) GATHER_CASE(32, 4)
+  GATHER_CASE(64, 1) GATHER_CASE(64, 2) GATHER_CASE(64, 4) GATHER_CASE(64, 8)
+  GATHER_CASE(128, 1) GATHER_CASE(128, 2) GATHER_CASE(128, 4) GATHER_CASE(128, 8)
+#undef GATHER_CASE
+  cudaFree(buf);
+  cudaFree(sink);
+  if (e != cudaSuccess) return e;
+  *reads_per_s = double(n_reads) / (ms * 1e-3);
+  *gb_per_s = *reads_per_s * granule * 1e-9;
+  return cudaSuccess;
+}
+
+}  // namespace awry

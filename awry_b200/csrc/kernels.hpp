@@ -1,0 +1,67 @@
+// kernels.hpp -- host-callable launchers of the sm_100a kernels (internal to libawry_b200).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "layout.cuh"
+
+namespace awry {
+
+// packed query stream: DNA 4 bits / symbol (16 per u64), amino 8 bits / symbol (8 per u64);
+// symbols are stored in SEARCH order (last query character first).  Query q starts at word
+// q + (qoff[q] >> log2(symbols per word)); the buffer needs packed_words(...) words (4 of them padding).
+inline uint64_t packed_words(int alphabet, uint64_t nq, uint64_t total_bytes) {
+  return nq + (total_bytes >> (alphabet == 0 ? 4 : 3)) + 4;
+}
+
+enum SearchOut { OUT_COUNT_U64 = 0, OUT_RANGE_U64 = 1, OUT_SP_CNT_U32 = 2 };
+
+struct SearchVariant {
+  int lanes = 0;          // lanes per query (nucleotide: 1, 2 or 4; amino: 1)
+  int tpb = 0;            // threads per block
+  int blocks_per_sm = 0;  // 0 = occupancy-derived
+};
+
+struct LaunchCounters {
+  uint64_t launches = 0;
+};
+
+cudaError_t init_device_tables();  // per device, once: ASCII -> device-symbol LUTs
+
+// reference-layout blocks (staged on the device) -> device layout
+cudaError_t launch_transpose(int alphabet, const uint64_t* d_ref_blocks, uint64_t first_ref_block,
+                             uint64_t n_ref_blocks, uint64_t bwt_len, uint4* d_blocks,
+                             unsigned int* d_dollar_row, cudaStream_t s);
+uint64_t table_entries(int alphabet, uint32_t k);
+cudaError_t launch_build_table(const IndexView& ix, uint2* d_table, uint32_t k, cudaStream_t s);
+
+cudaError_t launch_pack(int alphabet, const uint8_t* d_qbytes, const uint64_t* d_qoff, uint64_t nq,
+                        uint64_t* d_qwords, unsigned long long* d_first_bad, cudaStream_t s);
+cudaError_t launch_search(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
+                          uint64_t nq, SearchOut mode, void* d_out, const SearchVariant& v,
+                          int sm_count, cudaStream_t s);
+
+// locate: CSR offsets from pass 1, LF-walk pass 2
+cudaError_t scan_hit_offsets(const uint2* d_sp_cnt, uint64_t nq, uint64_t* d_hit_off, void* d_temp,
+                             size_t& temp_bytes, cudaStream_t s);
+// writes either awry_hit {seq_idx, local_pos} (d_hits) or global text positions (d_locs)
+cudaError_t launch_walk(const IndexView& ix, const uint2* d_sp_cnt, const uint64_t* d_hit_off,
+                        uint64_t nq, uint64_t n_hits, uint64_t* d_hits_pairs, uint64_t* d_locs,
+                        int sm_count, cudaStream_t s);
+cudaError_t sort_hit_segments(uint64_t* d_locs_in, uint64_t* d_locs_out, uint64_t n_hits,
+                              uint64_t nq, const uint64_t* d_hit_off, void* d_temp,
+                              size_t& temp_bytes, cudaStream_t s);
+cudaError_t launch_map_locations(const IndexView& ix, const uint64_t* d_locs, uint64_t n_hits,
+                                 uint64_t* d_hits_pairs, cudaStream_t s);
+
+cudaError_t launch_single_update(const IndexView& ix, uint32_t sp, uint32_t ep, uint32_t dsym,
+                                 uint32_t* d_out2, cudaStream_t s);
+cudaError_t launch_single_backstep(const IndexView& ix, uint32_t row, uint32_t* d_out, cudaStream_t s);
+
+cudaError_t run_random_gather(uint64_t footprint_bytes, uint32_t granule, uint32_t lanes,
+                              uint64_t n_reads, int iters, double* reads_per_s, double* gb_per_s);
+
+uint64_t kernel_launch_count();
+void kernel_launch_count_reset();
+
+}  // namespace awry

@@ -1,0 +1,232 @@
+// layout.cuh -- device-side index layout and rank primitives (sm_100a).
+//
+// Replaces the reference's rank structure: the 256-row windowed bit-vector blocks of
+// /root/reference/src/bwt.rs:12-25 (160 B nucleotide / 352 B amino, u64 milestones) and the
+// AVX2/NEON predicate + masked popcount of simd_instructions.rs:78-121.
+//
+// Device layout (row pointers are 32-bit: bwt_len < 2^32 is enforced at load time):
+//
+//   NUCLEOTIDE  block = 128 BWT rows = 64 B = 4 chunks of 16 B (one uint4 / one LDG.128 each)
+//               chunk j = { p0, p1, p2, cnt_j }   p_b = bit-plane b of rows 32j..32j+31
+//               (bit t = row 32j+t), cnt_j = #symbol j in BWT[0 .. block start)  (j: A,C,G,T).
+//               Row code (3 planes) = device symbol: A0 C1 G2 T3 N4 $5, padding rows 7.
+//               The N milestone is derived: start - (A+C+G+T) - [$ row < start].
+//               => 4 bits per BWT row all-in; one LF step reads one 64-B aligned block.
+//
+//   AMINO       block = 256 rows = 256 B = 8 chunks of 32 B (one LDG.256 each)
+//               chunk j = { p0..p4, cnt_{3j}, cnt_{3j+1}, cnt_{3j+2} }, 24 count slots,
+//               slot s-1 = #symbol s in BWT[0 .. block start), s = reference symbol index 1..21.
+//               Row code (5 planes) = reference symbol index (0 = '$' and padding rows).
+//
+// Ranks are INCLUSIVE, Occ(c,i) = #c in BWT[0..=i], as in bwt.rs:114-135 / fm_index.rs:559-582.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace awry {
+
+// ---- device symbol numbering -------------------------------------------------------------
+// nucleotide: A0 C1 G2 T3 N4 $5 (reference indices, alphabet.rs:228-235: $0 A1 C2 G3 N4 T5)
+// amino:      reference index unchanged (alphabet.rs:174-196), X = 20 is the ambiguity symbol
+constexpr int DNA_N = 4, DNA_SENTINEL = 5, DNA_PAD = 7;
+constexpr int AMINO_X = 20, AMINO_SENTINEL = 0;
+
+constexpr uint32_t DNA_ROWS_PER_BLOCK = 128, DNA_BLOCK_UINT4 = 4;
+constexpr uint32_t AMINO_ROWS_PER_BLOCK = 256, AMINO_BLOCK_UINT4 = 16;
+
+struct IndexView {
+  const uint4* __restrict__ blocks;
+  const uint64_t* __restrict__ sa_words;
+  const uint2* __restrict__ table;         // k-mer seeds: (sp, ep), empty = (1,0)
+  const uint64_t* __restrict__ seq_starts;
+  uint32_t c_lo[24];                       // C[c]      by device symbol (search.rs:43-48)
+  uint32_t c_hi[24];                       // C[c+1]-1  by device symbol
+  uint32_t bwt_len;
+  uint32_t dollar_row;                     // row whose BWT symbol is '$' (SA = 0)
+  uint32_t sa_ratio;
+  uint32_t sa_pow2;                        // 1 if sa_ratio is a power of two
+  uint32_t sa_ratio_shift;                 // log2(sa_ratio) when sa_pow2
+  uint32_t sa_bits;
+  uint32_t kmer_len;                       // 0 = no seed table
+  uint32_t n_seqs;
+  uint32_t alphabet;
+};
+
+// 128-/256-bit read-only loads that do not allocate in L1: every block is touched once per
+// step by one query, so L1 residency buys nothing and only evicts the query words.
+__device__ __forceinline__ uint4 ldg128(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+struct u32x8 {
+  uint32_t v[8];
+};
+__device__ __forceinline__ u32x8 ldg256(const void* p) {  // sm_100+: LDG.E.256
+  u32x8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]),
+                 "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+
+// mask of bits 0..=local for the 32-row chunk j (masked_popcount, simd_instructions.rs:96-121)
+__device__ __forceinline__ uint32_t chunk_mask(uint32_t local, uint32_t j) {
+  int n = int(local) + 1 - int(32 * j);
+  n = n < 0 ? 0 : n;
+  return n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
+}
+
+// ---- nucleotide --------------------------------------------------------------------------
+
+// rows of a chunk whose 3-bit code equals c; (m0,m1,m2) = code bits of c spread to full words
+__device__ __forceinline__ uint32_t dna_match(const uint4& ch, uint32_t m0, uint32_t m1, uint32_t m2) {
+  return ~(ch.x ^ m0) & ~(ch.y ^ m1) & ~(ch.z ^ m2);
+}
+
+struct DnaBlockRegs {
+  uint4 ch[4];
+};
+__device__ __forceinline__ DnaBlockRegs dna_load_block(const IndexView& ix, uint32_t blk) {
+  DnaBlockRegs b;
+  const uint4* p = ix.blocks + size_t(blk) * DNA_BLOCK_UINT4;
+#pragma unroll
+  for (int j = 0; j < 4; j++) b.ch[j] = ldg128(p + j);
+  return b;
+}
+// milestone of device symbol c (0..4) at the start of block blk
+__device__ __forceinline__ uint32_t dna_milestone(const IndexView& ix, const DnaBlockRegs& b,
+                                                  uint32_t blk, uint32_t c) {
+  if (c < 4) return c == 0 ? b.ch[0].w : c == 1 ? b.ch[1].w : c == 2 ? b.ch[2].w : b.ch[3].w;
+  uint32_t start = blk * DNA_ROWS_PER_BLOCK;
+  return start - (b.ch[0].w + b.ch[1].w + b.ch[2].w + b.ch[3].w) - (ix.dollar_row < start ? 1u : 0u);
+}
+// Occ(c, pos) within an already loaded block (c in 0..4)
+__device__ __forceinline__ uint32_t dna_occ_in_block(const IndexView& ix, const DnaBlockRegs& b,
+                                                     uint32_t blk, uint32_t local, uint32_t c) {
+  uint32_t m0 = (c & 1) ? ~0u : 0u, m1 = (c & 2) ? ~0u : 0u, m2 = (c & 4) ? ~0u : 0u;
+  uint32_t r = dna_milestone(ix, b, blk, c);
+#pragma unroll
+  for (int j = 0; j < 4; j++) r += __popc(dna_match(b.ch[j], m0, m1, m2) & chunk_mask(local, j));
+  return r;
+}
+__device__ __forceinline__ uint32_t dna_code_at(const DnaBlockRegs& b, uint32_t local) {
+  uint32_t j = local >> 5, t = local & 31;
+  uint4 ch = j == 0 ? b.ch[0] : j == 1 ? b.ch[1] : j == 2 ? b.ch[2] : b.ch[3];
+  return ((ch.x >> t) & 1u) | (((ch.y >> t) & 1u) << 1) | (((ch.z >> t) & 1u) << 2);
+}
+
+// ---- amino -------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t amino_match(const u32x8& ch, uint32_t s) {
+  uint32_t r = ~0u;
+#pragma unroll
+  for (int p = 0; p < 5; p++) r &= ((s >> p) & 1u) ? ch.v[p] : ~ch.v[p];
+  return r;
+}
+__device__ __forceinline__ uint32_t amino_milestone(const IndexView& ix, uint32_t blk, uint32_t s) {
+  uint32_t slot = s - 1;
+  const uint32_t* words =
+      reinterpret_cast<const uint32_t*>(ix.blocks + size_t(blk) * AMINO_BLOCK_UINT4);
+  return __ldg(words + 8 * (slot / 3) + 5 + (slot % 3));
+}
+// Occ(s, pos) for reference symbol index s in 1..21
+__device__ __forceinline__ uint32_t amino_occ(const IndexView& ix, uint32_t pos, uint32_t s) {
+  uint32_t blk = pos >> 8, local = pos & 255;
+  const char* base = reinterpret_cast<const char*>(ix.blocks + size_t(blk) * AMINO_BLOCK_UINT4);
+  uint32_t r = amino_milestone(ix, blk, s);
+  uint32_t last = local >> 5;
+  for (uint32_t j = 0; j <= last; j++) {
+    u32x8 ch = ldg256(base + 32 * j);
+    r += __popc(amino_match(ch, s) & chunk_mask(local, j));
+  }
+  return r;
+}
+// Occ at two positions of the SAME block with one pass over its chunks
+__device__ __forceinline__ void amino_occ2_same_block(const IndexView& ix, uint32_t blk,
+                                                      uint32_t la, uint32_t lb, uint32_t s,
+                                                      uint32_t& ra, uint32_t& rb) {
+  const char* base = reinterpret_cast<const char*>(ix.blocks + size_t(blk) * AMINO_BLOCK_UINT4);
+  uint32_t ms = amino_milestone(ix, blk, s);
+  uint32_t a = ms, b = ms;
+  uint32_t last = (la > lb ? la : lb) >> 5;
+  for (uint32_t j = 0; j <= last; j++) {
+    u32x8 ch = ldg256(base + 32 * j);
+    uint32_t m = amino_match(ch, s);
+    a += __popc(m & chunk_mask(la, j));
+    b += __popc(m & chunk_mask(lb, j));
+  }
+  ra = a;
+  rb = b;
+}
+__device__ __forceinline__ uint32_t amino_symbol_at(const IndexView& ix, uint32_t pos) {
+  uint32_t blk = pos >> 8, local = pos & 255, j = local >> 5, t = local & 31;
+  const uint32_t* w =
+      reinterpret_cast<const uint32_t*>(ix.blocks + size_t(blk) * AMINO_BLOCK_UINT4) + 8 * j;
+  uint32_t s = 0;
+#pragma unroll
+  for (int p = 0; p < 5; p++) s |= ((__ldg(w + p) >> t) & 1u) << p;
+  return s;
+}
+
+// ---- alphabet-generic scalar steps (one thread) ------------------------------------------
+// Used by the seed-table builder, the single-step API, the amino kernels and the slow paths.
+
+// update_range_with_symbol (fm_index.rs:559-582) for device symbol c; requires sp >= 1.
+template <int ALPHA>
+__device__ __forceinline__ void lf_update(const IndexView& ix, uint32_t& sp, uint32_t& ep, uint32_t c) {
+  uint32_t pa = sp - 1, pb = ep;
+  uint32_t ra, rb;
+  if (ALPHA == 0) {
+    uint32_t ba = pa >> 7, bb = pb >> 7;
+    DnaBlockRegs b = dna_load_block(ix, ba);
+    ra = dna_occ_in_block(ix, b, ba, pa & 127, c);
+    if (bb != ba) b = dna_load_block(ix, bb);
+    rb = dna_occ_in_block(ix, b, bb, pb & 127, c);
+  } else {
+    uint32_t ba = pa >> 8, bb = pb >> 8;
+    if (ba == bb) {
+      amino_occ2_same_block(ix, ba, pa & 255, pb & 255, c, ra, rb);
+    } else {
+      ra = amino_occ(ix, pa, c);
+      rb = amino_occ(ix, pb, c);
+    }
+  }
+  sp = ix.c_lo[c] + ra;
+  ep = ix.c_lo[c] + rb - 1;
+}
+
+// backstep (fm_index.rs:585-593): LF(row), or 0 when the row holds '$'
+template <int ALPHA>
+__device__ __forceinline__ uint32_t lf_backstep(const IndexView& ix, uint32_t row) {
+  if (ALPHA == 0) {
+    uint32_t blk = row >> 7, local = row & 127;
+    DnaBlockRegs b = dna_load_block(ix, blk);
+    uint32_t c = dna_code_at(b, local);
+    if (c >= DNA_SENTINEL) return 0;
+    return ix.c_lo[c] + dna_occ_in_block(ix, b, blk, local, c) - 1;
+  } else {
+    uint32_t s = amino_symbol_at(ix, row);
+    if (s == AMINO_SENTINEL) return 0;
+    return ix.c_lo[s] + amino_occ(ix, row, s) - 1;
+  }
+}
+
+__device__ __forceinline__ bool row_is_sampled(const IndexView& ix, uint32_t row) {
+  return ix.sa_pow2 ? (row & (ix.sa_ratio - 1)) == 0 : (row % ix.sa_ratio) == 0;
+}
+// CompressedSuffixArray::reconstruct_value (compressed_suffix_array.rs:76-106)
+__device__ __forceinline__ uint64_t sa_sample(const IndexView& ix, uint32_t row) {
+  uint64_t e = ix.sa_pow2 ? (row >> ix.sa_ratio_shift) : (row / ix.sa_ratio);
+  uint64_t bit = e * ix.sa_bits;
+  uint64_t w = bit >> 6;
+  uint32_t s = uint32_t(bit & 63);
+  uint64_t v = __ldg(ix.sa_words + w) >> s;
+  if (s + ix.sa_bits > 64) v |= __ldg(ix.sa_words + w + 1) << (64 - s);
+  return ix.sa_bits >= 64 ? v : (v & ((1ull << ix.sa_bits) - 1));
+}
+
+}  // namespace awry

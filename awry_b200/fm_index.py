@@ -1,0 +1,402 @@
+"""Host-side mirror of the reference's public search API over the C ABI (ctypes).
+
+Names, argument meaning and error behaviour follow /root/reference/src:
+  FmIndex.load / from_parts            fm_index_file.rs:132, fm_index.rs:271-289
+  count_string / locate_string         fm_index.rs:499-501, :516-544
+  parallel_count / parallel_locate     fm_index.rs:455-487
+  update_range_with_symbol / backstep  fm_index.rs:559-593
+  initial_search_range                 fm_index.rs:383
+  SearchRange                          search.rs:25-81
+  LocalizedSequencePosition            sequence_index.rs:32-78
+Where the reference panics (empty query, sentinel in a query) this raises AwryError.
+"""
+import ctypes as C
+import enum
+import os
+from typing import Iterable, List, NamedTuple, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libawry_b200.so")
+
+
+class AwryError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[awry_b200 {code}] {message}")
+        self.code = code
+
+
+class SymbolAlphabet(enum.IntEnum):  # alphabet.rs:28-31
+    Nucleotide = 0
+    Amino = 1
+
+
+class Symbol(NamedTuple):  # alphabet.rs:76-79 (ASCII-encoded symbols only)
+    alphabet: SymbolAlphabet
+    ascii: str
+
+    @classmethod
+    def new_ascii(cls, alphabet: SymbolAlphabet, ch: str) -> "Symbol":
+        return cls(alphabet, ch.upper())
+
+
+class SearchRange(NamedTuple):  # search.rs:25-28
+    start_ptr: int
+    end_ptr: int
+
+    @classmethod
+    def zero(cls) -> "SearchRange":
+        return cls(1, 0)
+
+    def is_empty(self) -> bool:
+        return self.start_ptr > self.end_ptr
+
+    def len(self) -> int:
+        return 0 if self.is_empty() else self.end_ptr - self.start_ptr + 1
+
+    def range_iter(self) -> range:
+        return range(0, 0) if self.is_empty() else range(self.start_ptr, self.end_ptr + 1)
+
+
+class LocalizedSequencePosition(NamedTuple):  # sequence_index.rs:33-36
+    sequence_idx: int
+    local_position: int
+
+
+class _Range(C.Structure):
+    _fields_ = [("start_ptr", C.c_uint64), ("end_ptr", C.c_uint64)]
+
+
+class _Info(C.Structure):
+    _fields_ = [("version", C.c_uint64), ("sa_ratio", C.c_uint64), ("bwt_len", C.c_uint64),
+                ("alphabet", C.c_uint32), ("kmer_len", C.c_uint32), ("n_prefix_sums", C.c_uint32),
+                ("n_devices", C.c_uint32), ("prefix_sums", C.c_uint64 * 23),
+                ("n_sequences", C.c_uint64), ("device_bytes_blocks", C.c_uint64),
+                ("device_bytes_sa", C.c_uint64), ("device_bytes_table", C.c_uint64),
+                ("devices", C.c_int32 * 16)]
+
+
+class _Parts(C.Structure):
+    _fields_ = [("alphabet", C.c_uint32), ("kmer_len", C.c_uint32), ("sa_ratio", C.c_uint64),
+                ("bwt_len", C.c_uint64), ("version", C.c_uint64), ("blocks", C.c_void_p),
+                ("prefix_sums", C.c_void_p), ("sa_words", C.c_void_p), ("seq_starts", C.c_void_p),
+                ("headers", C.c_void_p), ("n_sequences", C.c_uint64)]
+
+
+class Profile(C.Structure):
+    _fields_ = [("launches", C.c_uint64), ("search_launches", C.c_uint64), ("search_ms", C.c_double),
+                ("walk_launches", C.c_uint64), ("walk_ms", C.c_double), ("pack_launches", C.c_uint64),
+                ("pack_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+# every symbol include/awry_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = ["awry_index_load", "awry_index_from_parts", "awry_index_free", "awry_index_info",
+           "awry_index_sequence_header", "awry_count_batch", "awry_search_batch",
+           "awry_locate_batch", "awry_hits_free", "awry_initial_range", "awry_update_range",
+           "awry_backstep", "awry_count_device", "awry_locate_device", "awry_device_free",
+           "awry_device_check", "awry_profile_enable", "awry_profile_reset", "awry_profile_get",
+           "awry_bench_random_gather", "awry_set_search_variant", "awry_last_error", "awry_version"]
+
+
+def native():
+    """The loaded C-ABI library.  Raises (never falls back) when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} is missing: build it with `make -C awry_b200/csrc` (or "
+            "`python -c 'import __graft_entry__ as g; g.build()'`). awry_b200 has no CPU fallback.")
+    L = C.CDLL(path)
+    vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
+    L.awry_last_error.restype = C.c_char_p
+    L.awry_version.restype = C.c_char_p
+    L.awry_index_load.argtypes = [C.c_char_p, vp, i32, C.POINTER(vp)]
+    L.awry_index_from_parts.argtypes = [C.POINTER(_Parts), vp, i32, C.POINTER(vp)]
+    L.awry_index_free.argtypes = [vp]
+    L.awry_index_free.restype = None
+    L.awry_index_info.argtypes = [vp, C.POINTER(_Info)]
+    L.awry_index_sequence_header.argtypes = [vp, u64, C.POINTER(C.c_char_p), C.POINTER(u64)]
+    L.awry_count_batch.argtypes = [vp, vp, vp, u64, vp]
+    L.awry_search_batch.argtypes = [vp, vp, vp, u64, vp]
+    L.awry_locate_batch.argtypes = [vp, vp, vp, u64, C.c_uint32, vp, C.POINTER(vp), C.POINTER(u64)]
+    L.awry_hits_free.argtypes = [vp]
+    L.awry_hits_free.restype = None
+    L.awry_initial_range.argtypes = [vp, C.c_uint8, C.POINTER(_Range)]
+    L.awry_update_range.argtypes = [vp, _Range, C.c_uint8, C.POINTER(_Range)]
+    L.awry_backstep.argtypes = [vp, u64, C.POINTER(u64)]
+    L.awry_count_device.argtypes = [vp, i32, vp, vp, u64, vp, vp]
+    L.awry_locate_device.argtypes = [vp, i32, vp, vp, u64, C.c_uint32, vp, C.POINTER(vp),
+                                     C.POINTER(u64), vp]
+    L.awry_device_free.argtypes = [vp, i32, vp]
+    L.awry_device_check.argtypes = [vp, i32, vp]
+    L.awry_profile_enable.argtypes = [i32]
+    L.awry_profile_get.argtypes = [C.POINTER(Profile)]
+    L.awry_bench_random_gather.argtypes = [i32, u64, C.c_uint32, C.c_uint32, u64, i32,
+                                           C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.awry_set_search_variant.argtypes = [i32, i32, i32]
+    _LIB = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise AwryError(rc, native().awry_last_error().decode(errors="replace"))
+
+
+def pack_queries(queries: Iterable) -> Tuple[np.ndarray, np.ndarray]:
+    """Collects an iterable of str/bytes queries into the C ABI's (qbytes, qoff) form, order
+    preserved -- what the Rust facade does with its `impl ParallelIterator<Item=&str>`."""
+    qs = [q.encode() if isinstance(q, str) else bytes(q) for q in queries]
+    off = np.zeros(len(qs) + 1, dtype=np.uint64)
+    if qs:
+        off[1:] = np.cumsum([len(q) for q in qs], dtype=np.uint64)
+    data = np.frombuffer(b"".join(qs), dtype=np.uint8).copy() if qs else np.zeros(0, np.uint8)
+    return data, off
+
+
+LOCATE_BWT_ORDER, LOCATE_SORTED = 0, 1
+
+
+class FmIndex:
+    """Device-resident replica of an awry FM-index (query side)."""
+
+    def __init__(self, handle: int):
+        self._h = C.c_void_p(handle)
+        info = _Info()
+        _check(native().awry_index_info(self._h, C.byref(info)))
+        self._info = info
+
+    # ---- construction -------------------------------------------------------------------
+    @classmethod
+    def load(cls, path, devices: Sequence[int] = None) -> "FmIndex":
+        """FmIndex::load (fm_index_file.rs:132-160)."""
+        h = C.c_void_p()
+        dev = (C.c_int * len(devices))(*devices) if devices else None
+        _check(native().awry_index_load(os.fsencode(path), dev, len(devices) if devices else 0,
+                                        C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def from_parts(cls, alphabet, sa_ratio, bwt_len, kmer_len, blocks, prefix_sums, sa_words,
+                   seq_starts=None, headers=None, devices: Sequence[int] = None) -> "FmIndex":
+        """Device replica of the arrays the reference's FmIndex::new produced
+        (fm_index.rs:242-251), all in the reference layout."""
+        blocks = np.ascontiguousarray(blocks, dtype=np.uint64)
+        prefix_sums = np.ascontiguousarray(prefix_sums, dtype=np.uint64)
+        sa_words = np.ascontiguousarray(sa_words, dtype=np.uint64)
+        if seq_starts is None:
+            seq_starts = np.zeros(1, dtype=np.uint64)
+        seq_starts = np.ascontiguousarray(seq_starts, dtype=np.uint64)
+        hdr_arr = None
+        if headers is not None:
+            hdr_arr = (C.c_char_p * len(headers))(*[h.encode() for h in headers])
+        p = _Parts(int(alphabet), int(kmer_len), int(sa_ratio), int(bwt_len), 1, blocks.ctypes.data,
+                   prefix_sums.ctypes.data, sa_words.ctypes.data, seq_starts.ctypes.data,
+                   C.cast(hdr_arr, C.c_void_p) if hdr_arr is not None else None, len(seq_starts))
+        h = C.c_void_p()
+        dev = (C.c_int * len(devices))(*devices) if devices else None
+        _check(native().awry_index_from_parts(C.byref(p), dev, len(devices) if devices else 0,
+                                              C.byref(h)))
+        return cls(h.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            native().awry_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- getters (fm_index.rs:302-368) ----------------------------------------------------
+    @property
+    def handle(self):
+        return self._h
+
+    def alphabet(self) -> SymbolAlphabet:
+        return SymbolAlphabet(self._info.alphabet)
+
+    def suffix_array_compression_ratio(self) -> int:
+        return int(self._info.sa_ratio)
+
+    def bwt_len(self) -> int:
+        return int(self._info.bwt_len)
+
+    def version_number(self) -> int:
+        return int(self._info.version)
+
+    def prefix_sums(self) -> List[int]:
+        return [int(self._info.prefix_sums[i]) for i in range(self._info.n_prefix_sums)]
+
+    def kmer_len(self) -> int:
+        return int(self._info.kmer_len)
+
+    def n_devices(self) -> int:
+        return int(self._info.n_devices)
+
+    def device_bytes(self) -> dict:
+        return {"blocks": int(self._info.device_bytes_blocks), "sa": int(self._info.device_bytes_sa),
+                "table": int(self._info.device_bytes_table)}
+
+    def sequence_header(self, seq_idx: int) -> str:
+        p, n = C.c_char_p(), C.c_uint64()
+        _check(native().awry_index_sequence_header(self._h, seq_idx, C.byref(p), C.byref(n)))
+        return C.string_at(p, n.value).decode(errors="replace")
+
+    # ---- single steps ---------------------------------------------------------------------
+    @staticmethod
+    def _ascii(sym) -> int:
+        if isinstance(sym, Symbol):
+            sym = sym.ascii
+        if isinstance(sym, str):
+            return ord(sym)
+        if isinstance(sym, bytes):
+            return sym[0]
+        return int(sym)
+
+    def initial_search_range(self, sym) -> SearchRange:
+        r = _Range()
+        _check(native().awry_initial_range(self._h, self._ascii(sym), C.byref(r)))
+        return SearchRange(r.start_ptr, r.end_ptr)
+
+    def update_range_with_symbol(self, search_range: SearchRange, sym) -> SearchRange:
+        r = _Range()
+        _check(native().awry_update_range(self._h, _Range(search_range[0], search_range[1]),
+                                          self._ascii(sym), C.byref(r)))
+        return SearchRange(r.start_ptr, r.end_ptr)
+
+    def backstep(self, search_pointer: int) -> int:
+        out = C.c_uint64()
+        _check(native().awry_backstep(self._h, search_pointer, C.byref(out)))
+        return out.value
+
+    # ---- batched search -------------------------------------------------------------------
+    def count_packed(self, qbytes: np.ndarray, qoff: np.ndarray, out: np.ndarray = None) -> np.ndarray:
+        qbytes = np.ascontiguousarray(qbytes, dtype=np.uint8)
+        qoff = np.ascontiguousarray(qoff, dtype=np.uint64)
+        nq = len(qoff) - 1
+        counts = out if out is not None else np.empty(nq, dtype=np.uint64)
+        _check(native().awry_count_batch(self._h, qbytes.ctypes.data, qoff.ctypes.data, nq,
+                                         counts.ctypes.data))
+        return counts
+
+    def search_packed(self, qbytes: np.ndarray, qoff: np.ndarray) -> np.ndarray:
+        qbytes = np.ascontiguousarray(qbytes, dtype=np.uint8)
+        qoff = np.ascontiguousarray(qoff, dtype=np.uint64)
+        nq = len(qoff) - 1
+        ranges = np.empty((nq, 2), dtype=np.uint64)
+        _check(native().awry_search_batch(self._h, qbytes.ctypes.data, qoff.ctypes.data, nq,
+                                          ranges.ctypes.data))
+        return ranges
+
+    def locate_packed(self, qbytes: np.ndarray, qoff: np.ndarray, sorted_hits: bool = False):
+        """-> (hit_off uint64[nq+1], hits uint64[n_hits, 2] = (seq_idx, local_pos))"""
+        qbytes = np.ascontiguousarray(qbytes, dtype=np.uint8)
+        qoff = np.ascontiguousarray(qoff, dtype=np.uint64)
+        nq = len(qoff) - 1
+        hit_off = np.zeros(nq + 1, dtype=np.uint64)
+        hits, n = C.c_void_p(), C.c_uint64()
+        _check(native().awry_locate_batch(self._h, qbytes.ctypes.data, qoff.ctypes.data, nq,
+                                          LOCATE_SORTED if sorted_hits else LOCATE_BWT_ORDER,
+                                          hit_off.ctypes.data, C.byref(hits), C.byref(n)))
+        if n.value:
+            arr = np.ctypeslib.as_array(C.cast(hits, C.POINTER(C.c_uint64)), shape=(n.value, 2)).copy()
+        else:
+            arr = np.zeros((0, 2), dtype=np.uint64)
+        native().awry_hits_free(hits)
+        return hit_off, arr
+
+    def get_search_range_for_string(self, query) -> SearchRange:
+        qb, qo = pack_queries([query])
+        r = self.search_packed(qb, qo)[0]
+        return SearchRange(int(r[0]), int(r[1]))
+
+    def count_string(self, query) -> int:
+        """FmIndex::count_string (fm_index.rs:499-501): a batch of one."""
+        qb, qo = pack_queries([query])
+        return int(self.count_packed(qb, qo)[0])
+
+    def locate_string(self, query) -> List[LocalizedSequencePosition]:
+        """FmIndex::locate_string (fm_index.rs:516-544): hits in BWT-row order."""
+        qb, qo = pack_queries([query])
+        _, hits = self.locate_packed(qb, qo)
+        return [LocalizedSequencePosition(int(a), int(b)) for a, b in hits]
+
+    def parallel_count(self, queries: Iterable) -> List[int]:
+        """FmIndex::parallel_count (fm_index.rs:455-460); input order preserved."""
+        qb, qo = pack_queries(queries)
+        return [int(c) for c in self.count_packed(qb, qo)]
+
+    def parallel_locate(self, queries: Iterable) -> List[List[LocalizedSequencePosition]]:
+        """FmIndex::parallel_locate (fm_index.rs:479-487)."""
+        qb, qo = pack_queries(queries)
+        off, hits = self.locate_packed(qb, qo)
+        out = []
+        for i in range(len(qo) - 1):
+            seg = hits[int(off[i]):int(off[i + 1])]
+            out.append([LocalizedSequencePosition(int(a), int(b)) for a, b in seg])
+        return out
+
+    # ---- device-resident (raw device pointers, e.g. torch tensors' data_ptr()) -------------
+    def count_device(self, d_qbytes: int, d_qoff: int, nq: int, d_counts: int, stream: int = 0,
+                     replica: int = 0):
+        _check(native().awry_count_device(self._h, replica, d_qbytes, d_qoff, nq, d_counts, stream))
+
+    def locate_device(self, d_qbytes: int, d_qoff: int, nq: int, d_hit_off: int, sorted_hits=False,
+                      stream: int = 0, replica: int = 0):
+        """-> (device pointer to n_hits x {u64 seq_idx, u64 local_pos}, n_hits); free with device_free"""
+        hits, n = C.c_void_p(), C.c_uint64()
+        _check(native().awry_locate_device(self._h, replica, d_qbytes, d_qoff, nq,
+                                           LOCATE_SORTED if sorted_hits else LOCATE_BWT_ORDER,
+                                           d_hit_off, C.byref(hits), C.byref(n), stream))
+        return hits.value, n.value
+
+    def device_free(self, ptr: int, replica: int = 0):
+        _check(native().awry_device_free(self._h, replica, ptr))
+
+    def device_check(self, stream: int = 0, replica: int = 0):
+        _check(native().awry_device_check(self._h, replica, stream))
+
+
+def profile_enable(on: bool):
+    _check(native().awry_profile_enable(1 if on else 0))
+
+
+def profile_reset():
+    _check(native().awry_profile_reset())
+
+
+def profile_get() -> dict:
+    p = Profile()
+    _check(native().awry_profile_get(C.byref(p)))
+    return p.as_dict()
+
+
+def bench_random_gather(device: int, footprint_bytes: int, granule: int, lanes: int, n_reads: int,
+                        iters: int = 3):
+    r, g = C.c_double(), C.c_double()
+    _check(native().awry_bench_random_gather(device, footprint_bytes, granule, lanes, n_reads, iters,
+                                             C.byref(r), C.byref(g)))
+    return r.value, g.value
+
+
+def set_search_variant(lanes: int = 0, tpb: int = 0, blocks_per_sm: int = 0):
+    _check(native().awry_set_search_variant(lanes, tpb, blocks_per_sm))

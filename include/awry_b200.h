@@ -1,0 +1,207 @@
+/*
+ * awry_b200.h -- C ABI of the B200-native batched FM-index search path.
+ *
+ * Drop-in boundary for the query side of the Rust crate `awry` 0.3.1
+ * (awry::fm_index::FmIndex).  The reference has no FFI of its own; a thin Rust facade
+ * crate (rust/ in this repo) keeps the reference's public signatures
+ * and binds exactly these entry points.  Each declaration cites the reference interface it
+ * replaces (paths under /root/reference/src).
+ *
+ * Conventions: every function returns AWRY_OK (0) or a negative awry_status; nothing
+ * unwinds or aborts across this boundary; awry_last_error() gives a thread-local message.
+ * An awry_index is immutable after creation, so the *_batch calls may be issued
+ * concurrently from many host threads (each call uses a private stream and workspace),
+ * like `&self` methods called from the rayon pool in the reference.
+ * There is NO CPU fallback: every search entry point fails with AWRY_ERR_CUDA when no
+ * usable sm_100 device is present.
+ */
+#ifndef AWRY_B200_H
+#define AWRY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum awry_status {
+  AWRY_OK = 0,
+  AWRY_ERR_INVALID_ARG = -1,
+  AWRY_ERR_IO = -2,          /* FmIndex::load -> io::Error (fm_index_file.rs:132)              */
+  AWRY_ERR_FORMAT = -3,      /* bad label / header (fm_index_file.rs:145-150)                  */
+  AWRY_ERR_CUDA = -4,        /* no device, allocation or launch failure                        */
+  AWRY_ERR_INVALID_QUERY = -5, /* empty query or a query containing '$'/'#': the reference
+                                  panics or is UB here (fm_index.rs:406, bwt.rs:127)           */
+  AWRY_ERR_UNSUPPORTED = -6, /* e.g. bwt_len >= 2^32 (device layout uses 32-bit row pointers)  */
+  AWRY_ERR_NOMEM = -7
+} awry_status;
+
+/* awry::alphabet::SymbolAlphabet (alphabet.rs:28-31); values = the file header's alphabet id */
+enum { AWRY_NUCLEOTIDE = 0, AWRY_AMINO = 1 };
+
+typedef struct awry_index awry_index; /* opaque; replaces awry::fm_index::FmIndex (fm_index.rs:41-56) */
+
+/* awry::search::SearchRange (search.rs:25-28): inclusive [start_ptr, end_ptr], empty iff start > end */
+typedef struct awry_range {
+  uint64_t start_ptr;
+  uint64_t end_ptr;
+} awry_range;
+
+/* awry::sequence_index::LocalizedSequencePosition (sequence_index.rs:33-36) */
+typedef struct awry_hit {
+  uint64_t seq_idx;
+  uint64_t local_pos;
+} awry_hit;
+
+/* Getters of FmIndex (fm_index.rs:302-368) plus sizes of the device replica. */
+typedef struct awry_info {
+  uint64_t version;          /* version_number()  fm_index.rs:350 */
+  uint64_t sa_ratio;         /* suffix_array_compression_ratio()  fm_index.rs:320 */
+  uint64_t bwt_len;          /* bwt_len()  fm_index.rs:335 */
+  uint32_t alphabet;         /* alphabet()  fm_index.rs:302 */
+  uint32_t kmer_len;         /* KmerLookupTable::kmer_len  kmer_lookup_table.rs:86 */
+  uint32_t n_prefix_sums;    /* 7 / 23 */
+  uint32_t n_devices;
+  uint64_t prefix_sums[23];  /* prefix_sums()  fm_index.rs:368 */
+  uint64_t n_sequences;
+  uint64_t device_bytes_blocks; /* per replica */
+  uint64_t device_bytes_sa;
+  uint64_t device_bytes_table;
+  int32_t devices[16];
+} awry_info;
+
+/* The fields FmIndex::new hands over after the reference's CPU construction
+ * (fm_index.rs:242-251), all in the reference's own in-memory layout:
+ *   blocks      ceil(bwt_len/256) blocks, each = planes (3|5 x 4 u64) then milestones (8|24 u64)
+ *               (bwt.rs:12-25; same bytes as the file, fm_index_file.rs:58-68)
+ *   prefix_sums card+1 u64 (fm_index.rs:233-240)
+ *   sa_words    CompressedSuffixArray::data (compressed_suffix_array.rs:13,113-123)
+ *   seq_starts  SequenceIndex start positions (sequence_index.rs:10-13); headers optional */
+typedef struct awry_parts {
+  uint32_t alphabet;
+  uint32_t kmer_len;
+  uint64_t sa_ratio;
+  uint64_t bwt_len;
+  uint64_t version;
+  const uint64_t *blocks;
+  const uint64_t *prefix_sums;
+  const uint64_t *sa_words;
+  const uint64_t *seq_starts;
+  const char *const *headers; /* may be NULL */
+  uint64_t n_sequences;
+} awry_parts;
+
+/* ------------------------------------------------------------------ index lifetime */
+
+/* FmIndex::load (fm_index_file.rs:132-160, :184-287): reads an `.awry` v1 file, re-lays the
+ * BWT blocks out for the device, rebuilds the k-mer seed table on the device (the file's table
+ * is never consulted, as in the reference: kmer_lookup_table.rs:90-110) and replicates the
+ * index on each listed CUDA device.  devices == NULL / n_dev == 0 means device 0. */
+int awry_index_load(const char *path, const int *devices, int n_dev, awry_index **out);
+
+/* Device replica of an index the reference's FmIndex::new (fm_index.rs:142-268) just built. */
+int awry_index_from_parts(const awry_parts *parts, const int *devices, int n_dev, awry_index **out);
+
+void awry_index_free(awry_index *index);
+
+int awry_index_info(const awry_index *index, awry_info *info);
+
+/* SequenceIndex header lookup (sequence_index.rs:10-13); pointer valid until awry_index_free */
+int awry_index_sequence_header(const awry_index *index, uint64_t seq_idx, const char **header,
+                               uint64_t *header_len);
+
+/* ------------------------------------------------------------------ batched search (host buffers) */
+
+/* FmIndex::parallel_count (fm_index.rs:455-460); count_string (:499-501) is a batch of one.
+ * Queries are ASCII, concatenated in qbytes; query i = qbytes[qoff[i] .. qoff[i+1]).
+ * counts (caller-owned, nq entries) are written in input order. */
+int awry_count_batch(const awry_index *index, const uint8_t *qbytes, const uint64_t *qoff,
+                     uint64_t nq, uint64_t *counts);
+
+/* Same search, returning the final SearchRange per query (get_search_range_for_string,
+ * fm_index.rs:402-438).  Empty ranges are reported as SearchRange::zero() = (1,0). */
+int awry_search_batch(const awry_index *index, const uint8_t *qbytes, const uint64_t *qoff,
+                      uint64_t nq, awry_range *ranges);
+
+enum {
+  AWRY_LOCATE_BWT_ORDER = 0, /* per-query hits in BWT-row order, exactly the reference's
+                                push order (fm_index.rs:521) */
+  AWRY_LOCATE_SORTED = 1     /* per-query hits sorted ascending by (seq_idx, local_pos) */
+};
+
+/* FmIndex::parallel_locate (fm_index.rs:479-487); locate_string (:516-544) is a batch of one.
+ * hit_off (caller-owned, nq+1 entries) is the CSR offset array; *hits is library-owned
+ * (release with awry_hits_free) and holds *n_hits entries. */
+int awry_locate_batch(const awry_index *index, const uint8_t *qbytes, const uint64_t *qoff,
+                      uint64_t nq, uint32_t flags, uint64_t *hit_off, awry_hit **hits,
+                      uint64_t *n_hits);
+void awry_hits_free(awry_hit *hits);
+
+/* ------------------------------------------------------------------ single steps (public in the reference) */
+
+/* SearchRange::new / FmIndex::initial_search_range (search.rs:43-48, fm_index.rs:383) */
+int awry_initial_range(const awry_index *index, uint8_t ascii_symbol, awry_range *out);
+/* FmIndex::update_range_with_symbol (fm_index.rs:559-582); one-thread kernel launch */
+int awry_update_range(const awry_index *index, awry_range range, uint8_t ascii_symbol,
+                      awry_range *out);
+/* FmIndex::backstep (fm_index.rs:585-593); one-thread kernel launch */
+int awry_backstep(const awry_index *index, uint64_t bwt_row, uint64_t *out);
+
+/* ------------------------------------------------------------------ device-resident entry points
+ * Same kernels as the *_batch calls, for callers that already hold the queries in HBM
+ * (bench.py's kernel-only figure).  Pointers are device pointers on replica `replica`'s
+ * device; `cuda_stream` is a cudaStream_t (NULL = default stream).  Asynchronous. */
+int awry_count_device(const awry_index *index, int replica, const uint8_t *d_qbytes,
+                      const uint64_t *d_qoff, uint64_t nq, uint64_t *d_counts, void *cuda_stream);
+/* two-pass locate on device-resident queries; results stay on the device.  Synchronises once
+ * (the hit total sizes the output).  d_hit_off: nq+1 u64.  *d_hits is a device allocation
+ * released with awry_device_free. */
+int awry_locate_device(const awry_index *index, int replica, const uint8_t *d_qbytes,
+                       const uint64_t *d_qoff, uint64_t nq, uint32_t flags, uint64_t *d_hit_off,
+                       awry_hit **d_hits, uint64_t *n_hits, void *cuda_stream);
+int awry_device_free(const awry_index *index, int replica, void *d_ptr);
+/* The *_device calls are asynchronous, so an empty / sentinel-carrying query cannot be reported
+ * by them; it is latched per replica.  This synchronises `cuda_stream`, returns
+ * AWRY_ERR_INVALID_QUERY if any device batch since the last check held such a query (its result
+ * slot is then 0 / SearchRange::zero()), and clears the latch. */
+int awry_device_check(const awry_index *index, int replica, void *cuda_stream);
+
+/* ------------------------------------------------------------------ instrumentation */
+
+/* Per-kernel accounting kept by the library (CUDA events on the launching stream when
+ * profiling is enabled): launches = number of this library's kernels launched since the last
+ * reset; *_ms = summed device time of the dominant kernels. */
+typedef struct awry_profile {
+  uint64_t launches;
+  uint64_t search_launches;
+  double search_ms; /* backward-search kernel */
+  uint64_t walk_launches;
+  double walk_ms;   /* locate LF-walk kernel */
+  uint64_t pack_launches;
+  double pack_ms;   /* ASCII -> packed-symbol prepass */
+  uint64_t h2d_bytes;
+  uint64_t d2h_bytes;
+} awry_profile;
+int awry_profile_enable(int on);       /* event timing costs a sync per call: off by default */
+int awry_profile_reset(void);
+int awry_profile_get(awry_profile *out);
+
+/* Random-gather roofline microbenchmark: n_reads independent, uniformly random,
+ * `granule`-byte aligned reads of `granule` bytes (32, 64 or 128) over a buffer of
+ * `footprint_bytes`, `lanes` consecutive lanes cooperating on one granule (1, 2, 4 or 8).
+ * Returns achieved reads/s and GB/s. */
+int awry_bench_random_gather(int device, uint64_t footprint_bytes, uint32_t granule, uint32_t lanes,
+                             uint64_t n_reads, int iters, double *reads_per_s, double *gb_per_s);
+
+/* Tuning knob for experiments: selects the search-kernel variant (lanes per query 1/2/4,
+ * threads per block, blocks per SM).  0 keeps the default. */
+int awry_set_search_variant(int lanes_per_query, int threads_per_block, int blocks_per_sm);
+
+const char *awry_last_error(void);
+const char *awry_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AWRY_B200_H */

@@ -1,0 +1,254 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs.  Bar: bit-exact counts, ranges and locate lists (integer work)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import (brute_positions, device_from_parts, mixed_queries, oracle_from_parts)
+
+pytestmark = pytest.mark.gpu
+
+APPENDIX_A = {
+    "A": ((1, 7), [4, 11, 15, 6, 13, 1, 8]),
+    "TTA": ((18, 19), [2, 9]),
+    "GATTACA": ((11, 12), [0, 7]),
+    "ACA": ((1, 2), [4, 11]),
+    "N": ((14, 14), [14]),
+    "CAN": ((9, 9), [12]),
+    "ACGT": ((3, 3), [15]),
+    "GG": ((1, 0), []),
+    "TACAGATTACANACGT": ((16, 16), [3]),
+}
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "appendix_a.awry")
+
+
+@pytest.fixture(scope="module")
+def dna(fx):
+    text = fx.gen_text(0, 200_000, 1)
+    return fx.build_parts(text, 0, ratio=8, kmer_len=8)
+
+
+@pytest.fixture(scope="module")
+def dna_dev(dna):
+    ix = device_from_parts(dna)
+    yield ix
+    ix.close()
+
+
+@pytest.fixture(scope="module")
+def dna_or(po, dna):
+    return oracle_from_parts(po, dna)
+
+
+def edge_queries(text):
+    t = bytes(text[:400])
+    qs = [t[5:5 + n] for n in range(1, 14)]                 # shorter than / equal to / just above k
+    qs += [t[40:72].lower(), t[100:130].replace(b"T", b"U"), b"acgtn", b"N", b"NN", b"ACGTNACGT",
+           t[10:30] + b"N" + t[31:50], b"R", b"x", t[0:300], bytes(text[-40:]), bytes(text[-1:]),
+           b"A" * 64, b"ACGT" * 40, bytes(text) + b"A", b"TTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTG"]
+    return qs
+
+
+def test_golden_file_appendix_a():
+    from awry_b200 import FmIndex, SearchRange
+    with FmIndex.load(GOLDEN) as ix:
+        assert ix.bwt_len() == 20 and ix.suffix_array_compression_ratio() == 4
+        assert ix.prefix_sums() == [0, 1, 8, 11, 14, 15, 20]
+        assert ix.kmer_len() == 2 and ix.sequence_header(0) == "synthetic"
+        for q, (rng, locs) in APPENDIX_A.items():
+            assert ix.get_search_range_for_string(q) == SearchRange(*rng), q
+            assert ix.count_string(q) == len(locs), q
+            assert [h.local_position for h in ix.locate_string(q)] == locs, q
+            assert all(h.sequence_idx == 0 for h in ix.locate_string(q))
+
+
+@pytest.mark.parametrize("lanes", [0, 1, 2, 4, -1])
+def test_count_parity_cfg1_style(fx, dna, dna_dev, dna_or, lanes):
+    """parallel_count of 10k random 32-bp queries (half present, half random) + edge cases."""
+    from awry_b200 import fm_index as f
+    qb, qo = mixed_queries(fx, dna.text, 10_000, 32, seed=2)
+    f.set_search_variant(lanes)
+    try:
+        got = dna_dev.count_packed(qb, qo)
+        want, _ = dna_or.count_batch(qb, qo)
+        assert np.array_equal(got, want)
+        assert int((want > 0).sum()) >= 5000
+        qs = edge_queries(dna.text)
+        eb, eo = f.pack_queries(qs)
+        got = dna_dev.count_packed(eb, eo)
+        want, _ = dna_or.count_batch(eb, eo)
+        assert np.array_equal(got, want), [(q[:20], int(a), int(b)) for q, a, b in zip(qs, got, want) if a != b]
+        rg = dna_dev.search_packed(eb, eo)
+        for q, r in zip(qs, rg):
+            sp, ep = dna_or.search_range(q)
+            assert (int(r[0]), int(r[1])) == ((sp, ep) if sp <= ep else (1, 0)), q
+    finally:
+        f.set_search_variant(0)
+
+
+def test_counts_match_brute_force(fx, dna, dna_dev):
+    text = bytes(dna.text)
+    qb, qo, _ = fx.gen_substring_queries(dna.text, 300, 11, seed=5)
+    got = dna_dev.count_packed(qb, qo)
+    for i in range(300):
+        q = bytes(qb[11 * i:11 * i + 11])
+        assert int(got[i]) == len(brute_positions(text, q))
+
+
+@pytest.mark.parametrize("ratio", [1, 4, 5, 8, 32])
+def test_locate_parity(fx, po, ratio):
+    text = fx.gen_text(0, 60_000, 11 + ratio)
+    parts = fx.build_parts(text, 0, ratio=ratio, kmer_len=6)
+    orc = oracle_from_parts(po, parts)
+    qb1, qo1, _ = fx.gen_substring_queries(text, 2000, 20, seed=3)   # mostly unique
+    qb2, qo2, _ = fx.gen_substring_queries(text, 500, 5, seed=4)     # ~60 hits each
+    from awry_b200 import fm_index as f
+    qs = [bytes(qb1[20 * i:20 * i + 20]) for i in range(2000)] + [bytes(qb2[5 * i:5 * i + 5]) for i in range(500)]
+    qs += [b"A", b"ACGTTTTTTTTGGGGGGGGGGGGGCCCCCCCCCCC", bytes(text[:50]), bytes(text[-30:])]
+    qb, qo = f.pack_queries(qs)
+    with device_from_parts(parts) as ix:
+        off, hits = ix.locate_packed(qb, qo)
+        woff, whits, _ = orc.locate_batch(qb, qo)
+        assert np.array_equal(off, woff)
+        assert np.array_equal(hits, whits)          # BWT-row order == the reference's push order
+        soff, shits = ix.locate_packed(qb, qo, sorted_hits=True)
+        woff2, whits2, _ = orc.locate_batch(qb, qo, sorted_hits=True)
+        assert np.array_equal(soff, woff2) and np.array_equal(shits, whits2)
+    # oracle-of-the-oracle on a few
+    t = bytes(text)
+    for i in (0, 1, 2000, 2001, 2500):
+        lo, hi = int(woff[i]), int(woff[i + 1])
+        assert sorted(int(x) for x in whits[lo:hi, 1]) == brute_positions(t, qs[i])
+
+
+def test_amino_count_and_locate(fx, po):
+    text = fx.gen_text(1, 50_000, 6)
+    parts = fx.build_parts(text, 1, ratio=8, kmer_len=3)
+    orc = oracle_from_parts(po, parts)
+    from awry_b200 import fm_index as f
+    qb, qo = mixed_queries(fx, text, 4000, 4, seed=7, alphabet=1)
+    qs = [bytes(qb[4 * i:4 * i + 4]) for i in range(4000)]
+    qb3, qo3, _ = fx.gen_substring_queries(text, 1000, 12, seed=8)
+    qs += [bytes(qb3[12 * i:12 * i + 12]) for i in range(1000)]
+    qs += [b"A", b"AC", b"X", b"acd", b"BZJ", b"W" * 9, bytes(text[:300]), bytes(text[-20:]), b"M*K", b"ACDEFGHIKLMNPQRSTVWY"]
+    qb, qo = f.pack_queries(qs)
+    with device_from_parts(parts) as ix:
+        got = ix.count_packed(qb, qo)
+        want, _ = orc.count_batch(qb, qo)
+        assert np.array_equal(got, want)
+        off, hits = ix.locate_packed(qb, qo)
+        woff, whits, _ = orc.locate_batch(qb, qo)
+        assert np.array_equal(off, woff) and np.array_equal(hits, whits)
+    t = bytes(text)
+    for i in (0, 5, 4000, 4500):
+        assert int(want[i]) == len(brute_positions(t, qs[i]))
+
+
+def test_multi_record_and_n_text(fx, po):
+    """multi-record input: delimiters are literal N symbols (fm_index.rs:148-153); locate maps
+    to (record, offset) with the intended semantics (reference recursion: SURVEY Q4)."""
+    recs = [bytes(fx.gen_text(0, n, 20 + i)) for i, n in enumerate([700, 33, 1, 1500, 256, 90])]
+    recs[3] = recs[3][:100] + b"NNNNRYK" + recs[3][107:]
+    text, starts = fx.concat_records(recs, 0)
+    parts = fx.build_parts(text, 0, ratio=3, kmer_len=4, seq_starts=starts,
+                           headers=[f"rec{i}" for i in range(len(recs))])
+    orc = oracle_from_parts(po, parts)
+    from awry_b200 import fm_index as f
+    qs = []
+    for r in recs:
+        qs += [r[i:] for i in range(0, len(r), 37)] + [r[:5], r[-3:]]
+    qs += [b"N", b"NN", b"NNNN", b"AN", b"NA", b"ACGN", b"NNNNN"]
+    qb, qo = f.pack_queries(qs)
+    with device_from_parts(parts) as ix:
+        assert ix.sequence_header(3) == "rec3"
+        got = ix.count_packed(qb, qo)
+        want, _ = orc.count_batch(qb, qo)
+        assert np.array_equal(got, want)
+        assert all(int(c) > 0 for c in got[:len(qs) - 7])     # fm_index.rs:779-790 property
+        off, hits = ix.locate_packed(qb, qo)
+        woff, whits, _ = orc.locate_batch(qb, qo)
+        assert np.array_equal(off, woff) and np.array_equal(hits, whits)
+        assert int(hits[:, 0].max()) == len(recs) - 1
+
+
+def test_invalid_queries_are_errors(dna_dev):
+    from awry_b200 import AwryError, fm_index as f
+    for bad in ([b"ACGT", b""], [b"AC$T"], [b"#"], [b"ACGT", b"GGA$"]):
+        qb, qo = f.pack_queries(bad)
+        with pytest.raises(AwryError) as e:
+            dna_dev.count_packed(qb, qo)
+        assert e.value.code == -5
+        with pytest.raises(AwryError):
+            dna_dev.locate_packed(qb, qo)
+    assert dna_dev.count_string("ACGT") >= 0   # index still usable afterwards
+
+
+def test_single_step_api(dna, dna_dev, dna_or):
+    from awry_b200 import SearchRange
+    rng = dna_dev.initial_search_range("G")
+    assert tuple(rng) == dna_or.initial_range(dna_or.sym("G"))
+    for ch in "ACGTNacgu":
+        nxt = dna_dev.update_range_with_symbol(rng, ch)
+        assert tuple(nxt) == dna_or.update_range(rng.start_ptr, rng.end_ptr, dna_or.sym(ch)), ch
+    r = np.random.default_rng(0)
+    for row in [0, 1, 127, 128, 255, 256, dna.bwt_len - 1] + [int(x) for x in r.integers(0, dna.bwt_len, 40)]:
+        assert dna_dev.backstep(row) == dna_or.backstep(row), row
+    assert dna_dev.initial_search_range("$") == SearchRange(0, 0)
+
+
+def test_file_load_equals_parts(tmp_path, fx, dna, dna_dev, dna_or, po):
+    from awry_b200 import FmIndex
+    path = str(tmp_path / "t.awry")
+    dna.write(path)
+    qb, qo = mixed_queries(fx, dna.text, 3000, 24, seed=12)
+    with FmIndex.load(path) as ix:
+        assert ix.prefix_sums() == [int(x) for x in dna.prefix_sums]
+        assert ix.bwt_len() == dna.bwt_len and ix.kmer_len() == 8
+        assert np.array_equal(ix.count_packed(qb, qo), dna_dev.count_packed(qb, qo))
+        a = ix.locate_packed(qb, qo)
+        b = dna_dev.locate_packed(qb, qo)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    orc = po.OracleIndex.load(path)
+    assert np.array_equal(orc.count_batch(qb, qo)[0], dna_dev.count_packed(qb, qo))
+
+
+def test_device_resident_entry_points(fx, dna, dna_dev, dna_or):
+    import torch
+    qb, qo = mixed_queries(fx, dna.text, 20_000, 40, seed=14)
+    d_qb = torch.from_numpy(qb).cuda()
+    d_qo = torch.from_numpy(qo.astype(np.int64)).cuda()
+    d_counts = torch.zeros(20_000, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    dna_dev.count_device(d_qb.data_ptr(), d_qo.data_ptr(), 20_000, d_counts.data_ptr(), st)
+    dna_dev.device_check(st)
+    want, _ = dna_or.count_batch(qb, qo)
+    assert np.array_equal(d_counts.cpu().numpy().astype(np.uint64), want)
+    d_off = torch.zeros(20_001, dtype=torch.int64, device="cuda")
+    ptr, n = dna_dev.locate_device(d_qb.data_ptr(), d_qo.data_ptr(), 20_000, d_off.data_ptr(), stream=st)
+    woff, whits, _ = dna_or.locate_batch(qb, qo)
+    assert n == len(whits)
+    assert np.array_equal(d_off.cpu().numpy().astype(np.uint64), woff)
+    dna_dev.device_free(ptr)
+
+
+def test_ragged_lengths_and_order_preserved(fx, dna, dna_dev, dna_or):
+    from awry_b200 import fm_index as f
+    r = np.random.default_rng(3)
+    t = bytes(dna.text)
+    qs = []
+    for _ in range(5000):
+        n = int(r.integers(1, 200))
+        p = int(r.integers(0, len(t) - n))
+        q = bytearray(t[p:p + n])
+        if r.random() < 0.3:
+            q[int(r.integers(0, n))] = ord("ACGTN"[int(r.integers(0, 5))])
+        qs.append(bytes(q))
+    qb, qo = f.pack_queries(qs)
+    got = dna_dev.count_packed(qb, qo)
+    want, _ = dna_or.count_batch(qb, qo)
+    assert np.array_equal(got, want)
+    assert dna_dev.parallel_count(qs[:50]) == [int(x) for x in want[:50]]
+    loc = dna_dev.parallel_locate(qs[:50])
+    for i in range(50):
+        assert [tuple(h) for h in loc[i]] == dna_or.locate_string(qs[i])
