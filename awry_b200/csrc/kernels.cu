@@ -718,11 +718,14 @@ __global__ void __launch_bounds__(256) gather_kernel(const char* __restrict__ bu
   const uint32_t lane = threadIdx.x & 31, sub = lane % LANES;
   const uint64_t group = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) / LANES;
   uint32_t acc = 0;
+  // cheap address stream (the probe must not be ALU-bound): 64-bit LCG per group, high product
+  uint64_t x = mix64(seed ^ (group * 0x100000001B3ull));
   for (uint64_t it = 0; it < reads_per_group; it += UNROLL) {
     uint32_t v[UNROLL][NV * (BYTES >= 32 ? 8 : BYTES / 4)];
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) {
-      uint64_t g = mix64(seed ^ (group * 0x100000001B3ull + it + u)) % n_granules;
+      x = x * 6364136223846793005ull + 1442695040888963407ull;
+      uint64_t g = __umul64hi(x, n_granules);
       const char* p = buf + g * GRANULE + sub * BYTES;
       if (BYTES >= 32) {
 #pragma unroll

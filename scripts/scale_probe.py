@@ -1,0 +1,106 @@
+"""Bench-scale probe: build the synthetic index on the GPU, time the search-kernel variants on
+device-resident reads, check a sample against the CPU oracle."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from awry_b200 import FmIndex, fm_index as f  # noqa: E402
+from fixtures import pyfixture_gpu as fxg  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=3_100_000_000)
+    ap.add_argument("--alphabet", type=int, default=0)
+    ap.add_argument("--nq", type=int, default=10_000_000)
+    ap.add_argument("--qlen", type=int, default=150)
+    ap.add_argument("--k", type=int, default=13)
+    ap.add_argument("--ratio", type=int, default=8)
+    ap.add_argument("--variants", default="4,2,1")
+    ap.add_argument("--bps", default="0")
+    ap.add_argument("--check", type=int, default=20000)
+    ap.add_argument("--locate-nq", type=int, default=1_000_000)
+    ap.add_argument("--locate-qlen", type=int, default=50)
+    a = ap.parse_args()
+    t0 = time.time()
+    parts, phases = fxg.build_parts(a.alphabet, a.n, 3, ratio=a.ratio, kmer_len=a.k)
+    print("fixture build phases (s):", json.dumps({k: round(v, 2) for k, v in phases.items()}), flush=True)
+    t1 = time.time()
+    ix = FmIndex.from_parts(parts.alphabet, parts.ratio, parts.bwt_len, parts.kmer_len, parts.blocks,
+                            parts.prefix_sums, parts.sa_words)
+    print(f"from_parts {time.time()-t1:.2f}s device bytes {ix.device_bytes()}", flush=True)
+    d_q = torch.empty(a.nq * a.qlen, dtype=torch.uint8, device="cuda")
+    fxg.gen_queries_device(a.alphabet, a.n, 3, a.nq, a.qlen, 4, d_q.data_ptr())
+    d_off = torch.arange(0, a.nq + 1, dtype=torch.int64, device="cuda") * a.qlen
+    d_cnt = torch.zeros(a.nq, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    f.profile_enable(True)
+    results = []
+    for lanes in [int(x) for x in a.variants.split(",")]:
+        for bps in [int(x) for x in a.bps.split(",")]:
+            f.set_search_variant(lanes, 0, bps)
+            for it in range(3):
+                f.profile_reset()
+                ix.count_device(d_q.data_ptr(), d_off.data_ptr(), a.nq, d_cnt.data_ptr(), st)
+                torch.cuda.synchronize()
+                p = f.profile_get()
+            steps = a.nq * (a.qlen - a.k)
+            print(f"lanes={lanes} bps={bps}: search {p['search_ms']:.2f} ms pack {p['pack_ms']:.2f} ms  "
+                  f"{a.nq/p['search_ms']/1e3:.1f} M reads/s  {steps/p['search_ms']/1e6:.2f} G LF-steps/s  "
+                  f"alg {steps*104/p['search_ms']/1e6:.0f} GB/s", flush=True)
+            results.append({"lanes": lanes, "bps": bps, **p})
+    f.set_search_variant(0)
+    ix.device_check(st)
+    cnt = d_cnt.cpu().numpy()
+    print("count histogram:", np.unique(cnt, return_counts=True)[0][:5], flush=True)
+    if a.check:
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from oracle import pyoracle as po
+        orc = po.OracleIndex.from_parts(parts.alphabet, parts.ratio, parts.bwt_len, parts.kmer_len,
+                                        parts.blocks, parts.prefix_sums, parts.sa_words)
+        qb = d_q[: a.check * a.qlen].cpu().numpy()
+        qo = np.arange(a.check + 1, dtype=np.uint64) * np.uint64(a.qlen)
+        t2 = time.time()
+        want, st_or = orc.count_batch(qb, qo)
+        dt = time.time() - t2
+        print(f"oracle: {a.check} reads in {dt:.2f}s on {os.cpu_count()} threads = {a.check/dt/1e3:.1f} k reads/s; "
+              f"parity {'OK' if np.array_equal(want, cnt[:a.check].astype(np.uint64)) else 'MISMATCH'}; stats {st_or}", flush=True)
+        # locate
+        nq2, ql2 = a.locate_nq, a.locate_qlen
+        d_q2 = torch.empty(nq2 * ql2, dtype=torch.uint8, device="cuda")
+        fxg.gen_queries_device(a.alphabet, a.n, 3, nq2, ql2, 5, d_q2.data_ptr())
+        d_off2 = torch.arange(0, nq2 + 1, dtype=torch.int64, device="cuda") * ql2
+        d_hoff = torch.zeros(nq2 + 1, dtype=torch.int64, device="cuda")
+        for it in range(3):
+            f.profile_reset()
+            ptr, nh = ix.locate_device(d_q2.data_ptr(), d_off2.data_ptr(), nq2, d_hoff.data_ptr(), stream=st)
+            p = f.profile_get()
+            if it < 2:
+                ix.device_free(ptr)
+        print(f"locate: {nh} hits; search {p['search_ms']:.2f} ms walk {p['walk_ms']:.2f} ms "
+              f"{nh/p['walk_ms']/1e3:.1f} M hits/s", flush=True)
+        ncheck = min(a.check, nq2)
+        qb2 = d_q2[: ncheck * ql2].cpu().numpy()
+        qo2 = np.arange(ncheck + 1, dtype=np.uint64) * np.uint64(ql2)
+        woff, whits, st2 = orc.locate_batch(qb2, qo2)
+        hoff = d_hoff.cpu().numpy().astype(np.uint64)
+        nh_check = int(hoff[ncheck])
+        import ctypes as C
+        buf = torch.empty(nh_check * 2, dtype=torch.int64, device="cuda")
+        C.cdll.LoadLibrary("libcudart.so").cudaMemcpy(C.c_void_p(buf.data_ptr()), C.c_void_p(ptr), C.c_size_t(nh_check * 16), 3)
+        got = buf.cpu().numpy().astype(np.uint64).reshape(-1, 2)
+        ok = np.array_equal(hoff[: ncheck + 1], woff) and np.array_equal(got, whits)
+        print(f"locate parity on {ncheck} queries: {'OK' if ok else 'MISMATCH'}; oracle stats {st2}", flush=True)
+        ix.device_free(ptr)
+    print(f"total {time.time()-t0:.1f}s")
+
+
+if __name__ == "__main__":
+    main()
