@@ -218,9 +218,11 @@ struct Replica {
   uint4* d_blocks = nullptr;
   uint64_t* d_sa = nullptr;
   uint2* d_table = nullptr;
+  uint4* d_pair = nullptr;
   uint64_t* d_seq_starts = nullptr;
   unsigned long long* d_async_flag = nullptr;  // first bad query seen by *_device calls
-  size_t bytes_blocks = 0, bytes_sa = 0, bytes_table = 0;
+  size_t bytes_blocks = 0, bytes_sa = 0, bytes_table = 0, bytes_pair = 0;
+  uint32_t c2[16] = {0};
   IndexView view{};
   std::mutex ws_mu;
   std::vector<Workspace*> free_ws;
@@ -311,6 +313,8 @@ void set_view_constants(awry_index* ix, Replica& r) {
   v.sa_words = r.d_sa;
   v.table = r.d_table;
   v.seq_starts = r.d_seq_starts;
+  v.pair_blocks = r.d_pair;
+  for (int i = 0; i < 16; i++) v.c2[i] = r.c2[i];
   v.bwt_len = uint32_t(ix->bwt_len);
   v.sa_ratio = uint32_t(ix->sa_ratio);
   v.sa_pow2 = (ix->sa_ratio & (ix->sa_ratio - 1)) == 0 ? 1u : 0u;
@@ -425,6 +429,18 @@ void build_replica0(awry_index* ix, Replica& r, Source& src_blocks_then_rest, bo
   CU(cudaStreamDestroy(st));
 }
 
+// The *_device entry points take their scratch from the stream-ordered pool; without a release
+// threshold the pool hands the memory back to the driver at every synchronisation and each call
+// would re-map ~1 GB.
+void keep_pool_memory(int device) {
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  cudaGetLastError();
+}
+
 void finish_replica0(awry_index* ix, Replica& r) {
   DeviceGuard dg(r.device);
   if (ix->seq_starts.empty()) ix->seq_starts.push_back(0);
@@ -432,6 +448,7 @@ void finish_replica0(awry_index* ix, Replica& r) {
   CU(cudaMemcpy(r.d_seq_starts, ix->seq_starts.data(), ix->seq_starts.size() * 8, cudaMemcpyHostToDevice));
   CU(cudaMalloc(reinterpret_cast<void**>(&r.d_async_flag), 8));
   CU(cudaMemset(r.d_async_flag, 0xff, 8));
+  keep_pool_memory(r.device);
 
   // device seed table: k_dev = min(k_file, cap); the table only accelerates, results are those
   // of the plain backward search either way
@@ -453,6 +470,20 @@ void finish_replica0(awry_index* ix, Replica& r) {
     CU(launch_build_table(v, r.d_table, k, nullptr));
     CU(cudaDeviceSynchronize());
   }
+  // nucleotide pair index: two query symbols per block access (AWRY_B200_PAIR_INDEX=0 disables)
+  const char* env = getenv("AWRY_B200_PAIR_INDEX");
+  bool want_pair = ix->alphabet == AWRY_NUCLEOTIDE && !(env && env[0] == '0');
+  if (want_pair) {
+    size_t bytes = size_t(pair_block_count(ix->bwt_len)) * 128;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    if (bytes + bytes / 2 + (1u << 28) < free_b) {
+      CU(cudaMalloc(reinterpret_cast<void**>(&r.d_pair), bytes + 256));
+      CU(build_pair_index(r.view, r.d_pair, r.c2, nullptr));
+      r.bytes_pair = bytes;
+      r.view.pair_blocks = r.d_pair;
+      for (int i = 0; i < 16; i++) r.view.c2[i] = r.c2[i];
+    }
+  }
 }
 
 void clone_replica(awry_index* ix, const Replica& src, Replica& dst) {
@@ -467,6 +498,7 @@ void clone_replica(awry_index* ix, const Replica& src, Replica& dst) {
   CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_seq_starts), ix->seq_starts.size() * 8));
   CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_async_flag), 8));
   CU(cudaMemset(dst.d_async_flag, 0xff, 8));
+  keep_pool_memory(dst.device);
   // fan-out over NVLink instead of N PCIe uploads
   CU(cudaMemcpyPeer(dst.d_blocks, dst.device, src.d_blocks, src.device, src.bytes_blocks + 256));
   CU(cudaMemcpyPeer(dst.d_sa, dst.device, src.d_sa, src.device, src.bytes_sa));
@@ -474,6 +506,12 @@ void clone_replica(awry_index* ix, const Replica& src, Replica& dst) {
   if (src.bytes_table) {
     CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_table), src.bytes_table));
     CU(cudaMemcpyPeer(dst.d_table, dst.device, src.d_table, src.device, src.bytes_table));
+  }
+  if (src.bytes_pair) {
+    dst.bytes_pair = src.bytes_pair;
+    CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_pair), src.bytes_pair + 256));
+    CU(cudaMemcpyPeer(dst.d_pair, dst.device, src.d_pair, src.device, src.bytes_pair));
+    memcpy(dst.c2, src.c2, sizeof dst.c2);
   }
   uint32_t dollar = src.view.dollar_row;
   set_view_constants(ix, dst);
@@ -955,6 +993,7 @@ void awry_index_free(awry_index* ix) {
     cudaFree(r.d_blocks);
     cudaFree(r.d_sa);
     cudaFree(r.d_table);
+    cudaFree(r.d_pair);
     cudaFree(r.d_seq_starts);
     cudaFree(r.d_async_flag);
   }
@@ -978,6 +1017,7 @@ int awry_index_info(const awry_index* ix, awry_info* info) {
     info->device_bytes_blocks = ix->reps[0]->bytes_blocks;
     info->device_bytes_sa = ix->reps[0]->bytes_sa;
     info->device_bytes_table = ix->reps[0]->bytes_table;
+    info->device_bytes_pair = ix->reps[0]->bytes_pair;
     for (size_t i = 0; i < ix->reps.size() && i < 16; i++) info->devices[i] = ix->reps[i]->device;
   });
 }
@@ -1291,7 +1331,8 @@ int awry_bench_random_gather(int device, uint64_t footprint_bytes, uint32_t gran
 }
 
 int awry_set_search_variant(int lanes_per_query, int threads_per_block, int blocks_per_sm) {
-  if (lanes_per_query != 0 && lanes_per_query != -1 && lanes_per_query != 1 && lanes_per_query != 2 && lanes_per_query != 4)
+  if (lanes_per_query != 0 && lanes_per_query != -1 && lanes_per_query != 1 && lanes_per_query != 2 &&
+      lanes_per_query != 4 && lanes_per_query != 8)
     return AWRY_ERR_INVALID_ARG;
   g_variant.lanes = lanes_per_query;
   g_variant.tpb = threads_per_block;

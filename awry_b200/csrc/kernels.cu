@@ -196,6 +196,110 @@ cudaError_t launch_build_table(const IndexView& ix, uint2* d_table, uint32_t k, 
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ nucleotide pair index
+
+uint64_t pair_block_count(uint64_t bwt_len) { return (bwt_len + PAIR_ROWS_PER_BLOCK - 1) / PAIR_ROWS_PER_BLOCK; }
+
+// One CTA (3 warps) per 96-row pair block.  Row code = 4*BWT[row] + BWT[LF(row)], or "special".
+__global__ void __launch_bounds__(96)
+    pair_planes_kernel(IndexView ix, uint4* __restrict__ pair_blocks, uint32_t* __restrict__ hist /* [16][n] */,
+                       uint64_t n_pblocks) {
+  __shared__ uint32_t cnt[16];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 16) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t blk = blockIdx.x;
+  const uint64_t row64 = blk * PAIR_ROWS_PER_BLOCK + threadIdx.x;
+  uint32_t code = 16;  // special (also the padding rows past bwt_len)
+  if (row64 < ix.bwt_len) {
+    uint32_t row = uint32_t(row64);
+    uint32_t b1 = row >> 7, l1 = row & 127;
+    DnaBlockRegs blk1 = dna_load_block(ix, b1);
+    uint32_t a = dna_code_at(blk1, l1);
+    if (a < 4) {
+      uint32_t j = ix.c_lo[a] + dna_occ_in_block(ix, blk1, b1, l1, a) - 1;  // LF(row)
+      uint32_t lj = j & 127;
+      uint4 ch = ldg128(ix.blocks + size_t(j >> 7) * DNA_BLOCK_UINT4 + (lj >> 5));
+      uint32_t t = lj & 31;
+      uint32_t b = ((ch.x >> t) & 1u) | (((ch.y >> t) & 1u) << 1) | (((ch.z >> t) & 1u) << 2);
+      if (b < 4) code = 4 * a + b;
+    }
+  }
+  uint32_t* words = reinterpret_cast<uint32_t*>(pair_blocks + blk * PAIR_BLOCK_UINT4);
+#pragma unroll
+  for (int p = 0; p < 5; p++) {
+    uint32_t w = __ballot_sync(0xffffffffu, (code >> p) & 1u);
+    if (lane == 0) words[8 * warp + p] = w;
+  }
+  for (uint32_t p = 0; p < 16; p++) {
+    uint32_t m = __ballot_sync(0xffffffffu, code == p);
+    if (lane == 0 && m) atomicAdd(&cnt[p], uint32_t(__popc(m)));
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) hist[uint64_t(threadIdx.x) * n_pblocks + blk] = cnt[threadIdx.x];
+}
+
+// slot of pair count p inside a pair block, as a 32-bit word index
+__host__ __device__ __forceinline__ uint32_t pair_count_word(uint32_t p) {
+  return p < 9 ? 8 * (p / 3) + 5 + (p % 3) : 24 + (p - 9);
+}
+
+__global__ void pair_counts_kernel(const uint32_t* __restrict__ ms /* [16][n] exclusive sums */,
+                                   uint64_t n_pblocks, uint4* __restrict__ pair_blocks) {
+  uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (t >= n_pblocks * 16) return;
+  uint64_t blk = t >> 4;
+  uint32_t p = uint32_t(t) & 15;
+  uint32_t* words = reinterpret_cast<uint32_t*>(pair_blocks + blk * PAIR_BLOCK_UINT4);
+  words[pair_count_word(p)] = ms[uint64_t(p) * n_pblocks + blk];
+  if (p == 15) words[31] = 0;
+}
+
+// C2[4a+b] = C[b] + Occ(b, C[a]-1)
+__global__ void pair_c2_kernel(IndexView ix, uint32_t* __restrict__ out) {
+  uint32_t p = threadIdx.x;
+  if (p >= 16) return;
+  uint32_t a = p >> 2, b = p & 3;
+  uint32_t pos = ix.c_lo[a] - 1;  // C[a] >= 1: row 0 is the '$'-suffix
+  DnaBlockRegs blk = dna_load_block(ix, pos >> 7);
+  out[p] = ix.c_lo[b] + dna_occ_in_block(ix, blk, pos >> 7, pos & 127, b);
+}
+
+cudaError_t build_pair_index(const IndexView& ix, uint4* d_pair_blocks, uint32_t* c2_host, cudaStream_t s) {
+  const uint64_t n = pair_block_count(ix.bwt_len);
+  uint32_t* d_hist = nullptr;
+  cudaError_t e = cudaMalloc(&d_hist, n * 16 * sizeof(uint32_t) + 64);
+  if (e != cudaSuccess) return e;
+  void* d_temp = nullptr;
+  auto cleanup = [&](cudaError_t r) {
+    cudaFree(d_hist);
+    cudaFree(d_temp);
+    return r;
+  };
+  pair_planes_kernel<<<unsigned(n), 96, 0, s>>>(ix, d_pair_blocks, d_hist, n);
+  COUNT_LAUNCH();
+  if ((e = cudaGetLastError()) != cudaSuccess) return cleanup(e);
+  size_t tb = 0;
+  if ((e = cub::DeviceScan::ExclusiveSum(nullptr, tb, d_hist, d_hist, (long long)n, s)) != cudaSuccess) return cleanup(e);
+  if ((e = cudaMalloc(&d_temp, tb + 16)) != cudaSuccess) return cleanup(e);
+  for (int p = 0; p < 16; p++) {
+    e = cub::DeviceScan::ExclusiveSum(d_temp, tb, d_hist + uint64_t(p) * n, d_hist + uint64_t(p) * n, (long long)n, s);
+    COUNT_LAUNCH();
+    if (e != cudaSuccess) return cleanup(e);
+  }
+  uint64_t threads = n * 16;
+  pair_counts_kernel<<<unsigned((threads + 255) / 256), 256, 0, s>>>(d_hist, n, d_pair_blocks);
+  COUNT_LAUNCH();
+  if ((e = cudaGetLastError()) != cudaSuccess) return cleanup(e);
+  uint32_t* d_c2 = reinterpret_cast<uint32_t*>(d_hist);  // reuse after the counts are written
+  if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return cleanup(e);
+  pair_c2_kernel<<<1, 32, 0, s>>>(ix, d_c2);
+  COUNT_LAUNCH();
+  if ((e = cudaMemcpyAsync(c2_host, d_c2, 64, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return cleanup(e);
+  e = cudaStreamSynchronize(s);
+  return cleanup(e);
+}
+
 // ------------------------------------------------------------------ query packing prepass
 
 // 8 lanes per query; lane t packs words t, t+8, ...  Flags the first empty / sentinel query.
@@ -266,28 +370,29 @@ __device__ __forceinline__ void store_result(void* out, uint64_t q, uint32_t sp,
   }
 }
 
-// Packed-symbol reader: current word in a register, the next one prefetched.
+// Packed-symbol reader: current word in a register, the next one prefetched.  Word positions are
+// 32-bit indices into the packed buffer (a launch never packs more than 2^32 words = 32 GiB).
 template <int ALPHA>
 struct QueryStream {
   static constexpr int BITS = ALPHA == 0 ? 4 : 8;
   static constexpr int SPW = 64 / BITS;
   static constexpr int LOG_SPW = ALPHA == 0 ? 4 : 3;
-  const uint64_t* wp;
   uint64_t w, wnext;
+  uint32_t widx;    // index of the word held in wnext
   uint32_t inword;
-  __device__ __forceinline__ void open(const uint64_t* qwords, uint64_t q, uint64_t o0) {
-    wp = qwords + q + (o0 >> LOG_SPW);
-    w = __ldg(wp);
-    wnext = __ldg(wp + 1);  // buffer is padded by 2 words
+  __device__ __forceinline__ void open(const uint64_t* __restrict__ qwords, uint32_t q, uint64_t o0) {
+    widx = q + uint32_t(o0 >> LOG_SPW) + 1;
+    w = __ldg(qwords + (widx - 1));
+    wnext = __ldg(qwords + widx);  // buffer is padded
     inword = 0;
   }
-  __device__ __forceinline__ uint32_t next() {
+  __device__ __forceinline__ uint32_t next(const uint64_t* __restrict__ qwords) {
     uint32_t c = uint32_t(w) & ((1u << BITS) - 1u);
     w >>= BITS;
     if (++inword == SPW) {
       w = wnext;
-      wp++;
-      wnext = __ldg(wp + 1);
+      widx++;
+      wnext = __ldg(qwords + widx);
       inword = 0;
     }
     return c;
@@ -299,8 +404,9 @@ struct QueryStream {
 // which recomputes the k-1 steps), else the single-symbol range (search.rs:43-48).
 // Returns the number of symbols still to process.
 template <int ALPHA>
-__device__ __forceinline__ uint32_t begin_query(const IndexView& ix, QueryStream<ALPHA>& qs,
-                                                uint32_t len, uint32_t& sp, uint32_t& ep) {
+__device__ __forceinline__ uint32_t begin_query(const IndexView& ix, const uint64_t* __restrict__ qwords,
+                                                QueryStream<ALPHA>& qs, uint32_t len, uint32_t& sp,
+                                                uint32_t& ep) {
   const uint32_t k = ix.kmer_len;
   if (k != 0 && len >= k) {
     uint64_t idx = 0;
@@ -323,11 +429,11 @@ __device__ __forceinline__ uint32_t begin_query(const IndexView& ix, QueryStream
       uint2 r = __ldg(ix.table + idx);
       sp = r.x;
       ep = r.y;
-      for (uint32_t j = 0; j < k; j++) qs.next();
+      for (uint32_t j = 0; j < k; j++) qs.next(qwords);
       return len - k;
     }
   }
-  uint32_t c = qs.next();
+  uint32_t c = qs.next(qwords);
   if (c == (ALPHA == 0 ? uint32_t(DNA_SENTINEL) : uint32_t(AMINO_SENTINEL))) {
     sp = 1;
     ep = 0;
@@ -350,10 +456,10 @@ __global__ void __launch_bounds__(256) search_scalar_kernel(IndexView ix, const 
     uint32_t sp = 1, ep = 0;
     if (len != 0) {
       QueryStream<ALPHA> qs;
-      qs.open(qwords, q, o0);
-      uint32_t left = begin_query<ALPHA>(ix, qs, len, sp, ep);
+      qs.open(qwords, uint32_t(q), o0);
+      uint32_t left = begin_query<ALPHA>(ix, qwords, qs, len, sp, ep);
       while (left != 0 && sp <= ep) {  // early break: fm_index.rs:409-416 / :425-433
-        uint32_t c = qs.next();
+        uint32_t c = qs.next(qwords);
         left--;
         if (c == (ALPHA == 0 ? uint32_t(DNA_SENTINEL) : uint32_t(AMINO_SENTINEL))) {
           sp = 1;
@@ -426,23 +532,24 @@ __global__ void __launch_bounds__(TPB, MINB)
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t sub = lane % LANES;
   const uint32_t gmask = LANES == 1 ? (1u << lane) : (((1u << LANES) - 1u) << (lane - sub));
-  const uint64_t G = (gridDim.x * uint64_t(blockDim.x)) / LANES;
-  uint64_t q = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) / LANES;
-  uint64_t cur = 0;
+  const uint32_t G = (gridDim.x * blockDim.x) / LANES;  // nq < 2^32 per launch
+  const uint32_t nq32 = uint32_t(nq);
+  uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  uint32_t cur = 0;
   bool have = false;
   uint32_t sp = 1, ep = 0, left = 0;
   QueryStream<0> qs;
-  qs.wp = qwords;
   qs.w = qs.wnext = 0;
+  qs.widx = 0;
   qs.inword = 0;
 
   for (;;) {
     if (left == 0 || sp > ep) {
       if (have && sub == 0) store_result<MODE>(out, cur, sp, ep);
       have = false;
-      if (q >= nq) break;
+      if (q >= nq32) break;
       cur = q;
-      q += G;
+      q = (q + G < q) ? 0xffffffffu : q + G;
       have = true;
       uint64_t o0 = qoff[cur];
       uint32_t len = uint32_t(qoff[cur + 1] - o0);
@@ -451,11 +558,11 @@ __global__ void __launch_bounds__(TPB, MINB)
       left = 0;
       if (len != 0) {
         qs.open(qwords, cur, o0);
-        left = begin_query<0>(ix, qs, len, sp, ep);
+        left = begin_query<0>(ix, qwords, qs, len, sp, ep);
       }
       continue;
     }
-    uint32_t c = qs.next();
+    uint32_t c = qs.next(qwords);
     left--;
     uint32_t pa = sp - 1, pb = ep;
     uint32_t ba = pa >> 7, bb = pb >> 7;
@@ -484,21 +591,161 @@ __global__ void __launch_bounds__(TPB, MINB)
   }
 }
 
+template <int LANES, int MODE, int MINB>
+static cudaError_t launch_search_dna_b(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
+                                       uint64_t nq, void* d_out, int sm_count, int force_per_sm,
+                                       cudaStream_t s) {
+  constexpr int TPB = 256;
+  auto kern = search_dna_kernel<LANES, MODE, TPB, MINB>;
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, 0);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  if (force_per_sm > 0 && force_per_sm < per_sm) per_sm = force_per_sm;
+  uint64_t max_blocks = uint64_t(sm_count) * uint64_t(per_sm);
+  uint64_t need_blocks = (nq * LANES + TPB - 1) / TPB;
+  unsigned grid = unsigned(std::max<uint64_t>(1, std::min(max_blocks, need_blocks)));
+  kern<<<grid, TPB, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+// blocks_per_sm picks the register budget the kernel was compiled for (launch bounds 256 x MINB)
 template <int LANES, int MODE>
 static cudaError_t launch_search_dna(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
                                      uint64_t nq, void* d_out, const SearchVariant& v, int sm_count,
                                      cudaStream_t s) {
-  constexpr int TPB = 256;
-  auto kern = search_dna_kernel<LANES, MODE, TPB, 1>;
-  int per_sm = v.blocks_per_sm;
-  if (per_sm <= 0) {
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, 0);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
+  if (nq >= (1ull << 32)) return cudaErrorInvalidValue;
+  switch (v.blocks_per_sm) {
+    case 6: return launch_search_dna_b<LANES, MODE, 6>(ix, d_qwords, d_qoff, nq, d_out, sm_count, 0, s);
+    case 8: return launch_search_dna_b<LANES, MODE, 8>(ix, d_qwords, d_qoff, nq, d_out, sm_count, 0, s);
+    default:  // 0 / 4: no register cap (4 resident blocks); 1..3 run the same kernel on a smaller grid
+      return launch_search_dna_b<LANES, MODE, 4>(ix, d_qwords, d_qoff, nq, d_out, sm_count, v.blocks_per_sm, s);
   }
-  uint64_t groups_needed = nq;
+}
+
+// ---- nucleotide pair kernel: 4 lanes per query, two query symbols per 128-B block access ----
+// While at least two symbols remain and both are A/C/G/T the group reads ONE pair block
+// (4 x LDG.256) and applies two backward-search steps at once; a lone last symbol or an N
+// falls back to the 1-step block (4 x LDG.128).  Same persistent-group refill as above.
+__device__ __forceinline__ uint32_t pair_partial_rank(const u32x8& x, uint32_t sub, uint32_t local,
+                                                      uint32_t pair, uint32_t cnt_lane, uint32_t cnt_word) {
+  uint32_t r = 0;
+  if (sub < 3) {
+    uint32_t m = ~x.v[4];
+#pragma unroll
+    for (int p = 0; p < 4; p++) m &= ((pair >> p) & 1u) ? x.v[p] : ~x.v[p];
+    r = __popc(m & chunk_mask(local, sub));
+  }
+  if (sub == cnt_lane) {
+    uint32_t c = x.v[0];
+#pragma unroll
+    for (int i = 1; i < 8; i++) c = cnt_word == uint32_t(i) ? x.v[i] : c;
+    r += c;
+  }
+  return r;
+}
+
+template <int MODE, int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB)
+    search_dna_pair_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
+                           const uint64_t* __restrict__ qoff, uint64_t nq, void* __restrict__ out) {
+  constexpr int LANES = 4;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t sub = lane & 3;
+  const uint32_t gmask = 0xfu << (lane - sub);
+  const uint32_t G = (gridDim.x * blockDim.x) / LANES;
+  const uint32_t nq32 = uint32_t(nq);
+  uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  uint32_t cur = 0;
+  bool have = false;
+  uint32_t sp = 1, ep = 0, left = 0;
+  QueryStream<0> qs;
+  qs.w = qs.wnext = 0;
+  qs.widx = 0;
+  qs.inword = 0;
+
+  for (;;) {
+    if (left == 0 || sp > ep) {
+      if (have && sub == 0) store_result<MODE>(out, cur, sp, ep);
+      have = false;
+      if (q >= nq32) break;
+      cur = q;
+      q = (q + G < q) ? 0xffffffffu : q + G;
+      have = true;
+      uint64_t o0 = qoff[cur];
+      uint32_t len = uint32_t(qoff[cur + 1] - o0);
+      sp = 1;
+      ep = 0;
+      left = 0;
+      if (len != 0) {
+        qs.open(qwords, cur, o0);
+        left = begin_query<0>(ix, qwords, qs, len, sp, ep);
+      }
+      continue;
+    }
+    const uint32_t pa = sp - 1, pb = ep;
+    uint32_t c1 = uint32_t(qs.w) & 15u;
+    uint32_t c2 = qs.inword == 15 ? (uint32_t(qs.wnext) & 15u) : (uint32_t(qs.w >> 4) & 15u);
+    uint32_t ra, rb, base;
+    if (left >= 2 && (c1 | c2) < 4) {
+      qs.next(qwords);
+      qs.next(qwords);
+      left -= 2;
+      const uint32_t pair = 4 * c1 + c2;
+      const uint32_t cnt_lane = pair < 9 ? pair / 3 : 3;
+      const uint32_t cnt_word = pair < 9 ? 5 + pair % 3 : pair - 9;
+      uint32_t ba = __umulhi(pa, 0xAAAAAAABu) >> 6, bb = __umulhi(pb, 0xAAAAAAABu) >> 6;  // / 96
+      uint32_t la = pa - ba * PAIR_ROWS_PER_BLOCK, lb = pb - bb * PAIR_ROWS_PER_BLOCK;
+      u32x8 x = ldg256(ix.pair_blocks + size_t(ba) * PAIR_BLOCK_UINT4 + 2 * sub);
+      ra = pair_partial_rank(x, sub, la, pair, cnt_lane, cnt_word);
+      if (bb != ba) x = ldg256(ix.pair_blocks + size_t(bb) * PAIR_BLOCK_UINT4 + 2 * sub);
+      rb = pair_partial_rank(x, sub, lb, pair, cnt_lane, cnt_word);
+      base = ix.c2[pair];
+    } else {
+      qs.next(qwords);
+      left--;
+      if (c1 >= 4) {
+        if (c1 == DNA_N) {
+          lf_update<0>(ix, sp, ep, c1);
+        } else {
+          sp = 1;
+          ep = 0;
+        }
+        continue;
+      }
+      uint32_t ba = pa >> 7, bb = pb >> 7;
+      LaneChunks<4> y;
+      y.load(ix.blocks + size_t(ba) * DNA_BLOCK_UINT4, sub);
+      uint32_t m0 = (c1 & 1) ? ~0u : 0u, m1 = (c1 & 2) ? ~0u : 0u;
+      ra = dna_partial_rank<4>(y, sub, pa & 127, c1, m0, m1);
+      if (bb != ba) y.load(ix.blocks + size_t(bb) * DNA_BLOCK_UINT4, sub);
+      rb = dna_partial_rank<4>(y, sub, pb & 127, c1, m0, m1);
+      base = ix.c_lo[c1];
+    }
+    ra += __shfl_xor_sync(gmask, ra, 1);
+    rb += __shfl_xor_sync(gmask, rb, 1);
+    ra += __shfl_xor_sync(gmask, ra, 2);
+    rb += __shfl_xor_sync(gmask, rb, 2);
+    sp = base + ra;
+    ep = base + rb - 1;
+  }
+}
+
+template <int MODE>
+static cudaError_t launch_search_pair(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
+                                      uint64_t nq, void* d_out, const SearchVariant& v, int sm_count,
+                                      cudaStream_t s) {
+  if (nq >= (1ull << 32)) return cudaErrorInvalidValue;
+  constexpr int TPB = 256;
+  auto kern = search_dna_pair_kernel<MODE, TPB, 4>;
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, 0);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  if (v.blocks_per_sm > 0 && v.blocks_per_sm < per_sm) per_sm = v.blocks_per_sm;
   uint64_t max_blocks = uint64_t(sm_count) * uint64_t(per_sm);
-  uint64_t need_blocks = (groups_needed * LANES + TPB - 1) / TPB;
+  uint64_t need_blocks = (nq * 4 + TPB - 1) / TPB;
   unsigned grid = unsigned(std::max<uint64_t>(1, std::min(max_blocks, need_blocks)));
   kern<<<grid, TPB, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out);
   COUNT_LAUNCH();
@@ -510,10 +757,12 @@ static cudaError_t launch_search_mode(const IndexView& ix, const uint64_t* d_qwo
                                       uint64_t nq, void* d_out, const SearchVariant& v, int sm_count,
                                       cudaStream_t s) {
   if (ix.alphabet == 0 && v.lanes != -1) {
+    if (ix.pair_blocks != nullptr && (v.lanes == 0 || v.lanes == 8))
+      return launch_search_pair<MODE>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
     switch (v.lanes) {
       case 1: return launch_search_dna<1, MODE>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
-      case 2: return launch_search_dna<2, MODE>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
-      default: return launch_search_dna<4, MODE>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
+      case 4: return launch_search_dna<4, MODE>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
+      default: return launch_search_dna<2, MODE>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
     }
   }
   // amino (and lanes == -1: the scalar nucleotide kernel, kept for cross-checking)

@@ -17,7 +17,8 @@ inline uint64_t packed_words(int alphabet, uint64_t nq, uint64_t total_bytes) {
 enum SearchOut { OUT_COUNT_U64 = 0, OUT_RANGE_U64 = 1, OUT_SP_CNT_U32 = 2 };
 
 struct SearchVariant {
-  int lanes = 0;          // lanes per query (nucleotide: 1, 2 or 4; amino: 1)
+  int lanes = 0;          // nucleotide: 1, 2, 4 lanes per query on the 1-step blocks; 8 = pair-index
+                          // kernel (default when the pair index exists); -1 = scalar kernel
   int tpb = 0;            // threads per block
   int blocks_per_sm = 0;  // 0 = occupancy-derived
 };
@@ -34,6 +35,10 @@ cudaError_t launch_transpose(int alphabet, const uint64_t* d_ref_blocks, uint64_
                              unsigned int* d_dollar_row, cudaStream_t s);
 uint64_t table_entries(int alphabet, uint32_t k);
 cudaError_t launch_build_table(const IndexView& ix, uint2* d_table, uint32_t k, cudaStream_t s);
+
+// nucleotide pair index (two symbols per access), built from the 1-step device blocks
+uint64_t pair_block_count(uint64_t bwt_len);
+cudaError_t build_pair_index(const IndexView& ix, uint4* d_pair_blocks, uint32_t* c2_host /*16*/, cudaStream_t s);
 
 cudaError_t launch_pack(int alphabet, const uint8_t* d_qbytes, const uint64_t* d_qoff, uint64_t nq,
                         uint64_t* d_qwords, unsigned long long* d_first_bad, cudaStream_t s);

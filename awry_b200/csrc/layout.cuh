@@ -13,6 +13,18 @@
 //               The N milestone is derived: start - (A+C+G+T) - [$ row < start].
 //               => 4 bits per BWT row all-in; one LF step reads one 64-B aligned block.
 //
+//   NUCLEOTIDE PAIR INDEX (accelerator, derived from the blocks above at load time)
+//               block = 96 BWT rows = 128 B = 4 lane slices of 32 B (one LDG.256 each)
+//               row code (5 planes) = 4*a + b with a = BWT[row], b = BWT[LF(row)], both in
+//               A,C,G,T; plane 4 marks rows where either symbol is N or '$' (they match no pair).
+//               slice t < 3 = { p0..p4 of rows 32t..32t+31, cnt[3t], cnt[3t+1], cnt[3t+2] }
+//               slice 3     = { cnt[9] .. cnt[15], spare }
+//               cnt[p] = #rows with pair code p in BWT[0 .. block start).
+//               One access advances the backward search by TWO query symbols:
+//                 sp'' = C2[a,b] + Occ2(ab, sp-1),  ep'' = C2[a,b] + Occ2(ab, ep) - 1,
+//                 C2[a,b] = C[b] + Occ(b, C[a]-1)
+//               (two applications of fm_index.rs:559-582 composed).
+//
 //   AMINO       block = 256 rows = 256 B = 8 chunks of 32 B (one LDG.256 each)
 //               chunk j = { p0..p4, cnt_{3j}, cnt_{3j+1}, cnt_{3j+2} }, 24 count slots,
 //               slot s-1 = #symbol s in BWT[0 .. block start), s = reference symbol index 1..21.
@@ -33,12 +45,15 @@ constexpr int AMINO_X = 20, AMINO_SENTINEL = 0;
 
 constexpr uint32_t DNA_ROWS_PER_BLOCK = 128, DNA_BLOCK_UINT4 = 4;
 constexpr uint32_t AMINO_ROWS_PER_BLOCK = 256, AMINO_BLOCK_UINT4 = 16;
+constexpr uint32_t PAIR_ROWS_PER_BLOCK = 96, PAIR_BLOCK_UINT4 = 8;
 
 struct IndexView {
   const uint4* __restrict__ blocks;
   const uint64_t* __restrict__ sa_words;
   const uint2* __restrict__ table;         // k-mer seeds: (sp, ep), empty = (1,0)
   const uint64_t* __restrict__ seq_starts;
+  const uint4* __restrict__ pair_blocks;   // nucleotide two-step accelerator, or nullptr
+  uint32_t c2[16];                         // C2[4a+b]
   uint32_t c_lo[24];                       // C[c]      by device symbol (search.rs:43-48)
   uint32_t c_hi[24];                       // C[c+1]-1  by device symbol
   uint32_t bwt_len;

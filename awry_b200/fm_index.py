@@ -78,7 +78,7 @@ class _Info(C.Structure):
                 ("n_devices", C.c_uint32), ("prefix_sums", C.c_uint64 * 23),
                 ("n_sequences", C.c_uint64), ("device_bytes_blocks", C.c_uint64),
                 ("device_bytes_sa", C.c_uint64), ("device_bytes_table", C.c_uint64),
-                ("devices", C.c_int32 * 16)]
+                ("device_bytes_pair", C.c_uint64), ("devices", C.c_int32 * 16)]
 
 
 class _Parts(C.Structure):
@@ -254,7 +254,7 @@ class FmIndex:
 
     def device_bytes(self) -> dict:
         return {"blocks": int(self._info.device_bytes_blocks), "sa": int(self._info.device_bytes_sa),
-                "table": int(self._info.device_bytes_table)}
+                "table": int(self._info.device_bytes_table), "pair": int(self._info.device_bytes_pair)}
 
     def sequence_header(self, seq_idx: int) -> str:
         p, n = C.c_char_p(), C.c_uint64()

@@ -68,6 +68,7 @@ typedef struct awry_info {
   uint64_t device_bytes_blocks; /* per replica */
   uint64_t device_bytes_sa;
   uint64_t device_bytes_table;
+  uint64_t device_bytes_pair;   /* nucleotide two-symbol accelerator blocks */
   int32_t devices[16];
 } awry_info;
 
@@ -194,8 +195,9 @@ int awry_profile_get(awry_profile *out);
 int awry_bench_random_gather(int device, uint64_t footprint_bytes, uint32_t granule, uint32_t lanes,
                              uint64_t n_reads, int iters, double *reads_per_s, double *gb_per_s);
 
-/* Tuning knob for experiments: selects the search-kernel variant (lanes per query 1/2/4,
- * threads per block, blocks per SM).  0 keeps the default. */
+/* Tuning knob for experiments: selects the search-kernel variant.  lanes_per_query: 1/2/4 =
+ * that many lanes on the one-symbol blocks, 8 = the two-symbol (pair index) kernel, -1 = scalar
+ * kernel, 0 = default (pair kernel when the pair index exists).  blocks_per_sm caps residency. */
 int awry_set_search_variant(int lanes_per_query, int threads_per_block, int blocks_per_sm);
 
 const char *awry_last_error(void);

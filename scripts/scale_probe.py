@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--qlen", type=int, default=150)
     ap.add_argument("--k", type=int, default=13)
     ap.add_argument("--ratio", type=int, default=8)
-    ap.add_argument("--variants", default="4,2,1")
+    ap.add_argument("--variants", default="8,2")
     ap.add_argument("--bps", default="0")
     ap.add_argument("--check", type=int, default=20000)
     ap.add_argument("--locate-nq", type=int, default=1_000_000)

@@ -1,0 +1,104 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/awry_b200.h declares, compiles as C and C++, and fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, has_gpu
+
+HEADER = os.path.join(ROOT, "include", "awry_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(awry_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from awry_b200 import fm_index as f
+    lib = f.native()
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert sorted(f.EXPORTS) == syms
+    assert b"sm_100a" in lib.awry_version()
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    for comp, ext, std in (("gcc", "c", "-std=c99"), ("g++", "cpp", "-std=c++11")):
+        src = tmp_path / f"t.{ext}"
+        src.write_text('#include "awry_b200.h"\nint main(void){ awry_hit h; h.seq_idx = 0; return (int)h.seq_idx + (int)sizeof(awry_info) * 0; }\n')
+        subprocess.check_call([comp, std, "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                               "-c", str(src), "-o", str(tmp_path / f"t_{ext}.o")])
+
+
+def test_struct_layouts_match_ctypes(tmp_path):
+    """ctypes mirrors vs the compiler's view of include/awry_b200.h"""
+    from awry_b200 import fm_index as f
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "awry_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n", '
+                   'sizeof(awry_range), sizeof(awry_parts), sizeof(awry_info), sizeof(awry_profile), sizeof(awry_hit));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    assert sizes == [C.sizeof(f._Range), C.sizeof(f._Parts), C.sizeof(f._Info), C.sizeof(f.Profile), 16]
+
+
+def test_kernels_are_sm100a_native():
+    """the shipped library carries sm_100a SASS with the 256-bit global loads of the rank kernels"""
+    lib = os.path.join(ROOT, "awry_b200", "libawry_b200.so")
+    out = subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    assert "search_dna_kernel" in sass and "walk_kernel" in sass
+    assert re.search(r"LDG\.E\S*\.256", sass) and "POPC" in sass and "SHFL.BFLY" in sass
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_fails_loudly(tmp_path):
+    from awry_b200 import AwryError, FmIndex
+    golden = os.path.join(ROOT, "tests", "golden", "appendix_a.awry")
+    with pytest.raises(AwryError) as e:
+        FmIndex.load(golden)
+    assert e.value.code == -4 and "no CPU fallback" in str(e.value)
+    with pytest.raises(AwryError):
+        FmIndex.from_parts(0, 8, 1000, 4, np.zeros(80, np.uint64), np.zeros(7, np.uint64), np.zeros(64, np.uint64))
+
+
+def test_bad_arguments_are_errors_not_crashes(tmp_path):
+    from awry_b200 import fm_index as f
+    lib = f.native()
+    out = C.c_void_p()
+    assert lib.awry_index_load(None, None, 0, C.byref(out)) == -1
+    assert lib.awry_index_load(b"/nonexistent/x.awry", None, 0, C.byref(out)) == -2
+    assert b"cannot open" in lib.awry_last_error()
+    bad = tmp_path / "bad.awry"
+    bad.write_bytes(b"not an index at all, just some bytes....................")
+    assert lib.awry_index_load(os.fsencode(str(bad)), None, 0, C.byref(out)) == -3
+    assert lib.awry_count_batch(None, None, None, 5, None) == -1
+    assert lib.awry_index_info(None, None) == -1
+    lib.awry_index_free(None)
+    lib.awry_hits_free(None)
+    assert lib.awry_profile_get(None) == -1
+    assert lib.awry_set_search_variant(3, 0, 0) == -1
+
+
+def test_product_never_touches_the_oracle():
+    """the shipped package must not import, link or execute anything under oracle/ or fixtures/"""
+    pkg = os.path.join(ROOT, "awry_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".hpp", ".h", "Makefile")):
+                txt = open(os.path.join(dirpath, fn), errors="replace").read()
+                assert "oracle" not in txt.replace("oracle/ or fixtures/", ""), (fn, "mentions oracle")
+                assert "pyfixture" not in txt and "awo_" not in txt, fn
+    ldd = subprocess.run(["ldd", os.path.join(pkg, "libawry_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd and "fixture" not in ldd

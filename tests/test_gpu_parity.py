@@ -63,7 +63,7 @@ def test_golden_file_appendix_a():
             assert all(h.sequence_idx == 0 for h in ix.locate_string(q))
 
 
-@pytest.mark.parametrize("lanes", [0, 1, 2, 4, -1])
+@pytest.mark.parametrize("lanes", [0, 1, 2, 4, 8, -1])
 def test_count_parity_cfg1_style(fx, dna, dna_dev, dna_or, lanes):
     """parallel_count of 10k random 32-bp queries (half present, half random) + edge cases."""
     from awry_b200 import fm_index as f
