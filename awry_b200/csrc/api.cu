@@ -158,6 +158,8 @@ struct Workspace {
   size_t d_qoff_cap = 0;
   uint64_t* d_qwords = nullptr;
   size_t d_qwords_cap = 0;
+  uint32_t* d_defer = nullptr;
+  size_t d_defer_cap = 0;
   uint8_t* d_out = nullptr;
   size_t d_out_cap = 0;
   uint64_t* d_hit_off = nullptr;
@@ -203,6 +205,7 @@ struct Workspace {
     cudaFree(d_qbytes);
     cudaFree(d_qoff);
     cudaFree(d_qwords);
+    cudaFree(d_defer);
     cudaFree(d_out);
     cudaFree(d_hit_off);
     cudaFree(d_temp);
@@ -656,6 +659,7 @@ void enqueue_search(const awry_index* ix, Replica& r, Workspace* ws, const uint8
   Workspace::grow_dev(ws->d_qoff, ws->d_qoff_cap, size_t(nq) + 1);
   Workspace::grow_dev(ws->d_qwords, ws->d_qwords_cap, size_t(packed_words(ix->alphabet, nq, nbytes)));
   Workspace::grow_dev(ws->d_out, ws->d_out_cap, size_t(nq) * out_elem);
+  Workspace::grow_dev(ws->d_defer, ws->d_defer_cap, size_t(nq) + 1);
   const uint8_t* src_b = qbytes + c.b0;
   const uint64_t* src_o = qoff + c.q0;
   if (!src_pinned) {
@@ -677,7 +681,7 @@ void enqueue_search(const awry_index* ix, Replica& r, Workspace* ws, const uint8
   }
   {
     ProfScope p(0, r.device, ws->st);
-    CU(launch_search(r.view, ws->d_qwords - (c.b0 >> (ix->alphabet == 0 ? 4 : 3)), ws->d_qoff, nq, mode, ws->d_out, g_variant, r.sm_count, ws->st));
+    CU(launch_search(r.view, ws->d_qwords - (c.b0 >> (ix->alphabet == 0 ? 4 : 3)), ws->d_qoff, nq, mode, ws->d_out, ws->d_defer, g_variant, r.sm_count, ws->st));
   }
   CU(cudaMemcpyAsync(ws->h_flag, ws->d_flag, 8, cudaMemcpyDeviceToHost, ws->st));
 }
@@ -1200,15 +1204,16 @@ int awry_count_device(const awry_index* ix, int replica, const uint8_t* d_qbytes
     if (ends[1] < ends[0]) fail(AWRY_ERR_INVALID_ARG, "query offsets are not monotone");
     const int sh = ix->alphabet == 0 ? 4 : 3;
     uint64_t words = nq + ((ends[1] >> sh) - (ends[0] >> sh)) + 4;
-    uint64_t* d_qwords = nullptr;
-    CU(cudaMallocAsync(reinterpret_cast<void**>(&d_qwords), words * 8, st));
+    uint64_t* d_qwords = nullptr;  // packed queries, then the deferred-query list
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&d_qwords), words * 8 + (nq + 2) * 4, st));
+    uint32_t* d_defer = reinterpret_cast<uint32_t*>(d_qwords + words);
     {
       ProfScope p(2, r.device, st);
       CU(launch_pack(ix->alphabet, d_qbytes, d_qoff, nq, d_qwords - (ends[0] >> sh), r.d_async_flag, st));
     }
     {
       ProfScope p(0, r.device, st);
-      CU(launch_search(r.view, d_qwords - (ends[0] >> sh), d_qoff, nq, OUT_COUNT_U64, d_counts, g_variant, r.sm_count, st));
+      CU(launch_search(r.view, d_qwords - (ends[0] >> sh), d_qoff, nq, OUT_COUNT_U64, d_counts, d_defer, g_variant, r.sm_count, st));
     }
     CU(cudaFreeAsync(d_qwords, st));
   });
@@ -1238,13 +1243,14 @@ int awry_locate_device(const awry_index* ix, int replica, const uint8_t* d_qbyte
       uint64_t words = nq + ((ends[1] >> sh) - (ends[0] >> sh)) + 4;
       Workspace::grow_dev(ws->d_qwords, ws->d_qwords_cap, size_t(words));
       Workspace::grow_dev(ws->d_out, ws->d_out_cap, size_t(nq) * 8);
+      Workspace::grow_dev(ws->d_defer, ws->d_defer_cap, size_t(nq) + 1);
       {
         ProfScope p(2, r.device, st);
         CU(launch_pack(ix->alphabet, d_qbytes, d_qoff, nq, ws->d_qwords - (ends[0] >> sh), r.d_async_flag, st));
       }
       {
         ProfScope p(0, r.device, st);
-        CU(launch_search(r.view, ws->d_qwords - (ends[0] >> sh), d_qoff, nq, OUT_SP_CNT_U32, ws->d_out, g_variant, r.sm_count, st));
+        CU(launch_search(r.view, ws->d_qwords - (ends[0] >> sh), d_qoff, nq, OUT_SP_CNT_U32, ws->d_out, ws->d_defer, g_variant, r.sm_count, st));
       }
       uint64_t n = 0;
       uint64_t* h = locate_chunk_device(ix, r, ws, nq, flags, d_hit_off, &n, st);

@@ -445,12 +445,17 @@ __device__ __forceinline__ uint32_t begin_query(const IndexView& ix, const uint6
 }
 
 // ---- scalar kernel: one thread per query (any alphabet) ----
-template <int ALPHA, int MODE>
+// LIST: the queries to run are listed in defer[1 .. 1+defer[0]) (queries the cooperative kernels
+// handed back because they contain an ambiguity symbol).
+template <int ALPHA, int MODE, bool LIST>
 __global__ void __launch_bounds__(256) search_scalar_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
                                                             const uint64_t* __restrict__ qoff, uint64_t nq,
-                                                            void* __restrict__ out) {
+                                                            void* __restrict__ out,
+                                                            const uint32_t* __restrict__ defer) {
   uint64_t stride = gridDim.x * uint64_t(blockDim.x);
-  for (uint64_t q = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; q < nq; q += stride) {
+  uint64_t n = LIST ? uint64_t(defer[0]) : nq;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += stride) {
+    uint64_t q = LIST ? uint64_t(defer[1 + i]) : i;
     uint64_t o0 = qoff[q];
     uint32_t len = uint32_t(qoff[q + 1] - o0);
     uint32_t sp = 1, ep = 0;
@@ -625,9 +630,11 @@ static cudaError_t launch_search_dna(const IndexView& ix, const uint64_t* d_qwor
 }
 
 // ---- nucleotide pair kernel: 4 lanes per query, two query symbols per 128-B block access ----
-// While at least two symbols remain and both are A/C/G/T the group reads ONE pair block
-// (4 x LDG.256) and applies two backward-search steps at once; a lone last symbol or an N
-// falls back to the 1-step block (4 x LDG.128).  Same persistent-group refill as above.
+// While at least two symbols remain the group reads ONE pair block (4 x LDG.256) and applies two
+// backward-search steps at once; a lone last symbol uses the 1-step block (4 x LDG.128).
+// Queries holding an ambiguity symbol (N) are handed to the scalar kernel through `defer`
+// (defer[0] = count, then the query numbers), which keeps this kernel's register budget small.
+// Same persistent-group refill as above.
 __device__ __forceinline__ uint32_t pair_partial_rank(const u32x8& x, uint32_t sub, uint32_t local,
                                                       uint32_t pair, uint32_t cnt_lane, uint32_t cnt_word) {
   uint32_t r = 0;
@@ -649,16 +656,14 @@ __device__ __forceinline__ uint32_t pair_partial_rank(const u32x8& x, uint32_t s
 template <int MODE, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB)
     search_dna_pair_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
-                           const uint64_t* __restrict__ qoff, uint64_t nq, void* __restrict__ out) {
+                           const uint64_t* __restrict__ qoff, uint64_t nq, void* __restrict__ out,
+                           uint32_t* __restrict__ defer) {
   constexpr int LANES = 4;
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t sub = lane & 3;
-  const uint32_t gmask = 0xfu << (lane - sub);
-  const uint32_t G = (gridDim.x * blockDim.x) / LANES;
-  const uint32_t nq32 = uint32_t(nq);
-  uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
-  uint32_t cur = 0;
-  bool have = false;
+  constexpr uint32_t NONE = 0xffffffffu;
+  const uint32_t sub = threadIdx.x & 3;
+  const uint32_t gmask = 0xfu << ((threadIdx.x & 31) - sub);
+  uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;  // next query of this group
+  uint32_t cur = NONE;                                            // query in flight
   uint32_t sp = 1, ep = 0, left = 0;
   QueryStream<0> qs;
   qs.w = qs.wnext = 0;
@@ -667,12 +672,12 @@ __global__ void __launch_bounds__(TPB, MINB)
 
   for (;;) {
     if (left == 0 || sp > ep) {
-      if (have && sub == 0) store_result<MODE>(out, cur, sp, ep);
-      have = false;
-      if (q >= nq32) break;
+      if (cur != NONE && sub == 0) store_result<MODE>(out, cur, sp, ep);
+      cur = NONE;
+      if (q >= uint32_t(nq)) break;
       cur = q;
-      q = (q + G < q) ? 0xffffffffu : q + G;
-      have = true;
+      const uint32_t G = (gridDim.x * blockDim.x) / LANES;
+      q = (q + G < q) ? NONE : q + G;
       uint64_t o0 = qoff[cur];
       uint32_t len = uint32_t(qoff[cur + 1] - o0);
       sp = 1;
@@ -680,44 +685,75 @@ __global__ void __launch_bounds__(TPB, MINB)
       left = 0;
       if (len != 0) {
         qs.open(qwords, cur, o0);
-        left = begin_query<0>(ix, qwords, qs, len, sp, ep);
+        const uint32_t k = ix.kmer_len;
+        bool clean;
+        if (k != 0 && len >= k) {
+          uint64_t w = qs.w;  // k <= 16 symbols, all inside the first word
+          clean = (w & (0xCCCCCCCCCCCCCCCCull >> (4 * (16 - k)))) == 0;
+          if (clean) {
+            uint64_t idx = 0;
+#pragma unroll 1
+            for (uint32_t j = 0; j < k; j++) {
+              idx |= ((w >> (4 * j)) & 3ull) << (2 * j);
+              qs.next(qwords);
+            }
+            uint2 r = __ldg(ix.table + idx);
+            sp = r.x;
+            ep = r.y;
+            left = len - k;
+          }
+        } else {
+          uint32_t c = qs.next(qwords);
+          clean = c < 4;
+          if (clean) {
+            sp = ix.c_lo[c];
+            ep = ix.c_hi[c];
+            left = len - 1;
+          }
+        }
+        if (!clean) {  // hand the whole query to the scalar kernel
+          if (sub == 0) defer[1 + atomicAdd(defer, 1u)] = cur;
+          cur = NONE;
+        }
       }
       continue;
     }
     const uint32_t pa = sp - 1, pb = ep;
-    uint32_t c1 = uint32_t(qs.w) & 15u;
-    uint32_t c2 = qs.inword == 15 ? (uint32_t(qs.wnext) & 15u) : (uint32_t(qs.w >> 4) & 15u);
+    const uint32_t c1 = uint32_t(qs.w) & 15u;
     uint32_t ra, rb, base;
-    if (left >= 2 && (c1 | c2) < 4) {
+    if (left >= 2) {
+      const uint32_t c2 = qs.inword == 15 ? (uint32_t(qs.wnext) & 15u) : (uint32_t(qs.w >> 4) & 15u);
+      if ((c1 | c2) >= 4) {
+        if (sub == 0) defer[1 + atomicAdd(defer, 1u)] = cur;
+        cur = NONE;
+        left = 0;
+        continue;
+      }
       qs.next(qwords);
       qs.next(qwords);
       left -= 2;
       const uint32_t pair = 4 * c1 + c2;
       const uint32_t cnt_lane = pair < 9 ? pair / 3 : 3;
       const uint32_t cnt_word = pair < 9 ? 5 + pair % 3 : pair - 9;
-      uint32_t ba = __umulhi(pa, 0xAAAAAAABu) >> 6, bb = __umulhi(pb, 0xAAAAAAABu) >> 6;  // / 96
-      uint32_t la = pa - ba * PAIR_ROWS_PER_BLOCK, lb = pb - bb * PAIR_ROWS_PER_BLOCK;
+      const uint32_t ba = __umulhi(pa, 0xAAAAAAABu) >> 6, bb = __umulhi(pb, 0xAAAAAAABu) >> 6;  // / 96
       u32x8 x = ldg256(ix.pair_blocks + size_t(ba) * PAIR_BLOCK_UINT4 + 2 * sub);
-      ra = pair_partial_rank(x, sub, la, pair, cnt_lane, cnt_word);
+      ra = pair_partial_rank(x, sub, pa - ba * PAIR_ROWS_PER_BLOCK, pair, cnt_lane, cnt_word);
       if (bb != ba) x = ldg256(ix.pair_blocks + size_t(bb) * PAIR_BLOCK_UINT4 + 2 * sub);
-      rb = pair_partial_rank(x, sub, lb, pair, cnt_lane, cnt_word);
+      rb = pair_partial_rank(x, sub, pb - bb * PAIR_ROWS_PER_BLOCK, pair, cnt_lane, cnt_word);
       base = ix.c2[pair];
     } else {
-      qs.next(qwords);
-      left--;
       if (c1 >= 4) {
-        if (c1 == DNA_N) {
-          lf_update<0>(ix, sp, ep, c1);
-        } else {
-          sp = 1;
-          ep = 0;
-        }
+        if (sub == 0) defer[1 + atomicAdd(defer, 1u)] = cur;
+        cur = NONE;
+        left = 0;
         continue;
       }
-      uint32_t ba = pa >> 7, bb = pb >> 7;
+      qs.next(qwords);
+      left = 0;
+      const uint32_t ba = pa >> 7, bb = pb >> 7;
       LaneChunks<4> y;
       y.load(ix.blocks + size_t(ba) * DNA_BLOCK_UINT4, sub);
-      uint32_t m0 = (c1 & 1) ? ~0u : 0u, m1 = (c1 & 2) ? ~0u : 0u;
+      const uint32_t m0 = (c1 & 1) ? ~0u : 0u, m1 = (c1 & 2) ? ~0u : 0u;
       ra = dna_partial_rank<4>(y, sub, pa & 127, c1, m0, m1);
       if (bb != ba) y.load(ix.blocks + size_t(bb) * DNA_BLOCK_UINT4, sub);
       rb = dna_partial_rank<4>(y, sub, pb & 127, c1, m0, m1);
@@ -732,33 +768,52 @@ __global__ void __launch_bounds__(TPB, MINB)
   }
 }
 
-template <int MODE>
-static cudaError_t launch_search_pair(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
-                                      uint64_t nq, void* d_out, const SearchVariant& v, int sm_count,
-                                      cudaStream_t s) {
-  if (nq >= (1ull << 32)) return cudaErrorInvalidValue;
+template <int MODE, int MINB>
+static cudaError_t launch_search_pair_b(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
+                                        uint64_t nq, void* d_out, uint32_t* d_defer, int force_per_sm,
+                                        int sm_count, cudaStream_t s) {
   constexpr int TPB = 256;
-  auto kern = search_dna_pair_kernel<MODE, TPB, 4>;
+  auto kern = search_dna_pair_kernel<MODE, TPB, MINB>;
   int per_sm = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, 0);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
-  if (v.blocks_per_sm > 0 && v.blocks_per_sm < per_sm) per_sm = v.blocks_per_sm;
+  if (force_per_sm > 0 && force_per_sm < per_sm) per_sm = force_per_sm;
   uint64_t max_blocks = uint64_t(sm_count) * uint64_t(per_sm);
   uint64_t need_blocks = (nq * 4 + TPB - 1) / TPB;
   unsigned grid = unsigned(std::max<uint64_t>(1, std::min(max_blocks, need_blocks)));
-  kern<<<grid, TPB, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out);
+  kern<<<grid, TPB, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out, d_defer);
+  COUNT_LAUNCH();
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  // queries with ambiguity symbols: scalar kernel over the deferred list (empty for clean batches)
+  search_scalar_kernel<0, MODE, true><<<unsigned(sm_count) * 2, 256, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out, d_defer);
   COUNT_LAUNCH();
   return cudaGetLastError();
 }
 
 template <int MODE>
+static cudaError_t launch_search_pair(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
+                                      uint64_t nq, void* d_out, uint32_t* d_defer, const SearchVariant& v,
+                                      int sm_count, cudaStream_t s) {
+  if (nq >= (1ull << 32) - 1) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(d_defer, 0, 4, s);
+  if (e != cudaSuccess) return e;
+  switch (v.blocks_per_sm) {
+    case 4: return launch_search_pair_b<MODE, 4>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s);
+    case 8: return launch_search_pair_b<MODE, 8>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s);
+    case 0:
+    case 6: return launch_search_pair_b<MODE, 6>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s);
+    default: return launch_search_pair_b<MODE, 4>(ix, d_qwords, d_qoff, nq, d_out, d_defer, v.blocks_per_sm, sm_count, s);
+  }
+}
+
+template <int MODE>
 static cudaError_t launch_search_mode(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
-                                      uint64_t nq, void* d_out, const SearchVariant& v, int sm_count,
-                                      cudaStream_t s) {
+                                      uint64_t nq, void* d_out, uint32_t* d_defer, const SearchVariant& v,
+                                      int sm_count, cudaStream_t s) {
   if (ix.alphabet == 0 && v.lanes != -1) {
     if (ix.pair_blocks != nullptr && (v.lanes == 0 || v.lanes == 8))
-      return launch_search_pair<MODE>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
+      return launch_search_pair<MODE>(ix, d_qwords, d_qoff, nq, d_out, d_defer, v, sm_count, s);
     switch (v.lanes) {
       case 1: return launch_search_dna<1, MODE>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
       case 4: return launch_search_dna<4, MODE>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
@@ -770,21 +825,21 @@ static cudaError_t launch_search_mode(const IndexView& ix, const uint64_t* d_qwo
   uint64_t need_blocks = (nq + 255) / 256;
   unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * per_sm, need_blocks)));
   if (ix.alphabet == 0)
-    search_scalar_kernel<0, MODE><<<grid, 256, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out);
+    search_scalar_kernel<0, MODE, false><<<grid, 256, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out, nullptr);
   else
-    search_scalar_kernel<1, MODE><<<grid, 256, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out);
+    search_scalar_kernel<1, MODE, false><<<grid, 256, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out, nullptr);
   COUNT_LAUNCH();
   return cudaGetLastError();
 }
 
 cudaError_t launch_search(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
-                          uint64_t nq, SearchOut mode, void* d_out, const SearchVariant& v,
-                          int sm_count, cudaStream_t s) {
+                          uint64_t nq, SearchOut mode, void* d_out, uint32_t* d_defer,
+                          const SearchVariant& v, int sm_count, cudaStream_t s) {
   if (nq == 0) return cudaSuccess;
   switch (mode) {
-    case OUT_COUNT_U64: return launch_search_mode<OUT_COUNT_U64>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
-    case OUT_RANGE_U64: return launch_search_mode<OUT_RANGE_U64>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
-    default: return launch_search_mode<OUT_SP_CNT_U32>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
+    case OUT_COUNT_U64: return launch_search_mode<OUT_COUNT_U64>(ix, d_qwords, d_qoff, nq, d_out, d_defer, v, sm_count, s);
+    case OUT_RANGE_U64: return launch_search_mode<OUT_RANGE_U64>(ix, d_qwords, d_qoff, nq, d_out, d_defer, v, sm_count, s);
+    default: return launch_search_mode<OUT_SP_CNT_U32>(ix, d_qwords, d_qoff, nq, d_out, d_defer, v, sm_count, s);
   }
 }
 

@@ -42,9 +42,10 @@ cudaError_t build_pair_index(const IndexView& ix, uint4* d_pair_blocks, uint32_t
 
 cudaError_t launch_pack(int alphabet, const uint8_t* d_qbytes, const uint64_t* d_qoff, uint64_t nq,
                         uint64_t* d_qwords, unsigned long long* d_first_bad, cudaStream_t s);
+// d_defer: nq + 1 u32 of scratch (list of queries the cooperative kernel hands to the scalar one)
 cudaError_t launch_search(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
-                          uint64_t nq, SearchOut mode, void* d_out, const SearchVariant& v,
-                          int sm_count, cudaStream_t s);
+                          uint64_t nq, SearchOut mode, void* d_out, uint32_t* d_defer,
+                          const SearchVariant& v, int sm_count, cudaStream_t s);
 
 // locate: CSR offsets from pass 1, LF-walk pass 2
 cudaError_t scan_hit_offsets(const uint2* d_sp_cnt, uint64_t nq, uint64_t* d_hit_off, void* d_temp,

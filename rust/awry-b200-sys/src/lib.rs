@@ -1,0 +1,87 @@
+//! Raw bindings: one `extern "C"` item per declaration of include/awry_b200.h.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct awry_index {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default, PartialEq, Eq)]
+pub struct awry_range {
+    pub start_ptr: u64,
+    pub end_ptr: u64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default, PartialEq, Eq, PartialOrd, Ord)]
+pub struct awry_hit {
+    pub seq_idx: u64,
+    pub local_pos: u64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct awry_info {
+    pub version: u64,
+    pub sa_ratio: u64,
+    pub bwt_len: u64,
+    pub alphabet: u32,
+    pub kmer_len: u32,
+    pub n_prefix_sums: u32,
+    pub n_devices: u32,
+    pub prefix_sums: [u64; 23],
+    pub n_sequences: u64,
+    pub device_bytes_blocks: u64,
+    pub device_bytes_sa: u64,
+    pub device_bytes_table: u64,
+    pub device_bytes_pair: u64,
+    pub devices: [i32; 16],
+}
+
+#[repr(C)]
+pub struct awry_parts {
+    pub alphabet: u32,
+    pub kmer_len: u32,
+    pub sa_ratio: u64,
+    pub bwt_len: u64,
+    pub version: u64,
+    pub blocks: *const u64,
+    pub prefix_sums: *const u64,
+    pub sa_words: *const u64,
+    pub seq_starts: *const u64,
+    pub headers: *const *const c_char,
+    pub n_sequences: u64,
+}
+
+pub const AWRY_OK: c_int = 0;
+pub const AWRY_ERR_IO: c_int = -2;
+pub const AWRY_ERR_INVALID_QUERY: c_int = -5;
+pub const AWRY_LOCATE_BWT_ORDER: u32 = 0;
+pub const AWRY_LOCATE_SORTED: u32 = 1;
+
+extern "C" {
+    pub fn awry_index_load(path: *const c_char, devices: *const c_int, n_dev: c_int, out: *mut *mut awry_index) -> c_int;
+    pub fn awry_index_from_parts(parts: *const awry_parts, devices: *const c_int, n_dev: c_int, out: *mut *mut awry_index) -> c_int;
+    pub fn awry_index_free(index: *mut awry_index);
+    pub fn awry_index_info(index: *const awry_index, info: *mut awry_info) -> c_int;
+    pub fn awry_index_sequence_header(index: *const awry_index, seq_idx: u64, header: *mut *const c_char, header_len: *mut u64) -> c_int;
+    pub fn awry_count_batch(index: *const awry_index, qbytes: *const u8, qoff: *const u64, nq: u64, counts: *mut u64) -> c_int;
+    pub fn awry_search_batch(index: *const awry_index, qbytes: *const u8, qoff: *const u64, nq: u64, ranges: *mut awry_range) -> c_int;
+    pub fn awry_locate_batch(index: *const awry_index, qbytes: *const u8, qoff: *const u64, nq: u64, flags: u32,
+                             hit_off: *mut u64, hits: *mut *mut awry_hit, n_hits: *mut u64) -> c_int;
+    pub fn awry_hits_free(hits: *mut awry_hit);
+    pub fn awry_initial_range(index: *const awry_index, ascii_symbol: u8, out: *mut awry_range) -> c_int;
+    pub fn awry_update_range(index: *const awry_index, range: awry_range, ascii_symbol: u8, out: *mut awry_range) -> c_int;
+    pub fn awry_backstep(index: *const awry_index, bwt_row: u64, out: *mut u64) -> c_int;
+    pub fn awry_count_device(index: *const awry_index, replica: c_int, d_qbytes: *const u8, d_qoff: *const u64, nq: u64,
+                             d_counts: *mut u64, cuda_stream: *mut c_void) -> c_int;
+    pub fn awry_locate_device(index: *const awry_index, replica: c_int, d_qbytes: *const u8, d_qoff: *const u64, nq: u64,
+                              flags: u32, d_hit_off: *mut u64, d_hits: *mut *mut awry_hit, n_hits: *mut u64,
+                              cuda_stream: *mut c_void) -> c_int;
+    pub fn awry_device_free(index: *const awry_index, replica: c_int, d_ptr: *mut c_void) -> c_int;
+    pub fn awry_device_check(index: *const awry_index, replica: c_int, cuda_stream: *mut c_void) -> c_int;
+    pub fn awry_last_error() -> *const c_char;
+    pub fn awry_version() -> *const c_char;
+}

@@ -252,3 +252,21 @@ def test_ragged_lengths_and_order_preserved(fx, dna, dna_dev, dna_or):
     loc = dna_dev.parallel_locate(qs[:50])
     for i in range(50):
         assert [tuple(h) for h in loc[i]] == dna_or.locate_string(qs[i])
+
+
+def test_cxx_host_mirror_every_kmer(tmp_path, fx):
+    """the C++ mirror of the Rust API (include/awry_b200.hpp), driven like fm_index.rs:612-664"""
+    import subprocess
+    from conftest import ROOT
+    text = fx.gen_text(0, 1847, 0)
+    parts = fx.build_parts(text, 0)
+    idx, txt, exe = str(tmp_path / "n.awry"), str(tmp_path / "n.txt"), str(tmp_path / "mirror")
+    parts.write(idx)
+    open(txt, "wb").write(bytes(text))
+    lib = os.path.join(ROOT, "awry_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cxx_host_mirror.cpp"), "-o", exe, "-L", lib,
+                           "-lawry_b200", f"-Wl,-rpath,{lib}"])
+    out = subprocess.run([exe, idx, txt, "24"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("ok ")
