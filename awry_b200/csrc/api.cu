@@ -677,11 +677,11 @@ void enqueue_search(const awry_index* ix, Replica& r, Workspace* ws, const uint8
   // offsets stay absolute: the kernels subtract the chunk's byte base
   {
     ProfScope p(2, r.device, ws->st);
-    CU(launch_pack(ix->alphabet, ws->d_qbytes - c.b0, ws->d_qoff, nq, ws->d_qwords - (c.b0 >> (ix->alphabet == 0 ? 4 : 3)), ws->d_flag, ws->st));
+    CU(launch_pack(ix->alphabet, ws->d_qbytes - c.b0, ws->d_qoff, nq, ws->d_qwords - 4 * (c.b0 >> packed_unit_shift(ix->alphabet)), ws->d_flag, ws->st));
   }
   {
     ProfScope p(0, r.device, ws->st);
-    CU(launch_search(r.view, ws->d_qwords - (c.b0 >> (ix->alphabet == 0 ? 4 : 3)), ws->d_qoff, nq, mode, ws->d_out, ws->d_defer, g_variant, r.sm_count, ws->st));
+    CU(launch_search(r.view, ws->d_qwords - 4 * (c.b0 >> packed_unit_shift(ix->alphabet)), ws->d_qoff, nq, mode, ws->d_out, ws->d_defer, g_variant, r.sm_count, ws->st));
   }
   CU(cudaMemcpyAsync(ws->h_flag, ws->d_flag, 8, cudaMemcpyDeviceToHost, ws->st));
 }
@@ -1202,18 +1202,18 @@ int awry_count_device(const awry_index* ix, int replica, const uint8_t* d_qbytes
     CU(cudaMemcpyAsync(&ends[1], d_qoff + nq, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (ends[1] < ends[0]) fail(AWRY_ERR_INVALID_ARG, "query offsets are not monotone");
-    const int sh = ix->alphabet == 0 ? 4 : 3;
-    uint64_t words = nq + ((ends[1] >> sh) - (ends[0] >> sh)) + 4;
+    const int sh = packed_unit_shift(ix->alphabet);
+    uint64_t words = 4 * (nq + ((ends[1] >> sh) - (ends[0] >> sh)) + 2) + 32;
     uint64_t* d_qwords = nullptr;  // packed queries, then the deferred-query list
     CU(cudaMallocAsync(reinterpret_cast<void**>(&d_qwords), words * 8 + (nq + 2) * 4, st));
     uint32_t* d_defer = reinterpret_cast<uint32_t*>(d_qwords + words);
     {
       ProfScope p(2, r.device, st);
-      CU(launch_pack(ix->alphabet, d_qbytes, d_qoff, nq, d_qwords - (ends[0] >> sh), r.d_async_flag, st));
+      CU(launch_pack(ix->alphabet, d_qbytes, d_qoff, nq, d_qwords - 4 * (ends[0] >> sh), r.d_async_flag, st));
     }
     {
       ProfScope p(0, r.device, st);
-      CU(launch_search(r.view, d_qwords - (ends[0] >> sh), d_qoff, nq, OUT_COUNT_U64, d_counts, d_defer, g_variant, r.sm_count, st));
+      CU(launch_search(r.view, d_qwords - 4 * (ends[0] >> sh), d_qoff, nq, OUT_COUNT_U64, d_counts, d_defer, g_variant, r.sm_count, st));
     }
     CU(cudaFreeAsync(d_qwords, st));
   });
@@ -1237,20 +1237,20 @@ int awry_locate_device(const awry_index* ix, int replica, const uint8_t* d_qbyte
     CU(cudaMemcpyAsync(&ends[1], d_qoff + nq, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (ends[1] < ends[0]) fail(AWRY_ERR_INVALID_ARG, "query offsets are not monotone");
-    const int sh = ix->alphabet == 0 ? 4 : 3;
+    const int sh = packed_unit_shift(ix->alphabet);
     Workspace* ws = r.acquire();
     try {
-      uint64_t words = nq + ((ends[1] >> sh) - (ends[0] >> sh)) + 4;
+      uint64_t words = 4 * (nq + ((ends[1] >> sh) - (ends[0] >> sh)) + 2) + 32;
       Workspace::grow_dev(ws->d_qwords, ws->d_qwords_cap, size_t(words));
       Workspace::grow_dev(ws->d_out, ws->d_out_cap, size_t(nq) * 8);
       Workspace::grow_dev(ws->d_defer, ws->d_defer_cap, size_t(nq) + 1);
       {
         ProfScope p(2, r.device, st);
-        CU(launch_pack(ix->alphabet, d_qbytes, d_qoff, nq, ws->d_qwords - (ends[0] >> sh), r.d_async_flag, st));
+        CU(launch_pack(ix->alphabet, d_qbytes, d_qoff, nq, ws->d_qwords - 4 * (ends[0] >> sh), r.d_async_flag, st));
       }
       {
         ProfScope p(0, r.device, st);
-        CU(launch_search(r.view, ws->d_qwords - (ends[0] >> sh), d_qoff, nq, OUT_SP_CNT_U32, ws->d_out, ws->d_defer, g_variant, r.sm_count, st));
+        CU(launch_search(r.view, ws->d_qwords - 4 * (ends[0] >> sh), d_qoff, nq, OUT_SP_CNT_U32, ws->d_out, ws->d_defer, g_variant, r.sm_count, st));
       }
       uint64_t n = 0;
       uint64_t* h = locate_chunk_device(ix, r, ws, nq, flags, d_hit_off, &n, st);

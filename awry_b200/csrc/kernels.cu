@@ -309,7 +309,7 @@ __global__ void pack_kernel(const uint8_t* __restrict__ qbytes, const uint64_t* 
                             unsigned long long* first_bad) {
   constexpr int BITS = ALPHA == 0 ? 4 : 8;
   constexpr int SPW = 64 / BITS;
-  constexpr int LOG_SPW = ALPHA == 0 ? 4 : 3;
+  constexpr int UNIT_SHIFT = ALPHA == 0 ? 6 : 5;  // symbols per 4-word (32-B) unit
   constexpr uint32_t SENT = ALPHA == 0 ? DNA_SENTINEL : AMINO_SENTINEL;
   uint64_t gid = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 3;
   uint32_t sub = threadIdx.x & 7;
@@ -322,7 +322,7 @@ __global__ void pack_kernel(const uint8_t* __restrict__ qbytes, const uint64_t* 
       continue;
     }
     uint64_t nwords = (len + SPW - 1) / SPW;
-    uint64_t* dst = qwords + q + (o0 >> LOG_SPW);
+    uint64_t* dst = qwords + 4 * (q + (o0 >> UNIT_SHIFT));
     const uint8_t* src = qbytes + o0;
     bool bad = false;
     for (uint64_t wi = sub; wi < nwords; wi += 8) {
@@ -376,12 +376,12 @@ template <int ALPHA>
 struct QueryStream {
   static constexpr int BITS = ALPHA == 0 ? 4 : 8;
   static constexpr int SPW = 64 / BITS;
-  static constexpr int LOG_SPW = ALPHA == 0 ? 4 : 3;
+  static constexpr int UNIT_SHIFT = ALPHA == 0 ? 6 : 5;
   uint64_t w, wnext;
   uint32_t widx;    // index of the word held in wnext
   uint32_t inword;
   __device__ __forceinline__ void open(const uint64_t* __restrict__ qwords, uint32_t q, uint64_t o0) {
-    widx = q + uint32_t(o0 >> LOG_SPW) + 1;
+    widx = 4 * (q + uint32_t(o0 >> UNIT_SHIFT)) + 1;
     w = __ldg(qwords + (widx - 1));
     wnext = __ldg(qwords + widx);  // buffer is padded
     inword = 0;
@@ -635,21 +635,39 @@ static cudaError_t launch_search_dna(const IndexView& ix, const uint64_t* d_qwor
 // Queries holding an ambiguity symbol (N) are handed to the scalar kernel through `defer`
 // (defer[0] = count, then the query numbers), which keeps this kernel's register budget small.
 // Same persistent-group refill as above.
-__device__ __forceinline__ uint32_t pair_partial_rank(const u32x8& x, uint32_t sub, uint32_t local,
-                                                      uint32_t pair, uint32_t cnt_lane, uint32_t cnt_word) {
-  uint32_t r = 0;
-  if (sub < 3) {
-    uint32_t m = ~x.v[4];
+// low `n` bits set, n clamped to [0, 32] (BMSK)
+__device__ __forceinline__ uint32_t low_mask(int n) {
+  uint32_t m, len = uint32_t(n < 0 ? 0 : n);
+  asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(m) : "r"(0u), "r"(len));
+  return m;
+}
+
+// Which lane slice / 32-bit word of a pair block holds the count of pair p (see layout.cuh):
+// p 0-2 -> slice 0, 3-5 -> 1, 6-8 -> 2 (words 5..7), 9-15 -> slice 3 (words 0..6).
+__device__ __forceinline__ uint32_t pair_count_lane(uint32_t p) {
+  constexpr uint32_t LUT = (1u << 6) | (1u << 8) | (1u << 10) | (2u << 12) | (2u << 14) | (2u << 16) |
+                           (3u << 18) | (3u << 20) | (3u << 22) | (3u << 24) | (3u << 26) | (3u << 28) | (3u << 30);
+  return (LUT >> (2 * p)) & 3u;
+}
+
+// One pair block slice in registers: the rows of this lane's 32-row chunk that hold `pair`
+// (0 for slice 3) and this lane's share of the block-start count (0 unless it owns the slot).
+struct PairSlice {
+  uint32_t match, count;
+};
+__device__ __forceinline__ PairSlice pair_slice(const u32x8& x, uint32_t sub, uint32_t pair) {
+  PairSlice r;
+  uint32_t m = ~x.v[4];
 #pragma unroll
-    for (int p = 0; p < 4; p++) m &= ((pair >> p) & 1u) ? x.v[p] : ~x.v[p];
-    r = __popc(m & chunk_mask(local, sub));
-  }
-  if (sub == cnt_lane) {
-    uint32_t c = x.v[0];
-#pragma unroll
-    for (int i = 1; i < 8; i++) c = cnt_word == uint32_t(i) ? x.v[i] : c;
-    r += c;
-  }
+  for (int p = 0; p < 4; p++) m &= ((pair >> p) & 1u) ? x.v[p] : ~x.v[p];
+  r.match = sub < 3 ? m : 0u;
+  const uint32_t lane = pair_count_lane(pair);
+  const uint32_t word = lane < 3 ? pair + 5 - 3 * lane : pair - 9;
+  const uint32_t t0 = (word & 1) ? x.v[1] : x.v[0], t1 = (word & 1) ? x.v[3] : x.v[2];
+  const uint32_t t2 = (word & 1) ? x.v[5] : x.v[4], t3 = (word & 1) ? x.v[7] : x.v[6];
+  const uint32_t u0 = (word & 2) ? t1 : t0, u1 = (word & 2) ? t3 : t2;
+  const uint32_t c = (word & 4) ? u1 : u0;
+  r.count = sub == lane ? c : 0u;
   return r;
 }
 
@@ -659,112 +677,140 @@ __global__ void __launch_bounds__(TPB, MINB)
                            const uint64_t* __restrict__ qoff, uint64_t nq, void* __restrict__ out,
                            uint32_t* __restrict__ defer) {
   constexpr int LANES = 4;
-  constexpr uint32_t NONE = 0xffffffffu;
+  constexpr uint32_t NONE = 0xffffffffu, FULL = 0xffffffffu;
+  // The group's packed query is staged in shared memory (a 16-word ring = 256 symbols, refilled
+  // 8 words at a time for longer queries): one aligned 128-B global read per query instead of one
+  // 8-byte read per 16 symbols, which matters because random LINE REQUESTS are the scarce resource.
+  __shared__ uint64_t s_q[TPB / LANES][16];
   const uint32_t sub = threadIdx.x & 3;
-  const uint32_t gmask = 0xfu << ((threadIdx.x & 31) - sub);
+  const uint32_t gbase = (threadIdx.x & 31) - sub;
+  const uint32_t gmask = 0xfu << gbase;
+  uint64_t* const ring = s_q[threadIdx.x / LANES];
+  const uint32_t nq32 = uint32_t(nq);
   uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;  // next query of this group
   uint32_t cur = NONE;                                            // query in flight
-  uint32_t sp = 1, ep = 0, left = 0;
-  QueryStream<0> qs;
-  qs.w = qs.wnext = 0;
-  qs.widx = 0;
-  qs.inword = 0;
+  uint32_t sp = 1, ep = 0, left = 0, len = 0;
+  uint32_t ubase = 0;  // word index of the query's packed symbols
+  uint32_t wlim = 8;   // word index at which the ring slides by 8 words
 
+  // Every lane of the warp runs every iteration (the loop exit is a warp vote), so the rank
+  // reduction can use full-mask shuffles; a group whose query ended refills in the same iteration.
   for (;;) {
     if (left == 0 || sp > ep) {
       if (cur != NONE && sub == 0) store_result<MODE>(out, cur, sp, ep);
       cur = NONE;
-      if (q >= uint32_t(nq)) break;
-      cur = q;
-      const uint32_t G = (gridDim.x * blockDim.x) / LANES;
-      q = (q + G < q) ? NONE : q + G;
-      uint64_t o0 = qoff[cur];
-      uint32_t len = uint32_t(qoff[cur + 1] - o0);
-      sp = 1;
-      ep = 0;
       left = 0;
-      if (len != 0) {
-        qs.open(qwords, cur, o0);
-        const uint32_t k = ix.kmer_len;
-        bool clean;
-        if (k != 0 && len >= k) {
-          uint64_t w = qs.w;  // k <= 16 symbols, all inside the first word
-          clean = (w & (0xCCCCCCCCCCCCCCCCull >> (4 * (16 - k)))) == 0;
-          if (clean) {
-            uint64_t idx = 0;
+      if (q < nq32) {
+        cur = q;
+        const uint32_t G = (gridDim.x * blockDim.x) / LANES;
+        q = (q + G < q) ? NONE : q + G;
+        uint64_t ov = qoff[cur + (sub & 1)];  // lanes 0/1 fetch both ends with one request
+        uint64_t o0 = __shfl_sync(gmask, ov, gbase), o1 = __shfl_sync(gmask, ov, gbase + 1);
+        len = uint32_t(o1 - o0);
+        sp = 1;
+        ep = 0;
+        if (len != 0) {
+          ubase = 4 * (cur + uint32_t(o0 >> 6));
+          const uint32_t nwords = (len + 15) >> 4;
+          __syncwarp(gmask);
+          if (4 * sub < nwords) {
+            u32x8 t = ldg256(qwords + ubase + 4 * sub);
+#pragma unroll
+            for (int j = 0; j < 4; j++) ring[4 * sub + j] = uint64_t(t.v[2 * j]) | (uint64_t(t.v[2 * j + 1]) << 32);
+          }
+          __syncwarp(gmask);
+          wlim = 8;
+          const uint32_t k = ix.kmer_len;
+          const uint64_t w = ring[0];
+          bool clean;
+          if (k != 0 && len >= k) {
+            clean = (w & (0xCCCCCCCCCCCCCCCCull >> (4 * (16 - k)))) == 0;  // k <= 16: inside word 0
+            if (clean) {
+              uint64_t idx = 0;
 #pragma unroll 1
-            for (uint32_t j = 0; j < k; j++) {
-              idx |= ((w >> (4 * j)) & 3ull) << (2 * j);
-              qs.next(qwords);
+              for (uint32_t j = 0; j < k; j++) idx |= ((w >> (4 * j)) & 3ull) << (2 * j);
+              uint2 r = __ldg(ix.table + idx);
+              sp = r.x;
+              ep = r.y;
+              left = len - k;
             }
-            uint2 r = __ldg(ix.table + idx);
-            sp = r.x;
-            ep = r.y;
-            left = len - k;
+          } else {
+            uint32_t c = uint32_t(w) & 15u;
+            clean = c < 4;
+            if (clean) {
+              sp = ix.c_lo[c];
+              ep = ix.c_hi[c];
+              left = len - 1;
+            }
           }
-        } else {
-          uint32_t c = qs.next(qwords);
-          clean = c < 4;
-          if (clean) {
-            sp = ix.c_lo[c];
-            ep = ix.c_hi[c];
-            left = len - 1;
+          if (!clean) {  // hand the whole query to the scalar kernel
+            if (sub == 0) defer[1 + atomicAdd(defer, 1u)] = cur;
+            cur = NONE;
           }
-        }
-        if (!clean) {  // hand the whole query to the scalar kernel
-          if (sub == 0) defer[1 + atomicAdd(defer, 1u)] = cur;
-          cur = NONE;
         }
       }
-      continue;
+    }
+    if (__all_sync(FULL, cur == NONE && q >= nq32)) break;
+
+    bool active = left != 0 && sp <= ep;  // (a query that just ended is stored next iteration)
+    const uint32_t pos = len - left;      // search-order index of the next symbol
+    if (active && (pos >> 4) >= wlim) {   // long query: bring in words [wlim+8, wlim+16)
+      __syncwarp(gmask);
+      if (sub < 2) {
+        u32x8 t = ldg256(qwords + ubase + wlim + 8 + 4 * sub);  // in bounds: buffer padded by 32 words
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          ring[(wlim + 8 + 4 * sub + j) & 15] = uint64_t(t.v[2 * j]) | (uint64_t(t.v[2 * j + 1]) << 32);
+      }
+      __syncwarp(gmask);
+      wlim += 8;
+    }
+    const uint32_t c1 = uint32_t(ring[(pos >> 4) & 15] >> (4 * (pos & 15))) & 15u;
+    const uint32_t c2 = uint32_t(ring[((pos + 1) >> 4) & 15] >> (4 * ((pos + 1) & 15))) & 15u;
+    const bool two = left >= 2;
+    if (active && (two ? (c1 | c2) : c1) >= 4) {  // ambiguity symbol ahead: scalar kernel's job
+      if (sub == 0) defer[1 + atomicAdd(defer, 1u)] = cur;
+      cur = NONE;
+      left = 0;
+      active = false;
     }
     const uint32_t pa = sp - 1, pb = ep;
-    const uint32_t c1 = uint32_t(qs.w) & 15u;
-    uint32_t ra, rb, base;
-    if (left >= 2) {
-      const uint32_t c2 = qs.inword == 15 ? (uint32_t(qs.wnext) & 15u) : (uint32_t(qs.w >> 4) & 15u);
-      if ((c1 | c2) >= 4) {
-        if (sub == 0) defer[1 + atomicAdd(defer, 1u)] = cur;
-        cur = NONE;
-        left = 0;
-        continue;
+    uint32_t ra = 0, rb = 0, base = 0;
+    if (active) {
+      if (two) {
+        const uint32_t pair = 4 * c1 + c2;
+        const uint32_t ba = __umulhi(pa, 0xAAAAAAABu) >> 6, bb = __umulhi(pb, 0xAAAAAAABu) >> 6;  // / 96
+        const int na = int(pa - ba * PAIR_ROWS_PER_BLOCK) + 1 - int(32 * sub);
+        const int nb = int(pb - bb * PAIR_ROWS_PER_BLOCK) + 1 - int(32 * sub);
+        u32x8 x = ldg256(ix.pair_blocks + size_t(ba) * PAIR_BLOCK_UINT4 + 2 * sub);
+        PairSlice s = pair_slice(x, sub, pair);
+        ra = __popc(s.match & low_mask(na)) + s.count;
+        if (bb != ba) {  // the interval straddles two blocks (only while it is still wide)
+          x = ldg256(ix.pair_blocks + size_t(bb) * PAIR_BLOCK_UINT4 + 2 * sub);
+          s = pair_slice(x, sub, pair);
+        }
+        rb = __popc(s.match & low_mask(nb)) + s.count;
+        base = ix.c2[pair];
+      } else {
+        const uint32_t ba = pa >> 7, bb = pb >> 7;
+        LaneChunks<4> y;
+        y.load(ix.blocks + size_t(ba) * DNA_BLOCK_UINT4, sub);
+        const uint32_t m0 = (c1 & 1) ? ~0u : 0u, m1 = (c1 & 2) ? ~0u : 0u;
+        ra = dna_partial_rank<4>(y, sub, pa & 127, c1, m0, m1);
+        if (bb != ba) y.load(ix.blocks + size_t(bb) * DNA_BLOCK_UINT4, sub);
+        rb = dna_partial_rank<4>(y, sub, pb & 127, c1, m0, m1);
+        base = ix.c_lo[c1];
       }
-      qs.next(qwords);
-      qs.next(qwords);
-      left -= 2;
-      const uint32_t pair = 4 * c1 + c2;
-      const uint32_t cnt_lane = pair < 9 ? pair / 3 : 3;
-      const uint32_t cnt_word = pair < 9 ? 5 + pair % 3 : pair - 9;
-      const uint32_t ba = __umulhi(pa, 0xAAAAAAABu) >> 6, bb = __umulhi(pb, 0xAAAAAAABu) >> 6;  // / 96
-      u32x8 x = ldg256(ix.pair_blocks + size_t(ba) * PAIR_BLOCK_UINT4 + 2 * sub);
-      ra = pair_partial_rank(x, sub, pa - ba * PAIR_ROWS_PER_BLOCK, pair, cnt_lane, cnt_word);
-      if (bb != ba) x = ldg256(ix.pair_blocks + size_t(bb) * PAIR_BLOCK_UINT4 + 2 * sub);
-      rb = pair_partial_rank(x, sub, pb - bb * PAIR_ROWS_PER_BLOCK, pair, cnt_lane, cnt_word);
-      base = ix.c2[pair];
-    } else {
-      if (c1 >= 4) {
-        if (sub == 0) defer[1 + atomicAdd(defer, 1u)] = cur;
-        cur = NONE;
-        left = 0;
-        continue;
-      }
-      qs.next(qwords);
-      left = 0;
-      const uint32_t ba = pa >> 7, bb = pb >> 7;
-      LaneChunks<4> y;
-      y.load(ix.blocks + size_t(ba) * DNA_BLOCK_UINT4, sub);
-      const uint32_t m0 = (c1 & 1) ? ~0u : 0u, m1 = (c1 & 2) ? ~0u : 0u;
-      ra = dna_partial_rank<4>(y, sub, pa & 127, c1, m0, m1);
-      if (bb != ba) y.load(ix.blocks + size_t(bb) * DNA_BLOCK_UINT4, sub);
-      rb = dna_partial_rank<4>(y, sub, pb & 127, c1, m0, m1);
-      base = ix.c_lo[c1];
     }
-    ra += __shfl_xor_sync(gmask, ra, 1);
-    rb += __shfl_xor_sync(gmask, rb, 1);
-    ra += __shfl_xor_sync(gmask, ra, 2);
-    rb += __shfl_xor_sync(gmask, rb, 2);
-    sp = base + ra;
-    ep = base + rb - 1;
+    ra += __shfl_xor_sync(FULL, ra, 1);
+    rb += __shfl_xor_sync(FULL, rb, 1);
+    ra += __shfl_xor_sync(FULL, ra, 2);
+    rb += __shfl_xor_sync(FULL, rb, 2);
+    if (active) {
+      sp = base + ra;
+      ep = base + rb - 1;
+      left -= two ? 2 : 1;
+    }
   }
 }
 

@@ -8,11 +8,13 @@
 namespace awry {
 
 // packed query stream: DNA 4 bits / symbol (16 per u64), amino 8 bits / symbol (8 per u64);
-// symbols are stored in SEARCH order (last query character first).  Query q starts at word
-// q + (qoff[q] >> log2(symbols per word)); the buffer needs packed_words(...) words (4 of them padding).
+// symbols are stored in SEARCH order (last query character first).  Every query starts on a
+// 32-byte boundary so a lane group can stage it with aligned LDG.256: query q starts at word
+// 4 * (q + (qoff[q] >> 6))  (DNA; amino: >> 5) -- monotone and overlap-free without a scan.
 inline uint64_t packed_words(int alphabet, uint64_t nq, uint64_t total_bytes) {
-  return nq + (total_bytes >> (alphabet == 0 ? 4 : 3)) + 4;
+  return 4 * (nq + (total_bytes >> (alphabet == 0 ? 6 : 5)) + 2) + 32;
 }
+inline int packed_unit_shift(int alphabet) { return alphabet == 0 ? 6 : 5; }
 
 enum SearchOut { OUT_COUNT_U64 = 0, OUT_RANGE_U64 = 1, OUT_SP_CNT_U32 = 2 };
 
