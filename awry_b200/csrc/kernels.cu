@@ -303,14 +303,19 @@ cudaError_t build_pair_index(const IndexView& ix, uint4* d_pair_blocks, uint32_t
 // ------------------------------------------------------------------ query packing prepass
 
 // 8 lanes per query; lane t packs words t, t+8, ...  Flags the first empty / sentinel query.
+// The ASCII table is copied to shared memory first: per-lane indices differ, and divergent
+// constant-bank reads would serialise.
 template <int ALPHA>
-__global__ void pack_kernel(const uint8_t* __restrict__ qbytes, const uint64_t* __restrict__ qoff,
-                            uint64_t nq, uint64_t* __restrict__ qwords,
-                            unsigned long long* first_bad) {
+__global__ void __launch_bounds__(256)
+    pack_kernel(const uint8_t* __restrict__ qbytes, const uint64_t* __restrict__ qoff, uint64_t nq,
+                uint64_t* __restrict__ qwords, unsigned long long* first_bad) {
   constexpr int BITS = ALPHA == 0 ? 4 : 8;
   constexpr int SPW = 64 / BITS;
   constexpr int UNIT_SHIFT = ALPHA == 0 ? 6 : 5;  // symbols per 4-word (32-B) unit
   constexpr uint32_t SENT = ALPHA == 0 ? DNA_SENTINEL : AMINO_SENTINEL;
+  __shared__ uint8_t lut[256];
+  lut[threadIdx.x] = c_ascii_to_dsym[ALPHA][threadIdx.x];
+  __syncthreads();
   uint64_t gid = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 3;
   uint32_t sub = threadIdx.x & 7;
   uint64_t ngroups = (gridDim.x * uint64_t(blockDim.x)) >> 3;
@@ -328,13 +333,22 @@ __global__ void pack_kernel(const uint8_t* __restrict__ qbytes, const uint64_t* 
     for (uint64_t wi = sub; wi < nwords; wi += 8) {
       uint64_t word = 0;
       uint64_t first = wi * SPW;  // search-order index of this word's first symbol
+      if (first + SPW <= len) {
+        const uint8_t* p = src + (len - first - SPW);  // the SPW bytes of this word, ascending
 #pragma unroll
-      for (int t = 0; t < SPW; t++) {
-        uint64_t si = first + t;
-        if (si < len) {
-          uint32_t d = c_ascii_to_dsym[ALPHA][src[len - 1 - si]];
+        for (int t = 0; t < SPW; t++) {
+          uint32_t d = lut[p[SPW - 1 - t]];
           bad |= d == SENT;
           word |= uint64_t(d) << (BITS * t);
+        }
+      } else {
+        for (int t = 0; t < SPW; t++) {
+          uint64_t si = first + t;
+          if (si < len) {
+            uint32_t d = lut[src[len - 1 - si]];
+            bad |= d == SENT;
+            word |= uint64_t(d) << (BITS * t);
+          }
         }
       }
       dst[wi] = word;

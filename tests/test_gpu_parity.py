@@ -270,3 +270,25 @@ def test_cxx_host_mirror_every_kmer(tmp_path, fx):
     out = subprocess.run([exe, idx, txt, "24"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.startswith("ok ")
+
+
+def test_multi_replica_in_one_process(fx, dna, dna_or):
+    """awry_index_from_parts with several devices: replica 0 is cloned over NVLink, batches are split
+    by query bytes across replicas (one host thread each), results come back in input order."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from awry_b200 import fm_index as f
+    devs = list(range(min(n, 4)))
+    qb, qo = mixed_queries(fx, dna.text, 30_001, 36, seed=31)
+    with device_from_parts(dna, devices=devs) as ix:
+        assert ix.n_devices() == len(devs)
+        got = ix.count_packed(qb, qo)
+        want, _ = dna_or.count_batch(qb, qo)
+        assert np.array_equal(got, want)
+        off, hits = ix.locate_packed(qb, qo)
+        woff, whits, _ = dna_or.locate_batch(qb, qo)
+        assert np.array_equal(off, woff) and np.array_equal(hits, whits)
+        few = f.pack_queries([b"ACGT", b"GGGTTTAA", b"A"])      # fewer queries than 2 x replicas
+        assert np.array_equal(ix.count_packed(*few), dna_or.count_batch(*few)[0])
