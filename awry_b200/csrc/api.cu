@@ -613,8 +613,10 @@ void parallel_memcpy(void* dst, const void* src, size_t n) {
   for (auto& x : th) x.join();
 }
 
-constexpr uint64_t CHUNK_MAX_Q = 4u << 20;        // queries per pipeline chunk
-constexpr uint64_t CHUNK_MAX_BYTES = 512u << 20;  // query bytes per pipeline chunk
+// Pipeline chunk: small enough that the exposed first upload / last kernel are a few percent of a
+// 10 M-read batch, large enough (~0.9 M reads) to keep the persistent search grid busy.
+constexpr uint64_t CHUNK_MAX_Q = 1u << 20;        // queries per pipeline chunk
+constexpr uint64_t CHUNK_MAX_BYTES = 128u << 20;  // query bytes per pipeline chunk
 
 struct Chunk {
   uint64_t q0, q1, b0, b1;

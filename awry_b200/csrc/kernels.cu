@@ -938,14 +938,54 @@ __device__ __forceinline__ void map_location(const IndexView& ix, uint64_t loc, 
   out2[1] = loc - __ldg(ix.seq_starts + lo);
 }
 
-// One thread per hit, persistent with lane refill: a lane whose walk ends takes the next hit
-// (h += stride), so the geometric walk lengths (rows, not text positions, are sampled --
-// compressed_suffix_array.rs:109-111) do not idle the rest of the warp.
-// hit h -> query via binary search over the CSR offsets, row = sp[q] + (h - off[q]).
-template <int ALPHA, bool MAP>
+// Pass 2a: expand the CSR (query -> hit range) into one BWT row per hit, written into the low
+// 32 bits of each output slot (the walk overwrites the slot with the result).  A lane writes the
+// first 8 rows of its query; longer intervals are written by the whole warp, so a query with 10^5
+// hits costs ~3000 coalesced warp iterations instead of serialising one thread.
 __global__ void __launch_bounds__(256)
-    walk_kernel(IndexView ix, const uint2* __restrict__ sp_cnt, const uint64_t* __restrict__ hit_off,
-                uint64_t nq, uint64_t n_hits, uint64_t* __restrict__ out) {
+    expand_rows_kernel(const uint2* __restrict__ sp_cnt, const uint64_t* __restrict__ hit_off, uint64_t nq,
+                       uint32_t* __restrict__ out32, uint32_t slot_u32) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5;
+  const uint64_t nwarps = (gridDim.x * uint64_t(blockDim.x)) >> 5;
+  for (uint64_t base = warp * 32; base < nq; base += nwarps * 32) {
+    uint64_t q = base + lane;
+    uint32_t sp = 0, cnt = 0;
+    uint64_t off = 0;
+    if (q < nq) {
+      uint2 r = sp_cnt[q];
+      sp = r.x;
+      cnt = r.y;
+      off = hit_off[q];
+    }
+    uint32_t small = cnt < 8 ? cnt : 8;
+    for (uint32_t i = 0; i < small; i++) out32[(off + i) * slot_u32] = sp + i;
+    uint32_t big = __ballot_sync(0xffffffffu, cnt > 8);
+    while (big) {
+      int L = __ffs(big) - 1;
+      big &= big - 1;
+      uint32_t s = __shfl_sync(0xffffffffu, sp, L), c = __shfl_sync(0xffffffffu, cnt, L);
+      uint64_t o = __shfl_sync(0xffffffffu, off, L);
+      for (uint32_t i = 8 + lane; i < c; i += 32) out32[(o + i) * slot_u32] = s + i;
+    }
+  }
+}
+
+__device__ __forceinline__ void finish_hit(const IndexView& ix, uint32_t row, uint32_t steps, uint64_t* slot,
+                                           bool map) {
+  uint64_t loc = (sa_sample(ix, row) + steps) % ix.bwt_len;  // fm_index.rs:533-534
+  if (map)
+    map_location(ix, loc, slot);
+  else
+    slot[0] = loc;
+}
+
+// Pass 2b, any alphabet: one thread per hit, persistent with lane refill -- a lane whose walk ends
+// takes the next hit, so the geometric walk lengths (rows, not text positions, are sampled:
+// compressed_suffix_array.rs:109-111) do not idle the rest of the warp.
+template <int ALPHA, bool MAP>
+__global__ void __launch_bounds__(256) walk_scalar_kernel(IndexView ix, uint64_t n_hits, uint64_t* __restrict__ out) {
+  constexpr int SLOT = MAP ? 2 : 1;
   const uint64_t stride = gridDim.x * uint64_t(blockDim.x);
   uint64_t h = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
   uint64_t cur = 0;
@@ -956,25 +996,12 @@ __global__ void __launch_bounds__(256)
       if (h >= n_hits) break;
       cur = h;
       h += stride;
-      // largest q with hit_off[q] <= cur
-      uint64_t lo = 0, hi = nq - 1;
-      while (lo < hi) {
-        uint64_t mid = (lo + hi + 1) >> 1;
-        if (__ldg(hit_off + mid) <= cur)
-          lo = mid;
-        else
-          hi = mid - 1;
-      }
-      row = __ldg(&sp_cnt[lo].x) + uint32_t(cur - __ldg(hit_off + lo));
+      row = uint32_t(out[SLOT * cur]);
       steps = 0;
       have = true;
     }
     if (row_is_sampled(ix, row)) {
-      uint64_t loc = (sa_sample(ix, row) + steps) % ix.bwt_len;  // fm_index.rs:533-534
-      if (MAP)
-        map_location(ix, loc, out + 2 * cur);
-      else
-        out[cur] = loc;
+      finish_hit(ix, row, steps, out + SLOT * cur, MAP);
       have = false;
       continue;
     }
@@ -983,23 +1010,81 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Pass 2b, nucleotide: 2 lanes per hit, each LDG.256 half of the 64-B block, so one LF step is ONE
+// line request (the scalar walk issues four LDG.128 to the same line).  The lane holding the row's
+// chunk extracts the BWT symbol and broadcasts it; both lanes rank their two chunks; xor-shuffle.
+// Warp-convergent loop (exit by vote) so the shuffles use the full mask.
+template <bool MAP>
+__global__ void __launch_bounds__(256) walk_dna_kernel(IndexView ix, uint64_t n_hits, uint64_t* __restrict__ out) {
+  constexpr int SLOT = MAP ? 2 : 1;
+  constexpr uint32_t FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31, sub = lane & 1, gbase = lane - sub;
+  const uint64_t stride = (gridDim.x * uint64_t(blockDim.x)) >> 1;
+  uint64_t h = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 1;
+  uint64_t cur = 0;
+  uint32_t row = 0, steps = 0;
+  bool have = false;
+  for (;;) {
+    if (!have && h < n_hits) {
+      cur = h;
+      h += stride;
+      row = uint32_t(out[SLOT * cur]);
+      steps = 0;
+      have = true;
+    }
+    if (__all_sync(FULL, !have)) break;
+    if (have && row_is_sampled(ix, row)) {
+      if (sub == 0) finish_hit(ix, row, steps, out + SLOT * cur, MAP);
+      have = false;
+    }
+    const uint32_t blk = row >> 7, l = row & 127;
+    LaneChunks<2> x;
+    x.c[0] = x.c[1] = make_uint4(0, 0, 0, 0);
+    if (have) x.load(ix.blocks + size_t(blk) * DNA_BLOCK_UINT4, sub);
+    const uint4 ch = (l & 32) ? x.c[1] : x.c[0];
+    const uint32_t t = l & 31;
+    uint32_t c = ((ch.x >> t) & 1u) | (((ch.y >> t) & 1u) << 1) | (((ch.z >> t) & 1u) << 2);
+    c = __shfl_sync(FULL, c, gbase + (l >> 6));  // from the lane that owns chunk l/32
+    uint32_t r = 0;
+    if (have && c < 4) r = dna_partial_rank<2>(x, sub, l, c, (c & 1) ? ~0u : 0u, (c & 2) ? ~0u : 0u);
+    r += __shfl_xor_sync(FULL, r, 1);
+    if (have) {
+      if (c >= uint32_t(DNA_SENTINEL))
+        row = 0;  // the '$' row: fm_index.rs:587-589
+      else if (c == uint32_t(DNA_N))
+        row = lf_backstep<0>(ix, row);  // rare: scalar step
+      else
+        row = ix.c_lo[c] + r - 1;
+      steps++;
+    }
+  }
+}
+
 cudaError_t launch_walk(const IndexView& ix, const uint2* d_sp_cnt, const uint64_t* d_hit_off,
                         uint64_t nq, uint64_t n_hits, uint64_t* d_hits_pairs, uint64_t* d_locs,
                         int sm_count, cudaStream_t s) {
   if (n_hits == 0 || nq == 0) return cudaSuccess;
-  unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (n_hits + 255) / 256)));
-  bool map = d_hits_pairs != nullptr;
+  const bool map = d_hits_pairs != nullptr;
   uint64_t* out = map ? d_hits_pairs : d_locs;
+  {
+    unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (nq + 255) / 256)));
+    expand_rows_kernel<<<grid, 256, 0, s>>>(d_sp_cnt, d_hit_off, nq, reinterpret_cast<uint32_t*>(out), map ? 4u : 2u);
+    COUNT_LAUNCH();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
   if (ix.alphabet == 0) {
+    unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (2 * n_hits + 255) / 256)));
     if (map)
-      walk_kernel<0, true><<<grid, 256, 0, s>>>(ix, d_sp_cnt, d_hit_off, nq, n_hits, out);
+      walk_dna_kernel<true><<<grid, 256, 0, s>>>(ix, n_hits, out);
     else
-      walk_kernel<0, false><<<grid, 256, 0, s>>>(ix, d_sp_cnt, d_hit_off, nq, n_hits, out);
+      walk_dna_kernel<false><<<grid, 256, 0, s>>>(ix, n_hits, out);
   } else {
+    unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (n_hits + 255) / 256)));
     if (map)
-      walk_kernel<1, true><<<grid, 256, 0, s>>>(ix, d_sp_cnt, d_hit_off, nq, n_hits, out);
+      walk_scalar_kernel<1, true><<<grid, 256, 0, s>>>(ix, n_hits, out);
     else
-      walk_kernel<1, false><<<grid, 256, 0, s>>>(ix, d_sp_cnt, d_hit_off, nq, n_hits, out);
+      walk_scalar_kernel<1, false><<<grid, 256, 0, s>>>(ix, n_hits, out);
   }
   COUNT_LAUNCH();
   return cudaGetLastError();

@@ -321,7 +321,7 @@ def main():
     tr = traffic_from_profiles()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": tr["dram_bytes_per_launch"] if tr else None, "peak_source": peak_src,
-                "kernel": "search_dna_kernel", "kernel_ms": search_ms,
+                "kernel": "search_dna_pair_kernel", "kernel_ms": search_ms,
                 "kernel_share_of_step": prof["search_ms"] / ms_total,
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "lf_steps_per_s": nq * (L - a.kmer) / (search_ms * 1e-3)}

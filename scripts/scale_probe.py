@@ -26,7 +26,7 @@ def main():
     ap.add_argument("--variants", default="8,2")
     ap.add_argument("--bps", default="0")
     ap.add_argument("--check", type=int, default=20000)
-    ap.add_argument("--locate-nq", type=int, default=1_000_000)
+    ap.add_argument("--locate-nq", type=int, default=10_000_000)
     ap.add_argument("--locate-qlen", type=int, default=50)
     a = ap.parse_args()
     t0 = time.time()
