@@ -234,6 +234,24 @@ void fx_gen_substring_queries(const uint8_t* text, uint64_t n, uint64_t nq, uint
   for (auto& x : th) x.join();
 }
 
+// text[pos .. pos+len) of the synthetic text of (alphabet, seed) for each listed position, without
+// materialising the text: lets full-size tests verify located positions.
+void fx_gen_text_windows(int alphabet, uint64_t seed, const uint64_t* positions, uint64_t n, uint64_t len,
+                         uint8_t* out) {
+  unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; t++)
+    th.emplace_back([=] {
+      uint64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+      for (uint64_t i = lo; i < hi; i++)
+        for (uint64_t k = 0; k < len; k++) {
+          uint64_t r = rnd_at(seed, positions[i] + k);
+          out[i * len + k] = alphabet == 0 ? uint8_t(DNA4[r >> 62]) : uint8_t(AMINO20[((r >> 32) * 20) >> 32]);
+        }
+    });
+  for (auto& x : th) x.join();
+}
+
 uint64_t fx_num_blocks(uint64_t bwt_len) { return (bwt_len + 255) / 256; }
 uint64_t fx_block_words(int alphabet) { return shape_of(alphabet).block_words; }
 uint64_t fx_sa_words(uint64_t bwt_len, uint64_t ratio) { return sa_word_len(bwt_len, ratio); }

@@ -33,6 +33,8 @@ def lib():
         L.fx_gen_text.restype = None
         L.fx_gen_substring_queries.argtypes = [vp, u64, u64, u64, u64, vp, vp]
         L.fx_gen_substring_queries.restype = None
+        L.fx_gen_text_windows.argtypes = [C.c_int, u64, vp, u64, u64, vp]
+        L.fx_gen_text_windows.restype = None
         for name in ("fx_num_blocks",):
             getattr(L, name).argtypes = [u64]
             getattr(L, name).restype = u64
@@ -67,6 +69,14 @@ def gen_substring_queries(text, nq, qlen, seed):
                                    pos.ctypes.data)
     qoff = np.arange(nq + 1, dtype=np.uint64) * np.uint64(qlen)
     return qbytes, qoff, pos
+
+
+def gen_text_windows(alphabet, seed, positions, length):
+    """text[p : p+length] of the synthetic text for every p in positions -> uint8[len(positions), length]"""
+    positions = np.ascontiguousarray(positions, dtype=np.uint64)
+    out = np.empty((len(positions), length), dtype=np.uint8)
+    lib().fx_gen_text_windows(alphabet, seed, positions.ctypes.data, len(positions), length, out.ctypes.data)
+    return out
 
 
 class Parts:

@@ -58,7 +58,7 @@ def test_kernels_are_sm100a_native():
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in out.stdout
     sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-    assert "search_dna_kernel" in sass and "walk_kernel" in sass
+    assert "search_dna_pair_kernel" in sass and "walk_dna_kernel" in sass
     assert re.search(r"LDG\.E\S*\.256", sass) and "POPC" in sass and "SHFL.BFLY" in sass
 
 
