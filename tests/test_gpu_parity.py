@@ -292,3 +292,32 @@ def test_multi_replica_in_one_process(fx, dna, dna_or):
         assert np.array_equal(off, woff) and np.array_equal(hits, whits)
         few = f.pack_queries([b"ACGT", b"GGGTTTAA", b"A"])      # fewer queries than 2 x replicas
         assert np.array_equal(ix.count_packed(*few), dna_or.count_batch(*few)[0])
+
+
+def test_cfg5_repeat_rich_locate_under_skew(fx, po):
+    """BASELINE cfg 5 (scaled to what the CPU fixture builder sorts in seconds): repeat-rich DNA,
+    SA ratio 32, hit counts from 1 to thousands per query -- exercises the warp-cooperative CSR
+    expansion and the lane-refilling walk under load imbalance."""
+    from fixtures import repeats
+    text, regions = repeats.repeat_rich_text(4_000_000, seed=8)
+    parts = fx.build_parts(text, 0, ratio=32, kmer_len=8)
+    orc = oracle_from_parts(po, parts)
+    qb, qo = repeats.repeat_queries(text, regions, 4000, 50, seed=9)
+    with device_from_parts(parts) as ix:
+        counts = ix.count_packed(qb, qo)
+        want, _ = orc.count_batch(qb, qo)
+        assert np.array_equal(counts, want)
+        assert int(want.max()) >= 1000 and int(want.min()) >= 1 and float(np.median(want)) < 50
+        off, hits = ix.locate_packed(qb, qo)
+        woff, whits, st = orc.locate_batch(qb, qo)
+        assert np.array_equal(off, woff) and np.array_equal(hits, whits)
+        assert st["walk_steps"] / max(1, st["hits"]) > 20          # mean walk ~ ratio - 1
+        soff, shits = ix.locate_packed(qb, qo, sorted_hits=True)
+        woff2, whits2, _ = orc.locate_batch(qb, qo, sorted_hits=True)
+        assert np.array_equal(soff, woff2) and np.array_equal(shits, whits2)
+    # round trip on the biggest query: every located position holds the query
+    i = int(np.argmax(want))
+    q = bytes(qb[50 * i:50 * i + 50])
+    t = bytes(text)
+    lo, hi = int(woff[i]), int(woff[i + 1])
+    assert all(t[int(p):int(p) + 50] == q for p in whits[lo:hi, 1])
