@@ -306,51 +306,87 @@ cudaError_t build_pair_index(const IndexView& ix, uint4* d_pair_blocks, uint32_t
 // The ASCII table is copied to shared memory first: per-lane indices differ, and divergent
 // constant-bank reads would serialise.
 template <int ALPHA>
+__device__ __forceinline__ uint64_t pack_word_bytes(const uint8_t* __restrict__ src, uint32_t len, uint32_t first,
+                                                    const uint8_t* lut, bool& bad) {
+  constexpr int BITS = ALPHA == 0 ? 4 : 8;
+  constexpr int SPW = 64 / BITS;
+  constexpr uint32_t SENT = ALPHA == 0 ? DNA_SENTINEL : AMINO_SENTINEL;
+  uint64_t word = 0;
+#pragma unroll 4
+  for (int t = 0; t < SPW; t++) {
+    uint32_t si = first + t;
+    if (si < len) {
+      uint32_t d = lut[src[len - 1 - si]];
+      bad |= d == SENT;
+      word |= uint64_t(d) << (BITS * t);
+    }
+  }
+  return word;
+}
+
+template <int ALPHA>
 __global__ void __launch_bounds__(256)
     pack_kernel(const uint8_t* __restrict__ qbytes, const uint64_t* __restrict__ qoff, uint64_t nq,
                 uint64_t* __restrict__ qwords, unsigned long long* first_bad) {
-  constexpr int BITS = ALPHA == 0 ? 4 : 8;
-  constexpr int SPW = 64 / BITS;
+  constexpr int SPW = ALPHA == 0 ? 16 : 8;
+  constexpr int LOG_SPW = ALPHA == 0 ? 4 : 3;
   constexpr int UNIT_SHIFT = ALPHA == 0 ? 6 : 5;  // symbols per 4-word (32-B) unit
-  constexpr uint32_t SENT = ALPHA == 0 ? DNA_SENTINEL : AMINO_SENTINEL;
   __shared__ uint8_t lut[256];
   lut[threadIdx.x] = c_ascii_to_dsym[ALPHA][threadIdx.x];
   __syncthreads();
-  uint64_t gid = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 3;
-  uint32_t sub = threadIdx.x & 7;
-  uint64_t ngroups = (gridDim.x * uint64_t(blockDim.x)) >> 3;
-  for (uint64_t q = gid; q < nq; q += ngroups) {
-    uint64_t o0 = qoff[q], o1 = qoff[q + 1];
-    uint64_t len = o1 - o0;
-    if (len == 0 || o1 < o0) {
+  const uint32_t sub = threadIdx.x & 7;
+  const uint64_t ngroups = (gridDim.x * uint64_t(blockDim.x)) >> 3;
+  for (uint64_t q = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 3; q < nq; q += ngroups) {
+    const uint64_t o0 = qoff[q], o1 = qoff[q + 1];
+    if (o1 <= o0 || o1 - o0 >= (1ull << 32)) {  // empty (or absurd) query
       if (sub == 0) atomicMin(first_bad, (unsigned long long)q);
       continue;
     }
-    uint64_t nwords = (len + SPW - 1) / SPW;
-    uint64_t* dst = qwords + 4 * (q + (o0 >> UNIT_SHIFT));
-    const uint8_t* src = qbytes + o0;
+    const uint32_t len = uint32_t(o1 - o0);
+    const uint32_t nwords = (len + SPW - 1) >> LOG_SPW;
+    uint64_t* const dst = qwords + 4 * (q + (o0 >> UNIT_SHIFT));
+    const uint8_t* const src = qbytes + o0;
     bool bad = false;
-    for (uint64_t wi = sub; wi < nwords; wi += 8) {
-      uint64_t word = 0;
-      uint64_t first = wi * SPW;  // search-order index of this word's first symbol
-      if (first + SPW <= len) {
-        const uint8_t* p = src + (len - first - SPW);  // the SPW bytes of this word, ascending
+    for (uint32_t wi = sub; wi < nwords; wi += 8) {
+      const uint32_t first = wi << LOG_SPW;  // search-order index of this word's first symbol
+      uint64_t word;
+      bool done = false;
+      if (ALPHA == 0 && len >= 16) {
+        // 16 ASCII bases -> 16 nibbles without per-byte loads: 4-5 aligned 32-bit loads, funnel
+        // shift to the byte offset, then SIMD-in-register: ((c & 0xDF) >> 1) & 3 maps A,C,T,G to
+        // 0,1,2,3 and x ^ (x >> 1) swaps the last two.  The query's final, partial word reuses the
+        // first 16 bytes of the query and shifts the surplus symbols out.  Any byte that is not
+        // one of ACGT/acgt sends the word down the table path.
+        const uint32_t have = len - first;               // symbols left from `first` on
+        const uint32_t drop = have >= 16 ? 0 : 16 - have;  // surplus symbols of a partial word
+        const uint8_t* p = src + (have >= 16 ? have - 16 : 0);
+        const uint32_t sh = uint32_t(reinterpret_cast<uintptr_t>(p) & 3);
+        const uint32_t* a = reinterpret_cast<const uint32_t*>(p - sh);
+        uint32_t u[5];
 #pragma unroll
-        for (int t = 0; t < SPW; t++) {
-          uint32_t d = lut[p[SPW - 1 - t]];
-          bad |= d == SENT;
-          word |= uint64_t(d) << (BITS * t);
+        for (int j = 0; j < 4; j++) u[j] = __ldg(a + j);
+        u[4] = sh ? __ldg(a + 4) : 0u;  // only when it still overlaps the 16 bytes
+        uint32_t nibs[4];
+        bool clean = true;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          uint32_t w4 = __funnelshift_r(u[j], u[j + 1], 8 * sh);  // bytes 4j .. 4j+3
+          uint32_t rev = __byte_perm(w4, 0, 0x0123);              // search order: last byte first
+          uint32_t up = rev & 0xDFDFDFDFu;
+          uint32_t x4 = (up >> 1) & 0x03030303u;
+          uint32_t c4 = x4 ^ ((x4 >> 1) & 0x01010101u);
+          uint32_t sel = c4 | (c4 >> 4);
+          uint32_t nib = (sel & 0xffu) | ((sel >> 8) & 0xff00u);  // 4 nibbles = 4 codes
+          clean &= up == __byte_perm(0x54474341u, 0, nib);        // "ACGT"[code] per byte
+          nibs[j] = nib;
         }
-      } else {
-        for (int t = 0; t < SPW; t++) {
-          uint64_t si = first + t;
-          if (si < len) {
-            uint32_t d = lut[src[len - 1 - si]];
-            bad |= d == SENT;
-            word |= uint64_t(d) << (BITS * t);
-          }
+        if (clean) {
+          word = (uint64_t(nibs[1] | (nibs[0] << 16)) << 32) | uint64_t(nibs[3] | (nibs[2] << 16));
+          word >>= 4 * drop;
+          done = true;
         }
       }
+      if (!done) word = pack_word_bytes<ALPHA>(src, len, first, lut, bad);
       dst[wi] = word;
     }
     if (bad) atomicMin(first_bad, (unsigned long long)q);
@@ -644,7 +680,8 @@ static cudaError_t launch_search_dna(const IndexView& ix, const uint64_t* d_qwor
 }
 
 // ---- nucleotide pair kernel: 4 lanes per query, two query symbols per 128-B block access ----
-// While at least two symbols remain the group reads ONE pair block (4 x LDG.256) and applies two
+// While at least two symbols remain the group reads ONE pair block (4 x LDG.256; fetching only the
+// sectors a rank needs was measured and is NOT faster -- the line request is the unit of cost) and applies two
 // backward-search steps at once; a lone last symbol uses the 1-step block (4 x LDG.128).
 // Queries holding an ambiguity symbol (N) are handed to the scalar kernel through `defer`
 // (defer[0] = count, then the query numbers), which keeps this kernel's register budget small.
