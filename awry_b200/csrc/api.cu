@@ -807,12 +807,12 @@ uint64_t* locate_chunk_device(const awry_index* ix, Replica& r, Workspace* ws, u
   *n_hits_out = n_hits;
   if (n_hits == 0) return nullptr;
   uint64_t* d_hits = nullptr;
-  CU(cudaMalloc(reinterpret_cast<void**>(&d_hits), n_hits * 16));
+  CU(cudaMallocAsync(reinterpret_cast<void**>(&d_hits), n_hits * 16, st));  // pool: no driver round trip
   try {
     if (flags & AWRY_LOCATE_SORTED) {
       uint64_t *d_locs = nullptr, *d_sorted = nullptr;
-      CU(cudaMalloc(reinterpret_cast<void**>(&d_locs), n_hits * 8));
-      CU(cudaMalloc(reinterpret_cast<void**>(&d_sorted), n_hits * 8));
+      CU(cudaMallocAsync(reinterpret_cast<void**>(&d_locs), n_hits * 8, st));
+      CU(cudaMallocAsync(reinterpret_cast<void**>(&d_sorted), n_hits * 8, st));
       {
         ProfScope p(1, r.device, st);
         CU(launch_walk(r.view, d_sp_cnt, d_hit_off, nq, n_hits, nullptr, d_locs, r.sm_count, st));
@@ -822,15 +822,14 @@ uint64_t* locate_chunk_device(const awry_index* ix, Replica& r, Workspace* ws, u
       Workspace::grow_dev(reinterpret_cast<uint8_t*&>(ws->d_temp), ws->d_temp_cap, t2 + 16);
       CU(sort_hit_segments(d_locs, d_sorted, n_hits, nq, d_hit_off, ws->d_temp, t2, st));
       CU(launch_map_locations(r.view, d_sorted, n_hits, d_hits, st));
-      CU(cudaStreamSynchronize(st));
-      cudaFree(d_locs);
-      cudaFree(d_sorted);
+      cudaFreeAsync(d_locs, st);
+      cudaFreeAsync(d_sorted, st);
     } else {
       ProfScope p(1, r.device, st);
       CU(launch_walk(r.view, d_sp_cnt, d_hit_off, nq, n_hits, d_hits, nullptr, r.sm_count, st));
     }
   } catch (...) {
-    cudaFree(d_hits);
+    cudaFreeAsync(d_hits, st);
     throw;
   }
   return d_hits;
@@ -861,16 +860,16 @@ void locate_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
           cap = std::max<size_t>(size_t(part.n_hits + n_hits), cap * 2);
           void* np = realloc(part.hits, cap * sizeof(awry_hit));
           if (!np) {
-            cudaFree(d_hits);
+            cudaFreeAsync(d_hits, ws->st);
             fail(AWRY_ERR_NOMEM, "out of host memory for %llu hits", (unsigned long long)cap);
           }
           part.hits = static_cast<awry_hit*>(np);
         }
         CU(cudaMemcpyAsync(part.hits + part.n_hits, d_hits, n_hits * 16, cudaMemcpyDeviceToHost, ws->st));
       }
+      if (d_hits) cudaFreeAsync(d_hits, ws->st);
       CU(cudaStreamSynchronize(ws->st));
       g_prof.d2h += (nq + 1) * 8 + n_hits * 16;
-      if (d_hits) cudaFree(d_hits);
       for (uint64_t i = 0; i <= nq; i++) dst_off[i] += part.n_hits;
       part.n_hits += n_hits;
     }
@@ -1274,7 +1273,7 @@ int awry_device_free(const awry_index* ix, int replica, void* d_ptr) {
     if (replica < 0 || size_t(replica) >= ix->reps.size()) fail(AWRY_ERR_INVALID_ARG, "replica out of range");
     if (!d_ptr) return;
     DeviceGuard dg(ix->reps[size_t(replica)]->device);
-    CU(cudaFree(d_ptr));
+    CU(cudaFreeAsync(d_ptr, nullptr));  // came from the stream-ordered pool
   });
 }
 

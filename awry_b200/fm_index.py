@@ -317,10 +317,9 @@ class FmIndex:
         _check(native().awry_locate_batch(self._h, qbytes.ctypes.data, qoff.ctypes.data, nq,
                                           LOCATE_SORTED if sorted_hits else LOCATE_BWT_ORDER,
                                           hit_off.ctypes.data, C.byref(hits), C.byref(n)))
+        arr = np.empty((n.value, 2), dtype=np.uint64)
         if n.value:
-            arr = np.ctypeslib.as_array(C.cast(hits, C.POINTER(C.c_uint64)), shape=(n.value, 2)).copy()
-        else:
-            arr = np.zeros((0, 2), dtype=np.uint64)
+            C.memmove(arr.ctypes.data, hits, n.value * 16)
         native().awry_hits_free(hits)
         return hit_off, arr
 

@@ -42,6 +42,9 @@ def parse_args():
     ap.add_argument("--sa-ratio", type=int, default=8)
     ap.add_argument("--cpu-sample", type=int, default=4_000_000, help="reads timed on the CPU oracle (rank 0, N=1)")
     ap.add_argument("--ref-reads-per-step", type=int, default=1_000_000)
+    ap.add_argument("--locate-reads", type=int, default=1_000_000, help="cfg3: queries of the locate leg")
+    ap.add_argument("--locate-len", type=int, default=50)
+    ap.add_argument("--no-locate", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -290,6 +293,59 @@ def main():
                "ms_per_step": float(t_e.item()) / a.steps * 1e3, "host_buffers": "pinned"}
         assert np.array_equal(out, d_cnt.cpu().numpy().view(np.uint64)), "e2e and device-resident counts differ"
 
+    # ---- secondary metric (BASELINE cfg3): parallel_locate of 1 M x 50-bp queries, same index
+    locate = None
+    if not a.no_locate:
+        nl, ll = a.locate_reads, a.locate_len
+        d_lq = torch.empty(nl * ll, dtype=torch.uint8, device="cuda")
+        fxg.gen_queries_device(0, a.text_len, TEXT_SEED, nl, ll, QUERY_SEED + 1 + 1000 * rank, d_lq.data_ptr())
+        d_loff = torch.arange(0, nl + 1, dtype=torch.int64, device="cuda") * ll
+        d_hoff = torch.zeros(nl + 1, dtype=torch.int64, device="cuda")
+        n_hits = 0
+        for _ in range(2):
+            ptr, n_hits = ix.locate_device(d_lq.data_ptr(), d_loff.data_ptr(), nl, d_hoff.data_ptr(), stream=stream)
+            ix.device_free(ptr)
+        f.profile_enable(True)
+        f.profile_reset()
+        barrier()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for _ in range(a.steps):
+            ptr, n_hits = ix.locate_device(d_lq.data_ptr(), d_loff.data_ptr(), nl, d_hoff.data_ptr(), stream=stream)
+            ix.device_free(ptr)
+        l1.record()
+        barrier()
+        lp = f.profile_get()
+        f.profile_enable(False)
+        t_l = torch.tensor([l0.elapsed_time(l1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_l, op=dist.ReduceOp.MAX)
+        lms = float(t_l.item()) / a.steps
+        # end to end through the C ABI: pinned host queries in, CSR offsets + hits out to the host
+        hl_q = torch.empty(nl * ll, dtype=torch.uint8, pin_memory=True)
+        hl_q.copy_(d_lq)
+        hl_off = torch.empty(nl + 1, dtype=torch.int64, pin_memory=True)
+        hl_off.copy_(d_loff)
+        torch.cuda.synchronize()
+        lqb, lqo = hl_q.numpy(), hl_off.numpy().view(np.uint64)
+        ix.locate_packed(lqb, lqo)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            hoff_h, hits_h = ix.locate_packed(lqb, lqo)
+        dt = (time.perf_counter() - t0) / a.steps
+        t_le = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_le, op=dist.ReduceOp.MAX)
+        walk_ms = lp["walk_ms"] / max(1, lp["walk_launches"])
+        locate = {"workload": f"parallel_locate {nl} x {ll}-bp queries, SA ratio {a.sa_ratio} (cfg3)",
+                  "hits_per_query": n_hits / nl, "hits_per_s": world * n_hits / (lms * 1e-3),
+                  "queries_per_s": world * nl / (lms * 1e-3), "ms_per_step": lms, "walk_kernel_ms": walk_ms,
+                  "search_kernel_ms": lp["search_ms"] / max(1, lp["search_launches"]),
+                  "e2e_hits_per_s": world * len(hits_h) / float(t_le.item()),
+                  "e2e_ms_per_step": float(t_le.item()) * 1e3}
+        del d_lq, d_loff, d_hoff
+
     # ---- CPU baseline + parity + exact algorithmic work (rank 0, N = 1 only)
     cpu_baseline, parity, touches_per_read = None, None, None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -319,12 +375,24 @@ def main():
     search_ms = prof["search_ms"] / max(1, prof["search_launches"])
     achieved = alg_bytes_per_launch / (search_ms * 1e-3) / 1e9
     tr = traffic_from_profiles()
+    gather = None
+    if rank == 0:
+        try:   # the "random-access HBM roofline" of the north star: independent random 128-B reads
+            g_reads, g_gbs = f.bench_random_gather(local_rank, 4 << 30, 128, 4, 400_000_000, 2)
+            accesses = nq * (((L - a.kmer) + 1) // 2 + 1)          # pair steps (+ odd tail) + seed lookup
+            gather = {"granule_bytes": 128, "reads_per_s": g_reads, "gb_per_s": g_gbs,
+                      "kernel_block_reads_per_s": accesses / (search_ms * 1e-3),
+                      "frac_of_random_gather": accesses / (search_ms * 1e-3) / g_reads}
+        except Exception as e:  # noqa: BLE001
+            gather = {"error": str(e)}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": tr["dram_bytes_per_launch"] if tr else None, "peak_source": peak_src,
                 "kernel": "search_dna_pair_kernel", "kernel_ms": search_ms,
                 "kernel_share_of_step": prof["search_ms"] / ms_total,
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch,
-                "lf_steps_per_s": nq * (L - a.kmer) / (search_ms * 1e-3)}
+                "lf_steps_per_s": nq * (L - a.kmer) / (search_ms * 1e-3), "random_gather_roofline": gather,
+                "note": "achieved counts the reference algorithm's bytes (104 B per LF step); the pair index does two "
+                        "LF steps per 128-B block read, so achieved can exceed both `traffic` and the stream peak"}
 
     if rank == 0:
         line = {
@@ -336,7 +404,7 @@ def main():
                        "index": "replicated per GPU; ranks search disjoint batches; no collective on the data path",
                        "setup_s": round(setup_s, 1), "fixture_build_s": phases.get("total")},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": int(prof["launches"]), "parity_vs_oracle_on_sample": parity,
+            "gpu_launches": int(prof["launches"]), "parity_vs_oracle_on_sample": parity, "locate": locate,
         }
         print(json.dumps(line), flush=True)
     ix.close()

@@ -235,9 +235,8 @@ class OracleIndex:
                                   hit_off.ctypes.data, C.byref(hits), C.byref(n),
                                   1 if sorted_hits else 0, n_threads, C.byref(st)):
             raise OracleError(lib().awo_last_error().decode())
+        arr = np.empty((n.value, 2), dtype=np.uint64)
         if n.value:
-            arr = np.ctypeslib.as_array(C.cast(hits, C.POINTER(C.c_uint64)), shape=(n.value, 2)).copy()
-        else:
-            arr = np.zeros((0, 2), dtype=np.uint64)
+            C.memmove(arr.ctypes.data, hits, n.value * 16)
         lib().awo_free_ptr(hits)
         return hit_off, arr, st.as_dict()
