@@ -786,16 +786,16 @@ void for_each_replica_range(const awry_index* ix, const uint64_t* qoff, uint64_t
 
 struct LocatePart {
   std::vector<uint64_t> hit_off;  // local CSR over the replica's queries, size n+1
-  awry_hit* hits = nullptr;       // malloc'd
+  awry_hit* hits = nullptr;       // malloc'd, or the caller's buffer when ext_cap != 0
   uint64_t n_hits = 0;
+  uint64_t ext_cap = 0;           // caller-owned output: capacity in hits (0 = library allocates)
+  uint64_t* ext_off = nullptr;    // caller-owned CSR offsets to fill directly (single replica)
 };
 
-// device-side two-pass locate of a chunk whose queries are already packed on the device.
-// Leaves hit offsets in ws->d_hit_off (nq+1) and returns a fresh device buffer with the hits.
-uint64_t* locate_chunk_device(const awry_index* ix, Replica& r, Workspace* ws, uint64_t nq,
-                              uint32_t flags, uint64_t* d_hit_off, uint64_t* n_hits_out,
-                              cudaStream_t st) {
-  (void)ix;
+// device-side two-pass locate of a chunk whose queries were already searched (ws->d_out holds
+// (sp, count) per query).  Step 1: CSR offsets + hit total (one synchronisation).
+uint64_t locate_chunk_count(Replica& r, Workspace* ws, uint64_t nq, uint64_t* d_hit_off, cudaStream_t st) {
+  (void)r;
   const uint2* d_sp_cnt = reinterpret_cast<const uint2*>(ws->d_out);
   size_t temp = 0;
   CU(scan_hit_offsets(d_sp_cnt, nq, d_hit_off, nullptr, temp, st));
@@ -804,8 +804,14 @@ uint64_t* locate_chunk_device(const awry_index* ix, Replica& r, Workspace* ws, u
   uint64_t n_hits = 0;
   CU(cudaMemcpyAsync(&n_hits, d_hit_off + nq, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  *n_hits_out = n_hits;
+  return n_hits;
+}
+
+// Step 2: LF-walk every hit; returns a stream-ordered device buffer with n_hits awry_hit entries.
+uint64_t* locate_chunk_walk(Replica& r, Workspace* ws, uint64_t nq, uint64_t n_hits, uint32_t flags,
+                            const uint64_t* d_hit_off, cudaStream_t st) {
   if (n_hits == 0) return nullptr;
+  const uint2* d_sp_cnt = reinterpret_cast<const uint2*>(ws->d_out);
   uint64_t* d_hits = nullptr;
   CU(cudaMallocAsync(reinterpret_cast<void**>(&d_hits), n_hits * 16, st));  // pool: no driver round trip
   try {
@@ -835,9 +841,19 @@ uint64_t* locate_chunk_device(const awry_index* ix, Replica& r, Workspace* ws, u
   return d_hits;
 }
 
+uint64_t* locate_chunk_device(const awry_index* ix, Replica& r, Workspace* ws, uint64_t nq,
+                              uint32_t flags, uint64_t* d_hit_off, uint64_t* n_hits_out,
+                              cudaStream_t st) {
+  (void)ix;
+  *n_hits_out = locate_chunk_count(r, ws, nq, d_hit_off, st);
+  return locate_chunk_walk(r, ws, nq, *n_hits_out, flags, d_hit_off, st);
+}
+
 void locate_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, const uint64_t* qoff,
                        uint64_t q_lo, uint64_t q_hi, uint32_t flags, LocatePart& part) {
-  part.hit_off.assign(q_hi - q_lo + 1, 0);
+  const bool ext = part.ext_cap != 0 || part.ext_off != nullptr;
+  if (!part.ext_off) part.hit_off.assign(q_hi - q_lo + 1, 0);
+  uint64_t* off_base = part.ext_off ? part.ext_off : part.hit_off.data();
   if (q_lo >= q_hi) return;
   DeviceGuard dg(r.device);
   const bool src_pinned = is_pinned(qbytes) && is_pinned(qoff);
@@ -849,14 +865,15 @@ void locate_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
       uint64_t nq = c.q1 - c.q0;
       enqueue_search(ix, r, ws, qbytes, qoff, c, OUT_SP_CNT_U32, src_pinned);
       Workspace::grow_dev(ws->d_hit_off, ws->d_hit_off_cap, size_t(nq) + 1);
-      uint64_t n_hits = 0;
-      uint64_t* d_hits = locate_chunk_device(ix, r, ws, nq, flags, ws->d_hit_off, &n_hits, ws->st);
+      uint64_t n_hits = locate_chunk_count(r, ws, nq, ws->d_hit_off, ws->st);
       check_flag(ws, c);
       // offsets of this chunk, rebased onto the replica-local hit count so far
-      uint64_t* dst_off = part.hit_off.data() + (c.q0 - q_lo);
+      uint64_t* dst_off = off_base + (c.q0 - q_lo);
       CU(cudaMemcpyAsync(dst_off, ws->d_hit_off, (nq + 1) * 8, cudaMemcpyDeviceToHost, ws->st));
-      if (n_hits) {
-        if (part.n_hits + n_hits > cap) {
+      const bool fits = !ext || part.n_hits + n_hits <= part.ext_cap;
+      if (n_hits && fits) {
+        uint64_t* d_hits = locate_chunk_walk(r, ws, nq, n_hits, flags, ws->d_hit_off, ws->st);
+        if (!ext && part.n_hits + n_hits > cap) {
           cap = std::max<size_t>(size_t(part.n_hits + n_hits), cap * 2);
           void* np = realloc(part.hits, cap * sizeof(awry_hit));
           if (!np) {
@@ -866,17 +883,18 @@ void locate_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
           part.hits = static_cast<awry_hit*>(np);
         }
         CU(cudaMemcpyAsync(part.hits + part.n_hits, d_hits, n_hits * 16, cudaMemcpyDeviceToHost, ws->st));
+        cudaFreeAsync(d_hits, ws->st);
+        g_prof.d2h += n_hits * 16;
       }
-      if (d_hits) cudaFreeAsync(d_hits, ws->st);
       CU(cudaStreamSynchronize(ws->st));
-      g_prof.d2h += (nq + 1) * 8 + n_hits * 16;
+      g_prof.d2h += (nq + 1) * 8;
       for (uint64_t i = 0; i <= nq; i++) dst_off[i] += part.n_hits;
-      part.n_hits += n_hits;
+      part.n_hits += n_hits;  // keeps counting past the capacity so the caller learns the need
     }
   } catch (...) {
     cudaStreamSynchronize(ws->st);
     r.release(ws);
-    free(part.hits);
+    if (!ext) free(part.hits);
     part.hits = nullptr;
     throw;
   }
@@ -1113,6 +1131,43 @@ int awry_locate_batch(const awry_index* ix, const uint8_t* qbytes, const uint64_
 }
 
 void awry_hits_free(awry_hit* hits) { free(hits); }
+
+int awry_locate_batch_into(const awry_index* ix, const uint8_t* qbytes, const uint64_t* qoff, uint64_t nq,
+                           uint32_t flags, uint64_t* hit_off, awry_hit* hits, uint64_t capacity, uint64_t* n_hits) {
+  return guarded([&] {
+    need(ix);
+    if (!hit_off || !n_hits || (!hits && capacity)) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    *n_hits = 0;
+    hit_off[0] = 0;
+    if (nq == 0) return;
+    if (!qbytes || !qoff) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    validate_offsets(qoff, nq);
+    if (ix->reps.size() == 1) {  // hits and offsets land straight in the caller's (ideally pinned) buffers
+      LocatePart part;
+      part.hits = hits;
+      part.ext_cap = capacity;
+      part.ext_off = hit_off;  // marks the part as caller-owned even when capacity is 0
+      locate_on_replica(ix, *ix->reps[0], qbytes, qoff, 0, nq, flags, part);
+      *n_hits = part.n_hits;
+      if (part.n_hits > capacity)
+        fail(AWRY_ERR_CAPACITY, "hit buffer holds %llu entries, %llu needed", (unsigned long long)capacity,
+             (unsigned long long)part.n_hits);
+      return;
+    }
+    awry_hit* tmp = nullptr;
+    uint64_t n = 0;
+    int rc = awry_locate_batch(ix, qbytes, qoff, nq, flags, hit_off, &tmp, &n);
+    if (rc != AWRY_OK) fail(rc, "%s", g_err);
+    *n_hits = n;
+    if (n > capacity) {
+      free(tmp);
+      fail(AWRY_ERR_CAPACITY, "hit buffer holds %llu entries, %llu needed", (unsigned long long)capacity,
+           (unsigned long long)n);
+    }
+    if (n) memcpy(hits, tmp, n * sizeof(awry_hit));
+    free(tmp);
+  });
+}
 
 int awry_initial_range(const awry_index* ix, uint8_t ascii_symbol, awry_range* out) {
   return guarded([&] {

@@ -100,7 +100,7 @@ class Profile(C.Structure):
 # every symbol include/awry_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = ["awry_index_load", "awry_index_from_parts", "awry_index_free", "awry_index_info",
            "awry_index_sequence_header", "awry_count_batch", "awry_search_batch",
-           "awry_locate_batch", "awry_hits_free", "awry_initial_range", "awry_update_range",
+           "awry_locate_batch", "awry_locate_batch_into", "awry_hits_free", "awry_initial_range", "awry_update_range",
            "awry_backstep", "awry_count_device", "awry_locate_device", "awry_device_free",
            "awry_device_check", "awry_profile_enable", "awry_profile_reset", "awry_profile_get",
            "awry_bench_random_gather", "awry_set_search_variant", "awry_last_error", "awry_version"]
@@ -129,6 +129,7 @@ def native():
     L.awry_count_batch.argtypes = [vp, vp, vp, u64, vp]
     L.awry_search_batch.argtypes = [vp, vp, vp, u64, vp]
     L.awry_locate_batch.argtypes = [vp, vp, vp, u64, C.c_uint32, vp, C.POINTER(vp), C.POINTER(u64)]
+    L.awry_locate_batch_into.argtypes = [vp, vp, vp, u64, C.c_uint32, vp, vp, u64, C.POINTER(u64)]
     L.awry_hits_free.argtypes = [vp]
     L.awry_hits_free.restype = None
     L.awry_initial_range.argtypes = [vp, C.c_uint8, C.POINTER(_Range)]
@@ -322,6 +323,22 @@ class FmIndex:
             C.memmove(arr.ctypes.data, hits, n.value * 16)
         native().awry_hits_free(hits)
         return hit_off, arr
+
+    def locate_packed_into(self, qbytes: np.ndarray, qoff: np.ndarray, hit_off: np.ndarray, hits: np.ndarray,
+                           sorted_hits: bool = False) -> int:
+        """locate into caller-owned arrays (hit_off uint64[nq+1], hits uint64[capacity, 2], e.g. pinned);
+        returns the number of hits; raises AwryError(-8) with `.needed` set when hits is too small."""
+        qbytes = np.ascontiguousarray(qbytes, dtype=np.uint8)
+        qoff = np.ascontiguousarray(qoff, dtype=np.uint64)
+        n = C.c_uint64()
+        rc = native().awry_locate_batch_into(self._h, qbytes.ctypes.data, qoff.ctypes.data, len(qoff) - 1,
+                                             LOCATE_SORTED if sorted_hits else LOCATE_BWT_ORDER,
+                                             hit_off.ctypes.data, hits.ctypes.data, len(hits), C.byref(n))
+        if rc != 0:
+            err = AwryError(rc, native().awry_last_error().decode(errors="replace"))
+            err.needed = n.value
+            raise err
+        return n.value
 
     def get_search_range_for_string(self, query) -> SearchRange:
         qb, qo = pack_queries([query])

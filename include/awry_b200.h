@@ -34,7 +34,8 @@ typedef enum awry_status {
   AWRY_ERR_INVALID_QUERY = -5, /* empty query or a query containing '$'/'#': the reference
                                   panics or is UB here (fm_index.rs:406, bwt.rs:127)           */
   AWRY_ERR_UNSUPPORTED = -6, /* e.g. bwt_len >= 2^32 (device layout uses 32-bit row pointers)  */
-  AWRY_ERR_NOMEM = -7
+  AWRY_ERR_NOMEM = -7,
+  AWRY_ERR_CAPACITY = -8     /* caller-owned output buffer too small; the needed size is reported */
 } awry_status;
 
 /* awry::alphabet::SymbolAlphabet (alphabet.rs:28-31); values = the file header's alphabet id */
@@ -138,6 +139,14 @@ int awry_locate_batch(const awry_index *index, const uint8_t *qbytes, const uint
                       uint64_t nq, uint32_t flags, uint64_t *hit_off, awry_hit **hits,
                       uint64_t *n_hits);
 void awry_hits_free(awry_hit *hits);
+
+/* Same, with caller-owned output like `counts` above: up to `capacity` hits are written to `hits`
+ * (pinned memory makes the device->host copy a direct DMA).  *n_hits is always the total found; if
+ * it exceeds `capacity` the call returns AWRY_ERR_CAPACITY (hit_off is complete, hits is not) and
+ * can be repeated with a larger buffer.  capacity = 0 just fills hit_off / *n_hits. */
+int awry_locate_batch_into(const awry_index *index, const uint8_t *qbytes, const uint64_t *qoff,
+                           uint64_t nq, uint32_t flags, uint64_t *hit_off, awry_hit *hits,
+                           uint64_t capacity, uint64_t *n_hits);
 
 /* ------------------------------------------------------------------ single steps (public in the reference) */
 

@@ -72,6 +72,8 @@ extern "C" {
     pub fn awry_locate_batch(index: *const awry_index, qbytes: *const u8, qoff: *const u64, nq: u64, flags: u32,
                              hit_off: *mut u64, hits: *mut *mut awry_hit, n_hits: *mut u64) -> c_int;
     pub fn awry_hits_free(hits: *mut awry_hit);
+    pub fn awry_locate_batch_into(index: *const awry_index, qbytes: *const u8, qoff: *const u64, nq: u64, flags: u32,
+                                  hit_off: *mut u64, hits: *mut awry_hit, capacity: u64, n_hits: *mut u64) -> c_int;
     pub fn awry_initial_range(index: *const awry_index, ascii_symbol: u8, out: *mut awry_range) -> c_int;
     pub fn awry_update_range(index: *const awry_index, range: awry_range, ascii_symbol: u8, out: *mut awry_range) -> c_int;
     pub fn awry_backstep(index: *const awry_index, bwt_row: u64, out: *mut u64) -> c_int;

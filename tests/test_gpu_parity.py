@@ -321,3 +321,22 @@ def test_cfg5_repeat_rich_locate_under_skew(fx, po):
     t = bytes(text)
     lo, hi = int(woff[i]), int(woff[i + 1])
     assert all(t[int(p):int(p) + 50] == q for p in whits[lo:hi, 1])
+
+
+def test_locate_into_caller_buffers(fx, dna, dna_dev, dna_or):
+    import torch
+    from awry_b200 import AwryError
+    qb, qo = mixed_queries(fx, dna.text, 5000, 14, seed=41)
+    woff, whits, _ = dna_or.locate_batch(qb, qo)
+    n = len(whits)
+    hoff = torch.zeros(5001, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+    hits = torch.zeros((n + 7, 2), dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+    got = dna_dev.locate_packed_into(qb, qo, hoff, hits)
+    assert got == n and np.array_equal(hoff, woff) and np.array_equal(hits[:n], whits)
+    small = np.zeros((n // 2, 2), dtype=np.uint64)
+    with pytest.raises(AwryError) as e:
+        dna_dev.locate_packed_into(qb, qo, hoff, small)
+    assert e.value.code == -8 and e.value.needed == n and np.array_equal(hoff, woff)
+    with pytest.raises(AwryError) as e:
+        dna_dev.locate_packed_into(qb, qo, hoff, np.zeros((0, 2), dtype=np.uint64))
+    assert e.value.needed == n
