@@ -54,7 +54,7 @@ def main():
             steps = a.nq * (a.qlen - a.k)
             print(f"lanes={lanes} bps={bps}: search {p['search_ms']:.2f} ms pack {p['pack_ms']:.2f} ms  "
                   f"{a.nq/p['search_ms']/1e3:.1f} M reads/s  {steps/p['search_ms']/1e6:.2f} G LF-steps/s  "
-                  f"alg {steps*104/p['search_ms']/1e6:.0f} GB/s", flush=True)
+                  f"alg {steps*(104 if a.alphabet == 0 else 168)/p['search_ms']/1e6:.0f} GB/s", flush=True)
             results.append({"lanes": lanes, "bps": bps, **p})
     f.set_search_variant(0)
     ix.device_check(st)
