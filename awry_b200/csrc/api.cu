@@ -350,8 +350,8 @@ void build_replica0(awry_index* ix, Replica& r, Source& src_blocks_then_rest, bo
   CU(cudaDeviceGetAttribute(&r.sm_count, cudaDevAttrMultiProcessorCount, r.device));
   const uint64_t n_ref_blocks = (ix->bwt_len + 255) / 256;
   const size_t ref_block_bytes = ix->alphabet == AWRY_NUCLEOTIDE ? 160 : 352;
-  // nucleotide: 2 x 64-B device blocks per 256-row reference block; amino: one 256-B block
-  r.bytes_blocks = size_t(n_ref_blocks) * (ix->alphabet == AWRY_NUCLEOTIDE ? 128 : 256);
+  // nucleotide: 2 x 64-B device blocks per 256-row reference block; amino: 4 x 128-B blocks
+  r.bytes_blocks = size_t(n_ref_blocks) * (ix->alphabet == AWRY_NUCLEOTIDE ? 128 : 512);
   CU(cudaMalloc(reinterpret_cast<void**>(&r.d_blocks), r.bytes_blocks + 256));
   CU(cudaMemset(r.d_blocks, 0, r.bytes_blocks + 256));
   unsigned int* d_dollar = nullptr;

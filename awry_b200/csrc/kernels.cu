@@ -104,14 +104,16 @@ __global__ void transpose_dna_kernel(const uint64_t* __restrict__ ref, uint64_t 
   out[(first_rb + lrb) * 8 + h * 4 + j] = make_uint4(d0, d1, d2, uint32_t(cnt));
 }
 
-// one thread per 32-B output chunk; 8 chunks per 256-row reference block (bwt.rs:19-25)
+// Amino re-layout, step 1: one thread per 32-row slice (8 per 256-row reference block, bwt.rs:19-25)
+// re-encodes the 5 reference planes into planes of the symbol INDEX and writes them into slice 0/1
+// of the 64-row device block that owns the rows.
 __global__ void transpose_amino_kernel(const uint64_t* __restrict__ ref, uint64_t first_rb,
                                        uint64_t n_rb, uint64_t bwt_len, uint4* __restrict__ out,
                                        unsigned int* dollar_row) {
   uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
   if (t >= n_rb * 8) return;
   uint64_t lrb = t >> 3;
-  uint32_t j = uint32_t(t) & 7;
+  uint32_t j = uint32_t(t) & 7;  // 32-row slice of the reference block
   const uint64_t* rb = ref + lrb * 44;
   uint32_t w = j >> 1, sh = 32 * (j & 1);
   uint32_t r[5], d[5] = {0, 0, 0, 0, 0};
@@ -128,15 +130,34 @@ __global__ void transpose_amino_kernel(const uint64_t* __restrict__ ref, uint64_
 #pragma unroll
     for (int p = 0; p < 5; p++) d[p] |= ((idx >> p) & 1u) << bit;
   }
-  uint32_t c[3];
+  // device block = 64 rows: reference block x 4 + j/2; slice j%2; plane words 0..4 of the slice
+  uint32_t* o = reinterpret_cast<uint32_t*>(out + ((first_rb + lrb) * 4 + (j >> 1)) * AMINO_BLOCK_UINT4) + 8 * (j & 1);
 #pragma unroll
-  for (int i = 0; i < 3; i++) {
-    uint32_t s = 3 * j + i + 1;  // reference symbol index held by count slot 3j+i
-    c[i] = s <= 21 ? uint32_t(rb[20 + s]) : 0u;
+  for (int p = 0; p < 5; p++) o[p] = d[p];
+}
+
+// Amino re-layout, step 2: one thread per (reference block, symbol): block-start counts of the four
+// 64-row device blocks = the reference milestone + symbols seen in the earlier device blocks,
+// counted on the re-encoded planes so counts and planes agree for every input.
+__global__ void amino_counts_kernel(const uint64_t* __restrict__ ref, uint64_t first_rb, uint64_t n_rb,
+                                    uint4* __restrict__ out) {
+  uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (t >= n_rb * 32) return;
+  uint64_t lrb = t >> 5;
+  uint32_t s = uint32_t(t) & 31;
+  if (s == 0 || s > 21) return;
+  uint32_t cnt = uint32_t(ref[lrb * 44 + 20 + s]);
+  for (uint32_t d = 0; d < 4; d++) {
+    uint32_t* blk = reinterpret_cast<uint32_t*>(out + ((first_rb + lrb) * 4 + d) * AMINO_BLOCK_UINT4);
+    blk[amino_count_word(s)] = cnt;
+#pragma unroll
+    for (int sl = 0; sl < 2; sl++) {
+      uint32_t m = ~0u;
+#pragma unroll
+      for (int p = 0; p < 5; p++) m &= ((s >> p) & 1u) ? blk[8 * sl + p] : ~blk[8 * sl + p];
+      cnt += __popc(m);
+    }
   }
-  uint4* o = out + (first_rb + lrb) * 16 + 2 * j;
-  o[0] = make_uint4(d[0], d[1], d[2], d[3]);
-  o[1] = make_uint4(d[4], c[0], c[1], c[2]);
 }
 
 cudaError_t launch_transpose(int alphabet, const uint64_t* d_ref_blocks, uint64_t first_ref_block,
@@ -148,9 +169,14 @@ cudaError_t launch_transpose(int alphabet, const uint64_t* d_ref_blocks, uint64_
   if (alphabet == 0)
     transpose_dna_kernel<<<grid, 256, 0, s>>>(d_ref_blocks, first_ref_block, n_ref_blocks, bwt_len,
                                               d_blocks, d_dollar_row);
-  else
+  else {
     transpose_amino_kernel<<<grid, 256, 0, s>>>(d_ref_blocks, first_ref_block, n_ref_blocks,
                                                 bwt_len, d_blocks, d_dollar_row);
+    COUNT_LAUNCH();
+    uint64_t t2 = n_ref_blocks * 32;
+    amino_counts_kernel<<<unsigned((t2 + 255) / 256), 256, 0, s>>>(d_ref_blocks, first_ref_block,
+                                                                    n_ref_blocks, d_blocks);
+  }
   COUNT_LAUNCH();
   return cudaGetLastError();
 }
@@ -904,6 +930,167 @@ static cudaError_t launch_search_pair(const IndexView& ix, const uint64_t* d_qwo
   }
 }
 
+// ---- amino kernel: 4 lanes per query, one 128-B block (4 x LDG.256) per symbol ----
+// Same shape as the nucleotide pair kernel: the query (8-bit symbols) is staged in a 16-word
+// shared-memory ring with one aligned read, groups refill in-loop, the warp leaves by vote and
+// the rank reduction uses full-mask shuffles.  Slices 0/1 hold the planes of rows 0-31 / 32-63.
+struct AminoSlice {
+  uint32_t match, count;
+};
+__device__ __forceinline__ AminoSlice amino_slice(const u32x8& x, uint32_t sub, uint32_t sym) {
+  AminoSlice r;
+  r.match = sub < 2 ? amino_match(x, sym) : 0u;
+  const uint32_t cw = amino_count_word(sym);  // word index in the block: lane = cw / 8, word = cw % 8
+  const uint32_t word = cw & 7u;
+  const uint32_t t0 = (word & 1) ? x.v[1] : x.v[0], t1 = (word & 1) ? x.v[3] : x.v[2];
+  const uint32_t t2 = (word & 1) ? x.v[5] : x.v[4], t3 = (word & 1) ? x.v[7] : x.v[6];
+  const uint32_t u0 = (word & 2) ? t1 : t0, u1 = (word & 2) ? t3 : t2;
+  r.count = sub == (cw >> 3) ? ((word & 4) ? u1 : u0) : 0u;
+  return r;
+}
+
+template <int MODE, int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB)
+    search_amino_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
+                        const uint64_t* __restrict__ qoff, uint64_t nq, void* __restrict__ out) {
+  constexpr int LANES = 4;
+  constexpr uint32_t NONE = 0xffffffffu, FULL = 0xffffffffu;
+  __shared__ uint64_t s_q[TPB / LANES][16];  // 128 symbols
+  const uint32_t sub = threadIdx.x & 3;
+  const uint32_t gbase = (threadIdx.x & 31) - sub;
+  const uint32_t gmask = 0xfu << gbase;
+  uint64_t* const ring = s_q[threadIdx.x / LANES];
+  const uint32_t nq32 = uint32_t(nq);
+  uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  uint32_t cur = NONE;
+  uint32_t sp = 1, ep = 0, left = 0, len = 0;
+  uint32_t ubase = 0, wlim = 8;
+
+  for (;;) {
+    if (left == 0 || sp > ep) {
+      if (cur != NONE && sub == 0) store_result<MODE>(out, cur, sp, ep);
+      cur = NONE;
+      left = 0;
+      if (q < nq32) {
+        cur = q;
+        const uint32_t G = (gridDim.x * blockDim.x) / LANES;
+        q = (q + G < q) ? NONE : q + G;
+        uint64_t ov = qoff[cur + (sub & 1)];
+        uint64_t o0 = __shfl_sync(gmask, ov, gbase), o1 = __shfl_sync(gmask, ov, gbase + 1);
+        len = uint32_t(o1 - o0);
+        sp = 1;
+        ep = 0;
+        if (len != 0) {
+          ubase = 4 * (cur + uint32_t(o0 >> 5));
+          const uint32_t nwords = (len + 7) >> 3;
+          __syncwarp(gmask);
+          if (4 * sub < nwords) {
+            u32x8 t = ldg256(qwords + ubase + 4 * sub);
+#pragma unroll
+            for (int j = 0; j < 4; j++) ring[4 * sub + j] = uint64_t(t.v[2 * j]) | (uint64_t(t.v[2 * j + 1]) << 32);
+          }
+          __syncwarp(gmask);
+          wlim = 8;
+          const uint32_t k = ix.kmer_len;
+          const uint64_t w = ring[0];
+          bool seeded = false;
+          if (k != 0 && len >= k) {  // k <= 8: inside word 0
+            uint64_t idx = 0, mult = 1;
+            bool ok = true;
+#pragma unroll 1
+            for (uint32_t j = 0; j < k; j++) {
+              uint32_t c = uint32_t(w >> (8 * j)) & 0xffu;
+              ok &= (c != uint32_t(AMINO_X)) & (c != uint32_t(AMINO_SENTINEL));
+              idx += uint64_t(c == 21 ? 19 : c - 1) * mult;
+              mult *= 20;
+            }
+            if (ok) {
+              uint2 r = __ldg(ix.table + idx);
+              sp = r.x;
+              ep = r.y;
+              left = len - k;
+              seeded = true;
+            }
+          }
+          if (!seeded) {
+            uint32_t c = uint32_t(w) & 0xffu;
+            if (c != uint32_t(AMINO_SENTINEL)) {
+              sp = ix.c_lo[c];
+              ep = ix.c_hi[c];
+              left = len - 1;
+            }
+          }
+        }
+      }
+    }
+    if (__all_sync(FULL, cur == NONE && q >= nq32)) break;
+
+    bool active = left != 0 && sp <= ep;
+    const uint32_t pos = len - left;
+    if (active && (pos >> 3) >= wlim) {  // long query: bring in words [wlim+8, wlim+16)
+      __syncwarp(gmask);
+      if (sub < 2) {
+        u32x8 t = ldg256(qwords + ubase + wlim + 8 + 4 * sub);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          ring[(wlim + 8 + 4 * sub + j) & 15] = uint64_t(t.v[2 * j]) | (uint64_t(t.v[2 * j + 1]) << 32);
+      }
+      __syncwarp(gmask);
+      wlim += 8;
+    }
+    const uint32_t c = uint32_t(ring[(pos >> 3) & 15] >> (8 * (pos & 7))) & 0xffu;
+    if (active && (c == uint32_t(AMINO_SENTINEL) || c > 21)) {  // rejected by the prepass; stay defined
+      sp = 1;
+      ep = 0;
+      active = false;
+    }
+    const uint32_t pa = sp - 1, pb = ep;
+    uint32_t ra = 0, rb = 0;
+    if (active) {
+      const uint32_t ba = pa >> 6, bb = pb >> 6;
+      const int na = int(pa & 63) + 1 - int(32 * sub), nb = int(pb & 63) + 1 - int(32 * sub);
+      u32x8 x = ldg256(ix.blocks + size_t(ba) * AMINO_BLOCK_UINT4 + 2 * sub);
+      AminoSlice s = amino_slice(x, sub, c);
+      ra = __popc(s.match & low_mask(na)) + s.count;
+      if (bb != ba) {
+        x = ldg256(ix.blocks + size_t(bb) * AMINO_BLOCK_UINT4 + 2 * sub);
+        s = amino_slice(x, sub, c);
+      }
+      rb = __popc(s.match & low_mask(nb)) + s.count;
+    }
+    ra += __shfl_xor_sync(FULL, ra, 1);
+    rb += __shfl_xor_sync(FULL, rb, 1);
+    ra += __shfl_xor_sync(FULL, ra, 2);
+    rb += __shfl_xor_sync(FULL, rb, 2);
+    if (active) {
+      const uint32_t base = ix.c_lo[c];
+      sp = base + ra;
+      ep = base + rb - 1;
+      left--;
+    }
+  }
+}
+
+template <int MODE>
+static cudaError_t launch_search_amino(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
+                                       uint64_t nq, void* d_out, const SearchVariant& v, int sm_count,
+                                       cudaStream_t s) {
+  if (nq >= (1ull << 32) - 1) return cudaErrorInvalidValue;
+  constexpr int TPB = 256;
+  auto kern = search_amino_kernel<MODE, TPB, 6>;
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, 0);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  if (v.blocks_per_sm > 0 && v.blocks_per_sm < per_sm) per_sm = v.blocks_per_sm;
+  uint64_t max_blocks = uint64_t(sm_count) * uint64_t(per_sm);
+  uint64_t need_blocks = (nq * 4 + TPB - 1) / TPB;
+  unsigned grid = unsigned(std::max<uint64_t>(1, std::min(max_blocks, need_blocks)));
+  kern<<<grid, TPB, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
 template <int MODE>
 static cudaError_t launch_search_mode(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
                                       uint64_t nq, void* d_out, uint32_t* d_defer, const SearchVariant& v,
@@ -917,7 +1104,9 @@ static cudaError_t launch_search_mode(const IndexView& ix, const uint64_t* d_qwo
       default: return launch_search_dna<2, MODE>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
     }
   }
-  // amino (and lanes == -1: the scalar nucleotide kernel, kept for cross-checking)
+  if (ix.alphabet == 1 && v.lanes != -1)
+    return launch_search_amino<MODE>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
+  // lanes == -1: the scalar kernels, kept for cross-checking
   int per_sm = 8;
   uint64_t need_blocks = (nq + 255) / 256;
   unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * per_sm, need_blocks)));

@@ -25,9 +25,10 @@
 //                 C2[a,b] = C[b] + Occ(b, C[a]-1)
 //               (two applications of fm_index.rs:559-582 composed).
 //
-//   AMINO       block = 256 rows = 256 B = 8 chunks of 32 B (one LDG.256 each)
-//               chunk j = { p0..p4, cnt_{3j}, cnt_{3j+1}, cnt_{3j+2} }, 24 count slots,
-//               slot s-1 = #symbol s in BWT[0 .. block start), s = reference symbol index 1..21.
+//   AMINO       block = 64 rows = 128 B = 4 lane slices of 32 B (one LDG.256 each; one line per step)
+//               slice t < 2 = { p0..p4 of rows 32t..32t+31, cnt[3t], cnt[3t+1], cnt[3t+2] }
+//               slice 2     = { cnt[6] .. cnt[13] },  slice 3 = { cnt[14] .. cnt[21] }
+//               cnt[s-1] = #symbol s in BWT[0 .. block start), s = reference symbol index 1..21.
 //               Row code (5 planes) = reference symbol index (0 = '$' and padding rows).
 //
 // Ranks are INCLUSIVE, Occ(c,i) = #c in BWT[0..=i], as in bwt.rs:114-135 / fm_index.rs:559-582.
@@ -44,7 +45,7 @@ constexpr int DNA_N = 4, DNA_SENTINEL = 5, DNA_PAD = 7;
 constexpr int AMINO_X = 20, AMINO_SENTINEL = 0;
 
 constexpr uint32_t DNA_ROWS_PER_BLOCK = 128, DNA_BLOCK_UINT4 = 4;
-constexpr uint32_t AMINO_ROWS_PER_BLOCK = 256, AMINO_BLOCK_UINT4 = 16;
+constexpr uint32_t AMINO_ROWS_PER_BLOCK = 64, AMINO_BLOCK_UINT4 = 8;
 constexpr uint32_t PAIR_ROWS_PER_BLOCK = 96, PAIR_BLOCK_UINT4 = 8;
 
 struct IndexView {
@@ -142,43 +143,49 @@ __device__ __forceinline__ uint32_t amino_match(const u32x8& ch, uint32_t s) {
   for (int p = 0; p < 5; p++) r &= ((s >> p) & 1u) ? ch.v[p] : ~ch.v[p];
   return r;
 }
-__device__ __forceinline__ uint32_t amino_milestone(const IndexView& ix, uint32_t blk, uint32_t s) {
+// 32-bit word of an amino block that holds the block-start count of symbol s (1..21)
+__host__ __device__ __forceinline__ uint32_t amino_count_word(uint32_t s) {
   uint32_t slot = s - 1;
+  return slot < 3 ? 5 + slot : slot < 6 ? 8 + 5 + (slot - 3) : slot < 14 ? 16 + (slot - 6) : 24 + (slot - 14);
+}
+__device__ __forceinline__ uint32_t amino_milestone(const IndexView& ix, uint32_t blk, uint32_t s) {
   const uint32_t* words =
       reinterpret_cast<const uint32_t*>(ix.blocks + size_t(blk) * AMINO_BLOCK_UINT4);
-  return __ldg(words + 8 * (slot / 3) + 5 + (slot % 3));
+  return __ldg(words + amino_count_word(s));
 }
 // Occ(s, pos) for reference symbol index s in 1..21
 __device__ __forceinline__ uint32_t amino_occ(const IndexView& ix, uint32_t pos, uint32_t s) {
-  uint32_t blk = pos >> 8, local = pos & 255;
+  uint32_t blk = pos >> 6, local = pos & 63;
   const char* base = reinterpret_cast<const char*>(ix.blocks + size_t(blk) * AMINO_BLOCK_UINT4);
   uint32_t r = amino_milestone(ix, blk, s);
-  uint32_t last = local >> 5;
-  for (uint32_t j = 0; j <= last; j++) {
-    u32x8 ch = ldg256(base + 32 * j);
-    r += __popc(amino_match(ch, s) & chunk_mask(local, j));
+  u32x8 c0 = ldg256(base);
+  r += __popc(amino_match(c0, s) & chunk_mask(local, 0));
+  if (local >= 32) {
+    u32x8 c1 = ldg256(base + 32);
+    r += __popc(amino_match(c1, s) & chunk_mask(local, 1));
   }
   return r;
 }
-// Occ at two positions of the SAME block with one pass over its chunks
+// Occ at two positions of the SAME block with one pass over its row slices
 __device__ __forceinline__ void amino_occ2_same_block(const IndexView& ix, uint32_t blk,
                                                       uint32_t la, uint32_t lb, uint32_t s,
                                                       uint32_t& ra, uint32_t& rb) {
   const char* base = reinterpret_cast<const char*>(ix.blocks + size_t(blk) * AMINO_BLOCK_UINT4);
   uint32_t ms = amino_milestone(ix, blk, s);
-  uint32_t a = ms, b = ms;
-  uint32_t last = (la > lb ? la : lb) >> 5;
-  for (uint32_t j = 0; j <= last; j++) {
-    u32x8 ch = ldg256(base + 32 * j);
-    uint32_t m = amino_match(ch, s);
-    a += __popc(m & chunk_mask(la, j));
-    b += __popc(m & chunk_mask(lb, j));
+  u32x8 c0 = ldg256(base);
+  uint32_t m = amino_match(c0, s);
+  uint32_t a = ms + __popc(m & chunk_mask(la, 0)), b = ms + __popc(m & chunk_mask(lb, 0));
+  if ((la > lb ? la : lb) >= 32) {
+    u32x8 c1 = ldg256(base + 32);
+    m = amino_match(c1, s);
+    a += __popc(m & chunk_mask(la, 1));
+    b += __popc(m & chunk_mask(lb, 1));
   }
   ra = a;
   rb = b;
 }
 __device__ __forceinline__ uint32_t amino_symbol_at(const IndexView& ix, uint32_t pos) {
-  uint32_t blk = pos >> 8, local = pos & 255, j = local >> 5, t = local & 31;
+  uint32_t blk = pos >> 6, local = pos & 63, j = local >> 5, t = local & 31;
   const uint32_t* w =
       reinterpret_cast<const uint32_t*>(ix.blocks + size_t(blk) * AMINO_BLOCK_UINT4) + 8 * j;
   uint32_t s = 0;
@@ -202,9 +209,9 @@ __device__ __forceinline__ void lf_update(const IndexView& ix, uint32_t& sp, uin
     if (bb != ba) b = dna_load_block(ix, bb);
     rb = dna_occ_in_block(ix, b, bb, pb & 127, c);
   } else {
-    uint32_t ba = pa >> 8, bb = pb >> 8;
+    uint32_t ba = pa >> 6, bb = pb >> 6;
     if (ba == bb) {
-      amino_occ2_same_block(ix, ba, pa & 255, pb & 255, c, ra, rb);
+      amino_occ2_same_block(ix, ba, pa & 63, pb & 63, c, ra, rb);
     } else {
       ra = amino_occ(ix, pa, c);
       rb = amino_occ(ix, pb, c);

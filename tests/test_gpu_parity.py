@@ -134,12 +134,19 @@ def test_amino_count_and_locate(fx, po):
     qs += [b"A", b"AC", b"X", b"acd", b"BZJ", b"W" * 9, bytes(text[:300]), bytes(text[-20:]), b"M*K", b"ACDEFGHIKLMNPQRSTVWY"]
     qb, qo = f.pack_queries(qs)
     with device_from_parts(parts) as ix:
-        got = ix.count_packed(qb, qo)
         want, _ = orc.count_batch(qb, qo)
-        assert np.array_equal(got, want)
+        for variant in (0, -1):          # cooperative 4-lane kernel, scalar kernel
+            f.set_search_variant(variant)
+            try:
+                got = ix.count_packed(qb, qo)
+            finally:
+                f.set_search_variant(0)
+            assert np.array_equal(got, want), variant
         off, hits = ix.locate_packed(qb, qo)
         woff, whits, _ = orc.locate_batch(qb, qo)
         assert np.array_equal(off, woff) and np.array_equal(hits, whits)
+        for row in (0, 1, 63, 64, 65, 12345, parts.bwt_len - 1):
+            assert ix.backstep(row) == orc.backstep(row)
     t = bytes(text)
     for i in (0, 5, 4000, 4500):
         assert int(want[i]) == len(brute_positions(t, qs[i]))
