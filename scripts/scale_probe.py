@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--check", type=int, default=20000)
     ap.add_argument("--locate-nq", type=int, default=10_000_000)
     ap.add_argument("--locate-qlen", type=int, default=50)
+    ap.add_argument("--via-file", default="", help="also write the index as an .awry v1 file here and load it back")
     a = ap.parse_args()
     t0 = time.time()
     parts, phases = fxg.build_parts(a.alphabet, a.n, 3, ratio=a.ratio, kmer_len=a.k)
@@ -36,6 +37,18 @@ def main():
     ix = FmIndex.from_parts(parts.alphabet, parts.ratio, parts.bwt_len, parts.kmer_len, parts.blocks,
                             parts.prefix_sums, parts.sa_words)
     print(f"from_parts {time.time()-t1:.2f}s device bytes {ix.device_bytes()}", flush=True)
+    if a.via_file:
+        t2 = time.time()
+        parts.write(a.via_file, reference_table=False)
+        sz = os.path.getsize(a.via_file)
+        t3 = time.time()
+        ix2 = FmIndex.load(a.via_file)
+        t4 = time.time()
+        print(f"file: wrote {sz/1e9:.2f} GB in {t3-t2:.1f}s; awry_index_load {t4-t3:.2f}s = {sz/(t4-t3)/1e9:.2f} GB/s "
+              f"(incl. re-layout, seed table, pair index)", flush=True)
+        ix.close()
+        ix = ix2
+        os.remove(a.via_file)
     d_q = torch.empty(a.nq * a.qlen, dtype=torch.uint8, device="cuda")
     fxg.gen_queries_device(a.alphabet, a.n, 3, a.nq, a.qlen, 4, d_q.data_ptr())
     d_off = torch.arange(0, a.nq + 1, dtype=torch.int64, device="cuda") * a.qlen
