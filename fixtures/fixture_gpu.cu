@@ -12,6 +12,7 @@
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -221,6 +222,135 @@ __global__ void gen_queries_kernel(int alphabet, uint64_t n, uint64_t text_seed,
   }
 }
 
+// ---- prefix doubling on the GPU (for repeat-rich text where many suffixes share the packed key) ----
+struct MaxOp {
+  __host__ __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
+__global__ void pd_heads_kernel(const uint64_t* __restrict__ keys, uint64_t n1, uint8_t* __restrict__ head,
+                                uint32_t* __restrict__ v) {
+  uint64_t stride = gridDim.x * uint64_t(blockDim.x);
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n1; i += stride) {
+    bool hd = i == 0 || keys[i] != keys[i - 1];
+    head[i] = hd ? 1 : 0;
+    v[i] = hd ? uint32_t(i) : 0u;
+  }
+}
+__global__ void pd_scatter_rank_kernel(const uint32_t* __restrict__ sa, const uint32_t* __restrict__ grp, uint64_t n1,
+                                       uint32_t* __restrict__ rank) {
+  uint64_t stride = gridDim.x * uint64_t(blockDim.x);
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n1; i += stride) rank[sa[i]] = grp[i];
+}
+__global__ void pd_flag_unresolved_kernel(const uint8_t* __restrict__ head, uint64_t n1, uint8_t* __restrict__ unres) {
+  uint64_t stride = gridDim.x * uint64_t(blockDim.x);
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n1; i += stride)
+    unres[i] = (head[i] && (i + 1 == n1 || head[i + 1])) ? 0 : 1;
+}
+__global__ void pd_keys2_kernel(const uint32_t* __restrict__ U, uint64_t m, const uint32_t* __restrict__ sa,
+                                const uint32_t* __restrict__ grp, const uint32_t* __restrict__ rank, uint64_t h,
+                                uint64_t n1, uint64_t* __restrict__ keys2, uint32_t* __restrict__ vals2) {
+  uint64_t stride = gridDim.x * uint64_t(blockDim.x);
+  for (uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; j < m; j += stride) {
+    uint32_t slot = U[j], pos = sa[slot];
+    uint64_t nxt = uint64_t(pos) + h;
+    uint32_t k2 = nxt < n1 ? rank[nxt] + 1u : 0u;  // a suffix that ends first sorts first
+    keys2[j] = (uint64_t(grp[slot]) << 32) | k2;
+    vals2[j] = pos;
+  }
+}
+__global__ void pd_apply_kernel(const uint32_t* __restrict__ U, uint64_t m, const uint64_t* __restrict__ keys2,
+                                const uint32_t* __restrict__ vals2, uint32_t* __restrict__ sa,
+                                uint8_t* __restrict__ head, uint32_t* __restrict__ v) {
+  uint64_t stride = gridDim.x * uint64_t(blockDim.x);
+  for (uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; j < m; j += stride) {
+    uint32_t slot = U[j];
+    bool hd = j == 0 || keys2[j] != keys2[j - 1];
+    sa[slot] = vals2[j];
+    head[slot] = hd ? 1 : 0;
+    v[j] = hd ? slot : 0u;
+  }
+}
+__global__ void pd_regroup_kernel(const uint32_t* __restrict__ U, uint64_t m, const uint32_t* __restrict__ g2,
+                                  const uint32_t* __restrict__ sa, uint32_t* __restrict__ grp,
+                                  uint32_t* __restrict__ rank) {
+  uint64_t stride = gridDim.x * uint64_t(blockDim.x);
+  for (uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; j < m; j += stride) {
+    uint32_t slot = U[j];
+    grp[slot] = g2[j];
+    rank[sa[slot]] = g2[j];
+  }
+}
+
+// keys_sorted / sa: result of the first radix sort on keys of h0 symbols in which equal keys imply
+// equal first h0 symbols (3- or 5-bit keys).  Refines sa in place to the full suffix order.
+// kbuf[2]: two 8*n1-byte scratch buffers (the radix sort's key buffers), vscratch: 4*n1 bytes.
+int prefix_doubling(const uint64_t* keys_sorted, uint32_t* sa, uint64_t n1, uint64_t h0, uint64_t* kbuf0,
+                    uint64_t* kbuf1, uint32_t* vscratch, int* rounds_out) {
+  uint32_t *grp = nullptr, *rank = nullptr, *U = nullptr, *v = nullptr, *vals_out = nullptr;
+  uint8_t *head = nullptr, *unres = nullptr;
+  unsigned long long* d_num = nullptr;
+  void* d_temp = nullptr;
+  size_t temp_cap = 0;
+  auto need_temp = [&](size_t b) {
+    if (b > temp_cap) {
+      cudaFree(d_temp);
+      CU(cudaMalloc(&d_temp, b + 256));
+      temp_cap = b + 256;
+    }
+  };
+  int rounds = 0;
+  try {
+    CU(cudaMalloc(&grp, n1 * 4));
+    CU(cudaMalloc(&rank, n1 * 4));
+    CU(cudaMalloc(&U, n1 * 4));
+    CU(cudaMalloc(&v, n1 * 4));
+    CU(cudaMalloc(&vals_out, n1 * 4));
+    CU(cudaMalloc(&head, n1));
+    CU(cudaMalloc(&unres, n1));
+    CU(cudaMalloc(&d_num, 8));
+    const unsigned G = 148 * 16;
+    pd_heads_kernel<<<G, 256>>>(keys_sorted, n1, head, v);
+    size_t tb = 0;
+    CU(cub::DeviceScan::InclusiveScan(nullptr, tb, v, grp, MaxOp(), (long long)n1));
+    need_temp(tb);
+    CU(cub::DeviceScan::InclusiveScan(d_temp, tb, v, grp, MaxOp(), (long long)n1));
+    pd_scatter_rank_kernel<<<G, 256>>>(sa, grp, n1, rank);
+    // from here on the key buffers are scratch
+    for (uint64_t h = h0;; h *= 2) {
+      pd_flag_unresolved_kernel<<<G, 256>>>(head, n1, unres);
+      cub::CountingInputIterator<uint32_t> it(0);
+      CU(cub::DeviceSelect::Flagged(nullptr, tb, it, unres, U, d_num, (long long)n1));
+      need_temp(tb);
+      CU(cub::DeviceSelect::Flagged(d_temp, tb, it, unres, U, d_num, (long long)n1));
+      unsigned long long m = 0;
+      CU(cudaMemcpy(&m, d_num, 8, cudaMemcpyDeviceToHost));
+      if (m == 0) break;
+      if (h >= 2 * n1) throw std::string("prefix doubling did not converge");
+      rounds++;
+      pd_keys2_kernel<<<G, 256>>>(U, m, sa, grp, rank, h, n1, kbuf0, vscratch);
+      cub::DoubleBuffer<uint64_t> kb(kbuf0, kbuf1);
+      cub::DoubleBuffer<uint32_t> vb(vscratch, vals_out);
+      CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, kb, vb, (long long)m, 0, 64));
+      need_temp(tb);
+      CU(cub::DeviceRadixSort::SortPairs(d_temp, tb, kb, vb, (long long)m, 0, 64));
+      pd_apply_kernel<<<G, 256>>>(U, m, kb.Current(), vb.Current(), sa, head, v);
+      uint32_t* g2 = vb.Alternate();  // scratch for the regrouped starts
+      CU(cub::DeviceScan::InclusiveScan(nullptr, tb, v, g2, MaxOp(), (long long)m));
+      need_temp(tb);
+      CU(cub::DeviceScan::InclusiveScan(d_temp, tb, v, g2, MaxOp(), (long long)m));
+      pd_regroup_kernel<<<G, 256>>>(U, m, g2, sa, grp, rank);
+      CU(cudaDeviceSynchronize());
+    }
+  } catch (const std::string& msg) {
+    cudaFree(grp); cudaFree(rank); cudaFree(U); cudaFree(v); cudaFree(vals_out); cudaFree(head); cudaFree(unres);
+    cudaFree(d_num); cudaFree(d_temp);
+    throw;
+  }
+  cudaFree(grp); cudaFree(rank); cudaFree(U); cudaFree(v); cudaFree(vals_out); cudaFree(head); cudaFree(unres);
+  cudaFree(d_num); cudaFree(d_temp);
+  if (rounds_out) *rounds_out = rounds;
+  return 0;
+}
+
 double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -331,9 +461,37 @@ int fxg_build(int alphabet, uint64_t n, uint64_t text_seed, const uint8_t* host_
     unsigned long long n_tied = 0;
     CU(cudaMemcpy(&n_tied, d_num, 8, cudaMemcpyDeviceToHost));
     cudaFree(d_num);
-    if (n_tied > 0) {
-      if (n_tied > 200000000ull)
-        throw std::string("too many tied suffixes for the host fix-up (text too repetitive for this builder)");
+    unsigned long long HOST_FIXUP_MAX = 2000000ull;
+    if (const char* e = getenv("AWRY_FIXTURE_HOST_FIXUP_MAX")) HOST_FIXUP_MAX = strtoull(e, nullptr, 10);
+    if (n_tied > HOST_FIXUP_MAX) {
+      // repeat-rich text: GPU prefix doubling.  It needs keys whose equality implies equality of the
+      // first h0 symbols, which the 2-bit keys (sentinel packed as 'A') do not give: redo with 3 bits.
+      cudaFree(d_tied);
+      d_tied = nullptr;
+      uint64_t h0 = alphabet == 0 ? 21 : 12;
+      if (alphabet == 0 && pure2) {
+        make_keys<3>(d_sym, n1, d_keys[0], d_vals[0]);
+        cub::DoubleBuffer<uint64_t> kb3(d_keys[0], d_keys[1]);
+        cub::DoubleBuffer<uint32_t> vb3(d_vals[0], d_vals[1]);
+        size_t tb3 = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tb3, kb3, vb3, (long long)n1, 0, 64));
+        CU(cudaMalloc(&d_temp, tb3));
+        CU(cub::DeviceRadixSort::SortPairs(d_temp, tb3, kb3, vb3, (long long)n1, 0, 64));
+        CU(cudaDeviceSynchronize());
+        cudaFree(d_temp);
+        d_temp = nullptr;
+        keys_sorted = kb3.Current();
+        sa = vb3.Current();
+      }
+      uint64_t* other_keys = keys_sorted == d_keys[0] ? d_keys[1] : d_keys[0];
+      uint32_t* other_vals = sa == d_vals[0] ? d_vals[1] : d_vals[0];
+      // the doubling rounds reuse the key buffers as scratch once the group heads are extracted;
+      // keys_sorted itself is only read by the first kernel, so it may serve as scratch too
+      int rounds = 0;
+      prefix_doubling(keys_sorted, sa, n1, h0, other_keys, const_cast<uint64_t*>(keys_sorted), other_vals, &rounds);
+      ph[3] = now_s() - t;
+      t = now_s();
+    } else if (n_tied > 0) {
       std::vector<uint32_t> rows(n_tied), pos(n_tied);
       std::vector<uint64_t> rkeys(n_tied);
       CU(cudaMemcpy(rows.data(), d_rows, n_tied * 4, cudaMemcpyDeviceToHost));
@@ -363,8 +521,10 @@ int fxg_build(int alphabet, uint64_t n, uint64_t text_seed, const uint8_t* host_
     }
     cudaFree(d_tied);
     d_tied = nullptr;
-    ph[3] = now_s() - t;
-    t = now_s();
+    if (n_tied <= HOST_FIXUP_MAX) {
+      ph[3] = now_s() - t;
+      t = now_s();
+    }
 
     // keys are no longer needed: free them before allocating the outputs
     uint32_t* sa_keep = sa;

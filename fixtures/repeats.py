@@ -7,7 +7,7 @@ def repeat_rich_text(n, seed=8, tandem_arrays=40, families=((300, 400, 0.05), (6
     """-> (text uint8[n] over ACGT, list of (start, end) intervals that are repeat-derived)"""
     rng = np.random.default_rng(seed)
     acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
-    text = acgt[rng.integers(0, 4, n)]
+    text = acgt[rng.integers(0, 4, n, dtype=np.uint8)]
     regions = []
 
     def place(seq):

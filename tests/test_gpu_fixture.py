@@ -53,3 +53,26 @@ def test_device_query_generator_matches_cpu(fx):
     torch.cuda.synchronize()
     diff = (d.cpu().numpy() != qb).reshape(nq, qlen).sum(axis=1)
     assert diff.max() == 1 and 300 < int(diff.sum()) < 700
+
+
+@pytest.mark.parametrize("alphabet", [0, 1])
+def test_gpu_prefix_doubling_matches_cpu_builder(fx, alphabet, monkeypatch):
+    """repeat-rich text through the GPU prefix-doubling path (forced), against the CPU sorter"""
+    from fixtures import pyfixture_gpu as fxg, repeats
+    monkeypatch.setenv("AWRY_FIXTURE_HOST_FIXUP_MAX", "0")
+    if alphabet == 0:
+        text, _ = repeats.repeat_rich_text(1_500_000, seed=3)
+        text[1000:1040] = ord("N")
+    else:
+        rng = np.random.default_rng(4)
+        aa = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+        text = aa[rng.integers(0, 20, 400_000)]
+        unit = aa[rng.integers(0, 20, 37)]
+        text[5000:5000 + 37 * 300] = np.tile(unit, 300)
+        text[200_000:200_000 + 37 * 100] = np.tile(unit, 100)
+    text = np.ascontiguousarray(text)
+    want = fx.build_parts(text, alphabet, ratio=8, kmer_len=4)
+    got, phases = fxg.build_parts(alphabet, len(text), 0, ratio=8, kmer_len=4, host_text=text)
+    assert np.array_equal(got.prefix_sums, want.prefix_sums)
+    assert np.array_equal(got.sa_words, want.sa_words)
+    assert np.array_equal(got.blocks, want.blocks)
