@@ -1263,38 +1263,10 @@ __device__ __forceinline__ void finish_hit(const IndexView& ix, uint32_t row, ui
     slot[0] = loc;
 }
 
-// Pass 2b, any alphabet: one thread per hit, persistent with lane refill -- a lane whose walk ends
-// takes the next hit, so the geometric walk lengths (rows, not text positions, are sampled:
-// compressed_suffix_array.rs:109-111) do not idle the rest of the warp.
-template <int ALPHA, bool MAP>
-__global__ void __launch_bounds__(256) walk_scalar_kernel(IndexView ix, uint64_t n_hits, uint64_t* __restrict__ out) {
-  constexpr int SLOT = MAP ? 2 : 1;
-  const uint64_t stride = gridDim.x * uint64_t(blockDim.x);
-  uint64_t h = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-  uint64_t cur = 0;
-  uint32_t row = 0, steps = 0;
-  bool have = false;
-  for (;;) {
-    if (!have) {
-      if (h >= n_hits) break;
-      cur = h;
-      h += stride;
-      row = uint32_t(out[SLOT * cur]);
-      steps = 0;
-      have = true;
-    }
-    if (row_is_sampled(ix, row)) {
-      finish_hit(ix, row, steps, out + SLOT * cur, MAP);
-      have = false;
-      continue;
-    }
-    row = lf_backstep<ALPHA>(ix, row);
-    steps++;
-  }
-}
-
 // Pass 2b, nucleotide: 2 lanes per hit, each LDG.256 half of the 64-B block, so one LF step is ONE
-// line request (the scalar walk issues four LDG.128 to the same line).  The lane holding the row's
+// line request (a one-thread walk issues four LDG.128 to the same line).  Lanes refill: a pair whose
+// walk ends takes the next hit, so the geometric walk lengths (rows, not text positions, are sampled:
+// compressed_suffix_array.rs:109-111) do not idle the rest of the warp.  The lane holding the row's
 // chunk extracts the BWT symbol and broadcasts it; both lanes rank their two chunks; xor-shuffle.
 // Warp-convergent loop (exit by vote) so the shuffles use the full mask.
 template <bool MAP>
@@ -1343,6 +1315,55 @@ __global__ void __launch_bounds__(256) walk_dna_kernel(IndexView ix, uint64_t n_
   }
 }
 
+// Pass 2b, amino: 4 lanes per hit on the 128-B block (one line request per LF step); the lane that
+// holds the row's 32-row slice extracts the symbol index from its 5 planes and broadcasts it.
+template <bool MAP>
+__global__ void __launch_bounds__(256) walk_amino_kernel(IndexView ix, uint64_t n_hits, uint64_t* __restrict__ out) {
+  constexpr int SLOT = MAP ? 2 : 1;
+  constexpr uint32_t FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31, sub = lane & 3, gbase = lane - sub;
+  const uint64_t stride = (gridDim.x * uint64_t(blockDim.x)) >> 2;
+  uint64_t h = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 2;
+  uint64_t cur = 0;
+  uint32_t row = 0, steps = 0;
+  bool have = false;
+  for (;;) {
+    if (!have && h < n_hits) {
+      cur = h;
+      h += stride;
+      row = uint32_t(out[SLOT * cur]);
+      steps = 0;
+      have = true;
+    }
+    if (__all_sync(FULL, !have)) break;
+    if (have && row_is_sampled(ix, row)) {
+      if (sub == 0) finish_hit(ix, row, steps, out + SLOT * cur, MAP);
+      have = false;
+    }
+    const uint32_t blk = row >> 6, l = row & 63;
+    u32x8 x;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x.v[i] = 0;
+    if (have) x = ldg256(ix.blocks + size_t(blk) * AMINO_BLOCK_UINT4 + 2 * sub);
+    const uint32_t t = l & 31;
+    uint32_t c = 0;
+#pragma unroll
+    for (int p = 0; p < 5; p++) c |= ((x.v[p] >> t) & 1u) << p;
+    c = __shfl_sync(FULL, c, gbase + (l >> 5));  // from the lane that owns rows 32*(l/32)..
+    uint32_t r = 0;
+    if (have && c != uint32_t(AMINO_SENTINEL) && c <= 21) {
+      AminoSlice s = amino_slice(x, sub, c);
+      r = __popc(s.match & low_mask(int(l) + 1 - int(32 * sub))) + s.count;
+    }
+    r += __shfl_xor_sync(FULL, r, 1);
+    r += __shfl_xor_sync(FULL, r, 2);
+    if (have) {
+      row = (c == uint32_t(AMINO_SENTINEL) || c > 21) ? 0u : ix.c_lo[c] + r - 1;  // '$' row -> 0
+      steps++;
+    }
+  }
+}
+
 cudaError_t launch_walk(const IndexView& ix, const uint2* d_sp_cnt, const uint64_t* d_hit_off,
                         uint64_t nq, uint64_t n_hits, uint64_t* d_hits_pairs, uint64_t* d_locs,
                         int sm_count, cudaStream_t s) {
@@ -1363,11 +1384,11 @@ cudaError_t launch_walk(const IndexView& ix, const uint2* d_sp_cnt, const uint64
     else
       walk_dna_kernel<false><<<grid, 256, 0, s>>>(ix, n_hits, out);
   } else {
-    unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (n_hits + 255) / 256)));
+    unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (4 * n_hits + 255) / 256)));
     if (map)
-      walk_scalar_kernel<1, true><<<grid, 256, 0, s>>>(ix, n_hits, out);
+      walk_amino_kernel<true><<<grid, 256, 0, s>>>(ix, n_hits, out);
     else
-      walk_scalar_kernel<1, false><<<grid, 256, 0, s>>>(ix, n_hits, out);
+      walk_amino_kernel<false><<<grid, 256, 0, s>>>(ix, n_hits, out);
   }
   COUNT_LAUNCH();
   return cudaGetLastError();
