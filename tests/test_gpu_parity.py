@@ -314,7 +314,7 @@ def test_cfg5_repeat_rich_locate_under_skew(fx, po):
         counts = ix.count_packed(qb, qo)
         want, _ = orc.count_batch(qb, qo)
         assert np.array_equal(counts, want)
-        assert int(want.max()) >= 1000 and int(want.min()) >= 1 and float(np.median(want)) < 50
+        assert int(want.max()) >= 1000 and int(want.min()) == 1 and float(np.median(want)) < want.max() / 10
         off, hits = ix.locate_packed(qb, qo)
         woff, whits, st = orc.locate_batch(qb, qo)
         assert np.array_equal(off, woff) and np.array_equal(hits, whits)
