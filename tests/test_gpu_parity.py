@@ -347,3 +347,33 @@ def test_locate_into_caller_buffers(fx, dna, dna_dev, dna_or):
     with pytest.raises(AwryError) as e:
         dna_dev.locate_packed_into(qb, qo, hoff, np.zeros((0, 2), dtype=np.uint64))
     assert e.value.needed == n
+
+
+def test_concurrent_batches_from_many_host_threads(fx, dna, dna_dev, dna_or):
+    """the index is immutable; *_batch calls may run concurrently (like &self methods called from the
+    rayon pool in the reference).  Each call takes a private stream + workspace."""
+    import threading
+    jobs = []
+    for t in range(6):
+        qb, qo = mixed_queries(fx, dna.text, 4000 + 500 * t, 20 + 3 * t, seed=100 + t)
+        jobs.append((qb, qo, dna_or.count_batch(qb, qo)[0], dna_or.locate_batch(qb, qo)[:2]))
+    results, errors = [None] * len(jobs), []
+
+    def work(i):
+        try:
+            qb, qo = jobs[i][0], jobs[i][1]
+            for _ in range(3):
+                c = dna_dev.count_packed(qb, qo)
+                off, hits = dna_dev.locate_packed(qb, qo)
+            results[i] = (c, off, hits)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for (qb, qo, want, (woff, whits)), (c, off, hits) in zip(jobs, results):
+        assert np.array_equal(c, want) and np.array_equal(off, woff) and np.array_equal(hits, whits)
