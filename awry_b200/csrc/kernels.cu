@@ -1503,10 +1503,113 @@ __global__ void __launch_bounds__(256) gather_kernel(const char* __restrict__ bu
   if (acc == 0x12345678u) sink[0] = acc;
 }
 
-template <int GRANULE, int LANES>
+// ---- TMA variant of the probe: one THREAD per read; a 128-B bulk async copy (cp.async.bulk, the
+// 1-D TMA path) lands the granule in the thread's shared-memory slot and completes a per-thread
+// mbarrier, so a request in flight costs no registers.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load_128(void* dst_smem, const void* src_gmem, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 128, [%2];" ::"r"(
+                   smem_addr(dst_smem)),
+               "l"(src_gmem), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int DEPTH>
+__global__ void __launch_bounds__(256) gather_tma_kernel(const char* __restrict__ buf, uint64_t n_granules,
+                                                         uint64_t reads_per_thread, uint64_t seed,
+                                                         uint32_t* __restrict__ sink) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* slots = smem;                                                   // [DEPTH][256][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DEPTH * 256 * 128);  // [DEPTH][256]
+  const uint32_t t = threadIdx.x;
+#pragma unroll
+  for (int d = 0; d < DEPTH; d++) mbar_init(&bars[d * 256 + t], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  fence_proxy_async();
+  __syncthreads();
+  uint64_t x = mix64(seed ^ ((blockIdx.x * uint64_t(blockDim.x) + t) * 0x100000001B3ull));
+  uint32_t acc = 0;
+  auto issue = [&](int d) {
+    x = x * 6364136223846793005ull + 1442695040888963407ull;
+    uint64_t g = __umul64hi(x, n_granules);
+    mbar_expect_tx(&bars[d * 256 + t], 128);
+    bulk_load_128(slots + (size_t(d) * 256 + t) * 128, buf + g * 128, &bars[d * 256 + t]);
+  };
+#pragma unroll
+  for (int d = 0; d < DEPTH; d++) issue(d);
+  uint32_t parity = 0;
+  for (uint64_t it = 0; it < reads_per_thread; it += DEPTH) {
+#pragma unroll
+    for (int d = 0; d < DEPTH; d++) {
+      while (!mbar_try_wait(&bars[d * 256 + t], parity)) {
+      }
+      const uint4* s = reinterpret_cast<const uint4*>(slots + (size_t(d) * 256 + t) * 128);
+      uint4 a = s[(t + d) & 7];  // one 16-B word of the landed granule
+      acc ^= a.x ^ a.y ^ a.z ^ a.w;
+      fence_proxy_async();  // order the generic read before the next async write to the slot
+      if (it + DEPTH < reads_per_thread) issue(d);
+    }
+    parity ^= 1;
+  }
+  if (acc == 0x12345678u) sink[0] = acc;
+}
+
+template <int DEPTH>
+static cudaError_t gather_tma_run(const char* buf, uint64_t n_granules, uint64_t n_reads, int iters,
+                                  uint32_t* sink, double* ms_out) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t smem = size_t(DEPTH) * 256 * (128 + 8);
+  cudaError_t e = cudaFuncSetAttribute(gather_tma_kernel<DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_tma_kernel<DEPTH>, 256, smem);
+  if (e != cudaSuccess) return e;
+  unsigned grid = unsigned(sms * std::max(per_sm, 1));
+  uint64_t threads = uint64_t(grid) * 256;
+  uint64_t per_thread = ((n_reads + threads - 1) / threads + DEPTH - 1) / DEPTH * DEPTH;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int i = 0; i < iters + 1; i++) {
+    cudaEventRecord(e0);
+    gather_tma_kernel<DEPTH><<<grid, 256, smem>>>(buf, n_granules, per_thread, 0x5eed + i, sink);
+    cudaEventRecord(e1);
+    e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) return e;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (i > 0 && ms < best) best = ms;
+    COUNT_LAUNCH();
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  fprintf(stderr, "[gather_tma depth %d] %d blocks/SM, %llu reads/thread\n", DEPTH, per_sm, (unsigned long long)per_thread);
+  *ms_out = double(best) / (double(per_thread * threads) / double(n_reads));
+  return cudaGetLastError();
+}
+
+template <int GRANULE, int LANES, int UNROLL = 4>
 static cudaError_t gather_run(const char* buf, uint64_t n_granules, uint64_t n_reads, int iters,
                               uint32_t* sink, double* ms_out) {
-  constexpr int UNROLL = 4;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1555,6 +1658,13 @@ cudaError_t run_random_gather(uint64_t footprint_bytes, uint32_t granule, uint32
   GATHER_CASE(64, 1) GATHER_CASE(64, 2) GATHER_CASE(64, 4) GATHER_CASE(64, 8)
   GATHER_CASE(128, 1) GATHER_CASE(128, 2) GATHER_CASE(128, 4) GATHER_CASE(128, 8)
 #undef GATHER_CASE
+  // lanes = 104 / 102: the 128-B / 4-lane probe with ONE / TWO reads in flight per lane group (the
+  // dependent-chain shape of the search kernels) instead of four
+  if (granule == 128 && lanes == 104) e = gather_run<128, 4, 1>(buf, n_granules, n_reads, iters, sink, &ms);
+  if (granule == 128 && lanes == 102) e = gather_run<128, 4, 2>(buf, n_granules, n_reads, iters, sink, &ms);
+  // lanes = 201 / 202: one thread per read through cp.async.bulk + mbarrier, 1 / 2 reads in flight per thread
+  if (granule == 128 && lanes == 201) e = gather_tma_run<1>(buf, n_granules, n_reads, iters, sink, &ms);
+  if (granule == 128 && lanes == 202) e = gather_tma_run<2>(buf, n_granules, n_reads, iters, sink, &ms);
   cudaFree(buf);
   cudaFree(sink);
   if (e != cudaSuccess) return e;
