@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "../../include/awry_b200.h"
+#include "build.hpp"
 #include "kernels.hpp"
 
 using namespace awry;
@@ -444,6 +445,9 @@ void keep_pool_memory(int device) {
   cudaGetLastError();
 }
 
+// set by awry_index_build for replicas that exist only to fill a file's k-mer table section
+thread_local bool g_skip_pair_index = false;
+
 void finish_replica0(awry_index* ix, Replica& r) {
   DeviceGuard dg(r.device);
   if (ix->seq_starts.empty()) ix->seq_starts.push_back(0);
@@ -475,7 +479,7 @@ void finish_replica0(awry_index* ix, Replica& r) {
   }
   // nucleotide pair index: two query symbols per block access (AWRY_B200_PAIR_INDEX=0 disables)
   const char* env = getenv("AWRY_B200_PAIR_INDEX");
-  bool want_pair = ix->alphabet == AWRY_NUCLEOTIDE && !(env && env[0] == '0');
+  bool want_pair = ix->alphabet == AWRY_NUCLEOTIDE && !(env && env[0] == '0') && !g_skip_pair_index;
   if (want_pair) {
     size_t bytes = size_t(pair_block_count(ix->bwt_len)) * 128;
     CU(cudaMemGetInfo(&free_b, &total_b));
@@ -1002,6 +1006,135 @@ int awry_index_from_parts(const awry_parts* p, const int* devices, int n_dev, aw
     }
     *out = ix.release();
   });
+}
+
+uint64_t awry_parts_num_blocks(uint64_t bwt_len) { return (bwt_len + 255) / 256; }
+uint64_t awry_parts_block_words(uint32_t alphabet) { return alphabet == AWRY_NUCLEOTIDE ? 20 : 44; }
+uint64_t awry_parts_sa_words(uint64_t bwt_len, uint64_t sa_ratio) {
+  return bwt_len >= 2 && sa_ratio ? sa_word_len(bwt_len, sa_ratio) : 0;
+}
+
+int awry_build_parts(uint32_t alphabet, const uint8_t* text, uint64_t n, uint64_t sa_ratio, int device,
+                     uint64_t* blocks, uint64_t* prefix_sums, uint64_t* sa_words, double* phase_seconds) {
+  return guarded([&] {
+    if (!text || !blocks || !prefix_sums || !sa_words) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    if (alphabet > 1) fail(AWRY_ERR_INVALID_ARG, "invalid alphabet id %u", alphabet);
+    if (n + 1 >= (1ull << 32) - 256) fail(AWRY_ERR_UNSUPPORTED, "text of %llu symbols: 32-bit row pointers", (unsigned long long)n);
+    pick_devices(&device, 1);
+    std::string err;
+    if (build_parts(int(alphabet), text, n, sa_ratio ? sa_ratio : 8, device, blocks, prefix_sums, sa_words,
+                    phase_seconds, err) != 0)
+      fail(AWRY_ERR_CUDA, "index construction failed: %s", err.c_str());
+  });
+}
+
+int awry_index_build(const awry_build_args* a, const int* devices, int n_dev, awry_index** out) {
+  return guarded([&] {
+    if (out) *out = nullptr;
+    if (!a || !a->input_file_src) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    if (!a->output_file_src && !out) fail(AWRY_ERR_INVALID_ARG, "neither an output file nor an index handle requested");
+    if (a->alphabet > 1) fail(AWRY_ERR_INVALID_ARG, "invalid alphabet id %u", a->alphabet);
+    const int alphabet = int(a->alphabet);
+    const uint64_t ratio = a->suffix_array_compression_ratio ? a->suffix_array_compression_ratio : 8;  // fm_index.rs:122
+    const uint32_t k = a->lookup_table_kmer_len ? a->lookup_table_kmer_len : (alphabet == 0 ? 10u : 4u);
+    const int card = alphabet == 0 ? 6 : 22;
+    if (k > 255 || ipow(uint64_t(card - 2), k) > (1ull << 34)) fail(AWRY_ERR_UNSUPPORTED, "k-mer table of length %u too large", k);
+    // the sequence file first: I/O and format errors do not need a device
+    std::string text, err;
+    std::vector<uint64_t> starts;
+    std::vector<std::string> headers;
+    if (read_sequence_file(a->input_file_src, alphabet == 0 ? 'N' : 'X', text, starts, headers, err) != 0)
+      fail(AWRY_ERR_IO, "%s", err.c_str());
+    const uint64_t n = text.size(), bwt_len = n + 1;
+    if (bwt_len >= (1ull << 32) - 256) fail(AWRY_ERR_UNSUPPORTED, "text of %llu symbols: 32-bit row pointers", (unsigned long long)n);
+    int dev0 = a->device;
+    std::vector<int> devs = out ? pick_devices(devices ? devices : &dev0, devices ? n_dev : 1) : pick_devices(&dev0, 1);
+    std::vector<uint64_t> blocks(awry_parts_num_blocks(bwt_len) * awry_parts_block_words(a->alphabet));
+    std::vector<uint64_t> prefix(size_t(card) + 1), sa_words(sa_word_len(bwt_len, ratio) + 1);
+    if (build_parts(alphabet, reinterpret_cast<const uint8_t*>(text.data()), n, ratio, devs[0], blocks.data(),
+                    prefix.data(), sa_words.data(), nullptr, err) != 0)
+      fail(AWRY_ERR_CUDA, "index construction failed: %s", err.c_str());
+    std::string().swap(text);
+    // a device index of what was just built: the caller's FmIndex, and/or the replica that
+    // populates the reference-style k-mer table of the file
+    std::vector<const char*> hdr_ptrs;
+    for (auto& h : headers) hdr_ptrs.push_back(h.c_str());
+    awry_parts parts{};
+    parts.alphabet = a->alphabet;
+    parts.kmer_len = out ? k : 0;  // a file-only build needs no seed table
+    parts.sa_ratio = ratio;
+    parts.bwt_len = bwt_len;
+    parts.version = 1;
+    parts.blocks = blocks.data();
+    parts.prefix_sums = prefix.data();
+    parts.sa_words = sa_words.data();
+    parts.seq_starts = starts.data();
+    parts.headers = hdr_ptrs.data();
+    parts.n_sequences = starts.size();
+    awry_index* ix = nullptr;
+    g_skip_pair_index = !out;
+    int rc = awry_index_from_parts(&parts, devs.data(), int(devs.size()), &ix);
+    g_skip_pair_index = false;
+    if (rc != AWRY_OK) throw ApiError(rc, g_err);
+    std::unique_ptr<awry_index, void (*)(awry_index*)> holder(ix, awry_index_free);
+    if (a->output_file_src) {  // FmIndex::save (fm_index_file.rs:42-106)
+      FILE* f = fopen(a->output_file_src, "wb");
+      if (!f) fail(AWRY_ERR_IO, "cannot create %s: %s", a->output_file_src, strerror(errno));
+      std::unique_ptr<FILE, int (*)(FILE*)> closer(f, fclose);
+      setvbuf(f, nullptr, _IOFBF, 8u << 20);
+      bool ok = true;
+      auto put = [&](const void* p, size_t nbytes) {
+        if (ok && nbytes && fwrite(p, 1, nbytes, f) != nbytes) ok = false;
+      };
+      put("AWRY-Index\n", 11);  // fm_index_file.rs:18,47
+      uint64_t hdr[4] = {1, ratio, bwt_len, uint64_t(alphabet)};
+      put(hdr, sizeof hdr);
+      put(blocks.data(), blocks.size() * 8);
+      put(prefix.data(), prefix.size() * 8);
+      put(sa_words.data(), sa_word_len(bwt_len, ratio) * 8);
+      uint8_t kb = uint8_t(k);
+      put(&kb, 1);
+      {
+        Replica& r = *ix->reps[0];
+        DeviceGuard dg(r.device);
+        const uint64_t n_entries = ipow(uint64_t(card - 2), k), CH = 1u << 22;
+        ulonglong2* d_buf = nullptr;
+        CU(cudaMalloc(reinterpret_cast<void**>(&d_buf), std::min(n_entries, CH) * 16));
+        std::vector<uint64_t> h_buf(2 * std::min(n_entries, CH));
+        IndexView v = r.view;
+        v.kmer_len = 0;
+        for (uint64_t first = 0; first < n_entries && ok; first += CH) {
+          uint64_t cnt = std::min(CH, n_entries - first);
+          cudaError_t e = launch_ref_table(v, first, cnt, k, d_buf, nullptr);
+          if (e == cudaSuccess) e = cudaMemcpy(h_buf.data(), d_buf, cnt * 16, cudaMemcpyDeviceToHost);
+          if (e != cudaSuccess) {
+            cudaFree(d_buf);
+            fail(AWRY_ERR_CUDA, "k-mer table kernel failed: %s", cudaGetErrorString(e));
+          }
+          put(h_buf.data(), cnt * 16);
+        }
+        cudaFree(d_buf);
+      }
+      uint64_t n_seqs = starts.size();  // sequence_index.rs:144-152
+      put(&n_seqs, 8);
+      for (uint64_t i = 0; i < n_seqs; i++) {
+        uint64_t hl = headers[i].size();
+        put(&starts[i], 8);
+        put(&hl, 8);
+        put(headers[i].data(), hl);
+      }
+      if (fflush(f) != 0) ok = false;
+      if (!ok) fail(AWRY_ERR_IO, "write to %s failed", a->output_file_src);
+    }
+    if (out) *out = holder.release();
+  });
+}
+
+int awry_build_index_file(const awry_build_args* a) {
+  if (a && !a->output_file_src) {
+    return guarded([&] { fail(AWRY_ERR_INVALID_ARG, "output_file_src is null"); });
+  }
+  return awry_index_build(a, nullptr, 0, nullptr);
 }
 
 void awry_index_free(awry_index* ix) {

@@ -222,6 +222,52 @@ cudaError_t launch_build_table(const IndexView& ix, uint2* d_table, uint32_t k, 
   return cudaGetLastError();
 }
 
+// The k-mer table exactly as the REFERENCE populates and saves it (kmer_lookup_table.rs:121-167):
+// (card-2)^k entries of (start,end) u64; entry index = sum_j d_j * (card-2)^j with d_j the symbol
+// INDEX of the j-th character from the end, only indices 1 .. card-3 are ever visited (so T / Y and
+// every k-mer with a zero digit stay SearchRange::zero() = (1,0)), no early exit on empty ranges.
+// Written into `.awry` files by awry_build_index_file so the reference can load them; the search
+// path never reads it (kmer_lookup_table.rs:90-110).
+template <int ALPHA>
+__global__ void ref_table_kernel(IndexView ix, uint64_t first, uint64_t count, uint32_t k, ulonglong2* __restrict__ out) {
+  constexpr uint32_t ENC = ALPHA == 0 ? 4 : 20;  // num_encoding_symbols() = cardinality - 2
+  uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (t >= count) return;
+  uint64_t rest = first + t;
+  uint32_t d = uint32_t(rest % ENC);
+  rest /= ENC;
+  bool visited = d != 0;
+  // device symbol of reference index d (nucleotide: 1,2,3 -> A,C,G = 0,1,2; amino: unchanged)
+  uint32_t c = ALPHA == 0 ? d - 1 : d;
+  uint32_t sp = 1, ep = 0;
+  if (visited) {
+    sp = ix.c_lo[c];
+    ep = ix.c_hi[c];
+  }
+  for (uint32_t j = 1; j < k && visited; j++) {
+    d = uint32_t(rest % ENC);
+    rest /= ENC;
+    if (d == 0) {
+      visited = false;
+      break;
+    }
+    lf_update<ALPHA>(ix, sp, ep, ALPHA == 0 ? d - 1 : d);
+  }
+  out[t] = visited ? make_ulonglong2(sp, ep) : make_ulonglong2(1, 0);
+}
+
+cudaError_t launch_ref_table(const IndexView& ix, uint64_t first, uint64_t count, uint32_t k, void* d_out,
+                             cudaStream_t s) {
+  if (count == 0) return cudaSuccess;
+  unsigned grid = unsigned((count + 255) / 256);
+  if (ix.alphabet == 0)
+    ref_table_kernel<0><<<grid, 256, 0, s>>>(ix, first, count, k, static_cast<ulonglong2*>(d_out));
+  else
+    ref_table_kernel<1><<<grid, 256, 0, s>>>(ix, first, count, k, static_cast<ulonglong2*>(d_out));
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ nucleotide pair index
 
 uint64_t pair_block_count(uint64_t bwt_len) { return (bwt_len + PAIR_ROWS_PER_BLOCK - 1) / PAIR_ROWS_PER_BLOCK; }

@@ -38,6 +38,10 @@ cudaError_t launch_transpose(int alphabet, const uint64_t* d_ref_blocks, uint64_
 uint64_t table_entries(int alphabet, uint32_t k);
 cudaError_t launch_build_table(const IndexView& ix, uint2* d_table, uint32_t k, cudaStream_t s);
 
+// the reference's own (incomplete) k-mer table, for files written by awry_build_index_file
+cudaError_t launch_ref_table(const IndexView& ix, uint64_t first, uint64_t count, uint32_t k, void* d_out,
+                             cudaStream_t s);
+
 // nucleotide pair index (two symbols per access), built from the 1-step device blocks
 uint64_t pair_block_count(uint64_t bwt_len);
 cudaError_t build_pair_index(const IndexView& ix, uint4* d_pair_blocks, uint32_t* c2_host /*16*/, cudaStream_t s);

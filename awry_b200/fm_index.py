@@ -13,7 +13,7 @@ Where the reference panics (empty query, sentinel in a query) this raises AwryEr
 import ctypes as C
 import enum
 import os
-from typing import Iterable, List, NamedTuple, Sequence, Tuple
+from typing import Iterable, List, NamedTuple, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -88,6 +88,22 @@ class _Parts(C.Structure):
                 ("headers", C.c_void_p), ("n_sequences", C.c_uint64)]
 
 
+class BuildArgs(C.Structure):  # awry_build_args <- FmBuildArgs (fm_index.rs:78-96)
+    _fields_ = [("input_file_src", C.c_char_p), ("output_file_src", C.c_char_p), ("alphabet", C.c_uint32),
+                ("lookup_table_kmer_len", C.c_uint32), ("suffix_array_compression_ratio", C.c_uint64),
+                ("device", C.c_int32)]
+
+
+class FmBuildArgs(NamedTuple):  # fm_index.rs:78-96
+    input_file_src: str
+    suffix_array_output_src: Optional[str] = None      # libsufr's intermediate file: unused here
+    suffix_array_compression_ratio: Optional[int] = None
+    lookup_table_kmer_len: Optional[int] = None
+    alphabet: "SymbolAlphabet" = 0
+    max_query_len: Optional[int] = None                # a libsufr sort bound: unused here
+    remove_intermediate_suffix_array_file: bool = True
+
+
 class Profile(C.Structure):
     _fields_ = [("launches", C.c_uint64), ("search_launches", C.c_uint64), ("search_ms", C.c_double),
                 ("walk_launches", C.c_uint64), ("walk_ms", C.c_double), ("pack_launches", C.c_uint64),
@@ -98,7 +114,8 @@ class Profile(C.Structure):
 
 
 # every symbol include/awry_b200.h declares (checked by tests/test_abi.py)
-EXPORTS = ["awry_index_load", "awry_index_from_parts", "awry_index_free", "awry_index_info",
+EXPORTS = ["awry_index_build", "awry_build_index_file", "awry_build_parts", "awry_parts_num_blocks", "awry_parts_block_words",
+           "awry_parts_sa_words", "awry_index_load", "awry_index_from_parts", "awry_index_free", "awry_index_info",
            "awry_index_sequence_header", "awry_count_batch", "awry_search_batch",
            "awry_locate_batch", "awry_locate_batch_into", "awry_hits_free", "awry_initial_range", "awry_update_range",
            "awry_backstep", "awry_count_device", "awry_locate_device", "awry_device_free",
@@ -120,6 +137,15 @@ def native():
     vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
     L.awry_last_error.restype = C.c_char_p
     L.awry_version.restype = C.c_char_p
+    L.awry_index_build.argtypes = [C.POINTER(BuildArgs), vp, i32, C.POINTER(vp)]
+    L.awry_build_index_file.argtypes = [C.POINTER(BuildArgs)]
+    L.awry_build_parts.argtypes = [C.c_uint32, vp, u64, u64, i32, vp, vp, vp, vp]
+    L.awry_parts_num_blocks.argtypes = [u64]
+    L.awry_parts_num_blocks.restype = u64
+    L.awry_parts_block_words.argtypes = [C.c_uint32]
+    L.awry_parts_block_words.restype = u64
+    L.awry_parts_sa_words.argtypes = [u64, u64]
+    L.awry_parts_sa_words.restype = u64
     L.awry_index_load.argtypes = [C.c_char_p, vp, i32, C.POINTER(vp)]
     L.awry_index_from_parts.argtypes = [C.POINTER(_Parts), vp, i32, C.POINTER(vp)]
     L.awry_index_free.argtypes = [vp]
@@ -185,6 +211,18 @@ class FmIndex:
         dev = (C.c_int * len(devices))(*devices) if devices else None
         _check(native().awry_index_load(os.fsencode(path), dev, len(devices) if devices else 0,
                                         C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def new(cls, args: "FmBuildArgs", devices: Sequence[int] = None, save_to=None) -> "FmIndex":
+        """FmIndex::new (fm_index.rs:142-268) on the GPU: FASTA/FASTQ -> searchable index; with
+        `save_to` also FmIndex::save (fm_index_file.rs:42) of the same index."""
+        a = BuildArgs(os.fsencode(args.input_file_src), os.fsencode(save_to) if save_to else None,
+                      int(args.alphabet), int(args.lookup_table_kmer_len or 0),
+                      int(args.suffix_array_compression_ratio or 0), int(devices[0]) if devices else 0)
+        h = C.c_void_p()
+        dev = (C.c_int * len(devices))(*devices) if devices else None
+        _check(native().awry_index_build(C.byref(a), dev, len(devices) if devices else 0, C.byref(h)))
         return cls(h.value)
 
     @classmethod
@@ -390,6 +428,35 @@ class FmIndex:
 
     def device_check(self, stream: int = 0, replica: int = 0):
         _check(native().awry_device_check(self._h, replica, stream))
+
+
+def build_index_file(input_file_src, output_file_src, alphabet=SymbolAlphabet.Nucleotide,
+                     suffix_array_compression_ratio: int = 0, lookup_table_kmer_len: int = 0, device: int = 0):
+    """FmIndex::new + save on the GPU: FASTA/FASTQ -> `.awry` v1 file (load it with FmIndex.load)."""
+    a = BuildArgs(os.fsencode(input_file_src), os.fsencode(output_file_src), int(alphabet),
+                  int(lookup_table_kmer_len), int(suffix_array_compression_ratio), int(device))
+    _check(native().awry_build_index_file(C.byref(a)))
+    return output_file_src
+
+
+def build_parts(alphabet: int, text, n: int = None, sa_ratio: int = 8, device: int = 0):
+    """The construction pass of fm_index.rs:202-240 on the GPU.  `text`: uint8 numpy array (host) or an
+    int device pointer (then `n` is required).  -> (blocks, prefix_sums, sa_words, phase seconds)"""
+    L = native()
+    if isinstance(text, int):
+        ptr = text
+    else:
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        ptr, n = text.ctypes.data, len(text)
+    bwt_len = n + 1
+    blocks = np.empty(L.awry_parts_num_blocks(bwt_len) * L.awry_parts_block_words(int(alphabet)), dtype=np.uint64)
+    prefix = np.zeros(7 if int(alphabet) == 0 else 23, dtype=np.uint64)
+    sa_words = np.empty(L.awry_parts_sa_words(bwt_len, sa_ratio), dtype=np.uint64)
+    phases = np.zeros(8, dtype=np.float64)
+    _check(L.awry_build_parts(int(alphabet), ptr, n, sa_ratio, device, blocks.ctypes.data, prefix.ctypes.data,
+                              sa_words.ctypes.data, phases.ctypes.data))
+    names = ["ingest", "keys", "sort", "ties", "bwt", "milestones", "sa_pack_copy", "total"]
+    return blocks, prefix, sa_words, dict(zip(names, [float(x) for x in phases]))
 
 
 def profile_enable(on: bool):

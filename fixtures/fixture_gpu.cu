@@ -1,26 +1,14 @@
-// fixture_gpu.cu -- TEST/BENCH FIXTURE BUILDER on the GPU. Not part of the product path.
+// fixture_gpu.cu -- TEST/BENCH FIXTURES on the GPU. Not part of the product path.
 //
-// Builds, for a synthetic text, the arrays the reference's FmIndex::new produces
-// (/root/reference/src/fm_index.rs:202-240) in the REFERENCE layout -- BWT blocks of 256 rows
-// (bit-planes then u64 milestones, bwt.rs:12-25), prefix sums, bit-packed row-sampled suffix
-// array (compressed_suffix_array.rs:51-64) -- fast enough to be rebuilt inside every gpurun call
-// at the BASELINE sizes (3.1 Gbp DNA / 2 G residues).  The suffix array is one CUB radix sort
-// of (64-bit packed prefix, position) pairs; ties (suffixes sharing the whole packed prefix)
-// are rare on i.i.d. text and are resolved on the host by direct suffix comparison.
-// Cross-checked against the CPU builder (fixture_cpu.cpp) in tests/test_gpu_fixture.py.
-#include <algorithm>
-#include <chrono>
+// Device-side generators of the synthetic workloads of BASELINE.md: the seeded text (same counter-based
+// generator as fixture_cpu.cpp, so CPU and GPU fixtures agree byte for byte) and exact-substring
+// queries regenerated from the text's seed, written straight into device buffers.
+// (The GPU index builder that used to live here is now the product's awry_build_parts; the tests
+// check it bit for bit against the independent CPU builder in fixture_cpu.cpp.)
 #include <cstdint>
 #include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-#include <cub/device/device_select.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
 #include <cuda_runtime.h>
 #include <string>
-#include <vector>
 
 namespace {
 
@@ -29,15 +17,6 @@ int set_err(const std::string& m) {
   snprintf(g_err, sizeof g_err, "%s", m.c_str());
   return -1;
 }
-#define CU(x)                                                                     \
-  do {                                                                            \
-    cudaError_t e__ = (x);                                                        \
-    if (e__ != cudaSuccess) {                                                     \
-      char b__[400];                                                              \
-      snprintf(b__, sizeof b__, "%s: %s (line %d)", #x, cudaGetErrorString(e__), __LINE__); \
-      throw std::string(b__);                                                     \
-    }                                                                             \
-  } while (0)
 
 __host__ __device__ inline uint64_t mix64(uint64_t z) {
   z += 0x9E3779B97F4A7C15ull;
@@ -64,137 +43,11 @@ __host__ __device__ inline uint8_t index_to_ascii(int alphabet, uint8_t idx) {
   const char* A = "$ACDEFGHIKLMNPQRSTVWXY";
   return uint8_t(alphabet == 0 ? D[idx] : A[idx]);
 }
-__host__ __device__ inline uint8_t ascii_to_index(int alphabet, uint8_t ch) {
-  if (ch >= 'a' && ch <= 'z') ch = uint8_t(ch - 'a' + 'A');
-  if (ch == '$' || ch == '#') return 0;
-  if (alphabet == 0) return ch == 'A' ? 1 : ch == 'C' ? 2 : ch == 'G' ? 3 : (ch == 'T' || ch == 'U') ? 5 : 4;
-  const char* A = "$ACDEFGHIKLMNPQRSTVWXY";
-  for (int i = 1; i < 22; i++)
-    if (i != 20 && A[i] == char(ch)) return uint8_t(i);
-  return 20;
-}
-__host__ __device__ inline uint8_t index_to_code(int alphabet, uint8_t idx) {  // alphabet.rs:250-330
-  const uint8_t D[6] = {0x4, 0x6, 0x5, 0x3, 0x2, 0x1};
-  const uint8_t A[22] = {0x00, 0x0c, 0x17, 0x03, 0x06, 0x1e, 0x1a, 0x1b, 0x19, 0x15, 0x1c,
-                         0x1d, 0x08, 0x09, 0x04, 0x13, 0x0a, 0x05, 0x16, 0x01, 0x1f, 0x02};
-  return alphabet == 0 ? D[idx] : A[idx];
-}
 
-__global__ void gen_sym_kernel(int alphabet, uint64_t seed, uint64_t n, uint8_t* sym) {
+__global__ void gen_text_kernel(int alphabet, uint64_t seed, uint64_t n, uint8_t* out) {
   uint64_t stride = gridDim.x * uint64_t(blockDim.x);
-  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i <= n; i += stride)
-    sym[i] = i == n ? 0 : synth_index(alphabet, seed, i);
-}
-__global__ void ascii_to_sym_kernel(int alphabet, uint64_t n, uint8_t* sym) {  // in place; sym[n] = 0
-  uint64_t stride = gridDim.x * uint64_t(blockDim.x);
-  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i <= n; i += stride)
-    sym[i] = i == n ? 0 : ascii_to_index(alphabet, sym[i]);
-}
-
-// key = first SPK symbols of suffix i, BITS bits each, most significant first; positions past
-// the '$' read as 0.  BITS == 2 is only used for pure-ACGT text (A0 C1 G2 T3; '$' reads as 0,
-// which makes ties that the host fix-up resolves).
-template <int BITS>
-__global__ void make_keys_kernel(const uint8_t* __restrict__ sym, uint64_t n1, uint64_t first,
-                                 uint64_t count, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-  constexpr int SPK = 64 / BITS;
-  uint64_t stride = gridDim.x * uint64_t(blockDim.x);
-  for (uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; t < count; t += stride) {
-    uint64_t i = first + t;
-    uint64_t key = 0;
-#pragma unroll 8
-    for (int j = 0; j < SPK; j++) {
-      uint32_t s = i + j < n1 ? sym[i + j] : 0;
-      if (BITS == 2) s = s == 0 ? 0 : (s == 5 ? 3 : s - 1);
-      key = (key << BITS) | s;
-    }
-    if (BITS * SPK < 64) key <<= (64 - BITS * SPK);
-    keys[t] = key;
-    vals[t] = uint32_t(i);
-  }
-}
-
-__global__ void flag_ties_kernel(const uint64_t* __restrict__ keys, uint64_t n1, uint8_t* __restrict__ tied) {
-  uint64_t stride = gridDim.x * uint64_t(blockDim.x);
-  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n1; i += stride) {
-    bool t = (i > 0 && keys[i] == keys[i - 1]) || (i + 1 < n1 && keys[i] == keys[i + 1]);
-    tied[i] = t ? 1 : 0;
-  }
-}
-
-// One thread block per 256-row reference block: planes via warp ballots, per-block symbol counts.
-template <int ALPHA>
-__global__ void __launch_bounds__(256)
-    bwt_blocks_kernel(const uint8_t* __restrict__ sym, const uint32_t* __restrict__ sa, uint64_t n1,
-                      uint64_t* __restrict__ blocks, uint32_t* __restrict__ counts /* [card][n_blocks] */,
-                      uint64_t n_blocks) {
-  constexpr int PLANES = ALPHA == 0 ? 3 : 5;
-  constexpr int CARD = ALPHA == 0 ? 6 : 22;
-  constexpr int WORDS = PLANES * 4 + (ALPHA == 0 ? 8 : 24);
-  __shared__ uint32_t plane_words[PLANES][8];
-  __shared__ uint32_t cnt[CARD];
-  uint64_t b = blockIdx.x;
-  uint64_t row = b * 256 + threadIdx.x;
-  uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x < CARD) cnt[threadIdx.x] = 0;
-  __syncthreads();
-  bool valid = row < n1;
-  uint8_t idx = 0, code = 0;
-  if (valid) {
-    uint32_t v = sa[row];
-    idx = v == 0 ? 0 : sym[v - 1];  // fm_index.rs:220-223
-    code = index_to_code(ALPHA, idx);
-  }
-#pragma unroll
-  for (int p = 0; p < PLANES; p++) {
-    uint32_t w = __ballot_sync(0xffffffffu, valid && ((code >> p) & 1));
-    if (lane == 0) plane_words[p][warp] = w;
-  }
-  for (int s = 0; s < CARD; s++) {
-    uint32_t m = __ballot_sync(0xffffffffu, valid && idx == s);
-    if (lane == 0 && m) atomicAdd(&cnt[s], __popc(m));
-  }
-  __syncthreads();
-  uint64_t* out = blocks + b * WORDS;
-  if (threadIdx.x < PLANES * 4) {
-    int p = threadIdx.x / 4, w = threadIdx.x % 4;
-    out[threadIdx.x] = uint64_t(plane_words[p][2 * w]) | (uint64_t(plane_words[p][2 * w + 1]) << 32);
-  }
-  if (threadIdx.x < CARD) counts[uint64_t(threadIdx.x) * n_blocks + b] = cnt[threadIdx.x];
-}
-
-template <int ALPHA>
-__global__ void write_milestones_kernel(const uint64_t* __restrict__ ms /* [card][n_blocks] */,
-                                        uint64_t n_blocks, uint64_t* __restrict__ blocks) {
-  constexpr int PLANES = ALPHA == 0 ? 3 : 5;
-  constexpr int CARD = ALPHA == 0 ? 6 : 22;
-  constexpr int NMS = ALPHA == 0 ? 8 : 24;
-  constexpr int WORDS = PLANES * 4 + NMS;
-  uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-  if (t >= n_blocks * NMS) return;
-  uint64_t b = t / NMS;
-  int s = int(t % NMS);
-  blocks[b * WORDS + PLANES * 4 + s] = s < CARD ? ms[uint64_t(s) * n_blocks + b] : 0;
-}
-
-// one thread per output word of the bit-packed sampled SA
-__global__ void pack_sa_kernel(const uint32_t* __restrict__ sa, uint64_t n1, uint64_t ratio, uint32_t bits,
-                               uint64_t n_words, uint64_t* __restrict__ words) {
-  uint64_t w = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-  if (w >= n_words) return;
-  uint64_t n_elems = (n1 + ratio - 1) / ratio;
-  uint64_t lo_bit = w * 64, hi_bit = lo_bit + 63;
-  uint64_t e0 = lo_bit / bits, e1 = hi_bit / bits;
-  uint64_t out = 0;
-  for (uint64_t e = e0; e <= e1 && e < n_elems; e++) {
-    uint64_t v = sa[e * ratio];
-    uint64_t ebit = e * bits;
-    if (ebit >= lo_bit)
-      out |= v << (ebit - lo_bit);
-    else
-      out |= v >> (lo_bit - ebit);
-  }
-  words[w] = out;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += stride)
+    out[i] = index_to_ascii(alphabet, synth_index(alphabet, seed, i));
 }
 
 // queries regenerated from the text's seed: q = text[pos .. pos+qlen), optional single substitution
@@ -222,148 +75,6 @@ __global__ void gen_queries_kernel(int alphabet, uint64_t n, uint64_t text_seed,
   }
 }
 
-// ---- prefix doubling on the GPU (for repeat-rich text where many suffixes share the packed key) ----
-struct MaxOp {
-  __host__ __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
-};
-__global__ void pd_heads_kernel(const uint64_t* __restrict__ keys, uint64_t n1, uint8_t* __restrict__ head,
-                                uint32_t* __restrict__ v) {
-  uint64_t stride = gridDim.x * uint64_t(blockDim.x);
-  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n1; i += stride) {
-    bool hd = i == 0 || keys[i] != keys[i - 1];
-    head[i] = hd ? 1 : 0;
-    v[i] = hd ? uint32_t(i) : 0u;
-  }
-}
-__global__ void pd_scatter_rank_kernel(const uint32_t* __restrict__ sa, const uint32_t* __restrict__ grp, uint64_t n1,
-                                       uint32_t* __restrict__ rank) {
-  uint64_t stride = gridDim.x * uint64_t(blockDim.x);
-  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n1; i += stride) rank[sa[i]] = grp[i];
-}
-__global__ void pd_flag_unresolved_kernel(const uint8_t* __restrict__ head, uint64_t n1, uint8_t* __restrict__ unres) {
-  uint64_t stride = gridDim.x * uint64_t(blockDim.x);
-  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n1; i += stride)
-    unres[i] = (head[i] && (i + 1 == n1 || head[i + 1])) ? 0 : 1;
-}
-__global__ void pd_keys2_kernel(const uint32_t* __restrict__ U, uint64_t m, const uint32_t* __restrict__ sa,
-                                const uint32_t* __restrict__ grp, const uint32_t* __restrict__ rank, uint64_t h,
-                                uint64_t n1, uint64_t* __restrict__ keys2, uint32_t* __restrict__ vals2) {
-  uint64_t stride = gridDim.x * uint64_t(blockDim.x);
-  for (uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; j < m; j += stride) {
-    uint32_t slot = U[j], pos = sa[slot];
-    uint64_t nxt = uint64_t(pos) + h;
-    uint32_t k2 = nxt < n1 ? rank[nxt] + 1u : 0u;  // a suffix that ends first sorts first
-    keys2[j] = (uint64_t(grp[slot]) << 32) | k2;
-    vals2[j] = pos;
-  }
-}
-__global__ void pd_apply_kernel(const uint32_t* __restrict__ U, uint64_t m, const uint64_t* __restrict__ keys2,
-                                const uint32_t* __restrict__ vals2, uint32_t* __restrict__ sa,
-                                uint8_t* __restrict__ head, uint32_t* __restrict__ v) {
-  uint64_t stride = gridDim.x * uint64_t(blockDim.x);
-  for (uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; j < m; j += stride) {
-    uint32_t slot = U[j];
-    bool hd = j == 0 || keys2[j] != keys2[j - 1];
-    sa[slot] = vals2[j];
-    head[slot] = hd ? 1 : 0;
-    v[j] = hd ? slot : 0u;
-  }
-}
-__global__ void pd_regroup_kernel(const uint32_t* __restrict__ U, uint64_t m, const uint32_t* __restrict__ g2,
-                                  const uint32_t* __restrict__ sa, uint32_t* __restrict__ grp,
-                                  uint32_t* __restrict__ rank) {
-  uint64_t stride = gridDim.x * uint64_t(blockDim.x);
-  for (uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; j < m; j += stride) {
-    uint32_t slot = U[j];
-    grp[slot] = g2[j];
-    rank[sa[slot]] = g2[j];
-  }
-}
-
-// keys_sorted / sa: result of the first radix sort on keys of h0 symbols in which equal keys imply
-// equal first h0 symbols (3- or 5-bit keys).  Refines sa in place to the full suffix order.
-// kbuf[2]: two 8*n1-byte scratch buffers (the radix sort's key buffers), vscratch: 4*n1 bytes.
-int prefix_doubling(const uint64_t* keys_sorted, uint32_t* sa, uint64_t n1, uint64_t h0, uint64_t* kbuf0,
-                    uint64_t* kbuf1, uint32_t* vscratch, int* rounds_out) {
-  uint32_t *grp = nullptr, *rank = nullptr, *U = nullptr, *v = nullptr, *vals_out = nullptr;
-  uint8_t *head = nullptr, *unres = nullptr;
-  unsigned long long* d_num = nullptr;
-  void* d_temp = nullptr;
-  size_t temp_cap = 0;
-  auto need_temp = [&](size_t b) {
-    if (b > temp_cap) {
-      cudaFree(d_temp);
-      CU(cudaMalloc(&d_temp, b + 256));
-      temp_cap = b + 256;
-    }
-  };
-  int rounds = 0;
-  try {
-    CU(cudaMalloc(&grp, n1 * 4));
-    CU(cudaMalloc(&rank, n1 * 4));
-    CU(cudaMalloc(&U, n1 * 4));
-    CU(cudaMalloc(&v, n1 * 4));
-    CU(cudaMalloc(&vals_out, n1 * 4));
-    CU(cudaMalloc(&head, n1));
-    CU(cudaMalloc(&unres, n1));
-    CU(cudaMalloc(&d_num, 8));
-    const unsigned G = 148 * 16;
-    pd_heads_kernel<<<G, 256>>>(keys_sorted, n1, head, v);
-    size_t tb = 0;
-    CU(cub::DeviceScan::InclusiveScan(nullptr, tb, v, grp, MaxOp(), (long long)n1));
-    need_temp(tb);
-    CU(cub::DeviceScan::InclusiveScan(d_temp, tb, v, grp, MaxOp(), (long long)n1));
-    pd_scatter_rank_kernel<<<G, 256>>>(sa, grp, n1, rank);
-    // from here on the key buffers are scratch
-    for (uint64_t h = h0;; h *= 2) {
-      pd_flag_unresolved_kernel<<<G, 256>>>(head, n1, unres);
-      cub::CountingInputIterator<uint32_t> it(0);
-      CU(cub::DeviceSelect::Flagged(nullptr, tb, it, unres, U, d_num, (long long)n1));
-      need_temp(tb);
-      CU(cub::DeviceSelect::Flagged(d_temp, tb, it, unres, U, d_num, (long long)n1));
-      unsigned long long m = 0;
-      CU(cudaMemcpy(&m, d_num, 8, cudaMemcpyDeviceToHost));
-      if (m == 0) break;
-      if (h >= 2 * n1) throw std::string("prefix doubling did not converge");
-      rounds++;
-      pd_keys2_kernel<<<G, 256>>>(U, m, sa, grp, rank, h, n1, kbuf0, vscratch);
-      cub::DoubleBuffer<uint64_t> kb(kbuf0, kbuf1);
-      cub::DoubleBuffer<uint32_t> vb(vscratch, vals_out);
-      CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, kb, vb, (long long)m, 0, 64));
-      need_temp(tb);
-      CU(cub::DeviceRadixSort::SortPairs(d_temp, tb, kb, vb, (long long)m, 0, 64));
-      pd_apply_kernel<<<G, 256>>>(U, m, kb.Current(), vb.Current(), sa, head, v);
-      uint32_t* g2 = vb.Alternate();  // scratch for the regrouped starts
-      CU(cub::DeviceScan::InclusiveScan(nullptr, tb, v, g2, MaxOp(), (long long)m));
-      need_temp(tb);
-      CU(cub::DeviceScan::InclusiveScan(d_temp, tb, v, g2, MaxOp(), (long long)m));
-      pd_regroup_kernel<<<G, 256>>>(U, m, g2, sa, grp, rank);
-      CU(cudaDeviceSynchronize());
-    }
-  } catch (const std::string& msg) {
-    cudaFree(grp); cudaFree(rank); cudaFree(U); cudaFree(v); cudaFree(vals_out); cudaFree(head); cudaFree(unres);
-    cudaFree(d_num); cudaFree(d_temp);
-    throw;
-  }
-  cudaFree(grp); cudaFree(rank); cudaFree(U); cudaFree(v); cudaFree(vals_out); cudaFree(head); cudaFree(unres);
-  cudaFree(d_num); cudaFree(d_temp);
-  if (rounds_out) *rounds_out = rounds;
-  return 0;
-}
-
-double now_s() {
-  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
-}
-
-unsigned bits_per_element(uint64_t bwt_len) {
-  uint64_t v = bwt_len - 1;
-  return v ? 64u - unsigned(__builtin_clzll(v)) : 0u;
-}
-
-template <int BITS>
-void make_keys(const uint8_t* sym, uint64_t n1, uint64_t* keys, uint32_t* vals) {
-  make_keys_kernel<BITS><<<148 * 16, 256>>>(sym, n1, 0, n1, keys, vals);
-}
 
 }  // namespace
 
@@ -371,245 +82,13 @@ extern "C" {
 
 const char* fxg_last_error(void) { return g_err; }
 
-// Builds reference-layout index parts for text[0..n) + '$'.  host_text == NULL: the text is the
-// synthetic one of (alphabet, text_seed) (same generator as fx_gen_text).  Outputs are host
-// arrays sized like fixture_cpu's: blocks, prefix_sums (card+1), sa_words.  phase_s (8 doubles,
-// may be NULL): gen, keys, sort, ties, bwt, milestones, sa-pack+copy, total.
-int fxg_build(int alphabet, uint64_t n, uint64_t text_seed, const uint8_t* host_text, uint64_t ratio,
-              int device, uint64_t* blocks_out, uint64_t* prefix_sums_out, uint64_t* sa_words_out,
-              double* phase_s) {
-  uint8_t* d_sym = nullptr;
-  uint64_t *d_keys[2] = {nullptr, nullptr}, *d_blocks = nullptr, *d_ms = nullptr, *d_saw = nullptr;
-  uint32_t *d_vals[2] = {nullptr, nullptr}, *d_counts = nullptr;
-  uint8_t* d_tied = nullptr;
-  void* d_temp = nullptr;
-  int rc = 0;
-  double ph[8] = {0};
-  try {
-    if (ratio == 0) throw std::string("ratio must be >= 1");
-    const uint64_t n1 = n + 1;
-    if (n1 >= (1ull << 32)) throw std::string("GPU fixture builder is limited to < 2^32 symbols");
-    CU(cudaSetDevice(device));
-    const int card = alphabet == 0 ? 6 : 22;
-    const size_t words_per_block = alphabet == 0 ? 20 : 44;
-    const uint64_t n_blocks = (n1 + 255) / 256;
-    double t0 = now_s(), t = t0;
-    CU(cudaMalloc(&d_sym, n1 + 64));
-    bool pure2 = alphabet == 0;
-    if (host_text) {
-      CU(cudaMemcpy(d_sym, host_text, n, cudaMemcpyHostToDevice));
-      ascii_to_sym_kernel<<<148 * 16, 256>>>(alphabet, n, d_sym);
-      if (alphabet == 0)
-        for (uint64_t i = 0; i < n && pure2; i++) {
-          uint8_t x = ascii_to_index(0, host_text[i]);
-          if (x == 4 || x == 0) pure2 = false;
-        }
-      for (uint64_t i = 0; i < n; i++)
-        if (host_text[i] == '$' || host_text[i] == '#') throw std::string("text contains a sentinel");
-    } else {
-      gen_sym_kernel<<<148 * 16, 256>>>(alphabet, text_seed, n, d_sym);
-    }
-    CU(cudaDeviceSynchronize());
-    ph[0] = now_s() - t;
-    t = now_s();
-
-    for (int i = 0; i < 2; i++) {
-      CU(cudaMalloc(&d_keys[i], n1 * 8));
-      CU(cudaMalloc(&d_vals[i], n1 * 4));
-    }
-    if (alphabet == 0 && pure2)
-      make_keys<2>(d_sym, n1, d_keys[0], d_vals[0]);
-    else if (alphabet == 0)
-      make_keys<3>(d_sym, n1, d_keys[0], d_vals[0]);
-    else
-      make_keys<5>(d_sym, n1, d_keys[0], d_vals[0]);
-    CU(cudaDeviceSynchronize());
-    ph[1] = now_s() - t;
-    t = now_s();
-
-    cub::DoubleBuffer<uint64_t> kb(d_keys[0], d_keys[1]);
-    cub::DoubleBuffer<uint32_t> vb(d_vals[0], d_vals[1]);
-    size_t temp_bytes = 0;
-    CU(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, kb, vb, (long long)n1, 0, 64));
-    CU(cudaMalloc(&d_temp, temp_bytes));
-    CU(cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, kb, vb, (long long)n1, 0, 64));
-    CU(cudaDeviceSynchronize());
-    cudaFree(d_temp);
-    d_temp = nullptr;
-    ph[2] = now_s() - t;
-    t = now_s();
-    uint64_t* keys_sorted = kb.Current();
-    uint32_t* sa = vb.Current();
-
-    // ---- ties: rows whose key equals a neighbour's; fixed on the host by suffix comparison
-    CU(cudaMalloc(&d_tied, n1));
-    flag_ties_kernel<<<148 * 16, 256>>>(keys_sorted, n1, d_tied);
-    // compact the tied row numbers
-    uint32_t* d_rows = vb.Alternate();  // scratch: the other value buffer
-    unsigned long long* d_num = nullptr;
-    CU(cudaMalloc(&d_num, 8));
-    {
-      cub::CountingInputIterator<uint32_t> it(0);
-      size_t tb = 0;
-      CU(cub::DeviceSelect::Flagged(nullptr, tb, it, d_tied, d_rows, d_num, (long long)n1));
-      CU(cudaMalloc(&d_temp, tb));
-      CU(cub::DeviceSelect::Flagged(d_temp, tb, it, d_tied, d_rows, d_num, (long long)n1));
-      CU(cudaDeviceSynchronize());
-      cudaFree(d_temp);
-      d_temp = nullptr;
-    }
-    unsigned long long n_tied = 0;
-    CU(cudaMemcpy(&n_tied, d_num, 8, cudaMemcpyDeviceToHost));
-    cudaFree(d_num);
-    unsigned long long HOST_FIXUP_MAX = 2000000ull;
-    if (const char* e = getenv("AWRY_FIXTURE_HOST_FIXUP_MAX")) HOST_FIXUP_MAX = strtoull(e, nullptr, 10);
-    if (n_tied > HOST_FIXUP_MAX) {
-      // repeat-rich text: GPU prefix doubling.  It needs keys whose equality implies equality of the
-      // first h0 symbols, which the 2-bit keys (sentinel packed as 'A') do not give: redo with 3 bits.
-      cudaFree(d_tied);
-      d_tied = nullptr;
-      uint64_t h0 = alphabet == 0 ? 21 : 12;
-      if (alphabet == 0 && pure2) {
-        make_keys<3>(d_sym, n1, d_keys[0], d_vals[0]);
-        cub::DoubleBuffer<uint64_t> kb3(d_keys[0], d_keys[1]);
-        cub::DoubleBuffer<uint32_t> vb3(d_vals[0], d_vals[1]);
-        size_t tb3 = 0;
-        CU(cub::DeviceRadixSort::SortPairs(nullptr, tb3, kb3, vb3, (long long)n1, 0, 64));
-        CU(cudaMalloc(&d_temp, tb3));
-        CU(cub::DeviceRadixSort::SortPairs(d_temp, tb3, kb3, vb3, (long long)n1, 0, 64));
-        CU(cudaDeviceSynchronize());
-        cudaFree(d_temp);
-        d_temp = nullptr;
-        keys_sorted = kb3.Current();
-        sa = vb3.Current();
-      }
-      uint64_t* other_keys = keys_sorted == d_keys[0] ? d_keys[1] : d_keys[0];
-      uint32_t* other_vals = sa == d_vals[0] ? d_vals[1] : d_vals[0];
-      // the doubling rounds reuse the key buffers as scratch once the group heads are extracted;
-      // keys_sorted itself is only read by the first kernel, so it may serve as scratch too
-      int rounds = 0;
-      prefix_doubling(keys_sorted, sa, n1, h0, other_keys, const_cast<uint64_t*>(keys_sorted), other_vals, &rounds);
-      ph[3] = now_s() - t;
-      t = now_s();
-    } else if (n_tied > 0) {
-      std::vector<uint32_t> rows(n_tied), pos(n_tied);
-      std::vector<uint64_t> rkeys(n_tied);
-      CU(cudaMemcpy(rows.data(), d_rows, n_tied * 4, cudaMemcpyDeviceToHost));
-      // gather positions and keys of the tied rows
-      for (unsigned long long i = 0; i < n_tied;) {  // runs of consecutive rows -> few large copies
-        unsigned long long j = i + 1;
-        while (j < n_tied && rows[j] == rows[j - 1] + 1) j++;
-        CU(cudaMemcpy(pos.data() + i, sa + rows[i], (j - i) * 4, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(rkeys.data() + i, keys_sorted + rows[i], (j - i) * 8, cudaMemcpyDeviceToHost));
-        i = j;
-      }
-      std::vector<uint8_t> hsym(n1);
-      CU(cudaMemcpy(hsym.data(), d_sym, n1, cudaMemcpyDeviceToHost));
-      auto less = [&](uint32_t a, uint32_t b) {
-        if (a == b) return false;
-        uint64_t k = 0;
-        while (hsym[a + k] == hsym[b + k]) k++;  // terminates: '$' is unique
-        return hsym[a + k] < hsym[b + k];
-      };
-      for (unsigned long long i = 0; i < n_tied;) {
-        unsigned long long j = i + 1;
-        while (j < n_tied && rows[j] == rows[j - 1] + 1 && rkeys[j] == rkeys[i]) j++;
-        std::sort(pos.begin() + i, pos.begin() + j, less);
-        CU(cudaMemcpy(sa + rows[i], pos.data() + i, (j - i) * 4, cudaMemcpyHostToDevice));
-        i = j;
-      }
-    }
-    cudaFree(d_tied);
-    d_tied = nullptr;
-    if (n_tied <= HOST_FIXUP_MAX) {
-      ph[3] = now_s() - t;
-      t = now_s();
-    }
-
-    // keys are no longer needed: free them before allocating the outputs
-    uint32_t* sa_keep = sa;
-    for (int i = 0; i < 2; i++) {
-      cudaFree(d_keys[i]);
-      d_keys[i] = nullptr;
-      if (d_vals[i] != sa_keep) {
-        cudaFree(d_vals[i]);
-        d_vals[i] = nullptr;
-      }
-    }
-
-    CU(cudaMalloc(&d_blocks, n_blocks * words_per_block * 8));
-    CU(cudaMemset(d_blocks, 0, n_blocks * words_per_block * 8));
-    CU(cudaMalloc(&d_counts, uint64_t(card) * n_blocks * 4));
-    CU(cudaMalloc(&d_ms, uint64_t(card) * n_blocks * 8));
-    if (alphabet == 0)
-      bwt_blocks_kernel<0><<<unsigned(n_blocks), 256>>>(d_sym, sa, n1, d_blocks, d_counts, n_blocks);
-    else
-      bwt_blocks_kernel<1><<<unsigned(n_blocks), 256>>>(d_sym, sa, n1, d_blocks, d_counts, n_blocks);
-    CU(cudaDeviceSynchronize());
-    ph[4] = now_s() - t;
-    t = now_s();
-
-    {
-      size_t tb = 0;
-      CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_counts, d_ms, (long long)n_blocks));
-      CU(cudaMalloc(&d_temp, tb));
-      std::vector<uint64_t> totals(card, 0);
-      for (int s = 0; s < card; s++) {
-        CU(cub::DeviceScan::ExclusiveSum(d_temp, tb, d_counts + uint64_t(s) * n_blocks,
-                                         d_ms + uint64_t(s) * n_blocks, (long long)n_blocks));
-        uint64_t last_ms = 0;
-        uint32_t last_cnt = 0;
-        CU(cudaMemcpy(&last_ms, d_ms + uint64_t(s) * n_blocks + n_blocks - 1, 8, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(&last_cnt, d_counts + uint64_t(s) * n_blocks + n_blocks - 1, 4, cudaMemcpyDeviceToHost));
-        totals[s] = last_ms + last_cnt;
-      }
-      cudaFree(d_temp);
-      d_temp = nullptr;
-      uint64_t acc = 0;  // fm_index.rs:233-240
-      for (int c = 0; c <= card; c++) {
-        prefix_sums_out[c] = acc;
-        if (c < card) acc += totals[c];
-      }
-      const int nms = alphabet == 0 ? 8 : 24;
-      uint64_t threads = n_blocks * nms;
-      if (alphabet == 0)
-        write_milestones_kernel<0><<<unsigned((threads + 255) / 256), 256>>>(d_ms, n_blocks, d_blocks);
-      else
-        write_milestones_kernel<1><<<unsigned((threads + 255) / 256), 256>>>(d_ms, n_blocks, d_blocks);
-      CU(cudaDeviceSynchronize());
-    }
-    cudaFree(d_counts);
-    d_counts = nullptr;
-    cudaFree(d_ms);
-    d_ms = nullptr;
-    ph[5] = now_s() - t;
-    t = now_s();
-
-    unsigned bits = bits_per_element(n1);
-    uint64_t n_elems = (n1 + ratio - 1) / ratio;
-    uint64_t n_words = uint64_t(((unsigned __int128)n_elems * bits + 63) / 64);
-    CU(cudaMalloc(&d_saw, (n_words + 1) * 8));
-    pack_sa_kernel<<<unsigned((n_words + 255) / 256), 256>>>(sa, n1, ratio, bits, n_words, d_saw);
-    CU(cudaMemcpy(sa_words_out, d_saw, n_words * 8, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(blocks_out, d_blocks, n_blocks * words_per_block * 8, cudaMemcpyDeviceToHost));
-    ph[6] = now_s() - t;
-    ph[7] = now_s() - t0;
-  } catch (const std::string& m) {
-    rc = set_err(m);
-  }
-  cudaFree(d_sym);
-  for (int i = 0; i < 2; i++) {
-    cudaFree(d_keys[i]);
-    cudaFree(d_vals[i]);
-  }
-  cudaFree(d_blocks);
-  cudaFree(d_ms);
-  cudaFree(d_saw);
-  cudaFree(d_counts);
-  cudaFree(d_tied);
-  cudaFree(d_temp);
-  if (phase_s) memcpy(phase_s, ph, sizeof ph);
-  return rc;
+// ASCII text of (alphabet, seed) into a DEVICE buffer of n bytes (== fx_gen_text on the host)
+int fxg_gen_text_device(int alphabet, uint64_t n, uint64_t seed, void* d_out, void* stream) {
+  gen_text_kernel<<<148 * 16, 256, 0, static_cast<cudaStream_t>(stream)>>>(alphabet, seed, n,
+                                                                           static_cast<uint8_t*>(d_out));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err(cudaGetErrorString(e));
+  return 0;
 }
 
 // Synthetic queries straight into a DEVICE buffer (nq*qlen ASCII bytes): exact substrings of the

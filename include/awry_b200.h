@@ -113,6 +113,42 @@ int awry_index_info(const awry_index *index, awry_info *info);
 int awry_index_sequence_header(const awry_index *index, uint64_t seq_idx, const char **header,
                                uint64_t *header_len);
 
+/* ------------------------------------------------------------------ index construction on the GPU
+ * the reference builds on the CPU (FmIndex::new, fm_index.rs:142-268, libsufr suffix
+ * sort) and that path stays valid (awry_index_from_parts).  These entry points do the same work on
+ * the device and emit the reference's layout / file format. */
+
+/* FmBuildArgs (fm_index.rs:78-96), the fields that still mean something without libsufr */
+typedef struct awry_build_args {
+  const char *input_file_src;   /* FASTA or FASTQ */
+  const char *output_file_src;  /* `.awry` v1 file to write (FmIndex::save, fm_index_file.rs:42), or NULL */
+  uint32_t alphabet;            /* AWRY_NUCLEOTIDE / AWRY_AMINO */
+  uint32_t lookup_table_kmer_len;          /* 0 = default 10 / 4 (kmer_lookup_table.rs:23-24) */
+  uint64_t suffix_array_compression_ratio; /* 0 = default 8 (fm_index.rs:122) */
+  int32_t device;
+} awry_build_args;
+
+/* FmIndex::new (fm_index.rs:142-268): reads the sequence file (records upper-cased and joined by
+ * 'N' / 'X', as libsufr's read_sequence_file does for the reference), builds the index on
+ * devices[0] (args->device when `devices` is NULL) and returns a ready-to-search handle replicated on
+ * `devices`, like awry_index_load.  When args->output_file_src is not NULL it also does FmIndex::save
+ * (fm_index_file.rs:42-106): an `.awry` v1 file the reference can load, including its k-mer table
+ * section populated the way kmer_lookup_table.rs:121-167 does.  `out` may be NULL (file only).
+ * I/O and format errors of the input are reported before any device is touched. */
+int awry_index_build(const awry_build_args *args, const int *devices, int n_dev, awry_index **out);
+
+/* FmIndex::new + FmIndex::save without keeping the index: awry_index_build(args, NULL, 0, NULL). */
+int awry_build_index_file(const awry_build_args *args);
+
+/* The single construction pass of fm_index.rs:202-240 for text[0..n) + '$' (ASCII, host OR device
+ * pointer): fills caller-owned reference-layout arrays sized by the helpers below, ready for
+ * awry_index_from_parts.  phase_seconds: 8 doubles or NULL. */
+int awry_build_parts(uint32_t alphabet, const uint8_t *text, uint64_t n, uint64_t sa_ratio, int device,
+                     uint64_t *blocks, uint64_t *prefix_sums, uint64_t *sa_words, double *phase_seconds);
+uint64_t awry_parts_num_blocks(uint64_t bwt_len);                   /* bwt.rs:302-304 */
+uint64_t awry_parts_block_words(uint32_t alphabet);                 /* 20 / 44 u64 per block */
+uint64_t awry_parts_sa_words(uint64_t bwt_len, uint64_t sa_ratio);  /* compressed_suffix_array.rs:113-123 */
+
 /* ------------------------------------------------------------------ batched search (host buffers) */
 
 /* FmIndex::parallel_count (fm_index.rs:455-460); count_string (:499-501) is a batch of one.

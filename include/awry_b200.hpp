@@ -43,12 +43,32 @@ struct LocalizedSequencePosition {  // sequence_index.rs:32-78
   }
 };
 
+struct FmBuildArgs {  // fm_index.rs:78-96; 0 = the reference's default (ratio 8, k 10 / 4)
+  std::string input_file_src;
+  uint64_t suffix_array_compression_ratio = 0;
+  uint32_t lookup_table_kmer_len = 0;
+  SymbolAlphabet alphabet = SymbolAlphabet::Nucleotide;
+};
+
 class FmIndex {
  public:
   // FmIndex::load (fm_index_file.rs:132)
   static FmIndex load(const std::string& path, const std::vector<int>& devices = {}) {
     awry_index* h = nullptr;
     check(awry_index_load(path.c_str(), devices.empty() ? nullptr : devices.data(), int(devices.size()), &h));
+    return FmIndex(h);
+  }
+  // FmIndex::new (fm_index.rs:142-268) on the GPU; `save_to` non-empty = also FmIndex::save
+  static FmIndex build(const FmBuildArgs& args, const std::vector<int>& devices = {}, const std::string& save_to = "") {
+    awry_build_args a{};
+    a.input_file_src = args.input_file_src.c_str();
+    a.output_file_src = save_to.empty() ? nullptr : save_to.c_str();
+    a.alphabet = uint32_t(args.alphabet);
+    a.lookup_table_kmer_len = args.lookup_table_kmer_len;
+    a.suffix_array_compression_ratio = args.suffix_array_compression_ratio;
+    a.device = devices.empty() ? 0 : devices[0];
+    awry_index* h = nullptr;
+    check(awry_index_build(&a, devices.empty() ? nullptr : devices.data(), int(devices.size()), &h));
     return FmIndex(h);
   }
   // hand-over from the reference's CPU construction (FmIndex::new, fm_index.rs:142-268)

@@ -89,6 +89,20 @@ def test_bad_arguments_are_errors_not_crashes(tmp_path):
     lib.awry_hits_free(None)
     assert lib.awry_profile_get(None) == -1
     assert lib.awry_set_search_variant(3, 0, 0) == -1
+    # construction: argument and input-file errors are reported before any device is needed
+    assert lib.awry_index_build(None, None, 0, C.byref(out)) == -1
+    assert lib.awry_build_index_file(None) == -1
+    a = f.BuildArgs(b"/nonexistent/in.fa", os.fsencode(str(tmp_path / "o.awry")), 0, 0, 0, 0)
+    assert lib.awry_build_index_file(C.byref(a)) == -2 and b"cannot open" in lib.awry_last_error()
+    notfa = tmp_path / "reads.txt"
+    notfa.write_text("ACGT\n")
+    a = f.BuildArgs(os.fsencode(str(notfa)), None, 0, 0, 0, 0)
+    assert lib.awry_build_index_file(C.byref(a)) == -1          # no output file
+    assert lib.awry_index_build(C.byref(a), None, 0, C.byref(out)) == -2 and b"FASTA" in lib.awry_last_error()
+    a = f.BuildArgs(os.fsencode(str(notfa)), None, 7, 0, 0, 0)
+    assert lib.awry_index_build(C.byref(a), None, 0, C.byref(out)) == -1
+    assert lib.awry_parts_num_blocks(257) == 2 and lib.awry_parts_block_words(0) == 20 and lib.awry_parts_block_words(1) == 44
+    assert lib.awry_parts_sa_words(123451, 8) == (15432 * 17 + 63) // 64   # compressed_suffix_array.rs:113-130
 
 
 def test_product_never_touches_the_oracle():
