@@ -137,6 +137,8 @@ void prof_collect_locked() {
 }
 
 SearchVariant g_variant;  // experiments only (awry_set_search_variant)
+int g_locate_variant = 0;   // 0 = unsampled-SA gather when the array exists, 1 = always LF-walk (awry_set_locate_variant)
+
 
 // ------------------------------------------------------------------ index
 
@@ -223,9 +225,10 @@ struct Replica {
   uint64_t* d_sa = nullptr;
   uint2* d_table = nullptr;
   uint4* d_pair = nullptr;
+  uint32_t* d_full_sa = nullptr;  // unsampled suffix array (locate accelerator)
   uint64_t* d_seq_starts = nullptr;
   unsigned long long* d_async_flag = nullptr;  // first bad query seen by *_device calls
-  size_t bytes_blocks = 0, bytes_sa = 0, bytes_table = 0, bytes_pair = 0;
+  size_t bytes_blocks = 0, bytes_sa = 0, bytes_table = 0, bytes_pair = 0, bytes_full_sa = 0;
   uint32_t c2[16] = {0};
   IndexView view{};
   std::mutex ws_mu;
@@ -318,6 +321,7 @@ void set_view_constants(awry_index* ix, Replica& r) {
   v.table = r.d_table;
   v.seq_starts = r.d_seq_starts;
   v.pair_blocks = r.d_pair;
+  v.full_sa = r.d_full_sa;
   for (int i = 0; i < 16; i++) v.c2[i] = r.c2[i];
   v.bwt_len = uint32_t(ix->bwt_len);
   v.sa_ratio = uint32_t(ix->sa_ratio);
@@ -446,7 +450,7 @@ void keep_pool_memory(int device) {
 }
 
 // set by awry_index_build for replicas that exist only to fill a file's k-mer table section
-thread_local bool g_skip_pair_index = false;
+thread_local bool g_skip_accelerators = false;
 
 void finish_replica0(awry_index* ix, Replica& r) {
   DeviceGuard dg(r.device);
@@ -479,7 +483,7 @@ void finish_replica0(awry_index* ix, Replica& r) {
   }
   // nucleotide pair index: two query symbols per block access (AWRY_B200_PAIR_INDEX=0 disables)
   const char* env = getenv("AWRY_B200_PAIR_INDEX");
-  bool want_pair = ix->alphabet == AWRY_NUCLEOTIDE && !(env && env[0] == '0') && !g_skip_pair_index;
+  bool want_pair = ix->alphabet == AWRY_NUCLEOTIDE && !(env && env[0] == '0') && !g_skip_accelerators;
   if (want_pair) {
     size_t bytes = size_t(pair_block_count(ix->bwt_len)) * 128;
     CU(cudaMemGetInfo(&free_b, &total_b));
@@ -489,6 +493,21 @@ void finish_replica0(awry_index* ix, Replica& r) {
       r.bytes_pair = bytes;
       r.view.pair_blocks = r.d_pair;
       for (int i = 0; i < 16; i++) r.view.c2[i] = r.c2[i];
+    }
+  }
+  // unsampled suffix array: locate becomes a gather instead of a geometric LF-walk per hit.
+  // AWRY_B200_FULL_SA=0 never, =1 whenever it fits, default: when it takes < 1/3 of the free memory.
+  const char* fs = getenv("AWRY_B200_FULL_SA");
+  if (!(fs && fs[0] == '0') && !g_skip_accelerators && ix->sa_ratio > 1) {
+    size_t bytes = size_t(ix->bwt_len) * 4;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    const bool force = fs && fs[0] == '1';
+    if (force ? bytes + (1u << 28) < free_b : bytes < free_b / 3) {
+      CU(cudaMalloc(reinterpret_cast<void**>(&r.d_full_sa), bytes + 256));
+      CU(build_full_sa(r.view, r.d_full_sa, r.sm_count, nullptr));
+      CU(cudaDeviceSynchronize());
+      r.bytes_full_sa = bytes;
+      r.view.full_sa = r.d_full_sa;
     }
   }
 }
@@ -519,6 +538,11 @@ void clone_replica(awry_index* ix, const Replica& src, Replica& dst) {
     CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_pair), src.bytes_pair + 256));
     CU(cudaMemcpyPeer(dst.d_pair, dst.device, src.d_pair, src.device, src.bytes_pair));
     memcpy(dst.c2, src.c2, sizeof dst.c2);
+  }
+  if (src.bytes_full_sa) {
+    dst.bytes_full_sa = src.bytes_full_sa;
+    CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_full_sa), src.bytes_full_sa + 256));
+    CU(cudaMemcpyPeer(dst.d_full_sa, dst.device, src.d_full_sa, src.device, src.bytes_full_sa));
   }
   uint32_t dollar = src.view.dollar_row;
   set_view_constants(ix, dst);
@@ -815,6 +839,8 @@ uint64_t locate_chunk_count(Replica& r, Workspace* ws, uint64_t nq, uint64_t* d_
 uint64_t* locate_chunk_walk(Replica& r, Workspace* ws, uint64_t nq, uint64_t n_hits, uint32_t flags,
                             const uint64_t* d_hit_off, cudaStream_t st) {
   if (n_hits == 0) return nullptr;
+  IndexView view = r.view;
+  if (g_locate_variant == 1) view.full_sa = nullptr;
   const uint2* d_sp_cnt = reinterpret_cast<const uint2*>(ws->d_out);
   uint64_t* d_hits = nullptr;
   CU(cudaMallocAsync(reinterpret_cast<void**>(&d_hits), n_hits * 16, st));  // pool: no driver round trip
@@ -825,18 +851,18 @@ uint64_t* locate_chunk_walk(Replica& r, Workspace* ws, uint64_t nq, uint64_t n_h
       CU(cudaMallocAsync(reinterpret_cast<void**>(&d_sorted), n_hits * 8, st));
       {
         ProfScope p(1, r.device, st);
-        CU(launch_walk(r.view, d_sp_cnt, d_hit_off, nq, n_hits, nullptr, d_locs, r.sm_count, st));
+        CU(launch_walk(view, d_sp_cnt, d_hit_off, nq, n_hits, nullptr, d_locs, r.sm_count, st));
       }
       size_t t2 = 0;
       CU(sort_hit_segments(d_locs, d_sorted, n_hits, nq, d_hit_off, nullptr, t2, st));
       Workspace::grow_dev(reinterpret_cast<uint8_t*&>(ws->d_temp), ws->d_temp_cap, t2 + 16);
       CU(sort_hit_segments(d_locs, d_sorted, n_hits, nq, d_hit_off, ws->d_temp, t2, st));
-      CU(launch_map_locations(r.view, d_sorted, n_hits, d_hits, st));
+      CU(launch_map_locations(view, d_sorted, n_hits, d_hits, st));
       cudaFreeAsync(d_locs, st);
       cudaFreeAsync(d_sorted, st);
     } else {
       ProfScope p(1, r.device, st);
-      CU(launch_walk(r.view, d_sp_cnt, d_hit_off, nq, n_hits, d_hits, nullptr, r.sm_count, st));
+      CU(launch_walk(view, d_sp_cnt, d_hit_off, nq, n_hits, d_hits, nullptr, r.sm_count, st));
     }
   } catch (...) {
     cudaFreeAsync(d_hits, st);
@@ -1072,9 +1098,9 @@ int awry_index_build(const awry_build_args* a, const int* devices, int n_dev, aw
     parts.headers = hdr_ptrs.data();
     parts.n_sequences = starts.size();
     awry_index* ix = nullptr;
-    g_skip_pair_index = !out;
+    g_skip_accelerators = !out;
     int rc = awry_index_from_parts(&parts, devs.data(), int(devs.size()), &ix);
-    g_skip_pair_index = false;
+    g_skip_accelerators = false;
     if (rc != AWRY_OK) throw ApiError(rc, g_err);
     std::unique_ptr<awry_index, void (*)(awry_index*)> holder(ix, awry_index_free);
     if (a->output_file_src) {  // FmIndex::save (fm_index_file.rs:42-106)
@@ -1150,6 +1176,7 @@ void awry_index_free(awry_index* ix) {
     cudaFree(r.d_sa);
     cudaFree(r.d_table);
     cudaFree(r.d_pair);
+    cudaFree(r.d_full_sa);
     cudaFree(r.d_seq_starts);
     cudaFree(r.d_async_flag);
   }
@@ -1174,6 +1201,7 @@ int awry_index_info(const awry_index* ix, awry_info* info) {
     info->device_bytes_sa = ix->reps[0]->bytes_sa;
     info->device_bytes_table = ix->reps[0]->bytes_table;
     info->device_bytes_pair = ix->reps[0]->bytes_pair;
+    info->device_bytes_full_sa = ix->reps[0]->bytes_full_sa;
     for (size_t i = 0; i < ix->reps.size() && i < 16; i++) info->devices[i] = ix->reps[i]->device;
   });
 }
@@ -1522,6 +1550,13 @@ int awry_bench_random_gather(int device, uint64_t footprint_bytes, uint32_t gran
     cudaError_t e = run_random_gather(footprint_bytes, granule, lanes, n_reads, iters, reads_per_s, gb_per_s);
     if (e == cudaErrorInvalidValue) fail(AWRY_ERR_INVALID_ARG, "unsupported granule/lanes combination %u/%u", granule, lanes);
     CU(e);
+  });
+}
+
+int awry_set_locate_variant(int variant) {
+  return guarded([&] {
+    if (variant != 0 && variant != 1) fail(AWRY_ERR_INVALID_ARG, "locate variant must be 0 (default) or 1 (LF-walk)");
+    g_locate_variant = variant;
   });
 }
 

@@ -1410,12 +1410,181 @@ __global__ void __launch_bounds__(256) walk_amino_kernel(IndexView ix, uint64_t 
   }
 }
 
+// ---- unsampled suffix array: the locate accelerator (derived at load time, like the pair index) ----
+// The reference keeps SA[row] only for rows with row % ratio == 0 (compressed_suffix_array.rs:109-111)
+// and pays a geometric LF-walk per hit (fm_index.rs:521-537).  180 GB of HBM hold the whole array:
+// 4 B x bwt_len (12.4 GB for the 3.1 Gbp config).  It is rebuilt from the sampled one with ONE LF step
+// per BWT row: a walker starts at every sampled row r with p = SA[r] and writes SA[LF^s(r)] = p - s
+// until it reaches the next sampled row or the '$' row (SA = 0); the LF permutation is one cycle cut at
+// the sampled rows, so every row is written exactly once.  Same lane-group step as the walk kernels.
+__global__ void __launch_bounds__(256)
+    unsample_dna_kernel(IndexView ix, uint64_t n_elems, uint32_t* __restrict__ full) {
+  constexpr uint32_t FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31, sub = lane & 1, gbase = lane - sub;
+  const uint64_t stride = (gridDim.x * uint64_t(blockDim.x)) >> 1;
+  uint64_t e = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 1;
+  uint32_t row = 0, p = 0;
+  bool have = false;
+  for (;;) {
+    if (!have && e < n_elems) {
+      row = uint32_t(e * ix.sa_ratio);
+      p = uint32_t(sa_sample(ix, row));
+      e += stride;
+      have = true;
+      if (sub == 0) full[row] = p;
+    }
+    if (__all_sync(FULL, !have)) break;
+    const uint32_t blk = row >> 7, l = row & 127;
+    LaneChunks<2> x;
+    x.c[0] = x.c[1] = make_uint4(0, 0, 0, 0);
+    if (have) x.load(ix.blocks + size_t(blk) * DNA_BLOCK_UINT4, sub);
+    const uint4 ch = (l & 32) ? x.c[1] : x.c[0];
+    const uint32_t t = l & 31;
+    uint32_t c = ((ch.x >> t) & 1u) | (((ch.y >> t) & 1u) << 1) | (((ch.z >> t) & 1u) << 2);
+    c = __shfl_sync(FULL, c, gbase + (l >> 6));
+    uint32_t r = 0;
+    if (have && c < 4) r = dna_partial_rank<2>(x, sub, l, c, (c & 1) ? ~0u : 0u, (c & 2) ? ~0u : 0u);
+    r += __shfl_xor_sync(FULL, r, 1);
+    if (have) {
+      if (c >= uint32_t(DNA_SENTINEL)) {
+        have = false;  // the '$' row (SA = 0, already written): LF would wrap to row 0, a sampled row
+      } else {
+        row = c == uint32_t(DNA_N) ? lf_backstep<0>(ix, row) : ix.c_lo[c] + r - 1;
+        p--;
+        if (row_is_sampled(ix, row))
+          have = false;
+        else if (sub == 0)
+          full[row] = p;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    unsample_amino_kernel(IndexView ix, uint64_t n_elems, uint32_t* __restrict__ full) {
+  constexpr uint32_t FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31, sub = lane & 3, gbase = lane - sub;
+  const uint64_t stride = (gridDim.x * uint64_t(blockDim.x)) >> 2;
+  uint64_t e = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 2;
+  uint32_t row = 0, p = 0;
+  bool have = false;
+  for (;;) {
+    if (!have && e < n_elems) {
+      row = uint32_t(e * ix.sa_ratio);
+      p = uint32_t(sa_sample(ix, row));
+      e += stride;
+      have = true;
+      if (sub == 0) full[row] = p;
+    }
+    if (__all_sync(FULL, !have)) break;
+    const uint32_t blk = row >> 6, l = row & 63;
+    u32x8 x;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x.v[i] = 0;
+    if (have) x = ldg256(ix.blocks + size_t(blk) * AMINO_BLOCK_UINT4 + 2 * sub);
+    const uint32_t t = l & 31;
+    uint32_t c = 0;
+#pragma unroll
+    for (int q = 0; q < 5; q++) c |= ((x.v[q] >> t) & 1u) << q;
+    c = __shfl_sync(FULL, c, gbase + (l >> 5));
+    uint32_t r = 0;
+    const bool sym_ok = c != uint32_t(AMINO_SENTINEL) && c <= 21;
+    if (have && sym_ok) {
+      AminoSlice sl = amino_slice(x, sub, c);
+      r = __popc(sl.match & low_mask(int(l) + 1 - int(32 * sub))) + sl.count;
+    }
+    r += __shfl_xor_sync(FULL, r, 1);
+    r += __shfl_xor_sync(FULL, r, 2);
+    if (have) {
+      if (!sym_ok) {
+        have = false;
+      } else {
+        row = ix.c_lo[c] + r - 1;
+        p--;
+        if (row_is_sampled(ix, row))
+          have = false;
+        else if (sub == 0)
+          full[row] = p;
+      }
+    }
+  }
+}
+
+cudaError_t build_full_sa(const IndexView& ix, uint32_t* d_full, int sm_count, cudaStream_t s) {
+  const uint64_t n_elems = (uint64_t(ix.bwt_len) + ix.sa_ratio - 1) / ix.sa_ratio;
+  const uint64_t lanes = ix.alphabet == 0 ? 2 : 4;
+  unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (lanes * n_elems + 255) / 256)));
+  if (ix.alphabet == 0)
+    unsample_dna_kernel<<<grid, 256, 0, s>>>(ix, n_elems, d_full);
+  else
+    unsample_amino_kernel<<<grid, 256, 0, s>>>(ix, n_elems, d_full);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+// Locate pass 2 on the unsampled array: hit i of query q is SA[sp + i] -- no walk.  Same work split as
+// expand_rows_kernel: a lane copies the first 8 hits of its query, longer intervals are copied by the
+// whole warp (coalesced 128-B reads of SA, coalesced writes), so skewed hit counts cost bandwidth, not
+// serial steps.
+template <bool MAP>
+__global__ void __launch_bounds__(256)
+    gather_sa_kernel(IndexView ix, const uint2* __restrict__ sp_cnt, const uint64_t* __restrict__ hit_off,
+                     uint64_t nq, uint64_t* __restrict__ out) {
+  constexpr int SLOT = MAP ? 2 : 1;
+  const uint32_t* __restrict__ full = ix.full_sa;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5;
+  const uint64_t nwarps = (gridDim.x * uint64_t(blockDim.x)) >> 5;
+  for (uint64_t base = warp * 32; base < nq; base += nwarps * 32) {
+    uint64_t q = base + lane;
+    uint32_t sp = 0, cnt = 0;
+    uint64_t off = 0;
+    if (q < nq) {
+      uint2 r = sp_cnt[q];
+      sp = r.x;
+      cnt = r.y;
+      off = hit_off[q];
+    }
+    uint32_t small = cnt < 8 ? cnt : 8;
+    for (uint32_t i = 0; i < small; i++) {
+      uint64_t loc = __ldg(full + sp + i);
+      if (MAP)
+        map_location(ix, loc, out + SLOT * (off + i));
+      else
+        out[off + i] = loc;
+    }
+    uint32_t big = __ballot_sync(0xffffffffu, cnt > 8);
+    while (big) {
+      int L = __ffs(big) - 1;
+      big &= big - 1;
+      uint32_t s = __shfl_sync(0xffffffffu, sp, L), c = __shfl_sync(0xffffffffu, cnt, L);
+      uint64_t o = __shfl_sync(0xffffffffu, off, L);
+      for (uint32_t i = 8 + lane; i < c; i += 32) {
+        uint64_t loc = __ldg(full + s + i);
+        if (MAP)
+          map_location(ix, loc, out + SLOT * (o + i));
+        else
+          out[o + i] = loc;
+      }
+    }
+  }
+}
+
 cudaError_t launch_walk(const IndexView& ix, const uint2* d_sp_cnt, const uint64_t* d_hit_off,
                         uint64_t nq, uint64_t n_hits, uint64_t* d_hits_pairs, uint64_t* d_locs,
                         int sm_count, cudaStream_t s) {
   if (n_hits == 0 || nq == 0) return cudaSuccess;
   const bool map = d_hits_pairs != nullptr;
   uint64_t* out = map ? d_hits_pairs : d_locs;
+  if (ix.full_sa != nullptr) {  // unsampled array present: a gather instead of expand + walk
+    unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (nq + 255) / 256)));
+    if (map)
+      gather_sa_kernel<true><<<grid, 256, 0, s>>>(ix, d_sp_cnt, d_hit_off, nq, out);
+    else
+      gather_sa_kernel<false><<<grid, 256, 0, s>>>(ix, d_sp_cnt, d_hit_off, nq, out);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+  }
   {
     unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (nq + 255) / 256)));
     expand_rows_kernel<<<grid, 256, 0, s>>>(d_sp_cnt, d_hit_off, nq, reinterpret_cast<uint32_t*>(out), map ? 4u : 2u);

@@ -46,6 +46,9 @@ cudaError_t launch_ref_table(const IndexView& ix, uint64_t first, uint64_t count
 uint64_t pair_block_count(uint64_t bwt_len);
 cudaError_t build_pair_index(const IndexView& ix, uint4* d_pair_blocks, uint32_t* c2_host /*16*/, cudaStream_t s);
 
+// unsampled suffix array (locate accelerator): SA[row] for every row, 4 B each, from the sampled one
+cudaError_t build_full_sa(const IndexView& ix, uint32_t* d_full, int sm_count, cudaStream_t s);
+
 cudaError_t launch_pack(int alphabet, const uint8_t* d_qbytes, const uint64_t* d_qoff, uint64_t nq,
                         uint64_t* d_qwords, unsigned long long* d_first_bad, cudaStream_t s);
 // d_defer: nq + 1 u32 of scratch (list of queries the cooperative kernel hands to the scalar one)
@@ -56,7 +59,8 @@ cudaError_t launch_search(const IndexView& ix, const uint64_t* d_qwords, const u
 // locate: CSR offsets from pass 1, LF-walk pass 2
 cudaError_t scan_hit_offsets(const uint2* d_sp_cnt, uint64_t nq, uint64_t* d_hit_off, void* d_temp,
                              size_t& temp_bytes, cudaStream_t s);
-// writes either awry_hit {seq_idx, local_pos} (d_hits) or global text positions (d_locs)
+// writes either awry_hit {seq_idx, local_pos} (d_hits) or global text positions (d_locs); when
+// ix.full_sa is set the walk is replaced by a gather from the unsampled array
 cudaError_t launch_walk(const IndexView& ix, const uint2* d_sp_cnt, const uint64_t* d_hit_off,
                         uint64_t nq, uint64_t n_hits, uint64_t* d_hits_pairs, uint64_t* d_locs,
                         int sm_count, cudaStream_t s);

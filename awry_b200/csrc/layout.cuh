@@ -54,6 +54,7 @@ struct IndexView {
   const uint2* __restrict__ table;         // k-mer seeds: (sp, ep), empty = (1,0)
   const uint64_t* __restrict__ seq_starts;
   const uint4* __restrict__ pair_blocks;   // nucleotide two-step accelerator, or nullptr
+  const uint32_t* __restrict__ full_sa;    // unsampled suffix array (locate accelerator), or nullptr
   uint32_t c2[16];                         // C2[4a+b]
   uint32_t c_lo[24];                       // C[c]      by device symbol (search.rs:43-48)
   uint32_t c_hi[24];                       // C[c+1]-1  by device symbol

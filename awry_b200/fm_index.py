@@ -78,7 +78,8 @@ class _Info(C.Structure):
                 ("n_devices", C.c_uint32), ("prefix_sums", C.c_uint64 * 23),
                 ("n_sequences", C.c_uint64), ("device_bytes_blocks", C.c_uint64),
                 ("device_bytes_sa", C.c_uint64), ("device_bytes_table", C.c_uint64),
-                ("device_bytes_pair", C.c_uint64), ("devices", C.c_int32 * 16)]
+                ("device_bytes_pair", C.c_uint64), ("device_bytes_full_sa", C.c_uint64),
+                ("devices", C.c_int32 * 16)]
 
 
 class _Parts(C.Structure):
@@ -120,7 +121,7 @@ EXPORTS = ["awry_index_build", "awry_build_index_file", "awry_build_parts", "awr
            "awry_locate_batch", "awry_locate_batch_into", "awry_hits_free", "awry_initial_range", "awry_update_range",
            "awry_backstep", "awry_count_device", "awry_locate_device", "awry_device_free",
            "awry_device_check", "awry_profile_enable", "awry_profile_reset", "awry_profile_get",
-           "awry_bench_random_gather", "awry_set_search_variant", "awry_last_error", "awry_version"]
+           "awry_bench_random_gather", "awry_set_search_variant", "awry_set_locate_variant", "awry_last_error", "awry_version"]
 
 
 def native():
@@ -171,6 +172,7 @@ def native():
     L.awry_bench_random_gather.argtypes = [i32, u64, C.c_uint32, C.c_uint32, u64, i32,
                                            C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.awry_set_search_variant.argtypes = [i32, i32, i32]
+    L.awry_set_locate_variant.argtypes = [i32]
     _LIB = L
     return L
 
@@ -293,7 +295,8 @@ class FmIndex:
 
     def device_bytes(self) -> dict:
         return {"blocks": int(self._info.device_bytes_blocks), "sa": int(self._info.device_bytes_sa),
-                "table": int(self._info.device_bytes_table), "pair": int(self._info.device_bytes_pair)}
+                "table": int(self._info.device_bytes_table), "pair": int(self._info.device_bytes_pair),
+                "full_sa": int(self._info.device_bytes_full_sa)}
 
     def sequence_header(self, seq_idx: int) -> str:
         p, n = C.c_char_p(), C.c_uint64()
@@ -483,3 +486,8 @@ def bench_random_gather(device: int, footprint_bytes: int, granule: int, lanes: 
 
 def set_search_variant(lanes: int = 0, tpb: int = 0, blocks_per_sm: int = 0):
     _check(native().awry_set_search_variant(lanes, tpb, blocks_per_sm))
+
+
+def set_locate_variant(variant: int = 0):
+    """0 = gather from the unsampled suffix array when the index holds one (default); 1 = always LF-walk."""
+    _check(native().awry_set_locate_variant(variant))

@@ -301,26 +301,37 @@ def main():
         fxg.gen_queries_device(0, a.text_len, TEXT_SEED, nl, ll, QUERY_SEED + 1 + 1000 * rank, d_lq.data_ptr())
         d_loff = torch.arange(0, nl + 1, dtype=torch.int64, device="cuda") * ll
         d_hoff = torch.zeros(nl + 1, dtype=torch.int64, device="cuda")
-        n_hits = 0
-        for _ in range(2):
-            ptr, n_hits = ix.locate_device(d_lq.data_ptr(), d_loff.data_ptr(), nl, d_hoff.data_ptr(), stream=stream)
-            ix.device_free(ptr)
-        f.profile_enable(True)
-        f.profile_reset()
-        barrier()
-        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0.record()
-        for _ in range(a.steps):
-            ptr, n_hits = ix.locate_device(d_lq.data_ptr(), d_loff.data_ptr(), nl, d_hoff.data_ptr(), stream=stream)
-            ix.device_free(ptr)
-        l1.record()
-        barrier()
-        lp = f.profile_get()
-        f.profile_enable(False)
-        t_l = torch.tensor([l0.elapsed_time(l1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t_l, op=dist.ReduceOp.MAX)
-        lms = float(t_l.item()) / a.steps
+        def locate_leg(variant):
+            """device-resident two-pass locate, CUDA events; variant 0 = default pass 2, 1 = LF-walk"""
+            f.set_locate_variant(variant)
+            try:
+                nh = 0
+                for _ in range(2):
+                    ptr, nh = ix.locate_device(d_lq.data_ptr(), d_loff.data_ptr(), nl, d_hoff.data_ptr(), stream=stream)
+                    ix.device_free(ptr)
+                f.profile_enable(True)
+                f.profile_reset()
+                barrier()
+                l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                l0.record()
+                for _ in range(a.steps):
+                    ptr, nh = ix.locate_device(d_lq.data_ptr(), d_loff.data_ptr(), nl, d_hoff.data_ptr(), stream=stream)
+                    ix.device_free(ptr)
+                l1.record()
+                barrier()
+                prof_l = f.profile_get()
+                f.profile_enable(False)
+            finally:
+                f.set_locate_variant(0)
+            t = torch.tensor([l0.elapsed_time(l1)], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()) / a.steps, prof_l, nh
+
+        walk_lms, walk_lp, n_hits = locate_leg(1)
+        lms, lp, n_hits2 = locate_leg(0)
+        assert n_hits == n_hits2
+        unsampled = ix.device_bytes()["full_sa"] > 0
         # end to end through the C ABI: pinned host queries in, CSR offsets + hits out to the host
         hl_q = torch.empty(nl * ll, dtype=torch.uint8, pin_memory=True)
         hl_q.copy_(d_lq)
@@ -339,13 +350,17 @@ def main():
         t_le = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t_le, op=dist.ReduceOp.MAX)
-        walk_ms = lp["walk_ms"] / max(1, lp["walk_launches"])
         locate = {"workload": f"parallel_locate {nl} x {ll}-bp queries, SA ratio {a.sa_ratio} (cfg3)",
+                  "pass2": "gather from the unsampled suffix array (rebuilt on the device at load time)" if unsampled
+                           else "LF-walk to the sampled rows",
                   "hits_per_query": n_hits / nl, "hits_per_s": world * n_hits / (lms * 1e-3),
-                  "queries_per_s": world * nl / (lms * 1e-3), "ms_per_step": lms, "walk_kernel_ms": walk_ms,
+                  "queries_per_s": world * nl / (lms * 1e-3), "ms_per_step": lms,
+                  "pass2_kernel_ms": lp["walk_ms"] / max(1, lp["walk_launches"]),
                   "search_kernel_ms": lp["search_ms"] / max(1, lp["search_launches"]),
                   "e2e_hits_per_s": world * n_e2e / float(t_le.item()),
-                  "e2e_ms_per_step": float(t_le.item()) * 1e3}
+                  "e2e_ms_per_step": float(t_le.item()) * 1e3,
+                  "lf_walk_variant": {"hits_per_s": world * n_hits / (walk_lms * 1e-3), "ms_per_step": walk_lms,
+                                      "walk_kernel_ms": walk_lp["walk_ms"] / max(1, walk_lp["walk_launches"])}}
         del d_lq, d_loff, d_hoff
 
     # ---- CPU baseline + parity + exact algorithmic work (rank 0, N = 1 only)

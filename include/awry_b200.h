@@ -70,6 +70,7 @@ typedef struct awry_info {
   uint64_t device_bytes_sa;
   uint64_t device_bytes_table;
   uint64_t device_bytes_pair;   /* nucleotide two-symbol accelerator blocks */
+  uint64_t device_bytes_full_sa; /* unsampled suffix array (locate accelerator), 0 if not built */
   int32_t devices[16];
 } awry_info;
 
@@ -244,6 +245,13 @@ int awry_bench_random_gather(int device, uint64_t footprint_bytes, uint32_t gran
  * that many lanes on the one-symbol blocks, 8 = the two-symbol (pair index) kernel, -1 = scalar
  * kernel, 0 = default (pair kernel when the pair index exists).  blocks_per_sm caps residency. */
 int awry_set_search_variant(int lanes_per_query, int threads_per_block, int blocks_per_sm);
+
+/* Locate pass 2.  When memory allows (AWRY_B200_FULL_SA=0 disables, =1 forces) the index keeps the
+ * UNSAMPLED suffix array, rebuilt on the device at load time from the sampled one
+ * (compressed_suffix_array.rs:109-111) with one LF step per BWT row, and a hit is one read of SA[row]
+ * instead of the LF-walk of fm_index.rs:521-537; results are identical.  variant 0 = use it when
+ * present (default), 1 = always LF-walk to the sampled rows (the memory-lean path). */
+int awry_set_locate_variant(int variant);
 
 const char *awry_last_error(void);
 const char *awry_version(void);

@@ -37,6 +37,7 @@ pub struct awry_info {
     pub device_bytes_sa: u64,
     pub device_bytes_table: u64,
     pub device_bytes_pair: u64,
+    pub device_bytes_full_sa: u64,
     pub devices: [i32; 16],
 }
 
@@ -55,6 +56,17 @@ pub struct awry_parts {
     pub n_sequences: u64,
 }
 
+/// FmBuildArgs (fm_index.rs:78-96), the fields that mean something without libsufr
+#[repr(C)]
+pub struct awry_build_args {
+    pub input_file_src: *const c_char,
+    pub output_file_src: *const c_char,
+    pub alphabet: u32,
+    pub lookup_table_kmer_len: u32,
+    pub suffix_array_compression_ratio: u64,
+    pub device: i32,
+}
+
 pub const AWRY_OK: c_int = 0;
 pub const AWRY_ERR_IO: c_int = -2;
 pub const AWRY_ERR_INVALID_QUERY: c_int = -5;
@@ -64,6 +76,13 @@ pub const AWRY_LOCATE_SORTED: u32 = 1;
 extern "C" {
     pub fn awry_index_load(path: *const c_char, devices: *const c_int, n_dev: c_int, out: *mut *mut awry_index) -> c_int;
     pub fn awry_index_from_parts(parts: *const awry_parts, devices: *const c_int, n_dev: c_int, out: *mut *mut awry_index) -> c_int;
+    pub fn awry_index_build(args: *const awry_build_args, devices: *const c_int, n_dev: c_int, out: *mut *mut awry_index) -> c_int;
+    pub fn awry_build_index_file(args: *const awry_build_args) -> c_int;
+    pub fn awry_build_parts(alphabet: u32, text: *const u8, n: u64, sa_ratio: u64, device: c_int, blocks: *mut u64,
+                            prefix_sums: *mut u64, sa_words: *mut u64, phase_seconds: *mut f64) -> c_int;
+    pub fn awry_parts_num_blocks(bwt_len: u64) -> u64;
+    pub fn awry_parts_block_words(alphabet: u32) -> u64;
+    pub fn awry_parts_sa_words(bwt_len: u64, sa_ratio: u64) -> u64;
     pub fn awry_index_free(index: *mut awry_index);
     pub fn awry_index_info(index: *const awry_index, info: *mut awry_info) -> c_int;
     pub fn awry_index_sequence_header(index: *const awry_index, seq_idx: u64, header: *mut *const c_char, header_len: *mut u64) -> c_int;
@@ -84,6 +103,7 @@ extern "C" {
                               cuda_stream: *mut c_void) -> c_int;
     pub fn awry_device_free(index: *const awry_index, replica: c_int, d_ptr: *mut c_void) -> c_int;
     pub fn awry_device_check(index: *const awry_index, replica: c_int, cuda_stream: *mut c_void) -> c_int;
+    pub fn awry_set_locate_variant(variant: c_int) -> c_int;
     pub fn awry_last_error() -> *const c_char;
     pub fn awry_version() -> *const c_char;
 }

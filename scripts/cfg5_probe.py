@@ -51,19 +51,23 @@ def main():
     cnt = d_cnt.cpu().numpy()
     print(f"count: search {pc['search_ms']:.2f} ms; hits/query min {cnt.min()} median {int(np.median(cnt))} "
           f"mean {cnt.mean():.1f} max {cnt.max()} total {cnt.sum()}", flush=True)
-    for it in range(3):
-        f.profile_reset()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ptr, nh = ix.locate_device(d_q.data_ptr(), d_off.data_ptr(), a.nq, d_hoff.data_ptr(), stream=st)
-        e1.record()
-        torch.cuda.synchronize()
-        pl = f.profile_get()
-        ms = e0.elapsed_time(e1)
-        if it < 2:
-            ix.device_free(ptr)
-    print(f"locate: {nh} hits in {ms:.2f} ms ({nh/ms/1e3:.1f} M hits/s); search {pl['search_ms']:.2f} ms, "
-          f"walk {pl['walk_ms']:.2f} ms ({nh/pl['walk_ms']/1e3:.1f} M hits/s in the walk kernel)", flush=True)
+    print(f"device bytes {ix.device_bytes()}", flush=True)
+    for variant in (1, 0):          # LF-walk, then the unsampled-SA gather (kept for the parity check)
+        f.set_locate_variant(variant)
+        for it in range(3):
+            f.profile_reset()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ptr, nh = ix.locate_device(d_q.data_ptr(), d_off.data_ptr(), a.nq, d_hoff.data_ptr(), stream=st)
+            e1.record()
+            torch.cuda.synchronize()
+            pl = f.profile_get()
+            ms = e0.elapsed_time(e1)
+            if it < 2 or variant == 1:
+                ix.device_free(ptr)
+        print(f"locate variant {variant} ({'LF-walk' if variant else 'unsampled-SA gather'}): {nh} hits in {ms:.2f} ms "
+              f"({nh/ms/1e3:.1f} M hits/s); search {pl['search_ms']:.2f} ms, pass 2 {pl['walk_ms']:.2f} ms "
+              f"({nh/pl['walk_ms']/1e3:.1f} M hits/s in the pass-2 kernel)", flush=True)
     orc = po.OracleIndex.from_parts(parts.alphabet, parts.ratio, parts.bwt_len, parts.kmer_len, parts.blocks,
                                     parts.prefix_sums, parts.sa_words)
     ns = a.check

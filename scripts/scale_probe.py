@@ -33,10 +33,17 @@ def main():
     t0 = time.time()
     parts, phases = fxg.build_parts(a.alphabet, a.n, 3, ratio=a.ratio, kmer_len=a.k)
     print("fixture build phases (s):", json.dumps({k: round(v, 2) for k, v in phases.items()}), flush=True)
-    t1 = time.time()
-    ix = FmIndex.from_parts(parts.alphabet, parts.ratio, parts.bwt_len, parts.kmer_len, parts.blocks,
-                            parts.prefix_sums, parts.sa_words)
-    print(f"from_parts {time.time()-t1:.2f}s device bytes {ix.device_bytes()}", flush=True)
+    for full_sa in ("0", None):     # cost of rebuilding the unsampled suffix array at load time
+        if full_sa is None:
+            os.environ.pop("AWRY_B200_FULL_SA", None)
+        else:
+            os.environ["AWRY_B200_FULL_SA"] = full_sa
+        t1 = time.time()
+        ix = FmIndex.from_parts(parts.alphabet, parts.ratio, parts.bwt_len, parts.kmer_len, parts.blocks,
+                                parts.prefix_sums, parts.sa_words)
+        print(f"from_parts (AWRY_B200_FULL_SA={full_sa}) {time.time()-t1:.2f}s device bytes {ix.device_bytes()}", flush=True)
+        if full_sa is not None:
+            ix.close()
     if a.via_file:
         t2 = time.time()
         parts.write(a.via_file, reference_table=False)
@@ -91,14 +98,21 @@ def main():
         fxg.gen_queries_device(a.alphabet, a.n, 3, nq2, ql2, 5, d_q2.data_ptr())
         d_off2 = torch.arange(0, nq2 + 1, dtype=torch.int64, device="cuda") * ql2
         d_hoff = torch.zeros(nq2 + 1, dtype=torch.int64, device="cuda")
-        for it in range(3):
-            f.profile_reset()
-            ptr, nh = ix.locate_device(d_q2.data_ptr(), d_off2.data_ptr(), nq2, d_hoff.data_ptr(), stream=st)
-            p = f.profile_get()
-            if it < 2:
-                ix.device_free(ptr)
-        print(f"locate: {nh} hits; search {p['search_ms']:.2f} ms walk {p['walk_ms']:.2f} ms "
-              f"{nh/p['walk_ms']/1e3:.1f} M hits/s", flush=True)
+        for variant in (1, 0):      # LF-walk, then the unsampled-SA gather (left selected for the parity check)
+            f.set_locate_variant(variant)
+            for it in range(3):
+                f.profile_reset()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ptr, nh = ix.locate_device(d_q2.data_ptr(), d_off2.data_ptr(), nq2, d_hoff.data_ptr(), stream=st)
+                e1.record()
+                torch.cuda.synchronize()
+                p = f.profile_get()
+                if it < 2 or variant == 1:
+                    ix.device_free(ptr)
+            print(f"locate variant {variant} ({'LF-walk' if variant else 'unsampled-SA gather'}): {nh} hits; total "
+                  f"{e0.elapsed_time(e1):.2f} ms; search {p['search_ms']:.2f} ms pass2 {p['walk_ms']:.3f} ms "
+                  f"{nh/p['walk_ms']/1e3:.1f} M hits/s in pass 2", flush=True)
         ncheck = min(a.check, nq2)
         qb2 = d_q2[: ncheck * ql2].cpu().numpy()
         qo2 = np.arange(ncheck + 1, dtype=np.uint64) * np.uint64(ql2)

@@ -21,7 +21,7 @@ def _device_queries(fxg, alphabet, n, text_seed, nq, qlen, qseed):
 def _run_config(fx, po, alphabet, n, k, ratio, count_nq, count_len, loc_nq, loc_len, text_seed, sample=50_000):
     import ctypes as C
     import torch
-    from awry_b200 import FmIndex
+    from awry_b200 import FmIndex, fm_index as f
     from fixtures import pyfixture_gpu as fxg
     free, _ = torch.cuda.mem_get_info()
     if free < 100e9:
@@ -50,15 +50,24 @@ def _run_config(fx, po, alphabet, n, k, ratio, count_nq, count_len, loc_nq, loc_
         d_hoff = torch.zeros(loc_nq + 1, dtype=torch.int64, device="cuda")
         d_cnt = torch.zeros(loc_nq, dtype=torch.int64, device="cuda")
         ix.count_device(d_q.data_ptr(), d_off.data_ptr(), loc_nq, d_cnt.data_ptr(), st)
-        ptr, n_hits = ix.locate_device(d_q.data_ptr(), d_off.data_ptr(), loc_nq, d_hoff.data_ptr(), stream=st)
-        assert n_hits == int(d_cnt.sum()) >= loc_nq         # locate total == count total
-        hoff = d_hoff.cpu().numpy().view(np.uint64)
-        assert np.array_equal(np.diff(hoff), d_cnt.cpu().numpy().view(np.uint64))
-        buf = torch.empty(n_hits * 2, dtype=torch.int64, device="cuda")
-        rc = C.CDLL("libcudart.so").cudaMemcpy(C.c_void_p(buf.data_ptr()), C.c_void_p(ptr), C.c_size_t(n_hits * 16), 3)
-        assert rc == 0
-        ix.device_free(ptr)
-        hits = buf.cpu().numpy().view(np.uint64).reshape(-1, 2)
+        assert ix.device_bytes()["full_sa"] == 4 * parts.bwt_len
+        all_hits = []
+        for variant in (1, 0):      # LF-walk to the sampled rows, then the unsampled-SA gather
+            f.set_locate_variant(variant)
+            try:
+                ptr, n_hits = ix.locate_device(d_q.data_ptr(), d_off.data_ptr(), loc_nq, d_hoff.data_ptr(), stream=st)
+            finally:
+                f.set_locate_variant(0)
+            assert n_hits == int(d_cnt.sum()) >= loc_nq         # locate total == count total
+            hoff = d_hoff.cpu().numpy().view(np.uint64)
+            assert np.array_equal(np.diff(hoff), d_cnt.cpu().numpy().view(np.uint64))
+            buf = torch.empty(n_hits * 2, dtype=torch.int64, device="cuda")
+            rc = C.CDLL("libcudart.so").cudaMemcpy(C.c_void_p(buf.data_ptr()), C.c_void_p(ptr), C.c_size_t(n_hits * 16), 3)
+            assert rc == 0
+            ix.device_free(ptr)
+            all_hits.append(buf.cpu().numpy().view(np.uint64).reshape(-1, 2))
+        hits = all_hits[1]
+        assert np.array_equal(all_hits[0], hits)            # both pass-2 variants agree on every hit
         assert int(hits[:, 0].max()) == 0 and int(hits[:, 1].max()) <= n - loc_len
         # round trip on a strided sample of hits: text at the hit == the query that produced it
         step = max(1, n_hits // 200_000)

@@ -41,6 +41,16 @@ def dna_or(po, dna):
     return oracle_from_parts(po, dna)
 
 
+@pytest.fixture(params=[0, 1], ids=["unsampled_sa", "lf_walk"])
+def locate_variant(request):
+    """locate pass 2 both ways: gather from the unsampled suffix array (default when it fits) and the
+    LF-walk to the sampled rows (fm_index.rs:521-537)"""
+    from awry_b200 import fm_index as f
+    f.set_locate_variant(request.param)
+    yield request.param
+    f.set_locate_variant(0)
+
+
 def edge_queries(text):
     t = bytes(text[:400])
     qs = [t[5:5 + n] for n in range(1, 14)]                 # shorter than / equal to / just above k
@@ -50,7 +60,7 @@ def edge_queries(text):
     return qs
 
 
-def test_golden_file_appendix_a():
+def test_golden_file_appendix_a(locate_variant):
     from awry_b200 import FmIndex, SearchRange
     with FmIndex.load(GOLDEN) as ix:
         assert ix.bwt_len() == 20 and ix.suffix_array_compression_ratio() == 4
@@ -97,7 +107,7 @@ def test_counts_match_brute_force(fx, dna, dna_dev):
 
 
 @pytest.mark.parametrize("ratio", [1, 4, 5, 8, 32])
-def test_locate_parity(fx, po, ratio):
+def test_locate_parity(fx, po, ratio, locate_variant):
     text = fx.gen_text(0, 60_000, 11 + ratio)
     parts = fx.build_parts(text, 0, ratio=ratio, kmer_len=6)
     orc = oracle_from_parts(po, parts)
@@ -108,6 +118,7 @@ def test_locate_parity(fx, po, ratio):
     qs += [b"A", b"ACGTTTTTTTTGGGGGGGGGGGGGCCCCCCCCCCC", bytes(text[:50]), bytes(text[-30:])]
     qb, qo = f.pack_queries(qs)
     with device_from_parts(parts) as ix:
+        assert ix.device_bytes()["full_sa"] == (4 * parts.bwt_len if ratio > 1 else 0)
         off, hits = ix.locate_packed(qb, qo)
         woff, whits, _ = orc.locate_batch(qb, qo)
         assert np.array_equal(off, woff)
@@ -122,7 +133,7 @@ def test_locate_parity(fx, po, ratio):
         assert sorted(int(x) for x in whits[lo:hi, 1]) == brute_positions(t, qs[i])
 
 
-def test_amino_count_and_locate(fx, po):
+def test_amino_count_and_locate(fx, po, locate_variant):
     text = fx.gen_text(1, 50_000, 6)
     parts = fx.build_parts(text, 1, ratio=8, kmer_len=3)
     orc = oracle_from_parts(po, parts)
@@ -152,7 +163,7 @@ def test_amino_count_and_locate(fx, po):
         assert int(want[i]) == len(brute_positions(t, qs[i]))
 
 
-def test_multi_record_and_n_text(fx, po):
+def test_multi_record_and_n_text(fx, po, locate_variant):
     """multi-record input: delimiters are literal N symbols (fm_index.rs:148-153); locate maps
     to (record, offset) with the intended semantics (reference recursion: SURVEY Q4)."""
     recs = [bytes(fx.gen_text(0, n, 20 + i)) for i, n in enumerate([700, 33, 1, 1500, 256, 90])]
@@ -301,7 +312,7 @@ def test_multi_replica_in_one_process(fx, dna, dna_or):
         assert np.array_equal(ix.count_packed(*few), dna_or.count_batch(*few)[0])
 
 
-def test_cfg5_repeat_rich_locate_under_skew(fx, po):
+def test_cfg5_repeat_rich_locate_under_skew(fx, po, locate_variant):
     """BASELINE cfg 5 (scaled to what the CPU fixture builder sorts in seconds): repeat-rich DNA,
     SA ratio 32, hit counts from 1 to thousands per query -- exercises the warp-cooperative CSR
     expansion and the lane-refilling walk under load imbalance."""
@@ -330,7 +341,7 @@ def test_cfg5_repeat_rich_locate_under_skew(fx, po):
     assert all(t[int(p):int(p) + 50] == q for p in whits[lo:hi, 1])
 
 
-def test_locate_into_caller_buffers(fx, dna, dna_dev, dna_or):
+def test_locate_into_caller_buffers(fx, dna, dna_dev, dna_or, locate_variant):
     import torch
     from awry_b200 import AwryError
     qb, qo = mixed_queries(fx, dna.text, 5000, 14, seed=41)
