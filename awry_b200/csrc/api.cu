@@ -18,11 +18,16 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <condition_variable>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <vector>
 
 #include "../../include/awry_b200.h"
 #include "build.hpp"
 #include "kernels.hpp"
+#include "reads.hpp"
 
 using namespace awry;
 
@@ -295,6 +300,36 @@ struct Source {
   void read(void* dst, size_t n, const char* what) {
     if (n == 0) return;
     if (f) {
+      if (n >= (32u << 20)) {
+        // large sections (blocks, SA words): positional reads from several threads -- one thread
+        // copying out of the page cache tops out at a few GB/s, far below the PCIe rate behind it
+        off_t pos = ftello(f);
+        int fd = fileno(f);
+        unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+        size_t per = ((n + nt - 1) / nt + 4095) & ~size_t(4095);
+        std::vector<std::thread> th;
+        std::vector<int> ok(nt, 1);
+        for (unsigned t = 0; t < nt; t++) {
+          size_t lo = std::min(n, size_t(t) * per), hi = std::min(n, lo + per);
+          if (lo >= hi) break;
+          th.emplace_back([=, &ok] {
+            size_t done = lo;
+            while (done < hi) {
+              ssize_t r = pread(fd, static_cast<char*>(dst) + done, hi - done, pos + off_t(done));
+              if (r <= 0) {
+                ok[t] = 0;
+                return;
+              }
+              done += size_t(r);
+            }
+          });
+        }
+        for (auto& t : th) t.join();
+        for (unsigned t = 0; t < nt; t++)
+          if (!ok[t]) fail(AWRY_ERR_IO, "unexpected end of file while reading %s", what);
+        if (fseeko(f, pos + off_t(n), SEEK_SET) != 0) fail(AWRY_ERR_IO, "seek failed while reading %s", what);
+        return;
+      }
       if (fread(dst, 1, n, f) != n) fail(AWRY_ERR_IO, "unexpected end of file while reading %s", what);
       return;
     }
@@ -931,6 +966,319 @@ void locate_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
   r.release(ws);
 }
 
+// ------------------------------------------------------------------ streaming reads-file front-end
+// FASTQ / FASTA file of queries -> parallel_count / parallel_locate without a host-side parser:
+// a reader thread preads the file into a ring of pinned buffers, the raw bytes are uploaded and
+// parsed on the device (reads.cu), and the parsed (query bytes, CSR offsets) feed the same pack /
+// search / locate kernels as the *_device entry points.  A record cut by a chunk boundary is carried
+// into the next chunk by the host.
+
+struct ReadsOut {
+  std::vector<uint64_t> counts;
+  std::vector<uint64_t> hit_off;  // locate: CSR, n_reads + 1
+  awry_hit* hits = nullptr;       // locate: malloc'd
+  uint64_t n_hits = 0, hits_cap = 0;
+  uint64_t n_reads = 0, n_bases = 0, file_bytes = 0;
+};
+
+void parallel_pread(int fd, void* dst, size_t n, off_t pos, const char* what) {
+  unsigned nt = n >= (32u << 20) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+  size_t per = ((n + nt - 1) / nt + 4095) & ~size_t(4095);
+  std::vector<int> ok(nt, 1);
+  auto work = [&](unsigned t) {
+    size_t lo = std::min(n, size_t(t) * per), hi = std::min(n, lo + per);
+    while (lo < hi) {
+      ssize_t r = pread(fd, static_cast<char*>(dst) + lo, hi - lo, pos + off_t(lo));
+      if (r <= 0) {
+        ok[t] = 0;
+        return;
+      }
+      lo += size_t(r);
+    }
+  };
+  if (nt == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t);
+    for (auto& t : th) t.join();
+  }
+  for (unsigned t = 0; t < nt; t++)
+    if (!ok[t]) fail(AWRY_ERR_IO, "read error in %s", what);
+}
+
+void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_t flags, ReadsOut& out) {
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) fail(AWRY_ERR_IO, "cannot open %s: %s", path, strerror(errno));
+  struct FdCloser {
+    int fd;
+    ~FdCloser() { close(fd); }
+  } fdc{fd};
+  struct stat sb;
+  if (fstat(fd, &sb) != 0) fail(AWRY_ERR_IO, "cannot stat %s", path);
+  const uint64_t fsize = uint64_t(sb.st_size);
+  out.file_bytes = fsize;
+  // format: first non-blank byte
+  int fastq = -1;
+  uint64_t data_start = 0;
+  {
+    unsigned char head[4096];
+    ssize_t got = pread(fd, head, sizeof head, 0);
+    if (got >= 2 && head[0] == 0x1f && head[1] == 0x8b)
+      fail(AWRY_ERR_UNSUPPORTED, "%s is gzip-compressed; decompress it first", path);
+    for (ssize_t i = 0; i < got; i++) {
+      unsigned char c = head[i];
+      if (c == '\n' || c == '\r' || c == ' ' || c == '\t') continue;
+      fastq = c == '@' ? 1 : c == '>' ? 0 : -1;
+      data_start = uint64_t(i);
+      break;
+    }
+    if (fastq < 0) {
+      if (got <= 0 || data_start == 0) {
+        bool blank = true;
+        for (ssize_t i = 0; i < got; i++) blank &= (head[i] == '\n' || head[i] == '\r' || head[i] == ' ' || head[i] == '\t');
+        if (blank && fsize <= uint64_t(std::max<ssize_t>(got, 0))) {  // empty file: zero reads
+          if (locate) out.hit_off.assign(1, 0);
+          return;
+        }
+      }
+      fail(AWRY_ERR_FORMAT, "%s is neither FASTQ ('@') nor FASTA ('>')", path);
+    }
+  }
+  uint64_t CHUNK = 64ull << 20;
+  if (const char* e = getenv("AWRY_B200_READS_CHUNK")) CHUNK = std::max<uint64_t>(64, strtoull(e, nullptr, 10));
+  CHUNK = std::min<uint64_t>(CHUNK, 512ull << 20);
+  const uint64_t CARRY = CHUNK;  // the largest record that can straddle a chunk boundary
+  constexpr int NBUF = 3;
+
+  Replica& r = *ix->reps[0];
+  DeviceGuard dg(r.device);
+  Workspace* ws = r.acquire();
+  cudaStream_t st = ws->st;
+  uint8_t* h_buf[NBUF] = {nullptr, nullptr, nullptr};
+  uint8_t *d_raw = nullptr, *d_qbytes = nullptr;
+  uint32_t *d_nl = nullptr, *d_small = nullptr, *d_seq_len = nullptr, *d_is_hdr = nullptr, *d_hdr_rank = nullptr;
+  uint64_t *d_seq_off = nullptr, *d_qoff = nullptr;
+  size_t cap_lines = 0, cap_qoff = 0;
+  void* d_temp = nullptr;
+  ReadsPlan* h_plan = nullptr;
+
+  // reader thread state
+  std::mutex mu;
+  std::condition_variable cv;
+  struct Slot {
+    bool filled = false;
+    uint64_t n = 0;
+    bool eof = false;
+  } slots[NBUF];
+  bool stop = false;
+  std::string reader_err;
+  std::thread reader;
+
+  auto cleanup = [&] {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      stop = true;
+    }
+    cv.notify_all();
+    if (reader.joinable()) reader.join();
+    cudaStreamSynchronize(st);
+    for (auto& b : h_buf) cudaFreeHost(b);
+    cudaFree(d_raw);
+    cudaFree(d_qbytes);
+    cudaFree(d_nl);
+    cudaFree(d_small);
+    cudaFree(d_seq_len);
+    cudaFree(d_is_hdr);
+    cudaFree(d_hdr_rank);
+    cudaFree(d_seq_off);
+    cudaFree(d_qoff);
+    cudaFree(d_temp);
+    cudaFreeHost(h_plan);
+    r.release(ws);
+  };
+  try {
+    for (auto& b : h_buf) CU(cudaHostAlloc(reinterpret_cast<void**>(&b), CARRY + CHUNK + 64, cudaHostAllocDefault));
+    const uint32_t max_bytes = uint32_t(CARRY + CHUNK + 1);
+    CU(cudaMalloc(reinterpret_cast<void**>(&d_raw), max_bytes + 64));
+    CU(cudaMalloc(reinterpret_cast<void**>(&d_qbytes), max_bytes + 64));
+    CU(cudaMalloc(reinterpret_cast<void**>(&d_nl), size_t(max_bytes) * 4 + 64));
+    CU(cudaMalloc(reinterpret_cast<void**>(&d_small), 64));
+    const size_t temp_bytes = reads_temp_bytes(max_bytes);
+    CU(cudaMalloc(&d_temp, temp_bytes));
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&h_plan), sizeof(ReadsPlan) + 64, cudaHostAllocDefault));
+    uint32_t* h_n_lines = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(h_plan) + sizeof(ReadsPlan));
+
+    reader = std::thread([&] {
+      uint64_t pos = data_start;
+      for (int c = 0;; c++) {
+        Slot& s = slots[c % NBUF];
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return stop || !s.filled; });
+          if (stop) return;
+        }
+        uint64_t n = std::min<uint64_t>(CHUNK, fsize - pos);
+        try {
+          if (n) parallel_pread(fd, h_buf[c % NBUF] + CARRY, size_t(n), off_t(pos), path);
+        } catch (const ApiError& e) {
+          std::lock_guard<std::mutex> lk(mu);
+          reader_err = e.what();
+          s.filled = true;
+          s.n = 0;
+          s.eof = true;
+          cv.notify_all();
+          return;
+        }
+        pos += n;
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          s.n = n;
+          s.eof = pos >= fsize;
+          s.filled = true;
+        }
+        cv.notify_all();
+        if (pos >= fsize) return;
+      }
+    });
+
+    if (locate) out.hit_off.assign(1, 0);
+    const int sh = packed_unit_shift(ix->alphabet);
+    uint64_t tail_len = 0;
+    const uint8_t* tail_src = nullptr;
+    int prev_slot = -1;
+    for (int c = 0;; c++) {
+      const int si = c % NBUF;
+      Slot& s = slots[si];
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return s.filled; });
+      }
+      if (!reader_err.empty()) fail(AWRY_ERR_IO, "%s", reader_err.c_str());
+      uint8_t* base = h_buf[si] + CARRY - tail_len;
+      if (tail_len) memcpy(base, tail_src, tail_len);
+      if (prev_slot >= 0) {  // the previous buffer is free once its tail has moved
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          slots[prev_slot].filled = false;
+        }
+        cv.notify_all();
+      }
+      uint64_t n = tail_len + s.n;
+      const bool eof = s.eof;
+      if (eof && n && base[n - 1] != '\n') base[n++] = '\n';
+      if (n == 0) break;
+      CU(cudaMemcpyAsync(d_raw, base, n, cudaMemcpyHostToDevice, st));
+      g_prof.h2d += n;
+      CU(reads_find_lines(d_raw, uint32_t(n), d_nl, d_small, d_temp, temp_bytes, st));
+      CU(cudaMemcpyAsync(h_n_lines, d_small, 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      const uint32_t n_lines = *h_n_lines;
+      if (size_t(n_lines) + 2 > cap_lines) {
+        cudaFree(d_seq_len);
+        cudaFree(d_is_hdr);
+        cudaFree(d_hdr_rank);
+        cudaFree(d_seq_off);
+        d_seq_len = d_is_hdr = d_hdr_rank = nullptr;
+        d_seq_off = nullptr;
+        cap_lines = size_t(n_lines) + size_t(n_lines) / 4 + 1024;
+        CU(cudaMalloc(reinterpret_cast<void**>(&d_seq_len), cap_lines * 4));
+        CU(cudaMalloc(reinterpret_cast<void**>(&d_is_hdr), cap_lines * 4));
+        CU(cudaMalloc(reinterpret_cast<void**>(&d_hdr_rank), cap_lines * 4));
+        CU(cudaMalloc(reinterpret_cast<void**>(&d_seq_off), cap_lines * 8));
+      }
+      if (size_t(n_lines) + 2 > cap_qoff) {
+        cudaFree(d_qoff);
+        d_qoff = nullptr;
+        cap_qoff = size_t(n_lines) + size_t(n_lines) / 4 + 1024;
+        CU(cudaMalloc(reinterpret_cast<void**>(&d_qoff), cap_qoff * 8));
+      }
+      ReadsPlan* d_plan = reinterpret_cast<ReadsPlan*>(d_small + 4);
+      CU(reads_parse_lines(d_raw, uint32_t(n), d_nl, d_small, n_lines, fastq, eof ? 1 : 0, d_seq_len, d_is_hdr, d_seq_off,
+                           d_hdr_rank, d_plan, d_qbytes, d_qoff, d_temp, temp_bytes, st));
+      CU(cudaMemcpyAsync(h_plan, d_plan, sizeof(ReadsPlan), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      const ReadsPlan plan = *h_plan;
+      const uint64_t nq = plan.n_records;
+      if (nq) {
+        Workspace::grow_dev(ws->d_qwords, ws->d_qwords_cap, size_t(packed_words(ix->alphabet, nq, plan.seq_bytes)));
+        Workspace::grow_dev(ws->d_out, ws->d_out_cap, size_t(nq) * 8);
+        Workspace::grow_dev(ws->d_defer, ws->d_defer_cap, size_t(nq) + 1);
+        CU(cudaMemsetAsync(ws->d_flag, 0xff, 8, st));
+        {
+          ProfScope p(2, r.device, st);
+          CU(launch_pack(ix->alphabet, d_qbytes, d_qoff, nq, ws->d_qwords, ws->d_flag, st));
+        }
+        {
+          ProfScope p(0, r.device, st);
+          CU(launch_search(r.view, ws->d_qwords, d_qoff, nq, locate ? OUT_SP_CNT_U32 : OUT_COUNT_U64, ws->d_out, ws->d_defer,
+                           g_variant, r.sm_count, st));
+        }
+        CU(cudaMemcpyAsync(ws->h_flag, ws->d_flag, 8, cudaMemcpyDeviceToHost, st));
+        if (!locate) {
+          out.counts.resize(out.n_reads + nq);
+          CU(cudaMemcpyAsync(out.counts.data() + out.n_reads, ws->d_out, nq * 8, cudaMemcpyDeviceToHost, st));
+          g_prof.d2h += nq * 8;
+          CU(cudaStreamSynchronize(st));
+        } else {
+          Workspace::grow_dev(ws->d_hit_off, ws->d_hit_off_cap, size_t(nq) + 1);
+          uint64_t n_hits = locate_chunk_count(r, ws, nq, ws->d_hit_off, st);
+          out.hit_off.resize(out.n_reads + nq + 1);
+          uint64_t* dst_off = out.hit_off.data() + out.n_reads;
+          CU(cudaMemcpyAsync(dst_off, ws->d_hit_off, (nq + 1) * 8, cudaMemcpyDeviceToHost, st));
+          if (n_hits) {
+            uint64_t* d_hits = locate_chunk_walk(r, ws, nq, n_hits, flags, ws->d_hit_off, st);
+            if (out.n_hits + n_hits > out.hits_cap) {
+              uint64_t cap = std::max<uint64_t>(out.n_hits + n_hits, out.hits_cap * 2);
+              void* np = realloc(out.hits, cap * sizeof(awry_hit));
+              if (!np) {
+                cudaFreeAsync(d_hits, st);
+                fail(AWRY_ERR_NOMEM, "out of host memory for %llu hits", (unsigned long long)cap);
+              }
+              out.hits = static_cast<awry_hit*>(np);
+              out.hits_cap = cap;
+            }
+            CU(cudaMemcpyAsync(out.hits + out.n_hits, d_hits, n_hits * 16, cudaMemcpyDeviceToHost, st));
+            cudaFreeAsync(d_hits, st);
+            g_prof.d2h += n_hits * 16;
+          }
+          CU(cudaStreamSynchronize(st));
+          g_prof.d2h += (nq + 1) * 8;
+          for (uint64_t i = 0; i <= nq; i++) dst_off[i] += out.n_hits;
+          out.n_hits += n_hits;
+        }
+        if (*ws->h_flag != ~0ull)
+          fail(AWRY_ERR_INVALID_QUERY,
+               "read %llu of %s is empty or contains a sentinel ('$'/'#'): the reference panics on it "
+               "(fm_index.rs:406, bwt.rs:127)",
+               (unsigned long long)(out.n_reads + *ws->h_flag), path);
+        out.n_reads += nq;
+        out.n_bases += plan.seq_bytes;
+      }
+      tail_len = n - plan.consumed;
+      tail_src = base + plan.consumed;
+      prev_slot = si;
+      if (eof) {
+        for (uint64_t i = 0; i < tail_len; i++) {
+          uint8_t ch = tail_src[i];
+          if (ch != '\n' && ch != '\r' && ch != ' ' && ch != '\t')
+            fail(AWRY_ERR_FORMAT, "%s ends with a truncated %s record", path, fastq ? "FASTQ" : "FASTA");
+        }
+        break;
+      }
+      if (tail_len > CARRY)
+        fail(AWRY_ERR_UNSUPPORTED, "%s holds a record larger than %llu bytes (AWRY_B200_READS_CHUNK)", path,
+             (unsigned long long)CARRY);
+    }
+  } catch (...) {
+    cleanup();
+    free(out.hits);
+    out.hits = nullptr;
+    throw;
+  }
+  cleanup();
+}
+
 uint32_t ascii_to_dsym(const awry_index* ix, uint8_t ch, bool* sentinel) {
   if (ch >= 'a' && ch <= 'z') ch = uint8_t(ch - 'a' + 'A');
   *sentinel = (ch == '$' || ch == '#');
@@ -1329,6 +1677,47 @@ int awry_locate_batch_into(const awry_index* ix, const uint8_t* qbytes, const ui
     free(tmp);
   });
 }
+
+int awry_count_reads_file(const awry_index* ix, const char* path, uint64_t** counts, uint64_t* n_reads) {
+  return guarded([&] {
+    need(ix);
+    if (!path || !counts || !n_reads) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    *counts = nullptr;
+    *n_reads = 0;
+    ReadsOut out;
+    run_reads_file(ix, path, false, 0, out);
+    uint64_t* buf = static_cast<uint64_t*>(malloc(std::max<size_t>(8, out.n_reads * 8)));
+    if (!buf) fail(AWRY_ERR_NOMEM, "out of host memory for %llu counts", (unsigned long long)out.n_reads);
+    if (out.n_reads) memcpy(buf, out.counts.data(), out.n_reads * 8);
+    *counts = buf;
+    *n_reads = out.n_reads;
+  });
+}
+
+int awry_locate_reads_file(const awry_index* ix, const char* path, uint32_t flags, uint64_t** hit_off, awry_hit** hits,
+                           uint64_t* n_reads, uint64_t* n_hits) {
+  return guarded([&] {
+    need(ix);
+    if (!path || !hit_off || !hits || !n_reads || !n_hits) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    *hit_off = nullptr;
+    *hits = nullptr;
+    *n_reads = *n_hits = 0;
+    ReadsOut out;
+    run_reads_file(ix, path, true, flags, out);
+    uint64_t* off = static_cast<uint64_t*>(malloc((out.n_reads + 1) * 8));
+    if (!off) {
+      free(out.hits);
+      fail(AWRY_ERR_NOMEM, "out of host memory for %llu offsets", (unsigned long long)out.n_reads);
+    }
+    memcpy(off, out.hit_off.data(), (out.n_reads + 1) * 8);
+    *hit_off = off;
+    *hits = out.hits;
+    *n_reads = out.n_reads;
+    *n_hits = out.n_hits;
+  });
+}
+
+void awry_buffer_free(void* p) { free(p); }
 
 int awry_initial_range(const awry_index* ix, uint8_t ascii_symbol, awry_range* out) {
   return guarded([&] {

@@ -118,7 +118,8 @@ class Profile(C.Structure):
 EXPORTS = ["awry_index_build", "awry_build_index_file", "awry_build_parts", "awry_parts_num_blocks", "awry_parts_block_words",
            "awry_parts_sa_words", "awry_index_load", "awry_index_from_parts", "awry_index_free", "awry_index_info",
            "awry_index_sequence_header", "awry_count_batch", "awry_search_batch",
-           "awry_locate_batch", "awry_locate_batch_into", "awry_hits_free", "awry_initial_range", "awry_update_range",
+           "awry_locate_batch", "awry_locate_batch_into", "awry_hits_free", "awry_count_reads_file",
+           "awry_locate_reads_file", "awry_buffer_free", "awry_initial_range", "awry_update_range",
            "awry_backstep", "awry_count_device", "awry_locate_device", "awry_device_free",
            "awry_device_check", "awry_profile_enable", "awry_profile_reset", "awry_profile_get",
            "awry_bench_random_gather", "awry_set_search_variant", "awry_set_locate_variant", "awry_last_error", "awry_version"]
@@ -171,6 +172,11 @@ def native():
     L.awry_profile_get.argtypes = [C.POINTER(Profile)]
     L.awry_bench_random_gather.argtypes = [i32, u64, C.c_uint32, C.c_uint32, u64, i32,
                                            C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.awry_count_reads_file.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(u64)]
+    L.awry_locate_reads_file.argtypes = [vp, C.c_char_p, C.c_uint32, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64),
+                                         C.POINTER(u64)]
+    L.awry_buffer_free.argtypes = [vp]
+    L.awry_buffer_free.restype = None
     L.awry_set_search_variant.argtypes = [i32, i32, i32]
     L.awry_set_locate_variant.argtypes = [i32]
     _LIB = L
@@ -380,6 +386,32 @@ class FmIndex:
             err.needed = n.value
             raise err
         return n.value
+
+    # ---- streaming reads-file front-end (FASTQ / FASTA parsed on the device) ---------------
+    def count_reads_file(self, path) -> np.ndarray:
+        """parallel_count over every record of a FASTQ / FASTA file; read i of the file is entry i."""
+        ptr, n = C.c_void_p(), C.c_uint64()
+        _check(native().awry_count_reads_file(self._h, os.fsencode(path), C.byref(ptr), C.byref(n)))
+        out = np.empty(n.value, dtype=np.uint64)
+        if n.value:
+            C.memmove(out.ctypes.data, ptr, n.value * 8)
+        native().awry_buffer_free(ptr)
+        return out
+
+    def locate_reads_file(self, path, sorted_hits: bool = False):
+        """parallel_locate over a FASTQ / FASTA file -> (hit_off uint64[n_reads+1], hits uint64[n_hits, 2])"""
+        off_p, hits_p, n, nh = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
+        _check(native().awry_locate_reads_file(self._h, os.fsencode(path),
+                                               LOCATE_SORTED if sorted_hits else LOCATE_BWT_ORDER,
+                                               C.byref(off_p), C.byref(hits_p), C.byref(n), C.byref(nh)))
+        off = np.empty(n.value + 1, dtype=np.uint64)
+        C.memmove(off.ctypes.data, off_p, (n.value + 1) * 8)
+        hits = np.empty((nh.value, 2), dtype=np.uint64)
+        if nh.value:
+            C.memmove(hits.ctypes.data, hits_p, nh.value * 16)
+        native().awry_buffer_free(off_p)
+        native().awry_hits_free(hits_p)
+        return off, hits
 
     def get_search_range_for_string(self, query) -> SearchRange:
         qb, qo = pack_queries([query])

@@ -89,6 +89,9 @@ def test_bad_arguments_are_errors_not_crashes(tmp_path):
     lib.awry_hits_free(None)
     assert lib.awry_profile_get(None) == -1
     assert lib.awry_set_search_variant(3, 0, 0) == -1
+    n = C.c_uint64()
+    assert lib.awry_count_reads_file(None, b"x.fq", C.byref(out), C.byref(n)) == -1
+    lib.awry_buffer_free(None)
     # construction: argument and input-file errors are reported before any device is needed
     assert lib.awry_index_build(None, None, 0, C.byref(out)) == -1
     assert lib.awry_build_index_file(None) == -1
