@@ -175,6 +175,35 @@ struct Workspace {
   void* d_temp = nullptr;
   size_t d_temp_cap = 0;
   unsigned long long* d_flag = nullptr;
+  // reads-file front-end scratch, kept across calls (pinned allocations cost ~0.4 ms per MiB)
+  struct ReadsScratch {
+    uint64_t chunk = 0, carry = 0;
+    uint8_t* h_buf[3] = {nullptr, nullptr, nullptr};
+    uint8_t *d_raw = nullptr, *d_qbytes = nullptr;
+    uint32_t *d_nl = nullptr, *d_small = nullptr, *d_seq_len = nullptr, *d_is_hdr = nullptr, *d_hdr_rank = nullptr;
+    uint64_t *d_seq_off = nullptr, *d_qoff = nullptr;
+    size_t cap_lines = 0, cap_qoff = 0, temp_bytes = 0;
+    void* d_temp = nullptr;
+    void* h_plan = nullptr;
+    void release() {
+      for (auto& b : h_buf) {
+        cudaFreeHost(b);
+        b = nullptr;
+      }
+      cudaFree(d_raw);
+      cudaFree(d_qbytes);
+      cudaFree(d_nl);
+      cudaFree(d_small);
+      cudaFree(d_seq_len);
+      cudaFree(d_is_hdr);
+      cudaFree(d_hdr_rank);
+      cudaFree(d_seq_off);
+      cudaFree(d_qoff);
+      cudaFree(d_temp);
+      cudaFreeHost(h_plan);
+      *this = ReadsScratch();
+    }
+  } rs;
 
   template <class T>
   static void grow_dev(T*& p, size_t& cap, size_t need) {
@@ -218,6 +247,7 @@ struct Workspace {
     cudaFree(d_hit_off);
     cudaFree(d_temp);
     cudaFree(d_flag);
+    rs.release();
     if (done) cudaEventDestroy(done);
     if (st) cudaStreamDestroy(st);
   }
@@ -982,7 +1012,7 @@ struct ReadsOut {
 };
 
 void parallel_pread(int fd, void* dst, size_t n, off_t pos, const char* what) {
-  unsigned nt = n >= (32u << 20) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+  unsigned nt = n >= (4u << 20) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
   size_t per = ((n + nt - 1) / nt + 4095) & ~size_t(4095);
   std::vector<int> ok(nt, 1);
   auto work = [&](unsigned t) {
@@ -1048,20 +1078,16 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
   uint64_t CHUNK = 64ull << 20;
   if (const char* e = getenv("AWRY_B200_READS_CHUNK")) CHUNK = std::max<uint64_t>(64, strtoull(e, nullptr, 10));
   CHUNK = std::min<uint64_t>(CHUNK, 512ull << 20);
-  const uint64_t CARRY = CHUNK;  // the largest record that can straddle a chunk boundary
+  // the largest record that can straddle a chunk boundary (AWRY_B200_READS_CARRY, default min(chunk, 16 MiB))
+  uint64_t CARRY = std::min<uint64_t>(CHUNK, 16ull << 20);
+  if (const char* e = getenv("AWRY_B200_READS_CARRY")) CARRY = std::min<uint64_t>(std::max<uint64_t>(64, strtoull(e, nullptr, 10)), 1ull << 30);
   constexpr int NBUF = 3;
 
   Replica& r = *ix->reps[0];
   DeviceGuard dg(r.device);
   Workspace* ws = r.acquire();
   cudaStream_t st = ws->st;
-  uint8_t* h_buf[NBUF] = {nullptr, nullptr, nullptr};
-  uint8_t *d_raw = nullptr, *d_qbytes = nullptr;
-  uint32_t *d_nl = nullptr, *d_small = nullptr, *d_seq_len = nullptr, *d_is_hdr = nullptr, *d_hdr_rank = nullptr;
-  uint64_t *d_seq_off = nullptr, *d_qoff = nullptr;
-  size_t cap_lines = 0, cap_qoff = 0;
-  void* d_temp = nullptr;
-  ReadsPlan* h_plan = nullptr;
+  Workspace::ReadsScratch& rs = ws->rs;
 
   // reader thread state
   std::mutex mu;
@@ -1083,30 +1109,32 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
     cv.notify_all();
     if (reader.joinable()) reader.join();
     cudaStreamSynchronize(st);
-    for (auto& b : h_buf) cudaFreeHost(b);
-    cudaFree(d_raw);
-    cudaFree(d_qbytes);
-    cudaFree(d_nl);
-    cudaFree(d_small);
-    cudaFree(d_seq_len);
-    cudaFree(d_is_hdr);
-    cudaFree(d_hdr_rank);
-    cudaFree(d_seq_off);
-    cudaFree(d_qoff);
-    cudaFree(d_temp);
-    cudaFreeHost(h_plan);
     r.release(ws);
   };
   try {
-    for (auto& b : h_buf) CU(cudaHostAlloc(reinterpret_cast<void**>(&b), CARRY + CHUNK + 64, cudaHostAllocDefault));
     const uint32_t max_bytes = uint32_t(CARRY + CHUNK + 1);
-    CU(cudaMalloc(reinterpret_cast<void**>(&d_raw), max_bytes + 64));
-    CU(cudaMalloc(reinterpret_cast<void**>(&d_qbytes), max_bytes + 64));
-    CU(cudaMalloc(reinterpret_cast<void**>(&d_nl), size_t(max_bytes) * 4 + 64));
-    CU(cudaMalloc(reinterpret_cast<void**>(&d_small), 64));
-    const size_t temp_bytes = reads_temp_bytes(max_bytes);
-    CU(cudaMalloc(&d_temp, temp_bytes));
-    CU(cudaHostAlloc(reinterpret_cast<void**>(&h_plan), sizeof(ReadsPlan) + 64, cudaHostAllocDefault));
+    if (rs.chunk != CHUNK || rs.carry != CARRY) {
+      rs.release();
+      for (auto& b : rs.h_buf) CU(cudaHostAlloc(reinterpret_cast<void**>(&b), CARRY + CHUNK + 64, cudaHostAllocDefault));
+      CU(cudaMalloc(reinterpret_cast<void**>(&rs.d_raw), max_bytes + 64));
+      CU(cudaMalloc(reinterpret_cast<void**>(&rs.d_qbytes), max_bytes + 64));
+      CU(cudaMalloc(reinterpret_cast<void**>(&rs.d_nl), size_t(max_bytes) * 4 + 64));
+      CU(cudaMalloc(reinterpret_cast<void**>(&rs.d_small), 64));
+      rs.temp_bytes = reads_temp_bytes(max_bytes);
+      CU(cudaMalloc(&rs.d_temp, rs.temp_bytes));
+      CU(cudaHostAlloc(&rs.h_plan, sizeof(ReadsPlan) + 64, cudaHostAllocDefault));
+      rs.chunk = CHUNK;
+      rs.carry = CARRY;
+    }
+    uint8_t** h_buf = rs.h_buf;
+    uint8_t *d_raw = rs.d_raw, *d_qbytes = rs.d_qbytes;
+    uint32_t *d_nl = rs.d_nl, *d_small = rs.d_small;
+    uint32_t *&d_seq_len = rs.d_seq_len, *&d_is_hdr = rs.d_is_hdr, *&d_hdr_rank = rs.d_hdr_rank;
+    uint64_t *&d_seq_off = rs.d_seq_off, *&d_qoff = rs.d_qoff;
+    size_t &cap_lines = rs.cap_lines, &cap_qoff = rs.cap_qoff;
+    void* d_temp = rs.d_temp;
+    const size_t temp_bytes = rs.temp_bytes;
+    ReadsPlan* h_plan = static_cast<ReadsPlan*>(rs.h_plan);
     uint32_t* h_n_lines = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(h_plan) + sizeof(ReadsPlan));
 
     reader = std::thread([&] {
