@@ -26,6 +26,7 @@
 
 #include "../../include/awry_b200.h"
 #include "build.hpp"
+#include "hostpack.hpp"
 #include "kernels.hpp"
 #include "reads.hpp"
 
@@ -142,6 +143,7 @@ void prof_collect_locked() {
 }
 
 SearchVariant g_variant;  // experiments only (awry_set_search_variant)
+int g_host_pack = -1;       // -1 = auto (AWRY_B200_HOST_PACK, CPU support, >= 4 pool threads), 0 = off, 1 = on
 int g_locate_variant = 0;   // 0 = unsampled-SA gather when the array exists, 1 = always LF-walk (awry_set_locate_variant)
 
 
@@ -159,6 +161,9 @@ struct Workspace {
   uint8_t* h_out = nullptr;
   size_t h_out_cap = 0;  // bytes
   unsigned long long* h_flag = nullptr;
+  uint64_t* h_exc = nullptr;  // host-packed chunks: exception list (bytes outside ACGT)
+  size_t h_exc_cap = 0;
+  std::vector<uint64_t> exc_tmp;
   // device
   uint8_t* d_qbytes = nullptr;
   size_t d_qbytes_cap = 0;
@@ -175,6 +180,8 @@ struct Workspace {
   void* d_temp = nullptr;
   size_t d_temp_cap = 0;
   unsigned long long* d_flag = nullptr;
+  uint64_t* d_exc = nullptr;
+  size_t d_exc_cap = 0;
   // reads-file front-end scratch, kept across calls (pinned allocations cost ~0.4 ms per MiB)
   struct ReadsScratch {
     uint64_t chunk = 0, carry = 0;
@@ -239,6 +246,8 @@ struct Workspace {
     cudaFreeHost(h_qoff);
     cudaFreeHost(h_out);
     cudaFreeHost(h_flag);
+    cudaFreeHost(h_exc);
+    cudaFree(d_exc);
     cudaFree(d_qbytes);
     cudaFree(d_qoff);
     cudaFree(d_qwords);
@@ -708,8 +717,15 @@ void parallel_memcpy(void* dst, const void* src, size_t n) {
 
 // Pipeline chunk: small enough that the exposed first upload / last kernel are a few percent of a
 // 10 M-read batch, large enough (~0.9 M reads) to keep the persistent search grid busy.
-constexpr uint64_t CHUNK_MAX_Q = 1u << 20;        // queries per pipeline chunk
-constexpr uint64_t CHUNK_MAX_BYTES = 128u << 20;  // query bytes per pipeline chunk
+constexpr uint64_t CHUNK_MAX_Q = 1u << 20;  // queries per pipeline chunk
+uint64_t chunk_max_bytes() {                 // query bytes per pipeline chunk (AWRY_B200_CHUNK_MB, default 128)
+  static const uint64_t v = [] {
+    uint64_t mb = 128;
+    if (const char* e = getenv("AWRY_B200_CHUNK_MB")) mb = std::min<uint64_t>(1024, std::max<uint64_t>(1, strtoull(e, nullptr, 10)));
+    return mb << 20;
+  }();
+  return v;
+}
 
 struct Chunk {
   uint64_t q0, q1, b0, b1;
@@ -739,6 +755,15 @@ std::vector<Chunk> make_chunks(const uint64_t* qoff, uint64_t q_lo, uint64_t q_h
   return out;
 }
 
+bool host_pack_enabled() {
+  if (g_host_pack >= 0) return g_host_pack == 1 && host_pack_supported();
+  static const bool on = [] {
+    if (const char* e = getenv("AWRY_B200_HOST_PACK")) return e[0] != '0' && host_pack_supported();
+    return host_pack_supported() && host_pool_threads() >= 4;
+  }();
+  return on;
+}
+
 void validate_offsets(const uint64_t* qoff, uint64_t nq) {
   // cheap sanity check on the ends; per-query monotonicity is checked on the device (prepass)
   if (nq && qoff[nq] < qoff[0]) fail(AWRY_ERR_INVALID_ARG, "query offsets are not monotone");
@@ -754,25 +779,58 @@ void enqueue_search(const awry_index* ix, Replica& r, Workspace* ws, const uint8
   Workspace::grow_dev(ws->d_qoff, ws->d_qoff_cap, size_t(nq) + 1);
   Workspace::grow_dev(ws->d_qwords, ws->d_qwords_cap, size_t(packed_words(ix->alphabet, nq, nbytes)));
   Workspace::grow_dev(ws->d_out, ws->d_out_cap, size_t(nq) * out_elem);
-  Workspace::grow_dev(ws->d_defer, ws->d_defer_cap, size_t(nq) + 1);
+  Workspace::grow_dev(ws->d_defer, ws->d_defer_cap, size_t(nq) + 2);
   const uint8_t* src_b = qbytes + c.b0;
   const uint64_t* src_o = qoff + c.q0;
-  if (!src_pinned) {
-    Workspace::grow_host(ws->h_qbytes, ws->h_qbytes_cap, size_t(nbytes) + 16);
-    Workspace::grow_host(ws->h_qoff, ws->h_qoff_cap, size_t(nq) + 1);
-    parallel_memcpy(ws->h_qbytes, src_b, nbytes);
-    parallel_memcpy(ws->h_qoff, src_o, (nq + 1) * 8);
-    src_b = ws->h_qbytes;
-    src_o = ws->h_qoff;
+  // Nucleotide chunks are packed to 2 bits per base by the host cores before the copy (a quarter of
+  // the PCIe bytes; works the same for pageable and pinned caller memory).  Chunks with many bytes
+  // outside ACGT go up as ASCII.
+  bool packed = false;
+  if (ix->alphabet == AWRY_NUCLEOTIDE && host_pack_enabled() && nbytes >= 4096) {
+    Workspace::grow_host(ws->h_qbytes, ws->h_qbytes_cap, size_t(nbytes) / 4 + 64);
+    packed = host_pack_dna(src_b, size_t(nbytes), ws->h_qbytes, ws->exc_tmp, 64);
   }
-  if (nbytes) CU(cudaMemcpyAsync(ws->d_qbytes, src_b, nbytes, cudaMemcpyHostToDevice, ws->st));
-  CU(cudaMemcpyAsync(ws->d_qoff, src_o, (nq + 1) * 8, cudaMemcpyHostToDevice, ws->st));
-  g_prof.h2d += nbytes + (nq + 1) * 8;
-  CU(cudaMemsetAsync(ws->d_flag, 0xff, 8, ws->st));
-  // offsets stay absolute: the kernels subtract the chunk's byte base
-  {
-    ProfScope p(2, r.device, ws->st);
-    CU(launch_pack(ix->alphabet, ws->d_qbytes - c.b0, ws->d_qoff, nq, ws->d_qwords - 4 * (c.b0 >> packed_unit_shift(ix->alphabet)), ws->d_flag, ws->st));
+  if (packed) {
+    const size_t n_exc = ws->exc_tmp.size();
+    const size_t pbytes = (size_t(nbytes) + 3) / 4;
+    if (!src_pinned) {  // offsets: staged through pinned memory by the pool
+      Workspace::grow_host(ws->h_qoff, ws->h_qoff_cap, size_t(nq) + 1);
+      parallel_memcpy(ws->h_qoff, src_o, (nq + 1) * 8);
+      src_o = ws->h_qoff;
+    }
+    CU(cudaMemcpyAsync(ws->d_qbytes, ws->h_qbytes, pbytes + 8, cudaMemcpyHostToDevice, ws->st));
+    CU(cudaMemcpyAsync(ws->d_qoff, src_o, (nq + 1) * 8, cudaMemcpyHostToDevice, ws->st));
+    if (n_exc) {
+      Workspace::grow_host(ws->h_exc, ws->h_exc_cap, n_exc);
+      Workspace::grow_dev(ws->d_exc, ws->d_exc_cap, n_exc);
+      memcpy(ws->h_exc, ws->exc_tmp.data(), n_exc * 8);
+      CU(cudaMemcpyAsync(ws->d_exc, ws->h_exc, n_exc * 8, cudaMemcpyHostToDevice, ws->st));
+    }
+    g_prof.h2d += pbytes + 8 + (nq + 1) * 8 + n_exc * 8;
+    CU(cudaMemsetAsync(ws->d_flag, 0xff, 8, ws->st));
+    {
+      ProfScope p(2, r.device, ws->st);
+      CU(launch_pack2(reinterpret_cast<const uint32_t*>(ws->d_qbytes), c.b0, ws->d_qoff, nq,
+                      ws->d_qwords - 4 * (c.b0 >> packed_unit_shift(ix->alphabet)), ws->d_exc, n_exc, ws->d_flag, ws->st));
+    }
+  } else {
+    if (!src_pinned) {
+      Workspace::grow_host(ws->h_qbytes, ws->h_qbytes_cap, size_t(nbytes) + 16);
+      Workspace::grow_host(ws->h_qoff, ws->h_qoff_cap, size_t(nq) + 1);
+      parallel_memcpy(ws->h_qbytes, src_b, nbytes);
+      parallel_memcpy(ws->h_qoff, src_o, (nq + 1) * 8);
+      src_b = ws->h_qbytes;
+      src_o = ws->h_qoff;
+    }
+    if (nbytes) CU(cudaMemcpyAsync(ws->d_qbytes, src_b, nbytes, cudaMemcpyHostToDevice, ws->st));
+    CU(cudaMemcpyAsync(ws->d_qoff, src_o, (nq + 1) * 8, cudaMemcpyHostToDevice, ws->st));
+    g_prof.h2d += nbytes + (nq + 1) * 8;
+    CU(cudaMemsetAsync(ws->d_flag, 0xff, 8, ws->st));
+    // offsets stay absolute: the kernels subtract the chunk's byte base
+    {
+      ProfScope p(2, r.device, ws->st);
+      CU(launch_pack(ix->alphabet, ws->d_qbytes - c.b0, ws->d_qoff, nq, ws->d_qwords - 4 * (c.b0 >> packed_unit_shift(ix->alphabet)), ws->d_flag, ws->st));
+    }
   }
   {
     ProfScope p(0, r.device, ws->st);
@@ -797,7 +855,7 @@ void search_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
   const size_t out_elem = mode == OUT_COUNT_U64 ? 8 : 16;
   const bool src_pinned = is_pinned(qbytes) && is_pinned(qoff);
   const bool dst_pinned = is_pinned(out);
-  auto chunks = make_chunks(qoff, q_lo, q_hi, CHUNK_MAX_Q, CHUNK_MAX_BYTES);
+  auto chunks = make_chunks(qoff, q_lo, q_hi, CHUNK_MAX_Q, chunk_max_bytes());
   constexpr int DEPTH = 3;
   Workspace* ws[DEPTH] = {nullptr, nullptr, nullptr};
   int pending[DEPTH] = {-1, -1, -1};
@@ -952,7 +1010,7 @@ void locate_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
   if (q_lo >= q_hi) return;
   DeviceGuard dg(r.device);
   const bool src_pinned = is_pinned(qbytes) && is_pinned(qoff);
-  auto chunks = make_chunks(qoff, q_lo, q_hi, CHUNK_MAX_Q, CHUNK_MAX_BYTES);
+  auto chunks = make_chunks(qoff, q_lo, q_hi, CHUNK_MAX_Q, chunk_max_bytes());
   Workspace* ws = r.acquire();
   size_t cap = 0;
   try {
@@ -1231,7 +1289,7 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
       if (nq) {
         Workspace::grow_dev(ws->d_qwords, ws->d_qwords_cap, size_t(packed_words(ix->alphabet, nq, plan.seq_bytes)));
         Workspace::grow_dev(ws->d_out, ws->d_out_cap, size_t(nq) * 8);
-        Workspace::grow_dev(ws->d_defer, ws->d_defer_cap, size_t(nq) + 1);
+        Workspace::grow_dev(ws->d_defer, ws->d_defer_cap, size_t(nq) + 2);
         CU(cudaMemsetAsync(ws->d_flag, 0xff, 8, st));
         {
           ProfScope p(2, r.device, st);
@@ -1877,7 +1935,7 @@ int awry_locate_device(const awry_index* ix, int replica, const uint8_t* d_qbyte
       uint64_t words = 4 * (nq + ((ends[1] >> sh) - (ends[0] >> sh)) + 2) + 32;
       Workspace::grow_dev(ws->d_qwords, ws->d_qwords_cap, size_t(words));
       Workspace::grow_dev(ws->d_out, ws->d_out_cap, size_t(nq) * 8);
-      Workspace::grow_dev(ws->d_defer, ws->d_defer_cap, size_t(nq) + 1);
+      Workspace::grow_dev(ws->d_defer, ws->d_defer_cap, size_t(nq) + 2);
       {
         ProfScope p(2, r.device, st);
         CU(launch_pack(ix->alphabet, d_qbytes, d_qoff, nq, ws->d_qwords - 4 * (ends[0] >> sh), r.d_async_flag, st));
@@ -1967,6 +2025,24 @@ int awry_bench_random_gather(int device, uint64_t footprint_bytes, uint32_t gran
     cudaError_t e = run_random_gather(footprint_bytes, granule, lanes, n_reads, iters, reads_per_s, gb_per_s);
     if (e == cudaErrorInvalidValue) fail(AWRY_ERR_INVALID_ARG, "unsupported granule/lanes combination %u/%u", granule, lanes);
     CU(e);
+  });
+}
+
+int awry_set_host_pack(int mode) {
+  return guarded([&] {
+    if (mode < -1 || mode > 1) fail(AWRY_ERR_INVALID_ARG, "host pack mode must be -1 (auto), 0 (off) or 1 (on)");
+    g_host_pack = mode;
+  });
+}
+
+int awry_host_pack_dna(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t* exceptions, uint64_t exc_cap, uint64_t* n_exc) {
+  return guarded([&] {
+    if (!src || !dst || !n_exc) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    std::vector<uint64_t> exc;
+    host_pack_dna(src, size_t(n), dst, exc, 0);
+    *n_exc = exc.size();
+    if (exceptions)
+      for (size_t i = 0; i < exc.size() && i < exc_cap; i++) exceptions[i] = exc[i];
   });
 }
 

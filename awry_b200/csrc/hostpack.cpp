@@ -1,0 +1,227 @@
+// hostpack.cpp -- host-side 2-bit packing of nucleotide queries ahead of the PCIe copy.
+//
+// Why: parallel_count's input is ASCII (`&str`, /root/reference/src/fm_index.rs:455-460); 10 M x 150-bp
+// reads are 1.5 GB, which a PCIe 5 x16 link moves in ~29 ms -- longer than the 20 ms the search kernel
+// needs.  The host cores pack the bases to 2 bits while earlier chunks are in flight, so only a quarter
+// of the bytes cross the link; the device expands them to its 4-bit search-order words (pack2_kernel).
+// Plain C++ (g++), no CUDA: SIMD levels are selected at run time.
+#include "hostpack.hpp"
+
+#include <immintrin.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+
+namespace awry {
+
+namespace {
+
+// ---------------------------------------------------------------- thread pool
+class Pool {
+ public:
+  explicit Pool(int n) : n_(n) {
+    for (int t = 1; t < n_; t++) workers_.emplace_back([this, t] { loop(t); });
+  }
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      quit_ = true;
+      gen_++;
+    }
+    cv_.notify_all();
+    for (auto& w : workers_) w.join();
+  }
+  int size() const { return n_; }
+  void run(const std::function<void(int, int)>& fn) {
+    std::lock_guard<std::mutex> serial(run_mu_);  // one parallel region at a time
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn;
+      pending_ = n_ - 1;
+      gen_++;
+    }
+    cv_.notify_all();
+    fn(0, n_);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void loop(int t) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(int, int)>* fn;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (quit_) return;
+        fn = fn_;
+      }
+      (*fn)(t, n_);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        pending_--;
+      }
+      done_cv_.notify_one();
+    }
+  }
+  int n_;
+  std::vector<std::thread> workers_;
+  std::mutex mu_, run_mu_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(int, int)>* fn_ = nullptr;
+  int pending_ = 0;
+  uint64_t gen_ = 0;
+  bool quit_ = false;
+};
+
+int default_threads() {
+  if (const char* e = getenv("AWRY_B200_HOST_THREADS")) {
+    int v = atoi(e);
+    if (v >= 1) return std::min(v, 64);
+  }
+  int hw = int(std::max(1u, std::thread::hardware_concurrency()));
+  int local = 1;
+  if (const char* e = getenv("LOCAL_WORLD_SIZE")) local = std::max(1, atoi(e));  // one process per GPU
+  return std::max(1, std::min(16, hw / local));
+}
+
+Pool& pool() {
+  static Pool p(default_threads());
+  return p;
+}
+
+// ---------------------------------------------------------------- packers
+inline bool is_acgt(uint8_t c) {
+  c &= 0xDF;
+  return c == 'A' || c == 'C' || c == 'G' || c == 'T';
+}
+
+void pack_scalar(const uint8_t* src, size_t lo, size_t hi, uint8_t* dst, std::vector<uint64_t>& exc) {
+  for (size_t i = lo; i < hi; i++) {
+    uint8_t c = src[i];
+    if (!is_acgt(c)) exc.push_back((uint64_t(i) << 8) | c);
+    uint8_t crumb = uint8_t((c >> 1) & 3u);
+    uint8_t sh = uint8_t(2 * (i & 3));
+    dst[i >> 2] = uint8_t((dst[i >> 2] & ~(3u << sh)) | (crumb << sh));
+  }
+}
+
+// [lo, hi) with lo % 32 == 0 and (hi - lo) % 32 == 0
+__attribute__((target("avx2,bmi2"))) void pack_avx2(const uint8_t* src, size_t lo, size_t hi, uint8_t* dst,
+                                                      std::vector<uint64_t>& exc) {
+  const __m256i up_mask = _mm256_set1_epi8(char(0xDF));
+  const __m256i cA = _mm256_set1_epi8('A'), cC = _mm256_set1_epi8('C'), cG = _mm256_set1_epi8('G'),
+                cT = _mm256_set1_epi8('T');
+  for (size_t i = lo; i < hi; i += 32) {
+    __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
+    __m256i up = _mm256_and_si256(v, up_mask);
+    __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(up, cA), _mm256_cmpeq_epi8(up, cC)),
+                                 _mm256_or_si256(_mm256_cmpeq_epi8(up, cG), _mm256_cmpeq_epi8(up, cT)));
+    uint32_t bad = ~uint32_t(_mm256_movemask_epi8(ok));
+    while (bad) {
+      unsigned b = unsigned(__builtin_ctz(bad));
+      bad &= bad - 1;
+      exc.push_back((uint64_t(i + b) << 8) | src[i + b]);
+    }
+    uint64_t w0 = uint64_t(_mm256_extract_epi64(v, 0)), w1 = uint64_t(_mm256_extract_epi64(v, 1)),
+             w2 = uint64_t(_mm256_extract_epi64(v, 2)), w3 = uint64_t(_mm256_extract_epi64(v, 3));
+    const uint64_t M = 0x0606060606060606ull;
+    uint64_t out = _pext_u64(w0, M) | (_pext_u64(w1, M) << 16) | (_pext_u64(w2, M) << 32) | (_pext_u64(w3, M) << 48);
+    memcpy(dst + (i >> 2), &out, 8);
+  }
+}
+
+// [lo, hi) with lo % 64 == 0 and (hi - lo) % 64 == 0
+__attribute__((target("avx512f,avx512bw"))) void pack_avx512(const uint8_t* src, size_t lo, size_t hi, uint8_t* dst,
+                                                               std::vector<uint64_t>& exc) {
+  const __m512i up_mask = _mm512_set1_epi8(char(0xDF));
+  const __m512i cA = _mm512_set1_epi8('A'), cC = _mm512_set1_epi8('C'), cG = _mm512_set1_epi8('G'),
+                cT = _mm512_set1_epi8('T');
+  const __m512i three = _mm512_set1_epi8(3);
+  const __m512i mul8 = _mm512_set1_epi16(0x0401);   // b0 + 4*b1      (pmaddubsw: unsigned a * signed b)
+  const __m512i mul16 = _mm512_set1_epi32(0x00100001);  // w0 + 16*w1 (pmaddwd)
+  for (size_t i = lo; i < hi; i += 64) {
+    __m512i v = _mm512_loadu_si512(src + i);
+    __m512i up = _mm512_and_si512(v, up_mask);
+    __mmask64 ok = _mm512_cmpeq_epi8_mask(up, cA) | _mm512_cmpeq_epi8_mask(up, cC) | _mm512_cmpeq_epi8_mask(up, cG) |
+                   _mm512_cmpeq_epi8_mask(up, cT);
+    uint64_t bad = ~uint64_t(ok);
+    while (bad) {
+      unsigned b = unsigned(__builtin_ctzll(bad));
+      bad &= bad - 1;
+      exc.push_back((uint64_t(i + b) << 8) | src[i + b]);
+    }
+    __m512i crumbs = _mm512_and_si512(_mm512_srli_epi16(v, 1), three);  // per byte: (c >> 1) & 3
+    __m512i w = _mm512_maddubs_epi16(crumbs, mul8);                      // 16-bit: c0 | c1 << 2
+    __m512i d = _mm512_madd_epi16(w, mul16);                             // 32-bit: c0 | c1<<2 | c2<<4 | c3<<6
+    __m128i bytes = _mm512_cvtepi32_epi8(d);                             // 16 packed bytes
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + (i >> 2)), bytes);
+  }
+}
+
+enum Level { SCALAR = 0, AVX2 = 1, AVX512 = 2 };
+Level simd_level() {
+  static Level l = [] {
+    if (const char* e = getenv("AWRY_B200_HOST_SIMD")) {  // tests: 0 scalar, 1 avx2, 2 avx512
+      int v = atoi(e);
+      if (v == 0) return SCALAR;
+      if (v == 1 && __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2")) return AVX2;
+    }
+    if (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw")) return AVX512;
+    if (__builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2")) return AVX2;
+    return SCALAR;
+  }();
+  return l;
+}
+
+}  // namespace
+
+bool host_pack_supported() { return __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2"); }
+int host_pool_threads() { return pool().size(); }
+void host_parallel(const std::function<void(int, int)>& fn) { pool().run(fn); }
+
+bool host_pack_dna(const uint8_t* src, size_t n, uint8_t* dst, std::vector<uint64_t>& exceptions, size_t max_exc_div) {
+  exceptions.clear();
+  if (n == 0) return true;
+  const Level lvl = simd_level();
+  const size_t G = 64;  // granule: both SIMD widths and whole output bytes
+  const size_t n_gran = n / G;
+  const int nt_pool = pool().size();
+  const int nt = int(std::max<size_t>(1, std::min<size_t>(size_t(nt_pool), n / (256u << 10) + 1)));
+  std::vector<std::vector<uint64_t>> exc(size_t(nt) + 1);
+  auto body = [&](int t, int) {
+    if (t >= nt) return;
+    size_t lo = n_gran * size_t(t) / size_t(nt) * G, hi = n_gran * size_t(t + 1) / size_t(nt) * G;
+    if (lo >= hi) return;
+    if (lvl == AVX512)
+      pack_avx512(src, lo, hi, dst, exc[size_t(t)]);
+    else if (lvl == AVX2)
+      pack_avx2(src, lo, hi, dst, exc[size_t(t)]);
+    else
+      pack_scalar(src, lo, hi, dst, exc[size_t(t)]);
+  };
+  if (nt == 1)
+    body(0, 1);
+  else
+    pool().run(body);
+  if (n_gran * G < n) {  // tail
+    memset(dst + (n_gran * G) / 4, 0, (n - n_gran * G + 3) / 4);
+    pack_scalar(src, n_gran * G, n, dst, exc[size_t(nt)]);
+  }
+  size_t total = 0;
+  for (auto& e : exc) total += e.size();
+  if (max_exc_div && total > n / max_exc_div + 16) return false;
+  exceptions.reserve(total);
+  for (auto& e : exc) exceptions.insert(exceptions.end(), e.begin(), e.end());
+  return true;
+}
+
+}  // namespace awry

@@ -478,6 +478,96 @@ cudaError_t launch_pack(int alphabet, const uint8_t* d_qbytes, const uint64_t* d
   return cudaGetLastError();
 }
 
+// ---- 2-bit host-packed nucleotide queries -> 4-bit search-order words ----
+// The host sends crumb i = (ascii[i] >> 1) & 3 (A0 C1 T2 G3) for every query byte of the chunk, four per
+// byte in text order (hostpack.cpp), a quarter of the PCIe bytes of the ASCII form.  8 lanes per query as
+// in pack_kernel; a word takes the 16 crumbs it covers with two 32-bit loads and a funnel shift, reverses
+// their order (search order = last character first), swaps codes 2 <-> 3 (device symbols are A0 C1 G2 T3)
+// and spreads each crumb to a nibble.  Bytes that were not ACGT (N, IUPAC codes, '$') come separately as
+// exceptions and are patched in afterwards.
+__device__ __forceinline__ uint32_t spread8_crumbs(uint32_t v) {  // 8 crumbs (16 bits) -> 8 nibbles
+  v &= 0xffffu;
+  v = (v | (v << 8)) & 0x00ff00ffu;
+  v = (v | (v << 4)) & 0x0f0f0f0fu;
+  v = (v | (v << 2)) & 0x33333333u;
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+    pack2_kernel(const uint32_t* __restrict__ crumbs, uint64_t base, const uint64_t* __restrict__ qoff, uint64_t nq,
+                 uint64_t* __restrict__ qwords, unsigned long long* first_bad) {
+  const uint32_t sub = threadIdx.x & 7;
+  const uint64_t ngroups = (gridDim.x * uint64_t(blockDim.x)) >> 3;
+  for (uint64_t q = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 3; q < nq; q += ngroups) {
+    const uint64_t o0 = qoff[q], o1 = qoff[q + 1];
+    if (o1 <= o0 || o1 - o0 >= (1ull << 32)) {
+      if (sub == 0) atomicMin(first_bad, (unsigned long long)q);
+      continue;
+    }
+    const uint32_t len = uint32_t(o1 - o0);
+    const uint32_t nwords = (len + 15) >> 4;
+    uint64_t* const dst = qwords + 4 * (q + (o0 >> 6));
+    const uint64_t c0 = o0 - base;  // crumb index of the query's first character
+    for (uint32_t wi = sub; wi < nwords; wi += 8) {
+      const uint32_t hi = len - 16 * wi;            // text positions [lo, hi) feed this word
+      const uint32_t lo = hi >= 16 ? hi - 16 : 0;
+      const uint32_t cnt = hi - lo;
+      const uint64_t bit = 2 * (c0 + lo);
+      const uint32_t* a = crumbs + (bit >> 5);
+      uint32_t x = __funnelshift_r(__ldg(a), __ldg(a + 1), uint32_t(bit & 31));  // crumb j = text position lo + j
+      x <<= 2 * (16 - cnt);                         // (cnt >= 1) drop what belongs to the next query
+      uint32_t r = __brev(x);                        // reverses crumb order and the two bits of each crumb
+      r = ((r & 0x55555555u) << 1) | ((r >> 1) & 0x55555555u);
+      r ^= (r >> 1) & 0x55555555u;                   // codes 2 <-> 3
+      dst[wi] = uint64_t(spread8_crumbs(r)) | (uint64_t(spread8_crumbs(r >> 16)) << 32);
+    }
+  }
+}
+
+// exceptions: (chunk-relative byte position << 8) | ASCII byte, for bytes outside ACGTacgt
+__global__ void patch_exceptions_kernel(const uint64_t* __restrict__ exc, uint64_t n_exc, uint64_t base,
+                                        const uint64_t* __restrict__ qoff, uint64_t nq, uint64_t* __restrict__ qwords,
+                                        unsigned long long* first_bad) {
+  uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (i >= n_exc) return;
+  const uint64_t pos = base + (exc[i] >> 8);
+  const uint32_t d = c_ascii_to_dsym[0][exc[i] & 0xff];
+  uint64_t lo = 0, hi = nq;  // last q with qoff[q] <= pos
+  while (hi - lo > 1) {
+    uint64_t mid = (lo + hi) >> 1;
+    if (qoff[mid] <= pos)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  const uint64_t q = lo, o0 = qoff[q], o1 = qoff[q + 1];
+  if (pos < o0 || pos >= o1) return;  // not inside any query of this chunk
+  if (d == uint32_t(DNA_SENTINEL)) {
+    atomicMin(first_bad, (unsigned long long)q);
+    return;
+  }
+  const uint32_t si = uint32_t(o1 - 1 - pos);  // search-order index
+  unsigned long long* w = reinterpret_cast<unsigned long long*>(qwords + 4 * (q + (o0 >> 6)) + (si >> 4));
+  const uint32_t sh = 4 * (si & 15);
+  atomicAnd(w, ~(0xfull << sh));
+  atomicOr(w, uint64_t(d) << sh);
+}
+
+cudaError_t launch_pack2(const uint32_t* d_crumbs, uint64_t base, const uint64_t* d_qoff, uint64_t nq, uint64_t* d_qwords,
+                         const uint64_t* d_exc, uint64_t n_exc, unsigned long long* d_first_bad, cudaStream_t s) {
+  if (nq == 0) return cudaSuccess;
+  uint64_t threads = nq * 8;
+  unsigned grid = unsigned(std::min<uint64_t>((threads + 255) / 256, 148 * 64));
+  pack2_kernel<<<grid, 256, 0, s>>>(d_crumbs, base, d_qoff, nq, d_qwords, d_first_bad);
+  COUNT_LAUNCH();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || n_exc == 0) return e;
+  patch_exceptions_kernel<<<unsigned((n_exc + 255) / 256), 256, 0, s>>>(d_exc, n_exc, base, d_qoff, nq, d_qwords,
+                                                                        d_first_bad);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ backward search
 
 template <int MODE>
@@ -851,6 +941,8 @@ __device__ __forceinline__ PairSlice pair_slice(const u32x8& x, uint32_t sub, ui
   return r;
 }
 
+constexpr uint32_t PAIR_TICKET = 16;  // queries per ticket
+
 template <int MODE, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB)
     search_dna_pair_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
@@ -867,9 +959,15 @@ __global__ void __launch_bounds__(TPB, MINB)
   const uint32_t gmask = 0xfu << gbase;
   uint64_t* const ring = s_q[threadIdx.x / LANES];
   const uint32_t nq32 = uint32_t(nq);
-  uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;  // next query of this group
-  uint32_t cur = NONE;                                            // query in flight
-  uint32_t sp = 1, ep = 0, left = 0, len = 0;
+  // Queries are handed out dynamically, PAIR_TICKET at a time, from a counter behind the deferred list
+  // (defer[nq + 1]): with a static stride every SM gets the same share and the kernel ends when the
+  // slowest SM does -- on B200 the SMs do not all see the same random-access throughput (the gather
+  // probe's SMs are busy between 52 % and 100 % of the time under a static split).
+  uint32_t* const ticket = defer + nq + 1;
+  uint32_t q = 0, q_end = 0;  // the group's current ticket: queries [q, q_end)
+  bool more = true;            // the counter has not run past nq yet
+  uint32_t cur = NONE;         // query in flight
+  uint32_t sp = 1, ep = 0, left = 0, len = 0, nwords = 0;
   uint32_t ubase = 0;  // word index of the query's packed symbols
   uint32_t wlim = 8;   // word index at which the ring slides by 8 words
 
@@ -880,10 +978,16 @@ __global__ void __launch_bounds__(TPB, MINB)
       if (cur != NONE && sub == 0) store_result<MODE>(out, cur, sp, ep);
       cur = NONE;
       left = 0;
-      if (q < nq32) {
-        cur = q;
-        const uint32_t G = (gridDim.x * blockDim.x) / LANES;
-        q = (q + G < q) ? NONE : q + G;
+      if (q == q_end && more) {
+        uint32_t t = 0;
+        if (sub == 0) t = atomicAdd(ticket, PAIR_TICKET);
+        t = __shfl_sync(gmask, t, gbase);
+        more = t < nq32;
+        q = more ? t : 0u;
+        q_end = more ? (nq32 - t < PAIR_TICKET ? nq32 : t + PAIR_TICKET) : 0u;
+      }
+      if (q < q_end) {
+        cur = q++;
         uint64_t ov = qoff[cur + (sub & 1)];  // lanes 0/1 fetch both ends with one request
         uint64_t o0 = __shfl_sync(gmask, ov, gbase), o1 = __shfl_sync(gmask, ov, gbase + 1);
         len = uint32_t(o1 - o0);
@@ -891,21 +995,29 @@ __global__ void __launch_bounds__(TPB, MINB)
         ep = 0;
         if (len != 0) {
           ubase = 4 * (cur + uint32_t(o0 >> 6));
-          const uint32_t nwords = (len + 15) >> 4;
+          nwords = (len + 15) >> 4;
+          // ambiguity symbols (code >= 4) are looked for once, while the query is staged, not per step;
+          // unused nibbles of the last word are 0
+          uint32_t amb = 0;
           __syncwarp(gmask);
           if (4 * sub < nwords) {
             u32x8 t = ldg256(qwords + ubase + 4 * sub);
 #pragma unroll
-            for (int j = 0; j < 4; j++) ring[4 * sub + j] = uint64_t(t.v[2 * j]) | (uint64_t(t.v[2 * j + 1]) << 32);
+            for (int j = 0; j < 4; j++) {
+              ring[4 * sub + j] = uint64_t(t.v[2 * j]) | (uint64_t(t.v[2 * j + 1]) << 32);
+              if (4 * sub + j < nwords) amb |= (t.v[2 * j] | t.v[2 * j + 1]) & 0xCCCCCCCCu;
+            }
           }
+          const bool clean = !__any_sync(gmask, amb != 0);
           __syncwarp(gmask);
           wlim = 8;
-          const uint32_t k = ix.kmer_len;
-          const uint64_t w = ring[0];
-          bool clean;
-          if (k != 0 && len >= k) {
-            clean = (w & (0xCCCCCCCCCCCCCCCCull >> (4 * (16 - k)))) == 0;  // k <= 16: inside word 0
-            if (clean) {
+          if (!clean) {  // hand the whole query to the scalar kernel
+            if (sub == 0) defer[1 + atomicAdd(defer, 1u)] = cur;
+            cur = NONE;
+          } else {
+            const uint32_t k = ix.kmer_len;
+            const uint64_t w = ring[0];
+            if (k != 0 && len >= k) {  // k <= 16: inside word 0
               uint64_t idx = 0;
 #pragma unroll 1
               for (uint32_t j = 0; j < k; j++) idx |= ((w >> (4 * j)) & 3ull) << (2 * j);
@@ -913,65 +1025,66 @@ __global__ void __launch_bounds__(TPB, MINB)
               sp = r.x;
               ep = r.y;
               left = len - k;
-            }
-          } else {
-            uint32_t c = uint32_t(w) & 15u;
-            clean = c < 4;
-            if (clean) {
+            } else {
+              uint32_t c = uint32_t(w) & 15u;
               sp = ix.c_lo[c];
               ep = ix.c_hi[c];
               left = len - 1;
             }
           }
-          if (!clean) {  // hand the whole query to the scalar kernel
-            if (sub == 0) defer[1 + atomicAdd(defer, 1u)] = cur;
-            cur = NONE;
-          }
         }
       }
     }
-    if (__all_sync(FULL, cur == NONE && q >= nq32)) break;
+    if (__all_sync(FULL, cur == NONE && q == q_end && !more)) break;
 
     bool active = left != 0 && sp <= ep;  // (a query that just ended is stored next iteration)
     const uint32_t pos = len - left;      // search-order index of the next symbol
     if (active && (pos >> 4) >= wlim) {   // long query: bring in words [wlim+8, wlim+16)
+      uint32_t amb = 0;
       __syncwarp(gmask);
       if (sub < 2) {
         u32x8 t = ldg256(qwords + ubase + wlim + 8 + 4 * sub);  // in bounds: buffer padded by 32 words
 #pragma unroll
-        for (int j = 0; j < 4; j++)
+        for (int j = 0; j < 4; j++) {
           ring[(wlim + 8 + 4 * sub + j) & 15] = uint64_t(t.v[2 * j]) | (uint64_t(t.v[2 * j + 1]) << 32);
+          if (wlim + 8 + 4 * sub + j < nwords) amb |= (t.v[2 * j] | t.v[2 * j + 1]) & 0xCCCCCCCCu;
+        }
       }
+      const bool clean = !__any_sync(gmask, amb != 0);
       __syncwarp(gmask);
       wlim += 8;
+      if (!clean) {  // ambiguity symbol further on: the scalar kernel redoes the whole query
+        if (sub == 0) defer[1 + atomicAdd(defer, 1u)] = cur;
+        cur = NONE;
+        left = 0;
+        active = false;
+      }
     }
-    const uint32_t c1 = uint32_t(ring[(pos >> 4) & 15] >> (4 * (pos & 15))) & 15u;
-    const uint32_t c2 = uint32_t(ring[((pos + 1) >> 4) & 15] >> (4 * ((pos + 1) & 15))) & 15u;
-    const bool two = left >= 2;
-    if (active && (two ? (c1 | c2) : c1) >= 4) {  // ambiguity symbol ahead: scalar kernel's job
-      if (sub == 0) defer[1 + atomicAdd(defer, 1u)] = cur;
-      cur = NONE;
-      left = 0;
-      active = false;
-    }
+    // A pair step always starts on an EVEN symbol index (an odd start takes one single-symbol step
+    // first), so both symbols are one byte of the ring: low nibble = symbol pos, high nibble = pos + 1.
+    const uint32_t qb = reinterpret_cast<const uint8_t*>(ring)[(pos >> 1) & 127];
+    const bool two = left >= 2 && (pos & 1) == 0;
     const uint32_t pa = sp - 1, pb = ep;
     uint32_t ra = 0, rb = 0, base = 0;
     if (active) {
       if (two) {
-        const uint32_t pair = 4 * c1 + c2;
-        const uint32_t ba = __umulhi(pa, 0xAAAAAAABu) >> 6, bb = __umulhi(pb, 0xAAAAAAABu) >> 6;  // / 96
-        const int na = int(pa - ba * PAIR_ROWS_PER_BLOCK) + 1 - int(32 * sub);
-        const int nb = int(pb - bb * PAIR_ROWS_PER_BLOCK) + 1 - int(32 * sub);
+        const uint32_t pair = ((qb & 3u) << 2) | (qb >> 4);
+        const uint32_t ba = __umulhi(pa, 0xAAAAAAABu) >> 6;  // / 96
+        const uint32_t la = pa - ba * PAIR_ROWS_PER_BLOCK, lb = pb - ba * PAIR_ROWS_PER_BLOCK;
         u32x8 x = ldg256(ix.pair_blocks + size_t(ba) * PAIR_BLOCK_UINT4 + 2 * sub);
         PairSlice s = pair_slice(x, sub, pair);
-        ra = __popc(s.match & low_mask(na)) + s.count;
-        if (bb != ba) {  // the interval straddles two blocks (only while it is still wide)
+        ra = __popc(s.match & low_mask(int(la) + 1 - int(32 * sub))) + s.count;
+        if (lb < PAIR_ROWS_PER_BLOCK) {
+          rb = __popc(s.match & low_mask(int(lb) + 1 - int(32 * sub))) + s.count;
+        } else {  // the interval straddles two blocks (only while it is still wide): a real branch
+          const uint32_t bb = __umulhi(pb, 0xAAAAAAABu) >> 6;
           x = ldg256(ix.pair_blocks + size_t(bb) * PAIR_BLOCK_UINT4 + 2 * sub);
           s = pair_slice(x, sub, pair);
+          rb = __popc(s.match & low_mask(int(pb - bb * PAIR_ROWS_PER_BLOCK) + 1 - int(32 * sub))) + s.count;
         }
-        rb = __popc(s.match & low_mask(nb)) + s.count;
         base = ix.c2[pair];
       } else {
+        const uint32_t c1 = (qb >> (4 * (pos & 1))) & 15u;
         const uint32_t ba = pa >> 7, bb = pb >> 7;
         LaneChunks<4> y;
         y.load(ix.blocks + size_t(ba) * DNA_BLOCK_UINT4, sub);
@@ -1021,13 +1134,15 @@ template <int MODE>
 static cudaError_t launch_search_pair(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
                                       uint64_t nq, void* d_out, uint32_t* d_defer, const SearchVariant& v,
                                       int sm_count, cudaStream_t s) {
-  if (nq >= (1ull << 32) - 1) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(d_defer, 0, 4, s);
+  if (nq >= (1ull << 32) - (1u << 24)) return cudaErrorInvalidValue;  // 32-bit ticket counter
+  cudaError_t e = cudaMemsetAsync(d_defer, 0, 4, s);                  // deferred-query count
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(d_defer + nq + 1, 0, 4, s);                     // ticket counter
   if (e != cudaSuccess) return e;
   switch (v.blocks_per_sm) {
     case 4: return launch_search_pair_b<MODE, 4>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s);
+    case 0:  // full residency (8 x 256 threads, 32 registers) measured best once the hand-out is dynamic
     case 8: return launch_search_pair_b<MODE, 8>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s);
-    case 0:
     case 6: return launch_search_pair_b<MODE, 6>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s);
     default: return launch_search_pair_b<MODE, 4>(ix, d_qwords, d_qoff, nq, d_out, d_defer, v.blocks_per_sm, sm_count, s);
   }
@@ -1055,7 +1170,8 @@ __device__ __forceinline__ AminoSlice amino_slice(const u32x8& x, uint32_t sub, 
 template <int MODE, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB)
     search_amino_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
-                        const uint64_t* __restrict__ qoff, uint64_t nq, void* __restrict__ out) {
+                        const uint64_t* __restrict__ qoff, uint64_t nq, void* __restrict__ out,
+                        uint32_t* __restrict__ ticket) {
   constexpr int LANES = 4;
   constexpr uint32_t NONE = 0xffffffffu, FULL = 0xffffffffu;
   __shared__ uint64_t s_q[TPB / LANES][16];  // 128 symbols
@@ -1064,7 +1180,8 @@ __global__ void __launch_bounds__(TPB, MINB)
   const uint32_t gmask = 0xfu << gbase;
   uint64_t* const ring = s_q[threadIdx.x / LANES];
   const uint32_t nq32 = uint32_t(nq);
-  uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  uint32_t q = 0, q_end = 0;  // dynamic hand-out of PAIR_TICKET queries at a time (see the pair kernel)
+  bool more = true;
   uint32_t cur = NONE;
   uint32_t sp = 1, ep = 0, left = 0, len = 0;
   uint32_t ubase = 0, wlim = 8;
@@ -1074,10 +1191,16 @@ __global__ void __launch_bounds__(TPB, MINB)
       if (cur != NONE && sub == 0) store_result<MODE>(out, cur, sp, ep);
       cur = NONE;
       left = 0;
-      if (q < nq32) {
-        cur = q;
-        const uint32_t G = (gridDim.x * blockDim.x) / LANES;
-        q = (q + G < q) ? NONE : q + G;
+      if (q == q_end && more) {
+        uint32_t t = 0;
+        if (sub == 0) t = atomicAdd(ticket, PAIR_TICKET);
+        t = __shfl_sync(gmask, t, gbase);
+        more = t < nq32;
+        q = more ? t : 0u;
+        q_end = more ? (nq32 - t < PAIR_TICKET ? nq32 : t + PAIR_TICKET) : 0u;
+      }
+      if (q < q_end) {
+        cur = q++;
         uint64_t ov = qoff[cur + (sub & 1)];
         uint64_t o0 = __shfl_sync(gmask, ov, gbase), o1 = __shfl_sync(gmask, ov, gbase + 1);
         len = uint32_t(o1 - o0);
@@ -1126,7 +1249,7 @@ __global__ void __launch_bounds__(TPB, MINB)
         }
       }
     }
-    if (__all_sync(FULL, cur == NONE && q >= nq32)) break;
+    if (__all_sync(FULL, cur == NONE && q == q_end && !more)) break;
 
     bool active = left != 0 && sp <= ep;
     const uint32_t pos = len - left;
@@ -1176,20 +1299,22 @@ __global__ void __launch_bounds__(TPB, MINB)
 
 template <int MODE>
 static cudaError_t launch_search_amino(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
-                                       uint64_t nq, void* d_out, const SearchVariant& v, int sm_count,
-                                       cudaStream_t s) {
-  if (nq >= (1ull << 32) - 1) return cudaErrorInvalidValue;
+                                       uint64_t nq, void* d_out, uint32_t* d_ticket, const SearchVariant& v,
+                                       int sm_count, cudaStream_t s) {
+  if (nq >= (1ull << 32) - (1u << 24)) return cudaErrorInvalidValue;  // 32-bit ticket counter
   constexpr int TPB = 256;
   auto kern = search_amino_kernel<MODE, TPB, 6>;
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, 0);
+  cudaError_t e = cudaMemsetAsync(d_ticket, 0, 4, s);
+  if (e != cudaSuccess) return e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, 0);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   if (v.blocks_per_sm > 0 && v.blocks_per_sm < per_sm) per_sm = v.blocks_per_sm;
   uint64_t max_blocks = uint64_t(sm_count) * uint64_t(per_sm);
   uint64_t need_blocks = (nq * 4 + TPB - 1) / TPB;
   unsigned grid = unsigned(std::max<uint64_t>(1, std::min(max_blocks, need_blocks)));
-  e = launch_with_table_window(kern, grid, TPB, s, ix, ix, d_qwords, d_qoff, nq, d_out);
+  e = launch_with_table_window(kern, grid, TPB, s, ix, ix, d_qwords, d_qoff, nq, d_out, d_ticket);
   COUNT_LAUNCH();
   return e;
 }
@@ -1208,7 +1333,7 @@ static cudaError_t launch_search_mode(const IndexView& ix, const uint64_t* d_qwo
     }
   }
   if (ix.alphabet == 1 && v.lanes != -1)
-    return launch_search_amino<MODE>(ix, d_qwords, d_qoff, nq, d_out, v, sm_count, s);
+    return launch_search_amino<MODE>(ix, d_qwords, d_qoff, nq, d_out, d_defer, v, sm_count, s);
   // lanes == -1: the scalar kernels, kept for cross-checking
   int per_sm = 8;
   uint64_t need_blocks = (nq + 255) / 256;
@@ -1824,11 +1949,11 @@ static cudaError_t gather_tma_run(const char* buf, uint64_t n_granules, uint64_t
 
 template <int GRANULE, int LANES, int UNROLL = 4>
 static cudaError_t gather_run(const char* buf, uint64_t n_granules, uint64_t n_reads, int iters,
-                              uint32_t* sink, double* ms_out) {
+                              uint32_t* sink, double* ms_out, int blocks_per_sm = 8) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  unsigned grid = unsigned(sms) * 8;
+  unsigned grid = unsigned(sms) * unsigned(blocks_per_sm);
   uint64_t groups = uint64_t(grid) * 256 / LANES;
   uint64_t per_group = ((n_reads + groups - 1) / groups + UNROLL - 1) / UNROLL * UNROLL;
   cudaEvent_t e0, e1;
@@ -1877,6 +2002,23 @@ cudaError_t run_random_gather(uint64_t footprint_bytes, uint32_t granule, uint32
   // dependent-chain shape of the search kernels) instead of four
   if (granule == 128 && lanes == 104) e = gather_run<128, 4, 1>(buf, n_granules, n_reads, iters, sink, &ms);
   if (granule == 128 && lanes == 102) e = gather_run<128, 4, 2>(buf, n_granules, n_reads, iters, sink, &ms);
+  // lanes = 1000 + 10 * blocks_per_sm + unroll: 128-B / 4-lane probe at reduced residency (256-thread blocks)
+  if (granule == 128 && lanes >= 1000 && lanes < 2000) {
+    int bps = int(lanes - 1000) / 10, un = int(lanes - 1000) % 10;
+    if (un == 1) e = gather_run<128, 4, 1>(buf, n_granules, n_reads, iters, sink, &ms, bps);
+    if (un == 2) e = gather_run<128, 4, 2>(buf, n_granules, n_reads, iters, sink, &ms, bps);
+    if (un == 4) e = gather_run<128, 4, 4>(buf, n_granules, n_reads, iters, sink, &ms, bps);
+    if (un == 8) e = gather_run<128, 4, 8>(buf, n_granules, n_reads, iters, sink, &ms, bps);
+  }
+  // lanes = 3000 + 10 * waves + unroll: full residency, `waves` x as many blocks as fit at once, so the
+  // hardware block scheduler balances the SMs dynamically (a static split ends with the slowest SM)
+  if (granule == 128 && lanes >= 3000 && lanes < 4000) {
+    int waves = int(lanes - 3000) / 10, un = int(lanes - 3000) % 10;
+    if (un == 1) e = gather_run<128, 4, 1>(buf, n_granules, n_reads, iters, sink, &ms, 8 * waves);
+    if (un == 2) e = gather_run<128, 4, 2>(buf, n_granules, n_reads, iters, sink, &ms, 8 * waves);
+    if (un == 4) e = gather_run<128, 4, 4>(buf, n_granules, n_reads, iters, sink, &ms, 8 * waves);
+    if (un == 8) e = gather_run<128, 4, 8>(buf, n_granules, n_reads, iters, sink, &ms, 8 * waves);
+  }
   // lanes = 201 / 202: one thread per read through cp.async.bulk + mbarrier, 1 / 2 reads in flight per thread
   if (granule == 128 && lanes == 201) e = gather_tma_run<1>(buf, n_granules, n_reads, iters, sink, &ms);
   if (granule == 128 && lanes == 202) e = gather_tma_run<2>(buf, n_granules, n_reads, iters, sink, &ms);

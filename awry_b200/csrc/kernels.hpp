@@ -51,7 +51,12 @@ cudaError_t build_full_sa(const IndexView& ix, uint32_t* d_full, int sm_count, c
 
 cudaError_t launch_pack(int alphabet, const uint8_t* d_qbytes, const uint64_t* d_qoff, uint64_t nq,
                         uint64_t* d_qwords, unsigned long long* d_first_bad, cudaStream_t s);
-// d_defer: nq + 1 u32 of scratch (list of queries the cooperative kernel hands to the scalar one)
+// nucleotide queries packed to 2 bits on the host (hostpack.hpp): crumbs of the chunk's bytes from
+// absolute query offset `base` on, plus the exception list for bytes outside ACGT
+cudaError_t launch_pack2(const uint32_t* d_crumbs, uint64_t base, const uint64_t* d_qoff, uint64_t nq, uint64_t* d_qwords,
+                         const uint64_t* d_exc, uint64_t n_exc, unsigned long long* d_first_bad, cudaStream_t s);
+// d_defer: nq + 2 u32 of scratch (count + list of queries the cooperative kernel hands to the scalar
+// one, then the ticket counter of the dynamic query hand-out)
 cudaError_t launch_search(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
                           uint64_t nq, SearchOut mode, void* d_out, uint32_t* d_defer,
                           const SearchVariant& v, int sm_count, cudaStream_t s);

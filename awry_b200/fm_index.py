@@ -22,7 +22,8 @@ _LIB = None
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libawry_b200.so")
+    # AWRY_B200_LIB: another build of the same library (kernel experiments); default = the in-tree one
+    return os.environ.get("AWRY_B200_LIB") or os.path.join(_HERE, "libawry_b200.so")
 
 
 class AwryError(RuntimeError):
@@ -122,7 +123,8 @@ EXPORTS = ["awry_index_build", "awry_build_index_file", "awry_build_parts", "awr
            "awry_locate_reads_file", "awry_buffer_free", "awry_initial_range", "awry_update_range",
            "awry_backstep", "awry_count_device", "awry_locate_device", "awry_device_free",
            "awry_device_check", "awry_profile_enable", "awry_profile_reset", "awry_profile_get",
-           "awry_bench_random_gather", "awry_set_search_variant", "awry_set_locate_variant", "awry_last_error", "awry_version"]
+           "awry_bench_random_gather", "awry_set_search_variant", "awry_set_locate_variant", "awry_set_host_pack",
+           "awry_host_pack_dna", "awry_last_error", "awry_version"]
 
 
 def native():
@@ -179,6 +181,8 @@ def native():
     L.awry_buffer_free.restype = None
     L.awry_set_search_variant.argtypes = [i32, i32, i32]
     L.awry_set_locate_variant.argtypes = [i32]
+    L.awry_set_host_pack.argtypes = [i32]
+    L.awry_host_pack_dna.argtypes = [vp, u64, vp, vp, u64, C.POINTER(u64)]
     _LIB = L
     return L
 
@@ -523,3 +527,18 @@ def set_search_variant(lanes: int = 0, tpb: int = 0, blocks_per_sm: int = 0):
 def set_locate_variant(variant: int = 0):
     """0 = gather from the unsampled suffix array when the index holds one (default); 1 = always LF-walk."""
     _check(native().awry_set_locate_variant(variant))
+
+
+def set_host_pack(mode: int = -1):
+    """-1 = auto, 0 = send ASCII queries over PCIe, 1 = pack nucleotide queries to 2 bits on the host first."""
+    _check(native().awry_set_host_pack(mode))
+
+
+def host_pack_dna(src: np.ndarray):
+    """the host packer alone (tests): -> (crumb bytes uint8[ceil(n/4)], exceptions uint64[] = (i << 8) | byte)"""
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    dst = np.zeros((len(src) + 3) // 4 + 64, dtype=np.uint8)
+    exc = np.zeros(len(src) + 1, dtype=np.uint64)
+    n = C.c_uint64()
+    _check(native().awry_host_pack_dna(src.ctypes.data, len(src), dst.ctypes.data, exc.ctypes.data, len(exc), C.byref(n)))
+    return dst[: (len(src) + 3) // 4], exc[: n.value]

@@ -290,7 +290,9 @@ def main():
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         e2e = {"value": world * nq * a.steps / float(t_e.item()), "unit": "reads/s",
                "h2d_bytes_per_step": p2["h2d_bytes"] // a.steps, "d2h_bytes_per_step": p2["d2h_bytes"] // a.steps,
-               "ms_per_step": float(t_e.item()) / a.steps * 1e3, "host_buffers": "pinned"}
+               "ms_per_step": float(t_e.item()) / a.steps * 1e3, "host_buffers": "pinned",
+               "host_pack": ("bases packed to 2 bits by the host thread pool before the copy"
+                             if p2["h2d_bytes"] // a.steps < nq * L else "ASCII bytes copied as they are")}
         assert np.array_equal(out, d_cnt.cpu().numpy().view(np.uint64)), "e2e and device-resident counts differ"
 
     # ---- secondary metric (BASELINE cfg3): parallel_locate of 1 M x 50-bp queries, same index
@@ -395,7 +397,9 @@ def main():
     gather = None
     if rank == 0:
         try:   # the "random-access HBM roofline" of the north star: independent random 128-B reads
-            g_reads, g_gbs = f.bench_random_gather(local_rank, 4 << 30, 128, 4, 400_000_000, 2)
+            # 4 lanes x LDG.256 per read, 4 in flight per lane group, 16 waves of blocks so the hardware
+            # balances the SMs (a static split stops at 37.8 G reads/s: it ends with the slowest SM)
+            g_reads, g_gbs = f.bench_random_gather(local_rank, 4 << 30, 128, 3164, 400_000_000, 2)
             accesses = nq * (((L - a.kmer) + 1) // 2 + 1)          # pair steps (+ odd tail) + seed lookup
             gather = {"granule_bytes": 128, "reads_per_s": g_reads, "gb_per_s": g_gbs,
                       "kernel_block_reads_per_s": accesses / (search_ms * 1e-3),

@@ -267,6 +267,18 @@ int awry_set_search_variant(int lanes_per_query, int threads_per_block, int bloc
  * present (default), 1 = always LF-walk to the sampled rows (the memory-lean path). */
 int awry_set_locate_variant(int variant);
 
+/* Host-side query packing (nucleotide): the *_batch calls turn ASCII bases into 2-bit codes on the host
+ * cores (AVX2/BMI2 or AVX-512BW, a process-wide thread pool: AWRY_B200_HOST_THREADS) while earlier
+ * chunks are in flight, so a quarter of the bytes cross PCIe; bytes outside ACGT travel as a side list.
+ * mode -1 = auto (on when the CPU supports it and the pool has >= 4 threads; AWRY_B200_HOST_PACK=0/1
+ * overrides), 0 = always send ASCII, 1 = always pack. */
+int awry_set_host_pack(int mode);
+/* The packer itself, exposed for tests: dst gets ceil(n/4) bytes, crumb i = (src[i] >> 1) & 3 at bits
+ * 2*(i%4) of dst[i/4]; exceptions (up to exc_cap) receive (i << 8) | src[i] for bytes outside ACGTacgt;
+ * *n_exc is their total number. */
+int awry_host_pack_dna(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t *exceptions,
+                       uint64_t exc_cap, uint64_t *n_exc);
+
 const char *awry_last_error(void);
 const char *awry_version(void);
 

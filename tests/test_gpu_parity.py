@@ -41,6 +41,16 @@ def dna_or(po, dna):
     return oracle_from_parts(po, dna)
 
 
+@pytest.fixture(autouse=True, params=[1, 0], ids=["hostpack", "ascii"])
+def host_pack_mode(request):
+    """every test of this module runs with nucleotide queries packed to 2 bits on the host (the default on
+    a many-core host) and with the ASCII bytes sent as they are"""
+    from awry_b200 import fm_index as f
+    f.set_host_pack(request.param)
+    yield request.param
+    f.set_host_pack(-1)
+
+
 @pytest.fixture(params=[0, 1], ids=["unsampled_sa", "lf_walk"])
 def locate_variant(request):
     """locate pass 2 both ways: gather from the unsampled suffix array (default when it fits) and the
@@ -200,6 +210,39 @@ def test_invalid_queries_are_errors(dna_dev):
         with pytest.raises(AwryError):
             dna_dev.locate_packed(qb, qo)
     assert dna_dev.count_string("ACGT") >= 0   # index still usable afterwards
+
+
+def test_invalid_and_ambiguous_queries_in_large_batches(fx, dna, dna_dev, dna_or):
+    """batches large enough for the host-packed path: sentinels and empty queries are still reported by
+    index, N / IUPAC / lower-case bytes travel as exceptions (few) or force the ASCII path (many)"""
+    from awry_b200 import AwryError, fm_index as f
+    qb, qo, _ = fx.gen_substring_queries(dna.text, 3000, 50, seed=21)
+    qs = [bytes(qb[50 * i:50 * i + 50]) for i in range(3000)]
+    for i in range(0, 3000, 97):                      # ~1 % ambiguous bytes: the exception list
+        q = bytearray(qs[i])
+        q[i % 50] = ord("N")
+        q[(i * 7) % 50] = ord("r")
+        qs[i] = bytes(q)
+    qs[5] = qs[5].lower()
+    qs[6] = qs[6].replace(b"T", b"U")
+    b, o = f.pack_queries(qs)
+    want, _ = dna_or.count_batch(b, o)
+    assert np.array_equal(dna_dev.count_packed(b, o), want)
+    woff, whits, _ = dna_or.locate_batch(b, o)
+    off, hits = dna_dev.locate_packed(b, o)
+    assert np.array_equal(off, woff) and np.array_equal(hits, whits)
+    many_n = [q[:10] + b"NNNNNNNN" + q[18:] for q in qs]   # 16 % ambiguous: the chunk goes up as ASCII
+    b2, o2 = f.pack_queries(many_n)
+    want2, _ = dna_or.count_batch(b2, o2)
+    assert np.array_equal(dna_dev.count_packed(b2, o2), want2)
+    for bad_at, bad in ((1234, qs[1234][:20] + b"$" + qs[1234][21:]), (2999, b""), (0, b"#" + qs[0][1:])):
+        bad_qs = list(qs)
+        bad_qs[bad_at] = bad
+        b3, o3 = f.pack_queries(bad_qs)
+        with pytest.raises(AwryError) as e:
+            dna_dev.count_packed(b3, o3)
+        assert e.value.code == -5 and f"query {bad_at} " in str(e.value)
+    assert np.array_equal(dna_dev.count_packed(b, o), want)
 
 
 def test_single_step_api(dna, dna_dev, dna_or):

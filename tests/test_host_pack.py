@@ -1,0 +1,42 @@
+"""Host-side 2-bit query packer (awry_b200/csrc/hostpack.cpp): every SIMD level against a numpy
+restatement.  Pure CPU; the device half (pack2_kernel) is covered by the GPU parity tests, which run the
+batch entry points with host packing both on and off."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CHECK = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+from awry_b200 import fm_index as f
+rng = np.random.default_rng(7)
+for n in (0, 1, 3, 4, 63, 64, 65, 127, 1000, 4097, 300_001, 3_000_000):
+    src = np.frombuffer(b"ACGTacgt", dtype=np.uint8)[rng.integers(0, 8, n)].copy()
+    k = max(1, n // 50)
+    if n:
+        pos = rng.integers(0, n, k)
+        src[pos] = np.frombuffer(b"NnRYKM$#U-*X\n", dtype=np.uint8)[rng.integers(0, 13, k)]
+    got, exc = f.host_pack_dna(src)
+    up = src & 0xDF
+    bad = ~((up == 65) | (up == 67) | (up == 71) | (up == 84))
+    want_exc = (np.nonzero(bad)[0].astype(np.uint64) << np.uint64(8)) | src[bad].astype(np.uint64)
+    assert np.array_equal(exc, want_exc), (n, len(exc), len(want_exc))
+    crumbs = ((src >> 1) & 3).astype(np.uint8)
+    pad = np.zeros((-n) %% 4, dtype=np.uint8)
+    c4 = np.concatenate([crumbs, pad]).reshape(-1, 4)
+    want = (c4[:, 0] | (c4[:, 1] << 2) | (c4[:, 2] << 4) | (c4[:, 3] << 6)).astype(np.uint8)
+    assert np.array_equal(got, want), n
+print("ok")
+""" % ROOT
+
+
+@pytest.mark.parametrize("simd", ["0", "1", "2"])
+def test_host_packer_matches_numpy(simd):
+    env = dict(os.environ, AWRY_B200_HOST_SIMD=simd, AWRY_B200_HOST_THREADS="5")
+    out = subprocess.run([sys.executable, "-c", CHECK], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr[-2000:]
