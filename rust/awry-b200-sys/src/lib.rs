@@ -91,6 +91,11 @@ extern "C" {
     pub fn awry_locate_batch(index: *const awry_index, qbytes: *const u8, qoff: *const u64, nq: u64, flags: u32,
                              hit_off: *mut u64, hits: *mut *mut awry_hit, n_hits: *mut u64) -> c_int;
     pub fn awry_hits_free(hits: *mut awry_hit);
+    pub fn awry_count_reads_file(index: *const awry_index, path: *const c_char, counts: *mut *mut u64, n_reads: *mut u64) -> c_int;
+    pub fn awry_locate_reads_file(index: *const awry_index, path: *const c_char, flags: u32, hit_off: *mut *mut u64,
+                                  hits: *mut *mut awry_hit, n_reads: *mut u64, n_hits: *mut u64) -> c_int;
+    pub fn awry_buffer_free(p: *mut c_void);
+    pub fn awry_set_host_pack(mode: c_int) -> c_int;
     pub fn awry_locate_batch_into(index: *const awry_index, qbytes: *const u8, qoff: *const u64, nq: u64, flags: u32,
                                   hit_off: *mut u64, hits: *mut awry_hit, capacity: u64, n_hits: *mut u64) -> c_int;
     pub fn awry_initial_range(index: *const awry_index, ascii_symbol: u8, out: *mut awry_range) -> c_int;

@@ -1,6 +1,7 @@
 //! `awry_b200::FmIndex`: the reference's query-side API (awry 0.3.1, src/fm_index.rs) on top of
 //! the CUDA library.  Signatures are the reference's:
 //!   load(&Path) -> Result<FmIndex, io::Error>                     fm_index_file.rs:132
+//!   new(&FmBuildArgs) -> Result<FmIndex, _>  (GPU construction)    fm_index.rs:142
 //!   count_string(&self, &str) -> u64                               fm_index.rs:499
 //!   locate_string(&self, &str) -> Vec<LocalizedSequencePosition>   fm_index.rs:516
 //!   parallel_count(&self, impl ParallelIterator<Item=&str>) -> Vec<u64>                       fm_index.rs:455
@@ -45,6 +46,17 @@ impl LocalizedSequencePosition {
     pub fn local_position(&self) -> usize { self.local_position }
 }
 
+/// awry::fm_index::FmBuildArgs (fm_index.rs:78-96), field for field
+pub struct FmBuildArgs {
+    pub input_file_src: std::path::PathBuf,
+    pub suffix_array_output_src: Option<std::path::PathBuf>,
+    pub suffix_array_compression_ratio: Option<u64>,
+    pub lookup_table_kmer_len: Option<u8>,
+    pub alphabet: SymbolAlphabet,
+    pub max_query_len: Option<usize>,
+    pub remove_intermediate_suffix_array_file: bool,
+}
+
 pub struct FmIndex {
     handle: *mut sys::awry_index,
     info: sys::awry_info,
@@ -75,6 +87,57 @@ impl FmIndex {
         let mut info = unsafe { std::mem::zeroed::<sys::awry_info>() };
         unsafe { sys::awry_index_info(handle, &mut info) };
         Ok(FmIndex { handle, info })
+    }
+
+    /// FmIndex::new (fm_index.rs:142-268) on the GPU: FASTA/FASTQ -> searchable index (awry_index_build).
+    /// `suffix_array_output_src`, `max_query_len` and `remove_intermediate_suffix_array_file` are libsufr
+    /// knobs with no meaning here and are ignored.
+    pub fn new(args: &FmBuildArgs) -> Result<FmIndex, io::Error> {
+        Self::build(args, None)
+    }
+
+    /// `new` followed by `save` (fm_index_file.rs:42) in one call: also writes the `.awry` v1 file.
+    pub fn new_and_save(args: &FmBuildArgs, fm_file_src: &Path) -> Result<FmIndex, io::Error> {
+        Self::build(args, Some(fm_file_src))
+    }
+
+    fn build(args: &FmBuildArgs, save_to: Option<&Path>) -> Result<FmIndex, io::Error> {
+        let cstr = |p: &Path| CString::new(p.to_string_lossy().as_bytes()).map_err(|e| io::Error::new(io::ErrorKind::InvalidInput, e));
+        let input = cstr(&args.input_file_src)?;
+        let output = match save_to { Some(p) => Some(cstr(p)?), None => None };
+        let devices: Vec<i32> = std::env::var("AWRY_B200_DEVICES").ok()
+            .map(|s| s.split(',').filter_map(|x| x.trim().parse().ok()).collect()).unwrap_or_default();
+        let a = sys::awry_build_args {
+            input_file_src: input.as_ptr(),
+            output_file_src: output.as_ref().map_or(std::ptr::null(), |c| c.as_ptr()),
+            alphabet: if args.alphabet == SymbolAlphabet::Nucleotide { 0 } else { 1 },
+            lookup_table_kmer_len: args.lookup_table_kmer_len.unwrap_or(0) as u32,
+            suffix_array_compression_ratio: args.suffix_array_compression_ratio.unwrap_or(0),
+            device: devices.first().copied().unwrap_or(0),
+        };
+        let mut handle = std::ptr::null_mut();
+        let rc = unsafe {
+            sys::awry_index_build(&a, if devices.is_empty() { std::ptr::null() } else { devices.as_ptr() },
+                                  devices.len() as i32, &mut handle)
+        };
+        if rc != sys::AWRY_OK {
+            let kind = if rc == sys::AWRY_ERR_IO { io::ErrorKind::NotFound } else { io::ErrorKind::InvalidData };
+            return Err(io::Error::new(kind, last_error()));
+        }
+        let mut info = unsafe { std::mem::zeroed::<sys::awry_info>() };
+        unsafe { sys::awry_index_info(handle, &mut info) };
+        Ok(FmIndex { handle, info })
+    }
+
+    /// parallel_count over every record of a FASTQ / FASTA file, parsed on the device (awry_count_reads_file).
+    pub fn parallel_count_file(&self, reads: &Path) -> Result<Vec<u64>, io::Error> {
+        let path = CString::new(reads.to_string_lossy().as_bytes()).map_err(|e| io::Error::new(io::ErrorKind::InvalidInput, e))?;
+        let (mut ptr, mut n) = (std::ptr::null_mut::<u64>(), 0u64);
+        let rc = unsafe { sys::awry_count_reads_file(self.handle, path.as_ptr(), &mut ptr, &mut n) };
+        if rc != sys::AWRY_OK { return Err(io::Error::new(io::ErrorKind::InvalidData, last_error())); }
+        let out = unsafe { std::slice::from_raw_parts(ptr, n as usize) }.to_vec();
+        unsafe { sys::awry_buffer_free(ptr as *mut std::ffi::c_void) };
+        Ok(out)
     }
 
     pub fn alphabet(&self) -> SymbolAlphabet { if self.info.alphabet == 0 { SymbolAlphabet::Nucleotide } else { SymbolAlphabet::Amino } }

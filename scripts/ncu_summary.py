@@ -68,7 +68,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio"]
 
 
-def full(rep, dst_prefix, bench_json=None):
+def full(rep, dst_prefix, bench_json=None, kernel_filter=None, traffic_json="profiles/search_kernel_traffic.json"):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
@@ -88,17 +88,25 @@ def full(rep, dst_prefix, bench_json=None):
     srows = list(csv.reader(io.StringIO(src)))
     starts = [i for i, r in enumerate(srows) if r and r[0] == "Address"]
     hot = []
+    # the launch to summarise: the first one matching the filter that carries DRAM counters
+    sel = 0
+    if kernel_filter:
+        for i, d in enumerate(out):
+            if kernel_filter in d["kernel"] and isinstance(d.get("dram__bytes_read.sum"), float) and d["dram__bytes_read.sum"] == d["dram__bytes_read.sum"]:
+                sel = i
+                break
     if starts:
-        h = srows[starts[0]]
-        end = starts[1] - 1 if len(starts) > 1 else len(srows)
-        body = [r for r in srows[starts[0] + 1:end] if len(r) > h.index("Instructions Executed")]
+        sel_s = min(sel, len(starts) - 1)
+        h = srows[starts[sel_s]]
+        end = starts[sel_s + 1] - 1 if len(starts) > sel_s + 1 else len(srows)
+        body = [r for r in srows[starts[sel_s] + 1:end] if len(r) > h.index("Instructions Executed")]
         iS, iE, iW = h.index("Source"), h.index("Instructions Executed"), h.index("Warp Stall Sampling (All Samples)")
         tot_samples = sum(int(r[iW]) for r in body if r[iW].isdigit())
         tot_inst = sum(int(r[iE]) for r in body if r[iE].isdigit())
         top = sorted(body, key=lambda r: -int(r[iW]) if r[iW].isdigit() else 0)[:12]
         hot = [{"sass": r[iS].strip(), "stall_samples": int(r[iW]), "share": int(r[iW]) / max(1, tot_samples),
                 "executed": int(r[iE])} for r in top]
-    first = out[0] if out else {}
+    first = out[sel] if out else {}
     traffic = {"kernel": first.get("kernel"),
                "dram_bytes_per_launch": first.get("dram__bytes_read.sum", 0) * (1e9 if first.get("dram__bytes_read.sum [unit]") == "Gbyte" else 1)
                + first.get("dram__bytes_write.sum", 0) * (1e6 if first.get("dram__bytes_write.sum [unit]") == "Mbyte" else 1e9 if first.get("dram__bytes_write.sum [unit]") == "Gbyte" else 1),
@@ -118,12 +126,16 @@ def full(rep, dst_prefix, bench_json=None):
         f.write("\n## instructions with the most warp-stall samples\n\n| share | samples | executed | SASS |\n|---:|---:|---:|---|\n")
         for h_ in hot:
             f.write(f"| {100*h_['share']:.1f}% | {h_['stall_samples']} | {h_['executed']} | `{h_['sass']}` |\n")
-    json.dump(traffic, open("profiles/search_kernel_traffic.json", "w"), indent=1)
-    print("wrote", dst_prefix + ".json/.md and profiles/search_kernel_traffic.json")
+    if traffic_json:
+        json.dump(traffic, open(traffic_json, "w"), indent=1)
+    print("wrote", dst_prefix + ".json/.md", traffic_json or "")
 
 
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
     else:
-        full(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
+        # full <rep> <dst_prefix> [bench.json|-] [kernel-name filter] [traffic.json|-]
+        a = sys.argv
+        full(a[2], a[3], a[4] if len(a) > 4 and a[4] != "-" else None, a[5] if len(a) > 5 else None,
+             (a[6] if a[6] != "-" else None) if len(a) > 6 else "profiles/search_kernel_traffic.json")
