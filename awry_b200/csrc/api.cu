@@ -8,6 +8,7 @@
 //   parallel_count / parallel_locate (rayon map)       fm_index.rs:455-487
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cerrno>
 #include <cstdarg>
 #include <cstdio>
@@ -164,6 +165,8 @@ struct Workspace {
   uint64_t* h_exc = nullptr;  // host-packed chunks: exception list (bytes outside ACGT)
   size_t h_exc_cap = 0;
   std::vector<uint64_t> exc_tmp;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;  // timing of a raw chunk's H2D copy (PackBalance)
+  uint64_t link_probe_bytes = 0;
   // device
   uint8_t* d_qbytes = nullptr;
   size_t d_qbytes_cap = 0;
@@ -257,6 +260,8 @@ struct Workspace {
     cudaFree(d_temp);
     cudaFree(d_flag);
     rs.release();
+    if (ev_a) cudaEventDestroy(ev_a);
+    if (ev_b) cudaEventDestroy(ev_b);
     if (done) cudaEventDestroy(done);
     if (st) cudaStreamDestroy(st);
   }
@@ -764,6 +769,50 @@ bool host_pack_enabled() {
   return on;
 }
 
+// Pack on the host or send ASCII?  Packing wins when the host cores pack faster than the PCIe link moves
+// bytes (16 threads: 84 GB/s vs 52 GB/s for one GPU) and loses when a process has few cores and shares
+// the host's uplinks (4 threads per GPU on an 8-GPU box: measured 690 M reads/s packed vs 1095 M raw).
+// Both rates are MEASURED and smoothed across calls: the host clock around the packer (H), CUDA events
+// around the copy of a raw first chunk, when nothing else is in flight (P); a call packs iff H > 1.15 P.
+// Mixing packed and raw chunks inside one call was measured and is worse than either: a 128-MiB raw copy
+// holds the copy engine for 2.6 ms and starves the search kernel (profiles/r01_s19_e2e_pack_share.log).
+// AWRY_B200_PACK_SHARE=<0..1> pins the packed share of the bytes instead (experiments).
+struct PackBalance {
+  std::mutex mu;
+  double host_rate = 0, link_rate = 0;  // bytes/s, 0 = not measured yet
+  double fixed_share = -1;
+  uint64_t calls = 0;
+  PackBalance() {
+    if (const char* e = getenv("AWRY_B200_PACK_SHARE")) fixed_share = std::min(1.0, std::max(0.0, atof(e)));
+  }
+  void note_host(double bytes, double seconds) {
+    if (seconds <= 0 || bytes < (8 << 20)) return;
+    std::lock_guard<std::mutex> lk(mu);
+    double r = bytes / seconds;
+    host_rate = host_rate > 0 ? 0.7 * host_rate + 0.3 * r : r;
+  }
+  void note_link(double bytes, double seconds) {
+    if (seconds <= 0 || bytes < (8 << 20)) return;
+    std::lock_guard<std::mutex> lk(mu);
+    double r = bytes / seconds;
+    link_rate = link_rate > 0 ? 0.7 * link_rate + 0.3 * r : r;
+  }
+  // per call: the packed share of the bytes and whether chunk 0 / chunk 1 serve as probes
+  struct Plan {
+    double share;
+    bool probe_link, probe_host;
+  };
+  Plan plan() {
+    std::lock_guard<std::mutex> lk(mu);
+    if (fixed_share >= 0) return Plan{fixed_share, false, false};
+    const bool refresh = calls++ % 32 == 0;
+    if (host_rate <= 0 || link_rate <= 0) return Plan{1.0, true, true};
+    const bool pack = host_rate > 1.15 * link_rate;
+    return Plan{pack ? 1.0 : 0.0, refresh && pack, refresh && !pack};
+  }
+};
+PackBalance g_balance;
+
 void validate_offsets(const uint64_t* qoff, uint64_t nq) {
   // cheap sanity check on the ends; per-query monotonicity is checked on the device (prepass)
   if (nq && qoff[nq] < qoff[0]) fail(AWRY_ERR_INVALID_ARG, "query offsets are not monotone");
@@ -771,8 +820,10 @@ void validate_offsets(const uint64_t* qoff, uint64_t nq) {
 
 // Uploads one chunk of queries and runs prepass + search on ws->st.  The search result lands
 // in ws->d_out in the requested mode.
+// `may_pack`: the caller's say on host packing for this chunk (see raw_chunk_period)
 void enqueue_search(const awry_index* ix, Replica& r, Workspace* ws, const uint8_t* qbytes,
-                    const uint64_t* qoff, const Chunk& c, SearchOut mode, bool src_pinned) {
+                    const uint64_t* qoff, const Chunk& c, SearchOut mode, bool src_pinned, bool may_pack = true,
+                    bool probe_link = false) {
   const uint64_t nq = c.q1 - c.q0, nbytes = c.b1 - c.b0;
   const size_t out_elem = mode == OUT_COUNT_U64 ? 8 : mode == OUT_RANGE_U64 ? 16 : 8;
   Workspace::grow_dev(ws->d_qbytes, ws->d_qbytes_cap, size_t(nbytes) + 16);
@@ -786,9 +837,12 @@ void enqueue_search(const awry_index* ix, Replica& r, Workspace* ws, const uint8
   // the PCIe bytes; works the same for pageable and pinned caller memory).  Chunks with many bytes
   // outside ACGT go up as ASCII.
   bool packed = false;
-  if (ix->alphabet == AWRY_NUCLEOTIDE && host_pack_enabled() && nbytes >= 4096) {
+  ws->link_probe_bytes = 0;
+  if (may_pack && ix->alphabet == AWRY_NUCLEOTIDE && host_pack_enabled() && nbytes >= 4096) {
     Workspace::grow_host(ws->h_qbytes, ws->h_qbytes_cap, size_t(nbytes) / 4 + 64);
+    auto t0 = std::chrono::steady_clock::now();
     packed = host_pack_dna(src_b, size_t(nbytes), ws->h_qbytes, ws->exc_tmp, 64);
+    if (packed) g_balance.note_host(double(nbytes), std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
   }
   if (packed) {
     const size_t n_exc = ws->exc_tmp.size();
@@ -822,7 +876,19 @@ void enqueue_search(const awry_index* ix, Replica& r, Workspace* ws, const uint8
       src_b = ws->h_qbytes;
       src_o = ws->h_qoff;
     }
+    const bool probe = probe_link && src_pinned && nbytes >= (8u << 20);
+    if (probe) {
+      if (!ws->ev_a) {
+        CU(cudaEventCreate(&ws->ev_a));
+        CU(cudaEventCreate(&ws->ev_b));
+      }
+      CU(cudaEventRecord(ws->ev_a, ws->st));
+    }
     if (nbytes) CU(cudaMemcpyAsync(ws->d_qbytes, src_b, nbytes, cudaMemcpyHostToDevice, ws->st));
+    if (probe) {
+      CU(cudaEventRecord(ws->ev_b, ws->st));
+      ws->link_probe_bytes = nbytes;
+    }
     CU(cudaMemcpyAsync(ws->d_qoff, src_o, (nq + 1) * 8, cudaMemcpyHostToDevice, ws->st));
     g_prof.h2d += nbytes + (nq + 1) * 8;
     CU(cudaMemsetAsync(ws->d_flag, 0xff, 8, ws->st));
@@ -863,18 +929,41 @@ void search_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
     if (pending[s] < 0) return;
     const Chunk& c = chunks[size_t(pending[s])];
     CU(cudaEventSynchronize(ws[s]->done));
+    if (ws[s]->link_probe_bytes) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, ws[s]->ev_a, ws[s]->ev_b) == cudaSuccess)
+        g_balance.note_link(double(ws[s]->link_probe_bytes), double(ms) * 1e-3);
+      ws[s]->link_probe_bytes = 0;
+    }
     check_flag(ws[s], c);
     if (!dst_pinned)
       parallel_memcpy(static_cast<char*>(out) + c.q0 * out_elem, ws[s]->h_out, (c.q1 - c.q0) * out_elem);
     pending[s] = -1;
   };
+  uint64_t bytes_total = 0, bytes_packed = 0;  // of the chunks enqueued so far (pinned sources only)
+  const bool balanced = src_pinned && ix->alphabet == AWRY_NUCLEOTIDE && host_pack_enabled();
+  PackBalance::Plan plan{1.0, false, false};
+  if (balanced) plan = g_balance.plan();
   try {
     for (size_t i = 0; i < chunks.size(); i++) {
       int s = int(i % DEPTH);
       if (!ws[s]) ws[s] = r.acquire();
       finish(s);
       const Chunk& c = chunks[i];
-      enqueue_search(ix, r, ws[s], qbytes, qoff, c, mode, src_pinned);
+      bool may_pack = true, probe = false;
+      if (balanced) {
+        if (i == 0 && plan.probe_link && chunks.size() > 1) {
+          may_pack = false;  // nothing else is in flight: the cleanest moment to time the link
+          probe = true;
+        } else if (i == 1 && plan.probe_host) {
+          may_pack = true;
+        } else {
+          may_pack = double(bytes_packed) < plan.share * double(bytes_total + (c.b1 - c.b0));
+        }
+        bytes_total += c.b1 - c.b0;
+        if (may_pack) bytes_packed += c.b1 - c.b0;
+      }
+      enqueue_search(ix, r, ws[s], qbytes, qoff, c, mode, src_pinned, may_pack, probe);
       size_t bytes = (c.q1 - c.q0) * out_elem;
       void* dst = static_cast<char*>(out) + c.q0 * out_elem;
       if (!dst_pinned) {

@@ -1,10 +1,6 @@
-for mb in 16 32 64 128; do
-  for th in 16; do
-    AWRY_B200_CHUNK_MB=$mb AWRY_B200_HOST_THREADS=$th python bench.py --steps 5 --warmup 3 --no-locate --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('chunk_mb $mb threads $th e2e ms', round(d['e2e']['ms_per_step'],2), 'M reads/s', round(d['e2e']['value']/1e6,1))"
-  done
+# e2e (C-ABI call, pinned host buffers) vs the share of the query bytes packed on the host
+for share in auto 1 0.8 0.7 0.6 0.5 0; do
+  if [ "$share" = auto ]; then unset AWRY_B200_PACK_SHARE; else export AWRY_B200_PACK_SHARE=$share; fi
+  python bench.py --steps 5 --warmup 3 --no-locate --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('pack share $share: e2e ms', round(d['e2e']['ms_per_step'],2), 'M reads/s', round(d['e2e']['value']/1e6,1), 'h2d MB', d['e2e']['h2d_bytes_per_step']//1000000, ' device-resident ms', round(d['ms_per_step'],2))"
 done
-AWRY_B200_CHUNK_MB=64 AWRY_B200_HOST_THREADS=8 python bench.py --steps 5 --warmup 3 --no-locate --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('chunk_mb 64 threads 8 e2e ms', round(d['e2e']['ms_per_step'],2))"
-AWRY_B200_HOST_PACK=0 python bench.py --steps 5 --warmup 3 --no-locate --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('ascii e2e ms', round(d['e2e']['ms_per_step'],2))"
