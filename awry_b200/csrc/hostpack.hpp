@@ -15,8 +15,8 @@ int host_pool_threads();
 void host_parallel(const std::function<void(int, int)>& fn);
 
 // src[0..n) ASCII -> dst: crumb i = (src[i] >> 1) & 3 at bits 2*(i%4) of dst[i/4]  (A0 C1 T2 G3, either
-// case).  Every byte that is not one of ACGTacgt is reported as (i << 8) | byte in `exceptions` (sorted
-// by i); its crumb is arbitrary and gets patched on the device.  Returns false (dst incomplete) when
+// case).  Every byte that is not one of ACGTacgt is reported as (i << 8) | byte in `exceptions` (in no
+// particular order); its crumb is arbitrary and gets patched on the device.  Returns false (dst incomplete) when
 // more than n / max_exc_div bytes are exceptions -- the caller then sends the chunk as ASCII.
 bool host_pack_dna(const uint8_t* src, size_t n, uint8_t* dst, std::vector<uint64_t>& exceptions, size_t max_exc_div);
 

@@ -25,7 +25,7 @@ for n in (0, 1, 3, 4, 63, 64, 65, 127, 1000, 4097, 300_001, 3_000_000):
     up = src & 0xDF
     bad = ~((up == 65) | (up == 67) | (up == 71) | (up == 84))
     want_exc = (np.nonzero(bad)[0].astype(np.uint64) << np.uint64(8)) | src[bad].astype(np.uint64)
-    assert np.array_equal(exc, want_exc), (n, len(exc), len(want_exc))
+    assert np.array_equal(np.sort(exc), want_exc), (n, len(exc), len(want_exc))
     crumbs = ((src >> 1) & 3).astype(np.uint8)
     pad = np.zeros((-n) %% 4, dtype=np.uint8)
     c4 = np.concatenate([crumbs, pad]).reshape(-1, 4)
