@@ -760,6 +760,36 @@ std::vector<Chunk> make_chunks(const uint64_t* qoff, uint64_t q_lo, uint64_t q_h
   return out;
 }
 
+// Pipeline fill and drain: the device idles while the host prepares the first chunk, and the host idles
+// while the device works on the last one.  Splitting the first chunk into 1/4 + 3/4 and the last into
+// 1/2 + 1/4 + 1/4 (by queries) shortens both ends without paying the per-chunk overhead everywhere.
+std::vector<Chunk> taper_chunks(std::vector<Chunk> in, const uint64_t* qoff) {
+  if (in.size() < 3) return in;
+  auto split = [&](const Chunk& c, std::initializer_list<double> cuts, std::vector<Chunk>& dst) {
+    uint64_t nq = c.q1 - c.q0, prev = c.q0;
+    for (double f : cuts) {
+      uint64_t at = c.q0 + uint64_t(double(nq) * f);
+      if (at > prev && at < c.q1) {
+        dst.push_back(Chunk{prev, at, qoff[prev], qoff[at]});
+        prev = at;
+      }
+    }
+    dst.push_back(Chunk{prev, c.q1, qoff[prev], qoff[c.q1]});
+  };
+  std::vector<Chunk> out;
+  const uint64_t MIN_SPLIT = 64u << 20;  // only chunks worth splitting
+  if (in.front().b1 - in.front().b0 >= MIN_SPLIT)
+    split(in.front(), {0.25}, out);
+  else
+    out.push_back(in.front());
+  for (size_t i = 1; i + 1 < in.size(); i++) out.push_back(in[i]);
+  if (in.back().b1 - in.back().b0 >= MIN_SPLIT)
+    split(in.back(), {0.5, 0.75}, out);
+  else
+    out.push_back(in.back());
+  return out;
+}
+
 bool host_pack_enabled() {
   if (g_host_pack >= 0) return g_host_pack == 1 && host_pack_supported();
   static const bool on = [] {
@@ -921,7 +951,7 @@ void search_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
   const size_t out_elem = mode == OUT_COUNT_U64 ? 8 : 16;
   const bool src_pinned = is_pinned(qbytes) && is_pinned(qoff);
   const bool dst_pinned = is_pinned(out);
-  auto chunks = make_chunks(qoff, q_lo, q_hi, CHUNK_MAX_Q, chunk_max_bytes());
+  auto chunks = taper_chunks(make_chunks(qoff, q_lo, q_hi, CHUNK_MAX_Q, chunk_max_bytes()), qoff);
   constexpr int DEPTH = 3;
   Workspace* ws[DEPTH] = {nullptr, nullptr, nullptr};
   int pending[DEPTH] = {-1, -1, -1};
@@ -1055,11 +1085,11 @@ uint64_t* locate_chunk_walk(Replica& r, Workspace* ws, uint64_t nq, uint64_t n_h
   if (g_locate_variant == 1) view.full_sa = nullptr;
   const uint2* d_sp_cnt = reinterpret_cast<const uint2*>(ws->d_out);
   uint64_t* d_hits = nullptr;
-  CU(cudaMallocAsync(reinterpret_cast<void**>(&d_hits), n_hits * 16, st));  // pool: no driver round trip
+  CU(cudaMallocAsync(reinterpret_cast<void**>(&d_hits), n_hits * 16 + 16, st));  // pool: no driver round trip
   try {
     if (flags & AWRY_LOCATE_SORTED) {
       uint64_t *d_locs = nullptr, *d_sorted = nullptr;
-      CU(cudaMallocAsync(reinterpret_cast<void**>(&d_locs), n_hits * 8, st));
+      CU(cudaMallocAsync(reinterpret_cast<void**>(&d_locs), n_hits * 8 + 16, st));
       CU(cudaMallocAsync(reinterpret_cast<void**>(&d_sorted), n_hits * 8, st));
       {
         ProfScope p(1, r.device, st);

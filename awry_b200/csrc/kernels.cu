@@ -1440,25 +1440,36 @@ __device__ __forceinline__ void finish_hit(const IndexView& ix, uint32_t row, ui
 // compressed_suffix_array.rs:109-111) do not idle the rest of the warp.  The lane holding the row's
 // chunk extracts the BWT symbol and broadcasts it; both lanes rank their two chunks; xor-shuffle.
 // Warp-convergent loop (exit by vote) so the shuffles use the full mask.
+constexpr uint64_t WALK_TICKET = 32;  // hits per ticket
+
 template <bool MAP>
 __global__ void __launch_bounds__(256) walk_dna_kernel(IndexView ix, uint64_t n_hits, uint64_t* __restrict__ out) {
   constexpr int SLOT = MAP ? 2 : 1;
   constexpr uint32_t FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31, sub = lane & 1, gbase = lane - sub;
-  const uint64_t stride = (gridDim.x * uint64_t(blockDim.x)) >> 1;
-  uint64_t h = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 1;
+  // hits are handed out dynamically, WALK_TICKET at a time; the counter sits behind the output slots
+  unsigned long long* const ticket = reinterpret_cast<unsigned long long*>(out + SLOT * n_hits);
+  uint64_t h = 0, h_end = 0;
+  bool more = true;
   uint64_t cur = 0;
   uint32_t row = 0, steps = 0;
   bool have = false;
   for (;;) {
-    if (!have && h < n_hits) {
-      cur = h;
-      h += stride;
+    if (!have && h == h_end && more) {
+      unsigned long long t = 0;
+      if (sub == 0) t = atomicAdd(ticket, (unsigned long long)WALK_TICKET);
+      t = __shfl_sync(0x3u << gbase, t, gbase);
+      more = t < n_hits;
+      h = more ? t : 0;
+      h_end = more ? (n_hits - t < WALK_TICKET ? n_hits : t + WALK_TICKET) : 0;
+    }
+    if (!have && h < h_end) {
+      cur = h++;
       row = uint32_t(out[SLOT * cur]);
       steps = 0;
       have = true;
     }
-    if (__all_sync(FULL, !have)) break;
+    if (__all_sync(FULL, !have && !more && h == h_end)) break;
     if (have && row_is_sampled(ix, row)) {
       if (sub == 0) finish_hit(ix, row, steps, out + SLOT * cur, MAP);
       have = false;
@@ -1493,20 +1504,28 @@ __global__ void __launch_bounds__(256) walk_amino_kernel(IndexView ix, uint64_t 
   constexpr int SLOT = MAP ? 2 : 1;
   constexpr uint32_t FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31, sub = lane & 3, gbase = lane - sub;
-  const uint64_t stride = (gridDim.x * uint64_t(blockDim.x)) >> 2;
-  uint64_t h = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 2;
+  unsigned long long* const ticket = reinterpret_cast<unsigned long long*>(out + SLOT * n_hits);
+  uint64_t h = 0, h_end = 0;
+  bool more = true;
   uint64_t cur = 0;
   uint32_t row = 0, steps = 0;
   bool have = false;
   for (;;) {
-    if (!have && h < n_hits) {
-      cur = h;
-      h += stride;
+    if (!have && h == h_end && more) {
+      unsigned long long t = 0;
+      if (sub == 0) t = atomicAdd(ticket, (unsigned long long)WALK_TICKET);
+      t = __shfl_sync(0xfu << gbase, t, gbase);
+      more = t < n_hits;
+      h = more ? t : 0;
+      h_end = more ? (n_hits - t < WALK_TICKET ? n_hits : t + WALK_TICKET) : 0;
+    }
+    if (!have && h < h_end) {
+      cur = h++;
       row = uint32_t(out[SLOT * cur]);
       steps = 0;
       have = true;
     }
-    if (__all_sync(FULL, !have)) break;
+    if (__all_sync(FULL, !have && !more && h == h_end)) break;
     if (have && row_is_sampled(ix, row)) {
       if (sub == 0) finish_hit(ix, row, steps, out + SLOT * cur, MAP);
       have = false;
@@ -1740,6 +1759,10 @@ cudaError_t launch_walk(const IndexView& ix, const uint2* d_sp_cnt, const uint64
     expand_rows_kernel<<<grid, 256, 0, s>>>(d_sp_cnt, d_hit_off, nq, reinterpret_cast<uint32_t*>(out), map ? 4u : 2u);
     COUNT_LAUNCH();
     cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  {  // ticket counter of the walk kernels: 8 bytes behind the output slots (the caller allocates +16)
+    cudaError_t e = cudaMemsetAsync(out + (map ? 2 : 1) * n_hits, 0, 8, s);
     if (e != cudaSuccess) return e;
   }
   if (ix.alphabet == 0) {

@@ -65,7 +65,8 @@ cudaError_t launch_search(const IndexView& ix, const uint64_t* d_qwords, const u
 cudaError_t scan_hit_offsets(const uint2* d_sp_cnt, uint64_t nq, uint64_t* d_hit_off, void* d_temp,
                              size_t& temp_bytes, cudaStream_t s);
 // writes either awry_hit {seq_idx, local_pos} (d_hits) or global text positions (d_locs); when
-// ix.full_sa is set the walk is replaced by a gather from the unsampled array
+// ix.full_sa is set the walk is replaced by a gather from the unsampled array.  The output buffer must
+// have 16 spare bytes behind its n_hits slots (the walk kernels' ticket counter).
 cudaError_t launch_walk(const IndexView& ix, const uint2* d_sp_cnt, const uint64_t* d_hit_off,
                         uint64_t nq, uint64_t n_hits, uint64_t* d_hits_pairs, uint64_t* d_locs,
                         int sm_count, cudaStream_t s);
