@@ -803,17 +803,21 @@ bool host_pack_enabled() {
 // bytes (16 threads: 84 GB/s vs 52 GB/s for one GPU) and loses when a process has few cores and shares
 // the host's uplinks (4 threads per GPU on an 8-GPU box: measured 690 M reads/s packed vs 1095 M raw).
 // Both rates are MEASURED and smoothed across calls: the host clock around the packer (H), CUDA events
-// around the copy of a raw first chunk, when nothing else is in flight (P); a call packs iff H > 1.15 P.
-// Mixing packed and raw chunks inside one call was measured and is worse than either: a 128-MiB raw copy
-// holds the copy engine for 2.6 ms and starves the search kernel (profiles/r01_s19_e2e_pack_share.log).
+// around the copy of a raw first chunk, when nothing else is in flight (P).  H > 1.15 P: pack everything
+// (one GPU, 16 threads: mixing raw chunks in was measured and is worse there -- a 128-MiB raw copy holds
+// the copy engine for 2.6 ms and starves the search kernel, profiles/r01_s19_e2e_pack_share.log).
+// Otherwise host and link are used together: a share f = H / (P + 0.75 H) of the bytes is packed
+// (+5 % / +14 % / -8 % at 2 / 4 / 8 GPUs of a 32-core box, profiles/r01_s23_e2e_mixed_multi_gpu.log).
 // AWRY_B200_PACK_SHARE=<0..1> pins the packed share of the bytes instead (experiments).
 struct PackBalance {
   std::mutex mu;
   double host_rate = 0, link_rate = 0;  // bytes/s, 0 = not measured yet
   double fixed_share = -1;
   uint64_t calls = 0;
+  bool mixed = true;  // AWRY_B200_PACK_MIXED=0: all-or-nothing
   PackBalance() {
     if (const char* e = getenv("AWRY_B200_PACK_SHARE")) fixed_share = std::min(1.0, std::max(0.0, atof(e)));
+    if (const char* e = getenv("AWRY_B200_PACK_MIXED")) mixed = e[0] != '0';
   }
   void note_host(double bytes, double seconds) {
     if (seconds <= 0 || bytes < (8 << 20)) return;
@@ -837,8 +841,11 @@ struct PackBalance {
     if (fixed_share >= 0) return Plan{fixed_share, false, false};
     const bool refresh = calls++ % 32 == 0;
     if (host_rate <= 0 || link_rate <= 0) return Plan{1.0, true, true};
-    const bool pack = host_rate > 1.15 * link_rate;
-    return Plan{pack ? 1.0 : 0.0, refresh && pack, refresh && !pack};
+    if (host_rate > 1.15 * link_rate) return Plan{1.0, refresh, false};
+    // the host is not clearly faster than the link: use both (see the share formula above)
+    double f = mixed ? host_rate / (link_rate + 0.75 * host_rate) : 0.0;
+    if (f < 0.15) f = 0.0;
+    return Plan{f, true, f == 0.0 && refresh};
   }
 };
 PackBalance g_balance;
