@@ -339,6 +339,9 @@ uint64_t ipow(uint64_t b, uint32_t e) {
 // sequential byte source: a file (FmIndex::load) or caller memory sections (FmIndex::new hand-over)
 struct Source {
   FILE* f = nullptr;
+  // arrays already on replica 0's device in the reference layout (awry_index_build): no staging
+  const uint64_t* dev_blocks = nullptr;
+  const uint64_t* dev_sa = nullptr;
   std::vector<std::pair<const uint8_t*, size_t>> segs;
   size_t cur = 0, off = 0;
   void read(void* dst, size_t n, const char* what) {
@@ -447,15 +450,18 @@ void build_replica0(awry_index* ix, Replica& r, Source& src_blocks_then_rest, bo
   const uint64_t CHUNK = 1u << 18;  // reference blocks per staging buffer (40 / 88 MiB)
   uint8_t* h_stage[2] = {nullptr, nullptr};
   uint64_t* d_stage[2] = {nullptr, nullptr};
-  cudaEvent_t ev[2];
+  cudaEvent_t ev[2] = {nullptr, nullptr};
   uint64_t chunk_blocks = std::min<uint64_t>(CHUNK, n_ref_blocks);
-  for (int i = 0; i < 2; i++) {
+  const bool staged = !src_blocks_then_rest.dev_blocks || !src_blocks_then_rest.dev_sa;
+  for (int i = 0; i < 2 && staged; i++) {
     CU(cudaHostAlloc(reinterpret_cast<void**>(&h_stage[i]), chunk_blocks * ref_block_bytes, cudaHostAllocDefault));
     CU(cudaMalloc(reinterpret_cast<void**>(&d_stage[i]), chunk_blocks * ref_block_bytes));
     CU(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
   }
   int slot = 0;
-  for (uint64_t b0 = 0; b0 < n_ref_blocks; b0 += chunk_blocks, slot ^= 1) {
+  if (src_blocks_then_rest.dev_blocks)
+    CU(launch_transpose(ix->alphabet, src_blocks_then_rest.dev_blocks, 0, n_ref_blocks, ix->bwt_len, r.d_blocks, d_dollar, st));
+  for (uint64_t b0 = 0; b0 < n_ref_blocks && !src_blocks_then_rest.dev_blocks; b0 += chunk_blocks, slot ^= 1) {
     uint64_t nb = std::min(chunk_blocks, n_ref_blocks - b0);
     CU(cudaEventSynchronize(ev[slot]));
     src_blocks_then_rest.read(h_stage[slot], nb * ref_block_bytes, "bwt blocks");
@@ -479,7 +485,10 @@ void build_replica0(awry_index* ix, Replica& r, Source& src_blocks_then_rest, bo
   r.bytes_sa = size_t(ix->n_sa_words + 2) * 8;
   CU(cudaMalloc(reinterpret_cast<void**>(&r.d_sa), r.bytes_sa));
   CU(cudaMemsetAsync(r.d_sa, 0, r.bytes_sa, st));
-  {
+  if (src_blocks_then_rest.dev_sa) {
+    CU(cudaMemcpyAsync(r.d_sa, src_blocks_then_rest.dev_sa, ix->n_sa_words * 8, cudaMemcpyDeviceToDevice, st));
+    CU(cudaStreamSynchronize(st));
+  } else {
     const size_t words_per_chunk = chunk_blocks * ref_block_bytes / 8;
     slot = 0;
     for (uint64_t w0 = 0; w0 < ix->n_sa_words; w0 += words_per_chunk, slot ^= 1) {
@@ -491,7 +500,7 @@ void build_replica0(awry_index* ix, Replica& r, Source& src_blocks_then_rest, bo
     }
     CU(cudaStreamSynchronize(st));
   }
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < 2 && staged; i++) {
     cudaFreeHost(h_stage[i]);
     cudaFree(d_stage[i]);
     cudaEventDestroy(ev[i]);
@@ -1614,6 +1623,35 @@ int awry_build_parts(uint32_t alphabet, const uint8_t* text, uint64_t n, uint64_
   });
 }
 
+int awry_read_sequence_file(const char* path, uint32_t alphabet, uint8_t** text, uint64_t* n_text, uint64_t** starts,
+                            uint64_t* n_records) {
+  return guarded([&] {
+    if (!path || !text || !n_text || !starts || !n_records) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    if (alphabet > 1) fail(AWRY_ERR_INVALID_ARG, "invalid alphabet id %u", alphabet);
+    *text = nullptr;
+    *starts = nullptr;
+    *n_text = *n_records = 0;
+    TextBuf t;
+    std::string err;
+    std::vector<uint64_t> st;
+    std::vector<std::string> hd;
+    if (read_sequence_file(path, alphabet == 0 ? 'N' : 'X', t, st, hd, err) != 0) fail(AWRY_ERR_IO, "%s", err.c_str());
+    uint8_t* tb = static_cast<uint8_t*>(malloc(t.size() + 1));
+    uint64_t* sb = static_cast<uint64_t*>(malloc(st.size() * 8 + 8));
+    if (!tb || !sb) {
+      free(tb);
+      free(sb);
+      fail(AWRY_ERR_NOMEM, "out of host memory");
+    }
+    memcpy(tb, t.data(), t.size());
+    memcpy(sb, st.data(), st.size() * 8);
+    *text = tb;
+    *n_text = t.size();
+    *starts = sb;
+    *n_records = st.size();
+  });
+}
+
 int awry_index_build(const awry_build_args* a, const int* devices, int n_dev, awry_index** out) {
   return guarded([&] {
     if (out) *out = nullptr;
@@ -1626,43 +1664,66 @@ int awry_index_build(const awry_build_args* a, const int* devices, int n_dev, aw
     const int card = alphabet == 0 ? 6 : 22;
     if (k > 255 || ipow(uint64_t(card - 2), k) > (1ull << 34)) fail(AWRY_ERR_UNSUPPORTED, "k-mer table of length %u too large", k);
     // the sequence file first: I/O and format errors do not need a device
-    std::string text, err;
+    const bool verbose = getenv("AWRY_B200_BUILD_VERBOSE") != nullptr;  // phase times on stderr
+    auto tick = [t = std::chrono::steady_clock::now(), verbose](const char* what) mutable {
+      auto now = std::chrono::steady_clock::now();
+      if (verbose) fprintf(stderr, "[awry_index_build] %-28s %.3f s\n", what, std::chrono::duration<double>(now - t).count());
+      t = now;
+    };
+    TextBuf text;
+    std::string err;
     std::vector<uint64_t> starts;
     std::vector<std::string> headers;
     if (read_sequence_file(a->input_file_src, alphabet == 0 ? 'N' : 'X', text, starts, headers, err) != 0)
       fail(AWRY_ERR_IO, "%s", err.c_str());
+    tick("read sequence file");
     const uint64_t n = text.size(), bwt_len = n + 1;
     if (bwt_len >= (1ull << 32) - 256) fail(AWRY_ERR_UNSUPPORTED, "text of %llu symbols: 32-bit row pointers", (unsigned long long)n);
     int dev0 = a->device;
     std::vector<int> devs = out ? pick_devices(devices ? devices : &dev0, devices ? n_dev : 1) : pick_devices(&dev0, 1);
-    std::vector<uint64_t> blocks(awry_parts_num_blocks(bwt_len) * awry_parts_block_words(a->alphabet));
-    std::vector<uint64_t> prefix(size_t(card) + 1), sa_words(sa_word_len(bwt_len, ratio) + 1);
-    if (build_parts(alphabet, reinterpret_cast<const uint8_t*>(text.data()), n, ratio, devs[0], blocks.data(),
-                    prefix.data(), sa_words.data(), nullptr, err) != 0)
+    // construction on devs[0]; the reference-layout arrays stay on the device and are re-laid out there
+    // (no 3.5 GB round trip through host memory); they are copied out only to write a file
+    std::vector<uint64_t> prefix(size_t(card) + 1);
+    DeviceParts dp;
+    struct DpGuard {
+      DeviceParts& d;
+      ~DpGuard() { d.release(); }
+    } dp_guard{dp};
+    double ph[8] = {0};
+    if (build_parts(alphabet, text.data(), n, ratio, devs[0], nullptr, prefix.data(), nullptr, ph, err, &dp) != 0)
       fail(AWRY_ERR_CUDA, "index construction failed: %s", err.c_str());
-    std::string().swap(text);
-    // a device index of what was just built: the caller's FmIndex, and/or the replica that
-    // populates the reference-style k-mer table of the file
-    std::vector<const char*> hdr_ptrs;
-    for (auto& h : headers) hdr_ptrs.push_back(h.c_str());
-    awry_parts parts{};
-    parts.alphabet = a->alphabet;
-    parts.kmer_len = out ? k : 0;  // a file-only build needs no seed table
-    parts.sa_ratio = ratio;
-    parts.bwt_len = bwt_len;
-    parts.version = 1;
-    parts.blocks = blocks.data();
-    parts.prefix_sums = prefix.data();
-    parts.sa_words = sa_words.data();
-    parts.seq_starts = starts.data();
-    parts.headers = hdr_ptrs.data();
-    parts.n_sequences = starts.size();
-    awry_index* ix = nullptr;
-    g_skip_accelerators = !out;
-    int rc = awry_index_from_parts(&parts, devs.data(), int(devs.size()), &ix);
-    g_skip_accelerators = false;
-    if (rc != AWRY_OK) throw ApiError(rc, g_err);
+    text.reset();
+    if (verbose)
+      fprintf(stderr, "[awry_index_build]   ingest %.3f keys %.3f sort %.3f ties %.3f bwt %.3f milestones %.3f sa-pack %.3f\n",
+              ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6]);
+    tick("suffix sort + BWT on device");
+    auto ixp = std::make_unique<awry_index>();
+    ixp->version = 1;
+    ixp->sa_ratio = ratio;
+    ixp->bwt_len = bwt_len;
+    ixp->alphabet = alphabet;
+    ixp->kmer_len_file = out ? k : 0;  // a file-only build needs no seed table
+    check_header(ixp.get());
+    ixp->seq_starts = starts;
+    ixp->headers = headers;
+    {
+      Source src;
+      src.dev_blocks = dp.d_blocks;
+      src.dev_sa = dp.d_sa_words;
+      src.segs.emplace_back(reinterpret_cast<const uint8_t*>(prefix.data()), size_t(card + 1) * 8);
+      g_skip_accelerators = !out;
+      try {
+        make_replicas(ixp.get(), devs, src, false);
+      } catch (...) {
+        g_skip_accelerators = false;
+        awry_index_free(ixp.release());
+        throw;
+      }
+      g_skip_accelerators = false;
+    }
+    awry_index* ix = ixp.release();
     std::unique_ptr<awry_index, void (*)(awry_index*)> holder(ix, awry_index_free);
+    tick("device layout + accelerators");
     if (a->output_file_src) {  // FmIndex::save (fm_index_file.rs:42-106)
       FILE* f = fopen(a->output_file_src, "wb");
       if (!f) fail(AWRY_ERR_IO, "cannot create %s: %s", a->output_file_src, strerror(errno));
@@ -1675,9 +1736,48 @@ int awry_index_build(const awry_build_args* a, const int* devices, int n_dev, aw
       put("AWRY-Index\n", 11);  // fm_index_file.rs:18,47
       uint64_t hdr[4] = {1, ratio, bwt_len, uint64_t(alphabet)};
       put(hdr, sizeof hdr);
-      put(blocks.data(), blocks.size() * 8);
+      // device arrays -> file through a pinned double buffer (D2H of chunk i+1 overlaps fwrite of chunk i)
+      auto put_device = [&](const uint64_t* d_src, uint64_t n_words) {
+        DeviceGuard dg(dp.device);
+        const uint64_t CH = (64u << 20) / 8;
+        uint64_t* hb[2] = {nullptr, nullptr};
+        cudaStream_t cs = nullptr;
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        try {
+          CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+          for (int i = 0; i < 2; i++) {
+            CU(cudaHostAlloc(reinterpret_cast<void**>(&hb[i]), CH * 8, cudaHostAllocDefault));
+            CU(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+          }
+          uint64_t n_chunks = (n_words + CH - 1) / CH;
+          auto issue = [&](uint64_t c) {
+            uint64_t w0 = c * CH, nw = std::min(CH, n_words - w0);
+            CU(cudaMemcpyAsync(hb[c & 1], d_src + w0, nw * 8, cudaMemcpyDeviceToHost, cs));
+            CU(cudaEventRecord(ev[c & 1], cs));
+          };
+          if (n_chunks) issue(0);
+          for (uint64_t c = 0; c < n_chunks; c++) {
+            CU(cudaEventSynchronize(ev[c & 1]));
+            if (c + 1 < n_chunks) issue(c + 1);
+            put(hb[c & 1], std::min(CH, n_words - c * CH) * 8);
+          }
+        } catch (...) {
+          for (int i = 0; i < 2; i++) {
+            cudaFreeHost(hb[i]);
+            if (ev[i]) cudaEventDestroy(ev[i]);
+          }
+          if (cs) cudaStreamDestroy(cs);
+          throw;
+        }
+        for (int i = 0; i < 2; i++) {
+          cudaFreeHost(hb[i]);
+          cudaEventDestroy(ev[i]);
+        }
+        cudaStreamDestroy(cs);
+      };
+      put_device(dp.d_blocks, dp.n_block_words);
       put(prefix.data(), prefix.size() * 8);
-      put(sa_words.data(), sa_word_len(bwt_len, ratio) * 8);
+      put_device(dp.d_sa_words, sa_word_len(bwt_len, ratio));
       uint8_t kb = uint8_t(k);
       put(&kb, 1);
       {
@@ -1711,6 +1811,7 @@ int awry_index_build(const awry_build_args* a, const int* devices, int n_dev, aw
       }
       if (fflush(f) != 0) ok = false;
       if (!ok) fail(AWRY_ERR_IO, "write to %s failed", a->output_file_src);
+      tick("write .awry file");
     }
     if (out) *out = holder.release();
   });

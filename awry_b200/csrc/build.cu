@@ -24,7 +24,10 @@
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cuda_runtime.h>
+#include <fcntl.h>
 #include <sys/stat.h>
+#include <thread>
+#include <unistd.h>
 #include <string>
 #include <vector>
 
@@ -329,7 +332,7 @@ void make_keys(const uint8_t* sym, uint64_t n1, uint64_t* keys, uint32_t* vals) 
 // Builds the reference-layout parts of text[0..n) + '$' (ASCII, host or device pointer).
 int build_parts_impl(int alphabet, const uint8_t* text, bool text_on_device, uint64_t n, uint64_t ratio, int device,
                      uint64_t* blocks_out, uint64_t* prefix_sums_out, uint64_t* sa_words_out, double* phase_s,
-                     std::string& err) {
+                     std::string& err, awry::DeviceParts* keep) {
   uint8_t* d_sym = nullptr;
   uint64_t *d_keys[2] = {nullptr, nullptr}, *d_blocks = nullptr, *d_ms = nullptr, *d_saw = nullptr;
   uint32_t *d_vals[2] = {nullptr, nullptr}, *d_counts = nullptr;
@@ -541,8 +544,18 @@ int build_parts_impl(int alphabet, const uint8_t* text, bool text_on_device, uin
     uint64_t n_words = uint64_t(((unsigned __int128)n_elems * bits + 63) / 64);
     CU(cudaMalloc(&d_saw, (n_words + 1) * 8));
     pack_sa_kernel<<<unsigned((n_words + 255) / 256), 256>>>(sa, n1, ratio, bits, n_words, d_saw);
-    CU(cudaMemcpy(sa_words_out, d_saw, n_words * 8, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(blocks_out, d_blocks, n_blocks * words_per_block * 8, cudaMemcpyDeviceToHost));
+    CU(cudaDeviceSynchronize());
+    if (sa_words_out) CU(cudaMemcpy(sa_words_out, d_saw, n_words * 8, cudaMemcpyDeviceToHost));
+    if (blocks_out) CU(cudaMemcpy(blocks_out, d_blocks, n_blocks * words_per_block * 8, cudaMemcpyDeviceToHost));
+    if (keep) {
+      keep->d_blocks = d_blocks;
+      keep->d_sa_words = d_saw;
+      keep->n_block_words = n_blocks * words_per_block;
+      keep->n_sa_words = n_words;
+      keep->device = device;
+      d_blocks = nullptr;
+      d_saw = nullptr;
+    }
     ph[6] = now_s() - t;
     ph[7] = now_s() - t0;
   } catch (const std::string& m) {
@@ -569,8 +582,20 @@ int build_parts_impl(int alphabet, const uint8_t* text, bool text_on_device, uin
 
 namespace awry {
 
+void DeviceParts::release() {
+  if (!d_blocks && !d_sa_words) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(device);
+  cudaFree(d_blocks);
+  cudaFree(d_sa_words);
+  d_blocks = d_sa_words = nullptr;
+  if (prev >= 0) cudaSetDevice(prev);
+}
+
 int build_parts(int alphabet, const uint8_t* text, uint64_t n, uint64_t ratio, int device, uint64_t* blocks_out,
-                uint64_t* prefix_sums_out, uint64_t* sa_words_out, double* phase_s, std::string& err) {
+                uint64_t* prefix_sums_out, uint64_t* sa_words_out, double* phase_s, std::string& err,
+                DeviceParts* keep) {
   if (alphabet != 0 && alphabet != 1) {
     err = "invalid alphabet";
     return -1;
@@ -585,7 +610,7 @@ int build_parts(int alphabet, const uint8_t* text, uint64_t n, uint64_t ratio, i
   int prev = -1;
   cudaGetDevice(&prev);
   int rc = build_parts_impl(alphabet, text, on_device, n, ratio, device, blocks_out, prefix_sums_out, sa_words_out,
-                            phase_s, err);
+                            phase_s, err, keep);
   if (prev >= 0) cudaSetDevice(prev);
   return rc;
 }
@@ -594,94 +619,242 @@ int build_parts(int alphabet, const uint8_t* text, uint64_t n, uint64_t ratio, i
 // libsufr::util::read_sequence_file (fm_index.rs:153): sequence lines of a record concatenated, records
 // joined by `delimiter`, start offset and header text (without the marker) kept.  Case is left as it is:
 // the device maps both cases to the same symbol (alphabet.rs:169-248), which is what upper-casing does.
-// Large reads + memchr: ~2 GB/s on one host thread.
-int read_sequence_file(const std::string& path, char delimiter, std::string& text, std::vector<uint64_t>& starts,
-                       std::vector<std::string>& headers, std::string& err) {
-  FILE* f = fopen(path.c_str(), "rb");
-  if (!f) {
-    err = "cannot open " + path;
-    return -1;
+// Large FASTA files are parsed by several threads, each on a byte range that begins at a line start
+// (positional reads + memchr); FASTQ and small files take the sequential path.
+namespace {
+
+struct LocalParse {
+  std::string text;
+  std::vector<std::pair<uint64_t, std::string>> recs;  // (offset in `text`, header)
+  std::string err;
+};
+
+// one FASTA line (no '\n'); `global_first`: nothing of the file precedes this parse
+inline void fasta_line(const char* p, size_t n, char delimiter, bool global_first, LocalParse& out) {
+  if (n && p[n - 1] == '\r') n--;
+  if (n && p[0] == '>') {
+    if (!(global_first && out.recs.empty() && out.text.empty())) out.text.push_back(delimiter);
+    out.recs.emplace_back(out.text.size(), std::string(p + 1, n - 1));
+    return;
   }
-  text.clear();
-  starts.clear();
-  headers.clear();
-  {
-    struct stat sb;
-    if (fstat(fileno(f), &sb) == 0 && sb.st_size > 0) text.reserve(size_t(sb.st_size));
+  if (!memchr(p, ' ', n) && !memchr(p, '\t', n)) {
+    out.text.append(p, n);
+    return;
   }
-  std::vector<char> buf(16u << 20);
-  std::string line;  // the current (possibly buffer-straddling) line
-  bool fastq = false, first = true, failed = false;
-  int fq_line = 0;  // 0 header, 1 sequence, 2 '+', 3 qualities
-  auto begin_record = [&](const char* p, size_t n) {
-    if (!starts.empty()) text.push_back(delimiter);
-    starts.push_back(text.size());
-    headers.emplace_back(p, n);
-  };
-  auto take_line = [&](const char* p, size_t n) {
-    if (n && p[n - 1] == '\r') n--;
-    if (first) {
-      if (n == 0) return;
-      fastq = p[0] == '@';
-      if (!fastq && p[0] != '>') {
-        err = "input is neither FASTA ('>') nor FASTQ ('@')";
-        failed = true;
-        return;
-      }
-      first = false;
+  for (size_t i = 0; i < n; i++)  // blanks inside sequence lines are dropped
+    if (p[i] != ' ' && p[i] != '\t') out.text.push_back(p[i]);
+}
+
+// lines that START in [lo, hi) of the file
+void fasta_range(int fd, uint64_t lo, uint64_t hi, uint64_t fsize, char delimiter, bool global_first, LocalParse& out) {
+  std::vector<char> buf(8u << 20);
+  std::string line;
+  uint64_t pos = lo;
+  bool done = false;
+  out.text.reserve(size_t(hi - lo));
+  while (!done && pos < fsize) {
+    ssize_t got = pread(fd, buf.data(), buf.size(), off_t(pos));
+    if (got <= 0) {
+      out.err = "read error";
+      return;
     }
-    if (fastq) {
-      if (fq_line == 0) {
-        if (n == 0) return;
-        begin_record(p + 1, n - 1);
-      } else if (fq_line == 1) {
-        text.append(p, n);
-      }
-      fq_line = (fq_line + 1) & 3;
-    } else if (n && p[0] == '>') {
-      begin_record(p + 1, n - 1);
-    } else {
-      size_t i = 0;
-      while (i < n) {  // blanks inside sequence lines are dropped
-        size_t j = i;
-        while (j < n && p[j] != ' ' && p[j] != '\t') j++;
-        text.append(p + i, j - i);
-        i = j + 1;
-      }
-    }
-  };
-  size_t got;
-  while (!failed && (got = fread(buf.data(), 1, buf.size(), f)) > 0) {
-    size_t pos = 0;
-    while (pos < got && !failed) {
-      const char* nl = static_cast<const char*>(memchr(buf.data() + pos, '\n', got - pos));
-      if (!nl) {
-        line.append(buf.data() + pos, got - pos);
+    size_t off = 0;
+    while (off < size_t(got)) {
+      // a line that starts at or after `hi` belongs to the next range
+      if (line.empty() && pos + off >= hi) {
+        done = true;
         break;
       }
-      size_t n = size_t(nl - (buf.data() + pos));
+      const char* nl = static_cast<const char*>(memchr(buf.data() + off, '\n', size_t(got) - off));
+      if (!nl) {
+        line.append(buf.data() + off, size_t(got) - off);
+        break;
+      }
+      size_t n = size_t(nl - (buf.data() + off));
       if (line.empty()) {
-        take_line(buf.data() + pos, n);
+        fasta_line(buf.data() + off, n, delimiter, global_first, out);
       } else {
-        line.append(buf.data() + pos, n);
-        take_line(line.data(), line.size());
+        line.append(buf.data() + off, n);
+        fasta_line(line.data(), line.size(), delimiter, global_first, out);
         line.clear();
       }
-      pos += n + 1;
+      off += n + 1;
     }
+    pos += uint64_t(got);
   }
-  if (!failed && !line.empty()) take_line(line.data(), line.size());
-  fclose(f);
-  if (failed) return -1;
-  if (starts.empty()) {
+  if (!line.empty()) fasta_line(line.data(), line.size(), delimiter, global_first, out);  // last line without '\n'
+}
+
+int finish_parse(std::vector<LocalParse>& parts, const std::string& path, awry::TextBuf& text,
+                 std::vector<uint64_t>& starts, std::vector<std::string>& headers, std::string& err) {
+  size_t total = 0, n_recs = 0;
+  for (auto& lp : parts) {
+    if (!lp.err.empty()) {
+      err = lp.err + " in " + path;
+      return -1;
+    }
+    total += lp.text.size();
+    n_recs += lp.recs.size();
+  }
+  if (n_recs == 0) {
     err = "no sequence records in " + path;
     return -1;
   }
-  if (text.empty()) {
+  if (total == 0) {
     err = "sequence records are empty in " + path;
     return -1;
   }
+  text.p.reset(new uint8_t[total + 64]);
+  text.n = total;
+  std::vector<size_t> base(parts.size() + 1, 0);
+  for (size_t i = 0; i < parts.size(); i++) base[i + 1] = base[i] + parts[i].text.size();
+  std::vector<std::thread> th;
+  for (size_t i = 0; i < parts.size(); i++)
+    th.emplace_back([&, i] {
+      if (!parts[i].text.empty()) memcpy(text.p.get() + base[i], parts[i].text.data(), parts[i].text.size());
+      std::string().swap(parts[i].text);
+    });
+  for (auto& t : th) t.join();
+  starts.reserve(n_recs);
+  headers.reserve(n_recs);
+  for (size_t i = 0; i < parts.size(); i++)
+    for (auto& r : parts[i].recs) {
+      starts.push_back(base[i] + r.first);
+      headers.push_back(std::move(r.second));
+    }
   return 0;
+}
+
+}  // namespace
+
+int read_sequence_file(const std::string& path, char delimiter, TextBuf& text, std::vector<uint64_t>& starts,
+                       std::vector<std::string>& headers, std::string& err) {
+  text.reset();
+  starts.clear();
+  headers.clear();
+  int fd = open(path.c_str(), O_RDONLY);
+  if (fd < 0) {
+    err = "cannot open " + path;
+    return -1;
+  }
+  struct Closer {
+    int fd;
+    ~Closer() { close(fd); }
+  } closer{fd};
+  struct stat sb;
+  if (fstat(fd, &sb) != 0) {
+    err = "cannot stat " + path;
+    return -1;
+  }
+  const uint64_t fsize = uint64_t(sb.st_size);
+  // format: first non-blank byte
+  uint64_t data_start = 0;
+  char first = 0;
+  {
+    char head[4096];
+    uint64_t pos = 0;
+    while (!first && pos < fsize) {
+      ssize_t got = pread(fd, head, sizeof head, off_t(pos));
+      if (got <= 0) break;
+      for (ssize_t i = 0; i < got; i++) {
+        char c = head[i];
+        if (c == '\n' || c == '\r') continue;
+        first = c;
+        data_start = pos + uint64_t(i);
+        break;
+      }
+      pos += uint64_t(got);
+    }
+  }
+  if (!first) {
+    err = "no sequence records in " + path;
+    return -1;
+  }
+  if (first != '>' && first != '@') {
+    err = "input is neither FASTA ('>') nor FASTQ ('@')";
+    return -1;
+  }
+  if (first == '>') {
+    // ---- FASTA: ranges that begin at line starts, one thread each
+    uint64_t range_min = 32u << 20;  // AWRY_B200_FASTA_RANGE_BYTES: smaller ranges (tests)
+    if (const char* e = getenv("AWRY_B200_FASTA_RANGE_BYTES")) range_min = std::max<uint64_t>(16, strtoull(e, nullptr, 10));
+    unsigned nt = unsigned(std::min<uint64_t>(std::min(8u, std::max(2u, std::thread::hardware_concurrency())),
+                                              (fsize - data_start) / range_min + 1));
+    std::vector<uint64_t> cut(nt + 1, fsize);
+    cut[0] = data_start;
+    bool ok = true;
+    for (unsigned t = 1; t < nt && ok; t++) {
+      uint64_t nominal = data_start + (fsize - data_start) * t / nt;
+      // the first line start at or after `nominal`: just past the first '\n' at or after nominal - 1
+      uint64_t pos = nominal - 1, found = fsize;
+      char tmp[65536];
+      for (int tries = 0; tries < 16 && found == fsize && pos < fsize; tries++) {  // up to 1 MiB
+        ssize_t got = pread(fd, tmp, sizeof tmp, off_t(pos));
+        if (got <= 0) break;
+        const char* nl = static_cast<const char*>(memchr(tmp, '\n', size_t(got)));
+        if (nl) found = pos + uint64_t(nl - tmp) + 1;
+        pos += uint64_t(got);
+      }
+      if (found == fsize && pos < fsize) ok = false;  // a line longer than 1 MiB: one range after all
+      cut[t] = std::max(found, cut[t - 1]);
+    }
+    if (!ok) {
+      nt = 1;
+      cut.assign({data_start, fsize});
+    }
+    std::vector<LocalParse> parts(nt);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++)
+      th.emplace_back([&, t] { fasta_range(fd, cut[t], cut[t + 1], fsize, delimiter, t == 0, parts[t]); });
+    for (auto& x : th) x.join();
+    return finish_parse(parts, path, text, starts, headers, err);
+  }
+  // ---- FASTQ: four lines per record, sequential
+  std::vector<LocalParse> parts(1);
+  LocalParse& lp = parts[0];
+  lp.text.reserve(size_t(fsize / 2));
+  std::vector<char> buf(16u << 20);
+  std::string line;
+  int fq_line = 0;  // 0 header, 1 sequence, 2 '+', 3 qualities
+  auto take_line = [&](const char* p, size_t n) {
+    if (n && p[n - 1] == '\r') n--;
+    if (fq_line == 0) {
+      if (n == 0) return;  // blank lines between records
+      if (!lp.recs.empty()) lp.text.push_back(delimiter);
+      lp.recs.emplace_back(lp.text.size(), std::string(p + 1, n - 1));
+    } else if (fq_line == 1) {
+      lp.text.append(p, n);
+    }
+    fq_line = (fq_line + 1) & 3;
+  };
+  uint64_t pos = data_start;
+  while (pos < fsize) {
+    ssize_t got = pread(fd, buf.data(), buf.size(), off_t(pos));
+    if (got <= 0) {
+      err = "read error in " + path;
+      return -1;
+    }
+    size_t off = 0;
+    while (off < size_t(got)) {
+      const char* nl = static_cast<const char*>(memchr(buf.data() + off, '\n', size_t(got) - off));
+      if (!nl) {
+        line.append(buf.data() + off, size_t(got) - off);
+        break;
+      }
+      size_t n = size_t(nl - (buf.data() + off));
+      if (line.empty()) {
+        take_line(buf.data() + off, n);
+      } else {
+        line.append(buf.data() + off, n);
+        take_line(line.data(), line.size());
+        line.clear();
+      }
+      off += n + 1;
+    }
+    pos += uint64_t(got);
+  }
+  if (!line.empty()) take_line(line.data(), line.size());
+  return finish_parse(parts, path, text, starts, headers, err);
 }
 
 }  // namespace awry

@@ -116,7 +116,7 @@ class Profile(C.Structure):
 
 
 # every symbol include/awry_b200.h declares (checked by tests/test_abi.py)
-EXPORTS = ["awry_index_build", "awry_build_index_file", "awry_build_parts", "awry_parts_num_blocks", "awry_parts_block_words",
+EXPORTS = ["awry_read_sequence_file", "awry_index_build", "awry_build_index_file", "awry_build_parts", "awry_parts_num_blocks", "awry_parts_block_words",
            "awry_parts_sa_words", "awry_index_load", "awry_index_from_parts", "awry_index_free", "awry_index_info",
            "awry_index_sequence_header", "awry_count_batch", "awry_search_batch",
            "awry_locate_batch", "awry_locate_batch_into", "awry_hits_free", "awry_count_reads_file",
@@ -141,6 +141,8 @@ def native():
     vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
     L.awry_last_error.restype = C.c_char_p
     L.awry_version.restype = C.c_char_p
+    L.awry_read_sequence_file.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp),
+                                          C.POINTER(u64)]
     L.awry_index_build.argtypes = [C.POINTER(BuildArgs), vp, i32, C.POINTER(vp)]
     L.awry_build_index_file.argtypes = [C.POINTER(BuildArgs)]
     L.awry_build_parts.argtypes = [C.c_uint32, vp, u64, u64, i32, vp, vp, vp, vp]
@@ -542,3 +544,19 @@ def host_pack_dna(src: np.ndarray):
     n = C.c_uint64()
     _check(native().awry_host_pack_dna(src.ctypes.data, len(src), dst.ctypes.data, exc.ctypes.data, len(exc), C.byref(n)))
     return dst[: (len(src) + 3) // 4], exc[: n.value]
+
+
+def read_sequence_file(path, alphabet: int = 0):
+    """libsufr's read_sequence_file as the builder sees it: -> (text uint8[], record starts uint64[])"""
+    tp, sp, n, nr = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
+    _check(native().awry_read_sequence_file(os.fsencode(path), int(alphabet), C.byref(tp), C.byref(n), C.byref(sp),
+                                            C.byref(nr)))
+    text = np.empty(n.value, dtype=np.uint8)
+    starts = np.empty(nr.value, dtype=np.uint64)
+    if n.value:
+        C.memmove(text.ctypes.data, tp, n.value)
+    if nr.value:
+        C.memmove(starts.ctypes.data, sp, nr.value * 8)
+    native().awry_buffer_free(tp)
+    native().awry_buffer_free(sp)
+    return text, starts

@@ -138,6 +138,13 @@ typedef struct awry_build_args {
  * I/O and format errors of the input are reported before any device is touched. */
 int awry_index_build(const awry_build_args *args, const int *devices, int n_dev, awry_index **out);
 
+/* What the reference gets from libsufr::util::read_sequence_file (fm_index.rs:153): the records of a
+ * FASTA / FASTQ file concatenated with 'N' / 'X' between them, and each record's start offset.  Host
+ * only (no device needed); large FASTA files are parsed by several threads.  *text and *starts are
+ * library-owned: release with awry_buffer_free. */
+int awry_read_sequence_file(const char *path, uint32_t alphabet, uint8_t **text, uint64_t *n_text,
+                            uint64_t **starts, uint64_t *n_records);
+
 /* FmIndex::new + FmIndex::save without keeping the index: awry_index_build(args, NULL, 0, NULL). */
 int awry_build_index_file(const awry_build_args *args);
 

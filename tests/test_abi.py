@@ -42,12 +42,14 @@ def test_struct_layouts_match_ctypes(tmp_path):
     """ctypes mirrors vs the compiler's view of include/awry_b200.h"""
     from awry_b200 import fm_index as f
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "awry_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n", '
-                   'sizeof(awry_range), sizeof(awry_parts), sizeof(awry_info), sizeof(awry_profile), sizeof(awry_hit));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "awry_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n", '
+                   'sizeof(awry_range), sizeof(awry_parts), sizeof(awry_info), sizeof(awry_profile), sizeof(awry_hit), '
+                   'sizeof(awry_build_args));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
-    assert sizes == [C.sizeof(f._Range), C.sizeof(f._Parts), C.sizeof(f._Info), C.sizeof(f.Profile), 16]
+    assert sizes == [C.sizeof(f._Range), C.sizeof(f._Parts), C.sizeof(f._Info), C.sizeof(f.Profile), 16,
+                     C.sizeof(f.BuildArgs)]
 
 
 def test_kernels_are_sm100a_native():
