@@ -23,6 +23,7 @@
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <zlib.h>
 #include <vector>
 
 #include "../../include/awry_b200.h"
@@ -1241,14 +1242,30 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
   if (fstat(fd, &sb) != 0) fail(AWRY_ERR_IO, "cannot stat %s", path);
   const uint64_t fsize = uint64_t(sb.st_size);
   out.file_bytes = fsize;
-  // format: first non-blank byte
+  // format: first non-blank byte (of the inflated stream when the file is gzip-compressed)
   int fastq = -1;
   uint64_t data_start = 0;
+  gzFile gz = nullptr;
+  struct GzCloser {
+    gzFile& g;
+    ~GzCloser() {
+      if (g) gzclose(g);
+    }
+  } gzc{gz};
   {
     unsigned char head[4096];
     ssize_t got = pread(fd, head, sizeof head, 0);
-    if (got >= 2 && head[0] == 0x1f && head[1] == 0x8b)
-      fail(AWRY_ERR_UNSUPPORTED, "%s is gzip-compressed; decompress it first", path);
+    bool at_end = fsize <= uint64_t(std::max<ssize_t>(got, 0));
+    if (got >= 2 && head[0] == 0x1f && head[1] == 0x8b) {
+      gz = gzopen(path, "rb");
+      if (!gz) fail(AWRY_ERR_IO, "cannot open %s as a gzip stream", path);
+      gzbuffer(gz, 4u << 20);
+      got = gzread(gz, head, sizeof head);
+      int zerr = Z_OK;
+      gzerror(gz, &zerr);  // a truncated stream returns the bytes it has and only flags the error
+      if (got < 0 || (zerr != Z_OK && zerr != Z_STREAM_END)) fail(AWRY_ERR_FORMAT, "%s: corrupt gzip stream", path);
+      at_end = got < ssize_t(sizeof head);
+    }
     for (ssize_t i = 0; i < got; i++) {
       unsigned char c = head[i];
       if (c == '\n' || c == '\r' || c == ' ' || c == '\t') continue;
@@ -1260,13 +1277,14 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
       if (got <= 0 || data_start == 0) {
         bool blank = true;
         for (ssize_t i = 0; i < got; i++) blank &= (head[i] == '\n' || head[i] == '\r' || head[i] == ' ' || head[i] == '\t');
-        if (blank && fsize <= uint64_t(std::max<ssize_t>(got, 0))) {  // empty file: zero reads
+        if (blank && at_end) {  // empty file: zero reads
           if (locate) out.hit_off.assign(1, 0);
           return;
         }
       }
       fail(AWRY_ERR_FORMAT, "%s is neither FASTQ ('@') nor FASTA ('>')", path);
     }
+    if (gz && gzseek(gz, z_off_t(data_start), SEEK_SET) < 0) fail(AWRY_ERR_FORMAT, "%s: corrupt gzip stream", path);
   }
   uint64_t CHUNK = 64ull << 20;
   if (const char* e = getenv("AWRY_B200_READS_CHUNK")) CHUNK = std::max<uint64_t>(64, strtoull(e, nullptr, 10));
@@ -1339,9 +1357,24 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
           cv.wait(lk, [&] { return stop || !s.filled; });
           if (stop) return;
         }
-        uint64_t n = std::min<uint64_t>(CHUNK, fsize - pos);
+        uint64_t n = gz ? 0 : std::min<uint64_t>(CHUNK, fsize - pos);
+        bool gz_end = false;
         try {
-          if (n) parallel_pread(fd, h_buf[c % NBUF] + CARRY, size_t(n), off_t(pos), path);
+          if (gz) {  // inflate on this thread (one zlib stream: ~0.3-0.5 GB/s); the device side is unchanged
+            while (n < CHUNK) {
+              int r = gzread(gz, h_buf[c % NBUF] + CARRY + n, unsigned(std::min<uint64_t>(CHUNK - n, 1u << 30)));
+              int zerr = Z_OK;
+              if (r <= 0) gzerror(gz, &zerr);
+              if (r < 0 || (zerr != Z_OK && zerr != Z_STREAM_END)) fail(AWRY_ERR_FORMAT, "%s: corrupt or truncated gzip stream", path);
+              if (r == 0) {
+                gz_end = true;
+                break;
+              }
+              n += uint64_t(r);
+            }
+          } else if (n) {
+            parallel_pread(fd, h_buf[c % NBUF] + CARRY, size_t(n), off_t(pos), path);
+          }
         } catch (const ApiError& e) {
           std::lock_guard<std::mutex> lk(mu);
           reader_err = e.what();
@@ -1352,14 +1385,15 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
           return;
         }
         pos += n;
+        const bool at_eof = gz ? gz_end : pos >= fsize;
         {
           std::lock_guard<std::mutex> lk(mu);
           s.n = n;
-          s.eof = pos >= fsize;
+          s.eof = at_eof;
           s.filled = true;
         }
         cv.notify_all();
-        if (pos >= fsize) return;
+        if (at_eof) return;
       }
     });
 

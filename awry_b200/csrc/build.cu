@@ -25,7 +25,9 @@
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cuda_runtime.h>
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <zlib.h>
 #include <thread>
 #include <unistd.h>
 #include <string>
@@ -741,6 +743,47 @@ int read_sequence_file(const std::string& path, char delimiter, TextBuf& text, s
     int fd;
     ~Closer() { close(fd); }
   } closer{fd};
+  {  // gzip-compressed input: inflate into an anonymous memory file, then parse that (same code below)
+    unsigned char magic[2] = {0, 0};
+    if (pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+      gzFile g = gzopen(path.c_str(), "rb");
+      int mfd = memfd_create("awry_b200_inflated", 0);
+      if (!g || mfd < 0) {
+        if (g) gzclose(g);
+        if (mfd >= 0) close(mfd);
+        err = "cannot inflate " + path;
+        return -1;
+      }
+      gzbuffer(g, 4u << 20);
+      std::vector<char> zb(16u << 20);
+      bool ok = true;
+      for (;;) {
+        int r = gzread(g, zb.data(), unsigned(zb.size()));
+        if (r <= 0) {
+          int zerr = Z_OK;
+          gzerror(g, &zerr);
+          if (r < 0 || (zerr != Z_OK && zerr != Z_STREAM_END)) ok = false;
+          break;
+        }
+        for (int w = 0; w < r && ok;) {
+          ssize_t k = write(mfd, zb.data() + w, size_t(r - w));
+          if (k <= 0)
+            ok = false;
+          else
+            w += int(k);
+        }
+        if (!ok) break;
+      }
+      gzclose(g);
+      if (!ok) {
+        close(mfd);
+        err = "corrupt gzip stream or out of memory while inflating " + path;
+        return -1;
+      }
+      close(closer.fd);
+      closer.fd = fd = mfd;
+    }
+  }
   struct stat sb;
   if (fstat(fd, &sb) != 0) {
     err = "cannot stat " + path;

@@ -195,9 +195,9 @@ int awry_locate_batch_into(const awry_index *index, const uint8_t *qbytes, const
 /* ------------------------------------------------------------------ streaming reads-file front-end
  * SURVEY.md 8(f) rank 4.  The reference's users parse their reads on the CPU and pass `&str`s to
  * parallel_count / parallel_locate (fm_index.rs:455-487); these entry points take the FASTQ ('@') or
- * FASTA ('>', sequences may span lines) file itself: raw chunks are uploaded from pinned memory while
- * a reader thread fetches the next ones, and the records are split on the device.  Read i of the
- * file is query i.  Results are library-owned; release each pointer with awry_buffer_free
+ * FASTA ('>', sequences may span lines) file itself, plain or gzip-compressed: raw chunks are uploaded
+ * from pinned memory while a reader thread fetches (or inflates) the next ones, and the records are split
+ * on the device.  Read i of the file is query i.  Results are library-owned; release each pointer with awry_buffer_free
  * (hits: awry_hits_free). */
 int awry_count_reads_file(const awry_index *index, const char *path, uint64_t **counts,
                           uint64_t *n_reads);

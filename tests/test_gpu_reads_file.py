@@ -120,10 +120,10 @@ def test_reads_file_errors(dev, tmp_path, monkeypatch):
     with pytest.raises(AwryError) as e:
         dev.count_reads_file(str(p))
     assert e.value.code == -3
-    p.write_bytes(b"\x1f\x8b\x08\x00garbage")
+    p.write_bytes(b"\x1f\x8b\x08\x00garbage")                      # gzip magic, corrupt stream
     with pytest.raises(AwryError) as e:
         dev.count_reads_file(str(p))
-    assert e.value.code == -6
+    assert e.value.code == -3
     p.write_bytes(b"@r1\nACGT\n+\nIIII\n@r2\nACGT\n+\n")           # truncated last record
     with pytest.raises(AwryError) as e:
         dev.count_reads_file(str(p))
@@ -143,3 +143,25 @@ def test_reads_file_errors(dev, tmp_path, monkeypatch):
     assert e.value.code == -6
     p.write_bytes(b"@r1\nACGT\n+\nIIII\n\n\n")                         # trailing blank lines are fine
     assert list(dev.count_reads_file(str(p))) == [int(dev.count_string("ACGT"))]
+
+
+@pytest.mark.parametrize("chunk", [900, 1 << 16, 64 << 20])
+def test_gzip_compressed_reads(fx, po, dna, dev, tmp_path, monkeypatch, chunk):
+    """reads.fastq.gz / reads.fa.gz: inflated by the reader thread, everything after that unchanged"""
+    import gzip
+    reads = _reads(fx, dna, 4000, seed=77)
+    wc, woff, whits = _expect(po, dna, dev, reads)
+    monkeypatch.setenv("AWRY_B200_READS_CHUNK", str(chunk))
+    for kind in ("fastq", "fasta"):
+        plain = str(tmp_path / f"r.{kind}")
+        (_write_fastq if kind == "fastq" else _write_fasta)(plain, reads)
+        gzp = plain + ".gz"
+        with open(plain, "rb") as fi, gzip.open(gzp, "wb", compresslevel=1) as fo:
+            fo.write(fi.read())
+        assert np.array_equal(dev.count_reads_file(gzp), wc)
+        off, hits = dev.locate_reads_file(gzp)
+        assert np.array_equal(off, woff) and np.array_equal(hits, whits)
+    empty = str(tmp_path / "empty.fq.gz")
+    with gzip.open(empty, "wb") as fo:
+        fo.write(b"")
+    assert len(dev.count_reads_file(empty)) == 0

@@ -47,6 +47,12 @@ for alphabet, letters in ((0, b"ACGTacgtN"), (1, b"ACDEFGHIKLMNPQRSTVWY")):
     want, wstarts = fx.concat_records([r.upper() for r in recs], alphabet)
     text, starts = f.read_sequence_file(path, alphabet)
     assert np.array_equal(np.frombuffer(text.tobytes().upper(), dtype=np.uint8), want) and np.array_equal(starts, wstarts)
+    # gzip-compressed input goes through the same parser
+    import gzip
+    with open(path, "rb") as fi, gzip.open(path + ".gz", "wb", compresslevel=1) as fo:
+        fo.write(fi.read())
+    t2, s2 = f.read_sequence_file(path + ".gz", alphabet)
+    assert np.array_equal(t2, text) and np.array_equal(s2, starts)
 print("ok")
 """ % ROOT
 
