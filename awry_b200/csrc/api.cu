@@ -947,7 +947,9 @@ void enqueue_search(const awry_index* ix, Replica& r, Workspace* ws, const uint8
   }
   {
     ProfScope p(0, r.device, ws->st);
-    CU(launch_search(r.view, ws->d_qwords - 4 * (c.b0 >> packed_unit_shift(ix->alphabet)), ws->d_qoff, nq, mode, ws->d_out, ws->d_defer, g_variant, r.sm_count, ws->st));
+    SearchVariant v = g_variant;
+    v.avg_len = uint32_t(std::min<uint64_t>(nbytes / std::max<uint64_t>(1, nq), 1u << 30));
+    CU(launch_search(r.view, ws->d_qwords - 4 * (c.b0 >> packed_unit_shift(ix->alphabet)), ws->d_qoff, nq, mode, ws->d_out, ws->d_defer, v, r.sm_count, ws->st));
   }
   CU(cudaMemcpyAsync(ws->h_flag, ws->d_flag, 8, cudaMemcpyDeviceToHost, ws->st));
 }
@@ -1466,8 +1468,10 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
         }
         {
           ProfScope p(0, r.device, st);
+          SearchVariant v = g_variant;
+          v.avg_len = uint32_t(std::min<uint64_t>(plan.seq_bytes / nq, 1u << 30));
           CU(launch_search(r.view, ws->d_qwords, d_qoff, nq, locate ? OUT_SP_CNT_U32 : OUT_COUNT_U64, ws->d_out, ws->d_defer,
-                           g_variant, r.sm_count, st));
+                           v, r.sm_count, st));
         }
         CU(cudaMemcpyAsync(ws->h_flag, ws->d_flag, 8, cudaMemcpyDeviceToHost, st));
         if (!locate) {
@@ -2166,7 +2170,9 @@ int awry_count_device(const awry_index* ix, int replica, const uint8_t* d_qbytes
     }
     {
       ProfScope p(0, r.device, st);
-      CU(launch_search(r.view, d_qwords - 4 * (ends[0] >> sh), d_qoff, nq, OUT_COUNT_U64, d_counts, d_defer, g_variant, r.sm_count, st));
+      SearchVariant v = g_variant;
+      v.avg_len = uint32_t(std::min<uint64_t>((ends[1] - ends[0]) / nq, 1u << 30));
+      CU(launch_search(r.view, d_qwords - 4 * (ends[0] >> sh), d_qoff, nq, OUT_COUNT_U64, d_counts, d_defer, v, r.sm_count, st));
     }
     CU(cudaFreeAsync(d_qwords, st));
   });
@@ -2203,7 +2209,9 @@ int awry_locate_device(const awry_index* ix, int replica, const uint8_t* d_qbyte
       }
       {
         ProfScope p(0, r.device, st);
-        CU(launch_search(r.view, ws->d_qwords - 4 * (ends[0] >> sh), d_qoff, nq, OUT_SP_CNT_U32, ws->d_out, ws->d_defer, g_variant, r.sm_count, st));
+        SearchVariant v = g_variant;
+        v.avg_len = uint32_t(std::min<uint64_t>((ends[1] - ends[0]) / nq, 1u << 30));
+        CU(launch_search(r.view, ws->d_qwords - 4 * (ends[0] >> sh), d_qoff, nq, OUT_SP_CNT_U32, ws->d_out, ws->d_defer, v, r.sm_count, st));
       }
       uint64_t n = 0;
       uint64_t* h = locate_chunk_device(ix, r, ws, nq, flags, d_hit_off, &n, st);

@@ -941,13 +941,12 @@ __device__ __forceinline__ PairSlice pair_slice(const u32x8& x, uint32_t sub, ui
   return r;
 }
 
-constexpr uint32_t PAIR_TICKET = 16;  // queries per ticket
 
 template <int MODE, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB)
     search_dna_pair_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
                            const uint64_t* __restrict__ qoff, uint64_t nq, void* __restrict__ out,
-                           uint32_t* __restrict__ defer) {
+                           uint32_t* __restrict__ defer, uint32_t ticket_sz) {
   constexpr int LANES = 4;
   constexpr uint32_t NONE = 0xffffffffu, FULL = 0xffffffffu;
   // The group's packed query is staged in shared memory (a 16-word ring = 256 symbols, refilled
@@ -959,7 +958,7 @@ __global__ void __launch_bounds__(TPB, MINB)
   const uint32_t gmask = 0xfu << gbase;
   uint64_t* const ring = s_q[threadIdx.x / LANES];
   const uint32_t nq32 = uint32_t(nq);
-  // Queries are handed out dynamically, PAIR_TICKET at a time, from a counter behind the deferred list
+  // Queries are handed out dynamically, ticket_sz at a time, from a counter behind the deferred list
   // (defer[nq + 1]): with a static stride every SM gets the same share and the kernel ends when the
   // slowest SM does -- on B200 the SMs do not all see the same random-access throughput (the gather
   // probe's SMs are busy between 52 % and 100 % of the time under a static split).
@@ -980,11 +979,11 @@ __global__ void __launch_bounds__(TPB, MINB)
       left = 0;
       if (q == q_end && more) {
         uint32_t t = 0;
-        if (sub == 0) t = atomicAdd(ticket, PAIR_TICKET);
+        if (sub == 0) t = atomicAdd(ticket, ticket_sz);
         t = __shfl_sync(gmask, t, gbase);
         more = t < nq32;
         q = more ? t : 0u;
-        q_end = more ? (nq32 - t < PAIR_TICKET ? nq32 : t + PAIR_TICKET) : 0u;
+        q_end = more ? (nq32 - t < ticket_sz ? nq32 : t + ticket_sz) : 0u;
       }
       if (q < q_end) {
         cur = q++;
@@ -1110,7 +1109,7 @@ __global__ void __launch_bounds__(TPB, MINB)
 template <int MODE, int MINB>
 static cudaError_t launch_search_pair_b(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
                                         uint64_t nq, void* d_out, uint32_t* d_defer, int force_per_sm,
-                                        int sm_count, cudaStream_t s) {
+                                        int sm_count, cudaStream_t s, uint32_t avg_len) {
   constexpr int TPB = 256;
   auto kern = search_dna_pair_kernel<MODE, TPB, MINB>;
   int per_sm = 0;
@@ -1121,7 +1120,12 @@ static cudaError_t launch_search_pair_b(const IndexView& ix, const uint64_t* d_q
   uint64_t max_blocks = uint64_t(sm_count) * uint64_t(per_sm);
   uint64_t need_blocks = (nq * 4 + TPB - 1) / TPB;
   unsigned grid = unsigned(std::max<uint64_t>(1, std::min(max_blocks, need_blocks)));
-  e = launch_with_table_window(kern, grid, TPB, s, ix, ix, d_qwords, d_qoff, nq, d_out, d_defer);
+  static const uint32_t ticket_env = [] {  // AWRY_B200_TICKET: fixed ticket size (experiments)
+    if (const char* e = getenv("AWRY_B200_TICKET")) return uint32_t(std::min(1024l, std::max(1l, strtol(e, nullptr, 10))));
+    return 0u;
+  }();
+  const uint32_t ticket_sz = ticket_env ? ticket_env : ticket_size(avg_len);
+  e = launch_with_table_window(kern, grid, TPB, s, ix, ix, d_qwords, d_qoff, nq, d_out, d_defer, ticket_sz);
   COUNT_LAUNCH();
   if (e != cudaSuccess) return e;
   // queries with ambiguity symbols: scalar kernel over the deferred list (empty for clean batches)
@@ -1140,11 +1144,11 @@ static cudaError_t launch_search_pair(const IndexView& ix, const uint64_t* d_qwo
   e = cudaMemsetAsync(d_defer + nq + 1, 0, 4, s);                     // ticket counter
   if (e != cudaSuccess) return e;
   switch (v.blocks_per_sm) {
-    case 4: return launch_search_pair_b<MODE, 4>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s);
+    case 4: return launch_search_pair_b<MODE, 4>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len);
     case 0:  // full residency (8 x 256 threads, 32 registers) measured best once the hand-out is dynamic
-    case 8: return launch_search_pair_b<MODE, 8>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s);
-    case 6: return launch_search_pair_b<MODE, 6>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s);
-    default: return launch_search_pair_b<MODE, 4>(ix, d_qwords, d_qoff, nq, d_out, d_defer, v.blocks_per_sm, sm_count, s);
+    case 8: return launch_search_pair_b<MODE, 8>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len);
+    case 6: return launch_search_pair_b<MODE, 6>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len);
+    default: return launch_search_pair_b<MODE, 4>(ix, d_qwords, d_qoff, nq, d_out, d_defer, v.blocks_per_sm, sm_count, s, v.avg_len);
   }
 }
 
@@ -1171,7 +1175,7 @@ template <int MODE, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB)
     search_amino_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
                         const uint64_t* __restrict__ qoff, uint64_t nq, void* __restrict__ out,
-                        uint32_t* __restrict__ ticket) {
+                        uint32_t* __restrict__ ticket, uint32_t ticket_sz) {
   constexpr int LANES = 4;
   constexpr uint32_t NONE = 0xffffffffu, FULL = 0xffffffffu;
   __shared__ uint64_t s_q[TPB / LANES][16];  // 128 symbols
@@ -1180,7 +1184,7 @@ __global__ void __launch_bounds__(TPB, MINB)
   const uint32_t gmask = 0xfu << gbase;
   uint64_t* const ring = s_q[threadIdx.x / LANES];
   const uint32_t nq32 = uint32_t(nq);
-  uint32_t q = 0, q_end = 0;  // dynamic hand-out of PAIR_TICKET queries at a time (see the pair kernel)
+  uint32_t q = 0, q_end = 0;  // dynamic hand-out of ticket_sz queries at a time (see the pair kernel)
   bool more = true;
   uint32_t cur = NONE;
   uint32_t sp = 1, ep = 0, left = 0, len = 0;
@@ -1193,11 +1197,11 @@ __global__ void __launch_bounds__(TPB, MINB)
       left = 0;
       if (q == q_end && more) {
         uint32_t t = 0;
-        if (sub == 0) t = atomicAdd(ticket, PAIR_TICKET);
+        if (sub == 0) t = atomicAdd(ticket, ticket_sz);
         t = __shfl_sync(gmask, t, gbase);
         more = t < nq32;
         q = more ? t : 0u;
-        q_end = more ? (nq32 - t < PAIR_TICKET ? nq32 : t + PAIR_TICKET) : 0u;
+        q_end = more ? (nq32 - t < ticket_sz ? nq32 : t + ticket_sz) : 0u;
       }
       if (q < q_end) {
         cur = q++;
@@ -1314,7 +1318,7 @@ static cudaError_t launch_search_amino(const IndexView& ix, const uint64_t* d_qw
   uint64_t max_blocks = uint64_t(sm_count) * uint64_t(per_sm);
   uint64_t need_blocks = (nq * 4 + TPB - 1) / TPB;
   unsigned grid = unsigned(std::max<uint64_t>(1, std::min(max_blocks, need_blocks)));
-  e = launch_with_table_window(kern, grid, TPB, s, ix, ix, d_qwords, d_qoff, nq, d_out, d_ticket);
+  e = launch_with_table_window(kern, grid, TPB, s, ix, ix, d_qwords, d_qoff, nq, d_out, d_ticket, ticket_size(v.avg_len));
   COUNT_LAUNCH();
   return e;
 }
@@ -1440,7 +1444,7 @@ __device__ __forceinline__ void finish_hit(const IndexView& ix, uint32_t row, ui
 // compressed_suffix_array.rs:109-111) do not idle the rest of the warp.  The lane holding the row's
 // chunk extracts the BWT symbol and broadcasts it; both lanes rank their two chunks; xor-shuffle.
 // Warp-convergent loop (exit by vote) so the shuffles use the full mask.
-constexpr uint64_t WALK_TICKET = 32;  // hits per ticket
+constexpr uint64_t WALK_TICKET = 32;  // hits per ticket (8 measured slower: 3.6 vs 2.5 ms per 10 M hits)
 
 template <bool MAP>
 __global__ void __launch_bounds__(256) walk_dna_kernel(IndexView ix, uint64_t n_hits, uint64_t* __restrict__ out) {

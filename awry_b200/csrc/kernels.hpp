@@ -23,7 +23,17 @@ struct SearchVariant {
                           // kernel (default when the pair index exists); -1 = scalar kernel
   int tpb = 0;            // threads per block
   int blocks_per_sm = 0;  // 0 = occupancy-derived
+  uint32_t avg_len = 0;   // mean query length of the batch (0 = unknown): sizes the tickets of the dynamic hand-out
 };
+
+// queries per ticket: about one 150-bp query's worth of LF steps, so that the last tickets do not leave
+// most lane groups idle (ticket 16 -> 1 on 150-bp reads: 17.6 -> 16.3 ms), while short queries still
+// share an atomic (12-residue peptides: 16 per ticket)
+inline uint32_t ticket_size(uint32_t avg_len) {
+  if (avg_len == 0) return 4;
+  uint32_t t = 200 / avg_len;
+  return t < 1 ? 1u : t > 16 ? 16u : t;
+}
 
 struct LaunchCounters {
   uint64_t launches = 0;
