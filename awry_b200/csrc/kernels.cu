@@ -1447,19 +1447,24 @@ __device__ __forceinline__ void finish_hit(const IndexView& ix, uint32_t row, ui
 constexpr uint64_t WALK_TICKET = 32;  // hits per ticket (8 measured slower: 3.6 vs 2.5 ms per 10 M hits)
 
 template <bool MAP>
-__global__ void __launch_bounds__(256) walk_dna_kernel(IndexView ix, uint64_t n_hits, uint64_t* __restrict__ out) {
+__global__ void __launch_bounds__(256) walk_dna_kernel(IndexView ix, uint64_t n_hits, uint64_t* __restrict__ out, bool dynamic) {
   constexpr int SLOT = MAP ? 2 : 1;
   constexpr uint32_t FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31, sub = lane & 1, gbase = lane - sub;
   // hits are handed out dynamically, WALK_TICKET at a time; the counter sits behind the output slots
   unsigned long long* const ticket = reinterpret_cast<unsigned long long*>(out + SLOT * n_hits);
-  uint64_t h = 0, h_end = 0;
-  bool more = true;
+  // small batches: a static stride keeps every group busy from the start (a ticket of 32 hits would feed
+  // only n_hits / 32 groups, and smaller tickets serialise on the counter: same-address atomics retire at
+  // ~0.35 G/s); large batches: tickets, so that the fast SMs take more
+  const uint64_t stride = (gridDim.x * uint64_t(blockDim.x)) >> 1;
+  uint64_t h = dynamic ? 0 : (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 1, h_end = dynamic ? 0 : n_hits;
+  const uint64_t step = dynamic ? 1 : stride;
+  bool more = dynamic;
   uint64_t cur = 0;
   uint32_t row = 0, steps = 0;
   bool have = false;
   for (;;) {
-    if (!have && h == h_end && more) {
+    if (!have && h >= h_end && more) {
       unsigned long long t = 0;
       if (sub == 0) t = atomicAdd(ticket, (unsigned long long)WALK_TICKET);
       t = __shfl_sync(0x3u << gbase, t, gbase);
@@ -1468,12 +1473,13 @@ __global__ void __launch_bounds__(256) walk_dna_kernel(IndexView ix, uint64_t n_
       h_end = more ? (n_hits - t < WALK_TICKET ? n_hits : t + WALK_TICKET) : 0;
     }
     if (!have && h < h_end) {
-      cur = h++;
+      cur = h;
+      h += step;
       row = uint32_t(out[SLOT * cur]);
       steps = 0;
       have = true;
     }
-    if (__all_sync(FULL, !have && !more && h == h_end)) break;
+    if (__all_sync(FULL, !have && !more && h >= h_end)) break;
     if (have && row_is_sampled(ix, row)) {
       if (sub == 0) finish_hit(ix, row, steps, out + SLOT * cur, MAP);
       have = false;
@@ -1504,18 +1510,20 @@ __global__ void __launch_bounds__(256) walk_dna_kernel(IndexView ix, uint64_t n_
 // Pass 2b, amino: 4 lanes per hit on the 128-B block (one line request per LF step); the lane that
 // holds the row's 32-row slice extracts the symbol index from its 5 planes and broadcasts it.
 template <bool MAP>
-__global__ void __launch_bounds__(256) walk_amino_kernel(IndexView ix, uint64_t n_hits, uint64_t* __restrict__ out) {
+__global__ void __launch_bounds__(256) walk_amino_kernel(IndexView ix, uint64_t n_hits, uint64_t* __restrict__ out, bool dynamic) {
   constexpr int SLOT = MAP ? 2 : 1;
   constexpr uint32_t FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31, sub = lane & 3, gbase = lane - sub;
   unsigned long long* const ticket = reinterpret_cast<unsigned long long*>(out + SLOT * n_hits);
-  uint64_t h = 0, h_end = 0;
-  bool more = true;
+  const uint64_t stride = (gridDim.x * uint64_t(blockDim.x)) >> 2;
+  uint64_t h = dynamic ? 0 : (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 2, h_end = dynamic ? 0 : n_hits;
+  const uint64_t step = dynamic ? 1 : stride;
+  bool more = dynamic;
   uint64_t cur = 0;
   uint32_t row = 0, steps = 0;
   bool have = false;
   for (;;) {
-    if (!have && h == h_end && more) {
+    if (!have && h >= h_end && more) {
       unsigned long long t = 0;
       if (sub == 0) t = atomicAdd(ticket, (unsigned long long)WALK_TICKET);
       t = __shfl_sync(0xfu << gbase, t, gbase);
@@ -1524,12 +1532,13 @@ __global__ void __launch_bounds__(256) walk_amino_kernel(IndexView ix, uint64_t 
       h_end = more ? (n_hits - t < WALK_TICKET ? n_hits : t + WALK_TICKET) : 0;
     }
     if (!have && h < h_end) {
-      cur = h++;
+      cur = h;
+      h += step;
       row = uint32_t(out[SLOT * cur]);
       steps = 0;
       have = true;
     }
-    if (__all_sync(FULL, !have && !more && h == h_end)) break;
+    if (__all_sync(FULL, !have && !more && h >= h_end)) break;
     if (have && row_is_sampled(ix, row)) {
       if (sub == 0) finish_hit(ix, row, steps, out + SLOT * cur, MAP);
       have = false;
@@ -1771,16 +1780,18 @@ cudaError_t launch_walk(const IndexView& ix, const uint2* d_sp_cnt, const uint64
   }
   if (ix.alphabet == 0) {
     unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (2 * n_hits + 255) / 256)));
+    const bool dynamic = n_hits >= 64 * ((uint64_t(grid) * 256) >> 1);
     if (map)
-      walk_dna_kernel<true><<<grid, 256, 0, s>>>(ix, n_hits, out);
+      walk_dna_kernel<true><<<grid, 256, 0, s>>>(ix, n_hits, out, dynamic);
     else
-      walk_dna_kernel<false><<<grid, 256, 0, s>>>(ix, n_hits, out);
+      walk_dna_kernel<false><<<grid, 256, 0, s>>>(ix, n_hits, out, dynamic);
   } else {
     unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (4 * n_hits + 255) / 256)));
+    const bool dynamic = n_hits >= 64 * ((uint64_t(grid) * 256) >> 2);
     if (map)
-      walk_amino_kernel<true><<<grid, 256, 0, s>>>(ix, n_hits, out);
+      walk_amino_kernel<true><<<grid, 256, 0, s>>>(ix, n_hits, out, dynamic);
     else
-      walk_amino_kernel<false><<<grid, 256, 0, s>>>(ix, n_hits, out);
+      walk_amino_kernel<false><<<grid, 256, 0, s>>>(ix, n_hits, out, dynamic);
   }
   COUNT_LAUNCH();
   return cudaGetLastError();

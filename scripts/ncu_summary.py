@@ -14,7 +14,7 @@ from collections import OrderedDict
 
 def short(name):
     name = re.sub(r"\(.*", "", name)
-    name = name.replace("void ", "").replace("awry::", "").replace("<unnamed>::", "fixture::")
+    name = name.replace("void ", "").replace("awry::", "").replace("<unnamed>::", "anon::")
     return re.sub(r"cub::CUB_\d+_SM_\d+::", "cub::", name)[:90]
 
 
@@ -38,9 +38,9 @@ def launches(src, dst):
         f.write("| kernel | launches | total ms | share | mean ms |\n|---|---:|---:|---:|---:|\n")
         for k, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k}` | {n} | {ns/1e6:.3f} | {100*ns/total:.1f}% | {ns/n/1e6:.3f} |\n")
-        f.write("\n## product kernels in launch order (fixture-builder and cub kernels omitted)\n\n| # | kernel | ms | grid | block |\n|---|---|---:|---|---|\n")
+        f.write("\n## product kernels in launch order (`anon::` = anonymous-namespace kernels of build.cu / reads.cu; cub and torch kernels and the synthetic-data generators omitted)\n\n| # | kernel | ms | grid | block |\n|---|---|---:|---|---|\n")
         for i, (k, ns, g, b) in enumerate(seq):
-            if not k.startswith(("fixture::", "cub::", "at::", "void at")):
+            if not k.startswith(("cub::", "at::", "void at")) and "gen_queries" not in k and "gen_text" not in k:
                 f.write(f"| {i} | `{k}` | {ns/1e6:.3f} | {g} | {b} |\n")
     print("wrote", dst)
 
