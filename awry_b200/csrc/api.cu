@@ -163,6 +163,7 @@ struct Workspace {
   uint8_t* h_out = nullptr;
   size_t h_out_cap = 0;  // bytes
   unsigned long long* h_flag = nullptr;
+  unsigned long long* h_total = nullptr;  // hit total of a locate chunk (second word of the h_flag allocation)
   uint64_t* h_exc = nullptr;  // host-packed chunks: exception list (bytes outside ACGT)
   size_t h_exc_cap = 0;
   std::vector<uint64_t> exc_tmp;
@@ -240,7 +241,8 @@ struct Workspace {
     device = dev;
     CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
-    CU(cudaHostAlloc(reinterpret_cast<void**>(&h_flag), sizeof(unsigned long long), cudaHostAllocDefault));
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&h_flag), 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+    h_total = h_flag + 1;
     CU(cudaMalloc(reinterpret_cast<void**>(&d_flag), sizeof(unsigned long long)));
   }
   void destroy() {
@@ -1081,6 +1083,15 @@ struct LocatePart {
   uint64_t* ext_off = nullptr;    // caller-owned CSR offsets to fill directly (single replica)
 };
 
+// CSR offsets of a searched chunk (ws->d_out holds (sp, count) per query), no synchronisation
+void locate_chunk_scan(Workspace* ws, uint64_t nq, uint64_t* d_hit_off, cudaStream_t st) {
+  const uint2* d_sp_cnt = reinterpret_cast<const uint2*>(ws->d_out);
+  size_t temp = 0;
+  CU(scan_hit_offsets(d_sp_cnt, nq, d_hit_off, nullptr, temp, st));
+  Workspace::grow_dev(reinterpret_cast<uint8_t*&>(ws->d_temp), ws->d_temp_cap, temp + 16);
+  CU(scan_hit_offsets(d_sp_cnt, nq, d_hit_off, ws->d_temp, temp, st));
+}
+
 // device-side two-pass locate of a chunk whose queries were already searched (ws->d_out holds
 // (sp, count) per query).  Step 1: CSR offsets + hit total (one synchronisation).
 uint64_t locate_chunk_count(Replica& r, Workspace* ws, uint64_t nq, uint64_t* d_hit_off, cudaStream_t st) {
@@ -1140,6 +1151,13 @@ uint64_t* locate_chunk_device(const awry_index* ix, Replica& r, Workspace* ws, u
   return locate_chunk_walk(r, ws, nq, *n_hits_out, flags, d_hit_off, st);
 }
 
+// parallel_locate over [q_lo, q_hi) on one replica.  The two passes of a chunk are separated by one small
+// device->host read (the hit total sizes pass 2), so chunks are kept small (256 k queries) and three are
+// in flight: while the host waits for chunk i's total, chunk i+1 is being packed, copied and searched,
+// and chunk i-1's hits are on their way back.
+constexpr uint64_t LOCATE_CHUNK_Q = 1u << 18;
+constexpr uint64_t LOCATE_CHUNK_BYTES = 32u << 20;
+
 void locate_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, const uint64_t* qoff,
                        uint64_t q_lo, uint64_t q_hi, uint32_t flags, LocatePart& part) {
   const bool ext = part.ext_cap != 0 || part.ext_off != nullptr;
@@ -1148,48 +1166,106 @@ void locate_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
   if (q_lo >= q_hi) return;
   DeviceGuard dg(r.device);
   const bool src_pinned = is_pinned(qbytes) && is_pinned(qoff);
-  auto chunks = make_chunks(qoff, q_lo, q_hi, CHUNK_MAX_Q, chunk_max_bytes());
-  Workspace* ws = r.acquire();
+  auto chunks = make_chunks(qoff, q_lo, q_hi, LOCATE_CHUNK_Q, std::min(chunk_max_bytes(), LOCATE_CHUNK_BYTES));
+  constexpr int DEPTH = 3;
+  struct Slot {
+    Workspace* ws = nullptr;
+    int chunk = -1;
+    int phase = 0;  // 1 = searched + scanned (total on its way), 2 = pass 2 enqueued (results on their way)
+    uint64_t base = 0;
+  } slot[DEPTH];
   size_t cap = 0;
-  try {
-    for (const Chunk& c : chunks) {
-      uint64_t nq = c.q1 - c.q0;
-      enqueue_search(ix, r, ws, qbytes, qoff, c, OUT_SP_CNT_U32, src_pinned);
-      Workspace::grow_dev(ws->d_hit_off, ws->d_hit_off_cap, size_t(nq) + 1);
-      uint64_t n_hits = locate_chunk_count(r, ws, nq, ws->d_hit_off, ws->st);
-      check_flag(ws, c);
-      // offsets of this chunk, rebased onto the replica-local hit count so far
-      uint64_t* dst_off = off_base + (c.q0 - q_lo);
-      CU(cudaMemcpyAsync(dst_off, ws->d_hit_off, (nq + 1) * 8, cudaMemcpyDeviceToHost, ws->st));
-      const bool fits = !ext || part.n_hits + n_hits <= part.ext_cap;
-      if (n_hits && fits) {
-        uint64_t* d_hits = locate_chunk_walk(r, ws, nq, n_hits, flags, ws->d_hit_off, ws->st);
-        if (!ext && part.n_hits + n_hits > cap) {
-          cap = std::max<size_t>(size_t(part.n_hits + n_hits), cap * 2);
-          void* np = realloc(part.hits, cap * sizeof(awry_hit));
-          if (!np) {
-            cudaFreeAsync(d_hits, ws->st);
-            fail(AWRY_ERR_NOMEM, "out of host memory for %llu hits", (unsigned long long)cap);
-          }
-          part.hits = static_cast<awry_hit*>(np);
-        }
-        CU(cudaMemcpyAsync(part.hits + part.n_hits, d_hits, n_hits * 16, cudaMemcpyDeviceToHost, ws->st));
-        cudaFreeAsync(d_hits, ws->st);
-        g_prof.d2h += n_hits * 16;
+  static const bool trace = getenv("AWRY_B200_TRACE") != nullptr;  // host-side stage times on stderr
+  const auto t_origin = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what, int i) {
+    if (trace)
+      fprintf(stderr, "[locate] %8.3f ms  %s %d\n",
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_origin).count(), what, i);
+  };
+  // offsets of a chunk are rebased onto the replica-local hit count before it; the slot shared with the
+  // next chunk (index nq) is written by that chunk, the very last one after the loop
+  auto stage_c = [&](Slot& s) {
+    if (s.phase != 2) return;
+    const Chunk& c = chunks[size_t(s.chunk)];
+    CU(cudaEventSynchronize(s.ws->done));
+    uint64_t* dst_off = off_base + (c.q0 - q_lo);
+    const uint64_t nq = c.q1 - c.q0, base = s.base;
+    if (base)
+      for (uint64_t i = 0; i < nq; i++) dst_off[i] += base;
+    s.phase = 0;
+    s.chunk = -1;
+  };
+  auto stage_a = [&](int i) {
+    Slot& s = slot[i % DEPTH];
+    if (!s.ws) s.ws = r.acquire();
+    stage_c(s);
+    Workspace* ws = s.ws;
+    const Chunk& c = chunks[size_t(i)];
+    const uint64_t nq = c.q1 - c.q0;
+    mark("A begin", i);
+    enqueue_search(ix, r, ws, qbytes, qoff, c, OUT_SP_CNT_U32, src_pinned);
+    mark("A searched", i);
+    Workspace::grow_dev(ws->d_hit_off, ws->d_hit_off_cap, size_t(nq) + 1);
+    locate_chunk_scan(ws, nq, ws->d_hit_off, ws->st);
+    CU(cudaMemcpyAsync(ws->h_total, ws->d_hit_off + nq, 8, cudaMemcpyDeviceToHost, ws->st));
+    CU(cudaEventRecord(ws->done, ws->st));
+    mark("A end", i);
+    s.chunk = i;
+    s.phase = 1;
+  };
+  auto stage_b = [&](int i) {
+    Slot& s = slot[i % DEPTH];
+    Workspace* ws = s.ws;
+    const Chunk& c = chunks[size_t(i)];
+    const uint64_t nq = c.q1 - c.q0;
+    mark("B wait", i);
+    CU(cudaEventSynchronize(ws->done));
+    mark("B total known", i);
+    const uint64_t n_hits = *ws->h_total;
+    check_flag(ws, c);
+    s.base = part.n_hits;
+    CU(cudaMemcpyAsync(off_base + (c.q0 - q_lo), ws->d_hit_off, nq * 8, cudaMemcpyDeviceToHost, ws->st));
+    g_prof.d2h += nq * 8;
+    const bool fits = !ext || part.n_hits + n_hits <= part.ext_cap;
+    if (n_hits && fits) {
+      if (!ext && part.n_hits + n_hits > cap) {
+        for (auto& o : slot) stage_c(o);  // copies into the old buffer must land before it moves
+        cap = std::max<size_t>(size_t(part.n_hits + n_hits), cap * 2);
+        void* np = realloc(part.hits, cap * sizeof(awry_hit));
+        if (!np) fail(AWRY_ERR_NOMEM, "out of host memory for %llu hits", (unsigned long long)cap);
+        part.hits = static_cast<awry_hit*>(np);
       }
-      CU(cudaStreamSynchronize(ws->st));
-      g_prof.d2h += (nq + 1) * 8;
-      for (uint64_t i = 0; i <= nq; i++) dst_off[i] += part.n_hits;
-      part.n_hits += n_hits;  // keeps counting past the capacity so the caller learns the need
+      uint64_t* d_hits = locate_chunk_walk(r, ws, nq, n_hits, flags, ws->d_hit_off, ws->st);
+      CU(cudaMemcpyAsync(part.hits + part.n_hits, d_hits, n_hits * 16, cudaMemcpyDeviceToHost, ws->st));
+      cudaFreeAsync(d_hits, ws->st);
+      g_prof.d2h += n_hits * 16;
     }
+    CU(cudaEventRecord(ws->done, ws->st));
+    mark("B end", i);
+    s.phase = 2;
+    part.n_hits += n_hits;  // keeps counting past the capacity so the caller learns the need
+  };
+  try {
+    stage_a(0);
+    for (int i = 0; i < int(chunks.size()); i++) {
+      if (i + 1 < int(chunks.size())) stage_a(i + 1);
+      stage_b(i);
+    }
+    for (auto& s : slot) stage_c(s);
+    off_base[q_hi - q_lo] = part.n_hits;
+    mark("done", int(chunks.size()));
   } catch (...) {
-    cudaStreamSynchronize(ws->st);
-    r.release(ws);
+    for (auto& s : slot)
+      if (s.ws) {
+        cudaStreamSynchronize(s.ws->st);
+        r.release(s.ws);
+      }
     if (!ext) free(part.hits);
     part.hits = nullptr;
     throw;
   }
-  r.release(ws);
+  for (auto& s : slot)
+    if (s.ws) r.release(s.ws);
 }
 
 // ------------------------------------------------------------------ streaming reads-file front-end

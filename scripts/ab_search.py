@@ -15,6 +15,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--variants", default="8:0,9:0,8:4,9:4")
     ap.add_argument("--reps", type=int, default=6)
+    ap.add_argument("--burst", type=int, default=1, help="launches back to back per measurement (sustained clocks)")
     ap.add_argument("--n", type=int, default=3_100_000_000)
     ap.add_argument("--nq", type=int, default=10_000_000)
     ap.add_argument("--qlen", type=int, default=150)
@@ -36,9 +37,10 @@ def main():
         for v in variants:
             f.set_search_variant(v[0], 0, v[1])
             f.profile_reset()
-            ix.count_device(d_q.data_ptr(), d_off.data_ptr(), a.nq, d_cnt.data_ptr(), st)
+            for _ in range(a.burst):
+                ix.count_device(d_q.data_ptr(), d_off.data_ptr(), a.nq, d_cnt.data_ptr(), st)
             torch.cuda.synchronize()
-            times[v].append(f.profile_get()["search_ms"])
+            times[v].append(f.profile_get()["search_ms"] / a.burst)
             s = int(d_cnt.sum())
             ref = s if ref is None else ref
             assert s == ref, "variants disagree"
