@@ -2082,6 +2082,11 @@ cudaError_t run_random_gather(uint64_t footprint_bytes, uint32_t granule, uint32
     if (un == 4) e = gather_run<128, 4, 4>(buf, n_granules, n_reads, iters, sink, &ms, 8 * waves);
     if (un == 8) e = gather_run<128, 4, 8>(buf, n_granules, n_reads, iters, sink, &ms, 8 * waves);
   }
+  // lanes = 4000 + waves / 5000 + waves: the same with 2 lanes x 2 LDG.256 / 1 lane x 4 LDG.256 per read
+  if (granule == 128 && lanes >= 4000 && lanes < 5000)
+    e = gather_run<128, 2, 4>(buf, n_granules, n_reads, iters, sink, &ms, 8 * int(lanes - 4000));
+  if (granule == 128 && lanes >= 5000 && lanes < 6000)
+    e = gather_run<128, 1, 4>(buf, n_granules, n_reads, iters, sink, &ms, 8 * int(lanes - 5000));
   // lanes = 201 / 202: one thread per read through cp.async.bulk + mbarrier, 1 / 2 reads in flight per thread
   if (granule == 128 && lanes == 201) e = gather_tma_run<1>(buf, n_granules, n_reads, iters, sink, &ms);
   if (granule == 128 && lanes == 202) e = gather_tma_run<2>(buf, n_granules, n_reads, iters, sink, &ms);
