@@ -1145,8 +1145,11 @@ static cudaError_t launch_search_pair(const IndexView& ix, const uint64_t* d_qwo
   if (e != cudaSuccess) return e;
   switch (v.blocks_per_sm) {
     case 4: return launch_search_pair_b<MODE, 4>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len);
-    case 0:  // full residency (8 x 256 threads, 32 registers) measured best once the hand-out is dynamic
+    // 8 x 256 threads/SM (32 registers) is fastest for an isolated launch (16.2 vs 16.6-17.0 ms), 6 x 256
+    // (40 registers) for launches back to back, where the part sits at its power cap (18.1 vs 18.7 ms,
+    // profiles/r01_s31_sustained_ab.log): batches arrive back to back in production, so 6 is the default
     case 8: return launch_search_pair_b<MODE, 8>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len);
+    case 0:
     case 6: return launch_search_pair_b<MODE, 6>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len);
     default: return launch_search_pair_b<MODE, 4>(ix, d_qwords, d_qoff, nq, d_out, d_defer, v.blocks_per_sm, sm_count, s, v.avg_len);
   }
