@@ -176,3 +176,39 @@ def test_build_errors(tmp_path):
     empty.write_text(">only a header\n")
     with pytest.raises(AwryError):
         f.build_index_file(str(empty), str(tmp_path / "o.awry"))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_sequence_files_build_byte_identical(fx, tmp_path, monkeypatch, seed):
+    """random multi-record FASTA files (both alphabets, ambiguity letters, repeats, tiny and empty-ish records,
+    host fix-up and forced GPU prefix doubling, multi-threaded FASTA parse) -> same `.awry` bytes as the CPU
+    restatement of FmIndex::new + save"""
+    from awry_b200 import fm_index as f
+    rng = np.random.default_rng(500 + seed)
+    alphabet = seed % 2
+    letters = b"ACGT" if alphabet == 0 else b"ACDEFGHIKLMNPQRSTVWY"
+    amb = b"NRYKM" if alphabet == 0 else b"XBZJ"
+    recs = []
+    for _ in range(int(rng.integers(1, 7))):
+        ln = int(rng.choice([1, 2, 5, 64, 255, 256, 257, 3000, 20000]))
+        r = bytearray(np.frombuffer(letters, dtype=np.uint8)[rng.integers(0, len(letters), ln)].tobytes())
+        if ln > 500 and rng.random() < 0.6:                      # tandem repeat: long ties
+            unit = bytes(r[:int(rng.integers(1, 40))])
+            reps = int(rng.integers(5, 60))
+            r[100:100 + len(unit) * reps] = (unit * reps)[: max(0, min(len(r) - 100, len(unit) * reps))]
+        for _ in range(int(rng.integers(0, 4))):
+            r[int(rng.integers(0, len(r)))] = amb[int(rng.integers(0, len(amb)))]
+        recs.append(bytes(r).decode())
+    headers = [f"r{i} seed {seed}" for i in range(len(recs))]
+    src = str(tmp_path / "in.fa")
+    _write_fasta(src, recs, headers, width=int(rng.integers(1, 100)), lower_every=2 if seed % 3 == 0 else 0)
+    ratio, k = int(rng.choice([1, 3, 8, 32])), int(rng.integers(1, 7 if alphabet == 0 else 4))
+    text, starts = fx.concat_records(recs, alphabet)
+    want = fx.build_parts(text, alphabet, ratio=ratio, kmer_len=k, seq_starts=starts, headers=headers)
+    want_path = want.write(str(tmp_path / "want.awry"))
+    if seed % 2 == 0:
+        monkeypatch.setenv("AWRY_B200_BUILD_HOST_FIXUP_MAX", "0")      # GPU prefix doubling for every tie
+    monkeypatch.setenv("AWRY_B200_FASTA_RANGE_BYTES", "300")           # several parser threads on a small file
+    got_path = f.build_index_file(src, str(tmp_path / "got.awry"), alphabet, suffix_array_compression_ratio=ratio,
+                                  lookup_table_kmer_len=k)
+    assert open(got_path, "rb").read() == open(want_path, "rb").read()
