@@ -339,6 +339,15 @@ uint64_t ipow(uint64_t b, uint32_t e) {
   return r;
 }
 
+// threads of a parallel positional read (AWRY_B200_IO_THREADS, default min(8, cores))
+unsigned io_threads() {
+  static const unsigned v = [] {
+    if (const char* e = getenv("AWRY_B200_IO_THREADS")) return unsigned(std::min(64l, std::max(1l, strtol(e, nullptr, 10))));
+    return std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+  }();
+  return v;
+}
+
 // sequential byte source: a file (FmIndex::load) or caller memory sections (FmIndex::new hand-over)
 struct Source {
   FILE* f = nullptr;
@@ -355,7 +364,7 @@ struct Source {
         // copying out of the page cache tops out at a few GB/s, far below the PCIe rate behind it
         off_t pos = ftello(f);
         int fd = fileno(f);
-        unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+        unsigned nt = io_threads();
         size_t per = ((n + nt - 1) / nt + 4095) & ~size_t(4095);
         std::vector<std::thread> th;
         std::vector<int> ok(nt, 1);
@@ -1284,7 +1293,7 @@ struct ReadsOut {
 };
 
 void parallel_pread(int fd, void* dst, size_t n, off_t pos, const char* what) {
-  unsigned nt = n >= (4u << 20) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+  unsigned nt = n >= (4u << 20) ? io_threads() : 1u;
   size_t per = ((n + nt - 1) / nt + 4095) & ~size_t(4095);
   std::vector<int> ok(nt, 1);
   auto work = [&](unsigned t) {
