@@ -1,0 +1,233 @@
+// build_api.cu -- entry points of the GPU index construction (device side and file reader: build.cu):
+// FmIndex::new (/root/reference/src/fm_index.rs:142-268) and FmIndex::save (fm_index_file.rs:42-106).
+#include "host.hpp"
+
+using namespace awry;
+using namespace awry::host;
+
+extern "C" {
+
+uint64_t awry_parts_num_blocks(uint64_t bwt_len) { return (bwt_len + 255) / 256; }
+
+uint64_t awry_parts_block_words(uint32_t alphabet) { return alphabet == AWRY_NUCLEOTIDE ? 20 : 44; }
+
+uint64_t awry_parts_sa_words(uint64_t bwt_len, uint64_t sa_ratio) {
+  return bwt_len >= 2 && sa_ratio ? sa_word_len(bwt_len, sa_ratio) : 0;
+}
+
+int awry_build_parts(uint32_t alphabet, const uint8_t* text, uint64_t n, uint64_t sa_ratio, int device,
+                     uint64_t* blocks, uint64_t* prefix_sums, uint64_t* sa_words, double* phase_seconds) {
+  return guarded([&] {
+    if (!text || !blocks || !prefix_sums || !sa_words) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    if (alphabet > 1) fail(AWRY_ERR_INVALID_ARG, "invalid alphabet id %u", alphabet);
+    if (n + 1 >= (1ull << 32) - 256) fail(AWRY_ERR_UNSUPPORTED, "text of %llu symbols: 32-bit row pointers", (unsigned long long)n);
+    pick_devices(&device, 1);
+    std::string err;
+    if (build_parts(int(alphabet), text, n, sa_ratio ? sa_ratio : 8, device, blocks, prefix_sums, sa_words,
+                    phase_seconds, err) != 0)
+      fail(AWRY_ERR_CUDA, "index construction failed: %s", err.c_str());
+  });
+}
+
+int awry_read_sequence_file(const char* path, uint32_t alphabet, uint8_t** text, uint64_t* n_text, uint64_t** starts,
+                            uint64_t* n_records) {
+  return guarded([&] {
+    if (!path || !text || !n_text || !starts || !n_records) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    if (alphabet > 1) fail(AWRY_ERR_INVALID_ARG, "invalid alphabet id %u", alphabet);
+    *text = nullptr;
+    *starts = nullptr;
+    *n_text = *n_records = 0;
+    TextBuf t;
+    std::string err;
+    std::vector<uint64_t> st;
+    std::vector<std::string> hd;
+    if (read_sequence_file(path, alphabet == 0 ? 'N' : 'X', t, st, hd, err) != 0) fail(AWRY_ERR_IO, "%s", err.c_str());
+    uint8_t* tb = static_cast<uint8_t*>(malloc(t.size() + 1));
+    uint64_t* sb = static_cast<uint64_t*>(malloc(st.size() * 8 + 8));
+    if (!tb || !sb) {
+      free(tb);
+      free(sb);
+      fail(AWRY_ERR_NOMEM, "out of host memory");
+    }
+    memcpy(tb, t.data(), t.size());
+    memcpy(sb, st.data(), st.size() * 8);
+    *text = tb;
+    *n_text = t.size();
+    *starts = sb;
+    *n_records = st.size();
+  });
+}
+
+int awry_index_build(const awry_build_args* a, const int* devices, int n_dev, awry_index** out) {
+  return guarded([&] {
+    if (out) *out = nullptr;
+    if (!a || !a->input_file_src) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    if (!a->output_file_src && !out) fail(AWRY_ERR_INVALID_ARG, "neither an output file nor an index handle requested");
+    if (a->alphabet > 1) fail(AWRY_ERR_INVALID_ARG, "invalid alphabet id %u", a->alphabet);
+    const int alphabet = int(a->alphabet);
+    const uint64_t ratio = a->suffix_array_compression_ratio ? a->suffix_array_compression_ratio : 8;  // fm_index.rs:122
+    const uint32_t k = a->lookup_table_kmer_len ? a->lookup_table_kmer_len : (alphabet == 0 ? 10u : 4u);
+    const int card = alphabet == 0 ? 6 : 22;
+    if (k > 255 || ipow(uint64_t(card - 2), k) > (1ull << 34)) fail(AWRY_ERR_UNSUPPORTED, "k-mer table of length %u too large", k);
+    // the sequence file first: I/O and format errors do not need a device
+    const bool verbose = getenv("AWRY_B200_BUILD_VERBOSE") != nullptr;  // phase times on stderr
+    auto tick = [t = std::chrono::steady_clock::now(), verbose](const char* what) mutable {
+      auto now = std::chrono::steady_clock::now();
+      if (verbose) fprintf(stderr, "[awry_index_build] %-28s %.3f s\n", what, std::chrono::duration<double>(now - t).count());
+      t = now;
+    };
+    TextBuf text;
+    std::string err;
+    std::vector<uint64_t> starts;
+    std::vector<std::string> headers;
+    if (read_sequence_file(a->input_file_src, alphabet == 0 ? 'N' : 'X', text, starts, headers, err) != 0)
+      fail(AWRY_ERR_IO, "%s", err.c_str());
+    tick("read sequence file");
+    const uint64_t n = text.size(), bwt_len = n + 1;
+    if (bwt_len >= (1ull << 32) - 256) fail(AWRY_ERR_UNSUPPORTED, "text of %llu symbols: 32-bit row pointers", (unsigned long long)n);
+    int dev0 = a->device;
+    std::vector<int> devs = out ? pick_devices(devices ? devices : &dev0, devices ? n_dev : 1) : pick_devices(&dev0, 1);
+    // construction on devs[0]; the reference-layout arrays stay on the device and are re-laid out there
+    // (no 3.5 GB round trip through host memory); they are copied out only to write a file
+    std::vector<uint64_t> prefix(size_t(card) + 1);
+    DeviceParts dp;
+    struct DpGuard {
+      DeviceParts& d;
+      ~DpGuard() { d.release(); }
+    } dp_guard{dp};
+    double ph[8] = {0};
+    if (build_parts(alphabet, text.data(), n, ratio, devs[0], nullptr, prefix.data(), nullptr, ph, err, &dp) != 0)
+      fail(AWRY_ERR_CUDA, "index construction failed: %s", err.c_str());
+    text.reset();
+    if (verbose)
+      fprintf(stderr, "[awry_index_build]   ingest %.3f keys %.3f sort %.3f ties %.3f bwt %.3f milestones %.3f sa-pack %.3f\n",
+              ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6]);
+    tick("suffix sort + BWT on device");
+    auto ixp = std::make_unique<awry_index>();
+    ixp->version = 1;
+    ixp->sa_ratio = ratio;
+    ixp->bwt_len = bwt_len;
+    ixp->alphabet = alphabet;
+    ixp->kmer_len_file = out ? k : 0;  // a file-only build needs no seed table
+    check_header(ixp.get());
+    ixp->seq_starts = starts;
+    ixp->headers = headers;
+    {
+      Source src;
+      src.dev_blocks = dp.d_blocks;
+      src.dev_sa = dp.d_sa_words;
+      src.segs.emplace_back(reinterpret_cast<const uint8_t*>(prefix.data()), size_t(card + 1) * 8);
+      g_skip_accelerators = !out;
+      try {
+        make_replicas(ixp.get(), devs, src, false);
+      } catch (...) {
+        g_skip_accelerators = false;
+        awry_index_free(ixp.release());
+        throw;
+      }
+      g_skip_accelerators = false;
+    }
+    awry_index* ix = ixp.release();
+    std::unique_ptr<awry_index, void (*)(awry_index*)> holder(ix, awry_index_free);
+    tick("device layout + accelerators");
+    if (a->output_file_src) {  // FmIndex::save (fm_index_file.rs:42-106)
+      FILE* f = fopen(a->output_file_src, "wb");
+      if (!f) fail(AWRY_ERR_IO, "cannot create %s: %s", a->output_file_src, strerror(errno));
+      std::unique_ptr<FILE, int (*)(FILE*)> closer(f, fclose);
+      setvbuf(f, nullptr, _IOFBF, 8u << 20);
+      bool ok = true;
+      auto put = [&](const void* p, size_t nbytes) {
+        if (ok && nbytes && fwrite(p, 1, nbytes, f) != nbytes) ok = false;
+      };
+      put("AWRY-Index\n", 11);  // fm_index_file.rs:18,47
+      uint64_t hdr[4] = {1, ratio, bwt_len, uint64_t(alphabet)};
+      put(hdr, sizeof hdr);
+      // device arrays -> file through a pinned double buffer (D2H of chunk i+1 overlaps fwrite of chunk i)
+      auto put_device = [&](const uint64_t* d_src, uint64_t n_words) {
+        DeviceGuard dg(dp.device);
+        const uint64_t CH = (64u << 20) / 8;
+        uint64_t* hb[2] = {nullptr, nullptr};
+        cudaStream_t cs = nullptr;
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        try {
+          CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+          for (int i = 0; i < 2; i++) {
+            CU(cudaHostAlloc(reinterpret_cast<void**>(&hb[i]), CH * 8, cudaHostAllocDefault));
+            CU(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+          }
+          uint64_t n_chunks = (n_words + CH - 1) / CH;
+          auto issue = [&](uint64_t c) {
+            uint64_t w0 = c * CH, nw = std::min(CH, n_words - w0);
+            CU(cudaMemcpyAsync(hb[c & 1], d_src + w0, nw * 8, cudaMemcpyDeviceToHost, cs));
+            CU(cudaEventRecord(ev[c & 1], cs));
+          };
+          if (n_chunks) issue(0);
+          for (uint64_t c = 0; c < n_chunks; c++) {
+            CU(cudaEventSynchronize(ev[c & 1]));
+            if (c + 1 < n_chunks) issue(c + 1);
+            put(hb[c & 1], std::min(CH, n_words - c * CH) * 8);
+          }
+        } catch (...) {
+          for (int i = 0; i < 2; i++) {
+            cudaFreeHost(hb[i]);
+            if (ev[i]) cudaEventDestroy(ev[i]);
+          }
+          if (cs) cudaStreamDestroy(cs);
+          throw;
+        }
+        for (int i = 0; i < 2; i++) {
+          cudaFreeHost(hb[i]);
+          cudaEventDestroy(ev[i]);
+        }
+        cudaStreamDestroy(cs);
+      };
+      put_device(dp.d_blocks, dp.n_block_words);
+      put(prefix.data(), prefix.size() * 8);
+      put_device(dp.d_sa_words, sa_word_len(bwt_len, ratio));
+      uint8_t kb = uint8_t(k);
+      put(&kb, 1);
+      {
+        Replica& r = *ix->reps[0];
+        DeviceGuard dg(r.device);
+        const uint64_t n_entries = ipow(uint64_t(card - 2), k), CH = 1u << 22;
+        ulonglong2* d_buf = nullptr;
+        CU(cudaMalloc(reinterpret_cast<void**>(&d_buf), std::min(n_entries, CH) * 16));
+        std::vector<uint64_t> h_buf(2 * std::min(n_entries, CH));
+        IndexView v = r.view;
+        v.kmer_len = 0;
+        for (uint64_t first = 0; first < n_entries && ok; first += CH) {
+          uint64_t cnt = std::min(CH, n_entries - first);
+          cudaError_t e = launch_ref_table(v, first, cnt, k, d_buf, nullptr);
+          if (e == cudaSuccess) e = cudaMemcpy(h_buf.data(), d_buf, cnt * 16, cudaMemcpyDeviceToHost);
+          if (e != cudaSuccess) {
+            cudaFree(d_buf);
+            fail(AWRY_ERR_CUDA, "k-mer table kernel failed: %s", cudaGetErrorString(e));
+          }
+          put(h_buf.data(), cnt * 16);
+        }
+        cudaFree(d_buf);
+      }
+      uint64_t n_seqs = starts.size();  // sequence_index.rs:144-152
+      put(&n_seqs, 8);
+      for (uint64_t i = 0; i < n_seqs; i++) {
+        uint64_t hl = headers[i].size();
+        put(&starts[i], 8);
+        put(&hl, 8);
+        put(headers[i].data(), hl);
+      }
+      if (fflush(f) != 0) ok = false;
+      if (!ok) fail(AWRY_ERR_IO, "write to %s failed", a->output_file_src);
+      tick("write .awry file");
+    }
+    if (out) *out = holder.release();
+  });
+}
+
+int awry_build_index_file(const awry_build_args* a) {
+  if (a && !a->output_file_src) {
+    return guarded([&] { fail(AWRY_ERR_INVALID_ARG, "output_file_src is null"); });
+  }
+  return awry_index_build(a, nullptr, 0, nullptr);
+}
+
+}  // extern "C"

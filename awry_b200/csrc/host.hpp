@@ -1,0 +1,390 @@
+// host.hpp -- shared host-side internals of libawry_b200 (not part of the ABI): error handling, profiling
+// accounting, per-call workspaces, device replicas and the helpers the translation units share.
+//   api.cu        index lifetime: `.awry` loader, replicas, getters, single steps, instrumentation
+//   batch.cu      batched count / locate pipelines (host buffers and device-resident entry points)
+//   reads_api.cu  streaming FASTQ / FASTA front-end (host side of reads.cu)
+//   build_api.cu  GPU index construction entry points (host side of build.cu)
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <cerrno>
+#include <chrono>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "../../include/awry_b200.h"
+#include "build.hpp"
+#include "hostpack.hpp"
+#include "kernels.hpp"
+#include "reads.hpp"
+
+namespace awry {
+namespace host {
+
+
+extern thread_local char g_err[1024];  // awry_last_error(): per thread
+
+struct ApiError : std::runtime_error {
+  int code;
+  ApiError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+[[noreturn]] void fail(int code, const char* fmt, ...);
+
+#define CU(expr)                                                                          \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess)                                                               \
+      fail(AWRY_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return AWRY_OK;
+  } catch (const ApiError& e) {
+    snprintf(g_err, sizeof g_err, "%s", e.what());
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    snprintf(g_err, sizeof g_err, "out of host memory");
+    return AWRY_ERR_NOMEM;
+  } catch (const std::exception& e) {
+    snprintf(g_err, sizeof g_err, "%s", e.what());
+    return AWRY_ERR_INVALID_ARG;
+  } catch (...) {
+    snprintf(g_err, sizeof g_err, "unknown error");
+    return AWRY_ERR_INVALID_ARG;
+  }
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    CU(cudaSetDevice(dev));
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// ------------------------------------------------------------------ profiling
+
+struct ProfState {
+  std::mutex mu;
+  bool enabled = false;
+  struct Span {
+    cudaEvent_t a, b;
+    int kind;  // 0 search, 1 walk, 2 pack
+    int device;
+  };
+  std::vector<Span> spans;
+  uint64_t n[3] = {0, 0, 0};
+  double ms[3] = {0, 0, 0};
+  std::atomic<uint64_t> h2d{0}, d2h{0};
+};
+extern ProfState g_prof;
+
+struct ProfScope {
+  bool on;
+  cudaStream_t st;
+  ProfState::Span sp{};
+  ProfScope(int kind, int device, cudaStream_t s) : st(s) {
+    on = g_prof.enabled;
+    if (!on) return;
+    sp.kind = kind;
+    sp.device = device;
+    cudaEventCreate(&sp.a);
+    cudaEventCreate(&sp.b);
+    cudaEventRecord(sp.a, st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(sp.b, st);
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    g_prof.spans.push_back(sp);
+  }
+};
+
+void prof_collect_locked();
+
+extern SearchVariant g_variant;  // experiments only (awry_set_search_variant)
+extern int g_host_pack;      // -1 = auto (AWRY_B200_HOST_PACK, CPU support, >= 4 pool threads), 0 = off, 1 = on
+extern int g_locate_variant;  // 0 = unsampled-SA gather when the array exists, 1 = always LF-walk (awry_set_locate_variant)
+
+
+// ------------------------------------------------------------------ index
+
+struct Workspace {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t done = nullptr;
+  // pinned staging
+  uint8_t* h_qbytes = nullptr;
+  size_t h_qbytes_cap = 0;
+  uint64_t* h_qoff = nullptr;
+  size_t h_qoff_cap = 0;  // entries
+  uint8_t* h_out = nullptr;
+  size_t h_out_cap = 0;  // bytes
+  unsigned long long* h_flag = nullptr;
+  unsigned long long* h_total = nullptr;  // hit total of a locate chunk (second word of the h_flag allocation)
+  uint64_t* h_exc = nullptr;  // host-packed chunks: exception list (bytes outside ACGT)
+  size_t h_exc_cap = 0;
+  std::vector<uint64_t> exc_tmp;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;  // timing of a raw chunk's H2D copy (PackBalance)
+  uint64_t link_probe_bytes = 0;
+  // device
+  uint8_t* d_qbytes = nullptr;
+  size_t d_qbytes_cap = 0;
+  uint64_t* d_qoff = nullptr;
+  size_t d_qoff_cap = 0;
+  uint64_t* d_qwords = nullptr;
+  size_t d_qwords_cap = 0;
+  uint32_t* d_defer = nullptr;
+  size_t d_defer_cap = 0;
+  uint8_t* d_out = nullptr;
+  size_t d_out_cap = 0;
+  uint64_t* d_hit_off = nullptr;
+  size_t d_hit_off_cap = 0;
+  void* d_temp = nullptr;
+  size_t d_temp_cap = 0;
+  unsigned long long* d_flag = nullptr;
+  uint64_t* d_exc = nullptr;
+  size_t d_exc_cap = 0;
+  // reads-file front-end scratch, kept across calls (pinned allocations cost ~0.4 ms per MiB)
+  struct ReadsScratch {
+    uint64_t chunk = 0, carry = 0;
+    uint8_t* h_buf[3] = {nullptr, nullptr, nullptr};
+    uint8_t *d_raw = nullptr, *d_qbytes = nullptr;
+    uint32_t *d_nl = nullptr, *d_small = nullptr, *d_seq_len = nullptr, *d_is_hdr = nullptr, *d_hdr_rank = nullptr;
+    uint64_t *d_seq_off = nullptr, *d_qoff = nullptr;
+    size_t cap_lines = 0, cap_qoff = 0, temp_bytes = 0;
+    void* d_temp = nullptr;
+    void* h_plan = nullptr;
+    void release() {
+      for (auto& b : h_buf) {
+        cudaFreeHost(b);
+        b = nullptr;
+      }
+      cudaFree(d_raw);
+      cudaFree(d_qbytes);
+      cudaFree(d_nl);
+      cudaFree(d_small);
+      cudaFree(d_seq_len);
+      cudaFree(d_is_hdr);
+      cudaFree(d_hdr_rank);
+      cudaFree(d_seq_off);
+      cudaFree(d_qoff);
+      cudaFree(d_temp);
+      cudaFreeHost(h_plan);
+      *this = ReadsScratch();
+    }
+  } rs;
+
+  template <class T>
+  static void grow_dev(T*& p, size_t& cap, size_t need) {
+    if (need <= cap) return;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = need + need / 8 + 256;
+    CU(cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T)));
+    cap = want;
+  }
+  template <class T>
+  static void grow_host(T*& p, size_t& cap, size_t need) {
+    if (need <= cap) return;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = need + need / 8 + 256;
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&p), want * sizeof(T), cudaHostAllocDefault));
+    cap = want;
+  }
+  void init(int dev) {
+    device = dev;
+    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&h_flag), 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+    h_total = h_flag + 1;
+    CU(cudaMalloc(reinterpret_cast<void**>(&d_flag), sizeof(unsigned long long)));
+  }
+  void destroy() {
+    cudaSetDevice(device);
+    if (st) cudaStreamSynchronize(st);
+    cudaFreeHost(h_qbytes);
+    cudaFreeHost(h_qoff);
+    cudaFreeHost(h_out);
+    cudaFreeHost(h_flag);
+    cudaFreeHost(h_exc);
+    cudaFree(d_exc);
+    cudaFree(d_qbytes);
+    cudaFree(d_qoff);
+    cudaFree(d_qwords);
+    cudaFree(d_defer);
+    cudaFree(d_out);
+    cudaFree(d_hit_off);
+    cudaFree(d_temp);
+    cudaFree(d_flag);
+    rs.release();
+    if (ev_a) cudaEventDestroy(ev_a);
+    if (ev_b) cudaEventDestroy(ev_b);
+    if (done) cudaEventDestroy(done);
+    if (st) cudaStreamDestroy(st);
+  }
+};
+
+struct Replica {
+  int device = 0;
+  int sm_count = 148;
+  uint4* d_blocks = nullptr;
+  uint64_t* d_sa = nullptr;
+  uint2* d_table = nullptr;
+  uint4* d_pair = nullptr;
+  uint32_t* d_full_sa = nullptr;  // unsampled suffix array (locate accelerator)
+  uint64_t* d_seq_starts = nullptr;
+  unsigned long long* d_async_flag = nullptr;  // first bad query seen by *_device calls
+  size_t bytes_blocks = 0, bytes_sa = 0, bytes_table = 0, bytes_pair = 0, bytes_full_sa = 0;
+  uint32_t c2[16] = {0};
+  IndexView view{};
+  std::mutex ws_mu;
+  std::vector<Workspace*> free_ws;
+  std::vector<Workspace*> all_ws;
+
+  Workspace* acquire() {
+    {
+      std::lock_guard<std::mutex> lk(ws_mu);
+      if (!free_ws.empty()) {
+        Workspace* w = free_ws.back();
+        free_ws.pop_back();
+        return w;
+      }
+    }
+    auto* w = new Workspace();
+    w->init(device);
+    std::lock_guard<std::mutex> lk(ws_mu);
+    all_ws.push_back(w);
+    return w;
+  }
+  void release(Workspace* w) {
+    std::lock_guard<std::mutex> lk(ws_mu);
+    free_ws.push_back(w);
+  }
+};
+
+}  // namespace host
+}  // namespace awry
+
+struct awry_index {
+  uint64_t version = 1, sa_ratio = 0, bwt_len = 0;
+  int alphabet = 0;
+  int card = 6;
+  uint32_t kmer_len_file = 0, kmer_len_dev = 0;
+  uint64_t prefix_sums[23] = {0};
+  uint64_t n_sa_words = 0;
+  uint32_t sa_bits = 0;
+  std::vector<uint64_t> seq_starts;
+  std::vector<std::string> headers;
+  std::vector<std::unique_ptr<awry::host::Replica>> reps;
+};
+
+namespace awry {
+namespace host {
+
+// ---- api.cu
+uint32_t bits_per_element(uint64_t bwt_len);                  // compressed_suffix_array.rs:124-130
+uint64_t sa_word_len(uint64_t bwt_len, uint64_t ratio);        // compressed_suffix_array.rs:113-123
+uint64_t ipow(uint64_t b, uint32_t e);
+unsigned io_threads();  // threads of a parallel positional read (AWRY_B200_IO_THREADS, default min(8, cores))
+// sequential byte source: a file (FmIndex::load) or caller memory sections (FmIndex::new hand-over)
+struct Source {
+  FILE* f = nullptr;
+  // arrays already on replica 0's device in the reference layout (awry_index_build): no staging
+  const uint64_t* dev_blocks = nullptr;
+  const uint64_t* dev_sa = nullptr;
+  std::vector<std::pair<const uint8_t*, size_t>> segs;
+  size_t cur = 0, off = 0;
+  void read(void* dst, size_t n, const char* what) {
+    if (n == 0) return;
+    if (f) {
+      if (n >= (32u << 20)) {
+        // large sections (blocks, SA words): positional reads from several threads -- one thread
+        // copying out of the page cache tops out at a few GB/s, far below the PCIe rate behind it
+        off_t pos = ftello(f);
+        int fd = fileno(f);
+        unsigned nt = io_threads();
+        size_t per = ((n + nt - 1) / nt + 4095) & ~size_t(4095);
+        std::vector<std::thread> th;
+        std::vector<int> ok(nt, 1);
+        for (unsigned t = 0; t < nt; t++) {
+          size_t lo = std::min(n, size_t(t) * per), hi = std::min(n, lo + per);
+          if (lo >= hi) break;
+          th.emplace_back([=, &ok] {
+            size_t done = lo;
+            while (done < hi) {
+              ssize_t r = pread(fd, static_cast<char*>(dst) + done, hi - done, pos + off_t(done));
+              if (r <= 0) {
+                ok[t] = 0;
+                return;
+              }
+              done += size_t(r);
+            }
+          });
+        }
+        for (auto& t : th) t.join();
+        for (unsigned t = 0; t < nt; t++)
+          if (!ok[t]) fail(AWRY_ERR_IO, "unexpected end of file while reading %s", what);
+        if (fseeko(f, pos + off_t(n), SEEK_SET) != 0) fail(AWRY_ERR_IO, "seek failed while reading %s", what);
+        return;
+      }
+      if (fread(dst, 1, n, f) != n) fail(AWRY_ERR_IO, "unexpected end of file while reading %s", what);
+      return;
+    }
+    uint8_t* d = static_cast<uint8_t*>(dst);
+    while (n) {
+      if (cur >= segs.size()) fail(AWRY_ERR_INVALID_ARG, "index parts too short while reading %s", what);
+      size_t take = std::min(segs[cur].second - off, n);
+      memcpy(d, segs[cur].first + off, take);
+      off += take;
+      d += take;
+      n -= take;
+      if (off == segs[cur].second) {
+        cur++;
+        off = 0;
+      }
+    }
+  }
+};
+
+extern thread_local bool g_skip_accelerators;  // replicas that exist only to fill a file's k-mer table section
+std::vector<int> pick_devices(const int* devices, int n_dev);
+void check_header(awry_index* ix);
+void make_replicas(awry_index* ix, const std::vector<int>& devs, Source& src, bool from_file);
+inline const awry_index* need(const awry_index* ix) {
+  if (!ix || ix->reps.empty()) fail(AWRY_ERR_INVALID_ARG, "null or empty index handle");
+  return ix;
+}
+
+// ---- batch.cu
+bool is_pinned(const void* p);
+void parallel_memcpy(void* dst, const void* src, size_t n);
+uint64_t locate_chunk_count(Replica& r, Workspace* ws, uint64_t nq, uint64_t* d_hit_off, cudaStream_t st);
+uint64_t* locate_chunk_walk(Replica& r, Workspace* ws, uint64_t nq, uint64_t n_hits, uint32_t flags,
+                            const uint64_t* d_hit_off, cudaStream_t st);
+
+}  // namespace host
+}  // namespace awry

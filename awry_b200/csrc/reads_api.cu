@@ -1,0 +1,402 @@
+// reads_api.cu -- host side of the streaming reads-file front-end (device side: reads.cu).
+#include <zlib.h>
+
+#include "host.hpp"
+
+using namespace awry;
+using namespace awry::host;
+
+namespace {
+
+// ------------------------------------------------------------------ streaming reads-file front-end
+// FASTQ / FASTA file of queries -> parallel_count / parallel_locate without a host-side parser:
+// a reader thread preads the file into a ring of pinned buffers, the raw bytes are uploaded and
+// parsed on the device (reads.cu), and the parsed (query bytes, CSR offsets) feed the same pack /
+// search / locate kernels as the *_device entry points.  A record cut by a chunk boundary is carried
+// into the next chunk by the host.
+
+struct ReadsOut {
+  std::vector<uint64_t> counts;
+  std::vector<uint64_t> hit_off;  // locate: CSR, n_reads + 1
+  awry_hit* hits = nullptr;       // locate: malloc'd
+  uint64_t n_hits = 0, hits_cap = 0;
+  uint64_t n_reads = 0, n_bases = 0, file_bytes = 0;
+};
+
+void parallel_pread(int fd, void* dst, size_t n, off_t pos, const char* what) {
+  unsigned nt = n >= (4u << 20) ? io_threads() : 1u;
+  size_t per = ((n + nt - 1) / nt + 4095) & ~size_t(4095);
+  std::vector<int> ok(nt, 1);
+  auto work = [&](unsigned t) {
+    size_t lo = std::min(n, size_t(t) * per), hi = std::min(n, lo + per);
+    while (lo < hi) {
+      ssize_t r = pread(fd, static_cast<char*>(dst) + lo, hi - lo, pos + off_t(lo));
+      if (r <= 0) {
+        ok[t] = 0;
+        return;
+      }
+      lo += size_t(r);
+    }
+  };
+  if (nt == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t);
+    for (auto& t : th) t.join();
+  }
+  for (unsigned t = 0; t < nt; t++)
+    if (!ok[t]) fail(AWRY_ERR_IO, "read error in %s", what);
+}
+
+void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_t flags, ReadsOut& out) {
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) fail(AWRY_ERR_IO, "cannot open %s: %s", path, strerror(errno));
+  struct FdCloser {
+    int fd;
+    ~FdCloser() { close(fd); }
+  } fdc{fd};
+  struct stat sb;
+  if (fstat(fd, &sb) != 0) fail(AWRY_ERR_IO, "cannot stat %s", path);
+  const uint64_t fsize = uint64_t(sb.st_size);
+  out.file_bytes = fsize;
+  // format: first non-blank byte (of the inflated stream when the file is gzip-compressed)
+  int fastq = -1;
+  uint64_t data_start = 0;
+  gzFile gz = nullptr;
+  struct GzCloser {
+    gzFile& g;
+    ~GzCloser() {
+      if (g) gzclose(g);
+    }
+  } gzc{gz};
+  {
+    unsigned char head[4096];
+    ssize_t got = pread(fd, head, sizeof head, 0);
+    bool at_end = fsize <= uint64_t(std::max<ssize_t>(got, 0));
+    if (got >= 2 && head[0] == 0x1f && head[1] == 0x8b) {
+      gz = gzopen(path, "rb");
+      if (!gz) fail(AWRY_ERR_IO, "cannot open %s as a gzip stream", path);
+      gzbuffer(gz, 4u << 20);
+      got = gzread(gz, head, sizeof head);
+      int zerr = Z_OK;
+      gzerror(gz, &zerr);  // a truncated stream returns the bytes it has and only flags the error
+      if (got < 0 || (zerr != Z_OK && zerr != Z_STREAM_END)) fail(AWRY_ERR_FORMAT, "%s: corrupt gzip stream", path);
+      at_end = got < ssize_t(sizeof head);
+    }
+    for (ssize_t i = 0; i < got; i++) {
+      unsigned char c = head[i];
+      if (c == '\n' || c == '\r' || c == ' ' || c == '\t') continue;
+      fastq = c == '@' ? 1 : c == '>' ? 0 : -1;
+      data_start = uint64_t(i);
+      break;
+    }
+    if (fastq < 0) {
+      if (got <= 0 || data_start == 0) {
+        bool blank = true;
+        for (ssize_t i = 0; i < got; i++) blank &= (head[i] == '\n' || head[i] == '\r' || head[i] == ' ' || head[i] == '\t');
+        if (blank && at_end) {  // empty file: zero reads
+          if (locate) out.hit_off.assign(1, 0);
+          return;
+        }
+      }
+      fail(AWRY_ERR_FORMAT, "%s is neither FASTQ ('@') nor FASTA ('>')", path);
+    }
+    if (gz && gzseek(gz, z_off_t(data_start), SEEK_SET) < 0) fail(AWRY_ERR_FORMAT, "%s: corrupt gzip stream", path);
+  }
+  uint64_t CHUNK = 64ull << 20;
+  if (const char* e = getenv("AWRY_B200_READS_CHUNK")) CHUNK = std::max<uint64_t>(64, strtoull(e, nullptr, 10));
+  CHUNK = std::min<uint64_t>(CHUNK, 512ull << 20);
+  // the largest record that can straddle a chunk boundary (AWRY_B200_READS_CARRY, default min(chunk, 16 MiB))
+  uint64_t CARRY = std::min<uint64_t>(CHUNK, 16ull << 20);
+  if (const char* e = getenv("AWRY_B200_READS_CARRY")) CARRY = std::min<uint64_t>(std::max<uint64_t>(64, strtoull(e, nullptr, 10)), 1ull << 30);
+  constexpr int NBUF = 3;
+
+  Replica& r = *ix->reps[0];
+  DeviceGuard dg(r.device);
+  Workspace* ws = r.acquire();
+  cudaStream_t st = ws->st;
+  Workspace::ReadsScratch& rs = ws->rs;
+
+  // reader thread state
+  std::mutex mu;
+  std::condition_variable cv;
+  struct Slot {
+    bool filled = false;
+    uint64_t n = 0;
+    bool eof = false;
+  } slots[NBUF];
+  bool stop = false;
+  std::string reader_err;
+  std::thread reader;
+
+  auto cleanup = [&] {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      stop = true;
+    }
+    cv.notify_all();
+    if (reader.joinable()) reader.join();
+    cudaStreamSynchronize(st);
+    r.release(ws);
+  };
+  try {
+    const uint32_t max_bytes = uint32_t(CARRY + CHUNK + 1);
+    if (rs.chunk != CHUNK || rs.carry != CARRY) {
+      rs.release();
+      for (auto& b : rs.h_buf) CU(cudaHostAlloc(reinterpret_cast<void**>(&b), CARRY + CHUNK + 64, cudaHostAllocDefault));
+      CU(cudaMalloc(reinterpret_cast<void**>(&rs.d_raw), max_bytes + 64));
+      CU(cudaMalloc(reinterpret_cast<void**>(&rs.d_qbytes), max_bytes + 64));
+      CU(cudaMalloc(reinterpret_cast<void**>(&rs.d_nl), size_t(max_bytes) * 4 + 64));
+      CU(cudaMalloc(reinterpret_cast<void**>(&rs.d_small), 64));
+      rs.temp_bytes = reads_temp_bytes(max_bytes);
+      CU(cudaMalloc(&rs.d_temp, rs.temp_bytes));
+      CU(cudaHostAlloc(&rs.h_plan, sizeof(ReadsPlan) + 64, cudaHostAllocDefault));
+      rs.chunk = CHUNK;
+      rs.carry = CARRY;
+    }
+    uint8_t** h_buf = rs.h_buf;
+    uint8_t *d_raw = rs.d_raw, *d_qbytes = rs.d_qbytes;
+    uint32_t *d_nl = rs.d_nl, *d_small = rs.d_small;
+    uint32_t *&d_seq_len = rs.d_seq_len, *&d_is_hdr = rs.d_is_hdr, *&d_hdr_rank = rs.d_hdr_rank;
+    uint64_t *&d_seq_off = rs.d_seq_off, *&d_qoff = rs.d_qoff;
+    size_t &cap_lines = rs.cap_lines, &cap_qoff = rs.cap_qoff;
+    void* d_temp = rs.d_temp;
+    const size_t temp_bytes = rs.temp_bytes;
+    ReadsPlan* h_plan = static_cast<ReadsPlan*>(rs.h_plan);
+    uint32_t* h_n_lines = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(h_plan) + sizeof(ReadsPlan));
+
+    reader = std::thread([&] {
+      uint64_t pos = data_start;
+      for (int c = 0;; c++) {
+        Slot& s = slots[c % NBUF];
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return stop || !s.filled; });
+          if (stop) return;
+        }
+        uint64_t n = gz ? 0 : std::min<uint64_t>(CHUNK, fsize - pos);
+        bool gz_end = false;
+        try {
+          if (gz) {  // inflate on this thread (one zlib stream: ~0.3-0.5 GB/s); the device side is unchanged
+            while (n < CHUNK) {
+              int r = gzread(gz, h_buf[c % NBUF] + CARRY + n, unsigned(std::min<uint64_t>(CHUNK - n, 1u << 30)));
+              int zerr = Z_OK;
+              if (r <= 0) gzerror(gz, &zerr);
+              if (r < 0 || (zerr != Z_OK && zerr != Z_STREAM_END)) fail(AWRY_ERR_FORMAT, "%s: corrupt or truncated gzip stream", path);
+              if (r == 0) {
+                gz_end = true;
+                break;
+              }
+              n += uint64_t(r);
+            }
+          } else if (n) {
+            parallel_pread(fd, h_buf[c % NBUF] + CARRY, size_t(n), off_t(pos), path);
+          }
+        } catch (const ApiError& e) {
+          std::lock_guard<std::mutex> lk(mu);
+          reader_err = e.what();
+          s.filled = true;
+          s.n = 0;
+          s.eof = true;
+          cv.notify_all();
+          return;
+        }
+        pos += n;
+        const bool at_eof = gz ? gz_end : pos >= fsize;
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          s.n = n;
+          s.eof = at_eof;
+          s.filled = true;
+        }
+        cv.notify_all();
+        if (at_eof) return;
+      }
+    });
+
+    if (locate) out.hit_off.assign(1, 0);
+    const int sh = packed_unit_shift(ix->alphabet);
+    uint64_t tail_len = 0;
+    const uint8_t* tail_src = nullptr;
+    int prev_slot = -1;
+    for (int c = 0;; c++) {
+      const int si = c % NBUF;
+      Slot& s = slots[si];
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return s.filled; });
+      }
+      if (!reader_err.empty()) fail(AWRY_ERR_IO, "%s", reader_err.c_str());
+      uint8_t* base = h_buf[si] + CARRY - tail_len;
+      if (tail_len) memcpy(base, tail_src, tail_len);
+      if (prev_slot >= 0) {  // the previous buffer is free once its tail has moved
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          slots[prev_slot].filled = false;
+        }
+        cv.notify_all();
+      }
+      uint64_t n = tail_len + s.n;
+      const bool eof = s.eof;
+      if (eof && n && base[n - 1] != '\n') base[n++] = '\n';
+      if (n == 0) break;
+      CU(cudaMemcpyAsync(d_raw, base, n, cudaMemcpyHostToDevice, st));
+      g_prof.h2d += n;
+      CU(reads_find_lines(d_raw, uint32_t(n), d_nl, d_small, d_temp, temp_bytes, st));
+      CU(cudaMemcpyAsync(h_n_lines, d_small, 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      const uint32_t n_lines = *h_n_lines;
+      if (size_t(n_lines) + 2 > cap_lines) {
+        cudaFree(d_seq_len);
+        cudaFree(d_is_hdr);
+        cudaFree(d_hdr_rank);
+        cudaFree(d_seq_off);
+        d_seq_len = d_is_hdr = d_hdr_rank = nullptr;
+        d_seq_off = nullptr;
+        cap_lines = size_t(n_lines) + size_t(n_lines) / 4 + 1024;
+        CU(cudaMalloc(reinterpret_cast<void**>(&d_seq_len), cap_lines * 4));
+        CU(cudaMalloc(reinterpret_cast<void**>(&d_is_hdr), cap_lines * 4));
+        CU(cudaMalloc(reinterpret_cast<void**>(&d_hdr_rank), cap_lines * 4));
+        CU(cudaMalloc(reinterpret_cast<void**>(&d_seq_off), cap_lines * 8));
+      }
+      if (size_t(n_lines) + 2 > cap_qoff) {
+        cudaFree(d_qoff);
+        d_qoff = nullptr;
+        cap_qoff = size_t(n_lines) + size_t(n_lines) / 4 + 1024;
+        CU(cudaMalloc(reinterpret_cast<void**>(&d_qoff), cap_qoff * 8));
+      }
+      ReadsPlan* d_plan = reinterpret_cast<ReadsPlan*>(d_small + 4);
+      CU(reads_parse_lines(d_raw, uint32_t(n), d_nl, d_small, n_lines, fastq, eof ? 1 : 0, d_seq_len, d_is_hdr, d_seq_off,
+                           d_hdr_rank, d_plan, d_qbytes, d_qoff, d_temp, temp_bytes, st));
+      CU(cudaMemcpyAsync(h_plan, d_plan, sizeof(ReadsPlan), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      const ReadsPlan plan = *h_plan;
+      const uint64_t nq = plan.n_records;
+      if (nq) {
+        Workspace::grow_dev(ws->d_qwords, ws->d_qwords_cap, size_t(packed_words(ix->alphabet, nq, plan.seq_bytes)));
+        Workspace::grow_dev(ws->d_out, ws->d_out_cap, size_t(nq) * 8);
+        Workspace::grow_dev(ws->d_defer, ws->d_defer_cap, size_t(nq) + 2);
+        CU(cudaMemsetAsync(ws->d_flag, 0xff, 8, st));
+        {
+          ProfScope p(2, r.device, st);
+          CU(launch_pack(ix->alphabet, d_qbytes, d_qoff, nq, ws->d_qwords, ws->d_flag, st));
+        }
+        {
+          ProfScope p(0, r.device, st);
+          SearchVariant v = g_variant;
+          v.avg_len = uint32_t(std::min<uint64_t>(plan.seq_bytes / nq, 1u << 30));
+          CU(launch_search(r.view, ws->d_qwords, d_qoff, nq, locate ? OUT_SP_CNT_U32 : OUT_COUNT_U64, ws->d_out, ws->d_defer,
+                           v, r.sm_count, st));
+        }
+        CU(cudaMemcpyAsync(ws->h_flag, ws->d_flag, 8, cudaMemcpyDeviceToHost, st));
+        if (!locate) {
+          out.counts.resize(out.n_reads + nq);
+          CU(cudaMemcpyAsync(out.counts.data() + out.n_reads, ws->d_out, nq * 8, cudaMemcpyDeviceToHost, st));
+          g_prof.d2h += nq * 8;
+          CU(cudaStreamSynchronize(st));
+        } else {
+          Workspace::grow_dev(ws->d_hit_off, ws->d_hit_off_cap, size_t(nq) + 1);
+          uint64_t n_hits = locate_chunk_count(r, ws, nq, ws->d_hit_off, st);
+          out.hit_off.resize(out.n_reads + nq + 1);
+          uint64_t* dst_off = out.hit_off.data() + out.n_reads;
+          CU(cudaMemcpyAsync(dst_off, ws->d_hit_off, (nq + 1) * 8, cudaMemcpyDeviceToHost, st));
+          if (n_hits) {
+            uint64_t* d_hits = locate_chunk_walk(r, ws, nq, n_hits, flags, ws->d_hit_off, st);
+            if (out.n_hits + n_hits > out.hits_cap) {
+              uint64_t cap = std::max<uint64_t>(out.n_hits + n_hits, out.hits_cap * 2);
+              void* np = realloc(out.hits, cap * sizeof(awry_hit));
+              if (!np) {
+                cudaFreeAsync(d_hits, st);
+                fail(AWRY_ERR_NOMEM, "out of host memory for %llu hits", (unsigned long long)cap);
+              }
+              out.hits = static_cast<awry_hit*>(np);
+              out.hits_cap = cap;
+            }
+            CU(cudaMemcpyAsync(out.hits + out.n_hits, d_hits, n_hits * 16, cudaMemcpyDeviceToHost, st));
+            cudaFreeAsync(d_hits, st);
+            g_prof.d2h += n_hits * 16;
+          }
+          CU(cudaStreamSynchronize(st));
+          g_prof.d2h += (nq + 1) * 8;
+          for (uint64_t i = 0; i <= nq; i++) dst_off[i] += out.n_hits;
+          out.n_hits += n_hits;
+        }
+        if (*ws->h_flag != ~0ull)
+          fail(AWRY_ERR_INVALID_QUERY,
+               "read %llu of %s is empty or contains a sentinel ('$'/'#'): the reference panics on it "
+               "(fm_index.rs:406, bwt.rs:127)",
+               (unsigned long long)(out.n_reads + *ws->h_flag), path);
+        out.n_reads += nq;
+        out.n_bases += plan.seq_bytes;
+      }
+      tail_len = n - plan.consumed;
+      tail_src = base + plan.consumed;
+      prev_slot = si;
+      if (eof) {
+        for (uint64_t i = 0; i < tail_len; i++) {
+          uint8_t ch = tail_src[i];
+          if (ch != '\n' && ch != '\r' && ch != ' ' && ch != '\t')
+            fail(AWRY_ERR_FORMAT, "%s ends with a truncated %s record", path, fastq ? "FASTQ" : "FASTA");
+        }
+        break;
+      }
+      if (tail_len > CARRY)
+        fail(AWRY_ERR_UNSUPPORTED, "%s holds a record larger than %llu bytes (AWRY_B200_READS_CHUNK)", path,
+             (unsigned long long)CARRY);
+    }
+  } catch (...) {
+    cleanup();
+    free(out.hits);
+    out.hits = nullptr;
+    throw;
+  }
+  cleanup();
+}
+
+}  // namespace
+
+extern "C" {
+
+int awry_count_reads_file(const awry_index* ix, const char* path, uint64_t** counts, uint64_t* n_reads) {
+  return guarded([&] {
+    need(ix);
+    if (!path || !counts || !n_reads) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    *counts = nullptr;
+    *n_reads = 0;
+    ReadsOut out;
+    run_reads_file(ix, path, false, 0, out);
+    uint64_t* buf = static_cast<uint64_t*>(malloc(std::max<size_t>(8, out.n_reads * 8)));
+    if (!buf) fail(AWRY_ERR_NOMEM, "out of host memory for %llu counts", (unsigned long long)out.n_reads);
+    if (out.n_reads) memcpy(buf, out.counts.data(), out.n_reads * 8);
+    *counts = buf;
+    *n_reads = out.n_reads;
+  });
+}
+
+int awry_locate_reads_file(const awry_index* ix, const char* path, uint32_t flags, uint64_t** hit_off, awry_hit** hits,
+                           uint64_t* n_reads, uint64_t* n_hits) {
+  return guarded([&] {
+    need(ix);
+    if (!path || !hit_off || !hits || !n_reads || !n_hits) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    *hit_off = nullptr;
+    *hits = nullptr;
+    *n_reads = *n_hits = 0;
+    ReadsOut out;
+    run_reads_file(ix, path, true, flags, out);
+    uint64_t* off = static_cast<uint64_t*>(malloc((out.n_reads + 1) * 8));
+    if (!off) {
+      free(out.hits);
+      fail(AWRY_ERR_NOMEM, "out of host memory for %llu offsets", (unsigned long long)out.n_reads);
+    }
+    memcpy(off, out.hit_off.data(), (out.n_reads + 1) * 8);
+    *hit_off = off;
+    *hits = out.hits;
+    *n_reads = out.n_reads;
+    *n_hits = out.n_hits;
+  });
+}
+
+void awry_buffer_free(void* p) { free(p); }
+
+}  // extern "C"
