@@ -12,7 +12,7 @@
 //   4. plan (one thread): complete records in the chunk, bytes consumed, sequence bytes
 //   5. one warp per line                    copies sequence bytes to a contiguous query buffer and
 //                                           writes the CSR offsets the search kernels take
-// A record cut by the chunk boundary is carried over by the host (api.cu).
+// A record cut by the chunk boundary is carried over by the host (reads_api.cu).
 #include <algorithm>
 #include <cstdint>
 #include <cub/device/device_scan.cuh>
