@@ -17,14 +17,13 @@
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
-#include "kernels.hpp"
+#include "kernels_common.cuh"
 
 namespace awry {
 
-static std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_launches{0};
 uint64_t kernel_launch_count() { return g_launches.load(); }
 void kernel_launch_count_reset() { g_launches.store(0); }
-#define COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
 
 // ------------------------------------------------------------------ symbol tables
 
@@ -697,51 +696,6 @@ __global__ void __launch_bounds__(256) search_scalar_kernel(IndexView ix, const 
 // with LANES-wide xor shuffles.  Groups are persistent: when a query finishes (all symbols
 // consumed or empty interval) the group moves to query q + G, so early exits refill lanes
 // instead of idling them; all groups of a warp stay converged on the step body.
-template <int LANES>
-struct LaneChunks;
-template <>
-struct LaneChunks<4> {
-  uint4 c[1];
-  __device__ __forceinline__ void load(const uint4* blk, uint32_t sub) { c[0] = ldg128(blk + sub); }
-};
-template <>
-struct LaneChunks<2> {
-  uint4 c[2];
-  __device__ __forceinline__ void load(const uint4* blk, uint32_t sub) {
-    u32x8 v = ldg256(blk + 2 * sub);
-    c[0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
-    c[1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
-  }
-};
-template <>
-struct LaneChunks<1> {
-  uint4 c[4];
-  __device__ __forceinline__ void load(const uint4* blk, uint32_t) {
-    u32x8 v = ldg256(blk);
-    u32x8 u = ldg256(blk + 2);
-    c[0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
-    c[1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
-    c[2] = make_uint4(u.v[0], u.v[1], u.v[2], u.v[3]);
-    c[3] = make_uint4(u.v[4], u.v[5], u.v[6], u.v[7]);
-  }
-};
-
-template <int LANES>
-__device__ __forceinline__ uint32_t dna_partial_rank(const LaneChunks<LANES>& x, uint32_t sub,
-                                                     uint32_t local, uint32_t c, uint32_t m0,
-                                                     uint32_t m1) {
-  constexpr int CH = 4 / LANES;
-  uint32_t r = 0;
-#pragma unroll
-  for (int i = 0; i < CH; i++) {
-    uint32_t j = sub * CH + i;
-    uint32_t pred = ~x.c[i].z & ~(x.c[i].x ^ m0) & ~(x.c[i].y ^ m1);
-    r += __popc(pred & chunk_mask(local, j));
-    r += (j == c) ? x.c[i].w : 0u;
-  }
-  return r;
-}
-
 template <int LANES, int MODE, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB)
     search_dna_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
@@ -905,13 +859,6 @@ static cudaError_t launch_with_table_window(Kern kern, unsigned grid, unsigned b
 // Queries holding an ambiguity symbol (N) are handed to the scalar kernel through `defer`
 // (defer[0] = count, then the query numbers), which keeps this kernel's register budget small.
 // Same persistent-group refill as above.
-// low `n` bits set, n clamped to [0, 32] (BMSK)
-__device__ __forceinline__ uint32_t low_mask(int n) {
-  uint32_t m, len = uint32_t(n < 0 ? 0 : n);
-  asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(m) : "r"(0u), "r"(len));
-  return m;
-}
-
 // Which lane slice / 32-bit word of a pair block holds the count of pair p (see layout.cuh):
 // p 0-2 -> slice 0, 3-5 -> 1, 6-8 -> 2 (words 5..7), 9-15 -> slice 3 (words 0..6).
 __device__ __forceinline__ uint32_t pair_count_lane(uint32_t p) {
@@ -1159,21 +1106,6 @@ static cudaError_t launch_search_pair(const IndexView& ix, const uint64_t* d_qwo
 // Same shape as the nucleotide pair kernel: the query (8-bit symbols) is staged in a 16-word
 // shared-memory ring with one aligned read, groups refill in-loop, the warp leaves by vote and
 // the rank reduction uses full-mask shuffles.  Slices 0/1 hold the planes of rows 0-31 / 32-63.
-struct AminoSlice {
-  uint32_t match, count;
-};
-__device__ __forceinline__ AminoSlice amino_slice(const u32x8& x, uint32_t sub, uint32_t sym) {
-  AminoSlice r;
-  r.match = sub < 2 ? amino_match(x, sym) : 0u;
-  const uint32_t cw = amino_count_word(sym);  // word index in the block: lane = cw / 8, word = cw % 8
-  const uint32_t word = cw & 7u;
-  const uint32_t t0 = (word & 1) ? x.v[1] : x.v[0], t1 = (word & 1) ? x.v[3] : x.v[2];
-  const uint32_t t2 = (word & 1) ? x.v[5] : x.v[4], t3 = (word & 1) ? x.v[7] : x.v[6];
-  const uint32_t u0 = (word & 2) ? t1 : t0, u1 = (word & 2) ? t3 : t2;
-  r.count = sub == (cw >> 3) ? ((word & 4) ? u1 : u0) : 0u;
-  return r;
-}
-
 template <int MODE, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB)
     search_amino_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
@@ -1362,743 +1294,6 @@ cudaError_t launch_search(const IndexView& ix, const uint64_t* d_qwords, const u
     case OUT_RANGE_U64: return launch_search_mode<OUT_RANGE_U64>(ix, d_qwords, d_qoff, nq, d_out, d_defer, v, sm_count, s);
     default: return launch_search_mode<OUT_SP_CNT_U32>(ix, d_qwords, d_qoff, nq, d_out, d_defer, v, sm_count, s);
   }
-}
-
-// ------------------------------------------------------------------ locate
-
-struct CountOf {
-  const uint2* r;
-  uint64_t nq;
-  __host__ __device__ uint64_t operator()(uint64_t i) const { return i < nq ? uint64_t(r[i].y) : 0ull; }
-};
-
-// exclusive scan of the per-query hit counts -> CSR offsets, d_hit_off[nq] = total
-cudaError_t scan_hit_offsets(const uint2* d_sp_cnt, uint64_t nq, uint64_t* d_hit_off, void* d_temp,
-                             size_t& temp_bytes, cudaStream_t s) {
-  cub::CountingInputIterator<uint64_t> idx(0);
-  cub::TransformInputIterator<uint64_t, CountOf, cub::CountingInputIterator<uint64_t>> in(idx, CountOf{d_sp_cnt, nq});
-  cudaError_t e = cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, in, d_hit_off, nq + 1, s);
-  if (d_temp != nullptr) COUNT_LAUNCH();
-  return e;
-}
-
-// get_seq_location, intended semantics (sequence_index.rs:108-141)
-__device__ __forceinline__ void map_location(const IndexView& ix, uint64_t loc, uint64_t* out2) {
-  uint32_t lo = 0;
-  if (ix.n_seqs > 1) {
-    uint32_t hi = ix.n_seqs - 1;
-    while (lo < hi) {
-      uint32_t mid = (lo + hi + 1) >> 1;
-      if (__ldg(ix.seq_starts + mid) <= loc)
-        lo = mid;
-      else
-        hi = mid - 1;
-    }
-  }
-  out2[0] = lo;
-  out2[1] = loc - __ldg(ix.seq_starts + lo);
-}
-
-// Pass 2a: expand the CSR (query -> hit range) into one BWT row per hit, written into the low
-// 32 bits of each output slot (the walk overwrites the slot with the result).  A lane writes the
-// first 8 rows of its query; longer intervals are written by the whole warp, so a query with 10^5
-// hits costs ~3000 coalesced warp iterations instead of serialising one thread.
-__global__ void __launch_bounds__(256)
-    expand_rows_kernel(const uint2* __restrict__ sp_cnt, const uint64_t* __restrict__ hit_off, uint64_t nq,
-                       uint32_t* __restrict__ out32, uint32_t slot_u32) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint64_t warp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5;
-  const uint64_t nwarps = (gridDim.x * uint64_t(blockDim.x)) >> 5;
-  for (uint64_t base = warp * 32; base < nq; base += nwarps * 32) {
-    uint64_t q = base + lane;
-    uint32_t sp = 0, cnt = 0;
-    uint64_t off = 0;
-    if (q < nq) {
-      uint2 r = sp_cnt[q];
-      sp = r.x;
-      cnt = r.y;
-      off = hit_off[q];
-    }
-    uint32_t small = cnt < 8 ? cnt : 8;
-    for (uint32_t i = 0; i < small; i++) out32[(off + i) * slot_u32] = sp + i;
-    uint32_t big = __ballot_sync(0xffffffffu, cnt > 8);
-    while (big) {
-      int L = __ffs(big) - 1;
-      big &= big - 1;
-      uint32_t s = __shfl_sync(0xffffffffu, sp, L), c = __shfl_sync(0xffffffffu, cnt, L);
-      uint64_t o = __shfl_sync(0xffffffffu, off, L);
-      for (uint32_t i = 8 + lane; i < c; i += 32) out32[(o + i) * slot_u32] = s + i;
-    }
-  }
-}
-
-__device__ __forceinline__ void finish_hit(const IndexView& ix, uint32_t row, uint32_t steps, uint64_t* slot,
-                                           bool map) {
-  uint64_t loc = (sa_sample(ix, row) + steps) % ix.bwt_len;  // fm_index.rs:533-534
-  if (map)
-    map_location(ix, loc, slot);
-  else
-    slot[0] = loc;
-}
-
-// Pass 2b, nucleotide: 2 lanes per hit, each LDG.256 half of the 64-B block, so one LF step is ONE
-// line request (a one-thread walk issues four LDG.128 to the same line).  Lanes refill: a pair whose
-// walk ends takes the next hit, so the geometric walk lengths (rows, not text positions, are sampled:
-// compressed_suffix_array.rs:109-111) do not idle the rest of the warp.  The lane holding the row's
-// chunk extracts the BWT symbol and broadcasts it; both lanes rank their two chunks; xor-shuffle.
-// Warp-convergent loop (exit by vote) so the shuffles use the full mask.
-constexpr uint64_t WALK_TICKET = 32;  // hits per ticket (8 measured slower: 3.6 vs 2.5 ms per 10 M hits)
-
-template <bool MAP>
-__global__ void __launch_bounds__(256) walk_dna_kernel(IndexView ix, uint64_t n_hits, uint64_t* __restrict__ out, bool dynamic) {
-  constexpr int SLOT = MAP ? 2 : 1;
-  constexpr uint32_t FULL = 0xffffffffu;
-  const uint32_t lane = threadIdx.x & 31, sub = lane & 1, gbase = lane - sub;
-  // hits are handed out dynamically, WALK_TICKET at a time; the counter sits behind the output slots
-  unsigned long long* const ticket = reinterpret_cast<unsigned long long*>(out + SLOT * n_hits);
-  // small batches: a static stride keeps every group busy from the start (a ticket of 32 hits would feed
-  // only n_hits / 32 groups, and smaller tickets serialise on the counter: same-address atomics retire at
-  // ~0.35 G/s); large batches: tickets, so that the fast SMs take more
-  const uint64_t stride = (gridDim.x * uint64_t(blockDim.x)) >> 1;
-  uint64_t h = dynamic ? 0 : (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 1, h_end = dynamic ? 0 : n_hits;
-  const uint64_t step = dynamic ? 1 : stride;
-  bool more = dynamic;
-  uint64_t cur = 0;
-  uint32_t row = 0, steps = 0;
-  bool have = false;
-  for (;;) {
-    if (!have && h >= h_end && more) {
-      unsigned long long t = 0;
-      if (sub == 0) t = atomicAdd(ticket, (unsigned long long)WALK_TICKET);
-      t = __shfl_sync(0x3u << gbase, t, gbase);
-      more = t < n_hits;
-      h = more ? t : 0;
-      h_end = more ? (n_hits - t < WALK_TICKET ? n_hits : t + WALK_TICKET) : 0;
-    }
-    if (!have && h < h_end) {
-      cur = h;
-      h += step;
-      row = uint32_t(out[SLOT * cur]);
-      steps = 0;
-      have = true;
-    }
-    if (__all_sync(FULL, !have && !more && h >= h_end)) break;
-    if (have && row_is_sampled(ix, row)) {
-      if (sub == 0) finish_hit(ix, row, steps, out + SLOT * cur, MAP);
-      have = false;
-    }
-    const uint32_t blk = row >> 7, l = row & 127;
-    LaneChunks<2> x;
-    x.c[0] = x.c[1] = make_uint4(0, 0, 0, 0);
-    if (have) x.load(ix.blocks + size_t(blk) * DNA_BLOCK_UINT4, sub);
-    const uint4 ch = (l & 32) ? x.c[1] : x.c[0];
-    const uint32_t t = l & 31;
-    uint32_t c = ((ch.x >> t) & 1u) | (((ch.y >> t) & 1u) << 1) | (((ch.z >> t) & 1u) << 2);
-    c = __shfl_sync(FULL, c, gbase + (l >> 6));  // from the lane that owns chunk l/32
-    uint32_t r = 0;
-    if (have && c < 4) r = dna_partial_rank<2>(x, sub, l, c, (c & 1) ? ~0u : 0u, (c & 2) ? ~0u : 0u);
-    r += __shfl_xor_sync(FULL, r, 1);
-    if (have) {
-      if (c >= uint32_t(DNA_SENTINEL))
-        row = 0;  // the '$' row: fm_index.rs:587-589
-      else if (c == uint32_t(DNA_N))
-        row = lf_backstep<0>(ix, row);  // rare: scalar step
-      else
-        row = ix.c_lo[c] + r - 1;
-      steps++;
-    }
-  }
-}
-
-// Pass 2b, amino: 4 lanes per hit on the 128-B block (one line request per LF step); the lane that
-// holds the row's 32-row slice extracts the symbol index from its 5 planes and broadcasts it.
-template <bool MAP>
-__global__ void __launch_bounds__(256) walk_amino_kernel(IndexView ix, uint64_t n_hits, uint64_t* __restrict__ out, bool dynamic) {
-  constexpr int SLOT = MAP ? 2 : 1;
-  constexpr uint32_t FULL = 0xffffffffu;
-  const uint32_t lane = threadIdx.x & 31, sub = lane & 3, gbase = lane - sub;
-  unsigned long long* const ticket = reinterpret_cast<unsigned long long*>(out + SLOT * n_hits);
-  const uint64_t stride = (gridDim.x * uint64_t(blockDim.x)) >> 2;
-  uint64_t h = dynamic ? 0 : (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 2, h_end = dynamic ? 0 : n_hits;
-  const uint64_t step = dynamic ? 1 : stride;
-  bool more = dynamic;
-  uint64_t cur = 0;
-  uint32_t row = 0, steps = 0;
-  bool have = false;
-  for (;;) {
-    if (!have && h >= h_end && more) {
-      unsigned long long t = 0;
-      if (sub == 0) t = atomicAdd(ticket, (unsigned long long)WALK_TICKET);
-      t = __shfl_sync(0xfu << gbase, t, gbase);
-      more = t < n_hits;
-      h = more ? t : 0;
-      h_end = more ? (n_hits - t < WALK_TICKET ? n_hits : t + WALK_TICKET) : 0;
-    }
-    if (!have && h < h_end) {
-      cur = h;
-      h += step;
-      row = uint32_t(out[SLOT * cur]);
-      steps = 0;
-      have = true;
-    }
-    if (__all_sync(FULL, !have && !more && h >= h_end)) break;
-    if (have && row_is_sampled(ix, row)) {
-      if (sub == 0) finish_hit(ix, row, steps, out + SLOT * cur, MAP);
-      have = false;
-    }
-    const uint32_t blk = row >> 6, l = row & 63;
-    u32x8 x;
-#pragma unroll
-    for (int i = 0; i < 8; i++) x.v[i] = 0;
-    if (have) x = ldg256(ix.blocks + size_t(blk) * AMINO_BLOCK_UINT4 + 2 * sub);
-    const uint32_t t = l & 31;
-    uint32_t c = 0;
-#pragma unroll
-    for (int p = 0; p < 5; p++) c |= ((x.v[p] >> t) & 1u) << p;
-    c = __shfl_sync(FULL, c, gbase + (l >> 5));  // from the lane that owns rows 32*(l/32)..
-    uint32_t r = 0;
-    if (have && c != uint32_t(AMINO_SENTINEL) && c <= 21) {
-      AminoSlice s = amino_slice(x, sub, c);
-      r = __popc(s.match & low_mask(int(l) + 1 - int(32 * sub))) + s.count;
-    }
-    r += __shfl_xor_sync(FULL, r, 1);
-    r += __shfl_xor_sync(FULL, r, 2);
-    if (have) {
-      row = (c == uint32_t(AMINO_SENTINEL) || c > 21) ? 0u : ix.c_lo[c] + r - 1;  // '$' row -> 0
-      steps++;
-    }
-  }
-}
-
-// ---- unsampled suffix array: the locate accelerator (derived at load time, like the pair index) ----
-// The reference keeps SA[row] only for rows with row % ratio == 0 (compressed_suffix_array.rs:109-111)
-// and pays a geometric LF-walk per hit (fm_index.rs:521-537).  180 GB of HBM hold the whole array:
-// 4 B x bwt_len (12.4 GB for the 3.1 Gbp config).  It is rebuilt from the sampled one with ONE LF step
-// per BWT row: a walker starts at every sampled row r with p = SA[r] and writes SA[LF^s(r)] = p - s
-// until it reaches the next sampled row or the '$' row (SA = 0); the LF permutation is one cycle cut at
-// the sampled rows, so every row is written exactly once.  Same lane-group step as the walk kernels.
-constexpr uint64_t UNSAMPLE_TICKET = 32;  // sampled rows per ticket
-
-__global__ void __launch_bounds__(256)
-    unsample_dna_kernel(IndexView ix, uint64_t n_elems, uint32_t* __restrict__ full) {
-  constexpr uint32_t FULL = 0xffffffffu;
-  const uint32_t lane = threadIdx.x & 31, sub = lane & 1, gbase = lane - sub;
-  // sampled rows are handed out dynamically, UNSAMPLE_TICKET at a time (walk lengths are geometric and the
-  // SMs do not all see the same random-access throughput); the counter sits behind the array
-  unsigned long long* const ticket = reinterpret_cast<unsigned long long*>(full + ((size_t(ix.bwt_len) + 3) & ~size_t(1)));
-  uint64_t e = 0, e_end = 0;
-  bool more = true;
-  uint32_t row = 0, p = 0;
-  bool have = false;
-  for (;;) {
-    if (!have && e == e_end && more) {
-      unsigned long long t = 0;
-      if (sub == 0) t = atomicAdd(ticket, (unsigned long long)UNSAMPLE_TICKET);
-      t = __shfl_sync(0x3u << gbase, t, gbase);
-      more = t < n_elems;
-      e = more ? t : 0;
-      e_end = more ? (n_elems - t < UNSAMPLE_TICKET ? n_elems : t + UNSAMPLE_TICKET) : 0;
-    }
-    if (!have && e < e_end) {
-      row = uint32_t(e * ix.sa_ratio);
-      p = uint32_t(sa_sample(ix, row));
-      e++;
-      have = true;
-      if (sub == 0) full[row] = p;
-    }
-    if (__all_sync(FULL, !have && !more && e == e_end)) break;
-    const uint32_t blk = row >> 7, l = row & 127;
-    LaneChunks<2> x;
-    x.c[0] = x.c[1] = make_uint4(0, 0, 0, 0);
-    if (have) x.load(ix.blocks + size_t(blk) * DNA_BLOCK_UINT4, sub);
-    const uint4 ch = (l & 32) ? x.c[1] : x.c[0];
-    const uint32_t t = l & 31;
-    uint32_t c = ((ch.x >> t) & 1u) | (((ch.y >> t) & 1u) << 1) | (((ch.z >> t) & 1u) << 2);
-    c = __shfl_sync(FULL, c, gbase + (l >> 6));
-    uint32_t r = 0;
-    if (have && c < 4) r = dna_partial_rank<2>(x, sub, l, c, (c & 1) ? ~0u : 0u, (c & 2) ? ~0u : 0u);
-    r += __shfl_xor_sync(FULL, r, 1);
-    if (have) {
-      if (c >= uint32_t(DNA_SENTINEL)) {
-        have = false;  // the '$' row (SA = 0, already written): LF would wrap to row 0, a sampled row
-      } else {
-        row = c == uint32_t(DNA_N) ? lf_backstep<0>(ix, row) : ix.c_lo[c] + r - 1;
-        p--;
-        if (row_is_sampled(ix, row))
-          have = false;
-        else if (sub == 0)
-          full[row] = p;
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256)
-    unsample_amino_kernel(IndexView ix, uint64_t n_elems, uint32_t* __restrict__ full) {
-  constexpr uint32_t FULL = 0xffffffffu;
-  const uint32_t lane = threadIdx.x & 31, sub = lane & 3, gbase = lane - sub;
-  unsigned long long* const ticket = reinterpret_cast<unsigned long long*>(full + ((size_t(ix.bwt_len) + 3) & ~size_t(1)));
-  uint64_t e = 0, e_end = 0;
-  bool more = true;
-  uint32_t row = 0, p = 0;
-  bool have = false;
-  for (;;) {
-    if (!have && e == e_end && more) {
-      unsigned long long t = 0;
-      if (sub == 0) t = atomicAdd(ticket, (unsigned long long)UNSAMPLE_TICKET);
-      t = __shfl_sync(0xfu << gbase, t, gbase);
-      more = t < n_elems;
-      e = more ? t : 0;
-      e_end = more ? (n_elems - t < UNSAMPLE_TICKET ? n_elems : t + UNSAMPLE_TICKET) : 0;
-    }
-    if (!have && e < e_end) {
-      row = uint32_t(e * ix.sa_ratio);
-      p = uint32_t(sa_sample(ix, row));
-      e++;
-      have = true;
-      if (sub == 0) full[row] = p;
-    }
-    if (__all_sync(FULL, !have && !more && e == e_end)) break;
-    const uint32_t blk = row >> 6, l = row & 63;
-    u32x8 x;
-#pragma unroll
-    for (int i = 0; i < 8; i++) x.v[i] = 0;
-    if (have) x = ldg256(ix.blocks + size_t(blk) * AMINO_BLOCK_UINT4 + 2 * sub);
-    const uint32_t t = l & 31;
-    uint32_t c = 0;
-#pragma unroll
-    for (int q = 0; q < 5; q++) c |= ((x.v[q] >> t) & 1u) << q;
-    c = __shfl_sync(FULL, c, gbase + (l >> 5));
-    uint32_t r = 0;
-    const bool sym_ok = c != uint32_t(AMINO_SENTINEL) && c <= 21;
-    if (have && sym_ok) {
-      AminoSlice sl = amino_slice(x, sub, c);
-      r = __popc(sl.match & low_mask(int(l) + 1 - int(32 * sub))) + sl.count;
-    }
-    r += __shfl_xor_sync(FULL, r, 1);
-    r += __shfl_xor_sync(FULL, r, 2);
-    if (have) {
-      if (!sym_ok) {
-        have = false;
-      } else {
-        row = ix.c_lo[c] + r - 1;
-        p--;
-        if (row_is_sampled(ix, row))
-          have = false;
-        else if (sub == 0)
-          full[row] = p;
-      }
-    }
-  }
-}
-
-cudaError_t build_full_sa(const IndexView& ix, uint32_t* d_full, int sm_count, cudaStream_t s) {
-  const uint64_t n_elems = (uint64_t(ix.bwt_len) + ix.sa_ratio - 1) / ix.sa_ratio;
-  const uint64_t lanes = ix.alphabet == 0 ? 2 : 4;
-  unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (lanes * n_elems + 255) / 256)));
-  // ticket counter: 8 aligned bytes behind the array (the caller allocates 4 * bwt_len + 256)
-  cudaError_t e0 = cudaMemsetAsync(d_full + ((size_t(ix.bwt_len) + 3) & ~size_t(1)), 0, 8, s);
-  if (e0 != cudaSuccess) return e0;
-  if (ix.alphabet == 0)
-    unsample_dna_kernel<<<grid, 256, 0, s>>>(ix, n_elems, d_full);
-  else
-    unsample_amino_kernel<<<grid, 256, 0, s>>>(ix, n_elems, d_full);
-  COUNT_LAUNCH();
-  return cudaGetLastError();
-}
-
-// Locate pass 2 on the unsampled array: hit i of query q is SA[sp + i] -- no walk.  Same work split as
-// expand_rows_kernel: a lane copies the first 8 hits of its query, longer intervals are copied by the
-// whole warp (coalesced 128-B reads of SA, coalesced writes), so skewed hit counts cost bandwidth, not
-// serial steps.
-template <bool MAP>
-__global__ void __launch_bounds__(256)
-    gather_sa_kernel(IndexView ix, const uint2* __restrict__ sp_cnt, const uint64_t* __restrict__ hit_off,
-                     uint64_t nq, uint64_t* __restrict__ out) {
-  constexpr int SLOT = MAP ? 2 : 1;
-  const uint32_t* __restrict__ full = ix.full_sa;
-  const uint32_t lane = threadIdx.x & 31;
-  const uint64_t warp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5;
-  const uint64_t nwarps = (gridDim.x * uint64_t(blockDim.x)) >> 5;
-  for (uint64_t base = warp * 32; base < nq; base += nwarps * 32) {
-    uint64_t q = base + lane;
-    uint32_t sp = 0, cnt = 0;
-    uint64_t off = 0;
-    if (q < nq) {
-      uint2 r = sp_cnt[q];
-      sp = r.x;
-      cnt = r.y;
-      off = hit_off[q];
-    }
-    uint32_t small = cnt < 8 ? cnt : 8;
-    for (uint32_t i = 0; i < small; i++) {
-      uint64_t loc = __ldg(full + sp + i);
-      if (MAP)
-        map_location(ix, loc, out + SLOT * (off + i));
-      else
-        out[off + i] = loc;
-    }
-    uint32_t big = __ballot_sync(0xffffffffu, cnt > 8);
-    while (big) {
-      int L = __ffs(big) - 1;
-      big &= big - 1;
-      uint32_t s = __shfl_sync(0xffffffffu, sp, L), c = __shfl_sync(0xffffffffu, cnt, L);
-      uint64_t o = __shfl_sync(0xffffffffu, off, L);
-      for (uint32_t i = 8 + lane; i < c; i += 32) {
-        uint64_t loc = __ldg(full + s + i);
-        if (MAP)
-          map_location(ix, loc, out + SLOT * (o + i));
-        else
-          out[o + i] = loc;
-      }
-    }
-  }
-}
-
-cudaError_t launch_walk(const IndexView& ix, const uint2* d_sp_cnt, const uint64_t* d_hit_off,
-                        uint64_t nq, uint64_t n_hits, uint64_t* d_hits_pairs, uint64_t* d_locs,
-                        int sm_count, cudaStream_t s) {
-  if (n_hits == 0 || nq == 0) return cudaSuccess;
-  const bool map = d_hits_pairs != nullptr;
-  uint64_t* out = map ? d_hits_pairs : d_locs;
-  if (ix.full_sa != nullptr) {  // unsampled array present: a gather instead of expand + walk
-    unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (nq + 255) / 256)));
-    if (map)
-      gather_sa_kernel<true><<<grid, 256, 0, s>>>(ix, d_sp_cnt, d_hit_off, nq, out);
-    else
-      gather_sa_kernel<false><<<grid, 256, 0, s>>>(ix, d_sp_cnt, d_hit_off, nq, out);
-    COUNT_LAUNCH();
-    return cudaGetLastError();
-  }
-  {
-    unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (nq + 255) / 256)));
-    expand_rows_kernel<<<grid, 256, 0, s>>>(d_sp_cnt, d_hit_off, nq, reinterpret_cast<uint32_t*>(out), map ? 4u : 2u);
-    COUNT_LAUNCH();
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-  }
-  {  // ticket counter of the walk kernels: 8 bytes behind the output slots (the caller allocates +16)
-    cudaError_t e = cudaMemsetAsync(out + (map ? 2 : 1) * n_hits, 0, 8, s);
-    if (e != cudaSuccess) return e;
-  }
-  if (ix.alphabet == 0) {
-    unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (2 * n_hits + 255) / 256)));
-    const bool dynamic = n_hits >= 64 * ((uint64_t(grid) * 256) >> 1);
-    if (map)
-      walk_dna_kernel<true><<<grid, 256, 0, s>>>(ix, n_hits, out, dynamic);
-    else
-      walk_dna_kernel<false><<<grid, 256, 0, s>>>(ix, n_hits, out, dynamic);
-  } else {
-    unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (4 * n_hits + 255) / 256)));
-    const bool dynamic = n_hits >= 64 * ((uint64_t(grid) * 256) >> 2);
-    if (map)
-      walk_amino_kernel<true><<<grid, 256, 0, s>>>(ix, n_hits, out, dynamic);
-    else
-      walk_amino_kernel<false><<<grid, 256, 0, s>>>(ix, n_hits, out, dynamic);
-  }
-  COUNT_LAUNCH();
-  return cudaGetLastError();
-}
-
-// per-query ascending sort of global text positions (== (seq_idx, local_pos) order)
-cudaError_t sort_hit_segments(uint64_t* d_locs_in, uint64_t* d_locs_out, uint64_t n_hits,
-                              uint64_t nq, const uint64_t* d_hit_off, void* d_temp,
-                              size_t& temp_bytes, cudaStream_t s) {
-  cudaError_t e = cub::DeviceSegmentedSort::SortKeys(d_temp, temp_bytes, d_locs_in, d_locs_out,
-                                                     (long long)n_hits, (long long)nq, d_hit_off,
-                                                     d_hit_off + 1, s);
-  if (d_temp != nullptr) COUNT_LAUNCH();
-  return e;
-}
-
-__global__ void map_locations_kernel(IndexView ix, const uint64_t* __restrict__ locs, uint64_t n,
-                                     uint64_t* __restrict__ out) {
-  uint64_t stride = gridDim.x * uint64_t(blockDim.x);
-  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += stride)
-    map_location(ix, locs[i], out + 2 * i);
-}
-
-cudaError_t launch_map_locations(const IndexView& ix, const uint64_t* d_locs, uint64_t n_hits,
-                                 uint64_t* d_hits_pairs, cudaStream_t s) {
-  if (n_hits == 0) return cudaSuccess;
-  unsigned grid = unsigned(std::min<uint64_t>((n_hits + 255) / 256, 148 * 16));
-  map_locations_kernel<<<grid, 256, 0, s>>>(ix, d_locs, n_hits, d_hits_pairs);
-  COUNT_LAUNCH();
-  return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------ single steps
-
-template <int ALPHA>
-__global__ void single_update_kernel(IndexView ix, uint32_t sp, uint32_t ep, uint32_t c, uint32_t* out) {
-  lf_update<ALPHA>(ix, sp, ep, c);
-  out[0] = sp;
-  out[1] = ep;
-}
-template <int ALPHA>
-__global__ void single_backstep_kernel(IndexView ix, uint32_t row, uint32_t* out) {
-  out[0] = lf_backstep<ALPHA>(ix, row);
-}
-cudaError_t launch_single_update(const IndexView& ix, uint32_t sp, uint32_t ep, uint32_t dsym,
-                                 uint32_t* d_out2, cudaStream_t s) {
-  if (ix.alphabet == 0)
-    single_update_kernel<0><<<1, 1, 0, s>>>(ix, sp, ep, dsym, d_out2);
-  else
-    single_update_kernel<1><<<1, 1, 0, s>>>(ix, sp, ep, dsym, d_out2);
-  COUNT_LAUNCH();
-  return cudaGetLastError();
-}
-cudaError_t launch_single_backstep(const IndexView& ix, uint32_t row, uint32_t* d_out, cudaStream_t s) {
-  if (ix.alphabet == 0)
-    single_backstep_kernel<0><<<1, 1, 0, s>>>(ix, row, d_out);
-  else
-    single_backstep_kernel<1><<<1, 1, 0, s>>>(ix, row, d_out);
-  COUNT_LAUNCH();
-  return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------ random-gather roofline probe
-
-__device__ __forceinline__ uint64_t mix64(uint64_t z) {
-  z += 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
-}
-
-// LANES consecutive lanes read one GRANULE-byte aligned granule at a uniformly random place;
-// UNROLL independent granules per group are in flight before any is consumed.
-template <int GRANULE, int LANES, int UNROLL>
-__global__ void __launch_bounds__(256) gather_kernel(const char* __restrict__ buf, uint64_t n_granules,
-                                                     uint64_t reads_per_group, uint64_t seed,
-                                                     uint32_t* __restrict__ sink) {
-  constexpr int BYTES = GRANULE / LANES;          // per lane
-  constexpr int NV = BYTES >= 32 ? BYTES / 32 : 1;  // vector loads per lane
-  const uint32_t lane = threadIdx.x & 31, sub = lane % LANES;
-  const uint64_t group = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) / LANES;
-  uint32_t acc = 0;
-  // cheap address stream (the probe must not be ALU-bound): 64-bit LCG per group, high product
-  uint64_t x = mix64(seed ^ (group * 0x100000001B3ull));
-  for (uint64_t it = 0; it < reads_per_group; it += UNROLL) {
-    uint32_t v[UNROLL][NV * (BYTES >= 32 ? 8 : BYTES / 4)];
-#pragma unroll
-    for (int u = 0; u < UNROLL; u++) {
-      x = x * 6364136223846793005ull + 1442695040888963407ull;
-      uint64_t g = __umul64hi(x, n_granules);
-      const char* p = buf + g * GRANULE + sub * BYTES;
-      if (BYTES >= 32) {
-#pragma unroll
-        for (int i = 0; i < NV; i++) {
-          u32x8 r = ldg256(p + 32 * i);
-#pragma unroll
-          for (int k = 0; k < 8; k++) v[u][8 * i + k] = r.v[k];
-        }
-      } else if (BYTES == 16) {
-        uint4 r = ldg128(reinterpret_cast<const uint4*>(p));
-        v[u][0] = r.x, v[u][1] = r.y, v[u][2] = r.z, v[u][3] = r.w;
-      } else {
-        uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
-        v[u][0] = r.x, v[u][1] = r.y;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UNROLL; u++)
-#pragma unroll
-      for (int k = 0; k < int(sizeof(v[0]) / 4); k++) acc ^= v[u][k];
-  }
-  if (acc == 0x12345678u) sink[0] = acc;
-}
-
-// ---- TMA variant of the probe: one THREAD per read; a 128-B bulk async copy (cp.async.bulk, the
-// 1-D TMA path) lands the granule in the thread's shared-memory slot and completes a per-thread
-// mbarrier, so a request in flight costs no registers.
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_load_128(void* dst_smem, const void* src_gmem, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 128, [%2];" ::"r"(
-                   smem_addr(dst_smem)),
-               "l"(src_gmem), "r"(smem_addr(bar))
-               : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-      : "=r"(ok)
-      : "r"(smem_addr(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-template <int DEPTH>
-__global__ void __launch_bounds__(256) gather_tma_kernel(const char* __restrict__ buf, uint64_t n_granules,
-                                                         uint64_t reads_per_thread, uint64_t seed,
-                                                         uint32_t* __restrict__ sink) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* slots = smem;                                                   // [DEPTH][256][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DEPTH * 256 * 128);  // [DEPTH][256]
-  const uint32_t t = threadIdx.x;
-#pragma unroll
-  for (int d = 0; d < DEPTH; d++) mbar_init(&bars[d * 256 + t], 1);
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  fence_proxy_async();
-  __syncthreads();
-  uint64_t x = mix64(seed ^ ((blockIdx.x * uint64_t(blockDim.x) + t) * 0x100000001B3ull));
-  uint32_t acc = 0;
-  auto issue = [&](int d) {
-    x = x * 6364136223846793005ull + 1442695040888963407ull;
-    uint64_t g = __umul64hi(x, n_granules);
-    mbar_expect_tx(&bars[d * 256 + t], 128);
-    bulk_load_128(slots + (size_t(d) * 256 + t) * 128, buf + g * 128, &bars[d * 256 + t]);
-  };
-#pragma unroll
-  for (int d = 0; d < DEPTH; d++) issue(d);
-  uint32_t parity = 0;
-  for (uint64_t it = 0; it < reads_per_thread; it += DEPTH) {
-#pragma unroll
-    for (int d = 0; d < DEPTH; d++) {
-      while (!mbar_try_wait(&bars[d * 256 + t], parity)) {
-      }
-      const uint4* s = reinterpret_cast<const uint4*>(slots + (size_t(d) * 256 + t) * 128);
-      uint4 a = s[(t + d) & 7];  // one 16-B word of the landed granule
-      acc ^= a.x ^ a.y ^ a.z ^ a.w;
-      fence_proxy_async();  // order the generic read before the next async write to the slot
-      if (it + DEPTH < reads_per_thread) issue(d);
-    }
-    parity ^= 1;
-  }
-  if (acc == 0x12345678u) sink[0] = acc;
-}
-
-template <int DEPTH>
-static cudaError_t gather_tma_run(const char* buf, uint64_t n_granules, uint64_t n_reads, int iters,
-                                  uint32_t* sink, double* ms_out) {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const size_t smem = size_t(DEPTH) * 256 * (128 + 8);
-  cudaError_t e = cudaFuncSetAttribute(gather_tma_kernel<DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  if (e != cudaSuccess) return e;
-  int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_tma_kernel<DEPTH>, 256, smem);
-  if (e != cudaSuccess) return e;
-  unsigned grid = unsigned(sms * std::max(per_sm, 1));
-  uint64_t threads = uint64_t(grid) * 256;
-  uint64_t per_thread = ((n_reads + threads - 1) / threads + DEPTH - 1) / DEPTH * DEPTH;
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
-  float best = 1e30f;
-  for (int i = 0; i < iters + 1; i++) {
-    cudaEventRecord(e0);
-    gather_tma_kernel<DEPTH><<<grid, 256, smem>>>(buf, n_granules, per_thread, 0x5eed + i, sink);
-    cudaEventRecord(e1);
-    e = cudaEventSynchronize(e1);
-    if (e != cudaSuccess) return e;
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    if (i > 0 && ms < best) best = ms;
-    COUNT_LAUNCH();
-  }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  fprintf(stderr, "[gather_tma depth %d] %d blocks/SM, %llu reads/thread\n", DEPTH, per_sm, (unsigned long long)per_thread);
-  *ms_out = double(best) / (double(per_thread * threads) / double(n_reads));
-  return cudaGetLastError();
-}
-
-template <int GRANULE, int LANES, int UNROLL = 4>
-static cudaError_t gather_run(const char* buf, uint64_t n_granules, uint64_t n_reads, int iters,
-                              uint32_t* sink, double* ms_out, int blocks_per_sm = 8) {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  unsigned grid = unsigned(sms) * unsigned(blocks_per_sm);
-  uint64_t groups = uint64_t(grid) * 256 / LANES;
-  uint64_t per_group = ((n_reads + groups - 1) / groups + UNROLL - 1) / UNROLL * UNROLL;
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
-  float best = 1e30f;
-  for (int i = 0; i < iters + 1; i++) {
-    cudaEventRecord(e0);
-    gather_kernel<GRANULE, LANES, UNROLL><<<grid, 256>>>(buf, n_granules, per_group, 0x5eed + i, sink);
-    cudaEventRecord(e1);
-    cudaError_t e = cudaEventSynchronize(e1);
-    if (e != cudaSuccess) return e;
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    if (i > 0 && ms < best) best = ms;
-    COUNT_LAUNCH();
-  }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  *ms_out = double(best) / (double(per_group * groups) / double(n_reads));  // normalise to n_reads
-  return cudaGetLastError();
-}
-
-cudaError_t run_random_gather(uint64_t footprint_bytes, uint32_t granule, uint32_t lanes,
-                              uint64_t n_reads, int iters, double* reads_per_s, double* gb_per_s) {
-  char* buf = nullptr;
-  uint32_t* sink = nullptr;
-  cudaError_t e = cudaMalloc(&buf, footprint_bytes);
-  if (e != cudaSuccess) return e;
-  e = cudaMalloc(&sink, 4);
-  if (e != cudaSuccess) {
-    cudaFree(buf);
-    return e;
-  }
-  cudaMemset(buf, 1, footprint_bytes);
-  uint64_t n_granules = footprint_bytes / granule;
-  double ms = 0;
-  e = cudaErrorInvalidValue;
-#define GATHER_CASE(G, L) \
-  if (granule == G && lanes == L) e = gather_run<G, L>(buf, n_granules, n_reads, iters, sink, &ms);
-  GATHER_CASE(32, 1) GATHER_CASE(32, 2) GATHER_CASE(32, 4)
-  GATHER_CASE(64, 1) GATHER_CASE(64, 2) GATHER_CASE(64, 4) GATHER_CASE(64, 8)
-  GATHER_CASE(128, 1) GATHER_CASE(128, 2) GATHER_CASE(128, 4) GATHER_CASE(128, 8)
-#undef GATHER_CASE
-  // lanes = 104 / 102: the 128-B / 4-lane probe with ONE / TWO reads in flight per lane group (the
-  // dependent-chain shape of the search kernels) instead of four
-  if (granule == 128 && lanes == 104) e = gather_run<128, 4, 1>(buf, n_granules, n_reads, iters, sink, &ms);
-  if (granule == 128 && lanes == 102) e = gather_run<128, 4, 2>(buf, n_granules, n_reads, iters, sink, &ms);
-  // lanes = 1000 + 10 * blocks_per_sm + unroll: 128-B / 4-lane probe at reduced residency (256-thread blocks)
-  if (granule == 128 && lanes >= 1000 && lanes < 2000) {
-    int bps = int(lanes - 1000) / 10, un = int(lanes - 1000) % 10;
-    if (un == 1) e = gather_run<128, 4, 1>(buf, n_granules, n_reads, iters, sink, &ms, bps);
-    if (un == 2) e = gather_run<128, 4, 2>(buf, n_granules, n_reads, iters, sink, &ms, bps);
-    if (un == 4) e = gather_run<128, 4, 4>(buf, n_granules, n_reads, iters, sink, &ms, bps);
-    if (un == 8) e = gather_run<128, 4, 8>(buf, n_granules, n_reads, iters, sink, &ms, bps);
-  }
-  // lanes = 3000 + 10 * waves + unroll: full residency, `waves` x as many blocks as fit at once, so the
-  // hardware block scheduler balances the SMs dynamically (a static split ends with the slowest SM)
-  if (granule == 128 && lanes >= 3000 && lanes < 4000) {
-    int waves = int(lanes - 3000) / 10, un = int(lanes - 3000) % 10;
-    if (un == 1) e = gather_run<128, 4, 1>(buf, n_granules, n_reads, iters, sink, &ms, 8 * waves);
-    if (un == 2) e = gather_run<128, 4, 2>(buf, n_granules, n_reads, iters, sink, &ms, 8 * waves);
-    if (un == 4) e = gather_run<128, 4, 4>(buf, n_granules, n_reads, iters, sink, &ms, 8 * waves);
-    if (un == 8) e = gather_run<128, 4, 8>(buf, n_granules, n_reads, iters, sink, &ms, 8 * waves);
-  }
-  // lanes = 4000 + waves / 5000 + waves: the same with 2 lanes x 2 LDG.256 / 1 lane x 4 LDG.256 per read
-  if (granule == 128 && lanes >= 4000 && lanes < 5000)
-    e = gather_run<128, 2, 4>(buf, n_granules, n_reads, iters, sink, &ms, 8 * int(lanes - 4000));
-  if (granule == 128 && lanes >= 5000 && lanes < 6000)
-    e = gather_run<128, 1, 4>(buf, n_granules, n_reads, iters, sink, &ms, 8 * int(lanes - 5000));
-  // lanes = 201 / 202: one thread per read through cp.async.bulk + mbarrier, 1 / 2 reads in flight per thread
-  if (granule == 128 && lanes == 201) e = gather_tma_run<1>(buf, n_granules, n_reads, iters, sink, &ms);
-  if (granule == 128 && lanes == 202) e = gather_tma_run<2>(buf, n_granules, n_reads, iters, sink, &ms);
-  cudaFree(buf);
-  cudaFree(sink);
-  if (e != cudaSuccess) return e;
-  *reads_per_s = double(n_reads) / (ms * 1e-3);
-  *gb_per_s = *reads_per_s * granule * 1e-9;
-  return cudaSuccess;
 }
 
 }  // namespace awry

@@ -1,0 +1,87 @@
+// kernels_common.cuh -- device helpers shared by the kernel translation units (kernels.cu: load-time
+// re-layout, seed table, pair index, query packing, backward search; kernels_locate.cu: locate pass 2, the
+// unsampled suffix array, single steps; kernels_probe.cu: the random-gather roofline probe).
+#pragma once
+#include <atomic>
+
+#include "kernels.hpp"
+
+namespace awry {
+
+extern std::atomic<uint64_t> g_launches;  // kernels launched by this library (awry_profile_get)
+#define COUNT_LAUNCH() ::awry::g_launches.fetch_add(1, std::memory_order_relaxed)
+
+// ---- a lane's share of a 64-B nucleotide block: LANES lanes cooperate on one block ----
+template <int LANES>
+struct LaneChunks;
+template <>
+struct LaneChunks<4> {
+  uint4 c[1];
+  __device__ __forceinline__ void load(const uint4* blk, uint32_t sub) { c[0] = ldg128(blk + sub); }
+};
+template <>
+struct LaneChunks<2> {
+  uint4 c[2];
+  __device__ __forceinline__ void load(const uint4* blk, uint32_t sub) {
+    u32x8 v = ldg256(blk + 2 * sub);
+    c[0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+    c[1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+  }
+};
+template <>
+struct LaneChunks<1> {
+  uint4 c[4];
+  __device__ __forceinline__ void load(const uint4* blk, uint32_t) {
+    u32x8 v = ldg256(blk);
+    u32x8 u = ldg256(blk + 2);
+    c[0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+    c[1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+    c[2] = make_uint4(u.v[0], u.v[1], u.v[2], u.v[3]);
+    c[3] = make_uint4(u.v[4], u.v[5], u.v[6], u.v[7]);
+  }
+};
+
+template <int LANES>
+__device__ __forceinline__ uint32_t dna_partial_rank(const LaneChunks<LANES>& x, uint32_t sub,
+                                                     uint32_t local, uint32_t c, uint32_t m0,
+                                                     uint32_t m1) {
+  constexpr int CH = 4 / LANES;
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < CH; i++) {
+    uint32_t j = sub * CH + i;
+    uint32_t pred = ~x.c[i].z & ~(x.c[i].x ^ m0) & ~(x.c[i].y ^ m1);
+    r += __popc(pred & chunk_mask(local, j));
+    r += (j == c) ? x.c[i].w : 0u;
+  }
+  return r;
+}
+
+
+// low `n` bits set, n clamped to [0, 32] (BMSK)
+__device__ __forceinline__ uint32_t low_mask(int n) {
+  uint32_t m, len = uint32_t(n < 0 ? 0 : n);
+  asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(m) : "r"(0u), "r"(len));
+  return m;
+}
+
+
+// ---- a lane's share of a 128-B amino block (4 lanes): matching rows of its 32-row slice and, in the
+// lane that holds it, the block-start count of the symbol ----
+struct AminoSlice {
+  uint32_t match, count;
+};
+__device__ __forceinline__ AminoSlice amino_slice(const u32x8& x, uint32_t sub, uint32_t sym) {
+  AminoSlice r;
+  r.match = sub < 2 ? amino_match(x, sym) : 0u;
+  const uint32_t cw = amino_count_word(sym);  // word index in the block: lane = cw / 8, word = cw % 8
+  const uint32_t word = cw & 7u;
+  const uint32_t t0 = (word & 1) ? x.v[1] : x.v[0], t1 = (word & 1) ? x.v[3] : x.v[2];
+  const uint32_t t2 = (word & 1) ? x.v[5] : x.v[4], t3 = (word & 1) ? x.v[7] : x.v[6];
+  const uint32_t u0 = (word & 2) ? t1 : t0, u1 = (word & 2) ? t3 : t2;
+  r.count = sub == (cw >> 3) ? ((word & 4) ? u1 : u0) : 0u;
+  return r;
+}
+
+
+}  // namespace awry
