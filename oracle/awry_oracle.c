@@ -5,6 +5,15 @@
  * in-memory block layout (160-B nucleotide / 352-B amino blocks) and `.awry` v1 file
  * format.  Scalar 4 x u64 plane arithmetic stands in for the AVX2/NEON intrinsics of
  * simd_instructions.rs (bit-identical by construction; gcc -O3 -mavx2 vectorises it).
+ *
+ * Pinning status: the reference is a Rust crate and no Rust toolchain exists in the build image, so
+ * no output of the reference binary itself is available (no oracle/_ref).  This restatement is pinned by
+ * what the reference's own tests hold for the path -- its literal vectors (bits_per_element table,
+ * symbol code tables) and its properties re-run at the same sizes (rank == brute force, sampled-SA round
+ * trip, every k-mer counted and located == substring search, save -> load equality) -- and by the worked
+ * example of SURVEY.md Appendix A (tests/test_oracle.py, tests/golden/appendix_a.awry).  It is NOT pinned
+ * by reference-generated vectors: by the task's rule, "parity unpinned" with respect to the reference
+ * binary.
  */
 #define _GNU_SOURCE
 #include "awry_oracle.h"
