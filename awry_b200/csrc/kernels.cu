@@ -905,14 +905,20 @@ __global__ void __launch_bounds__(TPB, MINB)
   const uint32_t gmask = 0xfu << gbase;
   uint64_t* const ring = s_q[threadIdx.x / LANES];
   const uint32_t nq32 = uint32_t(nq);
-  // Queries are handed out dynamically, ticket_sz at a time, from a counter behind the deferred list
-  // (defer[nq + 1]): with a static stride every SM gets the same share and the kernel ends when the
-  // slowest SM does -- on B200 the SMs do not all see the same random-access throughput (the gather
-  // probe's SMs are busy between 52 % and 100 % of the time under a static split).
+  // Queries are handed out dynamically from a counter behind the deferred list (defer[nq + 1]): with a
+  // static stride every SM gets the same share and the kernel ends when the slowest SM does -- on B200 the
+  // SMs do not all see the same random-access throughput (the gather probe's SMs are busy between 52 % and
+  // 100 % of the time under a static split).  The hand-out is per WARP: the warp keeps a pool [pn, pe) of
+  // query numbers in registers (identical in all lanes), the groups that need a query in an iteration are
+  // counted with one ballot and numbered by rank, and lane 0 tops the pool up with ONE atomic per
+  // `ticket_sz` queries.  So the counter sees one atomic per warp-ticket however the 8 groups of the warp
+  // drift apart (a per-group grab collapses once reads that end early dephase the groups: same-address
+  // atomics retire at ~0.5 G/s), and at the end of the batch at most ticket_sz - 1 queries wait in a pool.
   uint32_t* const ticket = defer + nq + 1;
-  uint32_t q = 0, q_end = 0;  // the group's current ticket: queries [q, q_end)
-  bool more = true;            // the counter has not run past nq yet
-  uint32_t cur = NONE;         // query in flight
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t pn = 0, pe = 0;  // the warp's pool of query numbers
+  bool more = true;         // the counter has not run past nq yet
+  uint32_t cur = NONE;      // query in flight
   uint32_t sp = 1, ep = 0, left = 0, len = 0, nwords = 0;
   uint32_t ubase = 0;  // word index of the query's packed symbols
   uint32_t wlim = 8;   // word index at which the ring slides by 8 words
@@ -920,20 +926,38 @@ __global__ void __launch_bounds__(TPB, MINB)
   // Every lane of the warp runs every iteration (the loop exit is a warp vote), so the rank
   // reduction can use full-mask shuffles; a group whose query ended refills in the same iteration.
   for (;;) {
-    if (left == 0 || sp > ep) {
+    const bool want = left == 0 || sp > ep;
+    const uint32_t wmask = __ballot_sync(FULL, want && sub == 0);  // one bit per group that needs a query
+    uint32_t next_q = NONE;
+    if (wmask) {  // warp-uniform
+      const uint32_t n_want = __popc(wmask), avail = pe - pn;
+      uint32_t b = 0, got = 0;
+      if (n_want > avail && more) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(ticket, ticket_sz);
+        t = __shfl_sync(FULL, t, 0);
+        b = t;
+        got = t < nq32 ? (nq32 - t < ticket_sz ? nq32 - t : ticket_sz) : 0u;
+        more = got == ticket_sz;
+      }
+      const uint32_t r = __popc(wmask & ((1u << gbase) - 1u));  // this group's rank among the needy ones
+      if (want) next_q = r < avail ? pn + r : (r - avail < got ? b + (r - avail) : NONE);
+      if (n_want <= avail) {
+        pn += n_want;
+      } else if (got) {
+        const uint32_t used = n_want - avail < got ? n_want - avail : got;
+        pn = b + used;
+        pe = b + got;
+      } else {
+        pn = pe;
+      }
+    }
+    if (want) {
       if (cur != NONE && sub == 0) store_result<MODE>(out, cur, sp, ep);
       cur = NONE;
       left = 0;
-      if (q == q_end && more) {
-        uint32_t t = 0;
-        if (sub == 0) t = atomicAdd(ticket, ticket_sz);
-        t = __shfl_sync(gmask, t, gbase);
-        more = t < nq32;
-        q = more ? t : 0u;
-        q_end = more ? (nq32 - t < ticket_sz ? nq32 : t + ticket_sz) : 0u;
-      }
-      if (q < q_end) {
-        cur = q++;
+      if (next_q != NONE) {
+        cur = next_q;
         uint64_t ov = qoff[cur + (sub & 1)];  // lanes 0/1 fetch both ends with one request
         uint64_t o0 = __shfl_sync(gmask, ov, gbase), o1 = __shfl_sync(gmask, ov, gbase + 1);
         len = uint32_t(o1 - o0);
@@ -981,7 +1005,7 @@ __global__ void __launch_bounds__(TPB, MINB)
         }
       }
     }
-    if (__all_sync(FULL, cur == NONE && q == q_end && !more)) break;
+    if (__all_sync(FULL, cur == NONE && pn == pe && !more)) break;
 
     bool active = left != 0 && sp <= ep;  // (a query that just ended is stored next iteration)
     const uint32_t pos = len - left;      // search-order index of the next symbol
@@ -1071,7 +1095,10 @@ static cudaError_t launch_search_pair_b(const IndexView& ix, const uint64_t* d_q
     if (const char* e = getenv("AWRY_B200_TICKET")) return uint32_t(std::min(1024l, std::max(1l, strtol(e, nullptr, 10))));
     return 0u;
   }();
-  const uint32_t ticket_sz = ticket_env ? ticket_env : ticket_size(avg_len);
+  // per-WARP ticket of the pair kernel (8 lane groups): one query per group for 150-bp reads, more for
+  // short queries
+  const uint32_t per_group = avg_len == 0 ? 2u : std::min(8u, std::max(1u, 200u / avg_len));
+  const uint32_t ticket_sz = ticket_env ? ticket_env : 8u * per_group;
   e = launch_with_table_window(kern, grid, TPB, s, ix, ix, d_qwords, d_qoff, nq, d_out, d_defer, ticket_sz);
   COUNT_LAUNCH();
   if (e != cudaSuccess) return e;

@@ -26,14 +26,11 @@ struct SearchVariant {
   uint32_t avg_len = 0;   // mean query length of the batch (0 = unknown): sizes the tickets of the dynamic hand-out
 };
 
-// Queries per ticket of the dynamic hand-out.  Small tickets shorten the tail (a lane group needs ~130 us
-// per 150-bp read, and the last tickets leave most groups idle: 64 / 16 / 4 / 1 reads per ticket give
-// 20.2 / 17.6 / 16.5 / 16.3 ms per 10 M reads), but every ticket is an atomic on ONE counter, and
-// same-address atomics retire at ~0.5 G/s.  One read per ticket only works while the 8 lane groups of a warp
-// finish in the same iteration and their grabs merge into one atomic; reads that end early (mismatches)
-// dephase them, and a batch with 1 % / 10 % of such reads then takes 21.4 / 28.3 ms instead of 16.7
-// (profiles/r01_s42_ticket_vs_mismatches.log).  Four reads per ticket cost 1 % on exact reads and are
-// immune (19.3 ms at 10 % mismatching reads, 11.2 ms at 100 %).
+// Queries per ticket of the per-GROUP dynamic hand-out (amino kernel).  Small tickets shorten the tail (a
+// lane group needs ~130 us per 150-bp read: 64 / 16 / 4 / 1 reads per ticket gave 20.2 / 17.6 / 16.5 /
+// 16.3 ms per 10 M reads in the pair kernel), but every ticket is an atomic on ONE counter and same-address
+// atomics retire at ~0.5 G/s, so one query per ticket collapses once the groups of a warp drift apart
+// (profiles/r01_s42_ticket_vs_mismatches.log); the pair kernel hands out per warp instead.
 inline uint32_t ticket_size(uint32_t avg_len) {
   if (avg_len == 0) return 4;
   uint32_t t = 600 / avg_len;
