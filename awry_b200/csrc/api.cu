@@ -231,6 +231,7 @@ void finish_replica0(awry_index* ix, Replica& r) {
   uint32_t k = std::min<uint32_t>(ix->kmer_len_file, cap);
   size_t free_b = 0, total_b = 0;
   CU(cudaMemGetInfo(&free_b, &total_b));
+  if (const char* e = getenv("AWRY_B200_KMER_DEV")) k = std::min<uint32_t>(uint32_t(std::max(0l, strtol(e, nullptr, 10))), cap);  // experiments
   while (k > 0 && table_entries(ix->alphabet, k) * 8 > free_b / 4) k--;
   ix->kmer_len_dev = k;
   uint32_t dollar = r.view.dollar_row;
