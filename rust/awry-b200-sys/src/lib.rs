@@ -67,6 +67,21 @@ pub struct awry_build_args {
     pub device: i32,
 }
 
+/// awry_profile: per-kernel accounting kept by the library
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct awry_profile {
+    pub launches: u64,
+    pub search_launches: u64,
+    pub search_ms: f64,
+    pub walk_launches: u64,
+    pub walk_ms: f64,
+    pub pack_launches: u64,
+    pub pack_ms: f64,
+    pub h2d_bytes: u64,
+    pub d2h_bytes: u64,
+}
+
 pub const AWRY_OK: c_int = 0;
 pub const AWRY_ERR_IO: c_int = -2;
 pub const AWRY_ERR_INVALID_QUERY: c_int = -5;
@@ -108,6 +123,15 @@ extern "C" {
                               cuda_stream: *mut c_void) -> c_int;
     pub fn awry_device_free(index: *const awry_index, replica: c_int, d_ptr: *mut c_void) -> c_int;
     pub fn awry_device_check(index: *const awry_index, replica: c_int, cuda_stream: *mut c_void) -> c_int;
+    pub fn awry_read_sequence_file(path: *const c_char, alphabet: u32, text: *mut *mut u8, n_text: *mut u64,
+                                   starts: *mut *mut u64, n_records: *mut u64) -> c_int;
+    pub fn awry_host_pack_dna(src: *const u8, n: u64, dst: *mut u8, exceptions: *mut u64, exc_cap: u64, n_exc: *mut u64) -> c_int;
+    pub fn awry_profile_enable(on: c_int) -> c_int;
+    pub fn awry_profile_reset() -> c_int;
+    pub fn awry_profile_get(out: *mut awry_profile) -> c_int;
+    pub fn awry_bench_random_gather(device: c_int, footprint_bytes: u64, granule: u32, lanes: u32, n_reads: u64, iters: c_int,
+                                    reads_per_s: *mut f64, gb_per_s: *mut f64) -> c_int;
+    pub fn awry_set_search_variant(lanes_per_query: c_int, threads_per_block: c_int, blocks_per_sm: c_int) -> c_int;
     pub fn awry_set_locate_variant(variant: c_int) -> c_int;
     pub fn awry_last_error() -> *const c_char;
     pub fn awry_version() -> *const c_char;

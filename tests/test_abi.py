@@ -121,3 +121,10 @@ def test_product_never_touches_the_oracle():
                 assert "pyfixture" not in txt and "awo_" not in txt, fn
     ldd = subprocess.run(["ldd", os.path.join(pkg, "libawry_b200.so")], capture_output=True, text=True).stdout
     assert "oracle" not in ldd and "fixture" not in ldd
+
+
+def test_rust_sys_crate_declares_every_symbol():
+    """the (uncompilable here) Rust -sys crate must at least name every function of the C header"""
+    rs = open(os.path.join(ROOT, "rust", "awry-b200-sys", "src", "lib.rs")).read()
+    have = set(re.findall(r"pub fn (awry_[a-z0-9_]+)", rs))
+    assert sorted(have) == declared_symbols()
