@@ -169,7 +169,9 @@ struct Workspace {
   struct ReadsScratch {
     uint64_t chunk = 0, carry = 0;
     uint8_t* h_buf[3] = {nullptr, nullptr, nullptr};
-    uint8_t *d_raw = nullptr, *d_qbytes = nullptr;
+    uint8_t *d_raw = nullptr, *d_raw_b = nullptr, *d_qbytes = nullptr;  // raw chunks: double-buffered
+    cudaStream_t st_in = nullptr;                                        // upload stream of the raw chunks
+    cudaEvent_t ev_in[2] = {nullptr, nullptr};
     uint32_t *d_nl = nullptr, *d_small = nullptr, *d_seq_len = nullptr, *d_is_hdr = nullptr, *d_hdr_rank = nullptr;
     uint64_t *d_seq_off = nullptr, *d_qoff = nullptr;
     size_t cap_lines = 0, cap_qoff = 0, temp_bytes = 0;
@@ -181,6 +183,10 @@ struct Workspace {
         b = nullptr;
       }
       cudaFree(d_raw);
+      cudaFree(d_raw_b);
+      if (st_in) cudaStreamDestroy(st_in);
+      for (auto& e : ev_in)
+        if (e) cudaEventDestroy(e);
       cudaFree(d_qbytes);
       cudaFree(d_nl);
       cudaFree(d_small);

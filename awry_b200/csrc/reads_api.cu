@@ -137,6 +137,7 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
     }
     cv.notify_all();
     if (reader.joinable()) reader.join();
+    if (rs.st_in) cudaStreamSynchronize(rs.st_in);
     cudaStreamSynchronize(st);
     r.release(ws);
   };
@@ -146,6 +147,9 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
       rs.release();
       for (auto& b : rs.h_buf) CU(cudaHostAlloc(reinterpret_cast<void**>(&b), CARRY + CHUNK + 64, cudaHostAllocDefault));
       CU(cudaMalloc(reinterpret_cast<void**>(&rs.d_raw), max_bytes + 64));
+      CU(cudaMalloc(reinterpret_cast<void**>(&rs.d_raw_b), max_bytes + 64));
+      CU(cudaStreamCreateWithFlags(&rs.st_in, cudaStreamNonBlocking));
+      for (auto& e : rs.ev_in) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       CU(cudaMalloc(reinterpret_cast<void**>(&rs.d_qbytes), max_bytes + 64));
       CU(cudaMalloc(reinterpret_cast<void**>(&rs.d_nl), size_t(max_bytes) * 4 + 64));
       CU(cudaMalloc(reinterpret_cast<void**>(&rs.d_small), 64));
@@ -156,7 +160,8 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
       rs.carry = CARRY;
     }
     uint8_t** h_buf = rs.h_buf;
-    uint8_t *d_raw = rs.d_raw, *d_qbytes = rs.d_qbytes;
+    uint8_t* const d_raw2[2] = {rs.d_raw, rs.d_raw_b};
+    uint8_t* d_qbytes = rs.d_qbytes;
     uint32_t *d_nl = rs.d_nl, *d_small = rs.d_small;
     uint32_t *&d_seq_len = rs.d_seq_len, *&d_is_hdr = rs.d_is_hdr, *&d_hdr_rank = rs.d_hdr_rank;
     uint64_t *&d_seq_off = rs.d_seq_off, *&d_qoff = rs.d_qoff;
@@ -216,16 +221,28 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
     });
 
     if (locate) out.hit_off.assign(1, 0);
-    const int sh = packed_unit_shift(ix->alphabet);
     uint64_t tail_len = 0;
     const uint8_t* tail_src = nullptr;
     int prev_slot = -1;
-    for (int c = 0;; c++) {
+    // a chunk as it goes to the device: the carried tail of the previous chunk + the freshly read bytes
+    struct In {
+      uint8_t* base = nullptr;
+      uint64_t n = 0;
+      bool eof = false;
+      int si = -1;
+    };
+    // assembles chunk c in its pinned slot and starts its upload on the input stream; the upload of chunk
+    // c + 1 is started as soon as chunk c's records are split (its tail is known), so it overlaps the search
+    // of chunk c.  Non-blocking mode gives up if the reader thread has not delivered the chunk yet.
+    auto stage_in = [&](int c, bool blocking, In& in) -> bool {
       const int si = c % NBUF;
       Slot& s = slots[si];
       {
         std::unique_lock<std::mutex> lk(mu);
-        cv.wait(lk, [&] { return s.filled; });
+        if (blocking)
+          cv.wait(lk, [&] { return s.filled; });
+        else if (!s.filled)
+          return false;
       }
       if (!reader_err.empty()) fail(AWRY_ERR_IO, "%s", reader_err.c_str());
       uint8_t* base = h_buf[si] + CARRY - tail_len;
@@ -236,13 +253,30 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
           slots[prev_slot].filled = false;
         }
         cv.notify_all();
+        prev_slot = -1;
       }
       uint64_t n = tail_len + s.n;
-      const bool eof = s.eof;
-      if (eof && n && base[n - 1] != '\n') base[n++] = '\n';
-      if (n == 0) break;
-      CU(cudaMemcpyAsync(d_raw, base, n, cudaMemcpyHostToDevice, st));
-      g_prof.h2d += n;
+      if (s.eof && n && base[n - 1] != '\n') base[n++] = '\n';
+      in.base = base;
+      in.n = n;
+      in.eof = s.eof;
+      in.si = si;
+      if (n) {
+        CU(cudaMemcpyAsync(d_raw2[c & 1], base, n, cudaMemcpyHostToDevice, rs.st_in));
+        CU(cudaEventRecord(rs.ev_in[c & 1], rs.st_in));
+        g_prof.h2d += n;
+      }
+      return true;
+    };
+    In in, nxt;
+    stage_in(0, true, in);
+    for (int c = 0;; c++) {
+      if (in.n == 0) break;
+      uint8_t* const d_raw = d_raw2[c & 1];
+      uint8_t* const base = in.base;
+      const uint64_t n = in.n;
+      const bool eof = in.eof;
+      CU(cudaStreamWaitEvent(st, rs.ev_in[c & 1], 0));
       CU(reads_find_lines(d_raw, uint32_t(n), d_nl, d_small, d_temp, temp_bytes, st));
       CU(cudaMemcpyAsync(h_n_lines, d_small, 4, cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
@@ -273,6 +307,22 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
       CU(cudaStreamSynchronize(st));
       const ReadsPlan plan = *h_plan;
       const uint64_t nq = plan.n_records;
+      tail_len = n - plan.consumed;
+      tail_src = base + plan.consumed;
+      prev_slot = in.si;
+      bool have_next = false;
+      if (eof) {
+        for (uint64_t i = 0; i < tail_len; i++) {
+          uint8_t ch = tail_src[i];
+          if (ch != '\n' && ch != '\r' && ch != ' ' && ch != '\t')
+            fail(AWRY_ERR_FORMAT, "%s ends with a truncated %s record", path, fastq ? "FASTQ" : "FASTA");
+        }
+      } else {
+        if (tail_len > CARRY)
+          fail(AWRY_ERR_UNSUPPORTED, "%s holds a record larger than %llu bytes (AWRY_B200_READS_CHUNK)", path,
+               (unsigned long long)CARRY);
+        have_next = stage_in(c + 1, false, nxt);  // its upload overlaps the search below
+      }
       if (nq) {
         Workspace::grow_dev(ws->d_qwords, ws->d_qwords_cap, size_t(packed_words(ix->alphabet, nq, plan.seq_bytes)));
         Workspace::grow_dev(ws->d_out, ws->d_out_cap, size_t(nq) * 8);
@@ -330,20 +380,9 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
         out.n_reads += nq;
         out.n_bases += plan.seq_bytes;
       }
-      tail_len = n - plan.consumed;
-      tail_src = base + plan.consumed;
-      prev_slot = si;
-      if (eof) {
-        for (uint64_t i = 0; i < tail_len; i++) {
-          uint8_t ch = tail_src[i];
-          if (ch != '\n' && ch != '\r' && ch != ' ' && ch != '\t')
-            fail(AWRY_ERR_FORMAT, "%s ends with a truncated %s record", path, fastq ? "FASTQ" : "FASTA");
-        }
-        break;
-      }
-      if (tail_len > CARRY)
-        fail(AWRY_ERR_UNSUPPORTED, "%s holds a record larger than %llu bytes (AWRY_B200_READS_CHUNK)", path,
-             (unsigned long long)CARRY);
+      if (eof) break;
+      if (!have_next) stage_in(c + 1, true, nxt);
+      in = nxt;
     }
   } catch (...) {
     cleanup();
