@@ -5,6 +5,115 @@
 using namespace awry;
 using namespace awry::host;
 
+namespace {
+
+// Sequential writer of an `.awry` v1 file (FmIndex::save, fm_index_file.rs:42-106; sequence index:
+// sequence_index.rs:144-152), shared by awry_index_build (arrays fresh from the construction) and
+// awry_index_save (arrays re-derived from the device layout).  Write errors are latched and reported by finish().
+struct AwryFileOut {
+  FILE* f = nullptr;
+  bool ok = true;
+  std::string path;
+  explicit AwryFileOut(const char* p) : path(p) {
+    f = fopen(p, "wb");  // create + truncate, as OpenOptions in fm_index_file.rs:43-47
+    if (!f) fail(AWRY_ERR_IO, "cannot create %s: %s", p, strerror(errno));
+    setvbuf(f, nullptr, _IOFBF, 8u << 20);
+  }
+  ~AwryFileOut() {
+    if (f) fclose(f);
+  }
+  AwryFileOut(const AwryFileOut&) = delete;
+  AwryFileOut& operator=(const AwryFileOut&) = delete;
+
+  void put(const void* p, size_t nbytes) {
+    if (ok && nbytes && fwrite(p, 1, nbytes, f) != nbytes) ok = false;
+  }
+  void put_header(uint64_t version, uint64_t ratio, uint64_t bwt_len, uint64_t alphabet) {
+    put("AWRY-Index\n", 11);  // fm_index_file.rs:18,47
+    uint64_t hdr[4] = {version, ratio, bwt_len, alphabet};  // generate_file_header, fm_index_file.rs:165-181
+    put(hdr, sizeof hdr);
+  }
+  // n_words u64 that live (or are produced) on `device` -> file through a pinned double buffer: the D2H copy
+  // of chunk i+1 overlaps the fwrite of chunk i.  produce(chunk, first_word, n, stream) returns the device
+  // address of words [first_word, first_word + n) and may launch the kernel that makes them on `stream`.
+  template <class Produce>
+  void put_device(int device, uint64_t n_words, uint64_t chunk_words, Produce&& produce) {
+    if (n_words == 0) return;
+    DeviceGuard dg(device);
+    const uint64_t CH = std::min(chunk_words, n_words);
+    struct Bufs {
+      uint64_t* hb[2] = {nullptr, nullptr};
+      cudaStream_t cs = nullptr;
+      cudaEvent_t ev[2] = {nullptr, nullptr};
+      ~Bufs() {
+        if (cs) cudaStreamSynchronize(cs);
+        for (int i = 0; i < 2; i++) {
+          cudaFreeHost(hb[i]);
+          if (ev[i]) cudaEventDestroy(ev[i]);
+        }
+        if (cs) cudaStreamDestroy(cs);
+      }
+    } b;
+    CU(cudaStreamCreateWithFlags(&b.cs, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      CU(cudaHostAlloc(reinterpret_cast<void**>(&b.hb[i]), CH * 8, cudaHostAllocDefault));
+      CU(cudaEventCreateWithFlags(&b.ev[i], cudaEventDisableTiming));
+    }
+    const uint64_t n_chunks = (n_words + CH - 1) / CH;
+    auto issue = [&](uint64_t c) {
+      const uint64_t w0 = c * CH, nw = std::min(CH, n_words - w0);
+      const uint64_t* d_src = produce(c, w0, nw, b.cs);
+      CU(cudaMemcpyAsync(b.hb[c & 1], d_src, nw * 8, cudaMemcpyDeviceToHost, b.cs));
+      CU(cudaEventRecord(b.ev[c & 1], b.cs));
+    };
+    issue(0);
+    for (uint64_t c = 0; c < n_chunks; c++) {
+      CU(cudaEventSynchronize(b.ev[c & 1]));
+      if (c + 1 < n_chunks) issue(c + 1);
+      put(b.hb[c & 1], std::min(CH, n_words - c * CH) * 8);
+    }
+  }
+  // 1 byte k, then (card-2)^k entries populated the way kmer_lookup_table.rs:121-167 does;
+  // computed on replica 0 from the rank blocks, so a handle needs no copy of a table nobody reads
+  void put_table_section(const awry_index* ix, uint32_t k) {
+    uint8_t kb = uint8_t(k);
+    put(&kb, 1);
+    Replica& r = *ix->reps[0];
+    DeviceGuard dg(r.device);
+    const uint64_t n_entries = ipow(uint64_t(ix->card - 2), k), CH = 1u << 22;
+    ulonglong2* d_buf = nullptr;
+    CU(cudaMalloc(reinterpret_cast<void**>(&d_buf), std::min(n_entries, CH) * 16));
+    std::unique_ptr<ulonglong2, void (*)(ulonglong2*)> d_guard(d_buf, [](ulonglong2* p) { cudaFree(p); });
+    std::vector<uint64_t> h_buf(2 * std::min(n_entries, CH));
+    IndexView v = r.view;
+    v.kmer_len = 0;
+    for (uint64_t first = 0; first < n_entries && ok; first += CH) {
+      uint64_t cnt = std::min(CH, n_entries - first);
+      cudaError_t e = launch_ref_table(v, first, cnt, k, d_buf, nullptr);
+      if (e == cudaSuccess) e = cudaMemcpy(h_buf.data(), d_buf, cnt * 16, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) fail(AWRY_ERR_CUDA, "k-mer table kernel failed: %s", cudaGetErrorString(e));
+      put(h_buf.data(), cnt * 16);
+    }
+  }
+  void put_sequence_index(const std::vector<uint64_t>& starts, const std::vector<std::string>& headers, uint64_t n_seqs) {
+    put(&n_seqs, 8);  // sequence_index.rs:144-152
+    for (uint64_t i = 0; i < n_seqs; i++) {
+      const uint64_t st = i < starts.size() ? starts[i] : 0, hl = i < headers.size() ? headers[i].size() : 0;
+      put(&st, 8);
+      put(&hl, 8);
+      if (hl) put(headers[i].data(), hl);
+    }
+  }
+  void finish() {
+    if (fflush(f) != 0) ok = false;
+    if (fclose(f) != 0) ok = false;
+    f = nullptr;
+    if (!ok) fail(AWRY_ERR_IO, "write to %s failed", path.c_str());
+  }
+};
+
+}  // namespace
+
 extern "C" {
 
 uint64_t awry_parts_num_blocks(uint64_t bwt_len) { return (bwt_len + 255) / 256; }
@@ -131,95 +240,53 @@ int awry_index_build(const awry_build_args* a, const int* devices, int n_dev, aw
     std::unique_ptr<awry_index, void (*)(awry_index*)> holder(ix, awry_index_free);
     tick("device layout + accelerators");
     if (a->output_file_src) {  // FmIndex::save (fm_index_file.rs:42-106)
-      FILE* f = fopen(a->output_file_src, "wb");
-      if (!f) fail(AWRY_ERR_IO, "cannot create %s: %s", a->output_file_src, strerror(errno));
-      std::unique_ptr<FILE, int (*)(FILE*)> closer(f, fclose);
-      setvbuf(f, nullptr, _IOFBF, 8u << 20);
-      bool ok = true;
-      auto put = [&](const void* p, size_t nbytes) {
-        if (ok && nbytes && fwrite(p, 1, nbytes, f) != nbytes) ok = false;
-      };
-      put("AWRY-Index\n", 11);  // fm_index_file.rs:18,47
-      uint64_t hdr[4] = {1, ratio, bwt_len, uint64_t(alphabet)};
-      put(hdr, sizeof hdr);
-      // device arrays -> file through a pinned double buffer (D2H of chunk i+1 overlaps fwrite of chunk i)
-      auto put_device = [&](const uint64_t* d_src, uint64_t n_words) {
-        DeviceGuard dg(dp.device);
-        const uint64_t CH = (64u << 20) / 8;
-        uint64_t* hb[2] = {nullptr, nullptr};
-        cudaStream_t cs = nullptr;
-        cudaEvent_t ev[2] = {nullptr, nullptr};
-        try {
-          CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-          for (int i = 0; i < 2; i++) {
-            CU(cudaHostAlloc(reinterpret_cast<void**>(&hb[i]), CH * 8, cudaHostAllocDefault));
-            CU(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
-          }
-          uint64_t n_chunks = (n_words + CH - 1) / CH;
-          auto issue = [&](uint64_t c) {
-            uint64_t w0 = c * CH, nw = std::min(CH, n_words - w0);
-            CU(cudaMemcpyAsync(hb[c & 1], d_src + w0, nw * 8, cudaMemcpyDeviceToHost, cs));
-            CU(cudaEventRecord(ev[c & 1], cs));
-          };
-          if (n_chunks) issue(0);
-          for (uint64_t c = 0; c < n_chunks; c++) {
-            CU(cudaEventSynchronize(ev[c & 1]));
-            if (c + 1 < n_chunks) issue(c + 1);
-            put(hb[c & 1], std::min(CH, n_words - c * CH) * 8);
-          }
-        } catch (...) {
-          for (int i = 0; i < 2; i++) {
-            cudaFreeHost(hb[i]);
-            if (ev[i]) cudaEventDestroy(ev[i]);
-          }
-          if (cs) cudaStreamDestroy(cs);
-          throw;
-        }
-        for (int i = 0; i < 2; i++) {
-          cudaFreeHost(hb[i]);
-          cudaEventDestroy(ev[i]);
-        }
-        cudaStreamDestroy(cs);
-      };
-      put_device(dp.d_blocks, dp.n_block_words);
-      put(prefix.data(), prefix.size() * 8);
-      put_device(dp.d_sa_words, sa_word_len(bwt_len, ratio));
-      uint8_t kb = uint8_t(k);
-      put(&kb, 1);
-      {
-        Replica& r = *ix->reps[0];
-        DeviceGuard dg(r.device);
-        const uint64_t n_entries = ipow(uint64_t(card - 2), k), CH = 1u << 22;
-        ulonglong2* d_buf = nullptr;
-        CU(cudaMalloc(reinterpret_cast<void**>(&d_buf), std::min(n_entries, CH) * 16));
-        std::vector<uint64_t> h_buf(2 * std::min(n_entries, CH));
-        IndexView v = r.view;
-        v.kmer_len = 0;
-        for (uint64_t first = 0; first < n_entries && ok; first += CH) {
-          uint64_t cnt = std::min(CH, n_entries - first);
-          cudaError_t e = launch_ref_table(v, first, cnt, k, d_buf, nullptr);
-          if (e == cudaSuccess) e = cudaMemcpy(h_buf.data(), d_buf, cnt * 16, cudaMemcpyDeviceToHost);
-          if (e != cudaSuccess) {
-            cudaFree(d_buf);
-            fail(AWRY_ERR_CUDA, "k-mer table kernel failed: %s", cudaGetErrorString(e));
-          }
-          put(h_buf.data(), cnt * 16);
-        }
-        cudaFree(d_buf);
-      }
-      uint64_t n_seqs = starts.size();  // sequence_index.rs:144-152
-      put(&n_seqs, 8);
-      for (uint64_t i = 0; i < n_seqs; i++) {
-        uint64_t hl = headers[i].size();
-        put(&starts[i], 8);
-        put(&hl, 8);
-        put(headers[i].data(), hl);
-      }
-      if (fflush(f) != 0) ok = false;
-      if (!ok) fail(AWRY_ERR_IO, "write to %s failed", a->output_file_src);
+      AwryFileOut fo(a->output_file_src);
+      fo.put_header(1, ratio, bwt_len, uint64_t(alphabet));
+      fo.put_device(dp.device, dp.n_block_words, (64u << 20) / 8,
+                    [&](uint64_t, uint64_t w0, uint64_t, cudaStream_t) { return dp.d_blocks + w0; });
+      fo.put(prefix.data(), prefix.size() * 8);
+      fo.put_device(dp.device, sa_word_len(bwt_len, ratio), (64u << 20) / 8,
+                    [&](uint64_t, uint64_t w0, uint64_t, cudaStream_t) { return dp.d_sa_words + w0; });
+      fo.put_table_section(ix, k);
+      fo.put_sequence_index(starts, headers, starts.size());
+      fo.finish();
       tick("write .awry file");
     }
     if (out) *out = holder.release();
+  });
+}
+
+int awry_index_save(const awry_index* ix, const char* path) {
+  return guarded([&] {
+    need(ix);
+    if (!path) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    Replica& r = *ix->reps[0];
+    const uint64_t n_rb = (ix->bwt_len + 255) / 256, wpb = ix->alphabet == AWRY_NUCLEOTIDE ? 20 : 44;
+    AwryFileOut fo(path);
+    fo.put_header(ix->version, ix->sa_ratio, ix->bwt_len, uint64_t(ix->alphabet));
+    {
+      // the handle keeps only the device layout: the bwt.rs blocks are re-derived chunk by chunk
+      DeviceGuard dg(r.device);
+      const uint64_t chunk_blocks = std::min<uint64_t>(1u << 18, n_rb);
+      struct Tmp {
+        uint64_t* d[2] = {nullptr, nullptr};
+        ~Tmp() {
+          cudaFree(d[0]);
+          cudaFree(d[1]);
+        }
+      } tmp;
+      for (auto& d : tmp.d) CU(cudaMalloc(reinterpret_cast<void**>(&d), chunk_blocks * wpb * 8));
+      fo.put_device(r.device, n_rb * wpb, chunk_blocks * wpb, [&](uint64_t c, uint64_t w0, uint64_t nw, cudaStream_t cs) {
+        CU(launch_untranspose(ix->alphabet, r.d_blocks, r.view.dollar_row, w0 / wpb, nw / wpb, tmp.d[c & 1], cs));
+        return static_cast<const uint64_t*>(tmp.d[c & 1]);
+      });
+    }
+    fo.put(ix->prefix_sums, size_t(ix->card + 1) * 8);
+    fo.put_device(r.device, ix->n_sa_words, (64u << 20) / 8,
+                  [&](uint64_t, uint64_t w0, uint64_t, cudaStream_t) { return static_cast<const uint64_t*>(r.d_sa + w0); });
+    fo.put_table_section(ix, ix->kmer_len_file);
+    fo.put_sequence_index(ix->seq_starts, ix->headers, ix->headers.size());
+    fo.finish();
   });
 }
 

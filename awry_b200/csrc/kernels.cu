@@ -180,6 +180,107 @@ cudaError_t launch_transpose(int alphabet, const uint64_t* d_ref_blocks, uint64_
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ FmIndex::save: device layout -> bwt.rs blocks
+
+// Inverse of transpose_dna_kernel: one thread per 64-bit plane word (4 per 256-row reference block,
+// bwt.rs:12-17).  Rows 64w..64w+63 of reference block rb are chunks 2(w&1), 2(w&1)+1 of device block
+// 2rb + (w>>1).  Device codes A0 C1 G2 T3 N4 $5 (padding 7) -> reference codes $100 A110 C101 G011 N010
+// T001 (alphabet.rs:309-327); padding rows come out as all-zero planes, as set_symbol_at never touched them.
+// The thread of word 0 also writes the 8 milestones (bwt.rs:29; fm_index.rs:212-217), N derived as in layout.cuh.
+__global__ void untranspose_dna_kernel(const uint4* __restrict__ blocks, uint64_t first_rb, uint64_t n_rb,
+                                       uint32_t dollar_row, uint64_t* __restrict__ ref) {
+  uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (t >= n_rb * 4) return;
+  const uint64_t lrb = t >> 2, rb = first_rb + lrb;
+  const uint32_t w = uint32_t(t) & 3;
+  const uint4* db = blocks + (rb * 2 + (w >> 1)) * DNA_BLOCK_UINT4;
+  uint64_t r0 = 0, r1 = 0, r2 = 0;
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    const uint4 ch = db[2 * (w & 1) + half];
+    const uint32_t d0 = ch.x, d1 = ch.y, d2 = ch.z;
+    const uint32_t isA = ~d0 & ~d1 & ~d2, isC = d0 & ~d1 & ~d2, isG = ~d0 & d1 & ~d2, isT = d0 & d1 & ~d2,
+                   isN = ~d0 & ~d1 & d2, isS = d0 & ~d1 & d2;
+    r0 |= uint64_t(isC | isG | isT) << (32 * half);
+    r1 |= uint64_t(isA | isG | isN) << (32 * half);
+    r2 |= uint64_t(isS | isA | isC) << (32 * half);
+  }
+  uint64_t* out = ref + lrb * 20;
+  out[w] = r0;
+  out[4 + w] = r1;
+  out[8 + w] = r2;
+  if (w == 0) {
+    const uint4* b0 = blocks + rb * 2 * DNA_BLOCK_UINT4;
+    const uint64_t a = b0[0].w, c = b0[1].w, g = b0[2].w, tt = b0[3].w, start = rb * 256;
+    const uint64_t s = dollar_row < start ? 1 : 0;
+    out[12] = s;
+    out[13] = a;
+    out[14] = c;
+    out[15] = g;
+    out[16] = start - (a + c + g + tt) - s;
+    out[17] = tt;
+    out[18] = 0;
+    out[19] = 0;
+  }
+}
+
+// Inverse of transpose_amino_kernel + amino_counts_kernel: one thread per 32-row slice (8 per reference
+// block, bwt.rs:19-25) turns the planes of the symbol INDEX back into planes of the reference's 5-bit codes
+// (alphabet.rs:255-303; '$' and padding rows are code 00000); slice 0 also writes the 24 milestones.
+__constant__ uint8_t c_amino_idx_to_code[32];
+__global__ void untranspose_amino_kernel(const uint4* __restrict__ blocks, uint64_t first_rb, uint64_t n_rb,
+                                         uint32_t dollar_row, uint64_t* __restrict__ ref) {
+  uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (t >= n_rb * 8) return;
+  const uint64_t lrb = t >> 3, rb = first_rb + lrb;
+  const uint32_t j = uint32_t(t) & 7;
+  const uint32_t* d =
+      reinterpret_cast<const uint32_t*>(blocks + (rb * 4 + (j >> 1)) * AMINO_BLOCK_UINT4) + 8 * (j & 1);
+  uint32_t dp[5], r[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+  for (int p = 0; p < 5; p++) dp[p] = d[p];
+  for (int bit = 0; bit < 32; bit++) {
+    uint32_t idx = 0;
+#pragma unroll
+    for (int p = 0; p < 5; p++) idx |= ((dp[p] >> bit) & 1u) << p;
+    const uint32_t code = c_amino_idx_to_code[idx];
+#pragma unroll
+    for (int p = 0; p < 5; p++) r[p] |= ((code >> p) & 1u) << bit;
+  }
+  uint32_t* out32 = reinterpret_cast<uint32_t*>(ref + lrb * 44);
+#pragma unroll
+  for (int p = 0; p < 5; p++) out32[(4 * p + (j >> 1)) * 2 + (j & 1)] = r[p];  // little-endian halves of the u64 words
+  if (j == 0) {
+    uint64_t* ms = ref + lrb * 44 + 20;
+    const uint32_t* b0 = reinterpret_cast<const uint32_t*>(blocks + rb * 4 * AMINO_BLOCK_UINT4);
+    ms[0] = dollar_row < rb * 256 ? 1 : 0;
+    for (uint32_t s = 1; s <= 21; s++) ms[s] = b0[amino_count_word(s)];
+    ms[22] = 0;
+    ms[23] = 0;
+  }
+}
+
+cudaError_t launch_untranspose(int alphabet, const uint4* d_blocks, uint32_t dollar_row, uint64_t first_ref_block,
+                               uint64_t n_ref_blocks, uint64_t* d_ref_blocks, cudaStream_t s) {
+  if (n_ref_blocks == 0) return cudaSuccess;
+  if (alphabet == 0) {
+    uint64_t threads = n_ref_blocks * 4;
+    untranspose_dna_kernel<<<unsigned((threads + 255) / 256), 256, 0, s>>>(d_blocks, first_ref_block, n_ref_blocks,
+                                                                            dollar_row, d_ref_blocks);
+  } else {
+    // same table as init_device_tables (index -> 5-bit code); indices 22..31 never occur in device blocks
+    static const uint8_t i2c[32] = {0x00, 0x0c, 0x17, 0x03, 0x06, 0x1e, 0x1a, 0x1b, 0x19, 0x15, 0x1c,
+                                    0x1d, 0x08, 0x09, 0x04, 0x13, 0x0a, 0x05, 0x16, 0x01, 0x1f, 0x02};
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_amino_idx_to_code, i2c, sizeof i2c, 0, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return e;
+    uint64_t threads = n_ref_blocks * 8;
+    untranspose_amino_kernel<<<unsigned((threads + 255) / 256), 256, 0, s>>>(d_blocks, first_ref_block, n_ref_blocks,
+                                                                              dollar_row, d_ref_blocks);
+  }
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ k-mer seed table
 
 uint64_t table_entries(int alphabet, uint32_t k) {

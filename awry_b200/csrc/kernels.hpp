@@ -47,6 +47,10 @@ cudaError_t init_device_tables();  // per device, once: ASCII -> device-symbol L
 cudaError_t launch_transpose(int alphabet, const uint64_t* d_ref_blocks, uint64_t first_ref_block,
                              uint64_t n_ref_blocks, uint64_t bwt_len, uint4* d_blocks,
                              unsigned int* d_dollar_row, cudaStream_t s);
+// the inverse (FmIndex::save of a handle that only holds the device layout): device blocks -> reference
+// blocks [first_ref_block, first_ref_block + n_ref_blocks) written to d_ref_blocks[0 ..)
+cudaError_t launch_untranspose(int alphabet, const uint4* d_blocks, uint32_t dollar_row, uint64_t first_ref_block,
+                               uint64_t n_ref_blocks, uint64_t* d_ref_blocks, cudaStream_t s);
 uint64_t table_entries(int alphabet, uint32_t k);
 cudaError_t launch_build_table(const IndexView& ix, uint2* d_table, uint32_t k, cudaStream_t s);
 

@@ -117,7 +117,7 @@ class Profile(C.Structure):
 
 # every symbol include/awry_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = ["awry_read_sequence_file", "awry_index_build", "awry_build_index_file", "awry_build_parts", "awry_parts_num_blocks", "awry_parts_block_words",
-           "awry_parts_sa_words", "awry_index_load", "awry_index_from_parts", "awry_index_free", "awry_index_info",
+           "awry_parts_sa_words", "awry_index_load", "awry_index_from_parts", "awry_index_free", "awry_index_save", "awry_index_info",
            "awry_index_sequence_header", "awry_count_batch", "awry_search_batch",
            "awry_locate_batch", "awry_locate_batch_into", "awry_hits_free", "awry_count_reads_file",
            "awry_locate_reads_file", "awry_buffer_free", "awry_initial_range", "awry_update_range",
@@ -155,6 +155,7 @@ def native():
     L.awry_index_load.argtypes = [C.c_char_p, vp, i32, C.POINTER(vp)]
     L.awry_index_from_parts.argtypes = [C.POINTER(_Parts), vp, i32, C.POINTER(vp)]
     L.awry_index_free.argtypes = [vp]
+    L.awry_index_save.argtypes = [vp, C.c_char_p]
     L.awry_index_free.restype = None
     L.awry_index_info.argtypes = [vp, C.POINTER(_Info)]
     L.awry_index_sequence_header.argtypes = [vp, u64, C.POINTER(C.c_char_p), C.POINTER(u64)]
@@ -261,6 +262,10 @@ class FmIndex:
         _check(native().awry_index_from_parts(C.byref(p), dev, len(devices) if devices else 0,
                                               C.byref(h)))
         return cls(h.value)
+
+    def save(self, path) -> None:
+        """FmIndex::save (fm_index_file.rs:42-106): `.awry` v1 file from this handle's device layout."""
+        _check(native().awry_index_save(self._h, os.fsencode(path)))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -114,6 +114,14 @@ int awry_index_info(const awry_index *index, awry_info *info);
 int awry_index_sequence_header(const awry_index *index, uint64_t seq_idx, const char **header,
                                uint64_t *header_len);
 
+/* FmIndex::save (fm_index_file.rs:42-106) of any handle -- loaded, handed over or built: writes an
+ * `.awry` v1 file the reference (and awry_index_load) reads.  The handle keeps only the device layout, so
+ * the bwt.rs blocks are re-derived from it on replica 0 (bit planes re-encoded to the reference's symbol
+ * codes, milestones from the block-start counts) and streamed out with the sampled suffix-array words; the
+ * k-mer table section is re-populated the way kmer_lookup_table.rs:121-167 does.  For a file the
+ * reference wrote, load followed by save reproduces it byte for byte.  An existing file is truncated. */
+int awry_index_save(const awry_index *index, const char *path);
+
 /* ------------------------------------------------------------------ index construction on the GPU
  * the reference builds on the CPU (FmIndex::new, fm_index.rs:142-268, libsufr suffix
  * sort) and that path stays valid (awry_index_from_parts).  These entry points do the same work on

@@ -77,6 +77,8 @@ class FmIndex {
     check(awry_index_from_parts(&parts, devices.empty() ? nullptr : devices.data(), int(devices.size()), &h));
     return FmIndex(h);
   }
+  // FmIndex::save (fm_index_file.rs:42-106)
+  void save(const std::string& path) const { check(awry_index_save(h_, path.c_str())); }
   FmIndex(FmIndex&& o) noexcept : h_(std::exchange(o.h_, nullptr)), info_(o.info_) {}
   FmIndex& operator=(FmIndex&& o) noexcept {
     if (this != &o) {

@@ -99,6 +99,7 @@ extern "C" {
     pub fn awry_parts_block_words(alphabet: u32) -> u64;
     pub fn awry_parts_sa_words(bwt_len: u64, sa_ratio: u64) -> u64;
     pub fn awry_index_free(index: *mut awry_index);
+    pub fn awry_index_save(index: *const awry_index, path: *const c_char) -> c_int;
     pub fn awry_index_info(index: *const awry_index, info: *mut awry_info) -> c_int;
     pub fn awry_index_sequence_header(index: *const awry_index, seq_idx: u64, header: *mut *const c_char, header_len: *mut u64) -> c_int;
     pub fn awry_count_batch(index: *const awry_index, qbytes: *const u8, qoff: *const u64, nq: u64, counts: *mut u64) -> c_int;

@@ -129,6 +129,14 @@ impl FmIndex {
         Ok(FmIndex { handle, info })
     }
 
+    /// FmIndex::save (fm_index_file.rs:42-106): writes this index as an `.awry` v1 file (awry_index_save).
+    pub fn save(&self, file_output_src: &Path) -> Result<(), io::Error> {
+        let path = CString::new(file_output_src.to_string_lossy().as_bytes()).map_err(|e| io::Error::new(io::ErrorKind::InvalidInput, e))?;
+        let rc = unsafe { sys::awry_index_save(self.handle, path.as_ptr()) };
+        if rc != sys::AWRY_OK { return Err(io::Error::new(io::ErrorKind::Other, last_error())); }
+        Ok(())
+    }
+
     /// parallel_count over every record of a FASTQ / FASTA file, parsed on the device (awry_count_reads_file).
     pub fn parallel_count_file(&self, reads: &Path) -> Result<Vec<u64>, io::Error> {
         let path = CString::new(reads.to_string_lossy().as_bytes()).map_err(|e| io::Error::new(io::ErrorKind::InvalidInput, e))?;
