@@ -11,6 +11,49 @@ namespace host {
 
 // ------------------------------------------------------------------ batched pipelines
 
+// AWRY_B200_TRACE=1: host-side stage times of the batched pipelines on stderr (scripts/locate_trace.py)
+static bool trace_on() {
+  static const bool on = getenv("AWRY_B200_TRACE") != nullptr;
+  return on;
+}
+static void trace_mark(const char* what, long long i = -1) {
+  if (!trace_on()) return;
+  static const auto t_origin = std::chrono::steady_clock::now();
+  fprintf(stderr, "[trace] %10.3f ms  %s %lld\n",
+          std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_origin).count(), what, i);
+}
+// device-side timeline of a traced call: events recorded on the chunk streams, printed relative to the first
+struct GpuTrace {
+  struct Ev {
+    cudaEvent_t e;
+    const char* what;
+    long long i;
+  };
+  std::vector<Ev> evs;
+  void mark(cudaStream_t st, const char* what, long long i) {
+    if (!trace_on()) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    evs.push_back(Ev{e, what, i});
+  }
+  void dump() {
+    if (evs.empty()) return;
+    for (auto& v : evs) cudaEventSynchronize(v.e);
+    for (auto& v : evs) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, evs[0].e, v.e);
+      fprintf(stderr, "[gpu]   %10.3f ms  %s %lld\n", ms, v.what, v.i);
+    }
+    for (auto& v : evs) cudaEventDestroy(v.e);
+    evs.clear();
+  }
+};
+static thread_local GpuTrace* g_gpu_trace = nullptr;
+static void gpu_mark(cudaStream_t st, const char* what, long long i) {
+  if (g_gpu_trace) g_gpu_trace->mark(st, what, i);
+}
+
 bool is_pinned(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -176,7 +219,7 @@ void validate_offsets(const uint64_t* qoff, uint64_t nq) {
 // `may_pack`: the caller's say on host packing for this chunk (see raw_chunk_period)
 void enqueue_search(const awry_index* ix, Replica& r, Workspace* ws, const uint8_t* qbytes,
                     const uint64_t* qoff, const Chunk& c, SearchOut mode, bool src_pinned, bool may_pack = true,
-                    bool probe_link = false) {
+                    bool probe_link = false, bool copy_flag = true) {
   const uint64_t nq = c.q1 - c.q0, nbytes = c.b1 - c.b0;
   const size_t out_elem = mode == OUT_COUNT_U64 ? 8 : mode == OUT_RANGE_U64 ? 16 : 8;
   Workspace::grow_dev(ws->d_qbytes, ws->d_qbytes_cap, size_t(nbytes) + 16);
@@ -196,6 +239,7 @@ void enqueue_search(const awry_index* ix, Replica& r, Workspace* ws, const uint8
     auto t0 = std::chrono::steady_clock::now();
     packed = host_pack_dna(src_b, size_t(nbytes), ws->h_qbytes, ws->exc_tmp, 64);
     if (packed) g_balance.note_host(double(nbytes), std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    trace_mark("  host pack done, bytes", (long long)nbytes);
   }
   if (packed) {
     const size_t n_exc = ws->exc_tmp.size();
@@ -214,6 +258,7 @@ void enqueue_search(const awry_index* ix, Replica& r, Workspace* ws, const uint8
       CU(cudaMemcpyAsync(ws->d_exc, ws->h_exc, n_exc * 8, cudaMemcpyHostToDevice, ws->st));
     }
     g_prof.h2d += pbytes + 8 + (nq + 1) * 8 + n_exc * 8;
+    gpu_mark(ws->st, "h2d done", (long long)c.q0);
     CU(cudaMemsetAsync(ws->d_flag, 0xff, 8, ws->st));
     {
       ProfScope p(2, r.device, ws->st);
@@ -251,13 +296,18 @@ void enqueue_search(const awry_index* ix, Replica& r, Workspace* ws, const uint8
       CU(launch_pack(ix->alphabet, ws->d_qbytes - c.b0, ws->d_qoff, nq, ws->d_qwords - 4 * (c.b0 >> packed_unit_shift(ix->alphabet)), ws->d_flag, ws->st));
     }
   }
+  gpu_mark(ws->st, "packed on device", (long long)c.q0);
   {
     ProfScope p(0, r.device, ws->st);
     SearchVariant v = g_variant;
     v.avg_len = uint32_t(std::min<uint64_t>(nbytes / std::max<uint64_t>(1, nq), 1u << 30));
     CU(launch_search(r.view, ws->d_qwords - 4 * (c.b0 >> packed_unit_shift(ix->alphabet)), ws->d_qoff, nq, mode, ws->d_out, ws->d_defer, v, r.sm_count, ws->st));
   }
-  CU(cudaMemcpyAsync(ws->h_flag, ws->d_flag, 8, cudaMemcpyDeviceToHost, ws->st));
+  gpu_mark(ws->st, "searched", (long long)c.q0);
+  // (the locate pipeline copies the flag together with the hit total, after the scan: one hand-over between
+  // the compute and copy engines per chunk instead of two)
+  if (copy_flag) CU(cudaMemcpyAsync(ws->h_flag, ws->d_flag, 8, cudaMemcpyDeviceToHost, ws->st));
+  trace_mark("  search enqueued, queries", (long long)nq);
 }
 
 void check_flag(Workspace* ws, const Chunk& c) {
@@ -420,6 +470,7 @@ uint64_t* locate_chunk_walk(Replica& r, Workspace* ws, uint64_t nq, uint64_t n_h
   const uint2* d_sp_cnt = reinterpret_cast<const uint2*>(ws->d_out);
   uint64_t* d_hits = nullptr;
   CU(cudaMallocAsync(reinterpret_cast<void**>(&d_hits), n_hits * 16 + 16, st));  // pool: no driver round trip
+  trace_mark("  hits buffer allocated, hits", (long long)n_hits);
   try {
     if (flags & AWRY_LOCATE_SORTED) {
       uint64_t *d_locs = nullptr, *d_sorted = nullptr;
@@ -456,11 +507,22 @@ uint64_t* locate_chunk_device(const awry_index* ix, Replica& r, Workspace* ws, u
 }
 
 // parallel_locate over [q_lo, q_hi) on one replica.  The two passes of a chunk are separated by one small
-// device->host read (the hit total sizes pass 2), so chunks are kept small (256 k queries) and three are
-// in flight: while the host waits for chunk i's total, chunk i+1 is being packed, copied and searched,
-// and chunk i-1's hits are on their way back.
-constexpr uint64_t LOCATE_CHUNK_Q = 1u << 18;
-constexpr uint64_t LOCATE_CHUNK_BYTES = 32u << 20;
+// device->host read (the hit total sizes pass 2), and three chunks are in flight: while the host waits for
+// chunk i's total, chunk i+1 is being packed, copied and searched, and chunk i-1's hits are on their way back.
+// Chunk size: every chunk pays ~0.4 ms of fixed device-side latency (a persistent search kernel that fills
+// the part and drains, a dozen small dependent operations, copies slowed 2-3x by the search kernel of the
+// neighbouring chunk: profiles/r01_s50_locate_gpu_timeline.log), so 1 M x 50-bp queries take 3.31 / 2.55 /
+// 2.51 / 2.71 ms end to end with chunks of 256 k / 384 k / 512 k / 1 M queries
+// (profiles/r01_s51_locate_chunk_sweep.log): 512 k.
+constexpr uint64_t LOCATE_CHUNK_BYTES = 64u << 20;
+static uint64_t locate_chunk_q() {  // AWRY_B200_LOCATE_CHUNK_Q: queries per chunk (experiments; read per call)
+  if (const char* e = getenv("AWRY_B200_LOCATE_CHUNK_Q")) return std::min<uint64_t>(1u << 24, std::max<uint64_t>(1024, strtoull(e, nullptr, 10)));
+  return 1u << 19;
+}
+static uint64_t locate_chunk_bytes() {
+  if (const char* e = getenv("AWRY_B200_LOCATE_CHUNK_MB")) return std::min<uint64_t>(1024, std::max<uint64_t>(1, strtoull(e, nullptr, 10))) << 20;
+  return LOCATE_CHUNK_BYTES;
+}
 
 void locate_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, const uint64_t* qoff,
                        uint64_t q_lo, uint64_t q_hi, uint32_t flags, LocatePart& part) {
@@ -470,7 +532,7 @@ void locate_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
   if (q_lo >= q_hi) return;
   DeviceGuard dg(r.device);
   const bool src_pinned = is_pinned(qbytes) && is_pinned(qoff);
-  auto chunks = make_chunks(qoff, q_lo, q_hi, LOCATE_CHUNK_Q, std::min(chunk_max_bytes(), LOCATE_CHUNK_BYTES));
+  auto chunks = make_chunks(qoff, q_lo, q_hi, locate_chunk_q(), std::min(chunk_max_bytes(), locate_chunk_bytes()));
   constexpr int DEPTH = 3;
   struct Slot {
     Workspace* ws = nullptr;
@@ -479,13 +541,7 @@ void locate_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
     uint64_t base = 0;
   } slot[DEPTH];
   size_t cap = 0;
-  static const bool trace = getenv("AWRY_B200_TRACE") != nullptr;  // host-side stage times on stderr
-  const auto t_origin = std::chrono::steady_clock::now();
-  auto mark = [&](const char* what, int i) {
-    if (trace)
-      fprintf(stderr, "[locate] %8.3f ms  %s %d\n",
-              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_origin).count(), what, i);
-  };
+  auto mark = [&](const char* what, int i) { trace_mark(what, i); };
   // offsets of a chunk are rebased onto the replica-local hit count before it; the slot shared with the
   // next chunk (index nq) is written by that chunk, the very last one after the loop
   auto stage_c = [&](Slot& s) {
@@ -507,12 +563,16 @@ void locate_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
     const Chunk& c = chunks[size_t(i)];
     const uint64_t nq = c.q1 - c.q0;
     mark("A begin", i);
-    enqueue_search(ix, r, ws, qbytes, qoff, c, OUT_SP_CNT_U32, src_pinned);
+    gpu_mark(ws->st, "chunk begins", i);
+    enqueue_search(ix, r, ws, qbytes, qoff, c, OUT_SP_CNT_U32, src_pinned, true, false, false);
     mark("A searched", i);
     Workspace::grow_dev(ws->d_hit_off, ws->d_hit_off_cap, size_t(nq) + 1);
     locate_chunk_scan(ws, nq, ws->d_hit_off, ws->st);
+    gpu_mark(ws->st, "scanned", i);
+    CU(cudaMemcpyAsync(ws->h_flag, ws->d_flag, 8, cudaMemcpyDeviceToHost, ws->st));
     CU(cudaMemcpyAsync(ws->h_total, ws->d_hit_off + nq, 8, cudaMemcpyDeviceToHost, ws->st));
     CU(cudaEventRecord(ws->done, ws->st));
+    gpu_mark(ws->st, "total copied", i);
     mark("A end", i);
     s.chunk = i;
     s.phase = 1;
@@ -528,7 +588,9 @@ void locate_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
     const uint64_t n_hits = *ws->h_total;
     check_flag(ws, c);
     s.base = part.n_hits;
+    gpu_mark(ws->st, "pass 2 begins", i);
     CU(cudaMemcpyAsync(off_base + (c.q0 - q_lo), ws->d_hit_off, nq * 8, cudaMemcpyDeviceToHost, ws->st));
+    gpu_mark(ws->st, "offsets copied", i);
     g_prof.d2h += nq * 8;
     const bool fits = !ext || part.n_hits + n_hits <= part.ext_cap;
     if (n_hits && fits) {
@@ -540,7 +602,9 @@ void locate_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
         part.hits = static_cast<awry_hit*>(np);
       }
       uint64_t* d_hits = locate_chunk_walk(r, ws, nq, n_hits, flags, ws->d_hit_off, ws->st);
+      gpu_mark(ws->st, "hits located", i);
       CU(cudaMemcpyAsync(part.hits + part.n_hits, d_hits, n_hits * 16, cudaMemcpyDeviceToHost, ws->st));
+      gpu_mark(ws->st, "hits copied", i);
       cudaFreeAsync(d_hits, ws->st);
       g_prof.d2h += n_hits * 16;
     }
@@ -549,6 +613,8 @@ void locate_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
     s.phase = 2;
     part.n_hits += n_hits;  // keeps counting past the capacity so the caller learns the need
   };
+  GpuTrace gpu_trace;
+  g_gpu_trace = trace_on() ? &gpu_trace : nullptr;
   try {
     stage_a(0);
     for (int i = 0; i < int(chunks.size()); i++) {
@@ -558,7 +624,10 @@ void locate_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
     for (auto& s : slot) stage_c(s);
     off_base[q_hi - q_lo] = part.n_hits;
     mark("done", int(chunks.size()));
+    g_gpu_trace = nullptr;
+    gpu_trace.dump();
   } catch (...) {
+    g_gpu_trace = nullptr;
     for (auto& s : slot)
       if (s.ws) {
         cudaStreamSynchronize(s.ws->st);

@@ -1,5 +1,6 @@
 // kernels.hpp -- host-callable launchers of the sm_100a kernels (internal to libawry_b200).
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -35,6 +36,13 @@ inline uint32_t ticket_size(uint32_t avg_len) {
   if (avg_len == 0) return 4;
   uint32_t t = 600 / avg_len;
   return t < 2 ? 2u : t > 16 ? 16u : t;
+}
+
+// ... and never so large that a lane group draws fewer than ~6 tickets over the batch: the kernel ends when the
+// last ticket does, so with ~1 ticket per group it runs for up to two ticket times (small pipeline chunks)
+inline uint32_t ticket_cap(uint32_t per_group, uint64_t nq, uint64_t n_groups) {
+  const uint64_t cap = nq / (6 * (n_groups ? n_groups : 1));
+  return uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(per_group, cap)));
 }
 
 struct LaunchCounters {
