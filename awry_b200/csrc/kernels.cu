@@ -1202,7 +1202,7 @@ static cudaError_t launch_search_pair_b(const IndexView& ix, const uint64_t* d_q
   // several (a 256 k-query chunk of 50-bp queries with 32-query tickets is 1.15 tickets per warp: the kernel
   // runs for two ticket times, 0.34 ms instead of ~0.2, profiles/r01_s50_locate_gpu_timeline.log)
   uint32_t per_group = avg_len == 0 ? 2u : std::min(8u, std::max(1u, 200u / avg_len));
-  per_group = ticket_cap(per_group, nq, uint64_t(grid) * (TPB / 4));
+  per_group = ticket_cap(per_group, nq, uint64_t(grid) * (TPB / 4), avg_len);
   const uint32_t ticket_sz = ticket_env ? ticket_env : 8u * per_group;
   e = launch_with_table_window(kern, grid, TPB, s, ix, ix, d_qwords, d_qoff, nq, d_out, d_defer, ticket_sz);
   COUNT_LAUNCH();
@@ -1385,8 +1385,9 @@ static cudaError_t launch_search_amino(const IndexView& ix, const uint64_t* d_qw
   uint64_t max_blocks = uint64_t(sm_count) * uint64_t(per_sm);
   uint64_t need_blocks = (nq * 4 + TPB - 1) / TPB;
   unsigned grid = unsigned(std::max<uint64_t>(1, std::min(max_blocks, need_blocks)));
-  const uint32_t ticket_sz = ticket_cap(ticket_size(v.avg_len), nq, uint64_t(grid) * (TPB / 4));
-  e = launch_with_table_window(kern, grid, TPB, s, ix, ix, d_qwords, d_qoff, nq, d_out, d_ticket, ticket_sz);
+  // (no batch-size cap here: the hand-out is per lane GROUP, and 12-residue peptides at 3.7 G/s with tickets
+  // of 2 would be 1.8 G same-address atomics/s, far above what one counter retires)
+  e = launch_with_table_window(kern, grid, TPB, s, ix, ix, d_qwords, d_qoff, nq, d_out, d_ticket, ticket_size(v.avg_len));
   COUNT_LAUNCH();
   return e;
 }

@@ -39,10 +39,13 @@ inline uint32_t ticket_size(uint32_t avg_len) {
 }
 
 // ... and never so large that a lane group draws fewer than ~6 tickets over the batch: the kernel ends when the
-// last ticket does, so with ~1 ticket per group it runs for up to two ticket times (small pipeline chunks)
-inline uint32_t ticket_cap(uint32_t per_group, uint64_t nq, uint64_t n_groups) {
+// last ticket does, so with ~1 ticket per group it runs for up to two ticket times (small pipeline chunks).
+// Very short queries keep a floor (50 / length queries per group): their tickets are cheap to finish and every
+// ticket is an atomic on one counter.
+inline uint32_t ticket_cap(uint32_t per_group, uint64_t nq, uint64_t n_groups, uint32_t avg_len) {
   const uint64_t cap = nq / (6 * (n_groups ? n_groups : 1));
-  return uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(per_group, cap)));
+  const uint64_t floor_ = avg_len ? std::max<uint32_t>(1, 50u / avg_len) : 1;
+  return uint32_t(std::min<uint64_t>(per_group, std::max<uint64_t>(floor_, cap)));
 }
 
 struct LaunchCounters {

@@ -431,3 +431,25 @@ def test_concurrent_batches_from_many_host_threads(fx, dna, dna_dev, dna_or):
     assert not errors, errors
     for (qb, qo, want, (woff, whits)), (c, off, hits) in zip(jobs, results):
         assert np.array_equal(c, want) and np.array_equal(off, woff) and np.array_equal(hits, whits)
+
+
+@pytest.mark.parametrize("chunk_q", [1024, 3000])
+def test_locate_pipeline_many_small_chunks(fx, dna, dna_dev, dna_or, locate_variant, monkeypatch, chunk_q):
+    """the 3-deep locate pipeline over many chunks (slot reuse, offsets rebased onto the hits before them,
+    growth of the library-owned hit buffer while copies are in flight): results must not depend on the
+    chunk size, whether the output is library-owned or caller-owned"""
+    import torch
+    monkeypatch.setenv("AWRY_B200_LOCATE_CHUNK_Q", str(chunk_q))      # read per call
+    qb, qo = mixed_queries(fx, dna.text, 20_000, 12, seed=77)         # 12-mers on 200 kbp: 0 .. several hits each
+    woff, whits, _ = dna_or.locate_batch(qb, qo)
+    assert int(np.diff(woff).max()) >= 2 and int(np.diff(woff).min()) == 0
+    off, hits = dna_dev.locate_packed(qb, qo)
+    assert np.array_equal(off, woff) and np.array_equal(hits, whits)
+    soff, shits = dna_dev.locate_packed(qb, qo, sorted_hits=True)
+    woff2, whits2, _ = dna_or.locate_batch(qb, qo, sorted_hits=True)
+    assert np.array_equal(soff, woff2) and np.array_equal(shits, whits2)
+    n = len(whits)
+    hoff = torch.zeros(len(qo), dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+    hbuf = torch.zeros((n + 3, 2), dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+    assert dna_dev.locate_packed_into(qb, qo, hoff, hbuf) == n
+    assert np.array_equal(hoff, woff) and np.array_equal(hbuf[:n], whits)
