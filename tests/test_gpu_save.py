@@ -102,3 +102,19 @@ def test_save_errors(fx, tmp_path):
         assert e.value.code == -2
         ix.save(str(tmp_path / "ok.awry"))                      # the handle is still usable afterwards
         assert np.array_equal(ix.parallel_count([text[:20].tobytes()]), [1])
+
+
+@pytest.mark.parametrize("alphabet,n", [(0, 70_000_123), (1, 68_000_001)])
+def test_save_streams_more_than_one_chunk_of_blocks(fx, tmp_path, alphabet, n):
+    """more than 2^18 reference blocks: the inverse re-layout runs chunk by chunk through the device and pinned
+    double buffers (first block of a chunk > 0, buffers reused) -- still the CPU writer's file, byte for byte"""
+    from awry_b200 import FmIndex
+    from fixtures import pyfixture_gpu as fxg
+    parts, _ = fxg.build_parts(alphabet, n, 5, ratio=16, kmer_len=3)     # index arrays by the GPU builder
+    assert len(parts.blocks) // (20 if alphabet == 0 else 44) > (1 << 18)
+    want_path = parts.write(str(tmp_path / "want.awry"))                # file by the CPU writer
+    got_path = str(tmp_path / "got.awry")
+    with FmIndex.load(want_path) as ix:
+        ix.save(got_path)
+    a, b = np.fromfile(want_path, dtype=np.uint8), np.fromfile(got_path, dtype=np.uint8)
+    assert a.shape == b.shape and np.array_equal(a, b)
