@@ -20,7 +20,8 @@ for n in (0, 1, 3, 4, 63, 64, 65, 127, 1000, 4097, 300_001, 3_000_000):
     k = max(1, n // 50)
     if n:
         pos = rng.integers(0, n, k)
-        src[pos] = np.frombuffer(b"NnRYKM$#U-*X\n", dtype=np.uint8)[rng.integers(0, 13, k)]
+        odd = np.frombuffer(b"NnRYKM$#U-*X\n \x00\x01\x10\x21\x41\x80\xc1\xe7\xd4\xff", dtype=np.uint8)
+        src[pos] = odd[rng.integers(0, len(odd), k)]       # incl. NUL / space / bytes with bit 7 set
     got, exc = f.host_pack_dna(src)
     up = src & 0xDF
     bad = ~((up == 65) | (up == 67) | (up == 71) | (up == 84))
