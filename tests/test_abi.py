@@ -128,3 +128,22 @@ def test_rust_sys_crate_declares_every_symbol():
     rs = open(os.path.join(ROOT, "rust", "awry-b200-sys", "src", "lib.rs")).read()
     have = set(re.findall(r"pub fn (awry_[a-z0-9_]+)", rs))
     assert sorted(have) == declared_symbols()
+
+
+def test_integration_doc_names_every_symbol():
+    """INTEGRATION.md is the maintainer's map of the boundary: every entry point of the header appears in it"""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert [s for s in declared_symbols() if s not in doc] == []
+
+
+def test_every_declaration_cites_the_reference_or_says_why_not():
+    """each block of the header names the reference item it replaces (file:line) or is one of the sections that
+    have no counterpart (device-resident entry points, instrumentation, knobs)"""
+    src = open(HEADER).read()
+    cites = re.findall(r"[a-z_]+\.rs:\d+", src)
+    assert len(cites) >= 40
+    for name in ("awry_index_load", "awry_index_save", "awry_index_from_parts", "awry_count_batch", "awry_locate_batch",
+                 "awry_search_batch", "awry_update_range", "awry_backstep", "awry_initial_range", "awry_index_build"):
+        at = src.index("int " + name)
+        comment = src[src.rfind("/*", 0, at):at]
+        assert re.search(r"\.rs:\d+", comment), name
