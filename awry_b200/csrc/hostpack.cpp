@@ -219,8 +219,8 @@ Level simd_level() {
       if (v == 1 && __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2")) return AVX2;
       if (v == 2 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw")) return AVX512;
     }
-    // AVX2 + PEXT first: measured 74 GB/s vs 63 GB/s for the AVX-512BW path on the 16-thread Sapphire
-    // Rapids host of the B200 box (profiles/r01_s21_host_pack_rate.log)
+    // AVX2 first: measured 121 GB/s vs 95 GB/s for the AVX-512BW path on the 16-thread Sapphire Rapids host
+    // of the B200 box (profiles/r01_s54_host_pack_rate_new_packer.log; 74 vs 63 GB/s with the PEXT packer)
     if (__builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2")) return AVX2;
     if (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw")) return AVX512;
     return SCALAR;
