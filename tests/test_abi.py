@@ -147,3 +147,10 @@ def test_every_declaration_cites_the_reference_or_says_why_not():
         at = src.index("int " + name)
         comment = src[src.rfind("/*", 0, at):at]
         assert re.search(r"\.rs:\d+", comment), name
+
+
+def test_cxx_mirror_compiles_against_the_header():
+    """include/awry_b200.hpp (the C++ mirror of the Rust API) and the test program that uses it compile cleanly;
+    the program itself runs in the GPU suite (test_cxx_host_mirror_every_kmer)"""
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I",
+                           os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cxx_host_mirror.cpp")])
