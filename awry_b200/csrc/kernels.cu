@@ -1197,10 +1197,10 @@ static cudaError_t launch_search_pair_b(const IndexView& ix, const uint64_t* d_q
     return 0u;
   }();
   // per-WARP ticket of the pair kernel (8 lane groups): one query per group for 150-bp reads, more for
-  // short queries
   // short queries; a small batch gets small tickets whatever the length, so that every warp still draws
-  // several (a 256 k-query chunk of 50-bp queries with 32-query tickets is 1.15 tickets per warp: the kernel
-  // runs for two ticket times, 0.34 ms instead of ~0.2, profiles/r01_s50_locate_gpu_timeline.log)
+  // several (a 256 k-query chunk of 50-bp queries with 32-query tickets is 1.15 tickets per warp).  Measured
+  // effect: small -- 1 M x 50-bp queries 0.567 -> 0.553 ms, a 256 k-query chunk 0.34 ms either way (there the
+  // fixed cost of filling and draining the persistent grid dominates, profiles/r01_s50_locate_gpu_timeline.log)
   uint32_t per_group = avg_len == 0 ? 2u : std::min(8u, std::max(1u, 200u / avg_len));
   per_group = ticket_cap(per_group, nq, uint64_t(grid) * (TPB / 4), avg_len);
   const uint32_t ticket_sz = ticket_env ? ticket_env : 8u * per_group;
