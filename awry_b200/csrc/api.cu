@@ -356,6 +356,7 @@ void make_replicas(awry_index* ix, const std::vector<int>& devs, Source& src, bo
     auto r = std::make_unique<Replica>();
     r->device = d;
     ix->reps.push_back(std::move(r));
+    ix->balance.push_back(std::make_unique<PackBalance>());
   }
   Replica& r0 = *ix->reps[0];
   build_replica0(ix, r0, src, from_file);

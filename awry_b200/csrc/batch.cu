@@ -158,142 +158,150 @@ bool host_pack_enabled() {
   return on;
 }
 
-// Pack on the host or send ASCII?  Packing wins when the host cores pack faster than the PCIe link moves
-// bytes (16 threads: 84 GB/s vs 52 GB/s for one GPU) and loses when a process has few cores and shares
-// the host's uplinks (4 threads per GPU on an 8-GPU box: measured 690 M reads/s packed vs 1095 M raw).
-// Both rates are MEASURED and smoothed across calls: the host clock around the packer (H), CUDA events
-// around the copy of a raw first chunk, when nothing else is in flight (P).  H > 1.15 P: pack everything
-// (one GPU, 16 threads: mixing raw chunks in was measured and is worse there -- a 128-MiB raw copy holds
-// the copy engine for 2.6 ms and starves the search kernel, profiles/r01_s19_e2e_pack_share.log).
-// Otherwise host and link are used together: a share f = H / (P + 0.75 H) of the bytes is packed
-// (+5 % / +14 % / -8 % at 2 / 4 / 8 GPUs of a 32-core box, profiles/r01_s23_e2e_mixed_multi_gpu.log).
-// AWRY_B200_PACK_SHARE=<0..1> pins the packed share of the bytes instead (experiments).
-struct PackBalance {
-  std::mutex mu;
-  double host_rate = 0, link_rate = 0;  // bytes/s, 0 = not measured yet
-  double fixed_share = -1;
-  uint64_t calls = 0;
-  bool mixed = true;  // AWRY_B200_PACK_MIXED=0: all-or-nothing
-  PackBalance() {
-    if (const char* e = getenv("AWRY_B200_PACK_SHARE")) fixed_share = std::min(1.0, std::max(0.0, atof(e)));
-    if (const char* e = getenv("AWRY_B200_PACK_MIXED")) mixed = e[0] != '0';
-  }
-  void note_host(double bytes, double seconds) {
-    if (seconds <= 0 || bytes < (8 << 20)) return;
-    std::lock_guard<std::mutex> lk(mu);
-    double r = bytes / seconds;
-    host_rate = host_rate > 0 ? 0.7 * host_rate + 0.3 * r : r;
-  }
-  void note_link(double bytes, double seconds) {
-    if (seconds <= 0 || bytes < (8 << 20)) return;
-    std::lock_guard<std::mutex> lk(mu);
-    double r = bytes / seconds;
-    link_rate = link_rate > 0 ? 0.7 * link_rate + 0.3 * r : r;
-  }
-  // per call: the packed share of the bytes and whether chunk 0 / chunk 1 serve as probes
-  struct Plan {
-    double share;
-    bool probe_link, probe_host;
-  };
-  Plan plan() {
-    std::lock_guard<std::mutex> lk(mu);
-    if (fixed_share >= 0) return Plan{fixed_share, false, false};
-    const bool refresh = calls++ % 32 == 0;
-    if (host_rate <= 0 || link_rate <= 0) return Plan{1.0, true, true};
-    if (host_rate > 1.15 * link_rate) return Plan{1.0, refresh, false};
-    // the host is not clearly faster than the link: use both (see the share formula above)
-    double f = mixed ? host_rate / (link_rate + 0.75 * host_rate) : 0.0;
-    if (f < 0.15) f = 0.0;
-    return Plan{f, true, f == 0.0 && refresh};
-  }
+// Where a batch's queries come from: ASCII bytes (the reference's `&str`s), or 2-bit codes the caller holds
+// already (awry_*_batch_packed2: crumb of byte position p at bits 2*(p%4) of crumbs[p/4], exceptions sorted
+// by position) -- then the host packer has nothing to do and a quarter of the bytes cross PCIe.
+struct QuerySource {
+  const uint8_t* qbytes = nullptr;
+  const uint8_t* crumbs = nullptr;
+  const uint64_t* exc = nullptr;  // ((position) << 8) | byte, ascending
+  uint64_t n_exc = 0;
+  const uint64_t* qoff = nullptr;
+  bool pinned = false;  // bytes / crumbs and offsets are page-locked: the copy engine reads them in place
 };
-PackBalance g_balance;
 
-void validate_offsets(const uint64_t* qoff, uint64_t nq) {
-  // cheap sanity check on the ends; per-query monotonicity is checked on the device (prepass)
-  if (nq && qoff[nq] < qoff[0]) fail(AWRY_ERR_INVALID_ARG, "query offsets are not monotone");
+// The chunker binary-searches the offsets and sizes every buffer from a chunk's byte range, so the ends of
+// every chunk are checked here (a non-monotone array can make b1 < b0 or a chunk absurdly large); inside a
+// chunk each query is checked against [b0, b1] on the device before it is touched (pack kernels).
+void validate_chunks(const std::vector<Chunk>& chunks, uint64_t max_bytes) {
+  for (const Chunk& c : chunks) {
+    if (c.b1 < c.b0) fail(AWRY_ERR_INVALID_ARG, "query offsets are not monotone (queries %llu..%llu)",
+                          (unsigned long long)c.q0, (unsigned long long)c.q1);
+    // one query may exceed the chunk budget; several may not
+    if (c.b1 - c.b0 > max_bytes && c.q1 - c.q0 > 1)
+      fail(AWRY_ERR_INVALID_ARG, "query offsets are not monotone (queries %llu..%llu)", (unsigned long long)c.q0,
+           (unsigned long long)c.q1);
+    if (c.b1 - c.b0 >= (1ull << 32)) fail(AWRY_ERR_INVALID_ARG, "query %llu is longer than 4 GiB", (unsigned long long)c.q0);
+  }
 }
 
 // Uploads one chunk of queries and runs prepass + search on ws->st.  The search result lands
 // in ws->d_out in the requested mode.
-// `may_pack`: the caller's say on host packing for this chunk (see raw_chunk_period)
-void enqueue_search(const awry_index* ix, Replica& r, Workspace* ws, const uint8_t* qbytes,
-                    const uint64_t* qoff, const Chunk& c, SearchOut mode, bool src_pinned, bool may_pack = true,
-                    bool probe_link = false, bool copy_flag = true) {
+// `may_pack`: the caller's say on host packing for this chunk (PackBalance)
+void enqueue_search(const awry_index* ix, Replica& r, PackBalance& bal, Workspace* ws, const QuerySource& qs,
+                    const Chunk& c, SearchOut mode, bool may_pack = true, bool probe_link = false, bool copy_flag = true) {
   const uint64_t nq = c.q1 - c.q0, nbytes = c.b1 - c.b0;
   const size_t out_elem = mode == OUT_COUNT_U64 ? 8 : mode == OUT_RANGE_U64 ? 16 : 8;
+  const int ush = packed_unit_shift(ix->alphabet);
   Workspace::grow_dev(ws->d_qbytes, ws->d_qbytes_cap, size_t(nbytes) + 16);
   Workspace::grow_dev(ws->d_qoff, ws->d_qoff_cap, size_t(nq) + 1);
   Workspace::grow_dev(ws->d_qwords, ws->d_qwords_cap, size_t(packed_words(ix->alphabet, nq, nbytes)));
   Workspace::grow_dev(ws->d_out, ws->d_out_cap, size_t(nq) * out_elem);
   Workspace::grow_dev(ws->d_defer, ws->d_defer_cap, size_t(nq) + 2);
-  const uint8_t* src_b = qbytes + c.b0;
-  const uint64_t* src_o = qoff + c.q0;
-  // Nucleotide chunks are packed to 2 bits per base by the host cores before the copy (a quarter of
-  // the PCIe bytes; works the same for pageable and pinned caller memory).  Chunks with many bytes
-  // outside ACGT go up as ASCII.
-  bool packed = false;
+  const uint64_t* src_o = qs.qoff + c.q0;
+  uint64_t* const d_words = ws->d_qwords - 4 * (c.b0 >> ush);
   ws->link_probe_bytes = 0;
-  if (may_pack && ix->alphabet == AWRY_NUCLEOTIDE && host_pack_enabled() && nbytes >= 4096) {
-    Workspace::grow_host(ws->h_qbytes, ws->h_qbytes_cap, size_t(nbytes) / 4 + 64);
-    auto t0 = std::chrono::steady_clock::now();
-    packed = host_pack_dna(src_b, size_t(nbytes), ws->h_qbytes, ws->exc_tmp, 64);
-    if (packed) g_balance.note_host(double(nbytes), std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
-    trace_mark("  host pack done, bytes", (long long)nbytes);
-  }
-  if (packed) {
-    const size_t n_exc = ws->exc_tmp.size();
-    const size_t pbytes = (size_t(nbytes) + 3) / 4;
-    if (!src_pinned) {  // offsets: staged through pinned memory by the pool
-      Workspace::grow_host(ws->h_qoff, ws->h_qoff_cap, size_t(nq) + 1);
-      parallel_memcpy(ws->h_qoff, src_o, (nq + 1) * 8);
-      src_o = ws->h_qoff;
+  auto stage_offsets = [&] {  // pageable offsets: staged through pinned memory
+    if (qs.pinned) return;
+    Workspace::grow_host(ws->h_qoff, ws->h_qoff_cap, size_t(nq) + 1);
+    parallel_memcpy(ws->h_qoff, src_o, (nq + 1) * 8);
+    src_o = ws->h_qoff;
+  };
+  if (qs.crumbs) {
+    // pre-packed by the caller: bytes [b0/4, ceil(b1/4)) of the crumb array, exceptions of [b0, b1)
+    const uint64_t cb0 = c.b0 >> 2, cb1 = (c.b1 + 3) >> 2;
+    const size_t pbytes = size_t(cb1 - cb0);
+    const uint8_t* src_c = qs.crumbs + cb0;
+    const uint64_t* e_lo = std::lower_bound(qs.exc, qs.exc + qs.n_exc, c.b0 << 8);
+    const uint64_t* e_hi = std::lower_bound(e_lo, qs.exc + qs.n_exc, c.b1 << 8);
+    const size_t n_exc = size_t(e_hi - e_lo);
+    stage_offsets();
+    if (!qs.pinned) {
+      Workspace::grow_host(ws->h_qbytes, ws->h_qbytes_cap, pbytes + 64);
+      parallel_memcpy(ws->h_qbytes, src_c, pbytes);
+      src_c = ws->h_qbytes;
     }
-    CU(cudaMemcpyAsync(ws->d_qbytes, ws->h_qbytes, pbytes + 8, cudaMemcpyHostToDevice, ws->st));
+    if (pbytes) CU(cudaMemcpyAsync(ws->d_qbytes, src_c, pbytes, cudaMemcpyHostToDevice, ws->st));
     CU(cudaMemcpyAsync(ws->d_qoff, src_o, (nq + 1) * 8, cudaMemcpyHostToDevice, ws->st));
     if (n_exc) {
-      Workspace::grow_host(ws->h_exc, ws->h_exc_cap, n_exc);
       Workspace::grow_dev(ws->d_exc, ws->d_exc_cap, n_exc);
-      memcpy(ws->h_exc, ws->exc_tmp.data(), n_exc * 8);
-      CU(cudaMemcpyAsync(ws->d_exc, ws->h_exc, n_exc * 8, cudaMemcpyHostToDevice, ws->st));
+      const uint64_t* src_e = e_lo;
+      if (!qs.pinned) {
+        Workspace::grow_host(ws->h_exc, ws->h_exc_cap, n_exc);
+        memcpy(ws->h_exc, e_lo, n_exc * 8);
+        src_e = ws->h_exc;
+      }
+      CU(cudaMemcpyAsync(ws->d_exc, src_e, n_exc * 8, cudaMemcpyHostToDevice, ws->st));
     }
-    g_prof.h2d += pbytes + 8 + (nq + 1) * 8 + n_exc * 8;
+    g_prof.h2d += pbytes + (nq + 1) * 8 + n_exc * 8;
     gpu_mark(ws->st, "h2d done", (long long)c.q0);
     CU(cudaMemsetAsync(ws->d_flag, 0xff, 8, ws->st));
     {
       ProfScope p(2, r.device, ws->st);
-      CU(launch_pack2(reinterpret_cast<const uint32_t*>(ws->d_qbytes), c.b0, ws->d_qoff, nq,
-                      ws->d_qwords - 4 * (c.b0 >> packed_unit_shift(ix->alphabet)), ws->d_exc, n_exc, ws->d_flag, ws->st));
+      CU(launch_pack2(reinterpret_cast<const uint32_t*>(ws->d_qbytes), cb0 << 2, ws->d_qoff, nq, d_words, ws->d_exc, n_exc,
+                      0, c.b0, c.b1, ws->d_flag, ws->st));
     }
   } else {
-    if (!src_pinned) {
-      Workspace::grow_host(ws->h_qbytes, ws->h_qbytes_cap, size_t(nbytes) + 16);
-      Workspace::grow_host(ws->h_qoff, ws->h_qoff_cap, size_t(nq) + 1);
-      parallel_memcpy(ws->h_qbytes, src_b, nbytes);
-      parallel_memcpy(ws->h_qoff, src_o, (nq + 1) * 8);
-      src_b = ws->h_qbytes;
-      src_o = ws->h_qoff;
+    const uint8_t* src_b = qs.qbytes + c.b0;
+    // Nucleotide chunks are packed to 2 bits per base by the host cores before the copy (a quarter of
+    // the PCIe bytes; works the same for pageable and pinned caller memory).  Chunks with many bytes
+    // outside ACGT go up as ASCII.
+    bool packed = false;
+    if (may_pack && ix->alphabet == AWRY_NUCLEOTIDE && host_pack_enabled() && nbytes >= 4096) {
+      Workspace::grow_host(ws->h_qbytes, ws->h_qbytes_cap, size_t(nbytes) / 4 + 64);
+      auto t0 = std::chrono::steady_clock::now();
+      packed = host_pack_dna(src_b, size_t(nbytes), ws->h_qbytes, ws->exc_tmp, 64);
+      if (packed) bal.note_host(double(nbytes), std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+      trace_mark("  host pack done, bytes", (long long)nbytes);
     }
-    const bool probe = probe_link && src_pinned && nbytes >= (8u << 20);
-    if (probe) {
-      if (!ws->ev_a) {
-        CU(cudaEventCreate(&ws->ev_a));
-        CU(cudaEventCreate(&ws->ev_b));
+    if (packed) {
+      const size_t n_exc = ws->exc_tmp.size();
+      const size_t pbytes = (size_t(nbytes) + 3) / 4;
+      stage_offsets();
+      CU(cudaMemcpyAsync(ws->d_qbytes, ws->h_qbytes, pbytes + 8, cudaMemcpyHostToDevice, ws->st));
+      CU(cudaMemcpyAsync(ws->d_qoff, src_o, (nq + 1) * 8, cudaMemcpyHostToDevice, ws->st));
+      if (n_exc) {
+        Workspace::grow_host(ws->h_exc, ws->h_exc_cap, n_exc);
+        Workspace::grow_dev(ws->d_exc, ws->d_exc_cap, n_exc);
+        memcpy(ws->h_exc, ws->exc_tmp.data(), n_exc * 8);
+        CU(cudaMemcpyAsync(ws->d_exc, ws->h_exc, n_exc * 8, cudaMemcpyHostToDevice, ws->st));
       }
-      CU(cudaEventRecord(ws->ev_a, ws->st));
-    }
-    if (nbytes) CU(cudaMemcpyAsync(ws->d_qbytes, src_b, nbytes, cudaMemcpyHostToDevice, ws->st));
-    if (probe) {
-      CU(cudaEventRecord(ws->ev_b, ws->st));
-      ws->link_probe_bytes = nbytes;
-    }
-    CU(cudaMemcpyAsync(ws->d_qoff, src_o, (nq + 1) * 8, cudaMemcpyHostToDevice, ws->st));
-    g_prof.h2d += nbytes + (nq + 1) * 8;
-    CU(cudaMemsetAsync(ws->d_flag, 0xff, 8, ws->st));
-    // offsets stay absolute: the kernels subtract the chunk's byte base
-    {
-      ProfScope p(2, r.device, ws->st);
-      CU(launch_pack(ix->alphabet, ws->d_qbytes - c.b0, ws->d_qoff, nq, ws->d_qwords - 4 * (c.b0 >> packed_unit_shift(ix->alphabet)), ws->d_flag, ws->st));
+      g_prof.h2d += pbytes + 8 + (nq + 1) * 8 + n_exc * 8;
+      gpu_mark(ws->st, "h2d done", (long long)c.q0);
+      CU(cudaMemsetAsync(ws->d_flag, 0xff, 8, ws->st));
+      {
+        ProfScope p(2, r.device, ws->st);
+        CU(launch_pack2(reinterpret_cast<const uint32_t*>(ws->d_qbytes), c.b0, ws->d_qoff, nq, d_words, ws->d_exc, n_exc,
+                        c.b0, c.b0, c.b1, ws->d_flag, ws->st));
+      }
+    } else {
+      if (!qs.pinned) {
+        Workspace::grow_host(ws->h_qbytes, ws->h_qbytes_cap, size_t(nbytes) + 16);
+        parallel_memcpy(ws->h_qbytes, src_b, nbytes);
+        src_b = ws->h_qbytes;
+      }
+      stage_offsets();
+      const bool probe = probe_link && qs.pinned && nbytes >= (8u << 20);
+      if (probe) {
+        if (!ws->ev_a) {
+          CU(cudaEventCreate(&ws->ev_a));
+          CU(cudaEventCreate(&ws->ev_b));
+        }
+        CU(cudaEventRecord(ws->ev_a, ws->st));
+      }
+      if (nbytes) CU(cudaMemcpyAsync(ws->d_qbytes, src_b, nbytes, cudaMemcpyHostToDevice, ws->st));
+      if (probe) {
+        CU(cudaEventRecord(ws->ev_b, ws->st));
+        ws->link_probe_bytes = nbytes;
+      }
+      CU(cudaMemcpyAsync(ws->d_qoff, src_o, (nq + 1) * 8, cudaMemcpyHostToDevice, ws->st));
+      g_prof.h2d += nbytes + (nq + 1) * 8;
+      CU(cudaMemsetAsync(ws->d_flag, 0xff, 8, ws->st));
+      // offsets stay absolute: the kernels subtract the chunk's byte base
+      {
+        ProfScope p(2, r.device, ws->st);
+        CU(launch_pack(ix->alphabet, ws->d_qbytes - c.b0, ws->d_qoff, nq, d_words, c.b0, c.b1, ws->d_flag, ws->st));
+      }
     }
   }
   gpu_mark(ws->st, "packed on device", (long long)c.q0);
@@ -301,7 +309,9 @@ void enqueue_search(const awry_index* ix, Replica& r, Workspace* ws, const uint8
     ProfScope p(0, r.device, ws->st);
     SearchVariant v = g_variant;
     v.avg_len = uint32_t(std::min<uint64_t>(nbytes / std::max<uint64_t>(1, nq), 1u << 30));
-    CU(launch_search(r.view, ws->d_qwords - 4 * (c.b0 >> packed_unit_shift(ix->alphabet)), ws->d_qoff, nq, mode, ws->d_out, ws->d_defer, v, r.sm_count, ws->st));
+    v.b_lo = c.b0;
+    v.b_hi = c.b1;
+    CU(launch_search(r.view, d_words, ws->d_qoff, nq, mode, ws->d_out, ws->d_defer, v, r.sm_count, ws->st));
   }
   gpu_mark(ws->st, "searched", (long long)c.q0);
   // (the locate pipeline copies the flag together with the hit total, after the scan: one hand-over between
@@ -310,23 +320,35 @@ void enqueue_search(const awry_index* ix, Replica& r, Workspace* ws, const uint8
   trace_mark("  search enqueued, queries", (long long)nq);
 }
 
+[[noreturn]] void fail_bad_query(unsigned long long code, uint64_t q_base) {
+  const unsigned long long q = q_base + (code >> 1);
+  if ((code & 1) == BAD_OFFSETS)
+    fail(AWRY_ERR_INVALID_ARG, "query offsets are not monotone at query %llu (its bytes lie outside the batch)", q);
+  fail(AWRY_ERR_INVALID_QUERY,
+       "query %llu is empty or contains a sentinel ('$'/'#'): the reference panics on it "
+       "(fm_index.rs:406, bwt.rs:127)", q);
+}
+
 void check_flag(Workspace* ws, const Chunk& c) {
-  if (*ws->h_flag != ~0ull)
-    fail(AWRY_ERR_INVALID_QUERY,
-         "query %llu is empty or contains a sentinel ('$'/'#'): the reference panics on it "
-         "(fm_index.rs:406, bwt.rs:127)",
-         (unsigned long long)(c.q0 + *ws->h_flag));
+  if (*ws->h_flag != ~0ull) fail_bad_query(*ws->h_flag, c.q0);
 }
 
 // count / range search over [q_lo, q_hi) on one replica, 3-deep pipeline
-void search_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, const uint64_t* qoff,
-                       uint64_t q_lo, uint64_t q_hi, SearchOut mode, void* out) {
+void search_on_replica(const awry_index* ix, size_t ri, const QuerySource& qs, uint64_t q_lo, uint64_t q_hi,
+                       SearchOut mode, void* out) {
   if (q_lo >= q_hi) return;
+  Replica& r = *ix->reps[ri];
+  PackBalance& bal = ix->balance_of(ri);
   DeviceGuard dg(r.device);
   const size_t out_elem = mode == OUT_COUNT_U64 ? 8 : 16;
-  const bool src_pinned = is_pinned(qbytes) && is_pinned(qoff);
+  const uint64_t* qoff = qs.qoff;
+  const bool src_pinned = qs.pinned;
   const bool dst_pinned = is_pinned(out);
-  auto chunks = taper_chunks(make_chunks(qoff, q_lo, q_hi, CHUNK_MAX_Q, chunk_max_bytes()), qoff);
+  // pre-packed queries are a quarter of the bytes: four times the reads per chunk keep the chunk count down
+  const uint64_t max_bytes = chunk_max_bytes() * (qs.crumbs ? 2 : 1);
+  auto chunks = make_chunks(qoff, q_lo, q_hi, CHUNK_MAX_Q, max_bytes);
+  validate_chunks(chunks, max_bytes);
+  chunks = taper_chunks(std::move(chunks), qoff);
   constexpr int DEPTH = 3;
   Workspace* ws[DEPTH] = {nullptr, nullptr, nullptr};
   int pending[DEPTH] = {-1, -1, -1};
@@ -337,7 +359,7 @@ void search_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
     if (ws[s]->link_probe_bytes) {
       float ms = 0;
       if (cudaEventElapsedTime(&ms, ws[s]->ev_a, ws[s]->ev_b) == cudaSuccess)
-        g_balance.note_link(double(ws[s]->link_probe_bytes), double(ms) * 1e-3);
+        bal.note_link(double(ws[s]->link_probe_bytes), double(ms) * 1e-3);
       ws[s]->link_probe_bytes = 0;
     }
     check_flag(ws[s], c);
@@ -346,9 +368,9 @@ void search_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
     pending[s] = -1;
   };
   uint64_t bytes_total = 0, bytes_packed = 0;  // of the chunks enqueued so far (pinned sources only)
-  const bool balanced = src_pinned && ix->alphabet == AWRY_NUCLEOTIDE && host_pack_enabled();
+  const bool balanced = src_pinned && !qs.crumbs && ix->alphabet == AWRY_NUCLEOTIDE && host_pack_enabled();
   PackBalance::Plan plan{1.0, false, false};
-  if (balanced) plan = g_balance.plan();
+  if (balanced) plan = bal.plan();
   try {
     for (size_t i = 0; i < chunks.size(); i++) {
       int s = int(i % DEPTH);
@@ -368,7 +390,7 @@ void search_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
         bytes_total += c.b1 - c.b0;
         if (may_pack) bytes_packed += c.b1 - c.b0;
       }
-      enqueue_search(ix, r, ws[s], qbytes, qoff, c, mode, src_pinned, may_pack, probe);
+      enqueue_search(ix, r, bal, ws[s], qs, c, mode, may_pack, probe);
       size_t bytes = (c.q1 - c.q0) * out_elem;
       void* dst = static_cast<char*>(out) + c.q0 * out_elem;
       if (!dst_pinned) {
@@ -524,15 +546,19 @@ static uint64_t locate_chunk_bytes() {
   return LOCATE_CHUNK_BYTES;
 }
 
-void locate_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, const uint64_t* qoff,
-                       uint64_t q_lo, uint64_t q_hi, uint32_t flags, LocatePart& part) {
+void locate_on_replica(const awry_index* ix, size_t ri, const QuerySource& qs, uint64_t q_lo, uint64_t q_hi,
+                       uint32_t flags, LocatePart& part) {
   const bool ext = part.ext_cap != 0 || part.ext_off != nullptr;
   if (!part.ext_off) part.hit_off.assign(q_hi - q_lo + 1, 0);
   uint64_t* off_base = part.ext_off ? part.ext_off : part.hit_off.data();
   if (q_lo >= q_hi) return;
+  Replica& r = *ix->reps[ri];
+  PackBalance& bal = ix->balance_of(ri);
   DeviceGuard dg(r.device);
-  const bool src_pinned = is_pinned(qbytes) && is_pinned(qoff);
-  auto chunks = make_chunks(qoff, q_lo, q_hi, locate_chunk_q(), std::min(chunk_max_bytes(), locate_chunk_bytes()));
+  const uint64_t* qoff = qs.qoff;
+  const uint64_t max_bytes = std::min(chunk_max_bytes(), locate_chunk_bytes());
+  auto chunks = make_chunks(qoff, q_lo, q_hi, locate_chunk_q(), max_bytes);
+  validate_chunks(chunks, max_bytes);
   constexpr int DEPTH = 3;
   struct Slot {
     Workspace* ws = nullptr;
@@ -564,7 +590,7 @@ void locate_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
     const uint64_t nq = c.q1 - c.q0;
     mark("A begin", i);
     gpu_mark(ws->st, "chunk begins", i);
-    enqueue_search(ix, r, ws, qbytes, qoff, c, OUT_SP_CNT_U32, src_pinned, true, false, false);
+    enqueue_search(ix, r, bal, ws, qs, c, OUT_SP_CNT_U32, true, false, false);
     mark("A searched", i);
     Workspace::grow_dev(ws->d_hit_off, ws->d_hit_off_cap, size_t(nq) + 1);
     locate_chunk_scan(ws, nq, ws->d_hit_off, ws->st);
@@ -641,6 +667,225 @@ void locate_on_replica(const awry_index* ix, Replica& r, const uint8_t* qbytes, 
     if (s.ws) r.release(s.ws);
 }
 
+// parallel_locate into the caller's pinned buffers with no host round trip between the passes (the
+// unsampled-SA gather, BWT order).  Per chunk: pack -> search -> scan -> the device hands the chunk its hit base
+// (advance_hit_base_kernel, ordered behind the previous chunk's by an event) -> the gather writes the hits
+// straight into `hits` (host memory, through its device view) and the rebased offsets into a device array
+// that one copy returns.  The host enqueues chunk after chunk and waits once at the end; a workspace is
+// reused when its chunk of three rounds ago has drained.  Returns the hit total (it may exceed capacity).
+// cfg3 end to end: 2.2 ms -> see profiles/ (the two-sync pipeline above stays for library-owned results,
+// sorted output and the LF-walk variants, which size their buffers from the total).
+uint64_t locate_direct_on_replica(const awry_index* ix, size_t ri, const QuerySource& qs, uint64_t nq, uint64_t* hit_off,
+                                  awry_hit* hits, void* hits_dev, uint64_t capacity) {
+  Replica& r = *ix->reps[ri];
+  PackBalance& bal = ix->balance_of(ri);
+  DeviceGuard dg(r.device);
+  const uint64_t* qoff = qs.qoff;
+  const uint64_t max_bytes = std::min(chunk_max_bytes(), locate_chunk_bytes());
+  auto chunks = make_chunks(qoff, 0, nq, locate_chunk_q(), max_bytes);
+  validate_chunks(chunks, max_bytes);
+  const bool off_pinned = is_pinned(hit_off);
+  constexpr int DEPTH = 3;
+  Workspace* ws[DEPTH] = {nullptr, nullptr, nullptr};
+  int pending[DEPTH] = {-1, -1, -1};
+  (void)hits;
+  auto finish = [&](int s) {
+    if (pending[s] < 0) return;
+    const Chunk& c = chunks[size_t(pending[s])];
+    CU(cudaEventSynchronize(ws[s]->done));
+    check_flag(ws[s], c);
+    if (!off_pinned) memcpy(hit_off + c.q0, ws[s]->h_out, (c.q1 - c.q0) * 8);
+    pending[s] = -1;
+  };
+  GpuTrace gpu_trace;
+  g_gpu_trace = trace_on() ? &gpu_trace : nullptr;
+  uint64_t total = 0;
+  try {
+    ws[0] = r.acquire();
+    unsigned long long* const d_running = ws[0]->d_base + 1;
+    CU(cudaMemsetAsync(d_running, 0, 8, ws[0]->st));
+    CU(cudaEventRecord(ws[0]->ev_adv, ws[0]->st));  // chunk 0 waits for the counter's reset like for a predecessor
+    cudaEvent_t prev_adv = ws[0]->ev_adv;
+    for (size_t i = 0; i < chunks.size(); i++) {
+      const int s = int(i % DEPTH);
+      if (!ws[s]) ws[s] = r.acquire();
+      finish(s);
+      Workspace* w = ws[s];
+      const Chunk& c = chunks[i];
+      const uint64_t n = c.q1 - c.q0;
+      gpu_mark(w->st, "chunk begins", (long long)i);
+      enqueue_search(ix, r, bal, w, qs, c, OUT_SP_CNT_U32, true, false, false);
+      Workspace::grow_dev(w->d_hit_off, w->d_hit_off_cap, size_t(n) + 1);
+      Workspace::grow_dev(w->d_off_out, w->d_off_out_cap, size_t(n) + 1);
+      locate_chunk_scan(w, n, w->d_hit_off, w->st);
+      gpu_mark(w->st, "scanned", (long long)i);
+      // (chunk 0 waits for the counter's reset; a slot's event is re-recorded only after the wait on its
+      // earlier state has been enqueued)
+      CU(launch_gather_direct(r.view, reinterpret_cast<const uint2*>(w->d_out), w->d_hit_off, n, d_running, w->d_base,
+                              hits_dev, capacity, w->d_off_out, r.sm_count, prev_adv, w->ev_adv, w->st));
+      prev_adv = w->ev_adv;
+      gpu_mark(w->st, "hits written", (long long)i);
+      uint64_t* dst = hit_off + c.q0;
+      if (!off_pinned) {
+        Workspace::grow_host(w->h_out, w->h_out_cap, size_t(n) * 8);
+        dst = reinterpret_cast<uint64_t*>(w->h_out);
+      }
+      CU(cudaMemcpyAsync(dst, w->d_off_out, n * 8, cudaMemcpyDeviceToHost, w->st));
+      CU(cudaMemcpyAsync(w->h_flag, w->d_flag, 8, cudaMemcpyDeviceToHost, w->st));
+      if (i + 1 == chunks.size()) CU(cudaMemcpyAsync(w->h_total, d_running, 8, cudaMemcpyDeviceToHost, w->st));
+      g_prof.d2h += n * 8 + 16;
+      CU(cudaEventRecord(w->done, w->st));
+      pending[s] = int(i);
+    }
+    const int last = int((chunks.size() - 1) % DEPTH);
+    for (int s = 0; s < DEPTH; s++) finish((last + 1 + s) % DEPTH);  // oldest first; the last chunk carries the total
+    total = *ws[last]->h_total;
+    g_prof.d2h += std::min(total, capacity) * sizeof(awry_hit);
+    hit_off[nq] = total;
+    g_gpu_trace = nullptr;
+    gpu_trace.dump();
+  } catch (...) {
+    g_gpu_trace = nullptr;
+    for (int s = 0; s < DEPTH; s++)
+      if (ws[s]) {
+        cudaStreamSynchronize(ws[s]->st);
+        r.release(ws[s]);
+      }
+    throw;
+  }
+  for (int s = 0; s < DEPTH; s++)
+    if (ws[s]) r.release(ws[s]);
+  return total;
+}
+
+// the device's view of a page-locked host buffer (cudaHostAlloc / cudaHostRegister), or nullptr
+void* device_view_of_pinned(const void* p) {
+  if (!p || !is_pinned(p)) return nullptr;
+  void* d = nullptr;
+  if (cudaHostGetDevicePointer(&d, const_cast<void*>(p), 0) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return d;
+}
+
+static bool direct_locate_enabled() {  // AWRY_B200_LOCATE_DIRECT=0: always the two-sync pipeline (A/B runs)
+  const char* e = getenv("AWRY_B200_LOCATE_DIRECT");
+  return !(e && e[0] == '0');
+}
+
+QuerySource ascii_source(const uint8_t* qbytes, const uint64_t* qoff) {
+  QuerySource qs;
+  qs.qbytes = qbytes;
+  qs.qoff = qoff;
+  qs.pinned = is_pinned(qbytes) && is_pinned(qoff);
+  return qs;
+}
+
+// awry_*_batch_packed2 arguments -> QuerySource (nucleotide only; exceptions must ascend by position)
+QuerySource packed2_source(const awry_index* ix, const uint8_t* crumbs, const uint64_t* qoff, uint64_t nq,
+                           const uint64_t* exceptions, uint64_t n_exc) {
+  if (ix->alphabet != AWRY_NUCLEOTIDE) fail(AWRY_ERR_UNSUPPORTED, "2-bit packed queries exist for the nucleotide alphabet only");
+  if (!crumbs || !qoff || (n_exc && !exceptions)) fail(AWRY_ERR_INVALID_ARG, "null argument");
+  for (uint64_t i = 1; i < n_exc; i++)
+    if ((exceptions[i] >> 8) <= (exceptions[i - 1] >> 8))
+      fail(AWRY_ERR_INVALID_ARG, "exception list is not strictly ascending by position (entry %llu)", (unsigned long long)i);
+  if (n_exc && (exceptions[n_exc - 1] >> 8) >= qoff[nq] && qoff[nq] >= qoff[0])
+    fail(AWRY_ERR_INVALID_ARG, "exception position %llu lies behind the last query byte",
+         (unsigned long long)(exceptions[n_exc - 1] >> 8));
+  QuerySource qs;
+  qs.crumbs = crumbs;
+  qs.exc = exceptions;
+  qs.n_exc = n_exc;
+  qs.qoff = qoff;
+  qs.pinned = is_pinned(crumbs) && is_pinned(qoff) && (n_exc == 0 || is_pinned(exceptions));
+  return qs;
+}
+
+void count_impl(const awry_index* ix, const QuerySource& qs, uint64_t nq, SearchOut mode, void* out) {
+  for_each_replica_range(ix, qs.qoff, nq, [&](size_t ri, uint64_t lo, uint64_t hi) {
+    search_on_replica(ix, ri, qs, lo, hi, mode, out);
+  });
+}
+
+void locate_owned_impl(const awry_index* ix, const QuerySource& qs, uint64_t nq, uint32_t flags, uint64_t* hit_off,
+                       awry_hit** hits, uint64_t* n_hits) {
+  size_t nr = ix->reps.size();
+  std::vector<LocatePart> parts(nr);
+  std::vector<std::pair<uint64_t, uint64_t>> ranges(nr, {0, 0});
+  try {
+    for_each_replica_range(ix, qs.qoff, nq, [&](size_t ri, uint64_t lo, uint64_t hi) {
+      ranges[ri] = {lo, hi};
+      locate_on_replica(ix, ri, qs, lo, hi, flags, parts[ri]);
+    });
+  } catch (...) {
+    for (auto& p : parts) free(p.hits);
+    throw;
+  }
+  // concatenate in range order (results of the reference's order-preserving collect)
+  uint64_t total = 0;
+  for (auto& p : parts) total += p.n_hits;
+  awry_hit* all = nullptr;
+  if (nr == 1) {
+    all = parts[0].hits;
+    parts[0].hits = nullptr;
+  } else if (total) {
+    all = static_cast<awry_hit*>(malloc(total * sizeof(awry_hit)));
+    if (!all) {
+      for (auto& p : parts) free(p.hits);
+      fail(AWRY_ERR_NOMEM, "out of host memory for %llu hits", (unsigned long long)total);
+    }
+  }
+  uint64_t base = 0;
+  for (size_t ri = 0; ri < nr; ri++) {
+    auto [lo, hi] = ranges[ri];
+    if (hi > lo)
+      for (uint64_t i = 0; i <= hi - lo; i++) hit_off[lo + i] = base + parts[ri].hit_off[i];
+    if (nr > 1 && parts[ri].n_hits) memcpy(all + base, parts[ri].hits, parts[ri].n_hits * sizeof(awry_hit));
+    base += parts[ri].n_hits;
+    if (nr > 1) free(parts[ri].hits);
+  }
+  hit_off[nq] = total;
+  *hits = all;
+  *n_hits = total;
+}
+
+void locate_into_impl(const awry_index* ix, const QuerySource& qs, uint64_t nq, uint32_t flags, uint64_t* hit_off,
+                      awry_hit* hits, uint64_t capacity, uint64_t* n_hits) {
+  auto too_small = [&](uint64_t need) {
+    fail(AWRY_ERR_CAPACITY, "hit buffer holds %llu entries, %llu needed", (unsigned long long)capacity,
+         (unsigned long long)need);
+  };
+  if (ix->reps.size() == 1) {
+    Replica& r0 = *ix->reps[0];
+    void* hits_dev = capacity ? device_view_of_pinned(hits) : nullptr;
+    if (hits_dev && !(flags & AWRY_LOCATE_SORTED) && r0.view.full_sa && g_locate_variant == 0 && direct_locate_enabled()) {
+      *n_hits = locate_direct_on_replica(ix, 0, qs, nq, hit_off, hits, hits_dev, capacity);
+      if (*n_hits > capacity) too_small(*n_hits);
+      return;
+    }
+    // hits and offsets land straight in the caller's (ideally pinned) buffers
+    LocatePart part;
+    part.hits = hits;
+    part.ext_cap = capacity;
+    part.ext_off = hit_off;  // marks the part as caller-owned even when capacity is 0
+    locate_on_replica(ix, 0, qs, 0, nq, flags, part);
+    *n_hits = part.n_hits;
+    if (part.n_hits > capacity) too_small(part.n_hits);
+    return;
+  }
+  awry_hit* tmp = nullptr;
+  uint64_t n = 0;
+  locate_owned_impl(ix, qs, nq, flags, hit_off, &tmp, &n);
+  *n_hits = n;
+  if (n > capacity) {
+    free(tmp);
+    too_small(n);
+  }
+  if (n) parallel_memcpy(hits, tmp, n * sizeof(awry_hit));
+  free(tmp);
+}
+
 }  // namespace host
 }  // namespace awry
 
@@ -651,10 +896,7 @@ int awry_count_batch(const awry_index* ix, const uint8_t* qbytes, const uint64_t
     need(ix);
     if (nq == 0) return;
     if (!qbytes || !qoff || !counts) fail(AWRY_ERR_INVALID_ARG, "null argument");
-    validate_offsets(qoff, nq);
-    for_each_replica_range(ix, qoff, nq, [&](size_t ri, uint64_t lo, uint64_t hi) {
-      search_on_replica(ix, *ix->reps[ri], qbytes, qoff, lo, hi, OUT_COUNT_U64, counts);
-    });
+    count_impl(ix, ascii_source(qbytes, qoff), nq, OUT_COUNT_U64, counts);
   });
 }
 
@@ -663,10 +905,17 @@ int awry_search_batch(const awry_index* ix, const uint8_t* qbytes, const uint64_
     need(ix);
     if (nq == 0) return;
     if (!qbytes || !qoff || !ranges) fail(AWRY_ERR_INVALID_ARG, "null argument");
-    validate_offsets(qoff, nq);
-    for_each_replica_range(ix, qoff, nq, [&](size_t ri, uint64_t lo, uint64_t hi) {
-      search_on_replica(ix, *ix->reps[ri], qbytes, qoff, lo, hi, OUT_RANGE_U64, ranges);
-    });
+    count_impl(ix, ascii_source(qbytes, qoff), nq, OUT_RANGE_U64, ranges);
+  });
+}
+
+int awry_count_batch_packed2(const awry_index* ix, const uint8_t* crumbs, const uint64_t* qoff, uint64_t nq,
+                             const uint64_t* exceptions, uint64_t n_exc, uint64_t* counts) {
+  return guarded([&] {
+    need(ix);
+    if (nq == 0) return;
+    if (!counts) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    count_impl(ix, packed2_source(ix, crumbs, qoff, nq, exceptions, n_exc), nq, OUT_COUNT_U64, counts);
   });
 }
 
@@ -680,45 +929,7 @@ int awry_locate_batch(const awry_index* ix, const uint8_t* qbytes, const uint64_
     hit_off[0] = 0;
     if (nq == 0) return;
     if (!qbytes || !qoff) fail(AWRY_ERR_INVALID_ARG, "null argument");
-    validate_offsets(qoff, nq);
-    size_t nr = ix->reps.size();
-    std::vector<LocatePart> parts(nr);
-    std::vector<std::pair<uint64_t, uint64_t>> ranges(nr, {0, 0});
-    try {
-      for_each_replica_range(ix, qoff, nq, [&](size_t ri, uint64_t lo, uint64_t hi) {
-        ranges[ri] = {lo, hi};
-        locate_on_replica(ix, *ix->reps[ri], qbytes, qoff, lo, hi, flags, parts[ri]);
-      });
-    } catch (...) {
-      for (auto& p : parts) free(p.hits);
-      throw;
-    }
-    // concatenate in range order (results of the reference's order-preserving collect)
-    uint64_t total = 0;
-    for (auto& p : parts) total += p.n_hits;
-    awry_hit* all = nullptr;
-    if (nr == 1) {
-      all = parts[0].hits;
-      parts[0].hits = nullptr;
-    } else if (total) {
-      all = static_cast<awry_hit*>(malloc(total * sizeof(awry_hit)));
-      if (!all) {
-        for (auto& p : parts) free(p.hits);
-        fail(AWRY_ERR_NOMEM, "out of host memory for %llu hits", (unsigned long long)total);
-      }
-    }
-    uint64_t base = 0;
-    for (size_t ri = 0; ri < nr; ri++) {
-      auto [lo, hi] = ranges[ri];
-      if (hi > lo)
-        for (uint64_t i = 0; i <= hi - lo; i++) hit_off[lo + i] = base + parts[ri].hit_off[i];
-      if (nr > 1 && parts[ri].n_hits) memcpy(all + base, parts[ri].hits, parts[ri].n_hits * sizeof(awry_hit));
-      base += parts[ri].n_hits;
-      if (nr > 1) free(parts[ri].hits);
-    }
-    hit_off[nq] = total;
-    *hits = all;
-    *n_hits = total;
+    locate_owned_impl(ix, ascii_source(qbytes, qoff), nq, flags, hit_off, hits, n_hits);
   });
 }
 
@@ -733,31 +944,20 @@ int awry_locate_batch_into(const awry_index* ix, const uint8_t* qbytes, const ui
     hit_off[0] = 0;
     if (nq == 0) return;
     if (!qbytes || !qoff) fail(AWRY_ERR_INVALID_ARG, "null argument");
-    validate_offsets(qoff, nq);
-    if (ix->reps.size() == 1) {  // hits and offsets land straight in the caller's (ideally pinned) buffers
-      LocatePart part;
-      part.hits = hits;
-      part.ext_cap = capacity;
-      part.ext_off = hit_off;  // marks the part as caller-owned even when capacity is 0
-      locate_on_replica(ix, *ix->reps[0], qbytes, qoff, 0, nq, flags, part);
-      *n_hits = part.n_hits;
-      if (part.n_hits > capacity)
-        fail(AWRY_ERR_CAPACITY, "hit buffer holds %llu entries, %llu needed", (unsigned long long)capacity,
-             (unsigned long long)part.n_hits);
-      return;
-    }
-    awry_hit* tmp = nullptr;
-    uint64_t n = 0;
-    int rc = awry_locate_batch(ix, qbytes, qoff, nq, flags, hit_off, &tmp, &n);
-    if (rc != AWRY_OK) fail(rc, "%s", g_err);
-    *n_hits = n;
-    if (n > capacity) {
-      free(tmp);
-      fail(AWRY_ERR_CAPACITY, "hit buffer holds %llu entries, %llu needed", (unsigned long long)capacity,
-           (unsigned long long)n);
-    }
-    if (n) memcpy(hits, tmp, n * sizeof(awry_hit));
-    free(tmp);
+    locate_into_impl(ix, ascii_source(qbytes, qoff), nq, flags, hit_off, hits, capacity, n_hits);
+  });
+}
+
+int awry_locate_batch_packed2(const awry_index* ix, const uint8_t* crumbs, const uint64_t* qoff, uint64_t nq,
+                              const uint64_t* exceptions, uint64_t n_exc, uint32_t flags, uint64_t* hit_off,
+                              awry_hit* hits, uint64_t capacity, uint64_t* n_hits) {
+  return guarded([&] {
+    need(ix);
+    if (!hit_off || !n_hits || (!hits && capacity)) fail(AWRY_ERR_INVALID_ARG, "null argument");
+    *n_hits = 0;
+    hit_off[0] = 0;
+    if (nq == 0) return;
+    locate_into_impl(ix, packed2_source(ix, crumbs, qoff, nq, exceptions, n_exc), nq, flags, hit_off, hits, capacity, n_hits);
   });
 }
 
@@ -784,12 +984,14 @@ int awry_count_device(const awry_index* ix, int replica, const uint8_t* d_qbytes
     uint32_t* d_defer = reinterpret_cast<uint32_t*>(d_qwords + words);
     {
       ProfScope p(2, r.device, st);
-      CU(launch_pack(ix->alphabet, d_qbytes, d_qoff, nq, d_qwords - 4 * (ends[0] >> sh), r.d_async_flag, st));
+      CU(launch_pack(ix->alphabet, d_qbytes, d_qoff, nq, d_qwords - 4 * (ends[0] >> sh), ends[0], ends[1], r.d_async_flag, st));
     }
     {
       ProfScope p(0, r.device, st);
       SearchVariant v = g_variant;
       v.avg_len = uint32_t(std::min<uint64_t>((ends[1] - ends[0]) / nq, 1u << 30));
+      v.b_lo = ends[0];
+      v.b_hi = ends[1];
       CU(launch_search(r.view, d_qwords - 4 * (ends[0] >> sh), d_qoff, nq, OUT_COUNT_U64, d_counts, d_defer, v, r.sm_count, st));
     }
     CU(cudaFreeAsync(d_qwords, st));
@@ -823,12 +1025,14 @@ int awry_locate_device(const awry_index* ix, int replica, const uint8_t* d_qbyte
       Workspace::grow_dev(ws->d_defer, ws->d_defer_cap, size_t(nq) + 2);
       {
         ProfScope p(2, r.device, st);
-        CU(launch_pack(ix->alphabet, d_qbytes, d_qoff, nq, ws->d_qwords - 4 * (ends[0] >> sh), r.d_async_flag, st));
+        CU(launch_pack(ix->alphabet, d_qbytes, d_qoff, nq, ws->d_qwords - 4 * (ends[0] >> sh), ends[0], ends[1], r.d_async_flag, st));
       }
       {
         ProfScope p(0, r.device, st);
         SearchVariant v = g_variant;
         v.avg_len = uint32_t(std::min<uint64_t>((ends[1] - ends[0]) / nq, 1u << 30));
+        v.b_lo = ends[0];
+        v.b_hi = ends[1];
         CU(launch_search(r.view, ws->d_qwords - 4 * (ends[0] >> sh), d_qoff, nq, OUT_SP_CNT_U32, ws->d_out, ws->d_defer, v, r.sm_count, st));
       }
       uint64_t n = 0;
@@ -866,8 +1070,7 @@ int awry_device_check(const awry_index* ix, int replica, void* cuda_stream) {
     CU(cudaMemcpyAsync(&flag, r.d_async_flag, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemsetAsync(r.d_async_flag, 0xff, 8, st));
     CU(cudaStreamSynchronize(st));
-    if (flag != ~0ull)
-      fail(AWRY_ERR_INVALID_QUERY, "query %llu of a device batch is empty or contains a sentinel", flag);
+    if (flag != ~0ull) fail_bad_query(flag, 0);
   });
 }
 
@@ -890,6 +1093,15 @@ int awry_host_pack_dna(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t* e
       for (size_t i = 0; i < exc.size() && i < exc_cap; i++) exceptions[i] = exc[i];
   });
 }
+
+int awry_set_host_threads(int n) {
+  return guarded([&] {
+    if (n < 0 || n > 256) fail(AWRY_ERR_INVALID_ARG, "host thread count must be 0 (default) .. 256");
+    host_set_threads(n);
+  });
+}
+
+int awry_host_threads(void) { return host_pool_threads(); }
 
 int awry_set_locate_variant(int variant) {
   return guarded([&] {

@@ -165,6 +165,11 @@ struct Workspace {
   unsigned long long* d_flag = nullptr;
   uint64_t* d_exc = nullptr;
   size_t d_exc_cap = 0;
+  // sync-free locate pass 2: [0] = this chunk's hit base, [1] = the call's running hit total (first slot's)
+  unsigned long long* d_base = nullptr;
+  cudaEvent_t ev_adv = nullptr;  // recorded after the chunk's advance_hit_base_kernel
+  uint64_t* d_off_out = nullptr;  // rebased CSR offsets of the chunk, on their way to the caller
+  size_t d_off_out_cap = 0;
   // reads-file front-end scratch, kept across calls (pinned allocations cost ~0.4 ms per MiB)
   struct ReadsScratch {
     uint64_t chunk = 0, carry = 0;
@@ -228,6 +233,8 @@ struct Workspace {
     CU(cudaHostAlloc(reinterpret_cast<void**>(&h_flag), 2 * sizeof(unsigned long long), cudaHostAllocDefault));
     h_total = h_flag + 1;
     CU(cudaMalloc(reinterpret_cast<void**>(&d_flag), sizeof(unsigned long long)));
+    CU(cudaMalloc(reinterpret_cast<void**>(&d_base), 2 * sizeof(unsigned long long)));
+    CU(cudaEventCreateWithFlags(&ev_adv, cudaEventDisableTiming));
   }
   void destroy() {
     cudaSetDevice(device);
@@ -246,6 +253,9 @@ struct Workspace {
     cudaFree(d_hit_off);
     cudaFree(d_temp);
     cudaFree(d_flag);
+    cudaFree(d_base);
+    cudaFree(d_off_out);
+    if (ev_adv) cudaEventDestroy(ev_adv);
     rs.release();
     if (ev_a) cudaEventDestroy(ev_a);
     if (ev_b) cudaEventDestroy(ev_b);
@@ -292,6 +302,56 @@ struct Replica {
   }
 };
 
+// Pack on the host or send ASCII?  Packing wins when the host cores pack faster than the PCIe link moves
+// bytes (16 threads: 121 GB/s vs 52 GB/s for one GPU) and loses when few cores feed many GPUs over shared
+// uplinks.  Both rates are MEASURED per index handle and smoothed across its calls: the host clock around the
+// packer (H), CUDA events around the copy of a raw first chunk, when nothing else of that replica is in
+// flight (P).  H > 1.15 P: pack everything (one GPU, 16 threads: mixing raw chunks in was measured and is
+// worse there -- a 128-MiB raw copy holds the copy engine for 2.6 ms and starves the search kernel,
+// profiles/r01_s19_e2e_pack_share.log).  Otherwise host and link are used together: a share
+// f = H / (P + 0.75 H) of the bytes is packed.  In a multi-replica call every replica thread measures its
+// own share of the pool and of the host's uplinks, which is what it has to balance.
+// AWRY_B200_PACK_SHARE=<0..1> pins the packed share of the bytes instead (experiments).
+struct PackBalance {
+  std::mutex mu;
+  double host_rate = 0, link_rate = 0;  // bytes/s, 0 = not measured yet
+  double fixed_share = -1;
+  uint64_t calls = 0;
+  bool mixed = true;  // AWRY_B200_PACK_MIXED=0: all-or-nothing
+  PackBalance() {
+    if (const char* e = getenv("AWRY_B200_PACK_SHARE")) fixed_share = std::min(1.0, std::max(0.0, atof(e)));
+    if (const char* e = getenv("AWRY_B200_PACK_MIXED")) mixed = e[0] != '0';
+  }
+  void note_host(double bytes, double seconds) {
+    if (seconds <= 0 || bytes < (8 << 20)) return;
+    std::lock_guard<std::mutex> lk(mu);
+    double r = bytes / seconds;
+    host_rate = host_rate > 0 ? 0.7 * host_rate + 0.3 * r : r;
+  }
+  void note_link(double bytes, double seconds) {
+    if (seconds <= 0 || bytes < (8 << 20)) return;
+    std::lock_guard<std::mutex> lk(mu);
+    double r = bytes / seconds;
+    link_rate = link_rate > 0 ? 0.7 * link_rate + 0.3 * r : r;
+  }
+  // per call: the packed share of the bytes and whether chunk 0 / chunk 1 serve as probes
+  struct Plan {
+    double share;
+    bool probe_link, probe_host;
+  };
+  Plan plan() {
+    std::lock_guard<std::mutex> lk(mu);
+    if (fixed_share >= 0) return Plan{fixed_share, false, false};
+    const bool refresh = calls++ % 32 == 0;
+    if (host_rate <= 0 || link_rate <= 0) return Plan{1.0, true, true};
+    if (host_rate > 1.15 * link_rate) return Plan{1.0, refresh, false};
+    // the host is not clearly faster than the link: use both (see the share formula above)
+    double f = mixed ? host_rate / (link_rate + 0.75 * host_rate) : 0.0;
+    if (f < 0.15) f = 0.0;
+    return Plan{f, true, f == 0.0 && refresh};
+  }
+};
+
 }  // namespace host
 }  // namespace awry
 
@@ -306,6 +366,9 @@ struct awry_index {
   std::vector<uint64_t> seq_starts;
   std::vector<std::string> headers;
   std::vector<std::unique_ptr<awry::host::Replica>> reps;
+  // per replica: host-pack vs raw-copy balance (measured rates; the only mutable state of a handle)
+  mutable std::vector<std::unique_ptr<awry::host::PackBalance>> balance;
+  awry::host::PackBalance& balance_of(size_t replica) const { return *balance[replica]; }
 };
 
 namespace awry {

@@ -14,6 +14,8 @@
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <memory>
 #include <mutex>
 #include <thread>
 
@@ -22,70 +24,125 @@ namespace awry {
 namespace {
 
 // ---------------------------------------------------------------- thread pool
+// A shared work-queue pool.  A parallel region is a JOB: `n_blocks` independent blocks handed out through an
+// atomic counter.  Several jobs may be open at once -- in a multi-replica call every replica's host thread
+// packs its own chunks (/root/reference/src/fm_index.rs:455-460 is ONE call over ONE batch, whatever the
+// number of GPUs behind it) -- and every worker serves the oldest job that still has blocks, so the
+// packing capacity of the whole host follows the demand instead of being split per caller.  The caller
+// works on its own job too and returns when all its blocks are done.  The pool grows on demand up to the
+// thread cap (host_set_threads); an exception thrown by a block is caught in the worker, remembered in
+// the job and rethrown from run() in the caller's thread, so nothing unwinds out of a pool thread.
 class Pool {
  public:
-  explicit Pool(int n) : n_(n) {
-    for (int t = 1; t < n_; t++) workers_.emplace_back([this, t] { loop(t); });
-  }
+  struct Job {
+    const std::function<void(size_t)>* fn = nullptr;
+    size_t n_blocks = 0;
+    std::atomic<size_t> next{0};
+    std::atomic<size_t> done{0};
+    std::atomic<bool> failed{false};
+    std::exception_ptr error;
+    std::mutex err_mu;
+  };
+
   ~Pool() {
     {
       std::lock_guard<std::mutex> lk(mu_);
       quit_ = true;
-      gen_++;
     }
     cv_.notify_all();
     for (auto& w : workers_) w.join();
   }
-  int size() const { return n_; }
-  void run(const std::function<void(int, int)>& fn) {
-    std::lock_guard<std::mutex> serial(run_mu_);  // one parallel region at a time
+  int cap() {
+    std::lock_guard<std::mutex> lk(mu_);
+    return cap_;
+  }
+  void set_cap(int n) {
+    std::lock_guard<std::mutex> lk(mu_);
+    cap_ = std::max(1, std::min(n, 256));
+  }
+  // runs fn(block) for block in [0, n_blocks) on up to `max_threads` threads (0 = the pool's cap)
+  void run(size_t n_blocks, const std::function<void(size_t)>& fn, int max_threads = 0) {
+    if (n_blocks == 0) return;
+    auto job = std::make_shared<Job>();
+    job->fn = &fn;
+    job->n_blocks = n_blocks;
+    int want;
     {
       std::lock_guard<std::mutex> lk(mu_);
-      fn_ = &fn;
-      pending_ = n_ - 1;
-      gen_++;
+      want = max_threads > 0 ? std::min(max_threads, cap_) : cap_;
+      want = int(std::min<size_t>(size_t(want), n_blocks));
+      // the caller is one of the threads; workers are shared between the open jobs
+      while (int(workers_.size()) + 1 < want) {
+        try {
+          workers_.emplace_back([this] { loop(); });
+        } catch (...) {
+          break;  // cannot spawn: run with what there is
+        }
+      }
+      if (want > 1) jobs_.push_back(job);
     }
-    cv_.notify_all();
-    fn(0, n_);
-    std::unique_lock<std::mutex> lk(mu_);
-    done_cv_.wait(lk, [this] { return pending_ == 0; });
-    fn_ = nullptr;
+    if (want > 1) cv_.notify_all();
+    work(*job);
+    if (want > 1) {
+      std::unique_lock<std::mutex> lk(mu_);
+      done_cv_.wait(lk, [&] { return job->done.load(std::memory_order_acquire) == job->n_blocks; });
+      jobs_.erase(std::remove(jobs_.begin(), jobs_.end(), job), jobs_.end());
+    }
+    if (job->error) std::rethrow_exception(job->error);
   }
 
  private:
-  void loop(int t) {
-    uint64_t seen = 0;
+  // takes blocks of `job` until none are left; returns after the last one it ran
+  void work(Job& job) {
     for (;;) {
-      const std::function<void(int, int)>* fn;
-      {
-        std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return gen_ != seen; });
-        seen = gen_;
-        if (quit_) return;
-        fn = fn_;
+      size_t b = job.next.fetch_add(1, std::memory_order_relaxed);
+      if (b >= job.n_blocks) return;
+      if (!job.failed.load(std::memory_order_relaxed)) {
+        try {
+          (*job.fn)(b);
+        } catch (...) {
+          std::lock_guard<std::mutex> lk(job.err_mu);
+          if (!job.error) job.error = std::current_exception();
+          job.failed.store(true, std::memory_order_relaxed);
+        }
       }
-      (*fn)(t, n_);
-      {
-        std::lock_guard<std::mutex> lk(mu_);
-        pending_--;
+      if (job.done.fetch_add(1, std::memory_order_acq_rel) + 1 == job.n_blocks) {
+        std::lock_guard<std::mutex> lk(mu_);  // pairs with the waiter's predicate check
+        done_cv_.notify_all();
       }
-      done_cv_.notify_one();
     }
   }
-  int n_;
+  void loop() {
+    for (;;) {
+      std::shared_ptr<Job> job;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] {
+          if (quit_) return true;
+          for (auto& j : jobs_)
+            if (j->next.load(std::memory_order_relaxed) < j->n_blocks) {
+              job = j;
+              return true;
+            }
+          return false;
+        });
+        if (quit_) return;
+      }
+      work(*job);
+    }
+  }
   std::vector<std::thread> workers_;
-  std::mutex mu_, run_mu_;
+  std::vector<std::shared_ptr<Job>> jobs_;
+  std::mutex mu_;
   std::condition_variable cv_, done_cv_;
-  const std::function<void(int, int)>* fn_ = nullptr;
-  int pending_ = 0;
-  uint64_t gen_ = 0;
+  int cap_ = 1;
   bool quit_ = false;
 };
 
 int default_threads() {
   if (const char* e = getenv("AWRY_B200_HOST_THREADS")) {
     int v = atoi(e);
-    if (v >= 1) return std::min(v, 64);
+    if (v >= 1) return std::min(v, 256);
   }
   int hw = int(std::max(1u, std::thread::hardware_concurrency()));
   int local = 1;
@@ -94,8 +151,12 @@ int default_threads() {
 }
 
 Pool& pool() {
-  static Pool p(default_threads());
-  return p;
+  static Pool* p = [] {
+    auto* q = new Pool();  // never destroyed: worker threads must not be joined from a static destructor
+    q->set_cap(default_threads());
+    return q;
+  }();
+  return *p;
 }
 
 // ---------------------------------------------------------------- packers
@@ -231,48 +292,51 @@ Level simd_level() {
 }  // namespace
 
 bool host_pack_supported() { return __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2"); }
-int host_pool_threads() { return pool().size(); }
-void host_parallel(const std::function<void(int, int)>& fn) { pool().run(fn); }
+int host_pool_threads() { return pool().cap(); }
+void host_set_threads(int n) { pool().set_cap(n <= 0 ? default_threads() : n); }
+int host_default_threads() { return default_threads(); }
+void host_parallel_blocks(size_t n_blocks, const std::function<void(size_t)>& fn, int max_threads) {
+  pool().run(n_blocks, fn, max_threads);
+}
 
-bool host_pack_dna(const uint8_t* src, size_t n, uint8_t* dst, std::vector<uint64_t>& exceptions, size_t max_exc_div) {
+bool host_pack_dna(const uint8_t* src, size_t n, uint8_t* dst, std::vector<uint64_t>& exceptions, size_t max_exc_div,
+                   int max_threads) {
   exceptions.clear();
   if (n == 0) return true;
   const Level lvl = simd_level();
   const size_t G = 64;  // granule: both SIMD widths and whole output bytes
   const size_t n_gran = n / G;
-  const int nt_pool = pool().size();
-  const int nt = int(std::max<size_t>(1, std::min<size_t>(size_t(nt_pool), n / (256u << 10) + 1)));
-  std::vector<std::vector<uint64_t>> exc(size_t(nt) + 1);
   // blocks of 256 KiB handed out dynamically: on a shared host the threads do not run at the same speed
   const size_t BLOCK = (256u << 10) / G;  // granules per block
-  std::atomic<size_t> next{0};
-  auto body = [&](int t, int) {
-    if (t >= nt) return;
-    for (;;) {
-      size_t g0 = next.fetch_add(BLOCK, std::memory_order_relaxed);
-      if (g0 >= n_gran) return;
-      size_t lo = g0 * G, hi = std::min(n_gran, g0 + BLOCK) * G;
-      if (lvl == AVX2)
-        pack_avx2(src, lo, hi, dst, exc[size_t(t)]);
-      else if (lvl == AVX512)
-        pack_avx512(src, lo, hi, dst, exc[size_t(t)]);
-      else
-        pack_scalar(src, lo, hi, dst, exc[size_t(t)]);
-    }
+  const size_t n_blocks = (n_gran + BLOCK - 1) / BLOCK;
+  // exceptions are collected per block (blocks are independent jobs of the shared pool); once their number
+  // passes the cut-off the chunk will travel as ASCII anyway, so the lists stop growing
+  const size_t exc_limit = max_exc_div ? n / max_exc_div + 16 : ~size_t(0);
+  std::vector<std::vector<uint64_t>> exc(n_blocks + 1);
+  std::atomic<size_t> n_exc{0};
+  auto body = [&](size_t b) {
+    if (n_exc.load(std::memory_order_relaxed) > exc_limit) return;
+    const size_t g0 = b * BLOCK;
+    const size_t lo = g0 * G, hi = std::min(n_gran, g0 + BLOCK) * G;
+    std::vector<uint64_t>& e = exc[b];
+    if (lvl == AVX2)
+      pack_avx2(src, lo, hi, dst, e);
+    else if (lvl == AVX512)
+      pack_avx512(src, lo, hi, dst, e);
+    else
+      pack_scalar(src, lo, hi, dst, e);
+    if (!e.empty()) n_exc.fetch_add(e.size(), std::memory_order_relaxed);
   };
-  if (nt == 1)
-    body(0, 1);
-  else
-    pool().run(body);
+  pool().run(n_blocks, body, max_threads);
   if (n_gran * G < n) {  // tail
     memset(dst + (n_gran * G) / 4, 0, (n - n_gran * G + 3) / 4);
-    pack_scalar(src, n_gran * G, n, dst, exc[size_t(nt)]);
+    pack_scalar(src, n_gran * G, n, dst, exc[n_blocks]);
+    n_exc.fetch_add(exc[n_blocks].size(), std::memory_order_relaxed);
   }
-  size_t total = 0;
-  for (auto& e : exc) total += e.size();
-  if (max_exc_div && total > n / max_exc_div + 16) return false;
+  const size_t total = n_exc.load();
+  if (total > exc_limit) return false;
   exceptions.reserve(total);
-  for (auto& e : exc) exceptions.insert(exceptions.end(), e.begin(), e.end());
+  for (auto& e : exc) exceptions.insert(exceptions.end(), e.begin(), e.end());  // ascending by position
   return true;
 }
 

@@ -499,7 +499,7 @@ __device__ __forceinline__ uint64_t pack_word_bytes(const uint8_t* __restrict__ 
 template <int ALPHA>
 __global__ void __launch_bounds__(256)
     pack_kernel(const uint8_t* __restrict__ qbytes, const uint64_t* __restrict__ qoff, uint64_t nq,
-                uint64_t* __restrict__ qwords, unsigned long long* first_bad) {
+                uint64_t* __restrict__ qwords, uint64_t b_lo, uint64_t b_hi, unsigned long long* first_bad) {
   constexpr int SPW = ALPHA == 0 ? 16 : 8;
   constexpr int LOG_SPW = ALPHA == 0 ? 4 : 3;
   constexpr int UNIT_SHIFT = ALPHA == 0 ? 6 : 5;  // symbols per 4-word (32-B) unit
@@ -510,8 +510,14 @@ __global__ void __launch_bounds__(256)
   const uint64_t ngroups = (gridDim.x * uint64_t(blockDim.x)) >> 3;
   for (uint64_t q = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 3; q < nq; q += ngroups) {
     const uint64_t o0 = qoff[q], o1 = qoff[q + 1];
-    if (o1 <= o0 || o1 - o0 >= (1ull << 32)) {  // empty (or absurd) query
-      if (sub == 0) atomicMin(first_bad, (unsigned long long)q);
+    // offsets are caller data: a query outside the batch's byte range [b_lo, b_hi] (non-monotone offsets) is
+    // refused before any load or store -- both buffers are sized from that range
+    if (o0 < b_lo || o1 > b_hi || o1 < o0 || o1 - o0 >= (1ull << 32)) {
+      if (sub == 0) atomicMin(first_bad, bad_query_code(q, BAD_OFFSETS));
+      continue;
+    }
+    if (o1 == o0) {  // empty query
+      if (sub == 0) atomicMin(first_bad, bad_query_code(q, BAD_QUERY));
       continue;
     }
     const uint32_t len = uint32_t(o1 - o0);
@@ -561,19 +567,20 @@ __global__ void __launch_bounds__(256)
       if (!done) word = pack_word_bytes<ALPHA>(src, len, first, lut, bad);
       dst[wi] = word;
     }
-    if (bad) atomicMin(first_bad, (unsigned long long)q);
+    if (bad) atomicMin(first_bad, bad_query_code(q, BAD_QUERY));
   }
 }
 
 cudaError_t launch_pack(int alphabet, const uint8_t* d_qbytes, const uint64_t* d_qoff, uint64_t nq,
-                        uint64_t* d_qwords, unsigned long long* d_first_bad, cudaStream_t s) {
+                        uint64_t* d_qwords, uint64_t b_lo, uint64_t b_hi, unsigned long long* d_first_bad,
+                        cudaStream_t s) {
   if (nq == 0) return cudaSuccess;
   uint64_t threads = nq * 8;
   unsigned grid = unsigned(std::min<uint64_t>((threads + 255) / 256, 148 * 64));
   if (alphabet == 0)
-    pack_kernel<0><<<grid, 256, 0, s>>>(d_qbytes, d_qoff, nq, d_qwords, d_first_bad);
+    pack_kernel<0><<<grid, 256, 0, s>>>(d_qbytes, d_qoff, nq, d_qwords, b_lo, b_hi, d_first_bad);
   else
-    pack_kernel<1><<<grid, 256, 0, s>>>(d_qbytes, d_qoff, nq, d_qwords, d_first_bad);
+    pack_kernel<1><<<grid, 256, 0, s>>>(d_qbytes, d_qoff, nq, d_qwords, b_lo, b_hi, d_first_bad);
   COUNT_LAUNCH();
   return cudaGetLastError();
 }
@@ -595,13 +602,17 @@ __device__ __forceinline__ uint32_t spread8_crumbs(uint32_t v) {  // 8 crumbs (1
 
 __global__ void __launch_bounds__(256)
     pack2_kernel(const uint32_t* __restrict__ crumbs, uint64_t base, const uint64_t* __restrict__ qoff, uint64_t nq,
-                 uint64_t* __restrict__ qwords, unsigned long long* first_bad) {
+                 uint64_t* __restrict__ qwords, uint64_t b_lo, uint64_t b_hi, unsigned long long* first_bad) {
   const uint32_t sub = threadIdx.x & 7;
   const uint64_t ngroups = (gridDim.x * uint64_t(blockDim.x)) >> 3;
   for (uint64_t q = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 3; q < nq; q += ngroups) {
     const uint64_t o0 = qoff[q], o1 = qoff[q + 1];
-    if (o1 <= o0 || o1 - o0 >= (1ull << 32)) {
-      if (sub == 0) atomicMin(first_bad, (unsigned long long)q);
+    if (o0 < b_lo || o1 > b_hi || o1 < o0 || o1 - o0 >= (1ull << 32)) {  // see pack_kernel
+      if (sub == 0) atomicMin(first_bad, bad_query_code(q, BAD_OFFSETS));
+      continue;
+    }
+    if (o1 == o0) {
+      if (sub == 0) atomicMin(first_bad, bad_query_code(q, BAD_QUERY));
       continue;
     }
     const uint32_t len = uint32_t(o1 - o0);
@@ -624,13 +635,13 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// exceptions: (chunk-relative byte position << 8) | ASCII byte, for bytes outside ACGTacgt
-__global__ void patch_exceptions_kernel(const uint64_t* __restrict__ exc, uint64_t n_exc, uint64_t base,
+// exceptions: ((byte position - exc_base) << 8) | ASCII byte, for bytes outside ACGTacgt
+__global__ void patch_exceptions_kernel(const uint64_t* __restrict__ exc, uint64_t n_exc, uint64_t exc_base,
                                         const uint64_t* __restrict__ qoff, uint64_t nq, uint64_t* __restrict__ qwords,
-                                        unsigned long long* first_bad) {
+                                        uint64_t b_lo, uint64_t b_hi, unsigned long long* first_bad) {
   uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
   if (i >= n_exc) return;
-  const uint64_t pos = base + (exc[i] >> 8);
+  const uint64_t pos = exc_base + (exc[i] >> 8);
   const uint32_t d = c_ascii_to_dsym[0][exc[i] & 0xff];
   uint64_t lo = 0, hi = nq;  // last q with qoff[q] <= pos
   while (hi - lo > 1) {
@@ -642,8 +653,9 @@ __global__ void patch_exceptions_kernel(const uint64_t* __restrict__ exc, uint64
   }
   const uint64_t q = lo, o0 = qoff[q], o1 = qoff[q + 1];
   if (pos < o0 || pos >= o1) return;  // not inside any query of this chunk
+  if (o0 < b_lo || o1 > b_hi || o1 - o0 >= (1ull << 32)) return;  // refused by pack2_kernel: its words do not exist
   if (d == uint32_t(DNA_SENTINEL)) {
-    atomicMin(first_bad, (unsigned long long)q);
+    atomicMin(first_bad, bad_query_code(q, BAD_QUERY));
     return;
   }
   const uint32_t si = uint32_t(o1 - 1 - pos);  // search-order index
@@ -654,16 +666,17 @@ __global__ void patch_exceptions_kernel(const uint64_t* __restrict__ exc, uint64
 }
 
 cudaError_t launch_pack2(const uint32_t* d_crumbs, uint64_t base, const uint64_t* d_qoff, uint64_t nq, uint64_t* d_qwords,
-                         const uint64_t* d_exc, uint64_t n_exc, unsigned long long* d_first_bad, cudaStream_t s) {
+                         const uint64_t* d_exc, uint64_t n_exc, uint64_t exc_base, uint64_t b_lo, uint64_t b_hi,
+                         unsigned long long* d_first_bad, cudaStream_t s) {
   if (nq == 0) return cudaSuccess;
   uint64_t threads = nq * 8;
   unsigned grid = unsigned(std::min<uint64_t>((threads + 255) / 256, 148 * 64));
-  pack2_kernel<<<grid, 256, 0, s>>>(d_crumbs, base, d_qoff, nq, d_qwords, d_first_bad);
+  pack2_kernel<<<grid, 256, 0, s>>>(d_crumbs, base, d_qoff, nq, d_qwords, b_lo, b_hi, d_first_bad);
   COUNT_LAUNCH();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || n_exc == 0) return e;
-  patch_exceptions_kernel<<<unsigned((n_exc + 255) / 256), 256, 0, s>>>(d_exc, n_exc, base, d_qoff, nq, d_qwords,
-                                                                        d_first_bad);
+  patch_exceptions_kernel<<<unsigned((n_exc + 255) / 256), 256, 0, s>>>(d_exc, n_exc, exc_base, d_qoff, nq, d_qwords,
+                                                                        b_lo, b_hi, d_first_bad);
   COUNT_LAUNCH();
   return cudaGetLastError();
 }
@@ -680,6 +693,16 @@ __device__ __forceinline__ void store_result(void* out, uint64_t q, uint32_t sp,
   } else {
     reinterpret_cast<uint2*>(out)[q] = empty ? make_uint2(1u, 0u) : make_uint2(sp, ep - sp + 1u);
   }
+}
+
+// Length of query (o0, o1) of a batch whose bytes span [b.lo, b.hi]; 0 for a query the prepass refused
+// (offsets outside the range: its packed words were never written) -- it is stored as an empty result and the
+// call fails with the prepass's error.
+struct ByteRange {
+  uint64_t lo, hi;
+};
+__device__ __forceinline__ uint32_t checked_len(uint64_t o0, uint64_t o1, const ByteRange& b) {
+  return (o0 < b.lo || o1 > b.hi || o1 < o0 || o1 - o0 >= (1ull << 32)) ? 0u : uint32_t(o1 - o0);
 }
 
 // Packed-symbol reader: current word in a register, the next one prefetched.  Word positions are
@@ -763,13 +786,13 @@ template <int ALPHA, int MODE, bool LIST>
 __global__ void __launch_bounds__(256) search_scalar_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
                                                             const uint64_t* __restrict__ qoff, uint64_t nq,
                                                             void* __restrict__ out,
-                                                            const uint32_t* __restrict__ defer) {
+                                                            const uint32_t* __restrict__ defer, ByteRange br) {
   uint64_t stride = gridDim.x * uint64_t(blockDim.x);
   uint64_t n = LIST ? uint64_t(defer[0]) : nq;
   for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += stride) {
     uint64_t q = LIST ? uint64_t(defer[1 + i]) : i;
     uint64_t o0 = qoff[q];
-    uint32_t len = uint32_t(qoff[q + 1] - o0);
+    uint32_t len = checked_len(o0, qoff[q + 1], br);
     uint32_t sp = 1, ep = 0;
     if (len != 0) {
       QueryStream<ALPHA> qs;
@@ -800,7 +823,7 @@ __global__ void __launch_bounds__(256) search_scalar_kernel(IndexView ix, const 
 template <int LANES, int MODE, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB)
     search_dna_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
-                      const uint64_t* __restrict__ qoff, uint64_t nq, void* __restrict__ out) {
+                      const uint64_t* __restrict__ qoff, uint64_t nq, void* __restrict__ out, ByteRange br) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t sub = lane % LANES;
   const uint32_t gmask = LANES == 1 ? (1u << lane) : (((1u << LANES) - 1u) << (lane - sub));
@@ -824,7 +847,7 @@ __global__ void __launch_bounds__(TPB, MINB)
       q = (q + G < q) ? 0xffffffffu : q + G;
       have = true;
       uint64_t o0 = qoff[cur];
-      uint32_t len = uint32_t(qoff[cur + 1] - o0);
+      uint32_t len = checked_len(o0, qoff[cur + 1], br);
       sp = 1;
       ep = 0;
       left = 0;
@@ -866,7 +889,7 @@ __global__ void __launch_bounds__(TPB, MINB)
 template <int LANES, int MODE, int MINB>
 static cudaError_t launch_search_dna_b(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
                                        uint64_t nq, void* d_out, int sm_count, int force_per_sm,
-                                       cudaStream_t s) {
+                                       cudaStream_t s, ByteRange br) {
   constexpr int TPB = 256;
   auto kern = search_dna_kernel<LANES, MODE, TPB, MINB>;
   int per_sm = 0;
@@ -877,7 +900,7 @@ static cudaError_t launch_search_dna_b(const IndexView& ix, const uint64_t* d_qw
   uint64_t max_blocks = uint64_t(sm_count) * uint64_t(per_sm);
   uint64_t need_blocks = (nq * LANES + TPB - 1) / TPB;
   unsigned grid = unsigned(std::max<uint64_t>(1, std::min(max_blocks, need_blocks)));
-  kern<<<grid, TPB, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out);
+  kern<<<grid, TPB, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out, br);
   COUNT_LAUNCH();
   return cudaGetLastError();
 }
@@ -889,10 +912,10 @@ static cudaError_t launch_search_dna(const IndexView& ix, const uint64_t* d_qwor
                                      cudaStream_t s) {
   if (nq >= (1ull << 32)) return cudaErrorInvalidValue;
   switch (v.blocks_per_sm) {
-    case 6: return launch_search_dna_b<LANES, MODE, 6>(ix, d_qwords, d_qoff, nq, d_out, sm_count, 0, s);
-    case 8: return launch_search_dna_b<LANES, MODE, 8>(ix, d_qwords, d_qoff, nq, d_out, sm_count, 0, s);
+    case 6: return launch_search_dna_b<LANES, MODE, 6>(ix, d_qwords, d_qoff, nq, d_out, sm_count, 0, s, ByteRange{v.b_lo, v.b_hi});
+    case 8: return launch_search_dna_b<LANES, MODE, 8>(ix, d_qwords, d_qoff, nq, d_out, sm_count, 0, s, ByteRange{v.b_lo, v.b_hi});
     default:  // 0 / 4: no register cap (4 resident blocks); 1..3 run the same kernel on a smaller grid
-      return launch_search_dna_b<LANES, MODE, 4>(ix, d_qwords, d_qoff, nq, d_out, sm_count, v.blocks_per_sm, s);
+      return launch_search_dna_b<LANES, MODE, 4>(ix, d_qwords, d_qoff, nq, d_out, sm_count, v.blocks_per_sm, s, ByteRange{v.b_lo, v.b_hi});
   }
 }
 
@@ -994,7 +1017,7 @@ template <int MODE, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB)
     search_dna_pair_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
                            const uint64_t* __restrict__ qoff, uint64_t nq, void* __restrict__ out,
-                           uint32_t* __restrict__ defer, uint32_t ticket_sz) {
+                           uint32_t* __restrict__ defer, uint32_t ticket_sz, ByteRange br) {
   constexpr int LANES = 4;
   constexpr uint32_t NONE = 0xffffffffu, FULL = 0xffffffffu;
   // The group's packed query is staged in shared memory (a 16-word ring = 256 symbols, refilled
@@ -1061,7 +1084,7 @@ __global__ void __launch_bounds__(TPB, MINB)
         cur = next_q;
         uint64_t ov = qoff[cur + (sub & 1)];  // lanes 0/1 fetch both ends with one request
         uint64_t o0 = __shfl_sync(gmask, ov, gbase), o1 = __shfl_sync(gmask, ov, gbase + 1);
-        len = uint32_t(o1 - o0);
+        len = checked_len(o0, o1, br);
         sp = 1;
         ep = 0;
         if (len != 0) {
@@ -1181,7 +1204,7 @@ __global__ void __launch_bounds__(TPB, MINB)
 template <int MODE, int MINB>
 static cudaError_t launch_search_pair_b(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
                                         uint64_t nq, void* d_out, uint32_t* d_defer, int force_per_sm,
-                                        int sm_count, cudaStream_t s, uint32_t avg_len) {
+                                        int sm_count, cudaStream_t s, uint32_t avg_len, ByteRange br) {
   constexpr int TPB = 256;
   auto kern = search_dna_pair_kernel<MODE, TPB, MINB>;
   int per_sm = 0;
@@ -1204,11 +1227,11 @@ static cudaError_t launch_search_pair_b(const IndexView& ix, const uint64_t* d_q
   uint32_t per_group = avg_len == 0 ? 2u : std::min(8u, std::max(1u, 200u / avg_len));
   per_group = ticket_cap(per_group, nq, uint64_t(grid) * (TPB / 4), avg_len);
   const uint32_t ticket_sz = ticket_env ? ticket_env : 8u * per_group;
-  e = launch_with_table_window(kern, grid, TPB, s, ix, ix, d_qwords, d_qoff, nq, d_out, d_defer, ticket_sz);
+  e = launch_with_table_window(kern, grid, TPB, s, ix, ix, d_qwords, d_qoff, nq, d_out, d_defer, ticket_sz, br);
   COUNT_LAUNCH();
   if (e != cudaSuccess) return e;
   // queries with ambiguity symbols: scalar kernel over the deferred list (empty for clean batches)
-  search_scalar_kernel<0, MODE, true><<<unsigned(sm_count) * 2, 256, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out, d_defer);
+  search_scalar_kernel<0, MODE, true><<<unsigned(sm_count) * 2, 256, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out, d_defer, br);
   COUNT_LAUNCH();
   return cudaGetLastError();
 }
@@ -1223,14 +1246,14 @@ static cudaError_t launch_search_pair(const IndexView& ix, const uint64_t* d_qwo
   e = cudaMemsetAsync(d_defer + nq + 1, 0, 4, s);                     // ticket counter
   if (e != cudaSuccess) return e;
   switch (v.blocks_per_sm) {
-    case 4: return launch_search_pair_b<MODE, 4>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len);
+    case 4: return launch_search_pair_b<MODE, 4>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, ByteRange{v.b_lo, v.b_hi});
     // 8 x 256 threads/SM (32 registers) is fastest for an isolated launch (16.2 vs 16.6-17.0 ms), 6 x 256
     // (40 registers) for launches back to back, where the part sits at its power cap (18.1 vs 18.7 ms,
     // profiles/r01_s31_sustained_ab.log): batches arrive back to back in production, so 6 is the default
-    case 8: return launch_search_pair_b<MODE, 8>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len);
+    case 8: return launch_search_pair_b<MODE, 8>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, ByteRange{v.b_lo, v.b_hi});
     case 0:
-    case 6: return launch_search_pair_b<MODE, 6>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len);
-    default: return launch_search_pair_b<MODE, 4>(ix, d_qwords, d_qoff, nq, d_out, d_defer, v.blocks_per_sm, sm_count, s, v.avg_len);
+    case 6: return launch_search_pair_b<MODE, 6>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, ByteRange{v.b_lo, v.b_hi});
+    default: return launch_search_pair_b<MODE, 4>(ix, d_qwords, d_qoff, nq, d_out, d_defer, v.blocks_per_sm, sm_count, s, v.avg_len, ByteRange{v.b_lo, v.b_hi});
   }
 }
 
@@ -1242,7 +1265,7 @@ template <int MODE, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB)
     search_amino_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
                         const uint64_t* __restrict__ qoff, uint64_t nq, void* __restrict__ out,
-                        uint32_t* __restrict__ ticket, uint32_t ticket_sz) {
+                        uint32_t* __restrict__ ticket, uint32_t ticket_sz, ByteRange br) {
   constexpr int LANES = 4;
   constexpr uint32_t NONE = 0xffffffffu, FULL = 0xffffffffu;
   __shared__ uint64_t s_q[TPB / LANES][16];  // 128 symbols
@@ -1274,7 +1297,7 @@ __global__ void __launch_bounds__(TPB, MINB)
         cur = q++;
         uint64_t ov = qoff[cur + (sub & 1)];
         uint64_t o0 = __shfl_sync(gmask, ov, gbase), o1 = __shfl_sync(gmask, ov, gbase + 1);
-        len = uint32_t(o1 - o0);
+        len = checked_len(o0, o1, br);
         sp = 1;
         ep = 0;
         if (len != 0) {
@@ -1387,7 +1410,8 @@ static cudaError_t launch_search_amino(const IndexView& ix, const uint64_t* d_qw
   unsigned grid = unsigned(std::max<uint64_t>(1, std::min(max_blocks, need_blocks)));
   // (no batch-size cap here: the hand-out is per lane GROUP, and 12-residue peptides at 3.7 G/s with tickets
   // of 2 would be 1.8 G same-address atomics/s, far above what one counter retires)
-  e = launch_with_table_window(kern, grid, TPB, s, ix, ix, d_qwords, d_qoff, nq, d_out, d_ticket, ticket_size(v.avg_len));
+  e = launch_with_table_window(kern, grid, TPB, s, ix, ix, d_qwords, d_qoff, nq, d_out, d_ticket, ticket_size(v.avg_len),
+                               ByteRange{v.b_lo, v.b_hi});
   COUNT_LAUNCH();
   return e;
 }
@@ -1412,9 +1436,9 @@ static cudaError_t launch_search_mode(const IndexView& ix, const uint64_t* d_qwo
   uint64_t need_blocks = (nq + 255) / 256;
   unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * per_sm, need_blocks)));
   if (ix.alphabet == 0)
-    search_scalar_kernel<0, MODE, false><<<grid, 256, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out, nullptr);
+    search_scalar_kernel<0, MODE, false><<<grid, 256, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out, nullptr, ByteRange{v.b_lo, v.b_hi});
   else
-    search_scalar_kernel<1, MODE, false><<<grid, 256, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out, nullptr);
+    search_scalar_kernel<1, MODE, false><<<grid, 256, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out, nullptr, ByteRange{v.b_lo, v.b_hi});
   COUNT_LAUNCH();
   return cudaGetLastError();
 }

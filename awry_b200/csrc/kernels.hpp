@@ -25,6 +25,7 @@ struct SearchVariant {
   int tpb = 0;            // threads per block
   int blocks_per_sm = 0;  // 0 = occupancy-derived
   uint32_t avg_len = 0;   // mean query length of the batch (0 = unknown): sizes the tickets of the dynamic hand-out
+  uint64_t b_lo = 0, b_hi = ~0ull;  // byte range of the batch's queries: offsets outside it are refused (see launch_pack)
 };
 
 // Queries per ticket of the per-GROUP dynamic hand-out (amino kernel).  Small tickets shorten the tail (a
@@ -76,12 +77,21 @@ cudaError_t build_pair_index(const IndexView& ix, uint4* d_pair_blocks, uint32_t
 // unsampled suffix array (locate accelerator): SA[row] for every row, 4 B each, from the sampled one
 cudaError_t build_full_sa(const IndexView& ix, uint32_t* d_full, int sm_count, cudaStream_t s);
 
+// The prepass latches the first query it refuses in *d_first_bad (atomicMin, ~0 = none) as
+// bad_query_code(q, kind): an empty / sentinel-carrying query (the reference panics, fm_index.rs:406,
+// bwt.rs:127), or a query whose offsets leave the batch's byte range [b_lo, b_hi] (offsets not monotone):
+// such a query is never loaded or stored.
+enum BadKind : unsigned { BAD_QUERY = 0, BAD_OFFSETS = 1 };
+__host__ __device__ inline unsigned long long bad_query_code(uint64_t q, unsigned kind) { return (q << 1) | kind; }
 cudaError_t launch_pack(int alphabet, const uint8_t* d_qbytes, const uint64_t* d_qoff, uint64_t nq,
-                        uint64_t* d_qwords, unsigned long long* d_first_bad, cudaStream_t s);
-// nucleotide queries packed to 2 bits on the host (hostpack.hpp): crumbs of the chunk's bytes from
-// absolute query offset `base` on, plus the exception list for bytes outside ACGT
+                        uint64_t* d_qwords, uint64_t b_lo, uint64_t b_hi, unsigned long long* d_first_bad,
+                        cudaStream_t s);
+// nucleotide queries packed to 2 bits (by hostpack.hpp, or by the caller: awry_*_batch_packed2): crumbs of
+// the query bytes from absolute query offset `base` on, plus the exception list for bytes outside ACGT,
+// entries ((position - exc_base) << 8) | byte
 cudaError_t launch_pack2(const uint32_t* d_crumbs, uint64_t base, const uint64_t* d_qoff, uint64_t nq, uint64_t* d_qwords,
-                         const uint64_t* d_exc, uint64_t n_exc, unsigned long long* d_first_bad, cudaStream_t s);
+                         const uint64_t* d_exc, uint64_t n_exc, uint64_t exc_base, uint64_t b_lo, uint64_t b_hi,
+                         unsigned long long* d_first_bad, cudaStream_t s);
 // d_defer: nq + 2 u32 of scratch (count + list of queries the cooperative kernel hands to the scalar
 // one, then the ticket counter of the dynamic query hand-out)
 cudaError_t launch_search(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
@@ -97,6 +107,12 @@ cudaError_t scan_hit_offsets(const uint2* d_sp_cnt, uint64_t nq, uint64_t* d_hit
 cudaError_t launch_walk(const IndexView& ix, const uint2* d_sp_cnt, const uint64_t* d_hit_off,
                         uint64_t nq, uint64_t n_hits, uint64_t* d_hits_pairs, uint64_t* d_locs,
                         int sm_count, cudaStream_t s);
+// sync-free pass 2 on the unsampled array (see kernels_locate.cu): hits go straight to `out_hits` (device view
+// of the caller's pinned awry_hit buffer) at *d_running + local offset, rebased offsets to d_off_out
+cudaError_t launch_gather_direct(const IndexView& ix, const uint2* d_sp_cnt, const uint64_t* d_local_off, uint64_t nq,
+                                 unsigned long long* d_running, unsigned long long* d_chunk_base, void* out_hits,
+                                 uint64_t capacity, uint64_t* d_off_out, int sm_count, cudaEvent_t wait_before_advance,
+                                 cudaEvent_t record_after_advance, cudaStream_t s);
 cudaError_t sort_hit_segments(uint64_t* d_locs_in, uint64_t* d_locs_out, uint64_t n_hits,
                               uint64_t nq, const uint64_t* d_hit_off, void* d_temp,
                               size_t& temp_bytes, cudaStream_t s);

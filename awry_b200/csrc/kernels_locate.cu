@@ -404,6 +404,80 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- locate pass 2 without a host round trip (awry_locate_batch_into on the unsampled array) ----
+// The two-pass scheme needs the hit total of a chunk only to place its hits behind those of the chunks before
+// it.  That running total lives on the device: advance_hit_base_kernel (one thread, ordered after the same
+// kernel of the previous chunk by an event) hands the chunk its base and adds the chunk's total; the gather
+// then writes every hit at base + local offset STRAIGHT INTO THE CALLER'S PINNED BUFFER (`out` is the device
+// view of host memory: 16-byte stores, 512 contiguous bytes per warp for singleton queries) and the rebased
+// CSR offsets into a device array that one copy returns.  Hits past `capacity` are dropped; the total still
+// counts them (AWRY_ERR_CAPACITY).
+__global__ void advance_hit_base_kernel(const uint64_t* __restrict__ local_off, uint64_t nq,
+                                        unsigned long long* running, unsigned long long* chunk_base) {
+  const unsigned long long b = *running;
+  *chunk_base = b;
+  *running = b + local_off[nq];
+}
+
+__global__ void __launch_bounds__(256)
+    gather_sa_direct_kernel(IndexView ix, const uint2* __restrict__ sp_cnt, const uint64_t* __restrict__ local_off,
+                            uint64_t nq, const unsigned long long* __restrict__ chunk_base,
+                            ulonglong2* __restrict__ out, uint64_t capacity, uint64_t* __restrict__ off_out) {
+  const uint32_t* __restrict__ full = ix.full_sa;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5;
+  const uint64_t nwarps = (gridDim.x * uint64_t(blockDim.x)) >> 5;
+  const uint64_t hbase = *chunk_base;
+  for (uint64_t base = warp * 32; base < nq; base += nwarps * 32) {
+    uint64_t q = base + lane;
+    uint32_t sp = 0, cnt = 0;
+    uint64_t off = 0;
+    if (q < nq) {
+      uint2 r = sp_cnt[q];
+      sp = r.x;
+      cnt = r.y;
+      off = hbase + local_off[q];
+      off_out[q] = off;
+    }
+    uint32_t small = cnt < 8 ? cnt : 8;
+    for (uint32_t i = 0; i < small; i++) {
+      uint64_t pr[2];
+      map_location(ix, __ldg(full + sp + i), pr);
+      if (off + i < capacity) out[off + i] = make_ulonglong2(pr[0], pr[1]);
+    }
+    uint32_t big = __ballot_sync(0xffffffffu, cnt > 8);
+    while (big) {
+      int L = __ffs(big) - 1;
+      big &= big - 1;
+      uint32_t s = __shfl_sync(0xffffffffu, sp, L), c = __shfl_sync(0xffffffffu, cnt, L);
+      uint64_t o = __shfl_sync(0xffffffffu, off, L);
+      for (uint32_t i = 8 + lane; i < c; i += 32) {
+        uint64_t pr[2];
+        map_location(ix, __ldg(full + s + i), pr);
+        if (o + i < capacity) out[o + i] = make_ulonglong2(pr[0], pr[1]);
+      }
+    }
+  }
+}
+
+cudaError_t launch_gather_direct(const IndexView& ix, const uint2* d_sp_cnt, const uint64_t* d_local_off, uint64_t nq,
+                                 unsigned long long* d_running, unsigned long long* d_chunk_base, void* out_hits,
+                                 uint64_t capacity, uint64_t* d_off_out, int sm_count, cudaEvent_t wait_before_advance,
+                                 cudaEvent_t record_after_advance, cudaStream_t s) {
+  if (nq == 0 || ix.full_sa == nullptr) return cudaErrorInvalidValue;
+  cudaError_t e;
+  if (wait_before_advance && (e = cudaStreamWaitEvent(s, wait_before_advance, 0)) != cudaSuccess) return e;
+  advance_hit_base_kernel<<<1, 1, 0, s>>>(d_local_off, nq, d_running, d_chunk_base);
+  COUNT_LAUNCH();
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (record_after_advance && (e = cudaEventRecord(record_after_advance, s)) != cudaSuccess) return e;
+  unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (nq + 255) / 256)));
+  gather_sa_direct_kernel<<<grid, 256, 0, s>>>(ix, d_sp_cnt, d_local_off, nq, d_chunk_base,
+                                               static_cast<ulonglong2*>(out_hits), capacity, d_off_out);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_walk(const IndexView& ix, const uint2* d_sp_cnt, const uint64_t* d_hit_off,
                         uint64_t nq, uint64_t n_hits, uint64_t* d_hits_pairs, uint64_t* d_locs,
                         int sm_count, cudaStream_t s) {

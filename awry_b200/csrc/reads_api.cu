@@ -330,12 +330,15 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
         CU(cudaMemsetAsync(ws->d_flag, 0xff, 8, st));
         {
           ProfScope p(2, r.device, st);
-          CU(launch_pack(ix->alphabet, d_qbytes, d_qoff, nq, ws->d_qwords, ws->d_flag, st));
+          // offsets come from the library's own record splitter: [0, seq_bytes]
+          CU(launch_pack(ix->alphabet, d_qbytes, d_qoff, nq, ws->d_qwords, 0, plan.seq_bytes, ws->d_flag, st));
         }
         {
           ProfScope p(0, r.device, st);
           SearchVariant v = g_variant;
           v.avg_len = uint32_t(std::min<uint64_t>(plan.seq_bytes / nq, 1u << 30));
+          v.b_lo = 0;
+          v.b_hi = plan.seq_bytes;
           CU(launch_search(r.view, ws->d_qwords, d_qoff, nq, locate ? OUT_SP_CNT_U32 : OUT_COUNT_U64, ws->d_out, ws->d_defer,
                            v, r.sm_count, st));
         }
@@ -376,7 +379,7 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
           fail(AWRY_ERR_INVALID_QUERY,
                "read %llu of %s is empty or contains a sentinel ('$'/'#'): the reference panics on it "
                "(fm_index.rs:406, bwt.rs:127)",
-               (unsigned long long)(out.n_reads + *ws->h_flag), path);
+               (unsigned long long)(out.n_reads + (*ws->h_flag >> 1)), path);
         out.n_reads += nq;
         out.n_bases += plan.seq_bytes;
       }

@@ -124,7 +124,8 @@ EXPORTS = ["awry_read_sequence_file", "awry_index_build", "awry_build_index_file
            "awry_backstep", "awry_count_device", "awry_locate_device", "awry_device_free",
            "awry_device_check", "awry_profile_enable", "awry_profile_reset", "awry_profile_get",
            "awry_bench_random_gather", "awry_set_search_variant", "awry_set_locate_variant", "awry_set_host_pack",
-           "awry_host_pack_dna", "awry_last_error", "awry_version"]
+           "awry_host_pack_dna", "awry_last_error", "awry_version", "awry_count_batch_packed2",
+           "awry_locate_batch_packed2", "awry_set_host_threads", "awry_host_threads"]
 
 
 def native():
@@ -186,6 +187,9 @@ def native():
     L.awry_set_locate_variant.argtypes = [i32]
     L.awry_set_host_pack.argtypes = [i32]
     L.awry_host_pack_dna.argtypes = [vp, u64, vp, vp, u64, C.POINTER(u64)]
+    L.awry_count_batch_packed2.argtypes = [vp, vp, vp, u64, vp, u64, vp]
+    L.awry_locate_batch_packed2.argtypes = [vp, vp, vp, u64, vp, u64, C.c_uint32, vp, vp, u64, C.POINTER(u64)]
+    L.awry_set_host_threads.argtypes = [i32]
     _LIB = L
     return L
 
@@ -398,6 +402,36 @@ class FmIndex:
             raise err
         return n.value
 
+    # ---- pre-packed nucleotide reads (2 bits per base; see include/awry_b200.h) --------------
+    def count_prepacked(self, crumbs: np.ndarray, qoff: np.ndarray, exceptions: np.ndarray = None,
+                        out: np.ndarray = None) -> np.ndarray:
+        """parallel_count on reads the caller holds as 2-bit codes (the output of host_pack_dna)."""
+        crumbs = np.ascontiguousarray(crumbs, dtype=np.uint8)
+        qoff = np.ascontiguousarray(qoff, dtype=np.uint64)
+        exc = np.zeros(0, np.uint64) if exceptions is None else np.ascontiguousarray(exceptions, dtype=np.uint64)
+        nq = len(qoff) - 1
+        counts = out if out is not None else np.empty(nq, dtype=np.uint64)
+        _check(native().awry_count_batch_packed2(self._h, crumbs.ctypes.data, qoff.ctypes.data, nq,
+                                                 exc.ctypes.data if len(exc) else None, len(exc), counts.ctypes.data))
+        return counts
+
+    def locate_prepacked_into(self, crumbs: np.ndarray, qoff: np.ndarray, exceptions: np.ndarray, hit_off: np.ndarray,
+                              hits: np.ndarray, sorted_hits: bool = False) -> int:
+        """parallel_locate on 2-bit packed reads into caller-owned arrays (see locate_packed_into)."""
+        crumbs = np.ascontiguousarray(crumbs, dtype=np.uint8)
+        qoff = np.ascontiguousarray(qoff, dtype=np.uint64)
+        exc = np.zeros(0, np.uint64) if exceptions is None else np.ascontiguousarray(exceptions, dtype=np.uint64)
+        n = C.c_uint64()
+        rc = native().awry_locate_batch_packed2(self._h, crumbs.ctypes.data, qoff.ctypes.data, len(qoff) - 1,
+                                                exc.ctypes.data if len(exc) else None, len(exc),
+                                                LOCATE_SORTED if sorted_hits else LOCATE_BWT_ORDER,
+                                                hit_off.ctypes.data, hits.ctypes.data, len(hits), C.byref(n))
+        if rc != 0:
+            err = AwryError(rc, native().awry_last_error().decode(errors="replace"))
+            err.needed = n.value
+            raise err
+        return n.value
+
     # ---- streaming reads-file front-end (FASTQ / FASTA parsed on the device) ---------------
     def count_reads_file(self, path) -> np.ndarray:
         """parallel_count over every record of a FASTQ / FASTA file; read i of the file is entry i."""
@@ -539,6 +573,15 @@ def set_locate_variant(variant: int = 0):
 def set_host_pack(mode: int = -1):
     """-1 = auto, 0 = send ASCII queries over PCIe, 1 = pack nucleotide queries to 2 bits on the host first."""
     _check(native().awry_set_host_pack(mode))
+
+
+def set_host_threads(n: int = 0):
+    """threads of the host-side packer pool (0 = default: min(16, cores / LOCAL_WORLD_SIZE))"""
+    _check(native().awry_set_host_threads(int(n)))
+
+
+def host_threads() -> int:
+    return int(native().awry_host_threads())
 
 
 def host_pack_dna(src: np.ndarray):

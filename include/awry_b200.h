@@ -27,7 +27,7 @@ extern "C" {
 
 typedef enum awry_status {
   AWRY_OK = 0,
-  AWRY_ERR_INVALID_ARG = -1,
+  AWRY_ERR_INVALID_ARG = -1, /* null pointer, query offsets not monotone, ... */
   AWRY_ERR_IO = -2,          /* FmIndex::load -> io::Error (fm_index_file.rs:132)              */
   AWRY_ERR_FORMAT = -3,      /* bad label / header (fm_index_file.rs:145-150)                  */
   AWRY_ERR_CUDA = -4,        /* no device, allocation or launch failure                        */
@@ -192,13 +192,32 @@ int awry_locate_batch(const awry_index *index, const uint8_t *qbytes, const uint
                       uint64_t *n_hits);
 void awry_hits_free(awry_hit *hits);
 
-/* Same, with caller-owned output like `counts` above: up to `capacity` hits are written to `hits`
- * (pinned memory makes the device->host copy a direct DMA).  *n_hits is always the total found; if
- * it exceeds `capacity` the call returns AWRY_ERR_CAPACITY (hit_off is complete, hits is not) and
- * can be repeated with a larger buffer.  capacity = 0 just fills hit_off / *n_hits. */
+/* Same, with caller-owned output like `counts` above: up to `capacity` hits are written to `hits`.
+ * *n_hits is always the total found; if it exceeds `capacity` the call returns AWRY_ERR_CAPACITY
+ * (hit_off is complete, hits is not) and can be repeated with a larger buffer.  capacity = 0 just fills
+ * hit_off / *n_hits.  With `hits` in page-locked memory (cudaHostAlloc / cudaHostRegister), BWT order and
+ * the unsampled suffix array present, the two passes run without a host round trip: the device keeps the
+ * running hit total and the gather kernel writes the hits straight into `hits`. */
 int awry_locate_batch_into(const awry_index *index, const uint8_t *qbytes, const uint64_t *qoff,
                            uint64_t nq, uint32_t flags, uint64_t *hit_off, awry_hit *hits,
                            uint64_t capacity, uint64_t *n_hits);
+
+/* ------------------------------------------------------------------ batched search on pre-packed reads
+ * The reference's callers hold `&str`s (fm_index.rs:455-487), so the calls above take ASCII and the
+ * library packs it to 2 bits per base on the host cores before the PCIe copy.  A caller that searches the
+ * same reads more than once, or stores them packed, can hand the 2-bit form over and skip that pass: a
+ * quarter of the bytes are read from host memory and nothing is computed on the host.  Nucleotide only.
+ *   crumbs      code of query byte p (p counted as in qoff) = (ascii >> 1) & 3  (A0 C1 T2 G3, either case)
+ *               at bits 2*(p%4) of crumbs[p/4]; the array holds ceil(qoff[nq]/4) bytes
+ *               (awry_host_pack_dna produces exactly this)
+ *   exceptions  every byte outside ACGTacgt (N, IUPAC codes, '$'...) as (p << 8) | ascii byte, strictly
+ *               ascending by p; its crumb is ignored
+ * Results are those of awry_count_batch / awry_locate_batch_into on the ASCII the codes stand for. */
+int awry_count_batch_packed2(const awry_index *index, const uint8_t *crumbs, const uint64_t *qoff,
+                             uint64_t nq, const uint64_t *exceptions, uint64_t n_exc, uint64_t *counts);
+int awry_locate_batch_packed2(const awry_index *index, const uint8_t *crumbs, const uint64_t *qoff,
+                              uint64_t nq, const uint64_t *exceptions, uint64_t n_exc, uint32_t flags,
+                              uint64_t *hit_off, awry_hit *hits, uint64_t capacity, uint64_t *n_hits);
 
 /* ------------------------------------------------------------------ streaming reads-file front-end
  * SURVEY.md 8(f) rank 4.  The reference's users parse their reads on the CPU and pass `&str`s to
@@ -227,7 +246,10 @@ int awry_backstep(const awry_index *index, uint64_t bwt_row, uint64_t *out);
 /* ------------------------------------------------------------------ device-resident entry points
  * Same kernels as the *_batch calls, for callers that already hold the queries in HBM
  * (bench.py's kernel-only figure).  Pointers are device pointers on replica `replica`'s
- * device; `cuda_stream` is a cudaStream_t (NULL = default stream).  Asynchronous. */
+ * device; `cuda_stream` is a cudaStream_t (NULL = default stream).  The kernels are enqueued on that
+ * stream and the call returns without waiting for them; it does read the first and last query offset
+ * back first (16 bytes, one stream synchronisation) to size its scratch, so it is not capturable in a
+ * CUDA graph. */
 int awry_count_device(const awry_index *index, int replica, const uint8_t *d_qbytes,
                       const uint64_t *d_qoff, uint64_t nq, uint64_t *d_counts, void *cuda_stream);
 /* two-pass locate on device-resident queries; results stay on the device.  Synchronises once
@@ -288,9 +310,15 @@ int awry_set_locate_variant(int variant);
  * mode -1 = auto (on when the CPU supports it and the pool has >= 4 threads; AWRY_B200_HOST_PACK=0/1
  * overrides), 0 = always send ASCII, 1 = always pack. */
 int awry_set_host_pack(int mode);
-/* The packer itself, exposed for tests: dst gets ceil(n/4) bytes, crumb i = (src[i] >> 1) & 3 at bits
- * 2*(i%4) of dst[i/4]; exceptions (up to exc_cap) receive (i << 8) | src[i] for bytes outside ACGTacgt;
- * *n_exc is their total number. */
+/* Threads the host-side packer may use (a process-wide pool shared by all calls and replicas; it grows on
+ * demand).  Default: AWRY_B200_HOST_THREADS, else min(16, cores / LOCAL_WORLD_SIZE) -- one process per GPU
+ * under torchrun shares the host; a process that drives several replicas itself should raise it to the
+ * cores it owns.  n = 0 restores the default. */
+int awry_set_host_threads(int n);
+int awry_host_threads(void);
+/* The packer itself (the producer of awry_*_batch_packed2's input): dst gets ceil(n/4) bytes, crumb i =
+ * (src[i] >> 1) & 3 at bits 2*(i%4) of dst[i/4]; exceptions (up to exc_cap, ascending by i) receive
+ * (i << 8) | src[i] for bytes outside ACGTacgt; *n_exc is their total number. */
 int awry_host_pack_dna(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t *exceptions,
                        uint64_t exc_cap, uint64_t *n_exc);
 

@@ -127,6 +127,13 @@ extern "C" {
     pub fn awry_read_sequence_file(path: *const c_char, alphabet: u32, text: *mut *mut u8, n_text: *mut u64,
                                    starts: *mut *mut u64, n_records: *mut u64) -> c_int;
     pub fn awry_host_pack_dna(src: *const u8, n: u64, dst: *mut u8, exceptions: *mut u64, exc_cap: u64, n_exc: *mut u64) -> c_int;
+    pub fn awry_count_batch_packed2(index: *const awry_index, crumbs: *const u8, qoff: *const u64, nq: u64,
+                                    exceptions: *const u64, n_exc: u64, counts: *mut u64) -> c_int;
+    pub fn awry_locate_batch_packed2(index: *const awry_index, crumbs: *const u8, qoff: *const u64, nq: u64,
+                                     exceptions: *const u64, n_exc: u64, flags: u32, hit_off: *mut u64,
+                                     hits: *mut awry_hit, capacity: u64, n_hits: *mut u64) -> c_int;
+    pub fn awry_set_host_threads(n: c_int) -> c_int;
+    pub fn awry_host_threads() -> c_int;
     pub fn awry_profile_enable(on: c_int) -> c_int;
     pub fn awry_profile_reset() -> c_int;
     pub fn awry_profile_get(out: *mut awry_profile) -> c_int;

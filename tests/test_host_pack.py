@@ -41,3 +41,49 @@ def test_host_packer_matches_numpy(simd):
     env = dict(os.environ, AWRY_B200_HOST_SIMD=simd, AWRY_B200_HOST_THREADS="5")
     out = subprocess.run([sys.executable, "-c", CHECK], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr[-2000:]
+
+
+def test_exceptions_come_back_ascending():
+    """awry_*_batch_packed2 wants the exception list sorted by position: the packer's own output is"""
+    from awry_b200 import fm_index as f
+    rng = np.random.default_rng(3)
+    src = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 2_000_003)].copy()
+    src[rng.integers(0, len(src), 5000)] = ord("N")
+    _, exc = f.host_pack_dna(src)
+    pos = exc >> np.uint64(8)
+    assert len(exc) > 4000 and np.all(pos[1:] > pos[:-1])
+
+
+def test_pool_serves_concurrent_callers_and_resizes():
+    """one process-wide pool, several parallel regions open at once (one per replica thread of a multi-GPU
+    call): every caller gets its own, complete result, whatever the thread cap"""
+    import threading
+    from awry_b200 import fm_index as f
+    rng = np.random.default_rng(11)
+    srcs = [np.frombuffer(b"ACGTacgtN", dtype=np.uint8)[rng.integers(0, 9, 1_500_000 + 77_777 * i)].copy() for i in range(6)]
+    want = [f.host_pack_dna(s) for s in srcs]
+    before = f.host_threads()
+    try:
+        for cap in (1, 3, 8):
+            f.set_host_threads(cap)
+            assert f.host_threads() == cap
+            got, errs = [None] * len(srcs), []
+
+            def work(i):
+                try:
+                    for _ in range(3):
+                        got[i] = f.host_pack_dna(srcs[i])
+                except Exception as e:  # noqa: BLE001
+                    errs.append(e)
+
+            th = [threading.Thread(target=work, args=(i,)) for i in range(len(srcs))]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            assert not errs, errs
+            for (a, ea), (b, eb) in zip(want, got):
+                assert np.array_equal(a, b) and np.array_equal(ea, eb)
+    finally:
+        f.set_host_threads(0)
+    assert f.host_threads() == before
