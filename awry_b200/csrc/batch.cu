@@ -1112,8 +1112,14 @@ int awry_set_locate_variant(int variant) {
 
 int awry_set_search_variant(int lanes_per_query, int threads_per_block, int blocks_per_sm) {
   if (lanes_per_query != 0 && lanes_per_query != -1 && lanes_per_query != 1 && lanes_per_query != 2 &&
-      lanes_per_query != 4 && lanes_per_query != 8)
+      lanes_per_query != 4 && lanes_per_query != 8 && lanes_per_query != 80 && lanes_per_query != 81 &&
+      lanes_per_query != 82)
     return AWRY_ERR_INVALID_ARG;
+  g_variant.slots = -1;  // default choice of the pair kernel's flavour
+  if (lanes_per_query >= 80) {  // 80 / 81 / 82: the pair kernel with 0 (branching refill) / 1 / 2 state-machine slots
+    g_variant.slots = lanes_per_query - 80;
+    lanes_per_query = 8;
+  }
   g_variant.lanes = lanes_per_query;
   g_variant.tpb = threads_per_block;
   g_variant.blocks_per_sm = blocks_per_sm;

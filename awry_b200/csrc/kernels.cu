@@ -1201,6 +1201,281 @@ __global__ void __launch_bounds__(TPB, MINB)
   }
 }
 
+// ---- nucleotide pair kernel, NS queries per lane group, every load of a query's life in the same slot of
+// the instruction stream ("state machine") ----
+// search_dna_pair_kernel above has two costs the block reads do not explain.  (1) A query's start is a chain
+// of three dependent loads (its offsets -> its packed words -> its seed-table entry) that runs inside a
+// divergent branch: while ONE lane group of a warp starts a query, the other seven wait for all three
+// latencies, so reads that end early (dephasing the groups) cost far more than the steps they save.
+// (2) One block read in flight per lane group: 384 per SM at 6 x 256 threads.
+// Here a lane group owns NS query SLOTS, and every slot is in one of five states whose load is issued at
+// the same point of the loop -- ST_OFFS (its two offsets), ST_WORDS (its packed symbols, into the
+// shared-memory ring), ST_SEED (its k-mer table entry), ST_STEP (one pair block = two LF steps, or a
+// one-symbol block), ST_RING (8 more words of a long query) -- then all slots consume.  A group that starts
+// a query spends three iterations on it without holding anyone up, the loads of the NS slots of a lane
+// overlap, and the warp-level bookkeeping (hand-out ballot, exit vote, loop) is paid once per NS block reads.
+// Everything else is as above: 4 lanes per query, per-warp pool of query numbers topped up with one atomic,
+// queries with an ambiguity symbol go to the scalar kernel through `defer`, full-mask xor-shuffles.
+// MEASURED (profiles/r02_s1_ab_state_machine_*.log, 10 launches back to back, 10 M x 150 bp): it LOSES --
+// 19.6 ms (1 slot, 8 x 256 threads/SM) and 18.7 ms (2 slots, 5 x 256) against 17.8 ms for the branching kernel,
+// 21.8 / 20.6 against 19.1 ms with 10 % mismatching reads, 0.58 / 0.57 against 0.54 ms for 1 M x 50 bp.
+// The state dispatch adds ~20 % instructions per block read, and at ~41 G block reads/s the part sits at its
+// power cap (sw_power_cap in every bench line): what a launch costs follows the instructions it issues, not
+// the loads it has in flight, so more memory-level parallelism per lane buys nothing here.  The default stays
+// search_dna_pair_kernel; this one is bit-exact (the GPU suite passes with AWRY_B200_SLOTS=1 and =2) and
+// selectable (awry_set_search_variant(81 / 82)) so the comparison can be repeated.
+template <int MODE, int TPB, int MINB, int NS>
+__global__ void __launch_bounds__(TPB, MINB)
+    search_dna_pairx_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
+                            const uint64_t* __restrict__ qoff, uint64_t nq, void* __restrict__ out,
+                            uint32_t* __restrict__ defer, uint32_t ticket_sz, ByteRange br) {
+  constexpr uint32_t NONE = 0xffffffffu, FULL = 0xffffffffu;
+  enum : uint32_t { ST_IDLE = 0, ST_OFFS = 1, ST_WORDS = 2, ST_SEED = 3, ST_STEP = 4, ST_RING = 5 };
+  constexpr uint32_t PC_STEP = 0x200u, PC_TWO = 0x100u;  // pc: "this slot issued a step" | "a two-symbol step" | symbols
+  __shared__ uint64_t s_q[NS][TPB / 4][16];
+  __shared__ uint32_t s_amb[NS][TPB / 4];  // an ambiguity symbol was seen while staging (set by any lane of the group)
+  const uint32_t lane = threadIdx.x & 31, sub = lane & 3, gbase = lane - sub;
+  const uint32_t gmask = 0xfu << gbase;
+  const uint32_t grp = threadIdx.x >> 2;
+  const uint32_t nq32 = uint32_t(nq);
+  uint32_t* const ticket = defer + nq + 1;
+  uint32_t pn = 0, pe = 0;  // the warp's pool of query numbers (see search_dna_pair_kernel)
+  bool more = true;
+  uint32_t st[NS], cur[NS], sp[NS], ep[NS], left[NS], len[NS], ubase[NS], wlim[NS];
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+    st[s] = ST_IDLE;
+    cur[s] = NONE;
+    sp[s] = 1;
+    ep[s] = 0;
+    left[s] = len[s] = ubase[s] = 0;
+    wlim[s] = 8;
+  }
+
+  for (;;) {
+    // ---- hand-out: lane `s` of a group reports slot s (NS <= 4), one ballot for the warp
+    bool want_here = false;
+#pragma unroll
+    for (int s = 0; s < NS; s++) want_here |= (sub == uint32_t(s)) && st[s] == ST_IDLE;
+    const uint32_t wmask = __ballot_sync(FULL, want_here);
+    if (wmask != 0 && (pn != pe || more)) {  // warp-uniform
+      const uint32_t n_want = __popc(wmask), avail = pe - pn;
+      uint32_t b = 0, got = 0;
+      if (n_want > avail && more) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(ticket, ticket_sz);
+        t = __shfl_sync(FULL, t, 0);
+        b = t;
+        got = t < nq32 ? (nq32 - t < ticket_sz ? nq32 - t : ticket_sz) : 0u;
+        more = got == ticket_sz;
+      }
+#pragma unroll
+      for (int s = 0; s < NS; s++) {
+        if (st[s] == ST_IDLE) {
+          const uint32_t r = __popc(wmask & ((1u << (gbase + s)) - 1u));  // this slot's rank among the needy ones
+          const uint32_t nx = r < avail ? pn + r : (r - avail < got ? b + (r - avail) : NONE);
+          if (nx != NONE) {
+            cur[s] = nx;
+            st[s] = ST_OFFS;
+          }
+        }
+      }
+      if (n_want <= avail) {
+        pn += n_want;
+      } else if (got) {
+        const uint32_t used = n_want - avail < got ? n_want - avail : got;
+        pn = b + used;
+        pe = b + got;
+      } else {
+        pn = pe;
+      }
+    }
+    bool idle = true;
+#pragma unroll
+    for (int s = 0; s < NS; s++) idle &= st[s] == ST_IDLE;
+    if (__all_sync(FULL, idle)) break;  // a slot still idle after the hand-out: the batch has been given out
+
+    // ---- issue: one load per slot
+    u32x8 x[NS];
+    uint32_t pc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+      pc[s] = 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) x[s].v[i] = 0;
+      if (st[s] == ST_STEP) {
+        const uint32_t pos = len[s] - left[s];       // search-order index of the next symbol
+        if ((pos >> 4) >= wlim[s]) st[s] = ST_RING;  // long query: the ring has to slide first
+      }
+      if (st[s] == ST_STEP) {
+        const uint32_t pos = len[s] - left[s];
+        // A pair step always starts on an EVEN symbol index (an odd start takes one single-symbol step
+        // first), so both symbols are one byte of the ring: low nibble = symbol pos, high nibble = pos + 1.
+        const uint32_t qb = reinterpret_cast<const uint8_t*>(s_q[s][grp])[(pos >> 1) & 127];
+        const uint32_t pa = sp[s] - 1;
+        if (left[s] >= 2 && (pos & 1) == 0) {
+          pc[s] = PC_STEP | PC_TWO | ((qb & 3u) << 2) | (qb >> 4);
+          const uint32_t ba = __umulhi(pa, 0xAAAAAAABu) >> 6;  // / 96
+          x[s] = ldg256(ix.pair_blocks + size_t(ba) * PAIR_BLOCK_UINT4 + 2 * sub);
+        } else {
+          pc[s] = PC_STEP | ((qb >> (4 * (pos & 1))) & 15u);
+          const uint4 c = ldg128(ix.blocks + size_t(pa >> 7) * DNA_BLOCK_UINT4 + sub);
+          x[s].v[0] = c.x;
+          x[s].v[1] = c.y;
+          x[s].v[2] = c.z;
+          x[s].v[3] = c.w;
+        }
+      } else if (st[s] == ST_OFFS) {
+        const uint64_t ov = __ldg(qoff + cur[s] + (sub & 1));  // lanes 0/1 fetch both ends with one request
+        x[s].v[0] = uint32_t(ov);
+        x[s].v[1] = uint32_t(ov >> 32);
+      } else if (st[s] == ST_WORDS) {
+        if (4 * sub < ((len[s] + 15) >> 4)) x[s] = ldg256(qwords + ubase[s] + 4 * sub);
+      } else if (st[s] == ST_SEED) {
+        const uint32_t k = ix.kmer_len;
+        const uint64_t w = s_q[s][grp][0];  // k <= 16: inside word 0
+        uint64_t idx = 0;
+#pragma unroll 1
+        for (uint32_t j = 0; j < k; j++) idx |= ((w >> (4 * j)) & 3ull) << (2 * j);
+        const uint2 r = __ldg(ix.table + idx);
+        x[s].v[0] = r.x;
+        x[s].v[1] = r.y;
+      } else if (st[s] == ST_RING) {
+        if (sub < 2) x[s] = ldg256(qwords + ubase[s] + wlim[s] + 8 + 4 * sub);  // in bounds: buffer padded by 32 words
+      }
+    }
+
+    // ---- consume
+    uint32_t ra[NS], rb[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+      ra[s] = rb[s] = 0;
+      uint64_t* const ring = s_q[s][grp];
+      if (st[s] == ST_STEP) {
+        const uint32_t pa = sp[s] - 1, pb = ep[s];
+        if (pc[s] & PC_TWO) {
+          const uint32_t pair = pc[s] & 15u;
+          const uint32_t ba = __umulhi(pa, 0xAAAAAAABu) >> 6;
+          const uint32_t la = pa - ba * PAIR_ROWS_PER_BLOCK, lb = pb - ba * PAIR_ROWS_PER_BLOCK;
+          PairSlice sl = pair_slice(x[s], sub, pair);
+          ra[s] = __popc(sl.match & low_mask(int(la) + 1 - int(32 * sub))) + sl.count;
+          if (lb < PAIR_ROWS_PER_BLOCK) {
+            rb[s] = __popc(sl.match & low_mask(int(lb) + 1 - int(32 * sub))) + sl.count;
+          } else {  // the interval straddles two blocks (only while it is still wide): a real branch
+            const uint32_t bb = __umulhi(pb, 0xAAAAAAABu) >> 6;
+            const u32x8 y = ldg256(ix.pair_blocks + size_t(bb) * PAIR_BLOCK_UINT4 + 2 * sub);
+            sl = pair_slice(y, sub, pair);
+            rb[s] = __popc(sl.match & low_mask(int(pb - bb * PAIR_ROWS_PER_BLOCK) + 1 - int(32 * sub))) + sl.count;
+          }
+        } else {
+          const uint32_t c1 = pc[s] & 15u;
+          const uint32_t ba = pa >> 7, bb = pb >> 7;
+          LaneChunks<4> y;
+          y.c[0] = make_uint4(x[s].v[0], x[s].v[1], x[s].v[2], x[s].v[3]);
+          const uint32_t m0 = (c1 & 1) ? ~0u : 0u, m1 = (c1 & 2) ? ~0u : 0u;
+          ra[s] = dna_partial_rank<4>(y, sub, pa & 127, c1, m0, m1);
+          if (bb != ba) y.load(ix.blocks + size_t(bb) * DNA_BLOCK_UINT4, sub);
+          rb[s] = dna_partial_rank<4>(y, sub, pb & 127, c1, m0, m1);
+        }
+      } else if (st[s] == ST_OFFS) {
+        const uint64_t ov = uint64_t(x[s].v[0]) | (uint64_t(x[s].v[1]) << 32);
+        const uint64_t o0 = __shfl_sync(gmask, ov, gbase), o1 = __shfl_sync(gmask, ov, gbase + 1);
+        len[s] = checked_len(o0, o1, br);
+        sp[s] = 1;
+        ep[s] = 0;
+        left[s] = 0;
+        wlim[s] = 8;
+        if (len[s] == 0) {  // refused by the prepass: an empty result, the call fails anyway
+          if (sub == 0) store_result<MODE>(out, cur[s], 1u, 0u);
+          st[s] = ST_IDLE;
+        } else {
+          ubase[s] = 4 * (cur[s] + uint32_t(o0 >> 6));
+          if (sub == 0) s_amb[s][grp] = 0;
+          st[s] = ST_WORDS;
+        }
+      } else if (st[s] == ST_WORDS) {
+        // ambiguity symbols (code >= 4) are looked for once, while the query is staged, not per step;
+        // unused nibbles of the last word are 0
+        const uint32_t nwords = (len[s] + 15) >> 4;
+        uint32_t amb = 0;
+        __syncwarp(gmask);  // the previous query's last ring reads, and the flag's reset, are done
+        if (4 * sub < nwords) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            ring[4 * sub + j] = uint64_t(x[s].v[2 * j]) | (uint64_t(x[s].v[2 * j + 1]) << 32);
+            if (4 * sub + j < nwords) amb |= (x[s].v[2 * j] | x[s].v[2 * j + 1]) & 0xCCCCCCCCu;
+          }
+        }
+        if (amb) s_amb[s][grp] = 1;
+        __syncwarp(gmask);
+        if (s_amb[s][grp]) {  // hand the whole query to the scalar kernel
+          if (sub == 0) defer[1 + atomicAdd(defer, 1u)] = cur[s];
+          st[s] = ST_IDLE;
+        } else if (ix.kmer_len != 0 && len[s] >= ix.kmer_len) {
+          st[s] = ST_SEED;
+        } else {
+          const uint32_t c = uint32_t(ring[0]) & 15u;
+          sp[s] = ix.c_lo[c];
+          ep[s] = ix.c_hi[c];
+          left[s] = len[s] - 1;
+          st[s] = ST_STEP;
+        }
+      } else if (st[s] == ST_SEED) {
+        sp[s] = x[s].v[0];
+        ep[s] = x[s].v[1];
+        left[s] = len[s] - ix.kmer_len;
+        st[s] = ST_STEP;
+      } else if (st[s] == ST_RING) {
+        const uint32_t nwords = (len[s] + 15) >> 4;
+        uint32_t amb = 0;
+        __syncwarp(gmask);
+        if (sub < 2) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            ring[(wlim[s] + 8 + 4 * sub + j) & 15] = uint64_t(x[s].v[2 * j]) | (uint64_t(x[s].v[2 * j + 1]) << 32);
+            if (wlim[s] + 8 + 4 * sub + j < nwords) amb |= (x[s].v[2 * j] | x[s].v[2 * j + 1]) & 0xCCCCCCCCu;
+          }
+        }
+        if (amb) s_amb[s][grp] = 1;
+        __syncwarp(gmask);
+        wlim[s] += 8;
+        if (s_amb[s][grp]) {  // ambiguity symbol further on: the scalar kernel redoes the whole query
+          if (sub == 0) defer[1 + atomicAdd(defer, 1u)] = cur[s];
+          st[s] = ST_IDLE;
+        } else {
+          st[s] = ST_STEP;
+        }
+      }
+    }
+    // rank reduction over the 4 lanes of every group, all slots, full-mask shuffles (every lane is here)
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+      ra[s] += __shfl_xor_sync(FULL, ra[s], 1);
+      rb[s] += __shfl_xor_sync(FULL, rb[s], 1);
+    }
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+      ra[s] += __shfl_xor_sync(FULL, ra[s], 2);
+      rb[s] += __shfl_xor_sync(FULL, rb[s], 2);
+    }
+    // ---- apply the steps; a query that ends (all symbols consumed, or an empty interval: the early break
+    // of fm_index.rs:409-416 / :425-433) is stored and its slot draws a new query in the next iteration
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+      if (pc[s] & PC_STEP) {
+        const uint32_t base = (pc[s] & PC_TWO) ? ix.c2[pc[s] & 15u] : ix.c_lo[pc[s] & 15u];
+        sp[s] = base + ra[s];
+        ep[s] = base + rb[s] - 1;
+        left[s] -= (pc[s] & PC_TWO) ? 2 : 1;
+      }
+      if (st[s] == ST_STEP && (left[s] == 0 || sp[s] > ep[s])) {  // (also: a query no longer than its seed)
+        if (sub == 0) store_result<MODE>(out, cur[s], sp[s], ep[s]);
+        st[s] = ST_IDLE;
+      }
+    }
+  }
+}
+
 template <int MODE, int MINB>
 static cudaError_t launch_search_pair_b(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
                                         uint64_t nq, void* d_out, uint32_t* d_defer, int force_per_sm,
@@ -1236,6 +1511,37 @@ static cudaError_t launch_search_pair_b(const IndexView& ix, const uint64_t* d_q
   return cudaGetLastError();
 }
 
+// the state-machine kernel: NS query slots per lane group, `per_sm` resident 256-thread blocks (register budget)
+template <int MODE, int MINB, int NS>
+static cudaError_t launch_search_pairx_b(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
+                                         uint64_t nq, void* d_out, uint32_t* d_defer, int sm_count, cudaStream_t s,
+                                         uint32_t avg_len, ByteRange br) {
+  constexpr int TPB = 256;
+  auto kern = search_dna_pairx_kernel<MODE, TPB, MINB, NS>;
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, 0);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  const uint64_t max_blocks = uint64_t(sm_count) * uint64_t(per_sm);
+  const uint64_t need_blocks = (nq * 4 + uint64_t(TPB) * NS - 1) / (uint64_t(TPB) * NS);
+  const unsigned grid = unsigned(std::max<uint64_t>(1, std::min(max_blocks, need_blocks)));
+  static const uint32_t ticket_env = [] {  // AWRY_B200_TICKET: fixed ticket size (experiments)
+    if (const char* e = getenv("AWRY_B200_TICKET")) return uint32_t(std::min(1024l, std::max(1l, strtol(e, nullptr, 10))));
+    return 0u;
+  }();
+  // per-WARP ticket: one query per slot (8 groups x NS slots) for 150-bp reads, more for short queries; small
+  // batches get small tickets so that every warp still draws several (see launch_search_pair_b)
+  uint32_t per_slot = avg_len == 0 ? 2u : std::min(8u, std::max(1u, 200u / avg_len));
+  per_slot = ticket_cap(per_slot, nq, uint64_t(grid) * (TPB / 4) * NS, avg_len);
+  const uint32_t ticket_sz = ticket_env ? ticket_env : 8u * NS * per_slot;
+  e = launch_with_table_window(kern, grid, TPB, s, ix, ix, d_qwords, d_qoff, nq, d_out, d_defer, ticket_sz, br);
+  COUNT_LAUNCH();
+  if (e != cudaSuccess) return e;
+  search_scalar_kernel<0, MODE, true><<<unsigned(sm_count) * 2, 256, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out, d_defer, br);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
 template <int MODE>
 static cudaError_t launch_search_pair(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
                                       uint64_t nq, void* d_out, uint32_t* d_defer, const SearchVariant& v,
@@ -1245,6 +1551,15 @@ static cudaError_t launch_search_pair(const IndexView& ix, const uint64_t* d_qwo
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(d_defer + nq + 1, 0, 4, s);                     // ticket counter
   if (e != cudaSuccess) return e;
+  const ByteRange br{v.b_lo, v.b_hi};
+  static const int slots_default = [] {
+    if (const char* e = getenv("AWRY_B200_SLOTS")) return std::max(0, std::min(2, atoi(e)));
+    return 0;
+  }();
+  const int slots = v.slots >= 0 ? v.slots : slots_default;
+  // the state-machine variant, kept selectable for A/B runs with its two best residencies (see the kernel)
+  if (slots == 1) return launch_search_pairx_b<MODE, 8, 1>(ix, d_qwords, d_qoff, nq, d_out, d_defer, sm_count, s, v.avg_len, br);
+  if (slots == 2) return launch_search_pairx_b<MODE, 5, 2>(ix, d_qwords, d_qoff, nq, d_out, d_defer, sm_count, s, v.avg_len, br);
   switch (v.blocks_per_sm) {
     case 4: return launch_search_pair_b<MODE, 4>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, ByteRange{v.b_lo, v.b_hi});
     // 8 x 256 threads/SM (32 registers) is fastest for an isolated launch (16.2 vs 16.6-17.0 ms), 6 x 256

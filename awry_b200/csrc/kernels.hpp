@@ -24,6 +24,8 @@ struct SearchVariant {
                           // kernel (default when the pair index exists); -1 = scalar kernel
   int tpb = 0;            // threads per block
   int blocks_per_sm = 0;  // 0 = occupancy-derived
+  int slots = -1;         // pair kernel: 0 = search_dna_pair_kernel; 1 / 2 = search_dna_pairx_kernel with that many
+                          // query slots per lane group; -1 = default (AWRY_B200_SLOTS, else the measured winner)
   uint32_t avg_len = 0;   // mean query length of the batch (0 = unknown): sizes the tickets of the dynamic hand-out
   uint64_t b_lo = 0, b_hi = ~0ull;  // byte range of the batch's queries: offsets outside it are refused (see launch_pack)
 };

@@ -294,7 +294,9 @@ int awry_bench_random_gather(int device, uint64_t footprint_bytes, uint32_t gran
 
 /* Tuning knob for experiments: selects the search-kernel variant.  lanes_per_query: 1/2/4 =
  * that many lanes on the one-symbol blocks, 8 = the two-symbol (pair index) kernel, -1 = scalar
- * kernel, 0 = default (pair kernel when the pair index exists).  blocks_per_sm caps residency. */
+ * kernel, 0 = default (pair kernel when the pair index exists); 80 / 81 / 82 = the pair kernel with its
+ * query start as a branch (80) or as states of 1 / 2 query slots per lane group (81 / 82).
+ * blocks_per_sm caps residency. */
 int awry_set_search_variant(int lanes_per_query, int threads_per_block, int blocks_per_sm);
 
 /* Locate pass 2.  When memory allows (AWRY_B200_FULL_SA=0 disables, =1 forces) the index keeps the
