@@ -80,6 +80,9 @@ void set_view_constants(awry_index* ix, Replica& r) {
   v.seq_starts = r.d_seq_starts;
   v.pair_blocks = r.d_pair;
   v.full_sa = r.d_full_sa;
+  v.walk_blocks = r.d_walk;
+  v.walk_rank = r.d_walk_rank;
+  v.pos_samples = r.d_pos_samples;
   for (int i = 0; i < 16; i++) v.c2[i] = r.c2[i];
   v.bwt_len = uint32_t(ix->bwt_len);
   v.sa_ratio = uint32_t(ix->sa_ratio);
@@ -275,6 +278,28 @@ void finish_replica0(awry_index* ix, Replica& r) {
       r.view.full_sa = r.d_full_sa;
     }
   }
+  // Memory-lean bounded locate (nucleotide): walk blocks + position-sampled suffix array, 4.57 + 32/ratio bits
+  // per row.  Built when the unsampled array is not (it did not fit, or AWRY_B200_FULL_SA=0), or on request
+  // (AWRY_B200_LEAN_SA=1: both, for A/B runs; =0: never -- locate then LF-walks to the file's row samples).
+  const char* ls = getenv("AWRY_B200_LEAN_SA");
+  const bool lean_never = ls && ls[0] == '0', lean_force = ls && ls[0] == '1';
+  if (ix->alphabet == AWRY_NUCLEOTIDE && !g_skip_accelerators && ix->sa_ratio > 1 && !lean_never &&
+      (lean_force || r.d_full_sa == nullptr)) {
+    const uint64_t nb = walk_block_count(ix->bwt_len);
+    const uint64_t n_pos = (ix->bwt_len + ix->sa_ratio - 1) / ix->sa_ratio;
+    const size_t bytes = size_t(nb) * 128 + size_t(nb + 1) * 4 + size_t(n_pos + 4) * 4;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    if (bytes + (1u << 28) < free_b) {
+      CU(cudaMalloc(reinterpret_cast<void**>(&r.d_walk), size_t(nb) * 128 + 256));
+      CU(cudaMalloc(reinterpret_cast<void**>(&r.d_walk_rank), size_t(nb + 1) * 4 + 256));
+      CU(cudaMalloc(reinterpret_cast<void**>(&r.d_pos_samples), size_t(n_pos + 4) * 4 + 256));
+      CU(build_lean_sa(r.view, r.d_walk, r.d_walk_rank, r.d_pos_samples, r.sm_count, nullptr));
+      r.bytes_lean = bytes;
+      r.view.walk_blocks = r.d_walk;
+      r.view.walk_rank = r.d_walk_rank;
+      r.view.pos_samples = r.d_pos_samples;
+    }
+  }
 }
 
 void clone_replica(awry_index* ix, const Replica& src, Replica& dst) {
@@ -308,6 +333,17 @@ void clone_replica(awry_index* ix, const Replica& src, Replica& dst) {
     dst.bytes_full_sa = src.bytes_full_sa;
     CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_full_sa), src.bytes_full_sa + 256));
     CU(cudaMemcpyPeer(dst.d_full_sa, dst.device, src.d_full_sa, src.device, src.bytes_full_sa));
+  }
+  if (src.bytes_lean) {
+    const uint64_t nb = walk_block_count(ix->bwt_len);
+    const uint64_t n_pos = (ix->bwt_len + ix->sa_ratio - 1) / ix->sa_ratio;
+    dst.bytes_lean = src.bytes_lean;
+    CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_walk), size_t(nb) * 128 + 256));
+    CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_walk_rank), size_t(nb + 1) * 4 + 256));
+    CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_pos_samples), size_t(n_pos + 4) * 4 + 256));
+    CU(cudaMemcpyPeer(dst.d_walk, dst.device, src.d_walk, src.device, size_t(nb) * 128));
+    CU(cudaMemcpyPeer(dst.d_walk_rank, dst.device, src.d_walk_rank, src.device, size_t(nb + 1) * 4));
+    CU(cudaMemcpyPeer(dst.d_pos_samples, dst.device, src.d_pos_samples, src.device, size_t(n_pos + 4) * 4));
   }
   uint32_t dollar = src.view.dollar_row;
   set_view_constants(ix, dst);
@@ -497,6 +533,9 @@ void awry_index_free(awry_index* ix) {
     cudaFree(r.d_table);
     cudaFree(r.d_pair);
     cudaFree(r.d_full_sa);
+    cudaFree(r.d_walk);
+    cudaFree(r.d_walk_rank);
+    cudaFree(r.d_pos_samples);
     cudaFree(r.d_seq_starts);
     cudaFree(r.d_async_flag);
   }
@@ -522,6 +561,7 @@ int awry_index_info(const awry_index* ix, awry_info* info) {
     info->device_bytes_table = ix->reps[0]->bytes_table;
     info->device_bytes_pair = ix->reps[0]->bytes_pair;
     info->device_bytes_full_sa = ix->reps[0]->bytes_full_sa;
+    info->device_bytes_lean_sa = ix->reps[0]->bytes_lean;
     for (size_t i = 0; i < ix->reps.size() && i < 16; i++) info->devices[i] = ix->reps[i]->device;
   });
 }

@@ -488,7 +488,8 @@ uint64_t* locate_chunk_walk(Replica& r, Workspace* ws, uint64_t nq, uint64_t n_h
                             const uint64_t* d_hit_off, cudaStream_t st) {
   if (n_hits == 0) return nullptr;
   IndexView view = r.view;
-  if (g_locate_variant == 1) view.full_sa = nullptr;
+  if (g_locate_variant != 0) view.full_sa = nullptr;      // 1, 2: walk
+  if (g_locate_variant == 1) view.walk_blocks = nullptr;  // 1: to the file's row samples
   const uint2* d_sp_cnt = reinterpret_cast<const uint2*>(ws->d_out);
   uint64_t* d_hits = nullptr;
   CU(cudaMallocAsync(reinterpret_cast<void**>(&d_hits), n_hits * 16 + 16, st));  // pool: no driver round trip
@@ -1105,7 +1106,8 @@ int awry_host_threads(void) { return host_pool_threads(); }
 
 int awry_set_locate_variant(int variant) {
   return guarded([&] {
-    if (variant != 0 && variant != 1) fail(AWRY_ERR_INVALID_ARG, "locate variant must be 0 (default) or 1 (LF-walk)");
+    if (variant < 0 || variant > 2)
+      fail(AWRY_ERR_INVALID_ARG, "locate variant must be 0 (default), 1 (LF-walk to row samples) or 2 (bounded walk)");
     g_locate_variant = variant;
   });
 }

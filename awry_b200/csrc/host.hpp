@@ -272,6 +272,10 @@ struct Replica {
   uint2* d_table = nullptr;
   uint4* d_pair = nullptr;
   uint32_t* d_full_sa = nullptr;  // unsampled suffix array (locate accelerator)
+  uint4* d_walk = nullptr;        // memory-lean locate: walk blocks, mark ranks, position-sampled SA (layout.cuh)
+  uint32_t* d_walk_rank = nullptr;
+  uint32_t* d_pos_samples = nullptr;
+  size_t bytes_lean = 0;
   uint64_t* d_seq_starts = nullptr;
   unsigned long long* d_async_flag = nullptr;  // first bad query seen by *_device calls
   size_t bytes_blocks = 0, bytes_sa = 0, bytes_table = 0, bytes_pair = 0, bytes_full_sa = 0;

@@ -85,6 +85,12 @@ cudaError_t build_full_sa(const IndexView& ix, uint32_t* d_full, int sm_count, c
 // such a query is never loaded or stored.
 enum BadKind : unsigned { BAD_QUERY = 0, BAD_OFFSETS = 1 };
 __host__ __device__ inline unsigned long long bad_query_code(uint64_t q, unsigned kind) { return (q << 1) | kind; }
+// memory-lean bounded locate (nucleotide): walk blocks (planes + position marks), their mark ranks and the
+// position-sampled suffix array, all derived from the 1-step blocks and the file's row-sampled array
+uint64_t walk_block_count(uint64_t bwt_len);
+cudaError_t build_lean_sa(const IndexView& ix, uint4* d_walk, uint32_t* d_rank, uint32_t* d_pos, int sm_count,
+                          cudaStream_t s);
+
 cudaError_t launch_pack(int alphabet, const uint8_t* d_qbytes, const uint64_t* d_qoff, uint64_t nq,
                         uint64_t* d_qwords, uint64_t b_lo, uint64_t b_hi, unsigned long long* d_first_bad,
                         cudaStream_t s);

@@ -228,13 +228,52 @@ __global__ void __launch_bounds__(256) walk_amino_kernel(IndexView ix, uint64_t 
 // the sampled rows, so every row is written exactly once.  Same lane-group step as the walk kernels.
 constexpr uint64_t UNSAMPLE_TICKET = 32;  // sampled rows per ticket
 
+// What a walker does with (row, SA[row]) at every row it passes:
+//   UNSAMPLE_FULL   full[row] = SA[row]                                   (the unsampled array)
+//   UNSAMPLE_MARK   sets the mark bit of rows with SA[row] % ratio == 0   (walk blocks, pass 1)
+//   UNSAMPLE_POS    pos_samples[rank of the marked row] = SA[row] / ratio (pass 2, once the ranks exist)
+enum UnsampleMode { UNSAMPLE_FULL = 0, UNSAMPLE_MARK = 1, UNSAMPLE_POS = 2 };
+
+// word index (32-bit words) of row group g's planes inside a walk block: 4g .. 4g+2, mark = 4g+3
+__device__ __forceinline__ uint32_t* walk_mark_word(uint4* walk, uint32_t row, uint32_t& bit) {
+  const uint32_t blk = row / WALK_ROWS_PER_BLOCK, l = row - blk * WALK_ROWS_PER_BLOCK;
+  bit = l & 31;
+  return reinterpret_cast<uint32_t*>(walk + size_t(blk) * WALK_BLOCK_UINT4) + 4 * (l >> 5) + 3;
+}
+// marked rows before `row` inside its walk block (one thread; load time only)
+__device__ __forceinline__ uint32_t walk_marks_before(const uint4* walk, uint32_t row) {
+  const uint32_t blk = row / WALK_ROWS_PER_BLOCK, l = row - blk * WALK_ROWS_PER_BLOCK;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(walk + size_t(blk) * WALK_BLOCK_UINT4);
+  uint32_t n = 0;
+  for (uint32_t g = 0; g < (l >> 5); g++) n += __popc(w[4 * g + 3]);
+  return n + __popc(w[4 * (l >> 5) + 3] & ((1u << (l & 31)) - 1u));
+}
+
+template <int MODE>
+__device__ __forceinline__ void unsample_visit(const IndexView& ix, uint32_t row, uint32_t p, uint32_t* __restrict__ full,
+                                               uint4* __restrict__ walk, uint32_t* __restrict__ pos_samples) {
+  if (MODE == UNSAMPLE_FULL) {
+    full[row] = p;
+    return;
+  }
+  if (p % ix.sa_ratio != 0) return;
+  if (MODE == UNSAMPLE_MARK) {
+    uint32_t bit;
+    uint32_t* w = walk_mark_word(walk, row, bit);
+    atomicOr(w, 1u << bit);
+  } else {
+    pos_samples[ix.walk_rank[row / WALK_ROWS_PER_BLOCK] + walk_marks_before(walk, row)] = p / ix.sa_ratio;
+  }
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(256)
-    unsample_dna_kernel(IndexView ix, uint64_t n_elems, uint32_t* __restrict__ full) {
+    unsample_dna_kernel(IndexView ix, uint64_t n_elems, uint32_t* __restrict__ full, uint4* __restrict__ walk,
+                        uint32_t* __restrict__ pos_samples, unsigned long long* __restrict__ ticket) {
   constexpr uint32_t FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31, sub = lane & 1, gbase = lane - sub;
   // sampled rows are handed out dynamically, UNSAMPLE_TICKET at a time (walk lengths are geometric and the
-  // SMs do not all see the same random-access throughput); the counter sits behind the array
-  unsigned long long* const ticket = reinterpret_cast<unsigned long long*>(full + ((size_t(ix.bwt_len) + 3) & ~size_t(1)));
+  // SMs do not all see the same random-access throughput)
   uint64_t e = 0, e_end = 0;
   bool more = true;
   uint32_t row = 0, p = 0;
@@ -253,7 +292,7 @@ __global__ void __launch_bounds__(256)
       p = uint32_t(sa_sample(ix, row));
       e++;
       have = true;
-      if (sub == 0) full[row] = p;
+      if (sub == 0) unsample_visit<MODE>(ix, row, p, full, walk, pos_samples);
     }
     if (__all_sync(FULL, !have && !more && e == e_end)) break;
     const uint32_t blk = row >> 7, l = row & 127;
@@ -269,14 +308,14 @@ __global__ void __launch_bounds__(256)
     r += __shfl_xor_sync(FULL, r, 1);
     if (have) {
       if (c >= uint32_t(DNA_SENTINEL)) {
-        have = false;  // the '$' row (SA = 0, already written): LF would wrap to row 0, a sampled row
+        have = false;  // the '$' row (SA = 0, already visited): LF would wrap to row 0, a sampled row
       } else {
         row = c == uint32_t(DNA_N) ? lf_backstep<0>(ix, row) : ix.c_lo[c] + r - 1;
         p--;
         if (row_is_sampled(ix, row))
           have = false;
         else if (sub == 0)
-          full[row] = p;
+          unsample_visit<MODE>(ix, row, p, full, walk, pos_samples);
       }
     }
   }
@@ -349,12 +388,194 @@ cudaError_t build_full_sa(const IndexView& ix, uint32_t* d_full, int sm_count, c
   cudaError_t e0 = cudaMemsetAsync(d_full + ((size_t(ix.bwt_len) + 3) & ~size_t(1)), 0, 8, s);
   if (e0 != cudaSuccess) return e0;
   if (ix.alphabet == 0)
-    unsample_dna_kernel<<<grid, 256, 0, s>>>(ix, n_elems, d_full);
+    unsample_dna_kernel<UNSAMPLE_FULL><<<grid, 256, 0, s>>>(
+        ix, n_elems, d_full, nullptr, nullptr,
+        reinterpret_cast<unsigned long long*>(d_full + ((size_t(ix.bwt_len) + 3) & ~size_t(1))));
   else
     unsample_amino_kernel<<<grid, 256, 0, s>>>(ix, n_elems, d_full);
   COUNT_LAUNCH();
   return cudaGetLastError();
 }
+
+// ---- memory-lean bounded locate: walk blocks + position-sampled suffix array (layout.cuh) ----
+
+// planes of the 1-step blocks re-laid into walk blocks (a 32-row group of a walk block is exactly one 32-row
+// chunk of a 64-B block: 224 = 7 x 32), marks cleared; the thread of group 6 also ranks A, C, G, T up to the
+// block start.  One thread per (walk block, row group).
+__global__ void walk_planes_kernel(IndexView ix, uint4* __restrict__ walk, uint64_t n_wblocks) {
+  const uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (t >= n_wblocks * 7) return;
+  const uint64_t blk = t / 7;
+  const uint32_t g = uint32_t(t - blk * 7);
+  const uint64_t row0 = blk * WALK_ROWS_PER_BLOCK + 32 * g;
+  const uint64_t covered = ((uint64_t(ix.bwt_len) + 255) / 256) * 256;  // rows the 1-step blocks hold (padded with code 7)
+  uint4 ch = make_uint4(~0u, ~0u, ~0u, 0u);
+  if (row0 < covered) ch = ldg128(ix.blocks + size_t(row0 >> 7) * DNA_BLOCK_UINT4 + ((row0 >> 5) & 3));
+  uint32_t* w = reinterpret_cast<uint32_t*>(walk + blk * WALK_BLOCK_UINT4);
+  w[4 * g + 0] = ch.x;
+  w[4 * g + 1] = ch.y;
+  w[4 * g + 2] = ch.z;
+  w[4 * g + 3] = 0;
+  if (g == 6) {
+    const uint64_t start = blk * WALK_ROWS_PER_BLOCK;
+    uint32_t cnt[4] = {0, 0, 0, 0};
+    if (start != 0 && start - 1 < covered) {
+      const uint32_t pos = uint32_t(start - 1);
+      DnaBlockRegs b = dna_load_block(ix, pos >> 7);
+      for (uint32_t c = 0; c < 4; c++) cnt[c] = dna_occ_in_block(ix, b, pos >> 7, pos & 127, c);
+    }
+    for (int c = 0; c < 4; c++) w[28 + c] = cnt[c];
+  }
+}
+
+__global__ void walk_mark_counts_kernel(const uint4* __restrict__ walk, uint64_t n_wblocks, uint32_t* __restrict__ out) {
+  const uint64_t blk = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (blk >= n_wblocks) return;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(walk + blk * WALK_BLOCK_UINT4);
+  uint32_t n = 0;
+  for (int g = 0; g < 7; g++) n += __popc(w[4 * g + 3]);
+  out[blk] = n;
+}
+
+uint64_t walk_block_count(uint64_t bwt_len) { return (bwt_len + WALK_ROWS_PER_BLOCK - 1) / WALK_ROWS_PER_BLOCK; }
+
+// view: blocks / sa_words set; d_walk: walk_block_count x 128 B; d_rank: walk_block_count + 1 u32;
+// d_pos: ceil(bwt_len / ratio) + 2 u32 (the last two words serve as the walkers' ticket counter)
+cudaError_t build_lean_sa(const IndexView& ix, uint4* d_walk, uint32_t* d_rank, uint32_t* d_pos, int sm_count,
+                          cudaStream_t s) {
+  if (ix.alphabet != 0) return cudaErrorInvalidValue;
+  const uint64_t nb = walk_block_count(ix.bwt_len);
+  const uint64_t n_elems = (uint64_t(ix.bwt_len) + ix.sa_ratio - 1) / ix.sa_ratio;
+  walk_planes_kernel<<<unsigned((nb * 7 + 255) / 256), 256, 0, s>>>(ix, d_walk, nb);
+  COUNT_LAUNCH();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  unsigned long long* ticket = reinterpret_cast<unsigned long long*>(d_pos + ((n_elems + 1) & ~uint64_t(1)));
+  const unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (2 * n_elems + 255) / 256)));
+  if ((e = cudaMemsetAsync(ticket, 0, 8, s)) != cudaSuccess) return e;
+  unsample_dna_kernel<UNSAMPLE_MARK><<<grid, 256, 0, s>>>(ix, n_elems, nullptr, d_walk, nullptr, ticket);
+  COUNT_LAUNCH();
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  walk_mark_counts_kernel<<<unsigned((nb + 255) / 256), 256, 0, s>>>(d_walk, nb, d_rank);
+  COUNT_LAUNCH();
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  size_t tb = 0;
+  if ((e = cub::DeviceScan::ExclusiveSum(nullptr, tb, d_rank, d_rank, (long long)(nb + 1), s)) != cudaSuccess) return e;
+  void* d_temp = nullptr;
+  if ((e = cudaMalloc(&d_temp, tb + 16)) != cudaSuccess) return e;
+  e = cub::DeviceScan::ExclusiveSum(d_temp, tb, d_rank, d_rank, (long long)(nb + 1), s);
+  COUNT_LAUNCH();
+  if (e == cudaSuccess) e = cudaMemsetAsync(ticket, 0, 8, s);
+  if (e == cudaSuccess) {
+    IndexView v = ix;
+    v.walk_blocks = d_walk;
+    v.walk_rank = d_rank;
+    unsample_dna_kernel<UNSAMPLE_POS><<<grid, 256, 0, s>>>(v, n_elems, nullptr, d_walk, d_pos, ticket);
+    COUNT_LAUNCH();
+    e = cudaGetLastError();
+  }
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  cudaFree(d_temp);
+  return e != cudaSuccess ? e : e2;
+}
+
+// Pass 2b on the walk blocks: 4 lanes per hit, one LDG.256 each = ONE line request per LF step; the lane
+// that holds the row's 32-row group extracts the symbol and the mark bit and broadcasts them.  A marked row
+// ends the walk: its rank among the marked rows (walk_rank + the marks before it in the block, already in
+// registers) indexes the position samples, and the hit is sample * ratio + steps.  At most ratio - 1 steps, no
+// wrap through the '$' row (text position 0 is marked).  Hits are handed out to a WARP in runs of consecutive
+// hit numbers (a pool in registers topped up with one atomic): the hits of a long interval are consecutive BWT
+// rows whose walks stay next to each other while their BWT symbols agree, so their block reads fall into the
+// same lines of the same load instruction and are served by one request (repeat-rich text, BASELINE cfg5).
+constexpr uint32_t LEAN_TICKET = 64;  // hits per warp ticket
+
+template <bool MAP>
+__global__ void __launch_bounds__(256) walk_lean_kernel(IndexView ix, uint64_t n_hits, uint64_t* __restrict__ out) {
+  constexpr int SLOT = MAP ? 2 : 1;
+  constexpr uint32_t FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31, sub = lane & 3, gbase = lane - sub;
+  const uint32_t gmask = 0xfu << gbase;
+  unsigned long long* const ticket = reinterpret_cast<unsigned long long*>(out + SLOT * n_hits);
+  uint64_t pn = 0, pe = 0;  // the warp's pool of hit numbers
+  bool more = true;
+  uint64_t cur = 0;
+  uint32_t row = 0, steps = 0;
+  bool have = false;
+  for (;;) {
+    const uint32_t wmask = __ballot_sync(FULL, !have && sub == 0);
+    if (wmask != 0 && (pn != pe || more)) {
+      const uint32_t n_want = __popc(wmask);
+      if (pe - pn < n_want && more) {  // top the pool up (the few hits left in it are taken first)
+        // (pool ranges are contiguous only within one ticket: drain the old one before drawing)
+        if (pn == pe) {
+          unsigned long long t = 0;
+          if (lane == 0) t = atomicAdd(ticket, (unsigned long long)LEAN_TICKET);
+          t = __shfl_sync(FULL, t, 0);
+          more = t < n_hits;
+          pn = more ? t : 0;
+          pe = more ? (n_hits - t < LEAN_TICKET ? n_hits : t + LEAN_TICKET) : 0;
+        }
+      }
+      const uint32_t r = __popc(wmask & ((1u << gbase) - 1u));
+      if (!have && pn + r < pe) {
+        cur = pn + r;
+        row = uint32_t(out[SLOT * cur]);
+        steps = 0;
+        have = true;
+      }
+      pn = pn + n_want < pe ? pn + n_want : pe;
+    }
+    if (__all_sync(FULL, !have && pn == pe && !more)) break;
+    const uint32_t blk = (row >> 5) / 7u;  // / 224
+    const uint32_t l = row - blk * WALK_ROWS_PER_BLOCK;
+    u32x8 x;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x.v[i] = 0;
+    if (have) x = ldg256(ix.walk_blocks + size_t(blk) * WALK_BLOCK_UINT4 + 2 * sub);
+    // the lane that holds the row's group reads its code and mark
+    const uint32_t g = l >> 5, t = l & 31, half = g & 1;
+    const uint32_t p0 = half ? x.v[4] : x.v[0], p1 = half ? x.v[5] : x.v[1], p2 = half ? x.v[6] : x.v[2],
+                   mk = half ? x.v[7] : x.v[3];
+    uint32_t cm = ((p0 >> t) & 1u) | (((p1 >> t) & 1u) << 1) | (((p2 >> t) & 1u) << 2) | (((mk >> t) & 1u) << 3);
+    cm = __shfl_sync(FULL, cm, gbase + (g >> 1));
+    const uint32_t c = cm & 7u;
+    const bool marked = have && (cm & 8u);
+    // rows of this lane's groups at or before the row: group 2*sub (words 0..3) and 2*sub+1 (words 4..7);
+    // lane 3 holds group 6 only (its words 4..7 are the counts)
+    const uint32_t ma = low_mask(int(l) + 1 - int(64 * sub)), mb = sub < 3 ? low_mask(int(l) + 1 - int(64 * sub + 32)) : 0u;
+    uint32_t r = 0;
+    if (have) {
+      if (marked) {  // marks strictly before the row
+        const uint32_t below_a = low_mask(int(l) - int(64 * sub)), below_b = sub < 3 ? low_mask(int(l) - int(64 * sub + 32)) : 0u;
+        r = __popc(x.v[3] & below_a) + __popc(x.v[7] & below_b);
+      } else if (c < 4) {
+        const uint32_t m0 = (c & 1) ? ~0u : 0u, m1 = (c & 2) ? ~0u : 0u;
+        r = __popc(~x.v[2] & ~(x.v[0] ^ m0) & ~(x.v[1] ^ m1) & ma) + __popc(~x.v[6] & ~(x.v[4] ^ m0) & ~(x.v[5] ^ m1) & mb);
+        if (sub == 3) r += c == 0 ? x.v[4] : c == 1 ? x.v[5] : c == 2 ? x.v[6] : x.v[7];
+      }
+    }
+    r += __shfl_xor_sync(FULL, r, 1);
+    r += __shfl_xor_sync(FULL, r, 2);
+    if (have) {
+      if (marked) {
+        if (sub == 0) {
+          const uint64_t loc = uint64_t(__ldg(ix.pos_samples + __ldg(ix.walk_rank + blk) + r)) * ix.sa_ratio + steps;
+          if (MAP)
+            map_location(ix, loc, out + SLOT * cur);
+          else
+            out[cur] = loc;
+        }
+        have = false;
+      } else {
+        // (a '$' row is always marked -- text position 0 -- so c is A, C, G, T or N here)
+        row = c < 4 ? ix.c_lo[c] + r - 1 : lf_backstep<0>(ix, row);
+        steps++;
+      }
+    }
+  }
+  (void)gmask;
+}
+
 
 // Locate pass 2 on the unsampled array: hit i of query q is SA[sp + i] -- no walk.  Same work split as
 // expand_rows_kernel: a lane copies the first 8 hits of its query, longer intervals are copied by the
@@ -504,7 +725,13 @@ cudaError_t launch_walk(const IndexView& ix, const uint2* d_sp_cnt, const uint64
     cudaError_t e = cudaMemsetAsync(out + (map ? 2 : 1) * n_hits, 0, 8, s);
     if (e != cudaSuccess) return e;
   }
-  if (ix.alphabet == 0) {
+  if (ix.alphabet == 0 && ix.walk_blocks != nullptr) {  // bounded walk on the position-sampled array
+    unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (4 * n_hits + 255) / 256)));
+    if (map)
+      walk_lean_kernel<true><<<grid, 256, 0, s>>>(ix, n_hits, out);
+    else
+      walk_lean_kernel<false><<<grid, 256, 0, s>>>(ix, n_hits, out);
+  } else if (ix.alphabet == 0) {
     unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (2 * n_hits + 255) / 256)));
     const bool dynamic = n_hits >= 64 * ((uint64_t(grid) * 256) >> 1);
     if (map)

@@ -25,6 +25,19 @@
 //                 C2[a,b] = C[b] + Occ(b, C[a]-1)
 //               (two applications of fm_index.rs:559-582 composed).
 //
+//   NUCLEOTIDE WALK BLOCKS + POSITION-SAMPLED SA (memory-lean locate; derived at load time)
+//               The file samples the suffix array by ROW (row % ratio == 0, compressed_suffix_array.rs:109-111),
+//               so a walk is geometric and unbounded.  Sampling by TEXT POSITION (SA[row] % ratio == 0) bounds
+//               it by ratio - 1 steps; it needs a mark bit per row and a rank over the marks.
+//               block = 224 BWT rows = 128 B = 4 lane slices of 32 B (one LDG.256 each)
+//               words 4g .. 4g+3 (g = 0..6) = { p0, p1, p2, mark } of rows 32g .. 32g+31
+//               (p_b = bit-plane b of the device row code, mark bit t = "SA[row 32g+t] % ratio == 0")
+//               words 28 .. 31 = #A, #C, #G, #T in BWT[0 .. block start)
+//               slice t < 3 holds row groups 2t and 2t+1, slice 3 holds group 6 and the counts: the BWT symbol,
+//               its rank AND the stop test of an LF step come from ONE aligned 128-B line.
+//               walk_rank[blk] = marked rows before the block; pos_samples[i] = SA[i-th marked row] / ratio.
+//               4.57 + 32/ratio bits per row (3.3 GB at 3.1 G rows, ratio 8) against 32 for the unsampled array.
+//
 //   AMINO       block = 64 rows = 128 B = 4 lane slices of 32 B (one LDG.256 each; one line per step)
 //               slice t < 2 = { p0..p4 of rows 32t..32t+31, cnt[3t], cnt[3t+1], cnt[3t+2] }
 //               slice 2     = { cnt[6] .. cnt[13] },  slice 3 = { cnt[14] .. cnt[21] }
@@ -47,6 +60,7 @@ constexpr int AMINO_X = 20, AMINO_SENTINEL = 0;
 constexpr uint32_t DNA_ROWS_PER_BLOCK = 128, DNA_BLOCK_UINT4 = 4;
 constexpr uint32_t AMINO_ROWS_PER_BLOCK = 64, AMINO_BLOCK_UINT4 = 8;
 constexpr uint32_t PAIR_ROWS_PER_BLOCK = 96, PAIR_BLOCK_UINT4 = 8;
+constexpr uint32_t WALK_ROWS_PER_BLOCK = 224, WALK_BLOCK_UINT4 = 8;
 
 struct IndexView {
   const uint4* __restrict__ blocks;
@@ -55,6 +69,9 @@ struct IndexView {
   const uint64_t* __restrict__ seq_starts;
   const uint4* __restrict__ pair_blocks;   // nucleotide two-step accelerator, or nullptr
   const uint32_t* __restrict__ full_sa;    // unsampled suffix array (locate accelerator), or nullptr
+  const uint4* __restrict__ walk_blocks;   // nucleotide walk blocks (planes + position marks), or nullptr
+  const uint32_t* __restrict__ walk_rank;  // marked rows before each walk block
+  const uint32_t* __restrict__ pos_samples;  // SA[marked row] / ratio, in row order
   uint32_t c2[16];                         // C2[4a+b]
   uint32_t c_lo[24];                       // C[c]      by device symbol (search.rs:43-48)
   uint32_t c_hi[24];                       // C[c+1]-1  by device symbol

@@ -80,6 +80,7 @@ class _Info(C.Structure):
                 ("n_sequences", C.c_uint64), ("device_bytes_blocks", C.c_uint64),
                 ("device_bytes_sa", C.c_uint64), ("device_bytes_table", C.c_uint64),
                 ("device_bytes_pair", C.c_uint64), ("device_bytes_full_sa", C.c_uint64),
+                ("device_bytes_lean_sa", C.c_uint64),
                 ("devices", C.c_int32 * 16)]
 
 
@@ -317,7 +318,7 @@ class FmIndex:
     def device_bytes(self) -> dict:
         return {"blocks": int(self._info.device_bytes_blocks), "sa": int(self._info.device_bytes_sa),
                 "table": int(self._info.device_bytes_table), "pair": int(self._info.device_bytes_pair),
-                "full_sa": int(self._info.device_bytes_full_sa)}
+                "full_sa": int(self._info.device_bytes_full_sa), "lean_sa": int(self._info.device_bytes_lean_sa)}
 
     def sequence_header(self, seq_idx: int) -> str:
         p, n = C.c_char_p(), C.c_uint64()
@@ -566,7 +567,8 @@ def set_search_variant(lanes: int = 0, tpb: int = 0, blocks_per_sm: int = 0):
 
 
 def set_locate_variant(variant: int = 0):
-    """0 = gather from the unsampled suffix array when the index holds one (default); 1 = always LF-walk."""
+    """0 = the best pass 2 the index holds (unsampled-SA gather, else the bounded walk on the position-sampled
+    array, else the LF-walk); 1 = always LF-walk to the file's row samples; 2 = the bounded walk if present."""
     _check(native().awry_set_locate_variant(variant))
 
 

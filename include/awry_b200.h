@@ -71,6 +71,7 @@ typedef struct awry_info {
   uint64_t device_bytes_table;
   uint64_t device_bytes_pair;   /* nucleotide two-symbol accelerator blocks */
   uint64_t device_bytes_full_sa; /* unsampled suffix array (locate accelerator), 0 if not built */
+  uint64_t device_bytes_lean_sa; /* walk blocks + position-sampled suffix array (bounded locate), 0 if not built */
   int32_t devices[16];
 } awry_info;
 
@@ -299,11 +300,16 @@ int awry_bench_random_gather(int device, uint64_t footprint_bytes, uint32_t gran
  * blocks_per_sm caps residency. */
 int awry_set_search_variant(int lanes_per_query, int threads_per_block, int blocks_per_sm);
 
-/* Locate pass 2.  When memory allows (AWRY_B200_FULL_SA=0 disables, =1 forces) the index keeps the
- * UNSAMPLED suffix array, rebuilt on the device at load time from the sampled one
- * (compressed_suffix_array.rs:109-111) with one LF step per BWT row, and a hit is one read of SA[row]
- * instead of the LF-walk of fm_index.rs:521-537; results are identical.  variant 0 = use it when
- * present (default), 1 = always LF-walk to the sampled rows (the memory-lean path). */
+/* Locate pass 2.  Three ways to turn a BWT row into a text position, identical results:
+ *   (a) the UNSAMPLED suffix array, rebuilt on the device at load time from the file's sampled one
+ *       (compressed_suffix_array.rs:109-111) with one LF step per BWT row: a hit is one read of SA[row]
+ *       instead of the LF-walk of fm_index.rs:521-537.  32 bits per row; kept when it takes < 1/3 of the free
+ *       memory (AWRY_B200_FULL_SA=0 never, =1 whenever it fits);
+ *   (b) nucleotide, when (a) is absent (or AWRY_B200_LEAN_SA=1): the suffix array sampled by TEXT POSITION
+ *       (SA[row] % ratio == 0) with a mark bit per row, both derived at load time: an LF-walk of at most
+ *       ratio - 1 steps, 4.57 + 32/ratio bits per row (without a new file format);
+ *   (c) the reference's own scheme: LF-walk to the next ROW the file sampled (geometric walk lengths).
+ * variant 0 = the best one present (default), 1 = always (c), 2 = (b) if present, else (c). */
 int awry_set_locate_variant(int variant);
 
 /* Host-side query packing (nucleotide): the *_batch calls turn ASCII bases into 2-bit codes on the host

@@ -38,6 +38,7 @@ pub struct awry_info {
     pub device_bytes_table: u64,
     pub device_bytes_pair: u64,
     pub device_bytes_full_sa: u64,
+    pub device_bytes_lean_sa: u64,
     pub devices: [i32; 16],
 }
 

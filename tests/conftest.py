@@ -10,6 +10,12 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# every index the GPU tests create also gets the memory-lean locate structures (walk blocks + position-sampled
+# suffix array), which the library otherwise only builds when the unsampled array does not fit: the
+# `locate_variant` fixtures then run all three pass-2 schemes on the same handle
+os.environ.setdefault("AWRY_B200_LEAN_SA", "1")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

@@ -52,7 +52,7 @@ def _run_config(fx, po, alphabet, n, k, ratio, count_nq, count_len, loc_nq, loc_
         ix.count_device(d_q.data_ptr(), d_off.data_ptr(), loc_nq, d_cnt.data_ptr(), st)
         assert ix.device_bytes()["full_sa"] == 4 * parts.bwt_len
         all_hits = []
-        for variant in (1, 0):      # LF-walk to the sampled rows, then the unsampled-SA gather
+        for variant in ((1, 2, 0) if alphabet == 0 else (1, 0)):   # LF-walk, bounded walk, unsampled-SA gather
             f.set_locate_variant(variant)
             try:
                 ptr, n_hits = ix.locate_device(d_q.data_ptr(), d_off.data_ptr(), loc_nq, d_hoff.data_ptr(), stream=st)
@@ -66,8 +66,9 @@ def _run_config(fx, po, alphabet, n, k, ratio, count_nq, count_len, loc_nq, loc_
             assert rc == 0
             ix.device_free(ptr)
             all_hits.append(buf.cpu().numpy().view(np.uint64).reshape(-1, 2))
-        hits = all_hits[1]
-        assert np.array_equal(all_hits[0], hits)            # both pass-2 variants agree on every hit
+        hits = all_hits[-1]
+        for other in all_hits[:-1]:
+            assert np.array_equal(other, hits)              # all pass-2 variants agree on every hit
         assert int(hits[:, 0].max()) == 0 and int(hits[:, 1].max()) <= n - loc_len
         # round trip on a strided sample of hits: text at the hit == the query that produced it
         step = max(1, n_hits // 200_000)
@@ -108,3 +109,55 @@ def test_cfg1_plumbing_1mbp_k13(fx, po):
         off, hits = ix.locate_packed(qb, qo, sorted_hits=True)
         woff, whits, _ = orc.locate_batch(qb, qo, sorted_hits=True)
         assert np.array_equal(off, woff) and np.array_equal(hits, whits)
+
+
+def test_cfg5_repeat_rich_1gbp_ratio32(po):
+    """cfg5 at scale: 1 Gbp repeat-rich DNA, SA ratio 32, 1 M x 50-bp queries whose hit counts run from 1 to
+    > 10^4.  The bounded walk (position-sampled array), the unsampled-SA gather and, on a prefix, the oracle
+    agree on every hit; count totals equal hit totals."""
+    import ctypes as C
+    import torch
+    from awry_b200 import FmIndex, fm_index as f
+    from fixtures import pyfixture_gpu as fxg, repeats
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100e9:
+        pytest.skip("needs ~100 GB of free HBM")
+    n, nq, L = 1_000_000_000, 1_000_000, 50
+    fams = ((300, 100_010, 0.15), (6000, 20_005, 0.15))
+    text, regions = repeats.repeat_rich_text(n, seed=8, tandem_arrays=40, families=fams)
+    parts, _ = fxg.build_parts(0, n, 0, ratio=32, kmer_len=13, host_text=text)
+    qb, qo = repeats.repeat_queries(text, regions, nq, L, seed=9)
+    del text
+    st = torch.cuda.current_stream().cuda_stream
+    cudart = C.CDLL("libcudart.so")
+    with FmIndex.from_parts(parts.alphabet, parts.ratio, parts.bwt_len, parts.kmer_len, parts.blocks,
+                            parts.prefix_sums, parts.sa_words) as ix:
+        assert ix.device_bytes()["lean_sa"] > 0 and ix.device_bytes()["full_sa"] > 0
+        d_q = torch.from_numpy(qb).cuda()
+        d_off = torch.from_numpy(qo.astype(np.int64)).cuda()
+        d_cnt = torch.zeros(nq, dtype=torch.int64, device="cuda")
+        d_hoff = torch.zeros(nq + 1, dtype=torch.int64, device="cuda")
+        ix.count_device(d_q.data_ptr(), d_off.data_ptr(), nq, d_cnt.data_ptr(), st)
+        total = int(d_cnt.sum())
+        assert int(d_cnt.max()) > 10_000 and int(d_cnt.min()) == 1
+        bufs = []
+        for variant in (2, 0):
+            f.set_locate_variant(variant)
+            try:
+                ptr, n_hits = ix.locate_device(d_q.data_ptr(), d_off.data_ptr(), nq, d_hoff.data_ptr(), stream=st)
+            finally:
+                f.set_locate_variant(0)
+            assert n_hits == total
+            assert torch.equal(d_hoff[1:] - d_hoff[:-1], d_cnt)
+            buf = torch.empty(n_hits * 2, dtype=torch.int64, device="cuda")
+            assert cudart.cudaMemcpy(C.c_void_p(buf.data_ptr()), C.c_void_p(ptr), C.c_size_t(n_hits * 16), 3) == 0
+            ix.device_free(ptr)
+            bufs.append(buf)
+        assert torch.equal(bufs[0], bufs[1])
+        ns = 2000
+        orc = po.OracleIndex.from_parts(parts.alphabet, parts.ratio, parts.bwt_len, parts.kmer_len, parts.blocks,
+                                        parts.prefix_sums, parts.sa_words)
+        woff, whits, _ = orc.locate_batch(qb[: ns * L], qo[: ns + 1])
+        assert np.array_equal(d_hoff[: ns + 1].cpu().numpy().view(np.uint64), woff)
+        got = bufs[0][: 2 * int(woff[-1])].cpu().numpy().view(np.uint64).reshape(-1, 2)
+        assert np.array_equal(got, whits)

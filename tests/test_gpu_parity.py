@@ -51,10 +51,10 @@ def host_pack_mode(request):
     f.set_host_pack(-1)
 
 
-@pytest.fixture(params=[0, 1], ids=["unsampled_sa", "lf_walk"])
+@pytest.fixture(params=[0, 1, 2], ids=["unsampled_sa", "lf_walk", "bounded_walk"])
 def locate_variant(request):
-    """locate pass 2 both ways: gather from the unsampled suffix array (default when it fits) and the
-    LF-walk to the sampled rows (fm_index.rs:521-537)"""
+    """locate pass 2 all three ways: gather from the unsampled suffix array (default when it fits), the
+    LF-walk to the sampled rows (fm_index.rs:521-537), and the bounded walk on the position-sampled array"""
     from awry_b200 import fm_index as f
     f.set_locate_variant(request.param)
     yield request.param
@@ -129,6 +129,7 @@ def test_locate_parity(fx, po, ratio, locate_variant):
     qb, qo = f.pack_queries(qs)
     with device_from_parts(parts) as ix:
         assert ix.device_bytes()["full_sa"] == (4 * parts.bwt_len if ratio > 1 else 0)
+        assert (ix.device_bytes()["lean_sa"] > 0) == (ratio > 1)
         off, hits = ix.locate_packed(qb, qo)
         woff, whits, _ = orc.locate_batch(qb, qo)
         assert np.array_equal(off, woff)

@@ -220,3 +220,37 @@ def test_one_batch_over_several_replicas(fx, dna, dna_or):
     finally:
         f.set_host_pack(-1)
         f.set_host_threads(0)
+
+
+@pytest.mark.parametrize("ratio", [2, 7, 8, 32, 64])
+def test_bounded_walk_is_the_default_without_the_unsampled_array(fx, po, monkeypatch, ratio):
+    """without the 4-byte-per-row array (AWRY_B200_FULL_SA=0) locate uses the suffix array
+    sampled by text position -- every walk ends within ratio - 1 steps -- and returns what the reference's
+    row-sampled walk returns, hit for hit, in BWT-row order.  Multi-record text with N runs included."""
+    from awry_b200 import fm_index as f
+    monkeypatch.setenv("AWRY_B200_FULL_SA", "0")
+    monkeypatch.delenv("AWRY_B200_LEAN_SA", raising=False)
+    recs = [bytes(fx.gen_text(0, n, 40 + i)) for i, n in enumerate([5000, 223, 224, 225, 1, 30_000, 447])]
+    recs[5] = recs[5][:1000] + b"NNNNNNNNNN" + recs[5][1010:]
+    text, starts = fx.concat_records(recs, 0)
+    parts = fx.build_parts(text, 0, ratio=ratio, kmer_len=5, seq_starts=starts, headers=[f"r{i}" for i in range(len(recs))])
+    orc = oracle_from_parts(po, parts)
+    qs = []
+    for r in recs:
+        qs += [r[i:i + 9] for i in range(0, max(1, len(r) - 9), 97)] + [r[:3], r[-2:]]
+    qs += [b"A", b"C", b"N", b"NN", b"AN", b"TTTT", b"ACG"]
+    qb, qo = f.pack_queries(qs)
+    woff, whits, _ = orc.locate_batch(qb, qo)
+    with device_from_parts(parts) as ix:
+        assert ix.device_bytes()["full_sa"] == 0 and ix.device_bytes()["lean_sa"] > 0
+        off, hits = ix.locate_packed(qb, qo)
+        assert np.array_equal(off, woff) and np.array_equal(hits, whits)
+        soff, shits = ix.locate_packed(qb, qo, sorted_hits=True)
+        woff2, whits2, _ = orc.locate_batch(qb, qo, sorted_hits=True)
+        assert np.array_equal(soff, woff2) and np.array_equal(shits, whits2)
+        f.set_locate_variant(1)                                  # the reference's own scheme on the same handle
+        try:
+            off1, hits1 = ix.locate_packed(qb, qo)
+        finally:
+            f.set_locate_variant(0)
+        assert np.array_equal(off1, woff) and np.array_equal(hits1, whits)
