@@ -84,7 +84,9 @@ void set_view_constants(awry_index* ix, Replica& r) {
   v.walk_rank = r.d_walk_rank;
   v.pos_samples = r.d_pos_samples;
   for (int i = 0; i < 16; i++) v.c2[i] = r.c2[i];
-  v.bwt_len = uint32_t(ix->bwt_len);
+  v.bwt_len = ix->wide ? 0xffffffffu : uint32_t(ix->bwt_len);
+  v.dollar_row = ix->wide ? 0xffffffffu : uint32_t(r.dollar_row);
+  v.wide = ix->wide ? &r.wview : nullptr;
   v.sa_ratio = uint32_t(ix->sa_ratio);
   v.sa_pow2 = (ix->sa_ratio & (ix->sa_ratio - 1)) == 0 ? 1u : 0u;
   v.sa_ratio_shift = v.sa_pow2 ? uint32_t(__builtin_ctzll(ix->sa_ratio)) : 0u;
@@ -106,6 +108,37 @@ void set_view_constants(awry_index* ix, Replica& r) {
       v.c_hi[s] = uint32_t(ix->prefix_sums[s + 1] - 1);
     }
   }
+  if (ix->wide) {
+    WideView& w = r.wview;
+    w.blocks = r.d_blocks;
+    w.sa_words = r.d_sa;
+    w.table = r.d_table_w;
+    w.seq_starts = r.d_seq_starts;
+    w.sb_counts = r.d_sb;
+    w.bwt_len = ix->bwt_len;
+    w.dollar_row = r.dollar_row;
+    w.sa_ratio = v.sa_ratio;
+    w.sa_pow2 = v.sa_pow2;
+    w.sa_ratio_shift = v.sa_ratio_shift;
+    w.sa_bits = v.sa_bits;
+    w.kmer_len = v.kmer_len;
+    w.n_seqs = v.n_seqs;
+    w.alphabet = v.alphabet;
+    w.sb_shift = ix->sb_shift;
+    for (int i = 0; i < 24; i++) w.c_lo[i] = 1, w.c_hi[i] = 0;
+    if (ix->alphabet == AWRY_NUCLEOTIDE) {
+      static const int ref_of_dsym[6] = {1, 2, 3, 5, 4, 0};  // A C G T N $
+      for (int d = 0; d < 6; d++) {
+        w.c_lo[d] = ix->prefix_sums[ref_of_dsym[d]];
+        w.c_hi[d] = ix->prefix_sums[ref_of_dsym[d] + 1] - 1;
+      }
+    } else {
+      for (int s2 = 0; s2 < 22; s2++) {
+        w.c_lo[s2] = ix->prefix_sums[s2];
+        w.c_hi[s2] = ix->prefix_sums[s2 + 1] - 1;
+      }
+    }
+  }
 }
 
 // Streams the reference-layout blocks through a pinned double buffer and re-lays them out on
@@ -120,9 +153,18 @@ void build_replica0(awry_index* ix, Replica& r, Source& src_blocks_then_rest, bo
   r.bytes_blocks = size_t(n_ref_blocks) * (ix->alphabet == AWRY_NUCLEOTIDE ? 128 : 512);
   CU(cudaMalloc(reinterpret_cast<void**>(&r.d_blocks), r.bytes_blocks + 256));
   CU(cudaMemset(r.d_blocks, 0, r.bytes_blocks + 256));
-  unsigned int* d_dollar = nullptr;
-  CU(cudaMalloc(reinterpret_cast<void**>(&d_dollar), 4));
-  CU(cudaMemset(d_dollar, 0xff, 4));
+  unsigned long long* d_dollar = nullptr;
+  CU(cudaMalloc(reinterpret_cast<void**>(&d_dollar), 8));
+  CU(cudaMemset(d_dollar, 0xff, 8));
+  // wide index: the u32 block counts become relative to superblocks of 2^sb_shift rows; the absolute counts of
+  // a superblock are the milestones of its first reference block (fm_index.rs:212-217), picked up as the
+  // blocks stream by
+  const uint32_t sbs = ix->sb_shift;
+  const uint64_t rb_per_sb = 1ull << (sbs - 8);
+  if (ix->wide) {
+    CU(cudaMalloc(reinterpret_cast<void**>(&r.d_sb), ix->n_superblocks() * SB_STRIDE * 8));
+    CU(cudaMemset(r.d_sb, 0, ix->n_superblocks() * SB_STRIDE * 8));
+  }
 
   cudaStream_t st;
   CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -138,21 +180,26 @@ void build_replica0(awry_index* ix, Replica& r, Source& src_blocks_then_rest, bo
     CU(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
   }
   int slot = 0;
-  if (src_blocks_then_rest.dev_blocks)
-    CU(launch_transpose(ix->alphabet, src_blocks_then_rest.dev_blocks, 0, n_ref_blocks, ix->bwt_len, r.d_blocks, d_dollar, st));
+  if (src_blocks_then_rest.dev_blocks) {
+    if (ix->wide) CU(launch_gather_superblocks(ix->alphabet, src_blocks_then_rest.dev_blocks, 0, n_ref_blocks, sbs, r.d_sb, st));
+    CU(launch_transpose(ix->alphabet, src_blocks_then_rest.dev_blocks, 0, n_ref_blocks, ix->bwt_len, r.d_blocks, d_dollar,
+                        r.d_sb, sbs, st));
+  }
   for (uint64_t b0 = 0; b0 < n_ref_blocks && !src_blocks_then_rest.dev_blocks; b0 += chunk_blocks, slot ^= 1) {
     uint64_t nb = std::min(chunk_blocks, n_ref_blocks - b0);
     CU(cudaEventSynchronize(ev[slot]));
     src_blocks_then_rest.read(h_stage[slot], nb * ref_block_bytes, "bwt blocks");
     CU(cudaMemcpyAsync(d_stage[slot], h_stage[slot], nb * ref_block_bytes, cudaMemcpyHostToDevice, st));
-    CU(launch_transpose(ix->alphabet, d_stage[slot], b0, nb, ix->bwt_len, r.d_blocks, d_dollar, st));
+    if (ix->wide && ((b0 + rb_per_sb - 1) / rb_per_sb) * rb_per_sb < b0 + nb)  // a superblock starts in this chunk
+      CU(launch_gather_superblocks(ix->alphabet, d_stage[slot], b0, nb, sbs, r.d_sb, st));
+    CU(launch_transpose(ix->alphabet, d_stage[slot], b0, nb, ix->bwt_len, r.d_blocks, d_dollar, r.d_sb, sbs, st));
     CU(cudaEventRecord(ev[slot], st));
   }
   CU(cudaStreamSynchronize(st));
-  unsigned int dollar = 0;
-  CU(cudaMemcpy(&dollar, d_dollar, 4, cudaMemcpyDeviceToHost));
+  unsigned long long dollar = 0;
+  CU(cudaMemcpy(&dollar, d_dollar, 8, cudaMemcpyDeviceToHost));
   cudaFree(d_dollar);
-  if (dollar == 0xffffffffu) fail(AWRY_ERR_FORMAT, "no sentinel row found in the BWT blocks");
+  if (dollar == ~0ull) fail(AWRY_ERR_FORMAT, "no sentinel row found in the BWT blocks");
 
   // prefix sums (fm_index_file.rs:265-270)
   src_blocks_then_rest.read(ix->prefix_sums, size_t(ix->card + 1) * 8, "prefix sums");
@@ -200,7 +247,7 @@ void build_replica0(awry_index* ix, Replica& r, Source& src_blocks_then_rest, bo
 
   // sequence starts on the device (filled by the caller into ix->seq_starts before this returns
   // for parts; for files they follow the table -- read by the caller after this function)
-  r.view.dollar_row = dollar;
+  r.dollar_row = dollar;
   CU(cudaStreamDestroy(st));
 }
 
@@ -235,12 +282,19 @@ void finish_replica0(awry_index* ix, Replica& r) {
   size_t free_b = 0, total_b = 0;
   CU(cudaMemGetInfo(&free_b, &total_b));
   if (const char* e = getenv("AWRY_B200_KMER_DEV")) k = std::min<uint32_t>(uint32_t(std::max(0l, strtol(e, nullptr, 10))), cap);  // experiments
-  while (k > 0 && table_entries(ix->alphabet, k) * 8 > free_b / 4) k--;
+  const size_t entry_bytes = ix->wide ? 16 : 8;
+  while (k > 0 && table_entries(ix->alphabet, k) * entry_bytes > free_b / 4) k--;
   ix->kmer_len_dev = k;
-  uint32_t dollar = r.view.dollar_row;
   set_view_constants(ix, r);
-  r.view.dollar_row = dollar;
-  if (k > 0) {
+  if (k > 0 && ix->wide) {
+    r.bytes_table = table_entries(ix->alphabet, k) * entry_bytes;
+    CU(cudaMalloc(reinterpret_cast<void**>(&r.d_table_w), r.bytes_table));
+    r.wview.table = r.d_table_w;
+    WideView v = r.wview;
+    v.kmer_len = 0;
+    CU(launch_build_table_wide(v, r.d_table_w, k, nullptr));
+    CU(cudaDeviceSynchronize());
+  } else if (k > 0) {
     r.bytes_table = table_entries(ix->alphabet, k) * 8;
     CU(cudaMalloc(reinterpret_cast<void**>(&r.d_table), r.bytes_table));
     r.view.table = r.d_table;
@@ -249,6 +303,7 @@ void finish_replica0(awry_index* ix, Replica& r) {
     CU(launch_build_table(v, r.d_table, k, nullptr));
     CU(cudaDeviceSynchronize());
   }
+  if (ix->wide) return;  // the pair index, the unsampled array and the walk blocks are 32-bit structures
   // nucleotide pair index: two query symbols per block access (AWRY_B200_PAIR_INDEX=0 disables)
   const char* env = getenv("AWRY_B200_PAIR_INDEX");
   bool want_pair = ix->alphabet == AWRY_NUCLEOTIDE && !(env && env[0] == '0') && !g_skip_accelerators;
@@ -319,10 +374,19 @@ void clone_replica(awry_index* ix, const Replica& src, Replica& dst) {
   CU(cudaMemcpyPeer(dst.d_blocks, dst.device, src.d_blocks, src.device, src.bytes_blocks + 256));
   CU(cudaMemcpyPeer(dst.d_sa, dst.device, src.d_sa, src.device, src.bytes_sa));
   CU(cudaMemcpyPeer(dst.d_seq_starts, dst.device, src.d_seq_starts, src.device, ix->seq_starts.size() * 8));
-  if (src.bytes_table) {
+  if (src.bytes_table && ix->wide) {
+    CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_table_w), src.bytes_table));
+    CU(cudaMemcpyPeer(dst.d_table_w, dst.device, src.d_table_w, src.device, src.bytes_table));
+  } else if (src.bytes_table) {
     CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_table), src.bytes_table));
     CU(cudaMemcpyPeer(dst.d_table, dst.device, src.d_table, src.device, src.bytes_table));
   }
+  if (ix->wide) {
+    const size_t sbb = ix->n_superblocks() * SB_STRIDE * 8;
+    CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_sb), sbb));
+    CU(cudaMemcpyPeer(dst.d_sb, dst.device, src.d_sb, src.device, sbb));
+  }
+  dst.dollar_row = src.dollar_row;
   if (src.bytes_pair) {
     dst.bytes_pair = src.bytes_pair;
     CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_pair), src.bytes_pair + 256));
@@ -345,9 +409,7 @@ void clone_replica(awry_index* ix, const Replica& src, Replica& dst) {
     CU(cudaMemcpyPeer(dst.d_walk_rank, dst.device, src.d_walk_rank, src.device, size_t(nb + 1) * 4));
     CU(cudaMemcpyPeer(dst.d_pos_samples, dst.device, src.d_pos_samples, src.device, size_t(n_pos + 4) * 4));
   }
-  uint32_t dollar = src.view.dollar_row;
   set_view_constants(ix, dst);
-  dst.view.dollar_row = dollar;
 }
 
 std::vector<int> pick_devices(const int* devices, int n_dev) {
@@ -378,9 +440,14 @@ void check_header(awry_index* ix) {
     fail(AWRY_ERR_FORMAT, "invalid symbol alphabet id %d", ix->alphabet);
   if (ix->sa_ratio == 0) fail(AWRY_ERR_FORMAT, "suffix array compression ratio is 0");
   if (ix->bwt_len < 2) fail(AWRY_ERR_FORMAT, "bwt_len %llu too small", (unsigned long long)ix->bwt_len);
-  if (ix->bwt_len >= (1ull << 32) - 256)
-    fail(AWRY_ERR_UNSUPPORTED, "bwt_len %llu >= 2^32: the device layout uses 32-bit row pointers",
-         (unsigned long long)ix->bwt_len);
+  if (ix->bwt_len >= (1ull << 56)) fail(AWRY_ERR_UNSUPPORTED, "bwt_len %llu >= 2^56", (unsigned long long)ix->bwt_len);
+  // 32-bit row pointers and the cooperative kernels while they suffice (every BASELINE config); 64-bit rows
+  // (SearchPtr = u64, search.rs:7) past that.  AWRY_B200_WIDE=1 forces the wide path on any index and
+  // AWRY_B200_SB_SHIFT shrinks its superblocks, so that small test indexes cross superblock borders.
+  ix->wide = ix->bwt_len >= (1ull << 32) - 256;
+  if (const char* e = getenv("AWRY_B200_WIDE")) ix->wide = ix->wide || e[0] == '1';
+  ix->sb_shift = SB_SHIFT;
+  if (const char* e = getenv("AWRY_B200_SB_SHIFT")) ix->sb_shift = uint32_t(std::min(31l, std::max(8l, strtol(e, nullptr, 10))));
   if (ix->sa_ratio >= (1ull << 32)) fail(AWRY_ERR_UNSUPPORTED, "suffix array compression ratio too large");
   ix->card = ix->alphabet == AWRY_NUCLEOTIDE ? 6 : 22;
   ix->sa_bits = bits_per_element(ix->bwt_len);
@@ -531,6 +598,8 @@ void awry_index_free(awry_index* ix) {
     cudaFree(r.d_blocks);
     cudaFree(r.d_sa);
     cudaFree(r.d_table);
+    cudaFree(r.d_table_w);
+    cudaFree(r.d_sb);
     cudaFree(r.d_pair);
     cudaFree(r.d_full_sa);
     cudaFree(r.d_walk);
@@ -582,13 +651,15 @@ int awry_initial_range(const awry_index* ix, uint8_t ascii_symbol, awry_range* o
     bool sent = false;
     uint32_t d = ascii_to_dsym(ix, ascii_symbol, &sent);
     // SearchRange::new accepts the sentinel too: [C[0], C[1]-1] (search.rs:43-48)
-    const IndexView& v = ix->reps[0]->view;
     if (sent) {
       out->start_ptr = ix->prefix_sums[0];
       out->end_ptr = ix->prefix_sums[1] - 1;
+    } else if (ix->wide) {
+      out->start_ptr = ix->reps[0]->wview.c_lo[d];
+      out->end_ptr = ix->reps[0]->wview.c_hi[d];
     } else {
-      out->start_ptr = v.c_lo[d];
-      out->end_ptr = v.c_hi[d];
+      out->start_ptr = ix->reps[0]->view.c_lo[d];
+      out->end_ptr = ix->reps[0]->view.c_hi[d];
     }
   });
 }
@@ -608,10 +679,9 @@ int awry_update_range(const awry_index* ix, awry_range range, uint8_t ascii_symb
     Workspace* ws = r.acquire();
     try {
       Workspace::grow_dev(ws->d_out, ws->d_out_cap, 16);
-      CU(launch_single_update(r.view, uint32_t(range.start_ptr), uint32_t(range.end_ptr), d,
-                              reinterpret_cast<uint32_t*>(ws->d_out), ws->st));
-      uint32_t res[2];
-      CU(cudaMemcpyAsync(res, ws->d_out, 8, cudaMemcpyDeviceToHost, ws->st));
+      CU(launch_single_update(r.view, range.start_ptr, range.end_ptr, d, reinterpret_cast<uint64_t*>(ws->d_out), ws->st));
+      uint64_t res[2];
+      CU(cudaMemcpyAsync(res, ws->d_out, 16, cudaMemcpyDeviceToHost, ws->st));
       CU(cudaStreamSynchronize(ws->st));
       out->start_ptr = res[0];
       out->end_ptr = res[1];
@@ -633,9 +703,9 @@ int awry_backstep(const awry_index* ix, uint64_t row, uint64_t* out) {
     Workspace* ws = r.acquire();
     try {
       Workspace::grow_dev(ws->d_out, ws->d_out_cap, 16);
-      CU(launch_single_backstep(r.view, uint32_t(row), reinterpret_cast<uint32_t*>(ws->d_out), ws->st));
-      uint32_t res = 0;
-      CU(cudaMemcpyAsync(&res, ws->d_out, 4, cudaMemcpyDeviceToHost, ws->st));
+      CU(launch_single_backstep(r.view, row, reinterpret_cast<uint64_t*>(ws->d_out), ws->st));
+      uint64_t res = 0;
+      CU(cudaMemcpyAsync(&res, ws->d_out, 8, cudaMemcpyDeviceToHost, ws->st));
       CU(cudaStreamSynchronize(ws->st));
       *out = res;
     } catch (...) {

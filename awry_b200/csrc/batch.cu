@@ -191,7 +191,7 @@ void validate_chunks(const std::vector<Chunk>& chunks, uint64_t max_bytes) {
 void enqueue_search(const awry_index* ix, Replica& r, PackBalance& bal, Workspace* ws, const QuerySource& qs,
                     const Chunk& c, SearchOut mode, bool may_pack = true, bool probe_link = false, bool copy_flag = true) {
   const uint64_t nq = c.q1 - c.q0, nbytes = c.b1 - c.b0;
-  const size_t out_elem = mode == OUT_COUNT_U64 ? 8 : mode == OUT_RANGE_U64 ? 16 : 8;
+  const size_t out_elem = mode == OUT_COUNT_U64 ? 8 : mode == OUT_RANGE_U64 ? 16 : sp_cnt_bytes(r.view);
   const int ush = packed_unit_shift(ix->alphabet);
   Workspace::grow_dev(ws->d_qbytes, ws->d_qbytes_cap, size_t(nbytes) + 16);
   Workspace::grow_dev(ws->d_qoff, ws->d_qoff_cap, size_t(nq) + 1);
@@ -460,23 +460,18 @@ struct LocatePart {
 };
 
 // CSR offsets of a searched chunk (ws->d_out holds (sp, count) per query), no synchronisation
-void locate_chunk_scan(Workspace* ws, uint64_t nq, uint64_t* d_hit_off, cudaStream_t st) {
-  const uint2* d_sp_cnt = reinterpret_cast<const uint2*>(ws->d_out);
+void locate_chunk_scan(Replica& r, Workspace* ws, uint64_t nq, uint64_t* d_hit_off, cudaStream_t st) {
+  const void* d_sp_cnt = ws->d_out;
   size_t temp = 0;
-  CU(scan_hit_offsets(d_sp_cnt, nq, d_hit_off, nullptr, temp, st));
+  CU(scan_hit_offsets(r.view, d_sp_cnt, nq, d_hit_off, nullptr, temp, st));
   Workspace::grow_dev(reinterpret_cast<uint8_t*&>(ws->d_temp), ws->d_temp_cap, temp + 16);
-  CU(scan_hit_offsets(d_sp_cnt, nq, d_hit_off, ws->d_temp, temp, st));
+  CU(scan_hit_offsets(r.view, d_sp_cnt, nq, d_hit_off, ws->d_temp, temp, st));
 }
 
 // device-side two-pass locate of a chunk whose queries were already searched (ws->d_out holds
 // (sp, count) per query).  Step 1: CSR offsets + hit total (one synchronisation).
 uint64_t locate_chunk_count(Replica& r, Workspace* ws, uint64_t nq, uint64_t* d_hit_off, cudaStream_t st) {
-  (void)r;
-  const uint2* d_sp_cnt = reinterpret_cast<const uint2*>(ws->d_out);
-  size_t temp = 0;
-  CU(scan_hit_offsets(d_sp_cnt, nq, d_hit_off, nullptr, temp, st));
-  Workspace::grow_dev(reinterpret_cast<uint8_t*&>(ws->d_temp), ws->d_temp_cap, temp + 16);
-  CU(scan_hit_offsets(d_sp_cnt, nq, d_hit_off, ws->d_temp, temp, st));
+  locate_chunk_scan(r, ws, nq, d_hit_off, st);
   uint64_t n_hits = 0;
   CU(cudaMemcpyAsync(&n_hits, d_hit_off + nq, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
@@ -490,7 +485,7 @@ uint64_t* locate_chunk_walk(Replica& r, Workspace* ws, uint64_t nq, uint64_t n_h
   IndexView view = r.view;
   if (g_locate_variant != 0) view.full_sa = nullptr;      // 1, 2: walk
   if (g_locate_variant == 1) view.walk_blocks = nullptr;  // 1: to the file's row samples
-  const uint2* d_sp_cnt = reinterpret_cast<const uint2*>(ws->d_out);
+  const void* d_sp_cnt = ws->d_out;
   uint64_t* d_hits = nullptr;
   CU(cudaMallocAsync(reinterpret_cast<void**>(&d_hits), n_hits * 16 + 16, st));  // pool: no driver round trip
   trace_mark("  hits buffer allocated, hits", (long long)n_hits);
@@ -594,7 +589,7 @@ void locate_on_replica(const awry_index* ix, size_t ri, const QuerySource& qs, u
     enqueue_search(ix, r, bal, ws, qs, c, OUT_SP_CNT_U32, true, false, false);
     mark("A searched", i);
     Workspace::grow_dev(ws->d_hit_off, ws->d_hit_off_cap, size_t(nq) + 1);
-    locate_chunk_scan(ws, nq, ws->d_hit_off, ws->st);
+    locate_chunk_scan(r, ws, nq, ws->d_hit_off, ws->st);
     gpu_mark(ws->st, "scanned", i);
     CU(cudaMemcpyAsync(ws->h_flag, ws->d_flag, 8, cudaMemcpyDeviceToHost, ws->st));
     CU(cudaMemcpyAsync(ws->h_total, ws->d_hit_off + nq, 8, cudaMemcpyDeviceToHost, ws->st));
@@ -718,7 +713,7 @@ uint64_t locate_direct_on_replica(const awry_index* ix, size_t ri, const QuerySo
       enqueue_search(ix, r, bal, w, qs, c, OUT_SP_CNT_U32, true, false, false);
       Workspace::grow_dev(w->d_hit_off, w->d_hit_off_cap, size_t(n) + 1);
       Workspace::grow_dev(w->d_off_out, w->d_off_out_cap, size_t(n) + 1);
-      locate_chunk_scan(w, n, w->d_hit_off, w->st);
+      locate_chunk_scan(r, w, n, w->d_hit_off, w->st);
       gpu_mark(w->st, "scanned", (long long)i);
       // (chunk 0 waits for the counter's reset; a slot's event is re-recorded only after the wait on its
       // earlier state has been enqueued)
@@ -1022,7 +1017,7 @@ int awry_locate_device(const awry_index* ix, int replica, const uint8_t* d_qbyte
     try {
       uint64_t words = 4 * (nq + ((ends[1] >> sh) - (ends[0] >> sh)) + 2) + 32;
       Workspace::grow_dev(ws->d_qwords, ws->d_qwords_cap, size_t(words));
-      Workspace::grow_dev(ws->d_out, ws->d_out_cap, size_t(nq) * 8);
+      Workspace::grow_dev(ws->d_out, ws->d_out_cap, size_t(nq) * sp_cnt_bytes(r.view));
       Workspace::grow_dev(ws->d_defer, ws->d_defer_cap, size_t(nq) + 2);
       {
         ProfScope p(2, r.device, st);

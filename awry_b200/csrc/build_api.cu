@@ -277,7 +277,7 @@ int awry_index_save(const awry_index* ix, const char* path) {
       } tmp;
       for (auto& d : tmp.d) CU(cudaMalloc(reinterpret_cast<void**>(&d), chunk_blocks * wpb * 8));
       fo.put_device(r.device, n_rb * wpb, chunk_blocks * wpb, [&](uint64_t c, uint64_t w0, uint64_t nw, cudaStream_t cs) {
-        CU(launch_untranspose(ix->alphabet, r.d_blocks, r.view.dollar_row, w0 / wpb, nw / wpb, tmp.d[c & 1], cs));
+        CU(launch_untranspose(ix->alphabet, r.d_blocks, r.dollar_row, w0 / wpb, nw / wpb, tmp.d[c & 1], r.d_sb, ix->sb_shift, cs));
         return static_cast<const uint64_t*>(tmp.d[c & 1]);
       });
     }

@@ -281,6 +281,11 @@ struct Replica {
   size_t bytes_blocks = 0, bytes_sa = 0, bytes_table = 0, bytes_pair = 0, bytes_full_sa = 0;
   uint32_t c2[16] = {0};
   IndexView view{};
+  // wide index (bwt_len >= 2^32 - 256): 64-bit row pointers, kernels_wide.cu; view.wide points at wview
+  WideView wview{};
+  ulonglong2* d_table_w = nullptr;  // k-mer seeds with 64-bit row pointers
+  uint64_t* d_sb = nullptr;         // superblock counts the block counts are relative to
+  uint64_t dollar_row = 0;
   std::mutex ws_mu;
   std::vector<Workspace*> free_ws;
   std::vector<Workspace*> all_ws;
@@ -367,6 +372,9 @@ struct awry_index {
   uint64_t prefix_sums[23] = {0};
   uint64_t n_sa_words = 0;
   uint32_t sa_bits = 0;
+  bool wide = false;        // 64-bit row pointers (bwt_len >= 2^32 - 256, or AWRY_B200_WIDE=1)
+  uint32_t sb_shift = 31;   // log2(rows per superblock) of a wide index
+  uint64_t n_superblocks() const { return (bwt_len >> sb_shift) + 1; }
   std::vector<uint64_t> seq_starts;
   std::vector<std::string> headers;
   std::vector<std::unique_ptr<awry::host::Replica>> reps;

@@ -71,7 +71,7 @@ cudaError_t init_device_tables() {
 // one thread per 16-B output chunk; 8 chunks per 256-row reference block (bwt.rs:12-17)
 __global__ void transpose_dna_kernel(const uint64_t* __restrict__ ref, uint64_t first_rb,
                                      uint64_t n_rb, uint64_t bwt_len, uint4* __restrict__ out,
-                                     unsigned int* dollar_row) {
+                                     unsigned long long* dollar_row, const uint64_t* __restrict__ sb, uint32_t sb_shift) {
   uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
   if (t >= n_rb * 8) return;
   uint64_t lrb = t >> 3;
@@ -88,7 +88,7 @@ __global__ void transpose_dna_kernel(const uint64_t* __restrict__ ref, uint64_t 
   uint32_t d0 = ((isC | isT | isS) & valid) | ~valid;  // device codes A0 C1 G2 T3 N4 $5, pad 7
   uint32_t d1 = ((isG | isT) & valid) | ~valid;
   uint32_t d2 = ((isN | isS) & valid) | ~valid;
-  if (isS & valid) *dollar_row = uint32_t(row0 + (__ffs(isS & valid) - 1));
+  if (isS & valid) *dollar_row = row0 + uint64_t(__ffs(isS & valid) - 1);
   // milestone of symbol j (A,C,G,T = reference index 1,2,3,5) at the start of this 128-row block
   const int ref_idx = j == 3 ? 5 : int(j) + 1;
   uint64_t cnt = rb[12 + ref_idx];
@@ -100,6 +100,7 @@ __global__ void transpose_dna_kernel(const uint64_t* __restrict__ ref, uint64_t 
       cnt += uint64_t(__popcll(m));
     }
   }
+  if (sb != nullptr) cnt -= sb[(row0 >> sb_shift) * SB_STRIDE + j];  // wide index: relative to the superblock
   out[(first_rb + lrb) * 8 + h * 4 + j] = make_uint4(d0, d1, d2, uint32_t(cnt));
 }
 
@@ -108,7 +109,7 @@ __global__ void transpose_dna_kernel(const uint64_t* __restrict__ ref, uint64_t 
 // of the 64-row device block that owns the rows.
 __global__ void transpose_amino_kernel(const uint64_t* __restrict__ ref, uint64_t first_rb,
                                        uint64_t n_rb, uint64_t bwt_len, uint4* __restrict__ out,
-                                       unsigned int* dollar_row) {
+                                       unsigned long long* dollar_row) {
   uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
   if (t >= n_rb * 8) return;
   uint64_t lrb = t >> 3;
@@ -125,7 +126,7 @@ __global__ void transpose_amino_kernel(const uint64_t* __restrict__ ref, uint64_
 #pragma unroll
     for (int p = 0; p < 5; p++) code |= ((r[p] >> bit) & 1u) << p;
     uint32_t idx = ((valid >> bit) & 1u) ? c_amino_code_to_idx[code] : 0u;
-    if (((valid >> bit) & 1u) && code == 0) *dollar_row = uint32_t(row0 + bit);
+    if (((valid >> bit) & 1u) && code == 0) *dollar_row = row0 + uint64_t(bit);
 #pragma unroll
     for (int p = 0; p < 5; p++) d[p] |= ((idx >> p) & 1u) << bit;
   }
@@ -139,13 +140,15 @@ __global__ void transpose_amino_kernel(const uint64_t* __restrict__ ref, uint64_
 // 64-row device blocks = the reference milestone + symbols seen in the earlier device blocks,
 // counted on the re-encoded planes so counts and planes agree for every input.
 __global__ void amino_counts_kernel(const uint64_t* __restrict__ ref, uint64_t first_rb, uint64_t n_rb,
-                                    uint4* __restrict__ out) {
+                                    uint4* __restrict__ out, const uint64_t* __restrict__ sb, uint32_t sb_shift) {
   uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
   if (t >= n_rb * 32) return;
   uint64_t lrb = t >> 5;
   uint32_t s = uint32_t(t) & 31;
   if (s == 0 || s > 21) return;
-  uint32_t cnt = uint32_t(ref[lrb * 44 + 20 + s]);
+  uint64_t ms = ref[lrb * 44 + 20 + s];
+  if (sb != nullptr) ms -= sb[(((first_rb + lrb) * 256) >> sb_shift) * SB_STRIDE + s];  // wide index: relative
+  uint32_t cnt = uint32_t(ms);
   for (uint32_t d = 0; d < 4; d++) {
     uint32_t* blk = reinterpret_cast<uint32_t*>(out + ((first_rb + lrb) * 4 + d) * AMINO_BLOCK_UINT4);
     blk[amino_count_word(s)] = cnt;
@@ -161,21 +164,52 @@ __global__ void amino_counts_kernel(const uint64_t* __restrict__ ref, uint64_t f
 
 cudaError_t launch_transpose(int alphabet, const uint64_t* d_ref_blocks, uint64_t first_ref_block,
                              uint64_t n_ref_blocks, uint64_t bwt_len, uint4* d_blocks,
-                             unsigned int* d_dollar_row, cudaStream_t s) {
+                             unsigned long long* d_dollar_row, const uint64_t* d_sb, uint32_t sb_shift, cudaStream_t s) {
   if (n_ref_blocks == 0) return cudaSuccess;
   uint64_t threads = n_ref_blocks * 8;
   unsigned grid = unsigned((threads + 255) / 256);
   if (alphabet == 0)
     transpose_dna_kernel<<<grid, 256, 0, s>>>(d_ref_blocks, first_ref_block, n_ref_blocks, bwt_len,
-                                              d_blocks, d_dollar_row);
+                                              d_blocks, d_dollar_row, d_sb, sb_shift);
   else {
     transpose_amino_kernel<<<grid, 256, 0, s>>>(d_ref_blocks, first_ref_block, n_ref_blocks,
                                                 bwt_len, d_blocks, d_dollar_row);
     COUNT_LAUNCH();
     uint64_t t2 = n_ref_blocks * 32;
     amino_counts_kernel<<<unsigned((t2 + 255) / 256), 256, 0, s>>>(d_ref_blocks, first_ref_block,
-                                                                    n_ref_blocks, d_blocks);
+                                                                    n_ref_blocks, d_blocks, d_sb, sb_shift);
   }
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+// one thread per superblock that starts inside [first_rb, first_rb + n_rb): its absolute counts are the
+// milestones of its first reference block (fm_index.rs:212-217), reordered to SB_STRIDE slots
+__global__ void gather_superblocks_kernel(int alphabet, const uint64_t* __restrict__ ref, uint64_t first_rb, uint64_t n_rb,
+                                          uint32_t sb_shift, uint64_t* __restrict__ sb) {
+  const uint64_t rb_per_sb = 1ull << (sb_shift - 8);
+  const uint64_t s0 = (first_rb + rb_per_sb - 1) / rb_per_sb;
+  const uint64_t sidx = s0 + blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  const uint64_t rb = sidx * rb_per_sb;
+  if (rb >= first_rb + n_rb) return;
+  const uint64_t* ms = ref + (rb - first_rb) * (alphabet == 0 ? 20 : 44) + (alphabet == 0 ? 12 : 20);
+  uint64_t* o = sb + sidx * SB_STRIDE;
+  if (alphabet == 0) {
+    o[0] = ms[1];
+    o[1] = ms[2];
+    o[2] = ms[3];
+    o[3] = ms[5];
+  } else {
+    for (int i = 0; i < 22; i++) o[i] = ms[i];
+  }
+}
+cudaError_t launch_gather_superblocks(int alphabet, const uint64_t* d_ref_blocks, uint64_t first_ref_block,
+                                      uint64_t n_ref_blocks, uint32_t sb_shift, uint64_t* d_sb, cudaStream_t s) {
+  if (n_ref_blocks == 0) return cudaSuccess;
+  const uint64_t rb_per_sb = 1ull << (sb_shift - 8);
+  const uint64_t n = n_ref_blocks / rb_per_sb + 2;
+  gather_superblocks_kernel<<<unsigned((n + 127) / 128), 128, 0, s>>>(alphabet, d_ref_blocks, first_ref_block, n_ref_blocks,
+                                                                      sb_shift, d_sb);
   COUNT_LAUNCH();
   return cudaGetLastError();
 }
@@ -188,7 +222,8 @@ cudaError_t launch_transpose(int alphabet, const uint64_t* d_ref_blocks, uint64_
 // T001 (alphabet.rs:309-327); padding rows come out as all-zero planes, as set_symbol_at never touched them.
 // The thread of word 0 also writes the 8 milestones (bwt.rs:29; fm_index.rs:212-217), N derived as in layout.cuh.
 __global__ void untranspose_dna_kernel(const uint4* __restrict__ blocks, uint64_t first_rb, uint64_t n_rb,
-                                       uint32_t dollar_row, uint64_t* __restrict__ ref) {
+                                       uint64_t dollar_row, uint64_t* __restrict__ ref, const uint64_t* __restrict__ sb,
+                                       uint32_t sb_shift) {
   uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
   if (t >= n_rb * 4) return;
   const uint64_t lrb = t >> 2, rb = first_rb + lrb;
@@ -211,7 +246,15 @@ __global__ void untranspose_dna_kernel(const uint4* __restrict__ blocks, uint64_
   out[8 + w] = r2;
   if (w == 0) {
     const uint4* b0 = blocks + rb * 2 * DNA_BLOCK_UINT4;
-    const uint64_t a = b0[0].w, c = b0[1].w, g = b0[2].w, tt = b0[3].w, start = rb * 256;
+    const uint64_t start = rb * 256;
+    uint64_t a = b0[0].w, c = b0[1].w, g = b0[2].w, tt = b0[3].w;
+    if (sb != nullptr) {  // wide index: block counts are relative to the superblock
+      const uint64_t* o = sb + (start >> sb_shift) * SB_STRIDE;
+      a += o[0];
+      c += o[1];
+      g += o[2];
+      tt += o[3];
+    }
     const uint64_t s = dollar_row < start ? 1 : 0;
     out[12] = s;
     out[13] = a;
@@ -229,7 +272,8 @@ __global__ void untranspose_dna_kernel(const uint4* __restrict__ blocks, uint64_
 // (alphabet.rs:255-303; '$' and padding rows are code 00000); slice 0 also writes the 24 milestones.
 __constant__ uint8_t c_amino_idx_to_code[32];
 __global__ void untranspose_amino_kernel(const uint4* __restrict__ blocks, uint64_t first_rb, uint64_t n_rb,
-                                         uint32_t dollar_row, uint64_t* __restrict__ ref) {
+                                         uint64_t dollar_row, uint64_t* __restrict__ ref, const uint64_t* __restrict__ sb,
+                                         uint32_t sb_shift) {
   uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
   if (t >= n_rb * 8) return;
   const uint64_t lrb = t >> 3, rb = first_rb + lrb;
@@ -254,19 +298,21 @@ __global__ void untranspose_amino_kernel(const uint4* __restrict__ blocks, uint6
     uint64_t* ms = ref + lrb * 44 + 20;
     const uint32_t* b0 = reinterpret_cast<const uint32_t*>(blocks + rb * 4 * AMINO_BLOCK_UINT4);
     ms[0] = dollar_row < rb * 256 ? 1 : 0;
-    for (uint32_t s = 1; s <= 21; s++) ms[s] = b0[amino_count_word(s)];
+    const uint64_t* o = sb != nullptr ? sb + ((rb * 256) >> sb_shift) * SB_STRIDE : nullptr;
+    for (uint32_t s = 1; s <= 21; s++) ms[s] = uint64_t(b0[amino_count_word(s)]) + (o ? o[s] : 0ull);
     ms[22] = 0;
     ms[23] = 0;
   }
 }
 
-cudaError_t launch_untranspose(int alphabet, const uint4* d_blocks, uint32_t dollar_row, uint64_t first_ref_block,
-                               uint64_t n_ref_blocks, uint64_t* d_ref_blocks, cudaStream_t s) {
+cudaError_t launch_untranspose(int alphabet, const uint4* d_blocks, uint64_t dollar_row, uint64_t first_ref_block,
+                               uint64_t n_ref_blocks, uint64_t* d_ref_blocks, const uint64_t* d_sb, uint32_t sb_shift,
+                               cudaStream_t s) {
   if (n_ref_blocks == 0) return cudaSuccess;
   if (alphabet == 0) {
     uint64_t threads = n_ref_blocks * 4;
     untranspose_dna_kernel<<<unsigned((threads + 255) / 256), 256, 0, s>>>(d_blocks, first_ref_block, n_ref_blocks,
-                                                                            dollar_row, d_ref_blocks);
+                                                                            dollar_row, d_ref_blocks, d_sb, sb_shift);
   } else {
     // same table as init_device_tables (index -> 5-bit code); indices 22..31 never occur in device blocks
     static const uint8_t i2c[32] = {0x00, 0x0c, 0x17, 0x03, 0x06, 0x1e, 0x1a, 0x1b, 0x19, 0x15, 0x1c,
@@ -275,7 +321,7 @@ cudaError_t launch_untranspose(int alphabet, const uint4* d_blocks, uint32_t dol
     if (e != cudaSuccess) return e;
     uint64_t threads = n_ref_blocks * 8;
     untranspose_amino_kernel<<<unsigned((threads + 255) / 256), 256, 0, s>>>(d_blocks, first_ref_block, n_ref_blocks,
-                                                                              dollar_row, d_ref_blocks);
+                                                                              dollar_row, d_ref_blocks, d_sb, sb_shift);
   }
   COUNT_LAUNCH();
   return cudaGetLastError();
@@ -359,6 +405,7 @@ __global__ void ref_table_kernel(IndexView ix, uint64_t first, uint64_t count, u
 cudaError_t launch_ref_table(const IndexView& ix, uint64_t first, uint64_t count, uint32_t k, void* d_out,
                              cudaStream_t s) {
   if (count == 0) return cudaSuccess;
+  if (ix.wide) return launch_ref_table_wide(*ix.wide, first, count, k, d_out, s);
   unsigned grid = unsigned((count + 255) / 256);
   if (ix.alphabet == 0)
     ref_table_kernel<0><<<grid, 256, 0, s>>>(ix, first, count, k, static_cast<ulonglong2*>(d_out));
@@ -682,57 +729,6 @@ cudaError_t launch_pack2(const uint32_t* d_crumbs, uint64_t base, const uint64_t
 }
 
 // ------------------------------------------------------------------ backward search
-
-template <int MODE>
-__device__ __forceinline__ void store_result(void* out, uint64_t q, uint32_t sp, uint32_t ep) {
-  bool empty = sp > ep;
-  if (MODE == OUT_COUNT_U64) {
-    reinterpret_cast<uint64_t*>(out)[q] = empty ? 0ull : uint64_t(ep - sp) + 1ull;  // search.rs:66-71
-  } else if (MODE == OUT_RANGE_U64) {
-    reinterpret_cast<ulonglong2*>(out)[q] = empty ? make_ulonglong2(1, 0) : make_ulonglong2(sp, ep);
-  } else {
-    reinterpret_cast<uint2*>(out)[q] = empty ? make_uint2(1u, 0u) : make_uint2(sp, ep - sp + 1u);
-  }
-}
-
-// Length of query (o0, o1) of a batch whose bytes span [b.lo, b.hi]; 0 for a query the prepass refused
-// (offsets outside the range: its packed words were never written) -- it is stored as an empty result and the
-// call fails with the prepass's error.
-struct ByteRange {
-  uint64_t lo, hi;
-};
-__device__ __forceinline__ uint32_t checked_len(uint64_t o0, uint64_t o1, const ByteRange& b) {
-  return (o0 < b.lo || o1 > b.hi || o1 < o0 || o1 - o0 >= (1ull << 32)) ? 0u : uint32_t(o1 - o0);
-}
-
-// Packed-symbol reader: current word in a register, the next one prefetched.  Word positions are
-// 32-bit indices into the packed buffer (a launch never packs more than 2^32 words = 32 GiB).
-template <int ALPHA>
-struct QueryStream {
-  static constexpr int BITS = ALPHA == 0 ? 4 : 8;
-  static constexpr int SPW = 64 / BITS;
-  static constexpr int UNIT_SHIFT = ALPHA == 0 ? 6 : 5;
-  uint64_t w, wnext;
-  uint32_t widx;    // index of the word held in wnext
-  uint32_t inword;
-  __device__ __forceinline__ void open(const uint64_t* __restrict__ qwords, uint32_t q, uint64_t o0) {
-    widx = 4 * (q + uint32_t(o0 >> UNIT_SHIFT)) + 1;
-    w = __ldg(qwords + (widx - 1));
-    wnext = __ldg(qwords + widx);  // buffer is padded
-    inword = 0;
-  }
-  __device__ __forceinline__ uint32_t next(const uint64_t* __restrict__ qwords) {
-    uint32_t c = uint32_t(w) & ((1u << BITS) - 1u);
-    w >>= BITS;
-    if (++inword == SPW) {
-      w = wnext;
-      widx++;
-      wnext = __ldg(qwords + widx);
-      inword = 0;
-    }
-    return c;
-  }
-};
 
 // Start of a query: seed interval from the k-mer table when the last k symbols are all
 // encoding symbols (replaces KmerLookupTable::get_range_for_kmer, kmer_lookup_table.rs:90-110,
@@ -1762,6 +1758,7 @@ cudaError_t launch_search(const IndexView& ix, const uint64_t* d_qwords, const u
                           uint64_t nq, SearchOut mode, void* d_out, uint32_t* d_defer,
                           const SearchVariant& v, int sm_count, cudaStream_t s) {
   if (nq == 0) return cudaSuccess;
+  if (ix.wide) return launch_search_wide(*ix.wide, d_qwords, d_qoff, nq, mode, d_out, v.b_lo, v.b_hi, sm_count, s);
   switch (mode) {
     case OUT_COUNT_U64: return launch_search_mode<OUT_COUNT_U64>(ix, d_qwords, d_qoff, nq, d_out, d_defer, v, sm_count, s);
     case OUT_RANGE_U64: return launch_search_mode<OUT_RANGE_U64>(ix, d_qwords, d_qoff, nq, d_out, d_defer, v, sm_count, s);

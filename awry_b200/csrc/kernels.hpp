@@ -58,13 +58,20 @@ struct LaunchCounters {
 cudaError_t init_device_tables();  // per device, once: ASCII -> device-symbol LUTs
 
 // reference-layout blocks (staged on the device) -> device layout
+// d_sb: nullptr, or (wide indexes) the superblock table [superblock][SB_STRIDE] the block counts are made
+// relative to; sb_shift = log2(rows per superblock)
 cudaError_t launch_transpose(int alphabet, const uint64_t* d_ref_blocks, uint64_t first_ref_block,
                              uint64_t n_ref_blocks, uint64_t bwt_len, uint4* d_blocks,
-                             unsigned int* d_dollar_row, cudaStream_t s);
+                             unsigned long long* d_dollar_row, const uint64_t* d_sb, uint32_t sb_shift, cudaStream_t s);
+// wide indexes: absolute counts of the superblocks whose first reference block lies in [first, first + n)
+// of a reference-layout block array on the device -> d_sb
+cudaError_t launch_gather_superblocks(int alphabet, const uint64_t* d_ref_blocks, uint64_t first_ref_block,
+                                      uint64_t n_ref_blocks, uint32_t sb_shift, uint64_t* d_sb, cudaStream_t s);
 // the inverse (FmIndex::save of a handle that only holds the device layout): device blocks -> reference
 // blocks [first_ref_block, first_ref_block + n_ref_blocks) written to d_ref_blocks[0 ..)
-cudaError_t launch_untranspose(int alphabet, const uint4* d_blocks, uint32_t dollar_row, uint64_t first_ref_block,
-                               uint64_t n_ref_blocks, uint64_t* d_ref_blocks, cudaStream_t s);
+cudaError_t launch_untranspose(int alphabet, const uint4* d_blocks, uint64_t dollar_row, uint64_t first_ref_block,
+                               uint64_t n_ref_blocks, uint64_t* d_ref_blocks, const uint64_t* d_sb, uint32_t sb_shift,
+                               cudaStream_t s);
 uint64_t table_entries(int alphabet, uint32_t k);
 cudaError_t launch_build_table(const IndexView& ix, uint2* d_table, uint32_t k, cudaStream_t s);
 
@@ -107,12 +114,14 @@ cudaError_t launch_search(const IndexView& ix, const uint64_t* d_qwords, const u
                           const SearchVariant& v, int sm_count, cudaStream_t s);
 
 // locate: CSR offsets from pass 1, LF-walk pass 2
-cudaError_t scan_hit_offsets(const uint2* d_sp_cnt, uint64_t nq, uint64_t* d_hit_off, void* d_temp,
+// d_sp_cnt: the search kernels' OUT_SP_CNT result -- uint2 (sp, count) per query, ulonglong2 for a wide index
+cudaError_t scan_hit_offsets(const IndexView& ix, const void* d_sp_cnt, uint64_t nq, uint64_t* d_hit_off, void* d_temp,
                              size_t& temp_bytes, cudaStream_t s);
+inline size_t sp_cnt_bytes(const IndexView& ix) { return ix.wide ? 16 : 8; }
 // writes either awry_hit {seq_idx, local_pos} (d_hits) or global text positions (d_locs); when
 // ix.full_sa is set the walk is replaced by a gather from the unsampled array.  The output buffer must
 // have 16 spare bytes behind its n_hits slots (the walk kernels' ticket counter).
-cudaError_t launch_walk(const IndexView& ix, const uint2* d_sp_cnt, const uint64_t* d_hit_off,
+cudaError_t launch_walk(const IndexView& ix, const void* d_sp_cnt, const uint64_t* d_hit_off,
                         uint64_t nq, uint64_t n_hits, uint64_t* d_hits_pairs, uint64_t* d_locs,
                         int sm_count, cudaStream_t s);
 // sync-free pass 2 on the unsampled array (see kernels_locate.cu): hits go straight to `out_hits` (device view
@@ -127,9 +136,22 @@ cudaError_t sort_hit_segments(uint64_t* d_locs_in, uint64_t* d_locs_out, uint64_
 cudaError_t launch_map_locations(const IndexView& ix, const uint64_t* d_locs, uint64_t n_hits,
                                  uint64_t* d_hits_pairs, cudaStream_t s);
 
-cudaError_t launch_single_update(const IndexView& ix, uint32_t sp, uint32_t ep, uint32_t dsym,
-                                 uint32_t* d_out2, cudaStream_t s);
-cudaError_t launch_single_backstep(const IndexView& ix, uint32_t row, uint32_t* d_out, cudaStream_t s);
+cudaError_t launch_single_update(const IndexView& ix, uint64_t sp, uint64_t ep, uint32_t dsym,
+                                 uint64_t* d_out2, cudaStream_t s);
+cudaError_t launch_single_backstep(const IndexView& ix, uint64_t row, uint64_t* d_out, cudaStream_t s);
+
+// ---- kernels_wide.cu: indexes with 64-bit row pointers (the launchers above dispatch on IndexView::wide)
+cudaError_t launch_build_table_wide(const WideView& ix, ulonglong2* d_table, uint32_t k, cudaStream_t s);
+cudaError_t launch_search_wide(const WideView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff, uint64_t nq,
+                               SearchOut mode, void* d_out, uint64_t b_lo, uint64_t b_hi, int sm_count, cudaStream_t s);
+cudaError_t scan_hit_offsets_wide(const void* d_sp_cnt, uint64_t nq, uint64_t* d_hit_off, void* d_temp, size_t& temp_bytes,
+                                  cudaStream_t s);
+cudaError_t launch_walk_wide(const WideView& ix, const void* d_sp_cnt, const uint64_t* d_hit_off, uint64_t nq, uint64_t n_hits,
+                             uint64_t* d_hits_pairs, uint64_t* d_locs, int sm_count, cudaStream_t s);
+cudaError_t launch_single_update_wide(const WideView& ix, uint64_t sp, uint64_t ep, uint32_t dsym, uint64_t* d_out2,
+                                      cudaStream_t s);
+cudaError_t launch_single_backstep_wide(const WideView& ix, uint64_t row, uint64_t* d_out, cudaStream_t s);
+cudaError_t launch_ref_table_wide(const WideView& ix, uint64_t first, uint64_t count, uint32_t k, void* d_out, cudaStream_t s);
 
 cudaError_t run_random_gather(uint64_t footprint_bytes, uint32_t granule, uint32_t lanes,
                               uint64_t n_reads, int iters, double* reads_per_s, double* gb_per_s);

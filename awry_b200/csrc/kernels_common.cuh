@@ -11,6 +11,59 @@ namespace awry {
 extern std::atomic<uint64_t> g_launches;  // kernels launched by this library (awry_profile_get)
 #define COUNT_LAUNCH() ::awry::g_launches.fetch_add(1, std::memory_order_relaxed)
 
+// ---- shared by the search kernels (kernels.cu, kernels_wide.cu) ----
+
+template <int MODE>
+__device__ __forceinline__ void store_result(void* out, uint64_t q, uint32_t sp, uint32_t ep) {
+  bool empty = sp > ep;
+  if (MODE == OUT_COUNT_U64) {
+    reinterpret_cast<uint64_t*>(out)[q] = empty ? 0ull : uint64_t(ep - sp) + 1ull;  // search.rs:66-71
+  } else if (MODE == OUT_RANGE_U64) {
+    reinterpret_cast<ulonglong2*>(out)[q] = empty ? make_ulonglong2(1, 0) : make_ulonglong2(sp, ep);
+  } else {
+    reinterpret_cast<uint2*>(out)[q] = empty ? make_uint2(1u, 0u) : make_uint2(sp, ep - sp + 1u);
+  }
+}
+
+// Length of query (o0, o1) of a batch whose bytes span [b.lo, b.hi]; 0 for a query the prepass refused
+// (offsets outside the range: its packed words were never written) -- it is stored as an empty result and the
+// call fails with the prepass's error.
+struct ByteRange {
+  uint64_t lo, hi;
+};
+__device__ __forceinline__ uint32_t checked_len(uint64_t o0, uint64_t o1, const ByteRange& b) {
+  return (o0 < b.lo || o1 > b.hi || o1 < o0 || o1 - o0 >= (1ull << 32)) ? 0u : uint32_t(o1 - o0);
+}
+
+// Packed-symbol reader: current word in a register, the next one prefetched.  Word positions are
+// 32-bit indices into the packed buffer (a launch never packs more than 2^32 words = 32 GiB).
+template <int ALPHA>
+struct QueryStream {
+  static constexpr int BITS = ALPHA == 0 ? 4 : 8;
+  static constexpr int SPW = 64 / BITS;
+  static constexpr int UNIT_SHIFT = ALPHA == 0 ? 6 : 5;
+  uint64_t w, wnext;
+  uint32_t widx;    // index of the word held in wnext
+  uint32_t inword;
+  __device__ __forceinline__ void open(const uint64_t* __restrict__ qwords, uint32_t q, uint64_t o0) {
+    widx = 4 * (q + uint32_t(o0 >> UNIT_SHIFT)) + 1;
+    w = __ldg(qwords + (widx - 1));
+    wnext = __ldg(qwords + widx);  // buffer is padded
+    inword = 0;
+  }
+  __device__ __forceinline__ uint32_t next(const uint64_t* __restrict__ qwords) {
+    uint32_t c = uint32_t(w) & ((1u << BITS) - 1u);
+    w >>= BITS;
+    if (++inword == SPW) {
+      w = wnext;
+      widx++;
+      wnext = __ldg(qwords + widx);
+      inword = 0;
+    }
+    return c;
+  }
+};
+
 // ---- a lane's share of a 64-B nucleotide block: LANES lanes cooperate on one block ----
 template <int LANES>
 struct LaneChunks;

@@ -22,10 +22,12 @@ struct CountOf {
 };
 
 // exclusive scan of the per-query hit counts -> CSR offsets, d_hit_off[nq] = total
-cudaError_t scan_hit_offsets(const uint2* d_sp_cnt, uint64_t nq, uint64_t* d_hit_off, void* d_temp,
+cudaError_t scan_hit_offsets(const IndexView& ix, const void* d_sp_cnt, uint64_t nq, uint64_t* d_hit_off, void* d_temp,
                              size_t& temp_bytes, cudaStream_t s) {
+  if (ix.wide) return scan_hit_offsets_wide(d_sp_cnt, nq, d_hit_off, d_temp, temp_bytes, s);
   cub::CountingInputIterator<uint64_t> idx(0);
-  cub::TransformInputIterator<uint64_t, CountOf, cub::CountingInputIterator<uint64_t>> in(idx, CountOf{d_sp_cnt, nq});
+  cub::TransformInputIterator<uint64_t, CountOf, cub::CountingInputIterator<uint64_t>> in(
+      idx, CountOf{static_cast<const uint2*>(d_sp_cnt), nq});
   cudaError_t e = cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, in, d_hit_off, nq + 1, s);
   if (d_temp != nullptr) COUNT_LAUNCH();
   return e;
@@ -699,10 +701,12 @@ cudaError_t launch_gather_direct(const IndexView& ix, const uint2* d_sp_cnt, con
   return cudaGetLastError();
 }
 
-cudaError_t launch_walk(const IndexView& ix, const uint2* d_sp_cnt, const uint64_t* d_hit_off,
+cudaError_t launch_walk(const IndexView& ix, const void* d_sp_cnt_v, const uint64_t* d_hit_off,
                         uint64_t nq, uint64_t n_hits, uint64_t* d_hits_pairs, uint64_t* d_locs,
                         int sm_count, cudaStream_t s) {
   if (n_hits == 0 || nq == 0) return cudaSuccess;
+  if (ix.wide) return launch_walk_wide(*ix.wide, d_sp_cnt_v, d_hit_off, nq, n_hits, d_hits_pairs, d_locs, sm_count, s);
+  const uint2* d_sp_cnt = static_cast<const uint2*>(d_sp_cnt_v);
   const bool map = d_hits_pairs != nullptr;
   uint64_t* out = map ? d_hits_pairs : d_locs;
   if (ix.full_sa != nullptr) {  // unsampled array present: a gather instead of expand + walk
@@ -780,29 +784,31 @@ cudaError_t launch_map_locations(const IndexView& ix, const uint64_t* d_locs, ui
 // ------------------------------------------------------------------ single steps
 
 template <int ALPHA>
-__global__ void single_update_kernel(IndexView ix, uint32_t sp, uint32_t ep, uint32_t c, uint32_t* out) {
+__global__ void single_update_kernel(IndexView ix, uint32_t sp, uint32_t ep, uint32_t c, uint64_t* out) {
   lf_update<ALPHA>(ix, sp, ep, c);
   out[0] = sp;
   out[1] = ep;
 }
 template <int ALPHA>
-__global__ void single_backstep_kernel(IndexView ix, uint32_t row, uint32_t* out) {
+__global__ void single_backstep_kernel(IndexView ix, uint32_t row, uint64_t* out) {
   out[0] = lf_backstep<ALPHA>(ix, row);
 }
-cudaError_t launch_single_update(const IndexView& ix, uint32_t sp, uint32_t ep, uint32_t dsym,
-                                 uint32_t* d_out2, cudaStream_t s) {
+cudaError_t launch_single_update(const IndexView& ix, uint64_t sp, uint64_t ep, uint32_t dsym,
+                                 uint64_t* d_out2, cudaStream_t s) {
+  if (ix.wide) return launch_single_update_wide(*ix.wide, sp, ep, dsym, d_out2, s);
   if (ix.alphabet == 0)
-    single_update_kernel<0><<<1, 1, 0, s>>>(ix, sp, ep, dsym, d_out2);
+    single_update_kernel<0><<<1, 1, 0, s>>>(ix, uint32_t(sp), uint32_t(ep), dsym, d_out2);
   else
-    single_update_kernel<1><<<1, 1, 0, s>>>(ix, sp, ep, dsym, d_out2);
+    single_update_kernel<1><<<1, 1, 0, s>>>(ix, uint32_t(sp), uint32_t(ep), dsym, d_out2);
   COUNT_LAUNCH();
   return cudaGetLastError();
 }
-cudaError_t launch_single_backstep(const IndexView& ix, uint32_t row, uint32_t* d_out, cudaStream_t s) {
+cudaError_t launch_single_backstep(const IndexView& ix, uint64_t row, uint64_t* d_out, cudaStream_t s) {
+  if (ix.wide) return launch_single_backstep_wide(*ix.wide, row, d_out, s);
   if (ix.alphabet == 0)
-    single_backstep_kernel<0><<<1, 1, 0, s>>>(ix, row, d_out);
+    single_backstep_kernel<0><<<1, 1, 0, s>>>(ix, uint32_t(row), d_out);
   else
-    single_backstep_kernel<1><<<1, 1, 0, s>>>(ix, row, d_out);
+    single_backstep_kernel<1><<<1, 1, 0, s>>>(ix, uint32_t(row), d_out);
   COUNT_LAUNCH();
   return cudaGetLastError();
 }

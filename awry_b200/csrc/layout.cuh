@@ -4,7 +4,9 @@
 // /root/reference/src/bwt.rs:12-25 (160 B nucleotide / 352 B amino, u64 milestones) and the
 // AVX2/NEON predicate + masked popcount of simd_instructions.rs:78-121.
 //
-// Device layout (row pointers are 32-bit: bwt_len < 2^32 is enforced at load time):
+// Device layout.  Row pointers are 32-bit while bwt_len < 2^32 - 256 (every BASELINE config); larger indexes
+// use the SAME blocks through WideView below (64-bit row pointers, block counts relative to 2^31-row
+// superblocks) and the kernels of kernels_wide.cu.
 //
 //   NUCLEOTIDE  block = 128 BWT rows = 64 B = 4 chunks of 16 B (one uint4 / one LDG.128 each)
 //               chunk j = { p0, p1, p2, cnt_j }   p_b = bit-plane b of rows 32j..32j+31
@@ -62,6 +64,8 @@ constexpr uint32_t AMINO_ROWS_PER_BLOCK = 64, AMINO_BLOCK_UINT4 = 8;
 constexpr uint32_t PAIR_ROWS_PER_BLOCK = 96, PAIR_BLOCK_UINT4 = 8;
 constexpr uint32_t WALK_ROWS_PER_BLOCK = 224, WALK_BLOCK_UINT4 = 8;
 
+struct WideView;
+
 struct IndexView {
   const uint4* __restrict__ blocks;
   const uint64_t* __restrict__ sa_words;
@@ -84,6 +88,28 @@ struct IndexView {
   uint32_t kmer_len;                       // 0 = no seed table
   uint32_t n_seqs;
   uint32_t alphabet;
+  const WideView* wide;                    // HOST pointer, never read on the device: set for indexes with
+                                           // bwt_len >= 2^32 - 256; the launchers then run kernels_wide.cu
+};
+
+// ---- wide indexes: SearchPtr = u64 (search.rs:7), suffix-array elements up to 64 bits
+// (compressed_suffix_array.rs:124-130).  The block layouts above are unchanged; their u32 block-start counts
+// are relative to the start of the block's SUPERBLOCK (2^31 rows), whose absolute counts live in sb_counts.
+constexpr uint32_t SB_SHIFT = 31;   // rows per superblock = 2^31 (WideView::sb_shift; AWRY_B200_SB_SHIFT lowers it so that
+                                    // tests cross superblock borders on small indexes)
+constexpr uint32_t SB_STRIDE = 24;  // u64 counts per superblock: nucleotide A,C,G,T at 0..3; amino symbol index s at s
+struct WideView {
+  const uint4* __restrict__ blocks;
+  const uint64_t* __restrict__ sa_words;
+  const ulonglong2* __restrict__ table;      // k-mer seeds (sp, ep), empty = (1, 0)
+  const uint64_t* __restrict__ seq_starts;
+  const uint64_t* __restrict__ sb_counts;    // [superblock][SB_STRIDE]
+  uint64_t c_lo[24];                         // C[c]      by device symbol
+  uint64_t c_hi[24];                         // C[c+1]-1
+  uint64_t bwt_len;
+  uint64_t dollar_row;
+  uint32_t sa_ratio, sa_pow2, sa_ratio_shift, sa_bits, kmer_len, n_seqs, alphabet;
+  uint32_t sb_shift;                         // log2(rows per superblock), >= 8
 };
 
 // 128-/256-bit read-only loads that do not allocate in L1: every block is touched once per
@@ -124,12 +150,15 @@ __device__ __forceinline__ uint32_t dna_match(const uint4& ch, uint32_t m0, uint
 struct DnaBlockRegs {
   uint4 ch[4];
 };
-__device__ __forceinline__ DnaBlockRegs dna_load_block(const IndexView& ix, uint32_t blk) {
+__device__ __forceinline__ DnaBlockRegs dna_load_block(const uint4* __restrict__ blocks, uint64_t blk) {
   DnaBlockRegs b;
-  const uint4* p = ix.blocks + size_t(blk) * DNA_BLOCK_UINT4;
+  const uint4* p = blocks + size_t(blk) * DNA_BLOCK_UINT4;
 #pragma unroll
   for (int j = 0; j < 4; j++) b.ch[j] = ldg128(p + j);
   return b;
+}
+__device__ __forceinline__ DnaBlockRegs dna_load_block(const IndexView& ix, uint32_t blk) {
+  return dna_load_block(ix.blocks, blk);
 }
 // milestone of device symbol c (0..4) at the start of block blk
 __device__ __forceinline__ uint32_t dna_milestone(const IndexView& ix, const DnaBlockRegs& b,
