@@ -632,6 +632,7 @@ int awry_index_info(const awry_index* ix, awry_info* info) {
     info->device_bytes_full_sa = ix->reps[0]->bytes_full_sa;
     info->device_bytes_lean_sa = ix->reps[0]->bytes_lean;
     for (size_t i = 0; i < ix->reps.size() && i < 16; i++) info->devices[i] = ix->reps[i]->device;
+    info->row_pointer_bits = ix->wide ? 64 : 32;
   });
 }
 

@@ -20,6 +20,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
@@ -112,9 +114,9 @@ __global__ void flag_ties_kernel(const uint64_t* __restrict__ keys, uint64_t n1,
 }
 
 // One thread block per 256-row reference block: planes via warp ballots, per-block symbol counts.
-template <int ALPHA>
+template <int ALPHA, class SaT>
 __global__ void __launch_bounds__(256)
-    bwt_blocks_kernel(const uint8_t* __restrict__ sym, const uint32_t* __restrict__ sa, uint64_t n1,
+    bwt_blocks_kernel(const uint8_t* __restrict__ sym, const SaT* __restrict__ sa, uint64_t n1,
                       uint64_t* __restrict__ blocks, uint32_t* __restrict__ counts /* [card][n_blocks] */,
                       uint64_t n_blocks) {
   constexpr int PLANES = ALPHA == 0 ? 3 : 5;
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(256)
   bool valid = row < n1;
   uint8_t idx = 0, code = 0;
   if (valid) {
-    uint32_t v = sa[row];
+    const SaT v = sa[row];
     idx = v == 0 ? 0 : sym[v - 1];  // fm_index.rs:220-223
     code = index_to_code(ALPHA, idx);
   }
@@ -167,7 +169,8 @@ __global__ void write_milestones_kernel(const uint64_t* __restrict__ ms /* [card
 }
 
 // one thread per output word of the bit-packed sampled SA
-__global__ void pack_sa_kernel(const uint32_t* __restrict__ sa, uint64_t n1, uint64_t ratio, uint32_t bits,
+template <class SaT>
+__global__ void pack_sa_kernel(const SaT* __restrict__ sa, uint64_t n1, uint64_t ratio, uint32_t bits,
                                uint64_t n_words, uint64_t* __restrict__ words) {
   uint64_t w = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
   if (w >= n_words) return;
@@ -345,7 +348,7 @@ int build_parts_impl(int alphabet, const uint8_t* text, bool text_on_device, uin
   try {
     if (ratio == 0) throw std::string("ratio must be >= 1");
     const uint64_t n1 = n + 1;
-    if (n1 >= (1ull << 32)) throw std::string("the GPU builder is limited to < 2^32 symbols");
+    if (n1 >= (1ull << 32) - 256) throw std::string("internal: 2^32 symbols or more belong to build_parts_wide_impl");
     CU(cudaSetDevice(device));
     const int card = alphabet == 0 ? 6 : 22;
     const size_t words_per_block = alphabet == 0 ? 20 : 44;
@@ -498,9 +501,9 @@ int build_parts_impl(int alphabet, const uint8_t* text, bool text_on_device, uin
     CU(cudaMalloc(&d_counts, uint64_t(card) * n_blocks * 4));
     CU(cudaMalloc(&d_ms, uint64_t(card) * n_blocks * 8));
     if (alphabet == 0)
-      bwt_blocks_kernel<0><<<unsigned(n_blocks), 256>>>(d_sym, sa, n1, d_blocks, d_counts, n_blocks);
+      bwt_blocks_kernel<0, uint32_t><<<unsigned(n_blocks), 256>>>(d_sym, sa, n1, d_blocks, d_counts, n_blocks);
     else
-      bwt_blocks_kernel<1><<<unsigned(n_blocks), 256>>>(d_sym, sa, n1, d_blocks, d_counts, n_blocks);
+      bwt_blocks_kernel<1, uint32_t><<<unsigned(n_blocks), 256>>>(d_sym, sa, n1, d_blocks, d_counts, n_blocks);
     CU(cudaDeviceSynchronize());
     ph[4] = now_s() - t;
     t = now_s();
@@ -545,7 +548,7 @@ int build_parts_impl(int alphabet, const uint8_t* text, bool text_on_device, uin
     uint64_t n_elems = (n1 + ratio - 1) / ratio;
     uint64_t n_words = uint64_t(((unsigned __int128)n_elems * bits + 63) / 64);
     CU(cudaMalloc(&d_saw, (n_words + 1) * 8));
-    pack_sa_kernel<<<unsigned((n_words + 255) / 256), 256>>>(sa, n1, ratio, bits, n_words, d_saw);
+    pack_sa_kernel<uint32_t><<<unsigned((n_words + 255) / 256), 256>>>(sa, n1, ratio, bits, n_words, d_saw);
     CU(cudaDeviceSynchronize());
     if (sa_words_out) CU(cudaMemcpy(sa_words_out, d_saw, n_words * 8, cudaMemcpyDeviceToHost));
     if (blocks_out) CU(cudaMemcpy(blocks_out, d_blocks, n_blocks * words_per_block * 8, cudaMemcpyDeviceToHost));
@@ -579,6 +582,288 @@ int build_parts_impl(int alphabet, const uint8_t* text, bool text_on_device, uin
   return rc;
 }
 
+// ---- texts of 2^32 symbols or more: 64-bit suffix-array elements, sorted bucket by bucket ----
+// One radix sort of (64-bit key, 64-bit position) pairs over 5 G suffixes needs 160 GB of buffers.  The
+// suffixes are therefore sorted per FIRST SYMBOL (6 / 22 buckets, already in suffix order between them):
+// positions of the bucket selected with a stream compaction, keys of the following symbols packed as above,
+// one radix sort per bucket, written behind the previous bucket.  Ties (suffixes sharing the whole packed key:
+// a handful on random text) are fixed on the host by suffix comparison; repeat-rich text beyond 2^32 symbols
+// is refused (the prefix-doubling rounds above keep 32-bit ranks).  Also runs on small texts when
+// AWRY_B200_BUILD_WIDE=1 (tests).
+struct FirstSymbolIs {
+  const uint8_t* sym;
+  uint8_t want;
+  __host__ __device__ bool operator()(uint64_t i) const { return sym[i] == want; }
+};
+
+template <int BITS>
+__global__ void make_keys_at_kernel(const uint8_t* __restrict__ sym, uint64_t n1, const uint64_t* __restrict__ pos,
+                                    uint64_t count, uint64_t* __restrict__ keys) {
+  constexpr int SPK = 64 / BITS;
+  uint64_t stride = gridDim.x * uint64_t(blockDim.x);
+  for (uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; t < count; t += stride) {
+    const uint64_t i = pos[t] + 1;  // the first symbol is the bucket's: keys start behind it
+    uint64_t key = 0;
+#pragma unroll 8
+    for (int j = 0; j < SPK; j++) {
+      uint32_t s = i + j < n1 ? sym[i + j] : 0;
+      if (BITS == 2) s = s == 0 ? 0 : (s == 5 ? 3 : s - 1);
+      key = (key << BITS) | s;
+    }
+    if (BITS * SPK < 64) key <<= (64 - BITS * SPK);
+    keys[t] = key;
+  }
+}
+
+int build_parts_wide_impl(int alphabet, const uint8_t* text, bool text_on_device, uint64_t n, uint64_t ratio, int device,
+                          uint64_t* blocks_out, uint64_t* prefix_sums_out, uint64_t* sa_words_out, double* phase_s,
+                          std::string& err, awry::DeviceParts* keep) {
+  uint8_t* d_sym = nullptr;
+  uint64_t *d_sa = nullptr, *d_keys[2] = {nullptr, nullptr}, *d_pos[2] = {nullptr, nullptr};
+  uint64_t *d_blocks = nullptr, *d_ms = nullptr, *d_saw = nullptr;
+  uint32_t* d_counts = nullptr;
+  uint8_t* d_tied = nullptr;
+  void* d_temp = nullptr;
+  unsigned long long* d_num = nullptr;
+  int rc = 0;
+  double ph[8] = {0};
+  try {
+    if (ratio == 0) throw std::string("ratio must be >= 1");
+    const uint64_t n1 = n + 1;
+    CU(cudaSetDevice(device));
+    const int card = alphabet == 0 ? 6 : 22;
+    const size_t words_per_block = alphabet == 0 ? 20 : 44;
+    const uint64_t n_blocks = (n1 + 255) / 256;
+    double t0 = now_s(), t = t0;
+    CU(cudaMalloc(&d_sym, n1 + 64));
+    bool pure2 = alphabet == 0;
+    {
+      CU(cudaMemcpy(d_sym, text, n, text_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+      unsigned int* d_flags = nullptr;
+      CU(cudaMalloc(&d_flags, 8));
+      CU(cudaMemset(d_flags, 0, 8));
+      ascii_to_sym_kernel<<<148 * 16, 256>>>(alphabet, n, d_sym, d_flags);
+      unsigned int flags[2] = {0, 0};
+      CU(cudaMemcpy(flags, d_flags, 8, cudaMemcpyDeviceToHost));
+      cudaFree(d_flags);
+      if (flags[0]) throw std::string("text contains a sentinel ('$' or '#')");
+      if (flags[1]) pure2 = false;
+    }
+    ph[0] = now_s() - t;
+    t = now_s();
+
+    // symbol histogram on the host side of a device reduction: bucket sizes
+    std::vector<uint64_t> bucket(card, 0);
+    CU(cudaMalloc(&d_num, 8));
+    CU(cudaMalloc(&d_sa, n1 * 8));
+    uint64_t max_bucket = 0;
+    {
+      // sizes first (one counting pass per symbol is cheap next to the sorts)
+      for (int s = 0; s < card; s++) {
+        cub::CountingInputIterator<uint64_t> it(0);
+        cub::TransformInputIterator<int, FirstSymbolIs, cub::CountingInputIterator<uint64_t>> flag(it, FirstSymbolIs{d_sym, uint8_t(s)});
+        size_t tb = 0;
+        CU(cub::DeviceReduce::Sum(nullptr, tb, flag, d_num, (long long)n1));
+        CU(cudaMalloc(&d_temp, tb + 16));
+        CU(cub::DeviceReduce::Sum(d_temp, tb, flag, d_num, (long long)n1));
+        unsigned long long c = 0;
+        CU(cudaMemcpy(&c, d_num, 8, cudaMemcpyDeviceToHost));
+        cudaFree(d_temp);
+        d_temp = nullptr;
+        bucket[s] = c;
+        max_bucket = std::max<uint64_t>(max_bucket, c);
+      }
+    }
+    for (int i = 0; i < 2; i++) {
+      CU(cudaMalloc(&d_keys[i], (max_bucket + 1) * 8));
+      CU(cudaMalloc(&d_pos[i], (max_bucket + 1) * 8));
+    }
+    CU(cudaMalloc(&d_tied, max_bucket + 1));
+    ph[1] = now_s() - t;
+    t = now_s();
+
+    std::vector<uint8_t> hsym;  // host copy of the symbols, fetched only if a tie needs it
+    uint64_t base = 0, ties_total = 0;
+    for (int s = 0; s < card; s++) {
+      const uint64_t cnt = bucket[s];
+      if (cnt == 0) continue;
+      {  // positions whose first symbol is s, ascending
+        cub::CountingInputIterator<uint64_t> it(0);
+        size_t tb = 0;
+        CU(cub::DeviceSelect::If(nullptr, tb, it, d_pos[0], d_num, (long long)n1, FirstSymbolIs{d_sym, uint8_t(s)}));
+        CU(cudaMalloc(&d_temp, tb + 16));
+        CU(cub::DeviceSelect::If(d_temp, tb, it, d_pos[0], d_num, (long long)n1, FirstSymbolIs{d_sym, uint8_t(s)}));
+        cudaFree(d_temp);
+        d_temp = nullptr;
+      }
+      if (alphabet == 0 && pure2)
+        make_keys_at_kernel<2><<<148 * 16, 256>>>(d_sym, n1, d_pos[0], cnt, d_keys[0]);
+      else if (alphabet == 0)
+        make_keys_at_kernel<3><<<148 * 16, 256>>>(d_sym, n1, d_pos[0], cnt, d_keys[0]);
+      else
+        make_keys_at_kernel<5><<<148 * 16, 256>>>(d_sym, n1, d_pos[0], cnt, d_keys[0]);
+      cub::DoubleBuffer<uint64_t> kb(d_keys[0], d_keys[1]);
+      cub::DoubleBuffer<uint64_t> vb(d_pos[0], d_pos[1]);
+      size_t tb = 0;
+      CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, kb, vb, (long long)cnt, 0, 64));
+      CU(cudaMalloc(&d_temp, tb + 16));
+      CU(cub::DeviceRadixSort::SortPairs(d_temp, tb, kb, vb, (long long)cnt, 0, 64));
+      CU(cudaDeviceSynchronize());
+      cudaFree(d_temp);
+      d_temp = nullptr;
+      uint64_t* keys_sorted = kb.Current();
+      uint64_t* sa_b = vb.Current();
+      // ties inside the bucket
+      flag_ties_kernel<<<148 * 16, 256>>>(keys_sorted, cnt, d_tied);
+      uint64_t* d_rows = vb.Alternate();
+      {
+        cub::CountingInputIterator<uint64_t> it(0);
+        size_t tb2 = 0;
+        CU(cub::DeviceSelect::Flagged(nullptr, tb2, it, d_tied, d_rows, d_num, (long long)cnt));
+        CU(cudaMalloc(&d_temp, tb2 + 16));
+        CU(cub::DeviceSelect::Flagged(d_temp, tb2, it, d_tied, d_rows, d_num, (long long)cnt));
+        CU(cudaDeviceSynchronize());
+        cudaFree(d_temp);
+        d_temp = nullptr;
+      }
+      unsigned long long n_tied = 0;
+      CU(cudaMemcpy(&n_tied, d_num, 8, cudaMemcpyDeviceToHost));
+      ties_total += n_tied;
+      if (ties_total > 4000000ull)
+        throw std::string("repeat-rich text of 2^32 symbols or more: too many suffixes share their first 21-32 "
+                          "symbols for the host fix-up, and the prefix-doubling rounds keep 32-bit ranks");
+      if (n_tied > 0) {
+        std::vector<uint64_t> rows(n_tied), pos(n_tied), rkeys(n_tied);
+        CU(cudaMemcpy(rows.data(), d_rows, n_tied * 8, cudaMemcpyDeviceToHost));
+        for (unsigned long long i = 0; i < n_tied;) {  // runs of consecutive rows -> few large copies
+          unsigned long long j = i + 1;
+          while (j < n_tied && rows[j] == rows[j - 1] + 1) j++;
+          CU(cudaMemcpy(pos.data() + i, sa_b + rows[i], (j - i) * 8, cudaMemcpyDeviceToHost));
+          CU(cudaMemcpy(rkeys.data() + i, keys_sorted + rows[i], (j - i) * 8, cudaMemcpyDeviceToHost));
+          i = j;
+        }
+        if (hsym.empty()) {
+          hsym.resize(n1);
+          CU(cudaMemcpy(hsym.data(), d_sym, n1, cudaMemcpyDeviceToHost));
+        }
+        auto less = [&](uint64_t a, uint64_t b) {
+          if (a == b) return false;
+          uint64_t k = 0;
+          while (hsym[a + k] == hsym[b + k]) k++;  // terminates: '$' is unique
+          return hsym[a + k] < hsym[b + k];
+        };
+        for (unsigned long long i = 0; i < n_tied;) {
+          unsigned long long j = i + 1;
+          while (j < n_tied && rows[j] == rows[j - 1] + 1 && rkeys[j] == rkeys[i]) j++;
+          std::sort(pos.begin() + i, pos.begin() + j, less);
+          CU(cudaMemcpy(sa_b + rows[i], pos.data() + i, (j - i) * 8, cudaMemcpyHostToDevice));
+          i = j;
+        }
+      }
+      CU(cudaMemcpy(d_sa + base, sa_b, cnt * 8, cudaMemcpyDeviceToDevice));
+      base += cnt;
+    }
+    if (base != n1) throw std::string("internal: buckets do not add up");
+    for (int i = 0; i < 2; i++) {
+      cudaFree(d_keys[i]);
+      cudaFree(d_pos[i]);
+      d_keys[i] = d_pos[i] = nullptr;
+    }
+    cudaFree(d_tied);
+    d_tied = nullptr;
+    ph[2] = now_s() - t;
+    t = now_s();
+
+    CU(cudaMalloc(&d_blocks, n_blocks * words_per_block * 8));
+    CU(cudaMemset(d_blocks, 0, n_blocks * words_per_block * 8));
+    CU(cudaMalloc(&d_counts, uint64_t(card) * n_blocks * 4));
+    CU(cudaMalloc(&d_ms, uint64_t(card) * n_blocks * 8));
+    if (alphabet == 0)
+      bwt_blocks_kernel<0, uint64_t><<<unsigned(n_blocks), 256>>>(d_sym, d_sa, n1, d_blocks, d_counts, n_blocks);
+    else
+      bwt_blocks_kernel<1, uint64_t><<<unsigned(n_blocks), 256>>>(d_sym, d_sa, n1, d_blocks, d_counts, n_blocks);
+    CU(cudaDeviceSynchronize());
+    ph[4] = now_s() - t;
+    t = now_s();
+    {
+      size_t tb = 0;
+      CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_counts, d_ms, (long long)n_blocks));
+      CU(cudaMalloc(&d_temp, tb + 16));
+      std::vector<uint64_t> totals(card, 0);
+      for (int s = 0; s < card; s++) {
+        CU(cub::DeviceScan::ExclusiveSum(d_temp, tb, d_counts + uint64_t(s) * n_blocks, d_ms + uint64_t(s) * n_blocks,
+                                         (long long)n_blocks));
+        uint64_t last_ms = 0;
+        uint32_t last_cnt = 0;
+        CU(cudaMemcpy(&last_ms, d_ms + uint64_t(s) * n_blocks + n_blocks - 1, 8, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&last_cnt, d_counts + uint64_t(s) * n_blocks + n_blocks - 1, 4, cudaMemcpyDeviceToHost));
+        totals[s] = last_ms + last_cnt;
+      }
+      cudaFree(d_temp);
+      d_temp = nullptr;
+      uint64_t acc = 0;  // fm_index.rs:233-240
+      for (int c = 0; c <= card; c++) {
+        prefix_sums_out[c] = acc;
+        if (c < card) acc += totals[c];
+      }
+      const int nms = alphabet == 0 ? 8 : 24;
+      const uint64_t threads = n_blocks * nms;
+      if (alphabet == 0)
+        write_milestones_kernel<0><<<unsigned((threads + 255) / 256), 256>>>(d_ms, n_blocks, d_blocks);
+      else
+        write_milestones_kernel<1><<<unsigned((threads + 255) / 256), 256>>>(d_ms, n_blocks, d_blocks);
+      CU(cudaDeviceSynchronize());
+    }
+    cudaFree(d_counts);
+    d_counts = nullptr;
+    cudaFree(d_ms);
+    d_ms = nullptr;
+    ph[5] = now_s() - t;
+    t = now_s();
+
+    const unsigned bits = bits_per_element(n1);
+    const uint64_t n_elems = (n1 + ratio - 1) / ratio;
+    const uint64_t n_words = uint64_t(((unsigned __int128)n_elems * bits + 63) / 64);
+    CU(cudaMalloc(&d_saw, (n_words + 1) * 8));
+    pack_sa_kernel<uint64_t><<<unsigned((n_words + 255) / 256), 256>>>(d_sa, n1, ratio, bits, n_words, d_saw);
+    CU(cudaDeviceSynchronize());
+    cudaFree(d_sa);
+    d_sa = nullptr;
+    if (sa_words_out) CU(cudaMemcpy(sa_words_out, d_saw, n_words * 8, cudaMemcpyDeviceToHost));
+    if (blocks_out) CU(cudaMemcpy(blocks_out, d_blocks, n_blocks * words_per_block * 8, cudaMemcpyDeviceToHost));
+    if (keep) {
+      keep->d_blocks = d_blocks;
+      keep->d_sa_words = d_saw;
+      keep->n_block_words = n_blocks * words_per_block;
+      keep->n_sa_words = n_words;
+      keep->device = device;
+      d_blocks = nullptr;
+      d_saw = nullptr;
+    }
+    ph[6] = now_s() - t;
+    ph[7] = now_s() - t0;
+  } catch (const std::string& m) {
+    err = m;
+    rc = -1;
+  }
+  cudaFree(d_sym);
+  cudaFree(d_sa);
+  for (int i = 0; i < 2; i++) {
+    cudaFree(d_keys[i]);
+    cudaFree(d_pos[i]);
+  }
+  cudaFree(d_blocks);
+  cudaFree(d_ms);
+  cudaFree(d_saw);
+  cudaFree(d_counts);
+  cudaFree(d_tied);
+  cudaFree(d_temp);
+  cudaFree(d_num);
+  if (phase_s) memcpy(phase_s, ph, sizeof ph);
+  return rc;
+}
+
+
 
 }  // namespace
 
@@ -611,8 +896,13 @@ int build_parts(int alphabet, const uint8_t* text, uint64_t n, uint64_t ratio, i
   cudaGetLastError();
   int prev = -1;
   cudaGetDevice(&prev);
-  int rc = build_parts_impl(alphabet, text, on_device, n, ratio, device, blocks_out, prefix_sums_out, sa_words_out,
-                            phase_s, err, keep);
+  // 64-bit suffix-array elements from 2^32 - 256 symbols on (AWRY_B200_BUILD_WIDE=1: always -- tests)
+  const char* bw = getenv("AWRY_B200_BUILD_WIDE");
+  const bool wide = n + 1 >= (1ull << 32) - 256 || (bw && bw[0] == '1');
+  int rc = wide ? build_parts_wide_impl(alphabet, text, on_device, n, ratio, device, blocks_out, prefix_sums_out,
+                                        sa_words_out, phase_s, err, keep)
+                : build_parts_impl(alphabet, text, on_device, n, ratio, device, blocks_out, prefix_sums_out, sa_words_out,
+                                   phase_s, err, keep);
   if (prev >= 0) cudaSetDevice(prev);
   return rc;
 }

@@ -129,7 +129,7 @@ int awry_build_parts(uint32_t alphabet, const uint8_t* text, uint64_t n, uint64_
   return guarded([&] {
     if (!text || !blocks || !prefix_sums || !sa_words) fail(AWRY_ERR_INVALID_ARG, "null argument");
     if (alphabet > 1) fail(AWRY_ERR_INVALID_ARG, "invalid alphabet id %u", alphabet);
-    if (n + 1 >= (1ull << 32) - 256) fail(AWRY_ERR_UNSUPPORTED, "text of %llu symbols: 32-bit row pointers", (unsigned long long)n);
+    if (n + 1 >= (1ull << 56)) fail(AWRY_ERR_UNSUPPORTED, "text of %llu symbols", (unsigned long long)n);
     pick_devices(&device, 1);
     std::string err;
     if (build_parts(int(alphabet), text, n, sa_ratio ? sa_ratio : 8, device, blocks, prefix_sums, sa_words,
@@ -193,7 +193,7 @@ int awry_index_build(const awry_build_args* a, const int* devices, int n_dev, aw
       fail(AWRY_ERR_IO, "%s", err.c_str());
     tick("read sequence file");
     const uint64_t n = text.size(), bwt_len = n + 1;
-    if (bwt_len >= (1ull << 32) - 256) fail(AWRY_ERR_UNSUPPORTED, "text of %llu symbols: 32-bit row pointers", (unsigned long long)n);
+    if (bwt_len >= (1ull << 56)) fail(AWRY_ERR_UNSUPPORTED, "text of %llu symbols", (unsigned long long)n);
     int dev0 = a->device;
     std::vector<int> devs = out ? pick_devices(devices ? devices : &dev0, devices ? n_dev : 1) : pick_devices(&dev0, 1);
     // construction on devs[0]; the reference-layout arrays stay on the device and are re-laid out there

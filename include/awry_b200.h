@@ -33,7 +33,7 @@ typedef enum awry_status {
   AWRY_ERR_CUDA = -4,        /* no device, allocation or launch failure                        */
   AWRY_ERR_INVALID_QUERY = -5, /* empty query or a query containing '$'/'#': the reference
                                   panics or is UB here (fm_index.rs:406, bwt.rs:127)           */
-  AWRY_ERR_UNSUPPORTED = -6, /* e.g. bwt_len >= 2^32 (device layout uses 32-bit row pointers)  */
+  AWRY_ERR_UNSUPPORTED = -6, /* e.g. 2-bit packed queries on a protein index                       */
   AWRY_ERR_NOMEM = -7,
   AWRY_ERR_CAPACITY = -8     /* caller-owned output buffer too small; the needed size is reported */
 } awry_status;
@@ -73,6 +73,8 @@ typedef struct awry_info {
   uint64_t device_bytes_full_sa; /* unsampled suffix array (locate accelerator), 0 if not built */
   uint64_t device_bytes_lean_sa; /* walk blocks + position-sampled suffix array (bounded locate), 0 if not built */
   int32_t devices[16];
+  uint32_t row_pointer_bits;    /* 32 while bwt_len < 2^32 - 256, else 64 (SearchPtr = u64, search.rs:7) */
+  uint32_t reserved;
 } awry_info;
 
 /* The fields FmIndex::new hands over after the reference's CPU construction
