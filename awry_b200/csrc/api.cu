@@ -201,11 +201,16 @@ void build_replica0(awry_index* ix, Replica& r, Source& src_blocks_then_rest, bo
   cudaFree(d_dollar);
   if (dollar == ~0ull) fail(AWRY_ERR_FORMAT, "no sentinel row found in the BWT blocks");
 
-  // prefix sums (fm_index_file.rs:265-270)
+  // prefix sums (fm_index_file.rs:265-270): C[0] = 0, C[1] = 1 (one '$' row), non-decreasing, C[card] = bwt_len --
+  // every c_hi = C[c+1] - 1 and every row pointer the kernels form rests on this
   src_blocks_then_rest.read(ix->prefix_sums, size_t(ix->card + 1) * 8, "prefix sums");
   if (ix->prefix_sums[ix->card] != ix->bwt_len)
     fail(AWRY_ERR_FORMAT, "prefix sums do not add up to bwt_len (%llu vs %llu)",
          (unsigned long long)ix->prefix_sums[ix->card], (unsigned long long)ix->bwt_len);
+  if (ix->prefix_sums[0] != 0 || ix->prefix_sums[1] != 1)
+    fail(AWRY_ERR_FORMAT, "prefix sums do not start with 0, 1 (exactly one sentinel row)");
+  for (int c = 0; c < ix->card; c++)
+    if (ix->prefix_sums[c + 1] < ix->prefix_sums[c]) fail(AWRY_ERR_FORMAT, "prefix sums decrease at symbol %d", c);
 
   // sampled suffix array words, verbatim (fm_index_file.rs:272-278)
   r.bytes_sa = size_t(ix->n_sa_words + 2) * 8;
@@ -238,8 +243,17 @@ void build_replica0(awry_index* ix, Replica& r, Source& src_blocks_then_rest, bo
     uint8_t k = 0;
     src_blocks_then_rest.read(&k, 1, "kmer length");
     ix->kmer_len_file = k;
+    // (card-2)^k x 16 bytes must lie inside the file: an unbounded k would overflow the size and the seek
+    // would land anywhere
+    const uint32_t k_max = ix->alphabet == AWRY_NUCLEOTIDE ? 27 : 12;  // 4^27, 20^12 entries x 16 B < 2^63
+    if (k > k_max) fail(AWRY_ERR_FORMAT, "k-mer length %u in the file is implausible", unsigned(k));
     uint64_t n_entries = ipow(uint64_t(ix->card - 2), k);
     if (src_blocks_then_rest.f) {
+      struct stat sb;
+      const off_t here = ftello(src_blocks_then_rest.f);
+      if (fstat(fileno(src_blocks_then_rest.f), &sb) != 0 || here < 0 ||
+          uint64_t(sb.st_size) < uint64_t(here) + n_entries * 16 + 8)
+        fail(AWRY_ERR_FORMAT, "file too short for its k-mer table section (k = %u)", unsigned(k));
       if (fseeko(src_blocks_then_rest.f, off_t(n_entries * 16), SEEK_CUR) != 0)
         fail(AWRY_ERR_IO, "cannot seek past the kmer table");
     }
@@ -467,12 +481,16 @@ void make_replicas(awry_index* ix, const std::vector<int>& devs, Source& src, bo
     // sequence index (sequence_index.rs:155-183)
     uint64_t n = 0;
     src.read(&n, 8, "sequence count");
-    if (n > (1ull << 32)) fail(AWRY_ERR_FORMAT, "implausible sequence count");
+    if (n >= (1ull << 32)) fail(AWRY_ERR_FORMAT, "implausible sequence count");
     for (uint64_t i = 0; i < n; i++) {
       uint64_t start = 0, hl = 0;
       src.read(&start, 8, "sequence start");
       src.read(&hl, 8, "header length");
       if (hl > (1ull << 30)) fail(AWRY_ERR_FORMAT, "implausible header length");
+      // the device maps a position to its record by binary search over the starts (sequence_index.rs:108-141)
+      if (start >= ix->bwt_len || (i > 0 && start <= ix->seq_starts.back()))
+        fail(AWRY_ERR_FORMAT, "sequence start %llu of record %llu is out of order or beyond the text",
+             (unsigned long long)start, (unsigned long long)i);
       std::string h(hl, '\0');
       src.read(h.data(), hl, "header");
       ix->seq_starts.push_back(start);
@@ -540,6 +558,21 @@ int awry_index_load(const char* path, const int* devices, int n_dev, awry_index*
     if (hdr[3] > 1) fail(AWRY_ERR_FORMAT, "invalid symbol alphabet id %llu", (unsigned long long)hdr[3]);
     ix->alphabet = int(hdr[3]);
     check_header(ix.get());
+    {  // the sections the header implies must fit the file before anything is read or allocated from them
+      struct stat sb;
+      const uint64_t need_bytes = 43 + ((ix->bwt_len + 255) / 256) * (ix->alphabet == AWRY_NUCLEOTIDE ? 160 : 352) +
+                                  uint64_t(ix->card + 1) * 8 + ix->n_sa_words * 8 + 1 + 8;
+      if (fstat(fileno(f), &sb) != 0 || uint64_t(sb.st_size) < need_bytes)
+        fail(AWRY_ERR_FORMAT, "file is shorter (%lld bytes) than its header implies (>= %llu bytes)",
+             (long long)sb.st_size, (unsigned long long)need_bytes);
+      // ... and the k-mer table section, whose size hangs on one byte (kmer_lookup_table.rs:55-77)
+      uint8_t k = 0;
+      if (pread(fileno(f), &k, 1, off_t(need_bytes - 9)) != 1) fail(AWRY_ERR_IO, "cannot read the k-mer length");
+      if (k > (ix->alphabet == AWRY_NUCLEOTIDE ? 27 : 12)) fail(AWRY_ERR_FORMAT, "k-mer length %u in the file is implausible", unsigned(k));
+      if (uint64_t(sb.st_size) < need_bytes + ipow(uint64_t(ix->card - 2), k) * 16)
+        fail(AWRY_ERR_FORMAT, "file is shorter (%lld bytes) than its k-mer table section (k = %u) needs",
+             (long long)sb.st_size, unsigned(k));
+    }
     auto devs = pick_devices(devices, n_dev);
     Source src;
     src.f = f;

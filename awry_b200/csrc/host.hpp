@@ -99,6 +99,8 @@ struct ProfState {
 };
 extern ProfState g_prof;
 
+void prof_collect_locked();
+
 struct ProfScope {
   bool on;
   cudaStream_t st;
@@ -117,10 +119,9 @@ struct ProfScope {
     cudaEventRecord(sp.b, st);
     std::lock_guard<std::mutex> lk(g_prof.mu);
     g_prof.spans.push_back(sp);
+    if (g_prof.spans.size() >= 8192) prof_collect_locked();  // nobody asked for a while: fold the events in
   }
 };
-
-void prof_collect_locked();
 
 extern SearchVariant g_variant;  // experiments only (awry_set_search_variant)
 extern int g_host_pack;      // -1 = auto (AWRY_B200_HOST_PACK, CPU support, >= 4 pool threads), 0 = off, 1 = on

@@ -6,7 +6,7 @@ its range, results are concatenated in range order.  No collective sits on the d
 only communication is the final gather of results to the caller's rank.
 
 `split_by_bytes` is the same rule the C++ library applies across replicas inside one process
-(`for_each_replica_range`, awry_b200/csrc/api.cu).
+(`for_each_replica_range`, awry_b200/csrc/batch.cu).
 """
 from typing import Callable, List, Optional, Tuple
 

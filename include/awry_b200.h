@@ -261,6 +261,8 @@ int awry_count_device(const awry_index *index, int replica, const uint8_t *d_qby
 int awry_locate_device(const awry_index *index, int replica, const uint8_t *d_qbytes,
                        const uint64_t *d_qoff, uint64_t nq, uint32_t flags, uint64_t *d_hit_off,
                        awry_hit **d_hits, uint64_t *n_hits, void *cuda_stream);
+/* d_ptr came from the library's stream-ordered pool; the caller must have synchronised the stream that last
+ * used it (the release itself is not ordered against the caller's streams). */
 int awry_device_free(const awry_index *index, int replica, void *d_ptr);
 /* The *_device calls are asynchronous, so an empty / sentinel-carrying query cannot be reported
  * by them; it is latched per replica.  This synchronises `cuda_stream`, returns

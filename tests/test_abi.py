@@ -110,6 +110,24 @@ def test_bad_arguments_are_errors_not_crashes(tmp_path):
     assert lib.awry_parts_sa_words(123451, 8) == (15432 * 17 + 63) // 64   # compressed_suffix_array.rs:113-130
 
 
+def test_truncated_index_files_are_refused_before_any_device_work(tmp_path):
+    """the loader checks the sizes its header implies against the file before it seeks or allocates"""
+    from awry_b200 import fm_index as f
+    lib = f.native()
+    out = C.c_void_p()
+    golden = open(os.path.join(ROOT, "tests", "golden", "appendix_a.awry"), "rb").read()
+    for cut in (12, 43, 100, 203, 250, 270, len(golden) - 40):
+        p = tmp_path / f"cut{cut}.awry"
+        p.write_bytes(golden[:cut])
+        assert lib.awry_index_load(os.fsencode(str(p)), None, 0, C.byref(out)) == -3, cut
+    huge = bytearray(golden)
+    huge[27:35] = (2**40).to_bytes(8, "little")            # bwt_len far beyond the file
+    p = tmp_path / "huge.awry"
+    p.write_bytes(bytes(huge))
+    assert lib.awry_index_load(os.fsencode(str(p)), None, 0, C.byref(out)) == -3
+    assert b"shorter" in lib.awry_last_error()
+
+
 def test_product_never_touches_the_oracle():
     """the shipped package must not import, link or execute anything under oracle/ or fixtures/"""
     pkg = os.path.join(ROOT, "awry_b200")

@@ -254,3 +254,39 @@ def test_bounded_walk_is_the_default_without_the_unsampled_array(fx, po, monkeyp
         finally:
             f.set_locate_variant(0)
         assert np.array_equal(off1, woff) and np.array_equal(hits1, whits)
+
+
+def test_corrupt_index_files_fail_with_format_errors(tmp_path):
+    """ADVICE r1: untrusted file fields -- k-mer length, prefix sums, sequence starts and count -- are validated;
+    a corrupt file is AWRY_ERR_FORMAT, never an out-of-range row pointer or a load that does not end"""
+    import os
+    from awry_b200 import AwryError, FmIndex
+    golden = open(os.path.join(os.path.dirname(__file__), "golden", "appendix_a.awry"), "rb").read()
+    # layout of the 557-byte file (SURVEY Appendix A): blocks @43 (160 B), prefix sums @203 (7 x 8), SA @259 (8 B),
+    # k byte @267, table 16 x 16 B, sequence index @524: n, start, header_len, header
+    def variant(name, edit):
+        b = bytearray(golden)
+        edit(b)
+        p = tmp_path / f"{name}.awry"
+        p.write_bytes(bytes(b))
+        return str(p)
+
+    def put(b, at, v):
+        b[at:at + 8] = int(v).to_bytes(8, "little")
+
+    cases = {
+        "k_huge": lambda b: b.__setitem__(267, 40),
+        "prefix_decreasing": lambda b: (put(b, 203 + 16, 12), put(b, 203 + 24, 9)),
+        "prefix_first": lambda b: put(b, 203 + 8, 2),
+        "prefix_total": lambda b: put(b, 203 + 48, 21),
+        "seq_count": lambda b: put(b, 524, 2**32),
+        "seq_start_beyond": lambda b: put(b, 532, 20),
+        "alphabet": lambda b: put(b, 35, 2),
+        "ratio_zero": lambda b: put(b, 19, 0),
+    }
+    for name, edit in cases.items():
+        with pytest.raises(AwryError) as e:
+            FmIndex.load(variant(name, edit))
+        assert e.value.code == -3, (name, str(e.value))
+    with FmIndex.load(variant("intact", lambda b: None)) as ix:
+        assert ix.count_string("GATTACA") == 2
