@@ -311,7 +311,20 @@ void enqueue_search(const awry_index* ix, Replica& r, PackBalance& bal, Workspac
     v.avg_len = uint32_t(std::min<uint64_t>(nbytes / std::max<uint64_t>(1, nq), 1u << 30));
     v.b_lo = c.b0;
     v.b_hi = c.b1;
+    ws->gpu_probe_bytes = 0;
+    const bool time_kernel = qs.pinned && !qs.crumbs && nbytes >= (8u << 20);  // PackBalance: what the GPU consumes
+    if (time_kernel) {
+      if (!ws->ev_s0) {
+        CU(cudaEventCreate(&ws->ev_s0));
+        CU(cudaEventCreate(&ws->ev_s1));
+      }
+      CU(cudaEventRecord(ws->ev_s0, ws->st));
+    }
     CU(launch_search(r.view, d_words, ws->d_qoff, nq, mode, ws->d_out, ws->d_defer, v, r.sm_count, ws->st));
+    if (time_kernel) {
+      CU(cudaEventRecord(ws->ev_s1, ws->st));
+      ws->gpu_probe_bytes = nbytes;
+    }
   }
   gpu_mark(ws->st, "searched", (long long)c.q0);
   // (the locate pipeline copies the flag together with the hit total, after the scan: one hand-over between
@@ -361,6 +374,12 @@ void search_on_replica(const awry_index* ix, size_t ri, const QuerySource& qs, u
       if (cudaEventElapsedTime(&ms, ws[s]->ev_a, ws[s]->ev_b) == cudaSuccess)
         bal.note_link(double(ws[s]->link_probe_bytes), double(ms) * 1e-3);
       ws[s]->link_probe_bytes = 0;
+    }
+    if (ws[s]->gpu_probe_bytes) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, ws[s]->ev_s0, ws[s]->ev_s1) == cudaSuccess)
+        bal.note_gpu(double(ws[s]->gpu_probe_bytes), double(ms) * 1e-3);
+      ws[s]->gpu_probe_bytes = 0;
     }
     check_flag(ws[s], c);
     if (!dst_pinned)

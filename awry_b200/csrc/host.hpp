@@ -148,6 +148,8 @@ struct Workspace {
   std::vector<uint64_t> exc_tmp;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;  // timing of a raw chunk's H2D copy (PackBalance)
   uint64_t link_probe_bytes = 0;
+  cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;  // timing of a chunk's search kernel (PackBalance: what the GPU consumes)
+  uint64_t gpu_probe_bytes = 0;
   // device
   uint8_t* d_qbytes = nullptr;
   size_t d_qbytes_cap = 0;
@@ -260,6 +262,8 @@ struct Workspace {
     rs.release();
     if (ev_a) cudaEventDestroy(ev_a);
     if (ev_b) cudaEventDestroy(ev_b);
+    if (ev_s0) cudaEventDestroy(ev_s0);
+    if (ev_s1) cudaEventDestroy(ev_s1);
     if (done) cudaEventDestroy(done);
     if (st) cudaStreamDestroy(st);
   }
@@ -312,19 +316,20 @@ struct Replica {
   }
 };
 
-// Pack on the host or send ASCII?  Packing wins when the host cores pack faster than the PCIe link moves
-// bytes (16 threads: 121 GB/s vs 52 GB/s for one GPU) and loses when few cores feed many GPUs over shared
-// uplinks.  Both rates are MEASURED per index handle and smoothed across its calls: the host clock around the
-// packer (H), CUDA events around the copy of a raw first chunk, when nothing else of that replica is in
-// flight (P).  H > 1.15 P: pack everything (one GPU, 16 threads: mixing raw chunks in was measured and is
-// worse there -- a 128-MiB raw copy holds the copy engine for 2.6 ms and starves the search kernel,
-// profiles/r01_s19_e2e_pack_share.log).  Otherwise host and link are used together: a share
-// f = H / (P + 0.75 H) of the bytes is packed.  In a multi-replica call every replica thread measures its
-// own share of the pool and of the host's uplinks, which is what it has to balance.
+// Pack on the host or send ASCII?  Three rates decide, all MEASURED per replica of a handle and smoothed
+// across its calls, in query bytes per second: H, what the host packs for this replica (the host clock around
+// the packer -- in a multi-replica call that is the replica's share of the one pool); P, what its PCIe link
+// moves raw (CUDA events around the copy of a raw first chunk); G, what its search kernel consumes (CUDA
+// events around the kernel).  H >= 1.15 G: the host keeps the GPU fed on its own -- pack everything, a quarter
+// of the bytes cross the link (one GPU behind 16 host threads: H = 121, G = 82 GB/s; mixing raw chunks in was
+// measured and is worse there, a 128-MiB raw copy holds the copy engine for 2.6 ms,
+// profiles/r01_s19_e2e_pack_share.log).  Otherwise host and link work side by side: a share f = H / (H + P)
+// of the bytes is packed and the rest goes up as ASCII (the device packs it), so the GPU sees H + P -- several
+// GPUs behind few cores (2 GPUs / 24 threads: H = 60-90 per replica against G = 82) are fed by both.
 // AWRY_B200_PACK_SHARE=<0..1> pins the packed share of the bytes instead (experiments).
 struct PackBalance {
   std::mutex mu;
-  double host_rate = 0, link_rate = 0;  // bytes/s, 0 = not measured yet
+  double host_rate = 0, link_rate = 0, gpu_rate = 0;  // bytes/s, 0 = not measured yet
   double fixed_share = -1;
   uint64_t calls = 0;
   bool mixed = true;  // AWRY_B200_PACK_MIXED=0: all-or-nothing
@@ -344,6 +349,12 @@ struct PackBalance {
     double r = bytes / seconds;
     link_rate = link_rate > 0 ? 0.7 * link_rate + 0.3 * r : r;
   }
+  void note_gpu(double bytes, double seconds) {
+    if (seconds <= 0 || bytes < (8 << 20)) return;
+    std::lock_guard<std::mutex> lk(mu);
+    double r = bytes / seconds;
+    gpu_rate = gpu_rate > 0 ? 0.7 * gpu_rate + 0.3 * r : r;
+  }
   // per call: the packed share of the bytes and whether chunk 0 / chunk 1 serve as probes
   struct Plan {
     double share;
@@ -354,10 +365,13 @@ struct PackBalance {
     if (fixed_share >= 0) return Plan{fixed_share, false, false};
     const bool refresh = calls++ % 32 == 0;
     if (host_rate <= 0 || link_rate <= 0) return Plan{1.0, true, true};
-    if (host_rate > 1.15 * link_rate) return Plan{1.0, refresh, false};
-    // the host is not clearly faster than the link: use both (see the share formula above)
-    double f = mixed ? host_rate / (link_rate + 0.75 * host_rate) : 0.0;
+    // (until the kernel's rate is known, "clearly faster than the link" stands in for "feeds the GPU")
+    const bool host_suffices = gpu_rate > 0 ? host_rate >= 1.15 * gpu_rate : host_rate > 2.0 * link_rate;
+    if (host_suffices) return Plan{1.0, refresh, false};
+    if (!mixed) return host_rate > link_rate ? Plan{1.0, refresh, false} : Plan{0.0, true, refresh};
+    double f = host_rate / (host_rate + link_rate);  // host and link side by side
     if (f < 0.15) f = 0.0;
+    if (f > 0.9) f = 1.0;
     return Plan{f, true, f == 0.0 && refresh};
   }
 };

@@ -31,6 +31,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# the bench index carries all three locate schemes (unsampled array, position-sampled array + walk blocks, the
+# file's row samples) so that the locate legs can time each on the same handle; the count path does not read them
+os.environ.setdefault("AWRY_B200_LEAN_SA", "1")
+
 TEXT_SEED = 3
 QUERY_SEED = 4
 ALG_BYTES_PER_BLOCK = 104   # 3 x 32 B planes + one 8-B milestone per rank-block access
@@ -407,7 +411,7 @@ def secondary_cfg5(a, torch, f, fxg, po, stream):
         d_hoff = torch.zeros(nq + 1, dtype=torch.int64, device="cuda")
         res = {}
         f.profile_enable(True)
-        for variant in (1, 0):
+        for variant in (1, 2, 0):
             f.set_locate_variant(variant)
             try:
                 def once():
@@ -439,6 +443,14 @@ def secondary_cfg5(a, torch, f, fxg, po, stream):
             "gather": {"hits_per_s": res[0][1] / (res[0][0] * 1e-3), "ms_per_step": res[0][0], "pass2_kernel_ms": res[0][2],
                        "roofline": {"bound": "hbm", "algorithmic_bytes_per_hit": 4 + 16,
                                     "achieved_gbs": res[0][1] * 20 / (res[0][2] * 1e-3) / 1e9}},
+            "bounded_walk": {"what": "walk blocks + suffix array sampled by text position (derived at load time): at most "
+                                     "ratio - 1 LF steps per hit, consecutive hits of an interval walked side by side",
+                             "hits_per_s": res[2][1] / (res[2][0] * 1e-3), "ms_per_step": res[2][0], "pass2_kernel_ms": res[2][2],
+                             "device_bytes": ix.device_bytes()["lean_sa"], "unsampled_array_bytes": ix.device_bytes()["full_sa"],
+                             "roofline": {"bound": "hbm (random 128-B walk-block reads)", "mean_walk_len": (32 - 1) / 2,
+                                          "algorithmic_bytes_per_hit": 104 * (32 - 1) / 2 + 20,
+                                          "achieved_gbs": res[2][1] * (104 * 15.5 + 20) / (res[2][2] * 1e-3) / 1e9,
+                                          "lf_steps_per_s": res[2][1] * 15.5 / (res[2][2] * 1e-3)}},
             "lf_walk": {"hits_per_s": res[1][1] / (res[1][0] * 1e-3), "ms_per_step": res[1][0], "pass2_kernel_ms": res[1][2],
                         "mean_walk_len": walk,
                         "roofline": {"bound": "hbm (random block reads)", "algorithmic_bytes_per_hit": 104 * walk + 20,
@@ -570,6 +582,7 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     torch.cuda.synchronize()
     setup_s = time.time() - t_setup
+    dev_bytes = ix.device_bytes()
 
     def step_device():
         ix.count_device(d_q.data_ptr(), d_off.data_ptr(), nq, d_cnt.data_ptr(), stream)
@@ -722,8 +735,9 @@ def main():
             return float(t.item()) / a.steps, prof_l, nh
 
         walk_lms, walk_lp, n_hits = locate_leg(1)
+        lean_lms, lean_lp, n_hits3 = locate_leg(2)
         lms, lp, n_hits2 = locate_leg(0)
-        assert n_hits == n_hits2
+        assert n_hits == n_hits2 == n_hits3
         unsampled = ix.device_bytes()["full_sa"] > 0
         # end to end through the C ABI: pinned host queries in, CSR offsets + hits out to the host
         hl_q = pinned_like(torch, nl * ll, torch.uint8)
@@ -759,7 +773,11 @@ def main():
                           "path": "awry_locate_batch_into, pinned buffers: hits written by the gather kernel straight "
                                   "into the caller's buffer, one wait per call"},
                   "lf_walk_variant": {"hits_per_s": world * n_hits / (walk_lms * 1e-3), "ms_per_step": walk_lms,
-                                      "walk_kernel_ms": walk_lp["walk_ms"] / max(1, walk_lp["walk_launches"])}}
+                                      "walk_kernel_ms": walk_lp["walk_ms"] / max(1, walk_lp["walk_launches"])},
+                  "bounded_walk_variant": {"hits_per_s": world * n_hits / (lean_lms * 1e-3), "ms_per_step": lean_lms,
+                                           "walk_kernel_ms": lean_lp["walk_ms"] / max(1, lean_lp["walk_launches"]),
+                                           "device_bytes": ix.device_bytes()["lean_sa"],
+                                           "unsampled_array_bytes": ix.device_bytes()["full_sa"]}}
         del d_lq, d_loff, d_hoff
 
     # ---- CPU baseline + parity + exact algorithmic work (rank 0, N = 1 only)
@@ -878,7 +896,8 @@ def main():
             "metric": "count queries/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms_max / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": config_of(a), "setup": {"setup_s": round(setup_s, 1), "fixture_build_s": phases.get("total")},
+            "config": config_of(a), "setup": {"setup_s": round(setup_s, 1), "fixture_build_s": phases.get("total"),
+                                              "index_device_bytes": dev_bytes},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e_line, "clocks": clocks,
             "gpu_launches": int(prof["launches"]), "parity_vs_oracle_on_sample": parity,
             "e2e_prepacked": (inproc or {}).get("prepacked") or e2e_packed,

@@ -128,6 +128,39 @@ def test_truncated_index_files_are_refused_before_any_device_work(tmp_path):
     assert b"shorter" in lib.awry_last_error()
 
 
+def test_file_section_offsets_match_the_reference_format():
+    """.awry v1 section offsets at the BASELINE sizes (derived from fm_index_file.rs:42-106,
+    :165-181 and kmer_lookup_table.rs:55-77), computed with the size helpers the writer and loader use"""
+    from awry_b200 import fm_index as f
+    lib = f.native()
+
+    def offsets(alphabet, bwt_len, ratio, k):
+        card = 6 if alphabet == 0 else 22
+        blocks = 43                                            # 11-byte label + 4 x u64 header
+        prefix = blocks + lib.awry_parts_num_blocks(bwt_len) * lib.awry_parts_block_words(alphabet) * 8
+        sa = prefix + (card + 1) * 8
+        kbyte = sa + lib.awry_parts_sa_words(bwt_len, ratio) * 8
+        seq = kbyte + 1 + 16 * (card - 2) ** k
+        return prefix, sa, kbyte, seq
+
+    assert offsets(0, 3_100_000_001, 8, 13) == (1_937_500_203, 1_937_500_259, 3_487_500_267, 4_561_242_092)
+    assert offsets(1, 2_000_000_001, 8, 5) == (2_750_000_395, 2_750_000_579, 3_718_750_587, 3_769_950_588)
+    assert offsets(0, 20, 4, 2) == (203, 259, 267, 524)        # Appendix A: 557 bytes = 524 + 8 + 16 + 9
+    golden = open(os.path.join(ROOT, "tests", "golden", "appendix_a.awry"), "rb").read()
+    assert len(golden) == 557 and golden[267] == 2
+    assert int.from_bytes(golden[203 + 48:203 + 56], "little") == 20 and int.from_bytes(golden[524:532], "little") == 1
+
+
+def test_rust_pin_harness_is_shipped():
+    """the one-command check against the real crate (needs a Rust toolchain, absent here) exists and names the
+    reference calls it compares"""
+    rs = open(os.path.join(ROOT, "rust", "awry-b200", "tests", "against_reference.rs")).read()
+    for call in ("awry::fm_index::FmIndex::new", "parallel_count", "parallel_locate", ".save(", "FmIndex::load"):
+        assert call in rs, call
+    sh = open(os.path.join(ROOT, "scripts", "pin_against_reference.sh")).read()
+    assert "cargo test" in sh and "against_reference" in sh
+
+
 def test_product_never_touches_the_oracle():
     """the shipped package must not import, link or execute anything under oracle/ or fixtures/"""
     pkg = os.path.join(ROOT, "awry_b200")
