@@ -16,9 +16,9 @@ namespace host {
 
 thread_local char g_err[1024] = "";
 ProfState g_prof;
-SearchVariant g_variant;
-int g_host_pack = -1;      // -1 = auto (AWRY_B200_HOST_PACK, CPU support, >= 4 pool threads), 0 = off, 1 = on
-int g_locate_variant = 0;  // 0 = unsampled-SA gather when the array exists, 1 = always LF-walk
+std::atomic<uint64_t> g_variant_bits{uint64_t(1)};  // lanes 0, tpb 0, blocks_per_sm 0, slots -1 (see host.hpp)
+std::atomic<int> g_host_pack{-1};
+std::atomic<int> g_locate_variant{0};
 
 [[noreturn]] void fail(int code, const char* fmt, ...) {
   char buf[900];

@@ -150,7 +150,8 @@ std::vector<Chunk> taper_chunks(std::vector<Chunk> in, const uint64_t* qoff) {
 }
 
 bool host_pack_enabled() {
-  if (g_host_pack >= 0) return g_host_pack == 1 && host_pack_supported();
+  const int hp = g_host_pack.load(std::memory_order_relaxed);
+  if (hp >= 0) return hp == 1 && host_pack_supported();
   static const bool on = [] {
     if (const char* e = getenv("AWRY_B200_HOST_PACK")) return e[0] != '0' && host_pack_supported();
     return host_pack_supported() && host_pool_threads() >= 4;
@@ -307,7 +308,7 @@ void enqueue_search(const awry_index* ix, Replica& r, PackBalance& bal, Workspac
   gpu_mark(ws->st, "packed on device", (long long)c.q0);
   {
     ProfScope p(0, r.device, ws->st);
-    SearchVariant v = g_variant;
+    SearchVariant v = current_variant();
     v.avg_len = uint32_t(std::min<uint64_t>(nbytes / std::max<uint64_t>(1, nq), 1u << 30));
     v.b_lo = c.b0;
     v.b_hi = c.b1;
@@ -502,8 +503,9 @@ uint64_t* locate_chunk_walk(Replica& r, Workspace* ws, uint64_t nq, uint64_t n_h
                             const uint64_t* d_hit_off, cudaStream_t st) {
   if (n_hits == 0) return nullptr;
   IndexView view = r.view;
-  if (g_locate_variant != 0) view.full_sa = nullptr;      // 1, 2: walk
-  if (g_locate_variant == 1) view.walk_blocks = nullptr;  // 1: to the file's row samples
+  const int lv = g_locate_variant.load(std::memory_order_relaxed);
+  if (lv != 0) view.full_sa = nullptr;      // 1, 2: walk
+  if (lv == 1) view.walk_blocks = nullptr;  // 1: to the file's row samples
   const void* d_sp_cnt = ws->d_out;
   uint64_t* d_hits = nullptr;
   CU(cudaMallocAsync(reinterpret_cast<void**>(&d_hits), n_hits * 16 + 16, st));  // pool: no driver round trip
@@ -1003,7 +1005,7 @@ int awry_count_device(const awry_index* ix, int replica, const uint8_t* d_qbytes
     }
     {
       ProfScope p(0, r.device, st);
-      SearchVariant v = g_variant;
+      SearchVariant v = current_variant();
       v.avg_len = uint32_t(std::min<uint64_t>((ends[1] - ends[0]) / nq, 1u << 30));
       v.b_lo = ends[0];
       v.b_hi = ends[1];
@@ -1044,7 +1046,7 @@ int awry_locate_device(const awry_index* ix, int replica, const uint8_t* d_qbyte
       }
       {
         ProfScope p(0, r.device, st);
-        SearchVariant v = g_variant;
+        SearchVariant v = current_variant();
         v.avg_len = uint32_t(std::min<uint64_t>((ends[1] - ends[0]) / nq, 1u << 30));
         v.b_lo = ends[0];
         v.b_hi = ends[1];
@@ -1131,14 +1133,12 @@ int awry_set_search_variant(int lanes_per_query, int threads_per_block, int bloc
       lanes_per_query != 4 && lanes_per_query != 8 && lanes_per_query != 80 && lanes_per_query != 81 &&
       lanes_per_query != 82)
     return AWRY_ERR_INVALID_ARG;
-  g_variant.slots = -1;  // default choice of the pair kernel's flavour
+  int slots = -1;  // default choice of the pair kernel's flavour
   if (lanes_per_query >= 80) {  // 80 / 81 / 82: the pair kernel with 0 (branching refill) / 1 / 2 state-machine slots
-    g_variant.slots = lanes_per_query - 80;
+    slots = lanes_per_query - 80;
     lanes_per_query = 8;
   }
-  g_variant.lanes = lanes_per_query;
-  g_variant.tpb = threads_per_block;
-  g_variant.blocks_per_sm = blocks_per_sm;
+  store_variant(lanes_per_query, threads_per_block, blocks_per_sm, slots);
   return AWRY_OK;
 }
 

@@ -123,9 +123,26 @@ struct ProfScope {
   }
 };
 
-extern SearchVariant g_variant;  // experiments only (awry_set_search_variant)
-extern int g_host_pack;      // -1 = auto (AWRY_B200_HOST_PACK, CPU support, >= 4 pool threads), 0 = off, 1 = on
-extern int g_locate_variant;  // 0 = unsampled-SA gather when the array exists, 1 = always LF-walk (awry_set_locate_variant)
+// Process-wide EXPERIMENT knobs (awry_set_search_variant / _locate_variant / _host_pack): A/B switches for the
+// benchmarks and tests, not per-call configuration -- results never depend on them, only speed.  Atomics, so
+// that a thread flipping one while others search is a benign race: a call reads each knob once.
+extern std::atomic<uint64_t> g_variant_bits;  // lanes (16 bits, biased by 1) | tpb (16) | blocks_per_sm (16) | slots (8, biased by 1)
+extern std::atomic<int> g_host_pack;      // -1 = auto (AWRY_B200_HOST_PACK, CPU support, >= 4 pool threads), 0 = off, 1 = on
+extern std::atomic<int> g_locate_variant;  // 0 = best pass 2 present, 1 = LF-walk to row samples, 2 = bounded walk
+inline SearchVariant current_variant() {
+  const uint64_t b = g_variant_bits.load(std::memory_order_relaxed);
+  SearchVariant v;
+  v.lanes = int(b & 0xffff) - 1;
+  v.tpb = int((b >> 16) & 0xffff);
+  v.blocks_per_sm = int((b >> 32) & 0xffff);
+  v.slots = int((b >> 48) & 0xff) - 1;
+  return v;
+}
+inline void store_variant(int lanes, int tpb, int blocks_per_sm, int slots) {
+  g_variant_bits.store(uint64_t(uint16_t(lanes + 1)) | (uint64_t(uint16_t(tpb)) << 16) | (uint64_t(uint16_t(blocks_per_sm)) << 32) |
+                           (uint64_t(uint8_t(slots + 1)) << 48),
+                       std::memory_order_relaxed);
+}
 
 
 // ------------------------------------------------------------------ index

@@ -197,6 +197,11 @@ __attribute__((target("avx2,bmi2"))) void pack_avx2(const uint8_t* src, size_t l
   const __m256i mul16 = _mm256_set1_epi32(0x00100001);  // w0 + 16 * w1  (pmaddwd)
   const __m256i order = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);
   constexpr size_t PF = 2048;  // software prefetch distance (bytes)
+  // The packed bytes are read next by the PCIe DMA engine, not by a core: streaming stores keep them out of
+  // the caches and spare the read-for-ownership of every output line -- with several GPUs behind one host the
+  // packer is bound by host memory traffic (1 B read + 0.25 B written + 0.25 B read back by the DMA per base;
+  // a regular store adds another 0.25 B of ownership reads).  Needs a 32-byte aligned destination.
+  const bool stream = (reinterpret_cast<uintptr_t>(dst) & 31) == 0;
   size_t i = lo;
   for (; i + 128 <= hi; i += 128) {
     __m256i v[4], d[4], ok = _mm256_set1_epi8(char(0xFF));
@@ -212,7 +217,10 @@ __attribute__((target("avx2,bmi2"))) void pack_avx2(const uint8_t* src, size_t l
     }
     // per 128-bit lane: [d0 d1 d2 d3] of the low / high four dwords -> bytes; then interleave the two lanes
     const __m256i q = _mm256_packus_epi16(_mm256_packus_epi32(d[0], d[1]), _mm256_packus_epi32(d[2], d[3]));
-    _mm256_storeu_si256(reinterpret_cast<__m256i*>(dst + (i >> 2)), _mm256_permutevar8x32_epi32(q, order));
+    if (stream)
+      _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + (i >> 2)), _mm256_permutevar8x32_epi32(q, order));
+    else
+      _mm256_storeu_si256(reinterpret_cast<__m256i*>(dst + (i >> 2)), _mm256_permutevar8x32_epi32(q, order));
     if (__builtin_expect(_mm256_movemask_epi8(ok) != -1, 0)) {  // rare: list the bytes outside ACGTacgt
 #pragma GCC unroll 4
       for (int j = 0; j < 4; j++) {
@@ -226,6 +234,7 @@ __attribute__((target("avx2,bmi2"))) void pack_avx2(const uint8_t* src, size_t l
       }
     }
   }
+  if (stream) _mm_sfence();  // the streaming stores are globally visible before the block is reported done
   for (; i < hi; i += 32) {  // tail of the block: one 32-base step at a time
     __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
     __m256i up = _mm256_and_si256(v, up_mask);

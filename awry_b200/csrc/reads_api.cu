@@ -335,7 +335,7 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
         }
         {
           ProfScope p(0, r.device, st);
-          SearchVariant v = g_variant;
+          SearchVariant v = current_variant();
           v.avg_len = uint32_t(std::min<uint64_t>(plan.seq_bytes / nq, 1u << 30));
           v.b_lo = 0;
           v.b_hi = plan.seq_bytes;

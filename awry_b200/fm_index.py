@@ -594,9 +594,12 @@ def host_pack_dna(src: np.ndarray):
     """the host packer alone (tests): -> (crumb bytes uint8[ceil(n/4)], exceptions uint64[] = (i << 8) | byte)"""
     src = np.ascontiguousarray(src, dtype=np.uint8)
     dst = np.zeros((len(src) + 3) // 4 + 64, dtype=np.uint8)
-    exc = np.zeros(len(src) + 1, dtype=np.uint64)
+    exc = np.zeros(min(len(src), 1 << 20) + 1, dtype=np.uint64)
     n = C.c_uint64()
     _check(native().awry_host_pack_dna(src.ctypes.data, len(src), dst.ctypes.data, exc.ctypes.data, len(exc), C.byref(n)))
+    if n.value > len(exc):          # more exceptions than the first guess: once more with room for all
+        exc = np.zeros(n.value, dtype=np.uint64)
+        _check(native().awry_host_pack_dna(src.ctypes.data, len(src), dst.ctypes.data, exc.ctypes.data, len(exc), C.byref(n)))
     return dst[: (len(src) + 3) // 4], exc[: n.value]
 
 

@@ -487,6 +487,32 @@ def inprocess_leg(a, torch, f, fxg, parts, world, rank_sums, rank_hit_totals):
     f.set_host_threads(min(hw, 256))        # this process owns the host now: the other ranks wait on a socket
     res = {"index_on_n_devices_s": round(t_index, 2), "host_threads": f.host_threads(), "host_cores": hw}
     try:
+        # what the HOST can deliver, measured alone: the packer on all threads, and raw pinned -> device copies on
+        # all N links at once.  ASCII reads cross host memory once either way (read by the cores or by the DMA
+        # engines), so these two rates bound `ascii` below whatever the GPUs could search.
+        nb = nq * L
+        f.host_pack_dna(qb[:nb])
+        t0 = time.perf_counter()
+        for r in range(world):
+            f.host_pack_dna(qb[r * nb:(r + 1) * nb])
+        pack_gbs = world * nb / (time.perf_counter() - t0) / 1e9
+        dsts = []
+        for r in range(world):
+            with torch.cuda.device(r):
+                dsts.append((torch.empty(nb, dtype=torch.uint8, device=f"cuda:{r}"), torch.cuda.Stream(device=r)))
+        def raw_all():
+            for r, (dt_, st_) in enumerate(dsts):
+                with torch.cuda.device(r), torch.cuda.stream(st_):
+                    dt_.copy_(h_q[r * nb:(r + 1) * nb], non_blocking=True)
+            for r, (dt_, st_) in enumerate(dsts):
+                st_.synchronize()
+        raw_all()
+        t0 = time.perf_counter()
+        raw_all()
+        raw_gbs = world * nb / (time.perf_counter() - t0) / 1e9
+        del dsts
+        res["host_limits"] = {"pack_all_threads_gbs": pack_gbs, "raw_h2d_all_links_gbs": raw_gbs,
+                              "reads_per_s_if_only_packed": pack_gbs * 1e9 / L, "reads_per_s_if_only_raw": raw_gbs * 1e9 / L}
         for _ in range(3):
             ix.count_packed(qb, qo, out=out)
         f.profile_reset()
