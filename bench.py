@@ -151,14 +151,13 @@ def measured_peak():
 def traffic_from_profiles(kernel):
     """DRAM bytes per launch of a kernel from the committed `ncu --set full` capture of this bench command
     (profiles/kernel_traffic.json, written by scripts/ncu_summary.py), or None"""
-    for name in ("kernel_traffic.json", "search_kernel_traffic.json"):
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))):
         try:
-            d = json.load(open(os.path.join(ROOT, "profiles", name)))
+            d = json.load(open(path))
         except Exception:
             continue
-        if kernel in d and isinstance(d[kernel], dict):
-            return d[kernel]
-        if d.get("kernel", "").startswith(kernel):
+        if str(d.get("kernel", "")).startswith(kernel) and d.get("dram_bytes_per_launch"):
             return d
     return None
 
