@@ -83,6 +83,7 @@ void set_view_constants(awry_index* ix, Replica& r) {
   v.walk_blocks = r.d_walk;
   v.walk_rank = r.d_walk_rank;
   v.pos_samples = r.d_pos_samples;
+  v.lean_ratio = ix->lean_ratio;
   for (int i = 0; i < 16; i++) v.c2[i] = r.c2[i];
   v.bwt_len = ix->wide ? 0xffffffffu : uint32_t(ix->bwt_len);
   v.dollar_row = ix->wide ? 0xffffffffu : uint32_t(r.dollar_row);
@@ -354,10 +355,21 @@ void finish_replica0(awry_index* ix, Replica& r) {
   const bool lean_never = ls && ls[0] == '0', lean_force = ls && ls[0] == '1';
   if (ix->alphabet == AWRY_NUCLEOTIDE && !g_skip_accelerators && ix->sa_ratio > 1 && !lean_never &&
       (lean_force || r.d_full_sa == nullptr)) {
+    // The sampling distance is ours to choose (nothing of this is in the file): 4 unless the file samples more
+    // densely -- mean walk 1.5 steps, 12.6 bits per row -- doubled while the arrays would take more than a third
+    // of the free memory.  AWRY_B200_LEAN_RATIO overrides.
     const uint64_t nb = walk_block_count(ix->bwt_len);
-    const uint64_t n_pos = (ix->bwt_len + ix->sa_ratio - 1) / ix->sa_ratio;
-    const size_t bytes = size_t(nb) * 128 + size_t(nb + 1) * 4 + size_t(n_pos + 4) * 4;
     CU(cudaMemGetInfo(&free_b, &total_b));
+    uint64_t lr = std::min<uint64_t>(ix->sa_ratio, 4);
+    if (const char* e = getenv("AWRY_B200_LEAN_RATIO")) lr = std::min<uint64_t>(1u << 20, std::max<uint64_t>(2, strtoull(e, nullptr, 10)));
+    auto lean_bytes = [&](uint64_t ratio) {
+      return size_t(nb) * 128 + size_t(nb + 1) * 4 + size_t((ix->bwt_len + ratio - 1) / ratio + 4) * 4;
+    };
+    while (lr < (1u << 20) && lean_bytes(lr) > free_b / 3) lr *= 2;
+    ix->lean_ratio = uint32_t(lr);
+    r.view.lean_ratio = ix->lean_ratio;
+    const uint64_t n_pos = (ix->bwt_len + lr - 1) / lr;
+    const size_t bytes = lean_bytes(lr);
     if (bytes + (1u << 28) < free_b) {
       CU(cudaMalloc(reinterpret_cast<void**>(&r.d_walk), size_t(nb) * 128 + 256));
       CU(cudaMalloc(reinterpret_cast<void**>(&r.d_walk_rank), size_t(nb + 1) * 4 + 256));
@@ -414,7 +426,7 @@ void clone_replica(awry_index* ix, const Replica& src, Replica& dst) {
   }
   if (src.bytes_lean) {
     const uint64_t nb = walk_block_count(ix->bwt_len);
-    const uint64_t n_pos = (ix->bwt_len + ix->sa_ratio - 1) / ix->sa_ratio;
+    const uint64_t n_pos = (ix->bwt_len + ix->lean_ratio - 1) / ix->lean_ratio;
     dst.bytes_lean = src.bytes_lean;
     CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_walk), size_t(nb) * 128 + 256));
     CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_walk_rank), size_t(nb + 1) * 4 + 256));
@@ -666,6 +678,7 @@ int awry_index_info(const awry_index* ix, awry_info* info) {
     info->device_bytes_lean_sa = ix->reps[0]->bytes_lean;
     for (size_t i = 0; i < ix->reps.size() && i < 16; i++) info->devices[i] = ix->reps[i]->device;
     info->row_pointer_bits = ix->wide ? 64 : 32;
+    info->lean_sa_ratio = ix->reps[0]->bytes_lean ? ix->lean_ratio : 0;
   });
 }
 

@@ -701,6 +701,18 @@ uint64_t locate_direct_on_replica(const awry_index* ix, size_t ri, const QuerySo
   const uint64_t max_bytes = std::min(chunk_max_bytes(), locate_chunk_bytes());
   auto chunks = make_chunks(qoff, 0, nq, locate_chunk_q(), max_bytes);
   validate_chunks(chunks, max_bytes);
+  // A call of this size is latency-bound and the device idles while the host packs the first chunk (0.4 ms for
+  // 25 MB: profiles/r02_s2_locate_e2e_trace.log).  So the first chunk is cut to a quarter and goes up as it is --
+  // the copy engine starts at once, the device packs it -- while the host packs what follows.
+  bool first_raw = false;
+  if (chunks.size() >= 1 && chunks[0].q1 - chunks[0].q0 >= (1u << 16) && qs.pinned && !qs.crumbs &&
+      getenv("AWRY_B200_LOCATE_FIRST_RAW") == nullptr) {
+    const Chunk c = chunks[0];
+    const uint64_t cut = c.q0 + (c.q1 - c.q0) / 4;
+    chunks[0] = Chunk{c.q0, cut, qoff[c.q0], qoff[cut]};
+    chunks.insert(chunks.begin() + 1, Chunk{cut, c.q1, qoff[cut], qoff[c.q1]});
+    first_raw = true;
+  }
   const bool off_pinned = is_pinned(hit_off);
   constexpr int DEPTH = 3;
   Workspace* ws[DEPTH] = {nullptr, nullptr, nullptr};
@@ -731,7 +743,7 @@ uint64_t locate_direct_on_replica(const awry_index* ix, size_t ri, const QuerySo
       const Chunk& c = chunks[i];
       const uint64_t n = c.q1 - c.q0;
       gpu_mark(w->st, "chunk begins", (long long)i);
-      enqueue_search(ix, r, bal, w, qs, c, OUT_SP_CNT_U32, true, false, false);
+      enqueue_search(ix, r, bal, w, qs, c, OUT_SP_CNT_U32, !(first_raw && i == 0), false, false);
       Workspace::grow_dev(w->d_hit_off, w->d_hit_off_cap, size_t(n) + 1);
       Workspace::grow_dev(w->d_off_out, w->d_off_out_cap, size_t(n) + 1);
       locate_chunk_scan(r, w, n, w->d_hit_off, w->st);

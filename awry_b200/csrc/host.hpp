@@ -404,6 +404,7 @@ struct awry_index {
   uint64_t prefix_sums[23] = {0};
   uint64_t n_sa_words = 0;
   uint32_t sa_bits = 0;
+  uint32_t lean_ratio = 0;  // sampling distance of the derived position-sampled suffix array (0 = not built)
   bool wide = false;        // 64-bit row pointers (bwt_len >= 2^32 - 256, or AWRY_B200_WIDE=1)
   uint32_t sb_shift = 31;   // log2(rows per superblock) of a wide index
   uint64_t n_superblocks() const { return (bwt_len >> sb_shift) + 1; }

@@ -258,13 +258,13 @@ __device__ __forceinline__ void unsample_visit(const IndexView& ix, uint32_t row
     full[row] = p;
     return;
   }
-  if (p % ix.sa_ratio != 0) return;
+  if (p % ix.lean_ratio != 0) return;
   if (MODE == UNSAMPLE_MARK) {
     uint32_t bit;
     uint32_t* w = walk_mark_word(walk, row, bit);
     atomicOr(w, 1u << bit);
   } else {
-    pos_samples[ix.walk_rank[row / WALK_ROWS_PER_BLOCK] + walk_marks_before(walk, row)] = p / ix.sa_ratio;
+    pos_samples[ix.walk_rank[row / WALK_ROWS_PER_BLOCK] + walk_marks_before(walk, row)] = p / ix.lean_ratio;
   }
 }
 
@@ -441,18 +441,19 @@ __global__ void walk_mark_counts_kernel(const uint4* __restrict__ walk, uint64_t
 
 uint64_t walk_block_count(uint64_t bwt_len) { return (bwt_len + WALK_ROWS_PER_BLOCK - 1) / WALK_ROWS_PER_BLOCK; }
 
-// view: blocks / sa_words set; d_walk: walk_block_count x 128 B; d_rank: walk_block_count + 1 u32;
-// d_pos: ceil(bwt_len / ratio) + 2 u32 (the last two words serve as the walkers' ticket counter)
+// view: blocks / sa_words / lean_ratio set; d_walk: walk_block_count x 128 B; d_rank: walk_block_count + 1 u32;
+// d_pos: ceil(bwt_len / lean_ratio) + 4 u32 (the last words serve as the walkers' ticket counter)
 cudaError_t build_lean_sa(const IndexView& ix, uint4* d_walk, uint32_t* d_rank, uint32_t* d_pos, int sm_count,
                           cudaStream_t s) {
   if (ix.alphabet != 0) return cudaErrorInvalidValue;
   const uint64_t nb = walk_block_count(ix.bwt_len);
-  const uint64_t n_elems = (uint64_t(ix.bwt_len) + ix.sa_ratio - 1) / ix.sa_ratio;
+  const uint64_t n_elems = (uint64_t(ix.bwt_len) + ix.sa_ratio - 1) / ix.sa_ratio;  // walkers: one per row the FILE sampled
+  const uint64_t n_pos = (uint64_t(ix.bwt_len) + ix.lean_ratio - 1) / ix.lean_ratio;  // marked rows
   walk_planes_kernel<<<unsigned((nb * 7 + 255) / 256), 256, 0, s>>>(ix, d_walk, nb);
   COUNT_LAUNCH();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  unsigned long long* ticket = reinterpret_cast<unsigned long long*>(d_pos + ((n_elems + 1) & ~uint64_t(1)));
+  unsigned long long* ticket = reinterpret_cast<unsigned long long*>(d_pos + ((n_pos + 1) & ~uint64_t(1)));
   const unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * 8, (2 * n_elems + 255) / 256)));
   if ((e = cudaMemsetAsync(ticket, 0, 8, s)) != cudaSuccess) return e;
   unsample_dna_kernel<UNSAMPLE_MARK><<<grid, 256, 0, s>>>(ix, n_elems, nullptr, d_walk, nullptr, ticket);
@@ -561,7 +562,7 @@ __global__ void __launch_bounds__(256) walk_lean_kernel(IndexView ix, uint64_t n
     if (have) {
       if (marked) {
         if (sub == 0) {
-          const uint64_t loc = uint64_t(__ldg(ix.pos_samples + __ldg(ix.walk_rank + blk) + r)) * ix.sa_ratio + steps;
+          const uint64_t loc = uint64_t(__ldg(ix.pos_samples + __ldg(ix.walk_rank + blk) + r)) * ix.lean_ratio + steps;
           if (MAP)
             map_location(ix, loc, out + SLOT * cur);
           else

@@ -29,16 +29,17 @@
 //
 //   NUCLEOTIDE WALK BLOCKS + POSITION-SAMPLED SA (memory-lean locate; derived at load time)
 //               The file samples the suffix array by ROW (row % ratio == 0, compressed_suffix_array.rs:109-111),
-//               so a walk is geometric and unbounded.  Sampling by TEXT POSITION (SA[row] % ratio == 0) bounds
-//               it by ratio - 1 steps; it needs a mark bit per row and a rank over the marks.
+//               so a walk is geometric and unbounded.  Sampling by TEXT POSITION (SA[row] % r == 0) bounds
+//               it by r - 1 steps; it needs a mark bit per row and a rank over the marks.  Both are DERIVED at
+//               load time, so r is the library's choice, not the file's: r = min(file ratio, 4) by default.
 //               block = 224 BWT rows = 128 B = 4 lane slices of 32 B (one LDG.256 each)
 //               words 4g .. 4g+3 (g = 0..6) = { p0, p1, p2, mark } of rows 32g .. 32g+31
 //               (p_b = bit-plane b of the device row code, mark bit t = "SA[row 32g+t] % ratio == 0")
 //               words 28 .. 31 = #A, #C, #G, #T in BWT[0 .. block start)
 //               slice t < 3 holds row groups 2t and 2t+1, slice 3 holds group 6 and the counts: the BWT symbol,
 //               its rank AND the stop test of an LF step come from ONE aligned 128-B line.
-//               walk_rank[blk] = marked rows before the block; pos_samples[i] = SA[i-th marked row] / ratio.
-//               4.57 + 32/ratio bits per row (3.3 GB at 3.1 G rows, ratio 8) against 32 for the unsampled array.
+//               walk_rank[blk] = marked rows before the block; pos_samples[i] = SA[i-th marked row] / r.
+//               4.57 + 32/r bits per row (12.6 at r = 4: 4.9 GB at 3.1 G rows) against 32 for the unsampled array.
 //
 //   AMINO       block = 64 rows = 128 B = 4 lane slices of 32 B (one LDG.256 each; one line per step)
 //               slice t < 2 = { p0..p4 of rows 32t..32t+31, cnt[3t], cnt[3t+1], cnt[3t+2] }
@@ -75,7 +76,9 @@ struct IndexView {
   const uint32_t* __restrict__ full_sa;    // unsampled suffix array (locate accelerator), or nullptr
   const uint4* __restrict__ walk_blocks;   // nucleotide walk blocks (planes + position marks), or nullptr
   const uint32_t* __restrict__ walk_rank;  // marked rows before each walk block
-  const uint32_t* __restrict__ pos_samples;  // SA[marked row] / ratio, in row order
+  const uint32_t* __restrict__ pos_samples;  // SA[marked row] / lean_ratio, in row order
+  uint32_t lean_ratio;                     // a row is marked iff SA[row] % lean_ratio == 0 (the library's choice:
+                                           // the array is derived, not stored -- see finish_replica0)
   uint32_t c2[16];                         // C2[4a+b]
   uint32_t c_lo[24];                       // C[c]      by device symbol (search.rs:43-48)
   uint32_t c_hi[24];                       // C[c+1]-1  by device symbol

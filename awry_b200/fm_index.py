@@ -81,7 +81,7 @@ class _Info(C.Structure):
                 ("device_bytes_sa", C.c_uint64), ("device_bytes_table", C.c_uint64),
                 ("device_bytes_pair", C.c_uint64), ("device_bytes_full_sa", C.c_uint64),
                 ("device_bytes_lean_sa", C.c_uint64),
-                ("devices", C.c_int32 * 16), ("row_pointer_bits", C.c_uint32), ("reserved", C.c_uint32)]
+                ("devices", C.c_int32 * 16), ("row_pointer_bits", C.c_uint32), ("lean_sa_ratio", C.c_uint32)]
 
 
 class _Parts(C.Structure):
@@ -315,6 +315,10 @@ class FmIndex:
     def row_pointer_bits(self) -> int:
         """32 while bwt_len < 2^32 - 256 (cooperative kernels), else 64 (kernels_wide.cu)"""
         return int(self._info.row_pointer_bits)
+
+    def lean_sa_ratio(self) -> int:
+        """sampling distance of the derived position-sampled suffix array (bounded locate), 0 if not built"""
+        return int(self._info.lean_sa_ratio)
 
     def n_devices(self) -> int:
         return int(self._info.n_devices)

@@ -426,6 +426,7 @@ def secondary_cfg5(a, torch, f, fxg, po, stream):
                 f.set_locate_variant(0)
             res[variant] = (lms, nh, p["walk_ms"] / max(1, p["walk_launches"]), p["search_ms"] / max(1, p["search_launches"]))
         f.profile_enable(False)
+        lean_r = ix.lean_sa_ratio()
         cnt = np.diff(d_hoff.cpu().numpy().view(np.uint64))
         ns = 2000
         orc = po.OracleIndex.from_parts(parts.alphabet, parts.ratio, parts.bwt_len, parts.kmer_len, parts.blocks,
@@ -446,10 +447,12 @@ def secondary_cfg5(a, torch, f, fxg, po, stream):
                                      "ratio - 1 LF steps per hit, consecutive hits of an interval walked side by side",
                              "hits_per_s": res[2][1] / (res[2][0] * 1e-3), "ms_per_step": res[2][0], "pass2_kernel_ms": res[2][2],
                              "device_bytes": ix.device_bytes()["lean_sa"], "unsampled_array_bytes": ix.device_bytes()["full_sa"],
-                             "roofline": {"bound": "hbm (random 128-B walk-block reads)", "mean_walk_len": (32 - 1) / 2,
-                                          "algorithmic_bytes_per_hit": 104 * (32 - 1) / 2 + 20,
-                                          "achieved_gbs": res[2][1] * (104 * 15.5 + 20) / (res[2][2] * 1e-3) / 1e9,
-                                          "lf_steps_per_s": res[2][1] * 15.5 / (res[2][2] * 1e-3)}},
+                             "position_sampling_distance": lean_r,
+                             "roofline": {"bound": "hbm (random 128-B walk-block reads)", "mean_walk_len": (lean_r - 1) / 2,
+                                          "block_reads_per_hit": (lean_r - 1) / 2 + 1,
+                                          "algorithmic_bytes_per_hit": 104 * ((lean_r - 1) / 2 + 1) + 20,
+                                          "achieved_gbs": res[2][1] * (104 * ((lean_r - 1) / 2 + 1) + 20) / (res[2][2] * 1e-3) / 1e9,
+                                          "block_reads_per_s": res[2][1] * ((lean_r - 1) / 2 + 1) / (res[2][2] * 1e-3)}},
             "lf_walk": {"hits_per_s": res[1][1] / (res[1][0] * 1e-3), "ms_per_step": res[1][0], "pass2_kernel_ms": res[1][2],
                         "mean_walk_len": walk,
                         "roofline": {"bound": "hbm (random block reads)", "algorithmic_bytes_per_hit": 104 * walk + 20,
@@ -802,6 +805,7 @@ def main():
                   "bounded_walk_variant": {"hits_per_s": world * n_hits / (lean_lms * 1e-3), "ms_per_step": lean_lms,
                                            "walk_kernel_ms": lean_lp["walk_ms"] / max(1, lean_lp["walk_launches"]),
                                            "device_bytes": ix.device_bytes()["lean_sa"],
+                                           "position_sampling_distance": ix.lean_sa_ratio(),
                                            "unsampled_array_bytes": ix.device_bytes()["full_sa"]}}
         del d_lq, d_loff, d_hoff
 

@@ -74,7 +74,7 @@ typedef struct awry_info {
   uint64_t device_bytes_lean_sa; /* walk blocks + position-sampled suffix array (bounded locate), 0 if not built */
   int32_t devices[16];
   uint32_t row_pointer_bits;    /* 32 while bwt_len < 2^32 - 256, else 64 (SearchPtr = u64, search.rs:7) */
-  uint32_t reserved;
+  uint32_t lean_sa_ratio;       /* sampling distance of the derived position-sampled suffix array, 0 if not built */
 } awry_info;
 
 /* The fields FmIndex::new hands over after the reference's CPU construction
@@ -310,8 +310,10 @@ int awry_set_search_variant(int lanes_per_query, int threads_per_block, int bloc
  *       instead of the LF-walk of fm_index.rs:521-537.  32 bits per row; kept when it takes < 1/3 of the free
  *       memory (AWRY_B200_FULL_SA=0 never, =1 whenever it fits);
  *   (b) nucleotide, when (a) is absent (or AWRY_B200_LEAN_SA=1): the suffix array sampled by TEXT POSITION
- *       (SA[row] % ratio == 0) with a mark bit per row, both derived at load time: an LF-walk of at most
- *       ratio - 1 steps, 4.57 + 32/ratio bits per row (without a new file format);
+ *       (SA[row] % r == 0) with a mark bit per row, both derived at load time: an LF-walk of at most r - 1
+ *       steps, 4.57 + 32/r bits per row (without a new file format).  Being derived, r is
+ *       the library's choice, not the file's: min(file ratio, 4), doubled until the arrays fit a third of the
+ *       free device memory (AWRY_B200_LEAN_RATIO overrides);
  *   (c) the reference's own scheme: LF-walk to the next ROW the file sampled (geometric walk lengths).
  * variant 0 = the best one present (default), 1 = always (c), 2 = (b) if present, else (c). */
 int awry_set_locate_variant(int variant);

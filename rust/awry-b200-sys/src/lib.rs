@@ -41,7 +41,7 @@ pub struct awry_info {
     pub device_bytes_lean_sa: u64,
     pub devices: [i32; 16],
     pub row_pointer_bits: u32,
-    pub reserved: u32,
+    pub lean_sa_ratio: u32,
 }
 
 #[repr(C)]

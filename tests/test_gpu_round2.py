@@ -222,14 +222,16 @@ def test_one_batch_over_several_replicas(fx, dna, dna_or):
         f.set_host_threads(0)
 
 
-@pytest.mark.parametrize("ratio", [2, 7, 8, 32, 64])
-def test_bounded_walk_is_the_default_without_the_unsampled_array(fx, po, monkeypatch, ratio):
+@pytest.mark.parametrize("ratio,lean", [(2, None), (7, None), (8, None), (32, None), (64, 64), (8, 5), (32, 33), (3, 16)])
+def test_bounded_walk_is_the_default_without_the_unsampled_array(fx, po, monkeypatch, ratio, lean):
     """without the 4-byte-per-row array (AWRY_B200_FULL_SA=0) locate uses the suffix array
     sampled by text position -- every walk ends within ratio - 1 steps -- and returns what the reference's
     row-sampled walk returns, hit for hit, in BWT-row order.  Multi-record text with N runs included."""
     from awry_b200 import fm_index as f
     monkeypatch.setenv("AWRY_B200_FULL_SA", "0")
     monkeypatch.delenv("AWRY_B200_LEAN_SA", raising=False)
+    if lean:
+        monkeypatch.setenv("AWRY_B200_LEAN_RATIO", str(lean))   # the sampling distance is the library's, not the file's
     recs = [bytes(fx.gen_text(0, n, 40 + i)) for i, n in enumerate([5000, 223, 224, 225, 1, 30_000, 447])]
     recs[5] = recs[5][:1000] + b"NNNNNNNNNN" + recs[5][1010:]
     text, starts = fx.concat_records(recs, 0)
@@ -243,6 +245,7 @@ def test_bounded_walk_is_the_default_without_the_unsampled_array(fx, po, monkeyp
     woff, whits, _ = orc.locate_batch(qb, qo)
     with device_from_parts(parts) as ix:
         assert ix.device_bytes()["full_sa"] == 0 and ix.device_bytes()["lean_sa"] > 0
+        assert ix.lean_sa_ratio() == (lean or min(ratio, 4))
         off, hits = ix.locate_packed(qb, qo)
         assert np.array_equal(off, woff) and np.array_equal(hits, whits)
         soff, shits = ix.locate_packed(qb, qo, sorted_hits=True)
