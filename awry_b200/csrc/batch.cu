@@ -189,8 +189,10 @@ void validate_chunks(const std::vector<Chunk>& chunks, uint64_t max_bytes) {
 // Uploads one chunk of queries and runs prepass + search on ws->st.  The search result lands
 // in ws->d_out in the requested mode.
 // `may_pack`: the caller's say on host packing for this chunk (PackBalance)
+// `d_out_override`: where the search result goes instead of ws->d_out (a call-level array the chunks fill).
 void enqueue_search(const awry_index* ix, Replica& r, PackBalance& bal, Workspace* ws, const QuerySource& qs,
-                    const Chunk& c, SearchOut mode, bool may_pack = true, bool probe_link = false, bool copy_flag = true) {
+                    const Chunk& c, SearchOut mode, bool may_pack = true, bool probe_link = false, bool copy_flag = true,
+                    void* d_out_override = nullptr) {
   const uint64_t nq = c.q1 - c.q0, nbytes = c.b1 - c.b0;
   const size_t out_elem = mode == OUT_COUNT_U64 ? 8 : mode == OUT_RANGE_U64 ? 16 : sp_cnt_bytes(r.view);
   const int ush = packed_unit_shift(ix->alphabet);
@@ -251,8 +253,10 @@ void enqueue_search(const awry_index* ix, Replica& r, PackBalance& bal, Workspac
     if (may_pack && ix->alphabet == AWRY_NUCLEOTIDE && host_pack_enabled() && nbytes >= 4096) {
       Workspace::grow_host(ws->h_qbytes, ws->h_qbytes_cap, size_t(nbytes) / 4 + 64);
       auto t0 = std::chrono::steady_clock::now();
-      packed = host_pack_dna(src_b, size_t(nbytes), ws->h_qbytes, ws->exc_tmp, 64);
-      if (packed) bal.note_host(double(nbytes), std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+      int sharers = 1;
+      packed = host_pack_dna(src_b, size_t(nbytes), ws->h_qbytes, ws->exc_tmp, 64, 0, &sharers);
+      if (packed)
+        bal.note_host(double(nbytes), std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), sharers);
       trace_mark("  host pack done, bytes", (long long)nbytes);
     }
     if (packed) {
@@ -321,7 +325,8 @@ void enqueue_search(const awry_index* ix, Replica& r, PackBalance& bal, Workspac
       }
       CU(cudaEventRecord(ws->ev_s0, ws->st));
     }
-    CU(launch_search(r.view, d_words, ws->d_qoff, nq, mode, ws->d_out, ws->d_defer, v, r.sm_count, ws->st));
+    CU(launch_search(r.view, d_words, ws->d_qoff, nq, mode, d_out_override ? d_out_override : ws->d_out, ws->d_defer, v,
+                     r.sm_count, ws->st));
     if (time_kernel) {
       CU(cudaEventRecord(ws->ev_s1, ws->st));
       ws->gpu_probe_bytes = nbytes;
@@ -349,7 +354,7 @@ void check_flag(Workspace* ws, const Chunk& c) {
 
 // count / range search over [q_lo, q_hi) on one replica, 3-deep pipeline
 void search_on_replica(const awry_index* ix, size_t ri, const QuerySource& qs, uint64_t q_lo, uint64_t q_hi,
-                       SearchOut mode, void* out) {
+                       SearchOut mode, void* out, size_t n_active_replicas = 1) {
   if (q_lo >= q_hi) return;
   Replica& r = *ix->reps[ri];
   PackBalance& bal = ix->balance_of(ri);
@@ -390,7 +395,7 @@ void search_on_replica(const awry_index* ix, size_t ri, const QuerySource& qs, u
   uint64_t bytes_total = 0, bytes_packed = 0;  // of the chunks enqueued so far (pinned sources only)
   const bool balanced = src_pinned && !qs.crumbs && ix->alphabet == AWRY_NUCLEOTIDE && host_pack_enabled();
   PackBalance::Plan plan{1.0, false, false};
-  if (balanced) plan = bal.plan();
+  if (balanced) plan = bal.plan(n_active_replicas);
   try {
     for (size_t i = 0; i < chunks.size(); i++) {
       int s = int(i % DEPTH);
@@ -832,8 +837,10 @@ QuerySource packed2_source(const awry_index* ix, const uint8_t* crumbs, const ui
 }
 
 void count_impl(const awry_index* ix, const QuerySource& qs, uint64_t nq, SearchOut mode, void* out) {
+  const size_t nr = ix->reps.size();
+  const size_t active = (nr == 1 || nq < 2 * nr) ? 1 : nr;  // (for_each_replica_range's own rule)
   for_each_replica_range(ix, qs.qoff, nq, [&](size_t ri, uint64_t lo, uint64_t hi) {
-    search_on_replica(ix, ri, qs, lo, hi, mode, out);
+    search_on_replica(ix, ri, qs, lo, hi, mode, out, active);
   });
 }
 
@@ -879,6 +886,106 @@ void locate_owned_impl(const awry_index* ix, const QuerySource& qs, uint64_t nq,
   *n_hits = total;
 }
 
+// parallel_locate over SEVERAL replicas into the caller's pinned buffers (BWT order, unsampled array).  A
+// replica's hits start behind those of the replicas before it, which nobody knows until they have searched; so
+// the call has two phases with one meeting of the replica threads between them.  Phase 1, all replicas at once:
+// the chunk pipeline packs, uploads and searches, the (sp, count) pairs land in one array per replica, one scan
+// gives its local CSR offsets and its hit total.  The totals are prefix-summed on the host.  Phase 2, all
+// replicas at once: one gather per replica writes the hits STRAIGHT into the caller's buffer at its base, the
+// rebased offsets go back with one copy.  No staging buffer, no concatenation pass on the host.
+struct ReplicaLocateState {
+  uint64_t lo = 0, hi = 0, total = 0, base = 0;
+  Workspace* ws = nullptr;  // holds the call-level arrays of this replica (d_out: pairs, d_hit_off: local offsets)
+};
+
+void locate_multi_phase1(const awry_index* ix, size_t ri, const QuerySource& qs, ReplicaLocateState& st, size_t n_active) {
+  (void)n_active;
+  if (st.lo >= st.hi) return;
+  Replica& r = *ix->reps[ri];
+  PackBalance& bal = ix->balance_of(ri);
+  DeviceGuard dg(r.device);
+  const uint64_t n = st.hi - st.lo;
+  const uint64_t max_bytes = std::min(chunk_max_bytes(), locate_chunk_bytes());
+  auto chunks = make_chunks(qs.qoff, st.lo, st.hi, locate_chunk_q(), max_bytes);
+  validate_chunks(chunks, max_bytes);
+  st.ws = r.acquire();
+  Workspace* top = st.ws;
+  const size_t pair_bytes = sp_cnt_bytes(r.view);
+  Workspace::grow_dev(top->d_out, top->d_out_cap, size_t(n) * pair_bytes);
+  Workspace::grow_dev(top->d_hit_off, top->d_hit_off_cap, size_t(n) + 1);
+  Workspace::grow_dev(top->d_off_out, top->d_off_out_cap, size_t(n) + 1);
+  constexpr int DEPTH = 3;
+  Workspace* ws[DEPTH] = {nullptr, nullptr, nullptr};
+  int pending[DEPTH] = {-1, -1, -1};
+  auto finish = [&](int s) {
+    if (pending[s] < 0) return;
+    CU(cudaEventSynchronize(ws[s]->done));
+    check_flag(ws[s], chunks[size_t(pending[s])]);
+    pending[s] = -1;
+  };
+  try {
+    for (size_t i = 0; i < chunks.size(); i++) {
+      const int s = int(i % DEPTH);
+      if (!ws[s]) ws[s] = r.acquire();
+      finish(s);
+      const Chunk& c = chunks[i];
+      enqueue_search(ix, r, bal, ws[s], qs, c, OUT_SP_CNT_U32, true, false, true,
+                     top->d_out + size_t(c.q0 - st.lo) * pair_bytes);
+      CU(cudaEventRecord(ws[s]->done, ws[s]->st));
+      pending[s] = int(i);
+    }
+    for (int s = 0; s < DEPTH; s++) finish(s);  // every chunk has searched: the pairs are complete
+    locate_chunk_scan(r, top, n, top->d_hit_off, top->st);
+    CU(cudaMemcpyAsync(top->h_total, top->d_hit_off + n, 8, cudaMemcpyDeviceToHost, top->st));
+    CU(cudaStreamSynchronize(top->st));
+    st.total = *top->h_total;
+  } catch (...) {
+    for (int s = 0; s < DEPTH; s++)
+      if (ws[s]) {
+        cudaStreamSynchronize(ws[s]->st);
+        r.release(ws[s]);
+      }
+    cudaStreamSynchronize(top->st);
+    r.release(top);
+    st.ws = nullptr;
+    throw;
+  }
+  for (int s = 0; s < DEPTH; s++)
+    if (ws[s]) r.release(ws[s]);
+}
+
+void locate_multi_phase2(const awry_index* ix, size_t ri, ReplicaLocateState& st, uint64_t* hit_off, void* hits_dev,
+                         uint64_t capacity) {
+  if (st.lo >= st.hi || !st.ws) return;
+  Replica& r = *ix->reps[ri];
+  DeviceGuard dg(r.device);
+  Workspace* top = st.ws;
+  const uint64_t n = st.hi - st.lo;
+  const bool off_pinned = is_pinned(hit_off);
+  try {
+    unsigned long long base = st.base;
+    CU(cudaMemcpyAsync(top->d_base + 1, &base, 8, cudaMemcpyHostToDevice, top->st));  // (pageable source: copied at the call)
+    CU(launch_gather_direct(r.view, reinterpret_cast<const uint2*>(top->d_out), top->d_hit_off, n, top->d_base + 1, top->d_base,
+                            hits_dev, capacity, top->d_off_out, r.sm_count, nullptr, nullptr, top->st));
+    uint64_t* dst = hit_off + st.lo;
+    if (!off_pinned) {
+      Workspace::grow_host(top->h_out, top->h_out_cap, size_t(n) * 8);
+      dst = reinterpret_cast<uint64_t*>(top->h_out);
+    }
+    CU(cudaMemcpyAsync(dst, top->d_off_out, n * 8, cudaMemcpyDeviceToHost, top->st));
+    g_prof.d2h += n * 8 + std::min(st.total, capacity > st.base ? capacity - st.base : 0) * sizeof(awry_hit);
+    CU(cudaStreamSynchronize(top->st));
+    if (!off_pinned) parallel_memcpy(hit_off + st.lo, top->h_out, n * 8);
+  } catch (...) {
+    cudaStreamSynchronize(top->st);
+    r.release(top);
+    st.ws = nullptr;
+    throw;
+  }
+  r.release(top);
+  st.ws = nullptr;
+}
+
 void locate_into_impl(const awry_index* ix, const QuerySource& qs, uint64_t nq, uint32_t flags, uint64_t* hit_off,
                       awry_hit* hits, uint64_t capacity, uint64_t* n_hits) {
   auto too_small = [&](uint64_t need) {
@@ -902,6 +1009,47 @@ void locate_into_impl(const awry_index* ix, const QuerySource& qs, uint64_t nq, 
     *n_hits = part.n_hits;
     if (part.n_hits > capacity) too_small(part.n_hits);
     return;
+  }
+  {  // several replicas: two phases with the hits written straight into the caller's pinned buffer
+    void* hits_dev = capacity ? device_view_of_pinned(hits) : nullptr;
+    bool all_full_sa = true;
+    for (auto& rp : ix->reps) all_full_sa = all_full_sa && rp->view.full_sa != nullptr;
+    const size_t nr = ix->reps.size();
+    if (hits_dev && !(flags & AWRY_LOCATE_SORTED) && all_full_sa && g_locate_variant == 0 && direct_locate_enabled() &&
+        nq >= 2 * nr) {
+      std::vector<ReplicaLocateState> st(nr);
+      auto release_all = [&] {
+        for (size_t ri = 0; ri < nr; ri++)
+          if (st[ri].ws) {
+            cudaSetDevice(ix->reps[ri]->device);
+            cudaStreamSynchronize(st[ri].ws->st);
+            ix->reps[ri]->release(st[ri].ws);
+            st[ri].ws = nullptr;
+          }
+      };
+      try {
+        for_each_replica_range(ix, qs.qoff, nq, [&](size_t ri, uint64_t lo, uint64_t hi) {
+          st[ri].lo = lo;
+          st[ri].hi = hi;
+          locate_multi_phase1(ix, ri, qs, st[ri], nr);
+        });
+        uint64_t total = 0;
+        for (auto& x : st) {
+          x.base = total;
+          total += x.total;
+        }
+        for_each_replica_range(ix, qs.qoff, nq, [&](size_t ri, uint64_t, uint64_t) {
+          locate_multi_phase2(ix, ri, st[ri], hit_off, hits_dev, capacity);
+        });
+        hit_off[nq] = total;
+        *n_hits = total;
+      } catch (...) {
+        release_all();
+        throw;
+      }
+      if (*n_hits > capacity) too_small(*n_hits);
+      return;
+    }
   }
   awry_hit* tmp = nullptr;
   uint64_t n = 0;

@@ -334,8 +334,12 @@ struct Replica {
 };
 
 // Pack on the host or send ASCII?  Three rates decide, all MEASURED per replica of a handle and smoothed
-// across its calls, in query bytes per second: H, what the host packs for this replica (the host clock around
-// the packer -- in a multi-replica call that is the replica's share of the one pool); P, what its PCIe link
+// across its calls, in query bytes per second: H, what the host packs for this replica -- the POOL's rate (the
+// host clock around the packer, times the parallel regions that shared the pool meanwhile) divided by the
+// replicas of the call: a replica that timed only its own pack calls would see the pool whenever the others
+// happen to be copying, overrate it, and all replicas together would pack 40 % of the bytes where 25 % is right
+// (8 GPUs behind 32 cores: 0.95 G reads/s that way, profiles/r02_m8_bench_line_n8_before_global_balance.json);
+// P, what its PCIe link
 // moves raw (CUDA events around the copy of a raw first chunk); G, what its search kernel consumes (CUDA
 // events around the kernel).  H >= 1.15 G: the host keeps the GPU fed on its own -- pack everything, a quarter
 // of the bytes cross the link (one GPU behind 16 host threads: H = 121, G = 82 GB/s; mixing raw chunks in was
@@ -354,10 +358,10 @@ struct PackBalance {
     if (const char* e = getenv("AWRY_B200_PACK_SHARE")) fixed_share = std::min(1.0, std::max(0.0, atof(e)));
     if (const char* e = getenv("AWRY_B200_PACK_MIXED")) mixed = e[0] != '0';
   }
-  void note_host(double bytes, double seconds) {
+  void note_host(double bytes, double seconds, int sharers = 1) {  // host_rate: of the whole pool
     if (seconds <= 0 || bytes < (8 << 20)) return;
     std::lock_guard<std::mutex> lk(mu);
-    double r = bytes / seconds;
+    double r = bytes / seconds * double(sharers < 1 ? 1 : sharers);
     host_rate = host_rate > 0 ? 0.7 * host_rate + 0.3 * r : r;
   }
   void note_link(double bytes, double seconds) {
@@ -377,11 +381,12 @@ struct PackBalance {
     double share;
     bool probe_link, probe_host;
   };
-  Plan plan() {
+  Plan plan(size_t n_replicas = 1) {
     std::lock_guard<std::mutex> lk(mu);
     if (fixed_share >= 0) return Plan{fixed_share, false, false};
     const bool refresh = calls++ % 32 == 0;
-    if (host_rate <= 0 || link_rate <= 0) return Plan{1.0, true, true};
+    if (this->host_rate <= 0 || link_rate <= 0) return Plan{1.0, true, true};
+    const double host_rate = this->host_rate / double(n_replicas ? n_replicas : 1);  // this replica's share of the pool
     // (until the kernel's rate is known, "clearly faster than the link" stands in for "feeds the GPU")
     const bool host_suffices = gpu_rate > 0 ? host_rate >= 1.15 * gpu_rate : host_rate > 2.0 * link_rate;
     if (host_suffices) return Plan{1.0, refresh, false};

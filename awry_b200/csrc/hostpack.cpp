@@ -61,7 +61,9 @@ class Pool {
     cap_ = std::max(1, std::min(n, 256));
   }
   // runs fn(block) for block in [0, n_blocks) on up to `max_threads` threads (0 = the pool's cap)
-  void run(size_t n_blocks, const std::function<void(size_t)>& fn, int max_threads = 0) {
+  // open_before: parallel regions already open when this one starts (its competitors for the pool's threads)
+  void run(size_t n_blocks, const std::function<void(size_t)>& fn, int max_threads = 0, int* open_before = nullptr) {
+    if (open_before) *open_before = 0;
     if (n_blocks == 0) return;
     auto job = std::make_shared<Job>();
     job->fn = &fn;
@@ -79,6 +81,7 @@ class Pool {
           break;  // cannot spawn: run with what there is
         }
       }
+      if (open_before) *open_before = int(jobs_.size());
       if (want > 1) jobs_.push_back(job);
     }
     if (want > 1) cv_.notify_all();
@@ -309,8 +312,9 @@ void host_parallel_blocks(size_t n_blocks, const std::function<void(size_t)>& fn
 }
 
 bool host_pack_dna(const uint8_t* src, size_t n, uint8_t* dst, std::vector<uint64_t>& exceptions, size_t max_exc_div,
-                   int max_threads) {
+                   int max_threads, int* sharers) {
   exceptions.clear();
+  if (sharers) *sharers = 1;
   if (n == 0) return true;
   const Level lvl = simd_level();
   const size_t G = 64;  // granule: both SIMD widths and whole output bytes
@@ -336,7 +340,9 @@ bool host_pack_dna(const uint8_t* src, size_t n, uint8_t* dst, std::vector<uint6
       pack_scalar(src, lo, hi, dst, e);
     if (!e.empty()) n_exc.fetch_add(e.size(), std::memory_order_relaxed);
   };
-  pool().run(n_blocks, body, max_threads);
+  int open_before = 0;
+  pool().run(n_blocks, body, max_threads, &open_before);
+  if (sharers) *sharers = open_before + 1;
   if (n_gran * G < n) {  // tail
     memset(dst + (n_gran * G) / 4, 0, (n - n_gran * G + 3) / 4);
     pack_scalar(src, n_gran * G, n, dst, exc[n_blocks]);

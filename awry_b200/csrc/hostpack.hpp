@@ -23,7 +23,9 @@ void host_parallel_blocks(size_t n_blocks, const std::function<void(size_t)>& fn
 // case).  Every byte that is not one of ACGTacgt is reported as (i << 8) | byte in `exceptions`, ascending by
 // position; its crumb is arbitrary and gets patched on the device.  Returns false (dst incomplete) when
 // more than n / max_exc_div bytes are exceptions -- the caller then sends the chunk as ASCII.
+// *sharers: parallel regions that were open in the pool when this one started, itself included (the share of
+// the pool this call could count on was 1 / sharers).
 bool host_pack_dna(const uint8_t* src, size_t n, uint8_t* dst, std::vector<uint64_t>& exceptions, size_t max_exc_div,
-                   int max_threads = 0);
+                   int max_threads = 0, int* sharers = nullptr);
 
 }  // namespace awry
