@@ -72,6 +72,25 @@ uint64_t ipow(uint64_t b, uint32_t e) {
 
 
 
+// sizes of the arrays, in elements (AWRY_CHK in the checked build; the allocations carry 256 B of slack on top);
+// called again whenever one of the derived arrays has been built
+void set_limits(awry_index* ix, Replica& r) {
+  IndexView& v = r.view;
+  v.n_blocks_u4 = r.bytes_blocks / 16;
+  v.n_pair_u4 = r.d_pair ? pair_block_count(ix->bwt_len) * PAIR_BLOCK_UINT4 : 0;
+  v.n_table = ix->wide ? 0 : (r.d_table ? table_entries(ix->alphabet, ix->kmer_len_dev) : 0);
+  v.n_sa_words = ix->n_sa_words + 2;
+  v.n_full_sa = r.d_full_sa ? ix->bwt_len : 0;
+  v.n_walk_u4 = r.d_walk ? walk_block_count(ix->bwt_len) * WALK_BLOCK_UINT4 : 0;
+  v.n_walk_rank = r.d_walk ? walk_block_count(ix->bwt_len) + 1 : 0;
+  v.n_pos_samples = r.d_walk && ix->lean_ratio ? (ix->bwt_len + ix->lean_ratio - 1) / ix->lean_ratio : 0;
+  WideView& w = r.wview;
+  w.n_blocks_u4 = r.bytes_blocks / 16;
+  w.n_table = r.d_table_w ? table_entries(ix->alphabet, ix->kmer_len_dev) : 0;
+  w.n_sa_words = ix->n_sa_words + 2;
+  w.n_sb = ix->n_superblocks();
+}
+
 void set_view_constants(awry_index* ix, Replica& r) {
   IndexView& v = r.view;
   v.blocks = r.d_blocks;
@@ -84,6 +103,7 @@ void set_view_constants(awry_index* ix, Replica& r) {
   v.walk_rank = r.d_walk_rank;
   v.pos_samples = r.d_pos_samples;
   v.lean_ratio = ix->lean_ratio;
+  set_limits(ix, r);
   for (int i = 0; i < 16; i++) v.c2[i] = r.c2[i];
   v.bwt_len = ix->wide ? 0xffffffffu : uint32_t(ix->bwt_len);
   v.dollar_row = ix->wide ? 0xffffffffu : uint32_t(r.dollar_row);
@@ -126,6 +146,7 @@ void set_view_constants(awry_index* ix, Replica& r) {
     w.n_seqs = v.n_seqs;
     w.alphabet = v.alphabet;
     w.sb_shift = ix->sb_shift;
+    set_limits(ix, r);
     for (int i = 0; i < 24; i++) w.c_lo[i] = 1, w.c_hi[i] = 0;
     if (ix->alphabet == AWRY_NUCLEOTIDE) {
       static const int ref_of_dsym[6] = {1, 2, 3, 5, 4, 0};  // A C G T N $
@@ -305,6 +326,7 @@ void finish_replica0(awry_index* ix, Replica& r) {
     r.bytes_table = table_entries(ix->alphabet, k) * entry_bytes;
     CU(cudaMalloc(reinterpret_cast<void**>(&r.d_table_w), r.bytes_table));
     r.wview.table = r.d_table_w;
+    set_limits(ix, r);
     WideView v = r.wview;
     v.kmer_len = 0;
     CU(launch_build_table_wide(v, r.d_table_w, k, nullptr));
@@ -313,6 +335,7 @@ void finish_replica0(awry_index* ix, Replica& r) {
     r.bytes_table = table_entries(ix->alphabet, k) * 8;
     CU(cudaMalloc(reinterpret_cast<void**>(&r.d_table), r.bytes_table));
     r.view.table = r.d_table;
+    set_limits(ix, r);
     IndexView v = r.view;
     v.kmer_len = 0;
     CU(launch_build_table(v, r.d_table, k, nullptr));
@@ -330,6 +353,7 @@ void finish_replica0(awry_index* ix, Replica& r) {
       CU(build_pair_index(r.view, r.d_pair, r.c2, nullptr));
       r.bytes_pair = bytes;
       r.view.pair_blocks = r.d_pair;
+      set_limits(ix, r);
       for (int i = 0; i < 16; i++) r.view.c2[i] = r.c2[i];
     }
   }
@@ -346,6 +370,7 @@ void finish_replica0(awry_index* ix, Replica& r) {
       CU(cudaDeviceSynchronize());
       r.bytes_full_sa = bytes;
       r.view.full_sa = r.d_full_sa;
+      set_limits(ix, r);
     }
   }
   // Memory-lean bounded locate (nucleotide): walk blocks + position-sampled suffix array, 4.57 + 32/ratio bits
@@ -377,6 +402,7 @@ void finish_replica0(awry_index* ix, Replica& r) {
       CU(build_lean_sa(r.view, r.d_walk, r.d_walk_rank, r.d_pos_samples, r.sm_count, nullptr));
       r.bytes_lean = bytes;
       r.view.walk_blocks = r.d_walk;
+      set_limits(ix, r);
       r.view.walk_rank = r.d_walk_rank;
       r.view.pos_samples = r.d_pos_samples;
     }

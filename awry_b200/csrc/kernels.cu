@@ -438,6 +438,7 @@ __global__ void __launch_bounds__(96)
     if (a < 4) {
       uint32_t j = ix.c_lo[a] + dna_occ_in_block(ix, blk1, b1, l1, a) - 1;  // LF(row)
       uint32_t lj = j & 127;
+      AWRY_CHK(uint64_t(j >> 7) * DNA_BLOCK_UINT4 + 3 < ix.n_blocks_u4);
       uint4 ch = ldg128(ix.blocks + size_t(j >> 7) * DNA_BLOCK_UINT4 + (lj >> 5));
       uint32_t t = lj & 31;
       uint32_t b = ((ch.x >> t) & 1u) | (((ch.y >> t) & 1u) << 1) | (((ch.z >> t) & 1u) << 2);
@@ -757,6 +758,7 @@ __device__ __forceinline__ uint32_t begin_query(const IndexView& ix, const uint6
       }
     }
     if (ok) {
+      AWRY_CHK(idx < ix.n_table);
       uint2 r = __ldg(ix.table + idx);
       sp = r.x;
       ep = r.y;
@@ -859,6 +861,7 @@ __global__ void __launch_bounds__(TPB, MINB)
     uint32_t ba = pa >> 7, bb = pb >> 7;
     if (c < 4) {
       const uint4* blk = ix.blocks + size_t(ba) * DNA_BLOCK_UINT4;
+      AWRY_CHK(uint64_t(ba) * DNA_BLOCK_UINT4 + 3 < ix.n_blocks_u4 && uint64_t(bb) * DNA_BLOCK_UINT4 + 3 < ix.n_blocks_u4);
       LaneChunks<LANES> x;
       x.load(blk, sub);
       uint32_t m0 = (c & 1) ? ~0u : 0u, m1 = (c & 2) ? ~0u : 0u;
@@ -1091,6 +1094,7 @@ __global__ void __launch_bounds__(TPB, MINB)
           uint32_t amb = 0;
           __syncwarp(gmask);
           if (4 * sub < nwords) {
+            AWRY_CHK_QWORDS(ubase + 4 * sub, br, nq, 6);
             u32x8 t = ldg256(qwords + ubase + 4 * sub);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -1111,7 +1115,8 @@ __global__ void __launch_bounds__(TPB, MINB)
               uint64_t idx = 0;
 #pragma unroll 1
               for (uint32_t j = 0; j < k; j++) idx |= ((w >> (4 * j)) & 3ull) << (2 * j);
-              uint2 r = __ldg(ix.table + idx);
+              AWRY_CHK(idx < ix.n_table);
+      uint2 r = __ldg(ix.table + idx);
               sp = r.x;
               ep = r.y;
               left = len - k;
@@ -1133,6 +1138,7 @@ __global__ void __launch_bounds__(TPB, MINB)
       uint32_t amb = 0;
       __syncwarp(gmask);
       if (sub < 2) {
+        AWRY_CHK_QWORDS(ubase + wlim + 8 + 4 * sub, br, nq, 6);
         u32x8 t = ldg256(qwords + ubase + wlim + 8 + 4 * sub);  // in bounds: buffer padded by 32 words
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -1161,6 +1167,7 @@ __global__ void __launch_bounds__(TPB, MINB)
         const uint32_t pair = ((qb & 3u) << 2) | (qb >> 4);
         const uint32_t ba = __umulhi(pa, 0xAAAAAAABu) >> 6;  // / 96
         const uint32_t la = pa - ba * PAIR_ROWS_PER_BLOCK, lb = pb - ba * PAIR_ROWS_PER_BLOCK;
+        AWRY_CHK(uint64_t(ba) * PAIR_BLOCK_UINT4 + 7 < ix.n_pair_u4);
         u32x8 x = ldg256(ix.pair_blocks + size_t(ba) * PAIR_BLOCK_UINT4 + 2 * sub);
         PairSlice s = pair_slice(x, sub, pair);
         ra = __popc(s.match & low_mask(int(la) + 1 - int(32 * sub))) + s.count;
@@ -1168,6 +1175,7 @@ __global__ void __launch_bounds__(TPB, MINB)
           rb = __popc(s.match & low_mask(int(lb) + 1 - int(32 * sub))) + s.count;
         } else {  // the interval straddles two blocks (only while it is still wide): a real branch
           const uint32_t bb = __umulhi(pb, 0xAAAAAAABu) >> 6;
+          AWRY_CHK(uint64_t(bb) * PAIR_BLOCK_UINT4 + 7 < ix.n_pair_u4);
           x = ldg256(ix.pair_blocks + size_t(bb) * PAIR_BLOCK_UINT4 + 2 * sub);
           s = pair_slice(x, sub, pair);
           rb = __popc(s.match & low_mask(int(pb - bb * PAIR_ROWS_PER_BLOCK) + 1 - int(32 * sub))) + s.count;
@@ -1177,6 +1185,7 @@ __global__ void __launch_bounds__(TPB, MINB)
         const uint32_t c1 = (qb >> (4 * (pos & 1))) & 15u;
         const uint32_t ba = pa >> 7, bb = pb >> 7;
         LaneChunks<4> y;
+        AWRY_CHK(uint64_t(ba) * DNA_BLOCK_UINT4 + 3 < ix.n_blocks_u4 && uint64_t(bb) * DNA_BLOCK_UINT4 + 3 < ix.n_blocks_u4);
         y.load(ix.blocks + size_t(ba) * DNA_BLOCK_UINT4, sub);
         const uint32_t m0 = (c1 & 1) ? ~0u : 0u, m1 = (c1 & 2) ? ~0u : 0u;
         ra = dna_partial_rank<4>(y, sub, pa & 127, c1, m0, m1);
@@ -1312,9 +1321,11 @@ __global__ void __launch_bounds__(TPB, MINB)
         if (left[s] >= 2 && (pos & 1) == 0) {
           pc[s] = PC_STEP | PC_TWO | ((qb & 3u) << 2) | (qb >> 4);
           const uint32_t ba = __umulhi(pa, 0xAAAAAAABu) >> 6;  // / 96
+          AWRY_CHK(uint64_t(ba) * PAIR_BLOCK_UINT4 + 7 < ix.n_pair_u4);
           x[s] = ldg256(ix.pair_blocks + size_t(ba) * PAIR_BLOCK_UINT4 + 2 * sub);
         } else {
           pc[s] = PC_STEP | ((qb >> (4 * (pos & 1))) & 15u);
+          AWRY_CHK(uint64_t(pa >> 7) * DNA_BLOCK_UINT4 + 3 < ix.n_blocks_u4);
           const uint4 c = ldg128(ix.blocks + size_t(pa >> 7) * DNA_BLOCK_UINT4 + sub);
           x[s].v[0] = c.x;
           x[s].v[1] = c.y;
@@ -1326,18 +1337,25 @@ __global__ void __launch_bounds__(TPB, MINB)
         x[s].v[0] = uint32_t(ov);
         x[s].v[1] = uint32_t(ov >> 32);
       } else if (st[s] == ST_WORDS) {
-        if (4 * sub < ((len[s] + 15) >> 4)) x[s] = ldg256(qwords + ubase[s] + 4 * sub);
+        if (4 * sub < ((len[s] + 15) >> 4)) {
+          AWRY_CHK_QWORDS(ubase[s] + 4 * sub, br, nq, 6);
+          x[s] = ldg256(qwords + ubase[s] + 4 * sub);
+        }
       } else if (st[s] == ST_SEED) {
         const uint32_t k = ix.kmer_len;
         const uint64_t w = s_q[s][grp][0];  // k <= 16: inside word 0
         uint64_t idx = 0;
 #pragma unroll 1
         for (uint32_t j = 0; j < k; j++) idx |= ((w >> (4 * j)) & 3ull) << (2 * j);
+        AWRY_CHK(idx < ix.n_table);
         const uint2 r = __ldg(ix.table + idx);
         x[s].v[0] = r.x;
         x[s].v[1] = r.y;
       } else if (st[s] == ST_RING) {
-        if (sub < 2) x[s] = ldg256(qwords + ubase[s] + wlim[s] + 8 + 4 * sub);  // in bounds: buffer padded by 32 words
+        if (sub < 2) {
+          AWRY_CHK_QWORDS(ubase[s] + wlim[s] + 8 + 4 * sub, br, nq, 6);
+          x[s] = ldg256(qwords + ubase[s] + wlim[s] + 8 + 4 * sub);  // in bounds: buffer padded by 32 words
+        }
       }
     }
 
@@ -1359,6 +1377,7 @@ __global__ void __launch_bounds__(TPB, MINB)
             rb[s] = __popc(sl.match & low_mask(int(lb) + 1 - int(32 * sub))) + sl.count;
           } else {  // the interval straddles two blocks (only while it is still wide): a real branch
             const uint32_t bb = __umulhi(pb, 0xAAAAAAABu) >> 6;
+            AWRY_CHK(uint64_t(bb) * PAIR_BLOCK_UINT4 + 7 < ix.n_pair_u4);
             const u32x8 y = ldg256(ix.pair_blocks + size_t(bb) * PAIR_BLOCK_UINT4 + 2 * sub);
             sl = pair_slice(y, sub, pair);
             rb[s] = __popc(sl.match & low_mask(int(pb - bb * PAIR_ROWS_PER_BLOCK) + 1 - int(32 * sub))) + sl.count;
@@ -1370,6 +1389,7 @@ __global__ void __launch_bounds__(TPB, MINB)
           y.c[0] = make_uint4(x[s].v[0], x[s].v[1], x[s].v[2], x[s].v[3]);
           const uint32_t m0 = (c1 & 1) ? ~0u : 0u, m1 = (c1 & 2) ? ~0u : 0u;
           ra[s] = dna_partial_rank<4>(y, sub, pa & 127, c1, m0, m1);
+          AWRY_CHK(uint64_t(bb) * DNA_BLOCK_UINT4 + 3 < ix.n_blocks_u4);
           if (bb != ba) y.load(ix.blocks + size_t(bb) * DNA_BLOCK_UINT4, sub);
           rb[s] = dna_partial_rank<4>(y, sub, pb & 127, c1, m0, m1);
         }
@@ -1616,6 +1636,7 @@ __global__ void __launch_bounds__(TPB, MINB)
           const uint32_t nwords = (len + 7) >> 3;
           __syncwarp(gmask);
           if (4 * sub < nwords) {
+            AWRY_CHK_QWORDS(ubase + 4 * sub, br, nq, 5);
             u32x8 t = ldg256(qwords + ubase + 4 * sub);
 #pragma unroll
             for (int j = 0; j < 4; j++) ring[4 * sub + j] = uint64_t(t.v[2 * j]) | (uint64_t(t.v[2 * j + 1]) << 32);
@@ -1636,7 +1657,8 @@ __global__ void __launch_bounds__(TPB, MINB)
               mult *= 20;
             }
             if (ok) {
-              uint2 r = __ldg(ix.table + idx);
+              AWRY_CHK(idx < ix.n_table);
+      uint2 r = __ldg(ix.table + idx);
               sp = r.x;
               ep = r.y;
               left = len - k;
@@ -1661,6 +1683,7 @@ __global__ void __launch_bounds__(TPB, MINB)
     if (active && (pos >> 3) >= wlim) {  // long query: bring in words [wlim+8, wlim+16)
       __syncwarp(gmask);
       if (sub < 2) {
+        AWRY_CHK_QWORDS(ubase + wlim + 8 + 4 * sub, br, nq, 5);
         u32x8 t = ldg256(qwords + ubase + wlim + 8 + 4 * sub);
 #pragma unroll
         for (int j = 0; j < 4; j++)
@@ -1680,6 +1703,7 @@ __global__ void __launch_bounds__(TPB, MINB)
     if (active) {
       const uint32_t ba = pa >> 6, bb = pb >> 6;
       const int na = int(pa & 63) + 1 - int(32 * sub), nb = int(pb & 63) + 1 - int(32 * sub);
+      AWRY_CHK(uint64_t(ba) * AMINO_BLOCK_UINT4 + 7 < ix.n_blocks_u4 && uint64_t(bb) * AMINO_BLOCK_UINT4 + 7 < ix.n_blocks_u4);
       u32x8 x = ldg256(ix.blocks + size_t(ba) * AMINO_BLOCK_UINT4 + 2 * sub);
       AminoSlice s = amino_slice(x, sub, c);
       ra = __popc(s.match & low_mask(na)) + s.count;

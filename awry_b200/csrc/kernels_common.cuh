@@ -31,6 +31,10 @@ __device__ __forceinline__ void store_result(void* out, uint64_t q, uint32_t sp,
 struct ByteRange {
   uint64_t lo, hi;
 };
+// checked build: a 32-byte read of packed query words at absolute word index w (the buffer pointer is biased
+// by the batch's first byte) stays inside the packed_words() the batch was given
+#define AWRY_CHK_QWORDS(w, br, nq, shift) \
+  AWRY_CHK(uint64_t(w) >= 4 * ((br).lo >> (shift)) && uint64_t(w) - 4 * ((br).lo >> (shift)) + 3 < 4 * ((nq) + (((br).hi - (br).lo) >> (shift)) + 2) + 32)
 __device__ __forceinline__ uint32_t checked_len(uint64_t o0, uint64_t o1, const ByteRange& b) {
   return (o0 < b.lo || o1 > b.hi || o1 < o0 || o1 - o0 >= (1ull << 32)) ? 0u : uint32_t(o1 - o0);
 }

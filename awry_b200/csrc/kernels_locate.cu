@@ -46,6 +46,7 @@ __device__ __forceinline__ void map_location(const IndexView& ix, uint64_t loc, 
         hi = mid - 1;
     }
   }
+  AWRY_CHK(lo < ix.n_seqs && loc >= __ldg(ix.seq_starts + lo));
   out2[0] = lo;
   out2[1] = loc - __ldg(ix.seq_starts + lo);
 }
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(256) walk_dna_kernel(IndexView ix, uint64_t n_
     const uint32_t blk = row >> 7, l = row & 127;
     LaneChunks<2> x;
     x.c[0] = x.c[1] = make_uint4(0, 0, 0, 0);
+    AWRY_CHK(!have || uint64_t(blk) * DNA_BLOCK_UINT4 + 3 < ix.n_blocks_u4);
     if (have) x.load(ix.blocks + size_t(blk) * DNA_BLOCK_UINT4, sub);
     const uint4 ch = (l & 32) ? x.c[1] : x.c[0];
     const uint32_t t = l & 31;
@@ -201,6 +203,7 @@ __global__ void __launch_bounds__(256) walk_amino_kernel(IndexView ix, uint64_t 
     u32x8 x;
 #pragma unroll
     for (int i = 0; i < 8; i++) x.v[i] = 0;
+    AWRY_CHK(!have || uint64_t(blk) * AMINO_BLOCK_UINT4 + 7 < ix.n_blocks_u4);
     if (have) x = ldg256(ix.blocks + size_t(blk) * AMINO_BLOCK_UINT4 + 2 * sub);
     const uint32_t t = l & 31;
     uint32_t c = 0;
@@ -255,6 +258,7 @@ template <int MODE>
 __device__ __forceinline__ void unsample_visit(const IndexView& ix, uint32_t row, uint32_t p, uint32_t* __restrict__ full,
                                                uint4* __restrict__ walk, uint32_t* __restrict__ pos_samples) {
   if (MODE == UNSAMPLE_FULL) {
+    AWRY_CHK(row < ix.bwt_len);
     full[row] = p;
     return;
   }
@@ -264,7 +268,9 @@ __device__ __forceinline__ void unsample_visit(const IndexView& ix, uint32_t row
     uint32_t* w = walk_mark_word(walk, row, bit);
     atomicOr(w, 1u << bit);
   } else {
-    pos_samples[ix.walk_rank[row / WALK_ROWS_PER_BLOCK] + walk_marks_before(walk, row)] = p / ix.lean_ratio;
+    const uint32_t at = ix.walk_rank[row / WALK_ROWS_PER_BLOCK] + walk_marks_before(walk, row);
+    AWRY_CHK(row / WALK_ROWS_PER_BLOCK < ix.n_walk_rank && at < ix.n_pos_samples);
+    pos_samples[at] = p / ix.lean_ratio;
   }
 }
 
@@ -300,6 +306,7 @@ __global__ void __launch_bounds__(256)
     const uint32_t blk = row >> 7, l = row & 127;
     LaneChunks<2> x;
     x.c[0] = x.c[1] = make_uint4(0, 0, 0, 0);
+    AWRY_CHK(!have || uint64_t(blk) * DNA_BLOCK_UINT4 + 3 < ix.n_blocks_u4);
     if (have) x.load(ix.blocks + size_t(blk) * DNA_BLOCK_UINT4, sub);
     const uint4 ch = (l & 32) ? x.c[1] : x.c[0];
     const uint32_t t = l & 31;
@@ -353,6 +360,7 @@ __global__ void __launch_bounds__(256)
     u32x8 x;
 #pragma unroll
     for (int i = 0; i < 8; i++) x.v[i] = 0;
+    AWRY_CHK(!have || uint64_t(blk) * AMINO_BLOCK_UINT4 + 7 < ix.n_blocks_u4);
     if (have) x = ldg256(ix.blocks + size_t(blk) * AMINO_BLOCK_UINT4 + 2 * sub);
     const uint32_t t = l & 31;
     uint32_t c = 0;
@@ -534,6 +542,7 @@ __global__ void __launch_bounds__(256) walk_lean_kernel(IndexView ix, uint64_t n
     u32x8 x;
 #pragma unroll
     for (int i = 0; i < 8; i++) x.v[i] = 0;
+    AWRY_CHK(!have || uint64_t(blk) * WALK_BLOCK_UINT4 + 7 < ix.n_walk_u4);
     if (have) x = ldg256(ix.walk_blocks + size_t(blk) * WALK_BLOCK_UINT4 + 2 * sub);
     // the lane that holds the row's group reads its code and mark
     const uint32_t g = l >> 5, t = l & 31, half = g & 1;
@@ -562,6 +571,7 @@ __global__ void __launch_bounds__(256) walk_lean_kernel(IndexView ix, uint64_t n
     if (have) {
       if (marked) {
         if (sub == 0) {
+          AWRY_CHK(blk < ix.n_walk_rank && uint64_t(__ldg(ix.walk_rank + blk)) + r < ix.n_pos_samples && steps < ix.lean_ratio);
           const uint64_t loc = uint64_t(__ldg(ix.pos_samples + __ldg(ix.walk_rank + blk) + r)) * ix.lean_ratio + steps;
           if (MAP)
             map_location(ix, loc, out + SLOT * cur);
@@ -605,6 +615,7 @@ __global__ void __launch_bounds__(256)
     }
     uint32_t small = cnt < 8 ? cnt : 8;
     for (uint32_t i = 0; i < small; i++) {
+      AWRY_CHK(uint64_t(sp) + i < ix.n_full_sa);
       uint64_t loc = __ldg(full + sp + i);
       if (MAP)
         map_location(ix, loc, out + SLOT * (off + i));
@@ -618,6 +629,7 @@ __global__ void __launch_bounds__(256)
       uint32_t s = __shfl_sync(0xffffffffu, sp, L), c = __shfl_sync(0xffffffffu, cnt, L);
       uint64_t o = __shfl_sync(0xffffffffu, off, L);
       for (uint32_t i = 8 + lane; i < c; i += 32) {
+        AWRY_CHK(uint64_t(s) + i < ix.n_full_sa);
         uint64_t loc = __ldg(full + s + i);
         if (MAP)
           map_location(ix, loc, out + SLOT * (o + i));
@@ -666,6 +678,7 @@ __global__ void __launch_bounds__(256)
     uint32_t small = cnt < 8 ? cnt : 8;
     for (uint32_t i = 0; i < small; i++) {
       uint64_t pr[2];
+      AWRY_CHK(uint64_t(sp) + i < ix.n_full_sa);
       map_location(ix, __ldg(full + sp + i), pr);
       if (off + i < capacity) out[off + i] = make_ulonglong2(pr[0], pr[1]);
     }
@@ -677,6 +690,7 @@ __global__ void __launch_bounds__(256)
       uint64_t o = __shfl_sync(0xffffffffu, off, L);
       for (uint32_t i = 8 + lane; i < c; i += 32) {
         uint64_t pr[2];
+        AWRY_CHK(uint64_t(s) + i < ix.n_full_sa);
         map_location(ix, __ldg(full + s + i), pr);
         if (o + i < capacity) out[o + i] = make_ulonglong2(pr[0], pr[1]);
       }

@@ -22,6 +22,7 @@ namespace awry {
 __device__ __forceinline__ uint64_t w_dna_occ(const WideView& ix, uint64_t pos, uint32_t c) {  // c in 0..4
   const uint64_t blk = pos >> 7;
   const uint32_t local = uint32_t(pos) & 127;
+  AWRY_CHK(blk * DNA_BLOCK_UINT4 + 3 < ix.n_blocks_u4 && (blk >> (ix.sb_shift - 7)) < ix.n_sb);
   const DnaBlockRegs b = dna_load_block(ix.blocks, blk);
   const uint64_t* sb = ix.sb_counts + (blk >> (ix.sb_shift - 7)) * SB_STRIDE;
   uint64_t r;
@@ -38,6 +39,7 @@ __device__ __forceinline__ uint64_t w_dna_occ(const WideView& ix, uint64_t pos, 
   return r;
 }
 __device__ __forceinline__ uint32_t w_dna_code_at(const WideView& ix, uint64_t row) {
+  AWRY_CHK((row >> 7) * DNA_BLOCK_UINT4 + 3 < ix.n_blocks_u4);
   const uint4 ch = ldg128(ix.blocks + size_t(row >> 7) * DNA_BLOCK_UINT4 + ((uint32_t(row) >> 5) & 3));
   const uint32_t t = uint32_t(row) & 31;
   return ((ch.x >> t) & 1u) | (((ch.y >> t) & 1u) << 1) | (((ch.z >> t) & 1u) << 2);
@@ -45,6 +47,7 @@ __device__ __forceinline__ uint32_t w_dna_code_at(const WideView& ix, uint64_t r
 __device__ __forceinline__ uint64_t w_amino_occ(const WideView& ix, uint64_t pos, uint32_t s) {  // s in 1..21
   const uint64_t blk = pos >> 6;
   const uint32_t local = uint32_t(pos) & 63;
+  AWRY_CHK(blk * AMINO_BLOCK_UINT4 + 7 < ix.n_blocks_u4 && (blk >> (ix.sb_shift - 6)) < ix.n_sb);
   const char* base = reinterpret_cast<const char*>(ix.blocks + size_t(blk) * AMINO_BLOCK_UINT4);
   uint64_t r = __ldg(ix.sb_counts + (blk >> (ix.sb_shift - 6)) * SB_STRIDE + s) +
                __ldg(reinterpret_cast<const uint32_t*>(base) + amino_count_word(s));
@@ -58,6 +61,7 @@ __device__ __forceinline__ uint64_t w_amino_occ(const WideView& ix, uint64_t pos
 }
 __device__ __forceinline__ uint32_t w_amino_symbol_at(const WideView& ix, uint64_t pos) {
   const uint32_t local = uint32_t(pos) & 63, j = local >> 5, t = local & 31;
+  AWRY_CHK((pos >> 6) * AMINO_BLOCK_UINT4 + 7 < ix.n_blocks_u4);
   const uint32_t* w = reinterpret_cast<const uint32_t*>(ix.blocks + size_t(pos >> 6) * AMINO_BLOCK_UINT4) + 8 * j;
   uint32_t s = 0;
 #pragma unroll
@@ -94,6 +98,7 @@ __device__ __forceinline__ uint64_t w_sa_sample(const WideView& ix, uint64_t row
   const uint64_t bit = e * ix.sa_bits;  // < 2^64 for every bwt_len < 2^57
   const uint64_t w = bit >> 6;
   const uint32_t s = uint32_t(bit & 63);
+  AWRY_CHK(w + (s + ix.sa_bits > 64 ? 1 : 0) < ix.n_sa_words);
   uint64_t v = __ldg(ix.sa_words + w) >> s;
   if (s + ix.sa_bits > 64) v |= __ldg(ix.sa_words + w + 1) << (64 - s);
   return ix.sa_bits >= 64 ? v : (v & ((1ull << ix.sa_bits) - 1));
@@ -195,6 +200,7 @@ __global__ void __launch_bounds__(256) w_search_kernel(WideView ix, const uint64
           }
         }
         if (ok) {
+          AWRY_CHK(idx < ix.n_table);
           const ulonglong2 r = ix.table[idx];
           sp = r.x;
           ep = r.y;

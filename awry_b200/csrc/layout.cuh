@@ -52,6 +52,18 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// ---- checked build (libawry_b200_checked.so, `make checked`): compute-sanitizer is closed on the GPU pool this
+// was developed on, so every load whose address is computed from index or query DATA -- rank blocks, pair
+// blocks, seed table, suffix arrays, walk blocks, packed query words -- is bounds-checked by the code itself
+// against the array sizes the views carry; a violation is a device assert (the launch fails with
+// cudaErrorAssert, file and line on stderr).  tests/test_gpu_checked.py runs the GPU suite against that build.
+#ifdef AWRY_B200_CHECKED
+#include <cassert>
+#define AWRY_CHK(cond) assert(cond)
+#else
+#define AWRY_CHK(cond) ((void)0)
+#endif
+
 namespace awry {
 
 // ---- device symbol numbering -------------------------------------------------------------
@@ -93,6 +105,8 @@ struct IndexView {
   uint32_t alphabet;
   const WideView* wide;                    // HOST pointer, never read on the device: set for indexes with
                                            // bwt_len >= 2^32 - 256; the launchers then run kernels_wide.cu
+  // array sizes in elements (what AWRY_CHK checks against in the checked build)
+  uint64_t n_blocks_u4, n_pair_u4, n_table, n_sa_words, n_full_sa, n_walk_u4, n_walk_rank, n_pos_samples;
 };
 
 // ---- wide indexes: SearchPtr = u64 (search.rs:7), suffix-array elements up to 64 bits
@@ -113,6 +127,7 @@ struct WideView {
   uint64_t dollar_row;
   uint32_t sa_ratio, sa_pow2, sa_ratio_shift, sa_bits, kmer_len, n_seqs, alphabet;
   uint32_t sb_shift;                         // log2(rows per superblock), >= 8
+  uint64_t n_blocks_u4, n_table, n_sa_words, n_sb;  // array sizes in elements (checked build)
 };
 
 // 128-/256-bit read-only loads that do not allocate in L1: every block is touched once per
@@ -161,6 +176,7 @@ __device__ __forceinline__ DnaBlockRegs dna_load_block(const uint4* __restrict__
   return b;
 }
 __device__ __forceinline__ DnaBlockRegs dna_load_block(const IndexView& ix, uint32_t blk) {
+  AWRY_CHK(uint64_t(blk) * DNA_BLOCK_UINT4 + 3 < ix.n_blocks_u4);
   return dna_load_block(ix.blocks, blk);
 }
 // milestone of device symbol c (0..4) at the start of block blk
@@ -199,6 +215,7 @@ __host__ __device__ __forceinline__ uint32_t amino_count_word(uint32_t s) {
   return slot < 3 ? 5 + slot : slot < 6 ? 8 + 5 + (slot - 3) : slot < 14 ? 16 + (slot - 6) : 24 + (slot - 14);
 }
 __device__ __forceinline__ uint32_t amino_milestone(const IndexView& ix, uint32_t blk, uint32_t s) {
+  AWRY_CHK(uint64_t(blk) * AMINO_BLOCK_UINT4 + 7 < ix.n_blocks_u4 && s >= 1 && s <= 21);
   const uint32_t* words =
       reinterpret_cast<const uint32_t*>(ix.blocks + size_t(blk) * AMINO_BLOCK_UINT4);
   return __ldg(words + amino_count_word(s));
@@ -236,6 +253,7 @@ __device__ __forceinline__ void amino_occ2_same_block(const IndexView& ix, uint3
 }
 __device__ __forceinline__ uint32_t amino_symbol_at(const IndexView& ix, uint32_t pos) {
   uint32_t blk = pos >> 6, local = pos & 63, j = local >> 5, t = local & 31;
+  AWRY_CHK(uint64_t(blk) * AMINO_BLOCK_UINT4 + 7 < ix.n_blocks_u4);
   const uint32_t* w =
       reinterpret_cast<const uint32_t*>(ix.blocks + size_t(blk) * AMINO_BLOCK_UINT4) + 8 * j;
   uint32_t s = 0;
@@ -296,6 +314,7 @@ __device__ __forceinline__ uint64_t sa_sample(const IndexView& ix, uint32_t row)
   uint64_t bit = e * ix.sa_bits;
   uint64_t w = bit >> 6;
   uint32_t s = uint32_t(bit & 63);
+  AWRY_CHK(w + (s + ix.sa_bits > 64 ? 1 : 0) < ix.n_sa_words);
   uint64_t v = __ldg(ix.sa_words + w) >> s;
   if (s + ix.sa_bits > 64) v |= __ldg(ix.sa_words + w + 1) << (64 - s);
   return ix.sa_bits >= 64 ? v : (v & ((1ull << ix.sa_bits) - 1));
