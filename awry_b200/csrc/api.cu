@@ -399,6 +399,7 @@ void finish_replica0(awry_index* ix, Replica& r) {
       CU(cudaMalloc(reinterpret_cast<void**>(&r.d_walk), size_t(nb) * 128 + 256));
       CU(cudaMalloc(reinterpret_cast<void**>(&r.d_walk_rank), size_t(nb + 1) * 4 + 256));
       CU(cudaMalloc(reinterpret_cast<void**>(&r.d_pos_samples), size_t(n_pos + 4) * 4 + 256));
+      set_limits(ix, r);  // (the build kernels themselves run under the checks of the checked build)
       CU(build_lean_sa(r.view, r.d_walk, r.d_walk_rank, r.d_pos_samples, r.sm_count, nullptr));
       r.bytes_lean = bytes;
       r.view.walk_blocks = r.d_walk;

@@ -492,11 +492,20 @@ def inprocess_leg(a, torch, f, fxg, parts, world, rank_sums, rank_hit_totals):
         # what the HOST can deliver, measured alone: the packer on all threads, and raw pinned -> device copies on
         # all N links at once.  ASCII reads cross host memory once either way (read by the cores or by the DMA
         # engines), so these two rates bound `ascii` below whatever the GPUs could search.
+        import ctypes as C
         nb = nq * L
-        f.host_pack_dna(qb[:nb])
+        pk_dst = pinned_like(torch, nb // 4 + 64, torch.uint8).numpy()      # pinned and touched, like the library's staging
+        pk_exc = np.zeros(1 << 16, dtype=np.uint64)
+        pk_n = C.c_uint64()
+
+        def pack_once(r):
+            rc = f.native().awry_host_pack_dna(qb[r * nb:].ctypes.data, nb, pk_dst.ctypes.data, pk_exc.ctypes.data, len(pk_exc),
+                                               C.byref(pk_n))
+            assert rc == 0
+        pack_once(0)
         t0 = time.perf_counter()
         for r in range(world):
-            f.host_pack_dna(qb[r * nb:(r + 1) * nb])
+            pack_once(r)
         pack_gbs = world * nb / (time.perf_counter() - t0) / 1e9
         dsts = []
         for r in range(world):
