@@ -43,10 +43,11 @@ text = fx.gen_text(0, 50_000, 3)
 p = fx.build_parts(text, 0, ratio=8, kmer_len=0)
 n = p.bwt_len
 lie = np.array([0, 1, n, n, n, n, n], dtype=np.uint64)      # "every symbol is A": C rows then point past the BWT
-ix = FmIndex.from_parts(p.alphabet, p.ratio, n, 0, p.blocks, lie, p.sa_words)
+print("loading", flush=True)
+ix = FmIndex.from_parts(p.alphabet, p.ratio, n, 0, p.blocks, lie, p.sa_words)    # (the pair-index build already follows LF)
 qb, qo = f.pack_queries([b"ACGTACGTACGTACGTACGT", b"CCCCCCCC", b"GATTACA"])
 print("searching", flush=True)
-print(ix.count_packed(qb, qo))
+print("COUNTS", ix.count_packed(qb, qo))
 """
 
 
@@ -55,5 +56,6 @@ def test_the_checks_are_live(checked_lib):
     stops at the first such load with a device assert instead of reading whatever lies behind the array"""
     env = dict(os.environ, AWRY_B200_LIB=checked_lib, AWRY_B200_KMER_DEV="0")
     out = subprocess.run([sys.executable, "-c", LIVE % ROOT], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
-    assert "searching" in out.stdout
-    assert out.returncode != 0 and ("Assertion" in out.stderr or "assert" in out.stderr.lower()), out.stdout[-800:] + out.stderr[-1500:]
+    both = out.stdout[-800:] + out.stderr[-2500:]
+    assert "loading" in out.stdout and "COUNTS" not in out.stdout, both
+    assert out.returncode != 0 and "Assertion" in out.stderr and "device-side assert" in out.stderr, both
