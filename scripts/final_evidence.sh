@@ -7,7 +7,8 @@
 T=${1:-evidence}
 mkdir -p gpurun_out
 nproc > gpurun_out/${T}_host.txt; nvidia-smi -L >> gpurun_out/${T}_host.txt
-timeout 420 python -m pytest tests -m gpu -x -q --durations=8 > gpurun_out/${T}_tests.log 2>&1; echo "tests rc=$?"
+timeout 60 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/${T}_smoke.log
+timeout 600 python -m pytest tests -m gpu -x -q -rs --durations=8 > gpurun_out/${T}_tests.log 2>&1; echo "tests rc=$?"
 tail -14 gpurun_out/${T}_tests.log
 timeout 200 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; rc=$?; echo "bench rc=$rc"
 cut -c1-300 gpurun_out/${T}_bench.json
