@@ -49,7 +49,13 @@ void parallel_pread(int fd, void* dst, size_t n, off_t pos, const char* what) {
     if (!ok[t]) fail(AWRY_ERR_IO, "read error in %s", what);
 }
 
-void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_t flags, ReadsOut& out) {
+// `ri`: the replica that does the work.  [range_lo, range_hi): a byte range of a PLAIN file that begins at a
+// record start and ends at one (or at the end of the file), with the format already known (`fastq_known`) --
+// how run_reads_file_multi hands every replica its own segment; the default is the whole file.
+// `bad_read`: receives the segment-relative number of the read an AWRY_ERR_INVALID_QUERY is about.
+void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_t flags, ReadsOut& out, size_t ri = 0,
+                    uint64_t range_lo = 0, uint64_t range_hi = ~0ull, int fastq_known = -1, uint64_t* bad_read = nullptr) {
+  const bool ranged = range_hi != ~0ull;
   int fd = open(path, O_RDONLY);
   if (fd < 0) fail(AWRY_ERR_IO, "cannot open %s: %s", path, strerror(errno));
   struct FdCloser {
@@ -58,8 +64,8 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
   } fdc{fd};
   struct stat sb;
   if (fstat(fd, &sb) != 0) fail(AWRY_ERR_IO, "cannot stat %s", path);
-  const uint64_t fsize = uint64_t(sb.st_size);
-  out.file_bytes = fsize;
+  const uint64_t fsize = ranged ? std::min<uint64_t>(range_hi, uint64_t(sb.st_size)) : uint64_t(sb.st_size);
+  out.file_bytes = ranged ? fsize - std::min(fsize, range_lo) : fsize;
   // format: first non-blank byte (of the inflated stream when the file is gzip-compressed)
   int fastq = -1;
   uint64_t data_start = 0;
@@ -70,7 +76,14 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
       if (g) gzclose(g);
     }
   } gzc{gz};
-  {
+  if (ranged) {
+    fastq = fastq_known;
+    data_start = range_lo;
+    if (data_start >= fsize) {
+      if (locate) out.hit_off.assign(1, 0);
+      return;
+    }
+  } else {
     unsigned char head[4096];
     ssize_t got = pread(fd, head, sizeof head, 0);
     bool at_end = fsize <= uint64_t(std::max<ssize_t>(got, 0));
@@ -112,7 +125,7 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
   if (const char* e = getenv("AWRY_B200_READS_CARRY")) CARRY = std::min<uint64_t>(std::max<uint64_t>(64, strtoull(e, nullptr, 10)), 1ull << 30);
   constexpr int NBUF = 3;
 
-  Replica& r = *ix->reps[0];
+  Replica& r = *ix->reps[ri];
   DeviceGuard dg(r.device);
   Workspace* ws = r.acquire();
   cudaStream_t st = ws->st;
@@ -375,6 +388,7 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
           for (uint64_t i = 0; i <= nq; i++) dst_off[i] += out.n_hits;
           out.n_hits += n_hits;
         }
+        if (*ws->h_flag != ~0ull && bad_read) *bad_read = out.n_reads + (*ws->h_flag >> 1);
         if (*ws->h_flag != ~0ull)
           fail(AWRY_ERR_INVALID_QUERY,
                "read %llu of %s is empty or contains a sentinel ('$'/'#'): the reference panics on it "
@@ -396,6 +410,161 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
   cleanup();
 }
 
+// ---- one reads file over SEVERAL replicas (plain files) ----
+// The file is cut into one segment per replica at record starts found on the host (a window behind every
+// cut is scanned: FASTA -- a line that begins with '>'; FASTQ -- a line that begins with '@' whose next line
+// but one begins with '+', which a quality line that happens to begin with '@' never satisfies), every replica
+// runs the single-replica pipeline above on its segment with its own reader thread, and the results are
+// concatenated in file order.  A gzip stream cannot be entered in the middle and stays on replica 0; so does a
+// file too small to be worth splitting, and one whose record starts are not found (multi-line FASTQ).
+bool find_record_start(int fd, uint64_t from, uint64_t fsize, bool fastq, uint64_t& at) {
+  const uint64_t W = 4u << 20;
+  std::vector<char> buf(size_t(std::min<uint64_t>(W, fsize - from)));
+  if (buf.empty()) return false;
+  ssize_t got = pread(fd, buf.data(), buf.size(), off_t(from));
+  if (got <= 0) return false;
+  const size_t n = size_t(got);
+  auto line_end = [&](size_t p) {  // index of the '\n' ending the line that contains p, or n
+    const void* q = memchr(buf.data() + p, '\n', n - p);
+    return q ? size_t(static_cast<const char*>(q) - buf.data()) : n;
+  };
+  size_t p = line_end(0);  // never accept position 0: we do not know what precedes it
+  while (p < n) {
+    const size_t ls = p + 1;  // a line start
+    if (ls >= n) return false;
+    if (!fastq) {
+      if (buf[ls] == '>') {
+        at = from + ls;
+        return true;
+      }
+    } else if (buf[ls] == '@') {
+      const size_t e1 = line_end(ls);
+      const size_t e2 = e1 < n ? line_end(e1 + 1) : n;
+      if (e2 + 1 < n && buf[e2 + 1] == '+') {
+        at = from + ls;
+        return true;
+      }
+      if (e2 + 1 >= n) return false;  // window exhausted before the candidate could be confirmed
+    }
+    p = line_end(ls);
+  }
+  return false;
+}
+
+void run_reads_file_multi(const awry_index* ix, const char* path, bool locate, uint32_t flags, ReadsOut& out) {
+  const size_t nr = ix->reps.size();
+  const char* off = getenv("AWRY_B200_READS_REPLICAS");  // =1: always replica 0 (A/B runs)
+  uint64_t min_seg = 128ull << 20;
+  if (const char* e = getenv("AWRY_B200_READS_MIN_SEGMENT")) min_seg = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
+  std::vector<uint64_t> cuts;
+  int fastq = -1;
+  if (nr > 1 && !(off && off[0] == '1')) {
+    int fd = open(path, O_RDONLY);
+    if (fd >= 0) {
+      struct stat sb;
+      unsigned char head[4096];
+      ssize_t got = pread(fd, head, sizeof head, 0);
+      if (fstat(fd, &sb) == 0 && got >= 2 && !(head[0] == 0x1f && head[1] == 0x8b) && uint64_t(sb.st_size) >= 2 * min_seg) {
+        const uint64_t fsize = uint64_t(sb.st_size);
+        uint64_t data_start = 0;
+        for (ssize_t i = 0; i < got; i++) {
+          unsigned char c = head[i];
+          if (c == '\n' || c == '\r' || c == ' ' || c == '\t') continue;
+          fastq = c == '@' ? 1 : c == '>' ? 0 : -1;
+          data_start = uint64_t(i);
+          break;
+        }
+        if (fastq >= 0) {
+          const size_t nseg = size_t(std::min<uint64_t>(nr, fsize / min_seg));
+          cuts.push_back(data_start);
+          bool ok = nseg > 1;
+          for (size_t i = 1; i < nseg && ok; i++) {
+            uint64_t at = 0;
+            ok = find_record_start(fd, data_start + (fsize - data_start) * i / nseg, fsize, fastq == 1, at) && at > cuts.back();
+            if (ok) cuts.push_back(at);
+          }
+          if (ok)
+            cuts.push_back(fsize);
+          else
+            cuts.clear();
+        }
+      }
+      close(fd);
+    }
+  }
+  if (cuts.size() < 3) {  // one segment: the whole file on replica 0 (also: gzip, tiny files, unknown formats)
+    run_reads_file(ix, path, locate, flags, out);
+    return;
+  }
+  const size_t nseg = cuts.size() - 1;
+  std::vector<ReadsOut> outs(nseg);
+  std::vector<int> codes(nseg, 0);
+  std::vector<std::string> msgs(nseg);
+  std::vector<uint64_t> bad(nseg, ~0ull);
+  std::vector<std::thread> th;
+  for (size_t i = 0; i < nseg; i++)
+    th.emplace_back([&, i] {
+      try {
+        run_reads_file(ix, path, locate, flags, outs[i], i, cuts[i], cuts[i + 1], fastq, &bad[i]);
+      } catch (const ApiError& e) {
+        codes[i] = e.code;
+        msgs[i] = e.what();
+      } catch (const std::exception& e) {
+        codes[i] = AWRY_ERR_INVALID_ARG;
+        msgs[i] = e.what();
+      }
+    });
+  for (auto& t : th) t.join();
+  uint64_t reads_before = 0;
+  for (size_t i = 0; i < nseg; i++) {
+    if (codes[i]) {
+      for (auto& o : outs) free(o.hits);
+      if (codes[i] == AWRY_ERR_INVALID_QUERY && bad[i] != ~0ull)  // file-wide read number (the segments before it are complete)
+        fail(AWRY_ERR_INVALID_QUERY,
+             "read %llu of %s is empty or contains a sentinel ('$'/'#'): the reference panics on it (fm_index.rs:406, bwt.rs:127)",
+             (unsigned long long)(reads_before + bad[i]), path);
+      fail(codes[i], "%s", msgs[i].c_str());
+    }
+    reads_before += outs[i].n_reads;
+  }
+  // concatenate in file order
+  uint64_t n_reads = 0, n_hits = 0;
+  for (auto& o : outs) {
+    n_reads += o.n_reads;
+    n_hits += o.n_hits;
+    out.n_bases += o.n_bases;
+    out.file_bytes += o.file_bytes;
+  }
+  if (!locate) {
+    out.counts.resize(n_reads);
+    uint64_t at = 0;
+    for (auto& o : outs) {
+      if (o.n_reads) memcpy(out.counts.data() + at, o.counts.data(), o.n_reads * 8);
+      at += o.n_reads;
+    }
+  } else {
+    out.hit_off.assign(n_reads + 1, 0);
+    out.hits = n_hits ? static_cast<awry_hit*>(malloc(n_hits * sizeof(awry_hit))) : nullptr;
+    if (n_hits && !out.hits) {
+      for (auto& o : outs) free(o.hits);
+      fail(AWRY_ERR_NOMEM, "out of host memory for %llu hits", (unsigned long long)n_hits);
+    }
+    uint64_t at = 0, hbase = 0;
+    for (auto& o : outs) {
+      for (uint64_t i = 0; i < o.n_reads; i++) out.hit_off[at + i] = hbase + o.hit_off[i];
+      if (o.n_hits) memcpy(out.hits + hbase, o.hits, o.n_hits * sizeof(awry_hit));
+      free(o.hits);
+      o.hits = nullptr;
+      at += o.n_reads;
+      hbase += o.n_hits;
+    }
+    out.hit_off[n_reads] = n_hits;
+    out.hits_cap = n_hits;
+  }
+  out.n_reads = n_reads;
+  out.n_hits = n_hits;
+}
+
 }  // namespace
 
 extern "C" {
@@ -407,7 +576,7 @@ int awry_count_reads_file(const awry_index* ix, const char* path, uint64_t** cou
     *counts = nullptr;
     *n_reads = 0;
     ReadsOut out;
-    run_reads_file(ix, path, false, 0, out);
+    run_reads_file_multi(ix, path, false, 0, out);
     uint64_t* buf = static_cast<uint64_t*>(malloc(std::max<size_t>(8, out.n_reads * 8)));
     if (!buf) fail(AWRY_ERR_NOMEM, "out of host memory for %llu counts", (unsigned long long)out.n_reads);
     if (out.n_reads) memcpy(buf, out.counts.data(), out.n_reads * 8);
@@ -425,7 +594,7 @@ int awry_locate_reads_file(const awry_index* ix, const char* path, uint32_t flag
     *hits = nullptr;
     *n_reads = *n_hits = 0;
     ReadsOut out;
-    run_reads_file(ix, path, true, flags, out);
+    run_reads_file_multi(ix, path, true, flags, out);
     uint64_t* off = static_cast<uint64_t*>(malloc((out.n_reads + 1) * 8));
     if (!off) {
       free(out.hits);

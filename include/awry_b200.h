@@ -228,7 +228,9 @@ int awry_locate_batch_packed2(const awry_index *index, const uint8_t *crumbs, co
  * FASTA ('>', sequences may span lines) file itself, plain or gzip-compressed: raw chunks are uploaded
  * from pinned memory while a reader thread fetches (or inflates) the next ones, and the records are split
  * on the device.  Read i of the file is query i.  Results are library-owned; release each pointer with awry_buffer_free
- * (hits: awry_hits_free). */
+ * (hits: awry_hits_free).  On a handle with several replicas a plain file is cut into one segment per replica at
+ * record starts found on the host and every replica parses and searches its own segment (a gzip stream cannot be
+ * entered in the middle and stays on replica 0). */
 int awry_count_reads_file(const awry_index *index, const char *path, uint64_t **counts,
                           uint64_t *n_reads);
 int awry_locate_reads_file(const awry_index *index, const char *path, uint32_t flags,

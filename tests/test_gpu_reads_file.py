@@ -165,3 +165,42 @@ def test_gzip_compressed_reads(fx, po, dna, dev, tmp_path, monkeypatch, chunk):
     with gzip.open(empty, "wb") as fo:
         fo.write(b"")
     assert len(dev.count_reads_file(empty)) == 0
+
+
+@pytest.mark.parametrize("kind", ["fastq", "fasta"])
+def test_reads_file_over_several_replicas(tmp_path, fx, po, dna, monkeypatch, kind):
+    """a plain reads file on a handle with several replicas: the file is cut at record starts found on the host
+    (quality lines that begin with '@' must not fool it), every replica parses and searches its own segment,
+    the results come back in file order and equal the single-replica run and the oracle"""
+    import torch
+    from awry_b200 import AwryError, fm_index as f
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    reads = _reads(fx, dna, 30_000, seed=5)
+    path = str(tmp_path / ("r." + kind))
+    if kind == "fastq":
+        _write_fastq(path, reads)
+    else:
+        _write_fasta(path, reads)
+    orc = oracle_from_parts(po, dna)
+    qb, qo = f.pack_queries(reads)
+    want, _ = orc.count_batch(qb, qo)
+    woff, whits, _ = orc.locate_batch(qb, qo)
+    monkeypatch.setenv("AWRY_B200_READS_MIN_SEGMENT", "200000")       # (default 128 MiB: this file is a few MB)
+    with device_from_parts(dna, devices=list(range(min(n_dev, 8)))) as ix:
+        got = ix.count_reads_file(path)
+        assert np.array_equal(got, want)
+        off, hits = ix.locate_reads_file(path)
+        assert np.array_equal(off, woff) and np.array_equal(hits, whits)
+        monkeypatch.setenv("AWRY_B200_READS_REPLICAS", "1")            # the same handle, replica 0 only
+        assert np.array_equal(ix.count_reads_file(path), want)
+        monkeypatch.delenv("AWRY_B200_READS_REPLICAS")
+        # a sentinel in a late read is reported with its file-wide read number
+        bad = list(reads)
+        bad[27_123] = bad[27_123][:5] + b"$" + bad[27_123][6:] if len(bad[27_123]) > 6 else b"AC$GT"
+        bpath = str(tmp_path / ("bad." + kind))
+        (_write_fastq if kind == "fastq" else _write_fasta)(bpath, bad)
+        with pytest.raises(AwryError) as e:
+            ix.count_reads_file(bpath)
+        assert e.value.code == -5 and "read 27123 " in str(e.value)
