@@ -22,10 +22,14 @@ def main():
     ap.add_argument("--qlen", type=int, default=150)
     ap.add_argument("--dir", default="/dev/shm")
     ap.add_argument("--chunks", default="64,256")
+    ap.add_argument("--devices", type=int, default=1, help="replicas behind the handle (the file is cut into as many segments)")
+    ap.add_argument("--copies", type=int, default=1, help="write the reads this many times into the file")
     a = ap.parse_args()
     parts, _ = fxg.build_parts(0, a.n, 3, ratio=8, kmer_len=13)
+    os.environ.setdefault("AWRY_B200_FULL_SA", "0")
+    os.environ.setdefault("AWRY_B200_LEAN_SA", "0")
     ix = FmIndex.from_parts(parts.alphabet, parts.ratio, parts.bwt_len, parts.kmer_len, parts.blocks,
-                            parts.prefix_sums, parts.sa_words)
+                            parts.prefix_sums, parts.sa_words, devices=list(range(a.devices)))
     d_q = torch.empty(a.nq * a.qlen, dtype=torch.uint8, device="cuda")
     fxg.gen_queries_device(0, a.n, 3, a.nq, a.qlen, 4, d_q.data_ptr())
     d_off = torch.arange(0, a.nq + 1, dtype=torch.int64, device="cuda") * a.qlen
@@ -43,9 +47,13 @@ def main():
     rec[:, 6 + a.qlen:6 + 2 * a.qlen] = ord("I")
     rec[:, -1] = ord("\n")
     path = os.path.join(a.dir, "awry_probe_reads.fq")
-    rec.tofile(path)
+    with open(path, "wb") as fh:
+        for _ in range(a.copies):
+            rec.tofile(fh)
     size = os.path.getsize(path)
     del rec
+    want = np.tile(want, a.copies)
+    a.nq *= a.copies
     print(f"wrote {path}: {size/1e9:.2f} GB, {a.nq} reads in {time.time()-t0:.1f}s", flush=True)
     try:
         for chunk_mb in [int(x) for x in a.chunks.split(",")]:
@@ -57,6 +65,13 @@ def main():
             ok = np.array_equal(got, want)
             print(f"count_reads_file chunk {chunk_mb} MiB: {dt*1e3:.0f} ms = {a.nq/dt/1e6:.1f} M reads/s, "
                   f"{size/dt/1e9:.2f} GB/s of FASTQ; parity vs device-resident counts {'OK' if ok else 'MISMATCH'}", flush=True)
+        if a.devices > 1:
+            os.environ["AWRY_B200_READS_REPLICAS"] = "1"
+            t1 = time.perf_counter()
+            got = ix.count_reads_file(path)
+            dt = time.perf_counter() - t1
+            print(f"same handle, replica 0 only: {dt*1e3:.0f} ms = {a.nq/dt/1e6:.1f} M reads/s; parity {'OK' if np.array_equal(got, want) else 'MISMATCH'}", flush=True)
+            del os.environ["AWRY_B200_READS_REPLICAS"]
         t1 = time.perf_counter()
         off, hits = ix.locate_reads_file(path)
         dt = time.perf_counter() - t1
