@@ -698,7 +698,7 @@ void locate_on_replica(const awry_index* ix, size_t ri, const QuerySource& qs, u
 // cfg3 end to end: 2.2 ms -> see profiles/ (the two-sync pipeline above stays for library-owned results,
 // sorted output and the LF-walk variants, which size their buffers from the total).
 uint64_t locate_direct_on_replica(const awry_index* ix, size_t ri, const QuerySource& qs, uint64_t nq, uint64_t* hit_off,
-                                  awry_hit* hits, void* hits_dev, uint64_t capacity) {
+                                  void* hits_dev, uint64_t capacity) {
   Replica& r = *ix->reps[ri];
   PackBalance& bal = ix->balance_of(ri);
   DeviceGuard dg(r.device);
@@ -722,7 +722,6 @@ uint64_t locate_direct_on_replica(const awry_index* ix, size_t ri, const QuerySo
   constexpr int DEPTH = 3;
   Workspace* ws[DEPTH] = {nullptr, nullptr, nullptr};
   int pending[DEPTH] = {-1, -1, -1};
-  (void)hits;
   auto finish = [&](int s) {
     if (pending[s] < 0) return;
     const Chunk& c = chunks[size_t(pending[s])];
@@ -996,7 +995,7 @@ void locate_into_impl(const awry_index* ix, const QuerySource& qs, uint64_t nq, 
     Replica& r0 = *ix->reps[0];
     void* hits_dev = capacity ? device_view_of_pinned(hits) : nullptr;
     if (hits_dev && !(flags & AWRY_LOCATE_SORTED) && r0.view.full_sa && g_locate_variant == 0 && direct_locate_enabled()) {
-      *n_hits = locate_direct_on_replica(ix, 0, qs, nq, hit_off, hits, hits_dev, capacity);
+      *n_hits = locate_direct_on_replica(ix, 0, qs, nq, hit_off, hits_dev, capacity);
       if (*n_hits > capacity) too_small(*n_hits);
       return;
     }

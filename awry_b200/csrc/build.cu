@@ -21,10 +21,10 @@
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_reduce.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
+#include <thrust/iterator/transform_iterator.h>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <cuda_runtime.h>
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -284,7 +284,7 @@ int prefix_doubling(const uint64_t* keys_sorted, uint32_t* sa, uint64_t n1, uint
     // from here on the key buffers are scratch
     for (uint64_t h = h0;; h *= 2) {
       pd_flag_unresolved_kernel<<<G, 256>>>(head, n1, unres);
-      cub::CountingInputIterator<uint32_t> it(0);
+      thrust::counting_iterator<uint32_t> it(0);
       CU(cub::DeviceSelect::Flagged(nullptr, tb, it, unres, U, d_num, (long long)n1));
       need_temp(tb);
       CU(cub::DeviceSelect::Flagged(d_temp, tb, it, unres, U, d_num, (long long)n1));
@@ -408,7 +408,7 @@ int build_parts_impl(int alphabet, const uint8_t* text, bool text_on_device, uin
     unsigned long long* d_num = nullptr;
     CU(cudaMalloc(&d_num, 8));
     {
-      cub::CountingInputIterator<uint32_t> it(0);
+      thrust::counting_iterator<uint32_t> it(0);
       size_t tb = 0;
       CU(cub::DeviceSelect::Flagged(nullptr, tb, it, d_tied, d_rows, d_num, (long long)n1));
       CU(cudaMalloc(&d_temp, tb));
@@ -595,6 +595,11 @@ struct FirstSymbolIs {
   uint8_t want;
   __host__ __device__ bool operator()(uint64_t i) const { return sym[i] == want; }
 };
+struct FirstSymbolCount {  // the same as a 0/1 summand
+  const uint8_t* sym;
+  uint8_t want;
+  __host__ __device__ unsigned long long operator()(uint64_t i) const { return sym[i] == want ? 1ull : 0ull; }
+};
 
 template <int BITS>
 __global__ void make_keys_at_kernel(const uint8_t* __restrict__ sym, uint64_t n1, const uint64_t* __restrict__ pos,
@@ -660,8 +665,8 @@ int build_parts_wide_impl(int alphabet, const uint8_t* text, bool text_on_device
     {
       // sizes first (one counting pass per symbol is cheap next to the sorts)
       for (int s = 0; s < card; s++) {
-        cub::CountingInputIterator<uint64_t> it(0);
-        cub::TransformInputIterator<int, FirstSymbolIs, cub::CountingInputIterator<uint64_t>> flag(it, FirstSymbolIs{d_sym, uint8_t(s)});
+        thrust::counting_iterator<uint64_t> it(0);
+        auto flag = thrust::make_transform_iterator(it, FirstSymbolCount{d_sym, uint8_t(s)});
         size_t tb = 0;
         CU(cub::DeviceReduce::Sum(nullptr, tb, flag, d_num, (long long)n1));
         CU(cudaMalloc(&d_temp, tb + 16));
@@ -688,7 +693,7 @@ int build_parts_wide_impl(int alphabet, const uint8_t* text, bool text_on_device
       const uint64_t cnt = bucket[s];
       if (cnt == 0) continue;
       {  // positions whose first symbol is s, ascending
-        cub::CountingInputIterator<uint64_t> it(0);
+        thrust::counting_iterator<uint64_t> it(0);
         size_t tb = 0;
         CU(cub::DeviceSelect::If(nullptr, tb, it, d_pos[0], d_num, (long long)n1, FirstSymbolIs{d_sym, uint8_t(s)}));
         CU(cudaMalloc(&d_temp, tb + 16));
@@ -717,7 +722,7 @@ int build_parts_wide_impl(int alphabet, const uint8_t* text, bool text_on_device
       flag_ties_kernel<<<148 * 16, 256>>>(keys_sorted, cnt, d_tied);
       uint64_t* d_rows = vb.Alternate();
       {
-        cub::CountingInputIterator<uint64_t> it(0);
+        thrust::counting_iterator<uint64_t> it(0);
         size_t tb2 = 0;
         CU(cub::DeviceSelect::Flagged(nullptr, tb2, it, d_tied, d_rows, d_num, (long long)cnt));
         CU(cudaMalloc(&d_temp, tb2 + 16));

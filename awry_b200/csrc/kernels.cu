@@ -14,8 +14,8 @@
 #include <cstdio>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_segmented_sort.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include "kernels_common.cuh"
 

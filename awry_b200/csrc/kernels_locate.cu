@@ -6,8 +6,8 @@
 #include <algorithm>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_segmented_sort.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include "kernels_common.cuh"
 
@@ -25,9 +25,8 @@ struct CountOf {
 cudaError_t scan_hit_offsets(const IndexView& ix, const void* d_sp_cnt, uint64_t nq, uint64_t* d_hit_off, void* d_temp,
                              size_t& temp_bytes, cudaStream_t s) {
   if (ix.wide) return scan_hit_offsets_wide(d_sp_cnt, nq, d_hit_off, d_temp, temp_bytes, s);
-  cub::CountingInputIterator<uint64_t> idx(0);
-  cub::TransformInputIterator<uint64_t, CountOf, cub::CountingInputIterator<uint64_t>> in(
-      idx, CountOf{static_cast<const uint2*>(d_sp_cnt), nq});
+  thrust::counting_iterator<uint64_t> idx(0);
+  auto in = thrust::make_transform_iterator(idx, CountOf{static_cast<const uint2*>(d_sp_cnt), nq});
   cudaError_t e = cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, in, d_hit_off, nq + 1, s);
   if (d_temp != nullptr) COUNT_LAUNCH();
   return e;
@@ -505,7 +504,6 @@ __global__ void __launch_bounds__(256) walk_lean_kernel(IndexView ix, uint64_t n
   constexpr int SLOT = MAP ? 2 : 1;
   constexpr uint32_t FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31, sub = lane & 3, gbase = lane - sub;
-  const uint32_t gmask = 0xfu << gbase;
   unsigned long long* const ticket = reinterpret_cast<unsigned long long*>(out + SLOT * n_hits);
   uint64_t pn = 0, pe = 0;  // the warp's pool of hit numbers
   bool more = true;
@@ -586,7 +584,6 @@ __global__ void __launch_bounds__(256) walk_lean_kernel(IndexView ix, uint64_t n
       }
     }
   }
-  (void)gmask;
 }
 
 

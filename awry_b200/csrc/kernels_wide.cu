@@ -10,8 +10,8 @@
 // index is searched at the one-symbol-per-block rate, correct first.
 #include <algorithm>
 #include <cub/device/device_scan.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include "kernels_common.cuh"
 
@@ -264,9 +264,8 @@ struct WideCountOf {
 
 cudaError_t scan_hit_offsets_wide(const void* d_sp_cnt, uint64_t nq, uint64_t* d_hit_off, void* d_temp, size_t& temp_bytes,
                                   cudaStream_t s) {
-  cub::CountingInputIterator<uint64_t> idx(0);
-  cub::TransformInputIterator<uint64_t, WideCountOf, cub::CountingInputIterator<uint64_t>> in(
-      idx, WideCountOf{static_cast<const ulonglong2*>(d_sp_cnt), nq});
+  thrust::counting_iterator<uint64_t> idx(0);
+  auto in = thrust::make_transform_iterator(idx, WideCountOf{static_cast<const ulonglong2*>(d_sp_cnt), nq});
   cudaError_t e = cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, in, d_hit_off, nq + 1, s);
   if (d_temp != nullptr) COUNT_LAUNCH();
   return e;

@@ -17,7 +17,7 @@
 #include <cstdint>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <cuda_runtime.h>
 
 #include "reads.hpp"
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256)
 
 size_t reads_temp_bytes(uint32_t max_bytes) {
   size_t a = 0, b = 0, c = 0;
-  cub::CountingInputIterator<uint32_t> it(0);
+  thrust::counting_iterator<uint32_t> it(0);
   cub::DeviceSelect::If(nullptr, a, it, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), int(max_bytes),
                         IsNewline{nullptr});
   cub::DeviceScan::ExclusiveSum(nullptr, b, static_cast<uint32_t*>(nullptr), static_cast<uint64_t*>(nullptr), int(max_bytes));
@@ -144,7 +144,7 @@ size_t reads_temp_bytes(uint32_t max_bytes) {
 // Stage A: newline positions.  d_n_lines receives the count (device); the host reads it back to size stage B.
 cudaError_t reads_find_lines(const uint8_t* d_raw, uint32_t n_bytes, uint32_t* d_nl, uint32_t* d_n_lines, void* d_temp,
                              size_t temp_bytes, cudaStream_t s) {
-  cub::CountingInputIterator<uint32_t> it(0);
+  thrust::counting_iterator<uint32_t> it(0);
   return cub::DeviceSelect::If(d_temp, temp_bytes, it, d_nl, d_n_lines, int(n_bytes), IsNewline{d_raw}, s);
 }
 

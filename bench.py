@@ -597,7 +597,10 @@ def main():
     gloo = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        gloo = dist.new_group(backend="gloo")   # host-side waits that do not spin on a core (see the in-process leg)
+        try:   # host-side waits that do not spin on a core (see the in-process leg)
+            gloo = dist.new_group(backend="gloo")
+        except Exception:  # noqa: BLE001 -- no usable interface for gloo: wait on NCCL instead (spins, still correct)
+            gloo = None
     from awry_b200 import FmIndex, fm_index as f
     from fixtures import pyfixture_gpu as fxg
 
@@ -914,13 +917,13 @@ def main():
         del d_q, d_cnt
         torch.cuda.empty_cache()
         torch.cuda.synchronize()
-        dist.barrier(group=gloo)
+        dist.barrier(group=gloo) if gloo is not None else dist.barrier()
         if rank == 0:
             try:
                 inproc = inprocess_leg(a, torch, f, fxg, parts, world, rank_sums, rank_hits if not a.no_locate else None)
             except Exception as e:  # noqa: BLE001
                 inproc = {"error": repr(e)}
-        dist.barrier(group=gloo)      # the other ranks sleep on a socket meanwhile
+        dist.barrier(group=gloo) if gloo is not None else dist.barrier()   # the other ranks sleep on a socket meanwhile
 
     if rank == 0:
         e2e_line = e2e
