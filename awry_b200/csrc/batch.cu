@@ -95,18 +95,22 @@ struct Chunk {
   uint64_t q0, q1, b0, b1;
 };
 
-std::vector<Chunk> make_chunks(const uint64_t* qoff, uint64_t q_lo, uint64_t q_hi, uint64_t max_q,
-                               uint64_t max_bytes) {
+// `ramp_from` > 0: the first chunk holds about that many bytes and every following one up to 1.4 x its
+// predecessor, until max_bytes is reached (see ramped_chunks).
+std::vector<Chunk> make_chunks(const uint64_t* qoff, uint64_t q_lo, uint64_t q_hi, uint64_t max_q, uint64_t max_bytes,
+                               uint64_t ramp_from = 0) {
   std::vector<Chunk> out;
   uint64_t q = q_lo;
+  double cap = ramp_from ? double(std::min(ramp_from, max_bytes)) : double(max_bytes);
   while (q < q_hi) {
+    const uint64_t cap_bytes = uint64_t(cap);
     uint64_t hi = std::min(q_hi, q + max_q);
-    // largest hi with qoff[hi] - qoff[q] <= max_bytes (at least one query)
-    if (qoff[hi] - qoff[q] > max_bytes) {
+    // largest hi with qoff[hi] - qoff[q] <= cap_bytes (at least one query)
+    if (qoff[hi] - qoff[q] > cap_bytes) {
       uint64_t lo2 = q + 1, hi2 = hi;
       while (lo2 < hi2) {
         uint64_t mid = (lo2 + hi2 + 1) / 2;
-        if (qoff[mid] - qoff[q] <= max_bytes)
+        if (qoff[mid] - qoff[q] <= cap_bytes)
           lo2 = mid;
         else
           hi2 = mid - 1;
@@ -115,37 +119,39 @@ std::vector<Chunk> make_chunks(const uint64_t* qoff, uint64_t q_lo, uint64_t q_h
     }
     out.push_back(Chunk{q, hi, qoff[q], qoff[hi]});
     q = hi;
+    cap = std::min(double(max_bytes), cap * 1.4);
   }
   return out;
 }
 
-// Pipeline fill and drain: the device idles while the host prepares the first chunk, and the host idles
-// while the device works on the last one.  Splitting the first chunk into 1/4 + 3/4 and the last into
-// 1/2 + 1/4 + 1/4 (by queries) shortens both ends without paying the per-chunk overhead everywhere.
-std::vector<Chunk> taper_chunks(std::vector<Chunk> in, const uint64_t* qoff) {
+// Pipeline fill and drain.  Fill: the device idles while the host prepares the first chunk, and a chunk can only be
+// searched once it has been packed and copied -- so the chunks RAMP UP: 16 MB first, each following one at most
+// 1.4 x its predecessor (the search of chunk i, at ~82 GB/s of query bytes, then lasts as long as packing chunk
+// i + 1 at ~121 GB/s), full size after seven.  A first chunk of 1/4 followed by 3/4 left the device idle for 0.9 ms
+// of a 20 ms call (profiles/r02_s6_count_e2e_trace.log).  Drain: the host idles while the device works on the last
+// chunk; splitting it into 1/2 + 1/4 + 1/4 (by queries) shortens that end.
+std::vector<Chunk> ramped_chunks(const uint64_t* qoff, uint64_t q_lo, uint64_t q_hi, uint64_t max_q, uint64_t max_bytes) {
+  const uint64_t total = qoff[q_hi] >= qoff[q_lo] ? qoff[q_hi] - qoff[q_lo] : 0;
+  const uint64_t RAMP_FROM = 16u << 20;
+  std::vector<Chunk> in = make_chunks(qoff, q_lo, q_hi, max_q, max_bytes, total >= 3 * RAMP_FROM ? RAMP_FROM : 0);
   if (in.size() < 3) return in;
-  auto split = [&](const Chunk& c, std::initializer_list<double> cuts, std::vector<Chunk>& dst) {
-    uint64_t nq = c.q1 - c.q0, prev = c.q0;
-    for (double f : cuts) {
-      uint64_t at = c.q0 + uint64_t(double(nq) * f);
+  std::vector<Chunk> out(in.begin(), in.end() - 1);
+  const Chunk& c = in.back();
+  const uint64_t MIN_SPLIT = 64u << 20;  // only chunks worth splitting
+  if (c.b1 - c.b0 >= MIN_SPLIT) {
+    const uint64_t nq = c.q1 - c.q0;
+    uint64_t prev = c.q0;
+    for (double f : {0.5, 0.75}) {
+      const uint64_t at = c.q0 + uint64_t(double(nq) * f);
       if (at > prev && at < c.q1) {
-        dst.push_back(Chunk{prev, at, qoff[prev], qoff[at]});
+        out.push_back(Chunk{prev, at, qoff[prev], qoff[at]});
         prev = at;
       }
     }
-    dst.push_back(Chunk{prev, c.q1, qoff[prev], qoff[c.q1]});
-  };
-  std::vector<Chunk> out;
-  const uint64_t MIN_SPLIT = 64u << 20;  // only chunks worth splitting
-  if (in.front().b1 - in.front().b0 >= MIN_SPLIT)
-    split(in.front(), {0.25}, out);
-  else
-    out.push_back(in.front());
-  for (size_t i = 1; i + 1 < in.size(); i++) out.push_back(in[i]);
-  if (in.back().b1 - in.back().b0 >= MIN_SPLIT)
-    split(in.back(), {0.5, 0.75}, out);
-  else
-    out.push_back(in.back());
+    out.push_back(Chunk{prev, c.q1, qoff[prev], qoff[c.q1]});
+  } else {
+    out.push_back(c);
+  }
   return out;
 }
 
@@ -365,9 +371,10 @@ void search_on_replica(const awry_index* ix, size_t ri, const QuerySource& qs, u
   const bool dst_pinned = is_pinned(out);
   // pre-packed queries are a quarter of the bytes: four times the reads per chunk keep the chunk count down
   const uint64_t max_bytes = chunk_max_bytes() * (qs.crumbs ? 2 : 1);
-  auto chunks = make_chunks(qoff, q_lo, q_hi, CHUNK_MAX_Q, max_bytes);
+  if (qoff[q_hi] < qoff[q_lo]) fail(AWRY_ERR_INVALID_ARG, "query offsets are not monotone (queries %llu..%llu)",
+                                     (unsigned long long)q_lo, (unsigned long long)q_hi);
+  auto chunks = ramped_chunks(qoff, q_lo, q_hi, CHUNK_MAX_Q, max_bytes);
   validate_chunks(chunks, max_bytes);
-  chunks = taper_chunks(std::move(chunks), qoff);
   constexpr int DEPTH = 3;
   Workspace* ws[DEPTH] = {nullptr, nullptr, nullptr};
   int pending[DEPTH] = {-1, -1, -1};
@@ -392,6 +399,8 @@ void search_on_replica(const awry_index* ix, size_t ri, const QuerySource& qs, u
       parallel_memcpy(static_cast<char*>(out) + c.q0 * out_elem, ws[s]->h_out, (c.q1 - c.q0) * out_elem);
     pending[s] = -1;
   };
+  GpuTrace gpu_trace;  // AWRY_B200_TRACE=1: device-side timeline of the chunk pipeline on stderr
+  g_gpu_trace = trace_on() ? &gpu_trace : nullptr;
   uint64_t bytes_total = 0, bytes_packed = 0;  // of the chunks enqueued so far (pinned sources only)
   const bool balanced = src_pinned && !qs.crumbs && ix->alphabet == AWRY_NUCLEOTIDE && host_pack_enabled();
   PackBalance::Plan plan{1.0, false, false};
@@ -423,12 +432,16 @@ void search_on_replica(const awry_index* ix, size_t ri, const QuerySource& qs, u
         dst = ws[s]->h_out;
       }
       CU(cudaMemcpyAsync(dst, ws[s]->d_out, bytes, cudaMemcpyDeviceToHost, ws[s]->st));
+      gpu_mark(ws[s]->st, "results copied", (long long)c.q0);
       g_prof.d2h += bytes;
       CU(cudaEventRecord(ws[s]->done, ws[s]->st));
       pending[s] = int(i);
     }
     for (int s = 0; s < DEPTH; s++) finish(s);
+    g_gpu_trace = nullptr;
+    gpu_trace.dump();
   } catch (...) {
+    g_gpu_trace = nullptr;
     for (int s = 0; s < DEPTH; s++)
       if (ws[s]) {
         cudaStreamSynchronize(ws[s]->st);
