@@ -96,7 +96,7 @@ struct Chunk {
 };
 
 // `ramp_from` > 0: the first chunk holds about that many bytes and every following one up to 1.4 x its
-// predecessor, until max_bytes is reached (see ramped_chunks).
+// predecessor, until max_bytes is reached (see shaped_chunks).
 std::vector<Chunk> make_chunks(const uint64_t* qoff, uint64_t q_lo, uint64_t q_hi, uint64_t max_q, uint64_t max_bytes,
                                uint64_t ramp_from = 0) {
   std::vector<Chunk> out;
@@ -124,34 +124,41 @@ std::vector<Chunk> make_chunks(const uint64_t* qoff, uint64_t q_lo, uint64_t q_h
   return out;
 }
 
-// Pipeline fill and drain.  Fill: the device idles while the host prepares the first chunk, and a chunk can only be
-// searched once it has been packed and copied -- so the chunks RAMP UP: 16 MB first, each following one at most
-// 1.4 x its predecessor (the search of chunk i, at ~82 GB/s of query bytes, then lasts as long as packing chunk
-// i + 1 at ~121 GB/s), full size after seven.  A first chunk of 1/4 followed by 3/4 left the device idle for 0.9 ms
-// of a 20 ms call (profiles/r02_s6_count_e2e_trace.log).  Drain: the host idles while the device works on the last
-// chunk; splitting it into 1/2 + 1/4 + 1/4 (by queries) shortens that end.
-std::vector<Chunk> ramped_chunks(const uint64_t* qoff, uint64_t q_lo, uint64_t q_hi, uint64_t max_q, uint64_t max_bytes) {
+// Pipeline fill and drain: the device idles while the host prepares the first chunk, and the host idles while the
+// device works on the last one.  ASCII input (the host packs every chunk before its copy): the first chunk is split
+// into 1/4 + 3/4 and the last into 1/2 + 1/4 + 1/4 (by queries).  A finer ramp -- 16 MB first, every chunk 1.4 x its
+// predecessor -- was measured and LOSES there (21.0-21.5 against 19.9 ms per 10 M reads,
+// profiles/r02_s6_count_e2e_trace.log): packing and copying chunk i + 1 one after the other takes longer than
+// searching chunk i, so the device waits a little at every step of the ramp instead of once, and chunks of 0.1-0.4 M
+// reads run the persistent search kernel at 2.0-2.4 ms per M reads instead of 1.8.  Pre-packed input has no host
+// pass; there the ramp wins (19.0-19.3 -> 18.5 ms) and is used (`ramp`).
+std::vector<Chunk> shaped_chunks(const uint64_t* qoff, uint64_t q_lo, uint64_t q_hi, uint64_t max_q, uint64_t max_bytes,
+                                 bool ramp) {
   const uint64_t total = qoff[q_hi] >= qoff[q_lo] ? qoff[q_hi] - qoff[q_lo] : 0;
-  const uint64_t RAMP_FROM = 16u << 20;
-  std::vector<Chunk> in = make_chunks(qoff, q_lo, q_hi, max_q, max_bytes, total >= 3 * RAMP_FROM ? RAMP_FROM : 0);
+  const uint64_t RAMP_FROM = 16u << 20, MIN_SPLIT = 64u << 20;  // (only chunks worth splitting are split)
+  std::vector<Chunk> in = make_chunks(qoff, q_lo, q_hi, max_q, max_bytes, ramp && total >= 3 * RAMP_FROM ? RAMP_FROM : 0);
   if (in.size() < 3) return in;
-  std::vector<Chunk> out(in.begin(), in.end() - 1);
-  const Chunk& c = in.back();
-  const uint64_t MIN_SPLIT = 64u << 20;  // only chunks worth splitting
-  if (c.b1 - c.b0 >= MIN_SPLIT) {
-    const uint64_t nq = c.q1 - c.q0;
-    uint64_t prev = c.q0;
-    for (double f : {0.5, 0.75}) {
-      const uint64_t at = c.q0 + uint64_t(double(nq) * f);
+  auto split = [&](const Chunk& c, std::initializer_list<double> cuts, std::vector<Chunk>& dst) {
+    uint64_t nq = c.q1 - c.q0, prev = c.q0;
+    for (double f : cuts) {
+      uint64_t at = c.q0 + uint64_t(double(nq) * f);
       if (at > prev && at < c.q1) {
-        out.push_back(Chunk{prev, at, qoff[prev], qoff[at]});
+        dst.push_back(Chunk{prev, at, qoff[prev], qoff[at]});
         prev = at;
       }
     }
-    out.push_back(Chunk{prev, c.q1, qoff[prev], qoff[c.q1]});
-  } else {
-    out.push_back(c);
-  }
+    dst.push_back(Chunk{prev, c.q1, qoff[prev], qoff[c.q1]});
+  };
+  std::vector<Chunk> out;
+  if (!ramp && in.front().b1 - in.front().b0 >= MIN_SPLIT)
+    split(in.front(), {0.25}, out);
+  else
+    out.push_back(in.front());
+  for (size_t i = 1; i + 1 < in.size(); i++) out.push_back(in[i]);
+  if (in.back().b1 - in.back().b0 >= MIN_SPLIT)
+    split(in.back(), {0.5, 0.75}, out);
+  else
+    out.push_back(in.back());
   return out;
 }
 
@@ -373,7 +380,7 @@ void search_on_replica(const awry_index* ix, size_t ri, const QuerySource& qs, u
   const uint64_t max_bytes = chunk_max_bytes() * (qs.crumbs ? 2 : 1);
   if (qoff[q_hi] < qoff[q_lo]) fail(AWRY_ERR_INVALID_ARG, "query offsets are not monotone (queries %llu..%llu)",
                                      (unsigned long long)q_lo, (unsigned long long)q_hi);
-  auto chunks = ramped_chunks(qoff, q_lo, q_hi, CHUNK_MAX_Q, max_bytes);
+  auto chunks = shaped_chunks(qoff, q_lo, q_hi, CHUNK_MAX_Q, max_bytes, qs.crumbs != nullptr);
   validate_chunks(chunks, max_bytes);
   constexpr int DEPTH = 3;
   Workspace* ws[DEPTH] = {nullptr, nullptr, nullptr};
