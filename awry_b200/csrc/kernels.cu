@@ -1782,7 +1782,7 @@ cudaError_t launch_search(const IndexView& ix, const uint64_t* d_qwords, const u
                           uint64_t nq, SearchOut mode, void* d_out, uint32_t* d_defer,
                           const SearchVariant& v, int sm_count, cudaStream_t s) {
   if (nq == 0) return cudaSuccess;
-  if (ix.wide) return launch_search_wide(*ix.wide, d_qwords, d_qoff, nq, mode, d_out, v.b_lo, v.b_hi, sm_count, s);
+  if (ix.wide) return launch_search_wide(*ix.wide, d_qwords, d_qoff, nq, mode, d_out, d_defer, v, sm_count, s);
   switch (mode) {
     case OUT_COUNT_U64: return launch_search_mode<OUT_COUNT_U64>(ix, d_qwords, d_qoff, nq, d_out, d_defer, v, sm_count, s);
     case OUT_RANGE_U64: return launch_search_mode<OUT_RANGE_U64>(ix, d_qwords, d_qoff, nq, d_out, d_defer, v, sm_count, s);

@@ -143,7 +143,8 @@ cudaError_t launch_single_backstep(const IndexView& ix, uint64_t row, uint64_t* 
 // ---- kernels_wide.cu: indexes with 64-bit row pointers (the launchers above dispatch on IndexView::wide)
 cudaError_t launch_build_table_wide(const WideView& ix, ulonglong2* d_table, uint32_t k, cudaStream_t s);
 cudaError_t launch_search_wide(const WideView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff, uint64_t nq,
-                               SearchOut mode, void* d_out, uint64_t b_lo, uint64_t b_hi, int sm_count, cudaStream_t s);
+                               SearchOut mode, void* d_out, uint32_t* d_scratch /* >= 1 u32: ticket counter */,
+                               const SearchVariant& v, int sm_count, cudaStream_t s);
 cudaError_t scan_hit_offsets_wide(const void* d_sp_cnt, uint64_t nq, uint64_t* d_hit_off, void* d_temp, size_t& temp_bytes,
                                   cudaStream_t s);
 cudaError_t launch_walk_wide(const WideView& ix, const void* d_sp_cnt, const uint64_t* d_hit_off, uint64_t nq, uint64_t n_hits,

@@ -6,8 +6,9 @@
 // rows and runs the cooperative kernels of kernels.cu / kernels_locate.cu unchanged; an index past that limit
 // keeps the SAME device blocks (their u32 counts become relative to 2^31-row superblocks, layout.cuh) and is
 // searched by the kernels below: one thread per query / per hit, the plain algorithm of fm_index.rs:402-438,
-// :516-544, :559-593 on 64-bit rows.  No pair index, no unsampled array (both are 32-bit structures): a wide
-// index is searched at the one-symbol-per-block rate, correct first.
+// :516-544, :559-593 on 64-bit rows -- plus, for nucleotide search, a cooperative kernel (4 lanes per query, one
+// line request per LF step).  No pair index, no unsampled array (both are 32-bit structures): a wide index is
+// searched at the one-symbol-per-block rate.
 #include <algorithm>
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/counting_iterator.h>
@@ -232,6 +233,130 @@ __global__ void __launch_bounds__(256) w_search_kernel(WideView ix, const uint64
   }
 }
 
+// Nucleotide, cooperative: 4 lanes per query on the 64-B block (one LDG.128 each = ONE line request per LF
+// step instead of the eight of the one-thread kernel above), both ranks of a step from one block load when they
+// share the block, the u32 partial ranks reduced with xor-shuffles and the superblock count added after the
+// reduction; queries handed out dynamically per lane group (tickets), groups refill in-loop, the warp leaves by
+// vote.  The shape of search_dna_kernel<4> / search_amino_kernel on 64-bit rows; ambiguity symbols take the
+// scalar step.  (No pair index for wide indexes yet: one symbol per block read.)
+template <int MODE>
+__global__ void __launch_bounds__(256, 6)
+    w_search_dna_coop_kernel(WideView ix, const uint64_t* __restrict__ qwords, const uint64_t* __restrict__ qoff,
+                             uint64_t nq, void* __restrict__ out, uint32_t* __restrict__ ticket, uint32_t ticket_sz,
+                             ByteRange br) {
+  constexpr uint32_t NONE = 0xffffffffu, FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31, sub = lane & 3, gbase = lane - sub;
+  const uint32_t gmask = 0xfu << gbase;
+  const uint32_t nq32 = uint32_t(nq);
+  uint32_t q = 0, q_end = 0;
+  bool more = true;
+  uint32_t cur = NONE, left = 0;
+  uint64_t sp = 1, ep = 0;
+  QueryStream<0> qs;
+  qs.w = qs.wnext = 0;
+  qs.widx = 0;
+  qs.inword = 0;
+  for (;;) {
+    if (left == 0 || sp > ep) {
+      if (cur != NONE && sub == 0) w_store_result<MODE>(out, cur, sp, ep);
+      cur = NONE;
+      left = 0;
+      if (q == q_end && more) {
+        uint32_t t = 0;
+        if (sub == 0) t = atomicAdd(ticket, ticket_sz);
+        t = __shfl_sync(gmask, t, gbase);
+        more = t < nq32;
+        q = more ? t : 0u;
+        q_end = more ? (nq32 - t < ticket_sz ? nq32 : t + ticket_sz) : 0u;
+      }
+      if (q < q_end) {
+        cur = q++;
+        const uint64_t o0 = qoff[cur];
+        const uint32_t len = checked_len(o0, qoff[cur + 1], br);
+        sp = 1;
+        ep = 0;
+        if (len != 0) {
+          qs.open(qwords, cur, o0);
+          const uint32_t k = ix.kmer_len;
+          const uint64_t w = qs.w;
+          if (k != 0 && len >= k && (w & (0xCCCCCCCCCCCCCCCCull >> (4 * (16 - k)))) == 0) {
+            uint64_t idx = 0;
+#pragma unroll 1
+            for (uint32_t j = 0; j < k; j++) idx |= ((w >> (4 * j)) & 3ull) << (2 * j);
+            AWRY_CHK(idx < ix.n_table);
+            const ulonglong2 r = ix.table[idx];
+            sp = r.x;
+            ep = r.y;
+#pragma unroll 1
+            for (uint32_t j = 0; j < k; j++) qs.next(qwords);
+            left = len - k;
+          } else {
+            const uint32_t c = qs.next(qwords);
+            if (c <= uint32_t(DNA_N)) {
+              sp = ix.c_lo[c];
+              ep = ix.c_hi[c];
+              left = len - 1;
+            }
+          }
+        }
+      }
+    }
+    if (__all_sync(FULL, cur == NONE && q == q_end && !more)) break;
+    const bool active = left != 0 && sp <= ep;
+    uint32_t c = 7;
+    if (active) {
+      c = qs.next(qwords);
+      left--;
+    }
+    uint32_t ra = 0, rb = 0;
+    const uint64_t pa = sp - 1, pb = ep;
+    const uint64_t ba = pa >> 7, bb = pb >> 7;
+    if (active && c < 4) {
+      AWRY_CHK(ba * DNA_BLOCK_UINT4 + 3 < ix.n_blocks_u4 && bb * DNA_BLOCK_UINT4 + 3 < ix.n_blocks_u4);
+      LaneChunks<4> x;
+      x.load(ix.blocks + size_t(ba) * DNA_BLOCK_UINT4, sub);
+      const uint32_t m0 = (c & 1) ? ~0u : 0u, m1 = (c & 2) ? ~0u : 0u;
+      ra = dna_partial_rank<4>(x, sub, uint32_t(pa) & 127, c, m0, m1);
+      if (bb != ba) x.load(ix.blocks + size_t(bb) * DNA_BLOCK_UINT4, sub);
+      rb = dna_partial_rank<4>(x, sub, uint32_t(pb) & 127, c, m0, m1);
+    }
+    ra += __shfl_xor_sync(FULL, ra, 1);
+    rb += __shfl_xor_sync(FULL, rb, 1);
+    ra += __shfl_xor_sync(FULL, ra, 2);
+    rb += __shfl_xor_sync(FULL, rb, 2);
+    if (active) {
+      if (c < 4) {  // block counts are relative to the block's superblock
+        const uint64_t sa = __ldg(ix.sb_counts + (ba >> (ix.sb_shift - 7)) * SB_STRIDE + c);
+        const uint64_t sb = __ldg(ix.sb_counts + (bb >> (ix.sb_shift - 7)) * SB_STRIDE + c);
+        sp = ix.c_lo[c] + sa + ra;
+        ep = ix.c_lo[c] + sb + rb - 1;
+      } else if (c == uint32_t(DNA_N)) {
+        w_lf_update<0>(ix, sp, ep, c);  // rare: every lane of the group runs the scalar step
+      } else {
+        sp = 1;  // sentinel in a query: refused by the prepass; stay defined
+        ep = 0;
+      }
+    }
+  }
+}
+
+template <int MODE>
+static cudaError_t launch_search_wide_coop(const WideView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff, uint64_t nq,
+                                           void* d_out, uint32_t* d_ticket, uint32_t avg_len, ByteRange br, int sm_count,
+                                           cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(d_ticket, 0, 4, s);
+  if (e != cudaSuccess) return e;
+  auto kern = w_search_dna_coop_kernel<MODE>;
+  int per_sm = 0;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0)) != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  const uint64_t need_blocks = (nq * 4 + 255) / 256;
+  const unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * per_sm, need_blocks)));
+  kern<<<grid, 256, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out, d_ticket, ticket_size(avg_len), br);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
 template <int ALPHA>
 static cudaError_t launch_search_wide_a(const WideView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff, uint64_t nq,
                                         SearchOut mode, void* d_out, ByteRange br, int sm_count, cudaStream_t s) {
@@ -246,10 +371,18 @@ static cudaError_t launch_search_wide_a(const WideView& ix, const uint64_t* d_qw
 }
 
 cudaError_t launch_search_wide(const WideView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff, uint64_t nq,
-                               SearchOut mode, void* d_out, uint64_t b_lo, uint64_t b_hi, int sm_count, cudaStream_t s) {
+                               SearchOut mode, void* d_out, uint32_t* d_scratch, const SearchVariant& v, int sm_count,
+                               cudaStream_t s) {
   if (nq == 0) return cudaSuccess;
-  if (nq >= (1ull << 32)) return cudaErrorInvalidValue;  // 32-bit packed-word indices (QueryStream)
-  const ByteRange br{b_lo, b_hi};
+  if (nq >= (1ull << 32) - (1u << 24)) return cudaErrorInvalidValue;  // 32-bit packed-word indices and ticket counter
+  const ByteRange br{v.b_lo, v.b_hi};
+  if (ix.alphabet == 0 && v.lanes != -1) {  // lanes == -1: the one-thread kernels (cross-check)
+    switch (mode) {
+      case OUT_COUNT_U64: return launch_search_wide_coop<OUT_COUNT_U64>(ix, d_qwords, d_qoff, nq, d_out, d_scratch, v.avg_len, br, sm_count, s);
+      case OUT_RANGE_U64: return launch_search_wide_coop<OUT_RANGE_U64>(ix, d_qwords, d_qoff, nq, d_out, d_scratch, v.avg_len, br, sm_count, s);
+      default: return launch_search_wide_coop<OUT_SP_CNT_U32>(ix, d_qwords, d_qoff, nq, d_out, d_scratch, v.avg_len, br, sm_count, s);
+    }
+  }
   return ix.alphabet == 0 ? launch_search_wide_a<0>(ix, d_qwords, d_qoff, nq, mode, d_out, br, sm_count, s)
                           : launch_search_wide_a<1>(ix, d_qwords, d_qoff, nq, mode, d_out, br, sm_count, s);
 }

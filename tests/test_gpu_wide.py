@@ -36,7 +36,12 @@ def test_wide_dna_matches_oracle(fx, po, wide_env, tmp_path):
         assert ix.device_bytes()["pair"] == 0 and ix.device_bytes()["full_sa"] == 0 and ix.device_bytes()["lean_sa"] == 0
         for b, o in ((qb, qo), (eb, eo)):
             want, _ = orc.count_batch(b, o)
-            assert np.array_equal(ix.count_packed(b, o), want)
+            assert np.array_equal(ix.count_packed(b, o), want)           # cooperative kernel (4 lanes per query)
+            f.set_search_variant(-1)                                     # one thread per query
+            try:
+                assert np.array_equal(ix.count_packed(b, o), want)
+            finally:
+                f.set_search_variant(0)
             off, hits = ix.locate_packed(b, o)
             woff, whits, _ = orc.locate_batch(b, o)
             assert np.array_equal(off, woff) and np.array_equal(hits, whits)
