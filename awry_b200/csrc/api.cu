@@ -19,6 +19,7 @@ ProfState g_prof;
 std::atomic<uint64_t> g_variant_bits{uint64_t(1)};  // lanes 0, tpb 0, blocks_per_sm 0, slots -1 (see host.hpp)
 std::atomic<int> g_host_pack{-1};
 std::atomic<int> g_locate_variant{0};
+std::atomic<int> g_count_variant{0};
 
 [[noreturn]] void fail(int code, const char* fmt, ...) {
   char buf[900];
@@ -81,6 +82,7 @@ void set_limits(awry_index* ix, Replica& r) {
   v.n_table = ix->wide ? 0 : (r.d_table ? table_entries(ix->alphabet, ix->kmer_len_dev) : 0);
   v.n_sa_words = ix->n_sa_words + 2;
   v.n_full_sa = r.d_full_sa ? ix->bwt_len : 0;
+  v.n_rtext = r.d_rtext ? rtext_bytes(ix->bwt_len) : 0;
   v.n_walk_u4 = r.d_walk ? walk_block_count(ix->bwt_len) * WALK_BLOCK_UINT4 : 0;
   v.n_walk_rank = r.d_walk ? walk_block_count(ix->bwt_len) + 1 : 0;
   v.n_pos_samples = r.d_walk && ix->lean_ratio ? (ix->bwt_len + ix->lean_ratio - 1) / ix->lean_ratio : 0;
@@ -99,6 +101,7 @@ void set_view_constants(awry_index* ix, Replica& r) {
   v.seq_starts = r.d_seq_starts;
   v.pair_blocks = r.d_pair;
   v.full_sa = r.d_full_sa;
+  v.rtext = r.d_rtext;
   v.walk_blocks = r.d_walk;
   v.walk_rank = r.d_walk_rank;
   v.pos_samples = r.d_pos_samples;
@@ -373,6 +376,22 @@ void finish_replica0(awry_index* ix, Replica& r) {
       set_limits(ix, r);
     }
   }
+  // Nucleotide: the text itself, reversed, 4 bits per symbol (layout.cuh), read back out of BWT + unsampled array.
+  // With it the count kernel finishes a query whose interval has narrowed to one row with one suffix-array read
+  // and one or two lines of text instead of a block read per two symbols.  n / 2 bytes; AWRY_B200_TEXT=0 never.
+  const char* tx = getenv("AWRY_B200_TEXT");
+  if (ix->alphabet == AWRY_NUCLEOTIDE && r.d_full_sa && r.d_pair && !(tx && tx[0] == '0') && !g_skip_accelerators) {
+    const size_t bytes = rtext_bytes(ix->bwt_len);
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    if (bytes < free_b / 3) {
+      CU(cudaMalloc(reinterpret_cast<void**>(&r.d_rtext), bytes));
+      CU(build_rtext(r.view, r.d_rtext, nullptr));
+      CU(cudaDeviceSynchronize());
+      r.bytes_rtext = bytes;
+      r.view.rtext = r.d_rtext;
+      set_limits(ix, r);
+    }
+  }
   // Memory-lean bounded locate (nucleotide): walk blocks + position-sampled suffix array, 4.57 + 32/ratio bits
   // per row.  Built when the unsampled array is not (it did not fit, or AWRY_B200_FULL_SA=0), or on request
   // (AWRY_B200_LEAN_SA=1: both, for A/B runs; =0: never -- locate then LF-walks to the file's row samples).
@@ -450,6 +469,11 @@ void clone_replica(awry_index* ix, const Replica& src, Replica& dst) {
     dst.bytes_full_sa = src.bytes_full_sa;
     CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_full_sa), src.bytes_full_sa + 256));
     CU(cudaMemcpyPeer(dst.d_full_sa, dst.device, src.d_full_sa, src.device, src.bytes_full_sa));
+  }
+  if (src.bytes_rtext) {
+    dst.bytes_rtext = src.bytes_rtext;
+    CU(cudaMalloc(reinterpret_cast<void**>(&dst.d_rtext), src.bytes_rtext));
+    CU(cudaMemcpyPeer(dst.d_rtext, dst.device, src.d_rtext, src.device, src.bytes_rtext));
   }
   if (src.bytes_lean) {
     const uint64_t nb = walk_block_count(ix->bwt_len);
@@ -674,6 +698,7 @@ void awry_index_free(awry_index* ix) {
     cudaFree(r.d_sb);
     cudaFree(r.d_pair);
     cudaFree(r.d_full_sa);
+    cudaFree(r.d_rtext);
     cudaFree(r.d_walk);
     cudaFree(r.d_walk_rank);
     cudaFree(r.d_pos_samples);
@@ -706,6 +731,7 @@ int awry_index_info(const awry_index* ix, awry_info* info) {
     for (size_t i = 0; i < ix->reps.size() && i < 16; i++) info->devices[i] = ix->reps[i]->device;
     info->row_pointer_bits = ix->wide ? 64 : 32;
     info->lean_sa_ratio = ix->reps[0]->bytes_lean ? ix->lean_ratio : 0;
+    info->device_bytes_text = ix->reps[0]->bytes_rtext;
   });
 }
 

@@ -1299,6 +1299,14 @@ int awry_set_host_threads(int n) {
 
 int awry_host_threads(void) { return host_pool_threads(); }
 
+int awry_set_count_variant(int variant) {
+  return guarded([&] {
+    if (variant < 0 || variant > 1)
+      fail(AWRY_ERR_INVALID_ARG, "count variant must be 0 (default: finish one-row intervals in the text) or 1 (backward search only)");
+    g_count_variant = variant;
+  });
+}
+
 int awry_set_locate_variant(int variant) {
   return guarded([&] {
     if (variant < 0 || variant > 2)

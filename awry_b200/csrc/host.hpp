@@ -128,6 +128,7 @@ struct ProfScope {
 // that a thread flipping one while others search is a benign race: a call reads each knob once.
 extern std::atomic<uint64_t> g_variant_bits;  // lanes (16 bits, biased by 1) | tpb (16) | blocks_per_sm (16) | slots (8, biased by 1)
 extern std::atomic<int> g_host_pack;      // -1 = auto (AWRY_B200_HOST_PACK, CPU support, >= 4 pool threads), 0 = off, 1 = on
+extern std::atomic<int> g_count_variant;   // 0 = finish one-row intervals in the text when it is on the device, 1 = backward search only
 extern std::atomic<int> g_locate_variant;  // 0 = best pass 2 present, 1 = LF-walk to row samples, 2 = bounded walk
 inline SearchVariant current_variant() {
   const uint64_t b = g_variant_bits.load(std::memory_order_relaxed);
@@ -136,6 +137,7 @@ inline SearchVariant current_variant() {
   v.tpb = int((b >> 16) & 0xffff);
   v.blocks_per_sm = int((b >> 32) & 0xffff);
   v.slots = int((b >> 48) & 0xff) - 1;
+  v.finish_in_text = g_count_variant.load(std::memory_order_relaxed) == 0;
   return v;
 }
 inline void store_variant(int lanes, int tpb, int blocks_per_sm, int slots) {
@@ -294,6 +296,8 @@ struct Replica {
   uint2* d_table = nullptr;
   uint4* d_pair = nullptr;
   uint32_t* d_full_sa = nullptr;  // unsampled suffix array (locate accelerator)
+  uint8_t* d_rtext = nullptr;     // reversed 4-bit text (count accelerator, needs d_full_sa)
+  size_t bytes_rtext = 0;
   uint4* d_walk = nullptr;        // memory-lean locate: walk blocks, mark ranks, position-sampled SA (layout.cuh)
   uint32_t* d_walk_rank = nullptr;
   uint32_t* d_pos_samples = nullptr;

@@ -1012,7 +1012,16 @@ __device__ __forceinline__ PairSlice pair_slice(const u32x8& x, uint32_t sub, ui
 }
 
 
-template <int MODE, int TPB, int MINB>
+// VFY ("finish in the text", count mode, needs ix.full_sa and ix.rtext): once the interval has narrowed to ONE
+// row and at least VERIFY_MIN_LEFT symbols remain, the group stops stepping: SA[row] says where in the text
+// the matched suffix stands, and the remaining symbols are compared with the text in front of it -- one suffix
+// array read and one or two lines of text (4 x LDG.256 of the reversed, 4-bit-per-symbol copy, layout.cuh)
+// instead of one block read per two symbols.  The count is the one backward search arrives at: a one-row
+// interval can only stay one row (the row of the suffix `left` positions further left, when the text there
+// spells the rest of the query) or become empty (fm_index.rs:409-416 with update_range_with_symbol, :559-582).
+constexpr uint32_t VERIFY_MIN_LEFT = 8;
+
+template <int MODE, int TPB, int MINB, bool VFY = false>
 __global__ void __launch_bounds__(TPB, MINB)
     search_dna_pair_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
                            const uint64_t* __restrict__ qoff, uint64_t nq, void* __restrict__ out,
@@ -1202,6 +1211,49 @@ __global__ void __launch_bounds__(TPB, MINB)
       sp = base + ra;
       ep = base + rb - 1;
       left -= two ? 2 : 1;
+    }
+    if (VFY) {
+      // the unconsumed symbols [len - left, len) must all be in the ring (always, for queries of <= 256 symbols)
+      if (active && sp == ep && left >= VERIFY_MIN_LEFT && nwords <= wlim + 8) {
+        AWRY_CHK(sp < ix.n_full_sa);
+        const uint32_t p = __ldg(ix.full_sa + sp);  // the matched suffix stands at text[p ..]
+        bool ok = p >= left;                          // else the rest of the query would start before the text
+        if (ok) {
+          const uint32_t done = len - left;
+          // reversed text: rtext[i] = text[n - 1 - i], so the symbol of search-order index j (compared with
+          // text[p + done - 1 - j]) is rtext[rb0 + j]
+          const uint32_t rb0 = ix.bwt_len - p - done;
+          const uint32_t s_first = (rb0 + done) >> 6, s_last = (rb0 + len - 1) >> 6;  // 32-B sectors = 64 symbols
+          uint32_t bad = 0;
+          for (uint32_t sec = s_first + sub; sec <= s_last; sec += 4) {
+            AWRY_CHK(uint64_t(sec) * 32 + 31 < ix.n_rtext);
+            const u32x8 t = ldg256(ix.rtext + size_t(sec) * 32);
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+              const int j0 = int(sec * 64u + 16u * w - rb0);  // search-order index of the word's first symbol
+              int lo = int(done) - j0, hi = int(len) - j0;     // symbols [lo, hi) of the word take part
+              lo = lo < 0 ? 0 : lo;
+              hi = hi > 16 ? 16 : hi;
+              if (lo < hi) {
+                const int a = j0 >> 4;  // floor
+                const uint32_t sh = 4u * uint32_t(j0 & 15);
+                const uint64_t q0 = ring[a & 15], q1 = ring[(a + 1) & 15];
+                const uint64_t qw = sh ? (q0 >> sh) | (q1 << (64u - sh)) : q0;
+                const uint64_t tw = uint64_t(t.v[2 * w]) | (uint64_t(t.v[2 * w + 1]) << 32);
+                const uint64_t m_hi = hi >= 16 ? ~0ull : (1ull << (4 * hi)) - 1ull;
+                const uint64_t m_lo = (1ull << (4 * lo)) - 1ull;  // lo <= 15
+                bad |= ((qw ^ tw) & m_hi & ~m_lo) != 0ull ? 1u : 0u;
+              }
+            }
+          }
+          ok = !__any_sync(gmask, bad != 0u);
+        }
+        left = 0;  // finished either way: one row (count 1) or
+        if (!ok) {  // empty
+          sp = 1;
+          ep = 0;
+        }
+      }
     }
   }
 }
@@ -1492,12 +1544,12 @@ __global__ void __launch_bounds__(TPB, MINB)
   }
 }
 
-template <int MODE, int MINB>
+template <int MODE, int MINB, bool VFY = false>
 static cudaError_t launch_search_pair_b(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
                                         uint64_t nq, void* d_out, uint32_t* d_defer, int force_per_sm,
                                         int sm_count, cudaStream_t s, uint32_t avg_len, ByteRange br) {
   constexpr int TPB = 256;
-  auto kern = search_dna_pair_kernel<MODE, TPB, MINB>;
+  auto kern = search_dna_pair_kernel<MODE, TPB, MINB, VFY>;
   int per_sm = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, 0);
   if (e != cudaSuccess) return e;
@@ -1576,6 +1628,14 @@ static cudaError_t launch_search_pair(const IndexView& ix, const uint64_t* d_qwo
   // the state-machine variant, kept selectable for A/B runs with its two best residencies (see the kernel)
   if (slots == 1) return launch_search_pairx_b<MODE, 8, 1>(ix, d_qwords, d_qoff, nq, d_out, d_defer, sm_count, s, v.avg_len, br);
   if (slots == 2) return launch_search_pairx_b<MODE, 5, 2>(ix, d_qwords, d_qoff, nq, d_out, d_defer, sm_count, s, v.avg_len, br);
+  // count mode with the text on the device: finish one-row intervals by comparing with the text (see the kernel)
+  if (MODE == OUT_COUNT_U64 && v.finish_in_text && ix.rtext != nullptr && ix.full_sa != nullptr) {
+    switch (v.blocks_per_sm) {
+      case 4: return launch_search_pair_b<OUT_COUNT_U64, 4, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, br);
+      case 8: return launch_search_pair_b<OUT_COUNT_U64, 8, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, br);
+      default: return launch_search_pair_b<OUT_COUNT_U64, 6, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, br);
+    }
+  }
   switch (v.blocks_per_sm) {
     case 4: return launch_search_pair_b<MODE, 4>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, ByteRange{v.b_lo, v.b_hi});
     // 8 x 256 threads/SM (32 registers) is fastest for an isolated launch (16.2 vs 16.6-17.0 ms), 6 x 256

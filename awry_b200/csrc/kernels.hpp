@@ -26,6 +26,8 @@ struct SearchVariant {
   int blocks_per_sm = 0;  // 0 = occupancy-derived
   int slots = -1;         // pair kernel: 0 = search_dna_pair_kernel; 1 / 2 = search_dna_pairx_kernel with that many
                           // query slots per lane group; -1 = default (AWRY_B200_SLOTS, else the measured winner)
+  bool finish_in_text = true;  // count mode, pair kernel: finish one-row intervals by comparing with the text
+                               // (IndexView::rtext) instead of stepping on (awry_set_count_variant)
   uint32_t avg_len = 0;   // mean query length of the batch (0 = unknown): sizes the tickets of the dynamic hand-out
   uint64_t b_lo = 0, b_hi = ~0ull;  // byte range of the batch's queries: offsets outside it are refused (see launch_pack)
 };
@@ -85,6 +87,10 @@ cudaError_t build_pair_index(const IndexView& ix, uint4* d_pair_blocks, uint32_t
 
 // unsampled suffix array (locate accelerator): SA[row] for every row, 4 B each, from the sampled one
 cudaError_t build_full_sa(const IndexView& ix, uint32_t* d_full, int sm_count, cudaStream_t s);
+// The indexed text, reversed, 4 bits per symbol (IndexView::rtext, layout.cuh), from the blocks and ix.full_sa:
+// text[SA[row] - 1] = BWT[row].  d_rtext: rtext_bytes(bwt_len) bytes.
+inline size_t rtext_bytes(uint64_t bwt_len) { return ((size_t(bwt_len) + 1) / 2 + 127) / 128 * 128 + 128; }
+cudaError_t build_rtext(const IndexView& ix, uint8_t* d_rtext, cudaStream_t s);
 
 // The prepass latches the first query it refuses in *d_first_bad (atomicMin, ~0 = none) as
 // bad_query_code(q, kind): an empty / sentinel-carrying query (the reference panics, fm_index.rs:406,

@@ -406,6 +406,36 @@ cudaError_t build_full_sa(const IndexView& ix, uint32_t* d_full, int sm_count, c
   return cudaGetLastError();
 }
 
+// ---- the text, reversed (IndexView::rtext): text[SA[row] - 1] = BWT[row], so reversed index n - SA[row] (0 for
+// the '$' row, whose SA is 0) gets the row's device symbol.  One thread per row: rows and suffix-array elements
+// are read in order, the nibbles land at random (atomicOr into a zeroed array). ----
+__global__ void __launch_bounds__(256) rtext_kernel(IndexView ix, uint32_t* __restrict__ rtext) {
+  const uint64_t stride = gridDim.x * uint64_t(blockDim.x);
+  const uint32_t n = ix.bwt_len;
+  for (uint64_t r64 = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; r64 < n; r64 += stride) {
+    const uint32_t row = uint32_t(r64), l = row & 127, t = l & 31;
+    AWRY_CHK(uint64_t(row >> 7) * DNA_BLOCK_UINT4 + 3 < ix.n_blocks_u4 && row < ix.n_full_sa);
+    const uint4 ch = ldg128(ix.blocks + size_t(row >> 7) * DNA_BLOCK_UINT4 + (l >> 5));
+    const uint32_t c = ((ch.x >> t) & 1u) | (((ch.y >> t) & 1u) << 1) | (((ch.z >> t) & 1u) << 2);
+    const uint32_t p = __ldg(ix.full_sa + row);
+    const uint32_t i = p == 0 ? 0u : n - p;
+    AWRY_CHK(p < n && uint64_t(i >> 3) * 4 + 3 < ix.n_rtext);
+    atomicOr(rtext + (i >> 3), c << (4u * (i & 7u)));
+  }
+}
+
+cudaError_t build_rtext(const IndexView& ix, uint8_t* d_rtext, cudaStream_t s) {
+  if (ix.full_sa == nullptr || ix.alphabet != 0 || ix.wide != nullptr) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(d_rtext, 0, rtext_bytes(ix.bwt_len), s);
+  if (e != cudaSuccess) return e;
+  IndexView v = ix;
+  v.n_rtext = rtext_bytes(ix.bwt_len);
+  const unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(1u << 20, (uint64_t(ix.bwt_len) + 255) / 256)));
+  rtext_kernel<<<grid, 256, 0, s>>>(v, reinterpret_cast<uint32_t*>(d_rtext));
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
 // ---- memory-lean bounded locate: walk blocks + position-sampled suffix array (layout.cuh) ----
 
 // planes of the 1-step blocks re-laid into walk blocks (a 32-row group of a walk block is exactly one 32-row

@@ -41,6 +41,13 @@
 //               walk_rank[blk] = marked rows before the block; pos_samples[i] = SA[i-th marked row] / r.
 //               4.57 + 32/r bits per row (12.6 at r = 4: 4.9 GB at 3.1 G rows) against 32 for the unsampled array.
 //
+//   NUCLEOTIDE TEXT, REVERSED (count accelerator; derived at load time from the blocks + the unsampled array)
+//               rtext[i] = device symbol of text[n - 1 - i], 4 bits each (low nibble = even i): the format of a
+//               packed query, whose symbol 0 is the query's LAST one -- so "the rest of the query against the
+//               text in front of position p" is a word-wise XOR of two forward streams.  N and '$' keep their
+//               codes (4, 5): an A/C/G/T query symbol never equals them, as in the backward search.
+//               n / 2 bytes (1.55 GB at 3.1 G symbols).
+//
 //   AMINO       block = 64 rows = 128 B = 4 lane slices of 32 B (one LDG.256 each; one line per step)
 //               slice t < 2 = { p0..p4 of rows 32t..32t+31, cnt[3t], cnt[3t+1], cnt[3t+2] }
 //               slice 2     = { cnt[6] .. cnt[13] },  slice 3 = { cnt[14] .. cnt[21] }
@@ -89,6 +96,9 @@ struct IndexView {
   const uint4* __restrict__ walk_blocks;   // nucleotide walk blocks (planes + position marks), or nullptr
   const uint32_t* __restrict__ walk_rank;  // marked rows before each walk block
   const uint32_t* __restrict__ pos_samples;  // SA[marked row] / lean_ratio, in row order
+  const uint8_t* __restrict__ rtext;       // the indexed text REVERSED, one device symbol per 4 bits (the packed
+                                           // query format): rtext[i] = text[bwt_len - 1 - i], i even = low nibble;
+                                           // derived from BWT + unsampled SA at load time, or nullptr
   uint32_t lean_ratio;                     // a row is marked iff SA[row] % lean_ratio == 0 (the library's choice:
                                            // the array is derived, not stored -- see finish_replica0)
   uint32_t c2[16];                         // C2[4a+b]
@@ -107,6 +117,7 @@ struct IndexView {
                                            // bwt_len >= 2^32 - 256; the launchers then run kernels_wide.cu
   // array sizes in elements (what AWRY_CHK checks against in the checked build)
   uint64_t n_blocks_u4, n_pair_u4, n_table, n_sa_words, n_full_sa, n_walk_u4, n_walk_rank, n_pos_samples;
+  uint64_t n_rtext;  // bytes
 };
 
 // ---- wide indexes: SearchPtr = u64 (search.rs:7), suffix-array elements up to 64 bits

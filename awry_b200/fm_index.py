@@ -81,7 +81,8 @@ class _Info(C.Structure):
                 ("device_bytes_sa", C.c_uint64), ("device_bytes_table", C.c_uint64),
                 ("device_bytes_pair", C.c_uint64), ("device_bytes_full_sa", C.c_uint64),
                 ("device_bytes_lean_sa", C.c_uint64),
-                ("devices", C.c_int32 * 16), ("row_pointer_bits", C.c_uint32), ("lean_sa_ratio", C.c_uint32)]
+                ("devices", C.c_int32 * 16), ("row_pointer_bits", C.c_uint32), ("lean_sa_ratio", C.c_uint32),
+                ("device_bytes_text", C.c_uint64)]
 
 
 class _Parts(C.Structure):
@@ -124,7 +125,7 @@ EXPORTS = ["awry_read_sequence_file", "awry_index_build", "awry_build_index_file
            "awry_locate_reads_file", "awry_buffer_free", "awry_initial_range", "awry_update_range",
            "awry_backstep", "awry_count_device", "awry_locate_device", "awry_device_free",
            "awry_device_check", "awry_profile_enable", "awry_profile_reset", "awry_profile_get",
-           "awry_bench_random_gather", "awry_set_search_variant", "awry_set_locate_variant", "awry_set_host_pack",
+           "awry_bench_random_gather", "awry_set_search_variant", "awry_set_locate_variant", "awry_set_count_variant", "awry_set_host_pack",
            "awry_host_pack_dna", "awry_last_error", "awry_version", "awry_count_batch_packed2",
            "awry_locate_batch_packed2", "awry_set_host_threads", "awry_host_threads"]
 
@@ -186,6 +187,7 @@ def native():
     L.awry_buffer_free.restype = None
     L.awry_set_search_variant.argtypes = [i32, i32, i32]
     L.awry_set_locate_variant.argtypes = [i32]
+    L.awry_set_count_variant.argtypes = [i32]
     L.awry_set_host_pack.argtypes = [i32]
     L.awry_host_pack_dna.argtypes = [vp, u64, vp, vp, u64, C.POINTER(u64)]
     L.awry_count_batch_packed2.argtypes = [vp, vp, vp, u64, vp, u64, vp]
@@ -326,7 +328,7 @@ class FmIndex:
     def device_bytes(self) -> dict:
         return {"blocks": int(self._info.device_bytes_blocks), "sa": int(self._info.device_bytes_sa),
                 "table": int(self._info.device_bytes_table), "pair": int(self._info.device_bytes_pair),
-                "full_sa": int(self._info.device_bytes_full_sa), "lean_sa": int(self._info.device_bytes_lean_sa)}
+                "full_sa": int(self._info.device_bytes_full_sa), "lean_sa": int(self._info.device_bytes_lean_sa), "text": int(self._info.device_bytes_text)}
 
     def sequence_header(self, seq_idx: int) -> str:
         p, n = C.c_char_p(), C.c_uint64()
@@ -572,6 +574,12 @@ def bench_random_gather(device: int, footprint_bytes: int, granule: int, lanes: 
 
 def set_search_variant(lanes: int = 0, tpb: int = 0, blocks_per_sm: int = 0):
     _check(native().awry_set_search_variant(lanes, tpb, blocks_per_sm))
+
+
+def set_count_variant(variant: int = 0):
+    """0 = nucleotide counts finish one-row intervals by comparing with the text (when the index holds the
+    unsampled suffix array and the text); 1 = backward search to the last symbol.  Same counts either way."""
+    _check(native().awry_set_count_variant(variant))
 
 
 def set_locate_variant(variant: int = 0):

@@ -75,6 +75,7 @@ typedef struct awry_info {
   int32_t devices[16];
   uint32_t row_pointer_bits;    /* 32 while bwt_len < 2^32 - 256, else 64 (SearchPtr = u64, search.rs:7) */
   uint32_t lean_sa_ratio;       /* sampling distance of the derived position-sampled suffix array, 0 if not built */
+  uint64_t device_bytes_text;   /* nucleotide: the indexed text, reversed, 4 bits per symbol (count accelerator), 0 if not built */
 } awry_info;
 
 /* The fields FmIndex::new hands over after the reference's CPU construction
@@ -305,6 +306,15 @@ int awry_bench_random_gather(int device, uint64_t footprint_bytes, uint32_t gran
  * query start as a branch (80) or as states of 1 / 2 query slots per lane group (81 / 82).
  * blocks_per_sm caps residency. */
 int awry_set_search_variant(int lanes_per_query, int threads_per_block, int blocks_per_sm);
+
+/* Count, nucleotide.  Once backward search (fm_index.rs:402-438) has narrowed the interval to ONE row, the rest of
+ * the query can only keep that row or empty the interval, and which of the two is decided by the text in front
+ * of the occurrence.  When the index holds the unsampled suffix array and the text (4 bits per symbol, read back
+ * out of BWT + suffix array at load time: bwt_len / 2 bytes, AWRY_B200_TEXT=0 never), the count kernel looks the
+ * row's position up and compares the remaining symbols with the text -- 2-3 memory requests instead of one per
+ * two symbols; counts are identical.  variant 0 = do so when the arrays are present (default), 1 = backward
+ * search to the last symbol. */
+int awry_set_count_variant(int variant);
 
 /* Locate pass 2.  Three ways to turn a BWT row into a text position, identical results:
  *   (a) the UNSAMPLED suffix array, rebuilt on the device at load time from the file's sampled one

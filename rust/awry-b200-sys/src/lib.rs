@@ -42,6 +42,7 @@ pub struct awry_info {
     pub devices: [i32; 16],
     pub row_pointer_bits: u32,
     pub lean_sa_ratio: u32,
+    pub device_bytes_text: u64,
 }
 
 #[repr(C)]
@@ -144,6 +145,7 @@ extern "C" {
                                     reads_per_s: *mut f64, gb_per_s: *mut f64) -> c_int;
     pub fn awry_set_search_variant(lanes_per_query: c_int, threads_per_block: c_int, blocks_per_sm: c_int) -> c_int;
     pub fn awry_set_locate_variant(variant: c_int) -> c_int;
+    pub fn awry_set_count_variant(variant: c_int) -> c_int;
     pub fn awry_last_error() -> *const c_char;
     pub fn awry_version() -> *const c_char;
 }

@@ -25,7 +25,7 @@ def checked_lib():
 def test_parity_suites_pass_on_the_bounds_checked_build(checked_lib):
     env = dict(os.environ, AWRY_B200_LIB=checked_lib)
     out = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_gpu_fuzz.py",
-                          "tests/test_gpu_round2.py", "tests/test_gpu_wide.py", "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider",
+                          "tests/test_gpu_round2.py", "tests/test_gpu_wide.py", "tests/test_gpu_text_finish.py", "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider",
                           "-k", "not 4p6 and not several_replicas and not multi_replica and not cxx_host_mirror"],
                          cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     tail = out.stdout[-1500:] + out.stderr[-1500:]
