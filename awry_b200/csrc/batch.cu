@@ -199,6 +199,29 @@ void validate_chunks(const std::vector<Chunk>& chunks, uint64_t max_bytes) {
   }
 }
 
+// Sequencer reads are all the same length: then a chunk's offsets are first + i * len and the device writes them
+// itself (8 bytes per read that do not cross the link: 80 MB of the 455 MB a 10 M x 150-bp batch of packed reads
+// uploads).  Checked exactly, on the pool, per chunk; AWRY_B200_UNIFORM_OFFSETS=0 always copies.
+bool offsets_are_uniform(const uint64_t* off, uint64_t nq, uint64_t& len) {
+  static const bool on = [] {
+    const char* e = getenv("AWRY_B200_UNIFORM_OFFSETS");
+    return !(e && e[0] == '0');
+  }();
+  if (!on || nq < 4096) return false;
+  len = off[1] - off[0];
+  if (off[1] < off[0] || len == 0 || len >= (1ull << 32) || off[nq] - off[0] != len * nq) return false;
+  const uint64_t BLK = 1u << 16, nb = (nq + BLK - 1) / BLK, first = off[0], l = len;
+  std::atomic<bool> ok{true};
+  host_parallel_blocks(size_t(nb), [&](size_t b) {
+    if (!ok.load(std::memory_order_relaxed)) return;
+    const uint64_t lo = b * BLK, hi = std::min(nq, lo + BLK);
+    uint64_t bad = 0;
+    for (uint64_t i = lo; i <= hi; i++) bad |= off[i] ^ (first + i * l);
+    if (bad) ok.store(false, std::memory_order_relaxed);
+  });
+  return ok.load();
+}
+
 // Uploads one chunk of queries and runs prepass + search on ws->st.  The search result lands
 // in ws->d_out in the requested mode.
 // `may_pack`: the caller's say on host packing for this chunk (PackBalance)
@@ -217,8 +240,18 @@ void enqueue_search(const awry_index* ix, Replica& r, PackBalance& bal, Workspac
   const uint64_t* src_o = qs.qoff + c.q0;
   uint64_t* const d_words = ws->d_qwords - 4 * (c.b0 >> ush);
   ws->link_probe_bytes = 0;
+  uint64_t uni_len = 0;
+  const bool uniform = offsets_are_uniform(src_o, nq, uni_len);
+  auto upload_offsets = [&] {
+    if (uniform) {
+      CU(launch_fill_offsets(ws->d_qoff, c.b0, uni_len, nq, ws->st));
+    } else {
+      CU(cudaMemcpyAsync(ws->d_qoff, src_o, (nq + 1) * 8, cudaMemcpyHostToDevice, ws->st));
+      g_prof.h2d += (nq + 1) * 8;
+    }
+  };
   auto stage_offsets = [&] {  // pageable offsets: staged through pinned memory
-    if (qs.pinned) return;
+    if (qs.pinned || uniform) return;
     Workspace::grow_host(ws->h_qoff, ws->h_qoff_cap, size_t(nq) + 1);
     parallel_memcpy(ws->h_qoff, src_o, (nq + 1) * 8);
     src_o = ws->h_qoff;
@@ -238,7 +271,7 @@ void enqueue_search(const awry_index* ix, Replica& r, PackBalance& bal, Workspac
       src_c = ws->h_qbytes;
     }
     if (pbytes) CU(cudaMemcpyAsync(ws->d_qbytes, src_c, pbytes, cudaMemcpyHostToDevice, ws->st));
-    CU(cudaMemcpyAsync(ws->d_qoff, src_o, (nq + 1) * 8, cudaMemcpyHostToDevice, ws->st));
+    upload_offsets();
     if (n_exc) {
       Workspace::grow_dev(ws->d_exc, ws->d_exc_cap, n_exc);
       const uint64_t* src_e = e_lo;
@@ -249,7 +282,7 @@ void enqueue_search(const awry_index* ix, Replica& r, PackBalance& bal, Workspac
       }
       CU(cudaMemcpyAsync(ws->d_exc, src_e, n_exc * 8, cudaMemcpyHostToDevice, ws->st));
     }
-    g_prof.h2d += pbytes + (nq + 1) * 8 + n_exc * 8;
+    g_prof.h2d += pbytes + n_exc * 8;
     gpu_mark(ws->st, "h2d done", (long long)c.q0);
     CU(cudaMemsetAsync(ws->d_flag, 0xff, 8, ws->st));
     {
@@ -277,14 +310,14 @@ void enqueue_search(const awry_index* ix, Replica& r, PackBalance& bal, Workspac
       const size_t pbytes = (size_t(nbytes) + 3) / 4;
       stage_offsets();
       CU(cudaMemcpyAsync(ws->d_qbytes, ws->h_qbytes, pbytes + 8, cudaMemcpyHostToDevice, ws->st));
-      CU(cudaMemcpyAsync(ws->d_qoff, src_o, (nq + 1) * 8, cudaMemcpyHostToDevice, ws->st));
+      upload_offsets();
       if (n_exc) {
         Workspace::grow_host(ws->h_exc, ws->h_exc_cap, n_exc);
         Workspace::grow_dev(ws->d_exc, ws->d_exc_cap, n_exc);
         memcpy(ws->h_exc, ws->exc_tmp.data(), n_exc * 8);
         CU(cudaMemcpyAsync(ws->d_exc, ws->h_exc, n_exc * 8, cudaMemcpyHostToDevice, ws->st));
       }
-      g_prof.h2d += pbytes + 8 + (nq + 1) * 8 + n_exc * 8;
+      g_prof.h2d += pbytes + 8 + n_exc * 8;
       gpu_mark(ws->st, "h2d done", (long long)c.q0);
       CU(cudaMemsetAsync(ws->d_flag, 0xff, 8, ws->st));
       {
@@ -312,8 +345,8 @@ void enqueue_search(const awry_index* ix, Replica& r, PackBalance& bal, Workspac
         CU(cudaEventRecord(ws->ev_b, ws->st));
         ws->link_probe_bytes = nbytes;
       }
-      CU(cudaMemcpyAsync(ws->d_qoff, src_o, (nq + 1) * 8, cudaMemcpyHostToDevice, ws->st));
-      g_prof.h2d += nbytes + (nq + 1) * 8;
+      upload_offsets();
+      g_prof.h2d += nbytes;
       CU(cudaMemsetAsync(ws->d_flag, 0xff, 8, ws->st));
       // offsets stay absolute: the kernels subtract the chunk's byte base
       {

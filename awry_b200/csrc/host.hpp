@@ -395,7 +395,9 @@ struct PackBalance {
     const bool host_suffices = gpu_rate > 0 ? host_rate >= 1.15 * gpu_rate : host_rate > 2.0 * link_rate;
     if (host_suffices) return Plan{1.0, refresh, false};
     if (!mixed) return host_rate > link_rate ? Plan{1.0, refresh, false} : Plan{0.0, true, refresh};
-    double f = host_rate / (host_rate + link_rate);  // host and link side by side
+    // host and link side by side: a share f of the bytes is packed at host_rate and crosses the link as f / 4,
+    // the rest crosses as it is -- f / host_rate = (1 - 0.75 f) / link_rate
+    double f = host_rate / (link_rate + 0.75 * host_rate);
     if (f < 0.15) f = 0.0;
     if (f > 0.9) f = 1.0;
     return Plan{f, true, f == 0.0 && refresh};

@@ -729,6 +729,16 @@ cudaError_t launch_pack2(const uint32_t* d_crumbs, uint64_t base, const uint64_t
   return cudaGetLastError();
 }
 
+__global__ void fill_offsets_kernel(uint64_t* __restrict__ qoff, uint64_t first, uint64_t len, uint64_t n) {
+  const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (i <= n) qoff[i] = first + i * len;
+}
+cudaError_t launch_fill_offsets(uint64_t* d_qoff, uint64_t first, uint64_t len, uint64_t n, cudaStream_t s) {
+  fill_offsets_kernel<<<unsigned((n + 256) / 256), 256, 0, s>>>(d_qoff, first, len, n);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ backward search
 
 // Start of a query: seed interval from the k-mer table when the last k symbols are all

@@ -86,6 +86,9 @@ uint64_t pair_block_count(uint64_t bwt_len);
 cudaError_t build_pair_index(const IndexView& ix, uint4* d_pair_blocks, uint32_t* c2_host /*16*/, cudaStream_t s);
 
 // unsampled suffix array (locate accelerator): SA[row] for every row, 4 B each, from the sampled one
+// d_qoff[i] = first + i * len for i in [0, n]: the offsets of a chunk of equally long queries, written on the
+// device instead of copied to it
+cudaError_t launch_fill_offsets(uint64_t* d_qoff, uint64_t first, uint64_t len, uint64_t n, cudaStream_t s);
 cudaError_t build_full_sa(const IndexView& ix, uint32_t* d_full, int sm_count, cudaStream_t s);
 // The indexed text, reversed, 4 bits per symbol (IndexView::rtext, layout.cuh), from the blocks and ix.full_sa:
 // text[SA[row] - 1] = BWT[row].  d_rtext: rtext_bytes(bwt_len) bytes.
