@@ -757,7 +757,7 @@ __device__ __forceinline__ uint32_t begin_query(const IndexView& ix, const uint6
       uint64_t w = qs.w;  // k <= 16 symbols, all inside the first word
       uint64_t himask = 0xCCCCCCCCCCCCCCCCull >> (4 * (16 - k));
       ok = (w & himask) == 0;
-      for (uint32_t j = 0; j < k; j++) idx |= ((w >> (4 * j)) & 3ull) << (2 * j);
+      idx = kmer_index(w, k);
     } else {
       uint64_t w = qs.w, mult = 1;  // k <= 8
       for (uint32_t j = 0; j < k; j++) {
@@ -1132,8 +1132,7 @@ __global__ void __launch_bounds__(TPB, MINB)
             const uint64_t w = ring[0];
             if (k != 0 && len >= k) {  // k <= 16: inside word 0
               uint64_t idx = 0;
-#pragma unroll 1
-              for (uint32_t j = 0; j < k; j++) idx |= ((w >> (4 * j)) & 3ull) << (2 * j);
+              idx = kmer_index(w, k);
               AWRY_CHK(idx < ix.n_table);
       uint2 r = __ldg(ix.table + idx);
               sp = r.x;
@@ -1238,23 +1237,7 @@ __global__ void __launch_bounds__(TPB, MINB)
           for (uint32_t sec = s_first + sub; sec <= s_last; sec += 4) {
             AWRY_CHK(uint64_t(sec) * 32 + 31 < ix.n_rtext);
             const u32x8 t = ldg256(ix.rtext + size_t(sec) * 32);
-#pragma unroll
-            for (int w = 0; w < 4; w++) {
-              const int j0 = int(sec * 64u + 16u * w - rb0);  // search-order index of the word's first symbol
-              int lo = int(done) - j0, hi = int(len) - j0;     // symbols [lo, hi) of the word take part
-              lo = lo < 0 ? 0 : lo;
-              hi = hi > 16 ? 16 : hi;
-              if (lo < hi) {
-                const int a = j0 >> 4;  // floor
-                const uint32_t sh = 4u * uint32_t(j0 & 15);
-                const uint64_t q0 = ring[a & 15], q1 = ring[(a + 1) & 15];
-                const uint64_t qw = sh ? (q0 >> sh) | (q1 << (64u - sh)) : q0;
-                const uint64_t tw = uint64_t(t.v[2 * w]) | (uint64_t(t.v[2 * w + 1]) << 32);
-                const uint64_t m_hi = hi >= 16 ? ~0ull : (1ull << (4 * hi)) - 1ull;
-                const uint64_t m_lo = (1ull << (4 * lo)) - 1ull;  // lo <= 15
-                bad |= ((qw ^ tw) & m_hi & ~m_lo) != 0ull ? 1u : 0u;
-              }
-            }
+            bad |= text_sector_mismatch(t, ring, sec, rb0, done, len);
           }
           ok = !__any_sync(gmask, bad != 0u);
         }
@@ -1291,13 +1274,17 @@ __global__ void __launch_bounds__(TPB, MINB)
 // the loads it has in flight, so more memory-level parallelism per lane buys nothing here.  The default stays
 // search_dna_pair_kernel; this one is bit-exact (the GPU suite passes with AWRY_B200_SLOTS=1 and =2) and
 // selectable (awry_set_search_variant(81 / 82)) so the comparison can be repeated.
-template <int MODE, int TPB, int MINB, int NS>
+// VFY (count mode, see search_dna_pair_kernel): two more states -- ST_SA (the suffix-array element of a one-row
+// interval) and ST_TEXT (the sectors of the reversed text the rest of the query is compared with; at most 4, so
+// it is entered with at most 193 symbols left).  With the comparison a 150-bp read is ~8 dependent loads of
+// seven different kinds instead of ~70 block reads, which is the workload this kernel was written for.
+template <int MODE, int TPB, int MINB, int NS, bool VFY = false>
 __global__ void __launch_bounds__(TPB, MINB)
     search_dna_pairx_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
                             const uint64_t* __restrict__ qoff, uint64_t nq, void* __restrict__ out,
                             uint32_t* __restrict__ defer, uint32_t ticket_sz, ByteRange br) {
   constexpr uint32_t NONE = 0xffffffffu, FULL = 0xffffffffu;
-  enum : uint32_t { ST_IDLE = 0, ST_OFFS = 1, ST_WORDS = 2, ST_SEED = 3, ST_STEP = 4, ST_RING = 5 };
+  enum : uint32_t { ST_IDLE = 0, ST_OFFS = 1, ST_WORDS = 2, ST_SEED = 3, ST_STEP = 4, ST_RING = 5, ST_SA = 6, ST_TEXT = 7 };
   constexpr uint32_t PC_STEP = 0x200u, PC_TWO = 0x100u;  // pc: "this slot issued a step" | "a two-symbol step" | symbols
   __shared__ uint64_t s_q[NS][TPB / 4][16];
   __shared__ uint32_t s_amb[NS][TPB / 4];  // an ambiguity symbol was seen while staging (set by any lane of the group)
@@ -1407,8 +1394,7 @@ __global__ void __launch_bounds__(TPB, MINB)
         const uint32_t k = ix.kmer_len;
         const uint64_t w = s_q[s][grp][0];  // k <= 16: inside word 0
         uint64_t idx = 0;
-#pragma unroll 1
-        for (uint32_t j = 0; j < k; j++) idx |= ((w >> (4 * j)) & 3ull) << (2 * j);
+        idx = kmer_index(w, k);
         AWRY_CHK(idx < ix.n_table);
         const uint2 r = __ldg(ix.table + idx);
         x[s].v[0] = r.x;
@@ -1417,6 +1403,16 @@ __global__ void __launch_bounds__(TPB, MINB)
         if (sub < 2) {
           AWRY_CHK_QWORDS(ubase[s] + wlim[s] + 8 + 4 * sub, br, nq, 6);
           x[s] = ldg256(qwords + ubase[s] + wlim[s] + 8 + 4 * sub);  // in bounds: buffer padded by 32 words
+        }
+      } else if (VFY && st[s] == ST_SA) {
+        AWRY_CHK(sp[s] < ix.n_full_sa);
+        x[s].v[0] = __ldg(ix.full_sa + sp[s]);
+      } else if (VFY && st[s] == ST_TEXT) {  // ubase = reversed-text index of search-order symbol 0 (set by ST_SA)
+        const uint32_t done = len[s] - left[s];
+        const uint32_t sec = ((ubase[s] + done) >> 6) + sub;
+        if (sec <= ((ubase[s] + len[s] - 1) >> 6)) {
+          AWRY_CHK(uint64_t(sec) * 32 + 31 < ix.n_rtext);
+          x[s] = ldg256(ix.rtext + size_t(sec) * 32);
         }
       }
     }
@@ -1523,6 +1519,23 @@ __global__ void __launch_bounds__(TPB, MINB)
         } else {
           st[s] = ST_STEP;
         }
+      } else if (VFY && st[s] == ST_SA) {
+        const uint32_t p = x[s].v[0];  // the matched suffix stands at text[p ..]
+        if (p < left[s]) {             // the rest of the query would start before the text
+          if (sub == 0) store_result<MODE>(out, cur[s], 1u, 0u);
+          st[s] = ST_IDLE;
+        } else {
+          ubase[s] = ix.bwt_len - p - (len[s] - left[s]);  // (the ring needs no more words: ubase is free)
+          st[s] = ST_TEXT;
+        }
+      } else if (VFY && st[s] == ST_TEXT) {
+        const uint32_t done = len[s] - left[s], rb0 = ubase[s];
+        const uint32_t sec = ((rb0 + done) >> 6) + sub;
+        uint32_t bad = 0;
+        if (sec <= ((rb0 + len[s] - 1) >> 6)) bad = text_sector_mismatch(x[s], ring, sec, rb0, done, len[s]);
+        const bool ok = !__any_sync(gmask, bad != 0u);
+        if (sub == 0) store_result<MODE>(out, cur[s], ok ? sp[s] : 1u, ok ? ep[s] : 0u);  // one row, or empty
+        st[s] = ST_IDLE;
       }
     }
     // rank reduction over the 4 lanes of every group, all slots, full-mask shuffles (every lane is here)
@@ -1550,6 +1563,10 @@ __global__ void __launch_bounds__(TPB, MINB)
         if (sub == 0) store_result<MODE>(out, cur[s], sp[s], ep[s]);
         st[s] = ST_IDLE;
       }
+      // one row left and the unconsumed symbols all in the ring, within four text sectors: finish in the text
+      if (VFY && st[s] == ST_STEP && sp[s] == ep[s] && left[s] >= VERIFY_MIN_LEFT && left[s] <= 193u &&
+          ((len[s] + 15) >> 4) <= wlim[s] + 8)
+        st[s] = ST_SA;
     }
   }
 }
@@ -1590,12 +1607,12 @@ static cudaError_t launch_search_pair_b(const IndexView& ix, const uint64_t* d_q
 }
 
 // the state-machine kernel: NS query slots per lane group, `per_sm` resident 256-thread blocks (register budget)
-template <int MODE, int MINB, int NS>
+template <int MODE, int MINB, int NS, bool VFY = false>
 static cudaError_t launch_search_pairx_b(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
                                          uint64_t nq, void* d_out, uint32_t* d_defer, int sm_count, cudaStream_t s,
                                          uint32_t avg_len, ByteRange br) {
   constexpr int TPB = 256;
-  auto kern = search_dna_pairx_kernel<MODE, TPB, MINB, NS>;
+  auto kern = search_dna_pairx_kernel<MODE, TPB, MINB, NS, VFY>;
   int per_sm = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, 0);
   if (e != cudaSuccess) return e;
@@ -1631,21 +1648,25 @@ static cudaError_t launch_search_pair(const IndexView& ix, const uint64_t* d_qwo
   if (e != cudaSuccess) return e;
   const ByteRange br{v.b_lo, v.b_hi};
   static const int slots_default = [] {
-    if (const char* e = getenv("AWRY_B200_SLOTS")) return std::max(0, std::min(2, atoi(e)));
+    if (const char* e = getenv("AWRY_B200_SLOTS")) return std::max(0, std::min(4, atoi(e)));
     return 0;
   }();
   const int slots = v.slots >= 0 ? v.slots : slots_default;
-  // the state-machine variant, kept selectable for A/B runs with its two best residencies (see the kernel)
-  if (slots == 1) return launch_search_pairx_b<MODE, 8, 1>(ix, d_qwords, d_qoff, nq, d_out, d_defer, sm_count, s, v.avg_len, br);
-  if (slots == 2) return launch_search_pairx_b<MODE, 5, 2>(ix, d_qwords, d_qoff, nq, d_out, d_defer, sm_count, s, v.avg_len, br);
   // count mode with the text on the device: finish one-row intervals by comparing with the text (see the kernel)
   if (MODE == OUT_COUNT_U64 && v.finish_in_text && ix.rtext != nullptr && ix.full_sa != nullptr) {
+    if (slots == 1) return launch_search_pairx_b<OUT_COUNT_U64, 8, 1, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, sm_count, s, v.avg_len, br);
+    if (slots == 2) return launch_search_pairx_b<OUT_COUNT_U64, 5, 2, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, sm_count, s, v.avg_len, br);
+    if (slots == 3) return launch_search_pairx_b<OUT_COUNT_U64, 6, 1, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, sm_count, s, v.avg_len, br);
+    if (slots == 4) return launch_search_pairx_b<OUT_COUNT_U64, 4, 2, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, sm_count, s, v.avg_len, br);
     switch (v.blocks_per_sm) {
       case 4: return launch_search_pair_b<OUT_COUNT_U64, 4, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, br);
       case 8: return launch_search_pair_b<OUT_COUNT_U64, 8, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, br);
       default: return launch_search_pair_b<OUT_COUNT_U64, 6, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, br);
     }
   }
+  // the state-machine variant, kept selectable for A/B runs with its two best residencies (see the kernel)
+  if (slots == 1 || slots == 3) return launch_search_pairx_b<MODE, 8, 1>(ix, d_qwords, d_qoff, nq, d_out, d_defer, sm_count, s, v.avg_len, br);
+  if (slots == 2 || slots == 4) return launch_search_pairx_b<MODE, 5, 2>(ix, d_qwords, d_qoff, nq, d_out, d_defer, sm_count, s, v.avg_len, br);
   switch (v.blocks_per_sm) {
     case 4: return launch_search_pair_b<MODE, 4>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, ByteRange{v.b_lo, v.b_hi});
     // 8 x 256 threads/SM (32 registers) is fastest for an isolated launch (16.2 vs 16.6-17.0 ms), 6 x 256

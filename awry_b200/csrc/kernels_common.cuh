@@ -115,6 +115,21 @@ __device__ __forceinline__ uint32_t dna_partial_rank(const LaneChunks<LANES>& x,
 }
 
 
+// Seed-table index of the first k <= 16 symbols of a packed nucleotide word: the low 2 bits of nibbles 0 .. k-1,
+// squeezed together (symbol j at bits 2j).  Four mask-and-shift rounds per 32-bit half instead of a k-trip loop,
+// which was 17 % of the count kernel's instructions once a 150-bp read took ~8 loads instead of ~70.
+__device__ __forceinline__ uint32_t squeeze8(uint32_t x) {  // 8 nibbles -> 8 crumbs (16 bits)
+  x &= 0x33333333u;
+  x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+  x = (x | (x >> 4)) & 0x00FF00FFu;
+  x = (x | (x >> 8)) & 0x0000FFFFu;
+  return x;
+}
+__device__ __forceinline__ uint64_t kmer_index(uint64_t w, uint32_t k) {
+  const uint32_t v = squeeze8(uint32_t(w)) | (squeeze8(uint32_t(w >> 32)) << 16);
+  return k >= 16 ? uint64_t(v) : uint64_t(v & ((1u << (2 * k)) - 1u));
+}
+
 // low `n` bits set, n clamped to [0, 32] (BMSK)
 __device__ __forceinline__ uint32_t low_mask(int n) {
   uint32_t m, len = uint32_t(n < 0 ? 0 : n);
@@ -122,6 +137,30 @@ __device__ __forceinline__ uint32_t low_mask(int n) {
   return m;
 }
 
+
+// ---- "finish in the text" (layout.cuh: IndexView::rtext): one 32-byte sector of the reversed text (64 symbols,
+// 8 per word) against the packed query in the group's shared-memory ring.  `rb0` = reversed-text index of
+// search-order symbol 0, so the sector's first symbol has search-order index j0 = 64 * sec - rb0 (negative for
+// the sector the window starts in); symbols [done, len) take part.  Returns non-zero on a mismatch.
+// The ring is read as 32 words of 8 symbols; words outside the loaded part are masked out, not avoided.
+__device__ __forceinline__ uint32_t text_sector_mismatch(const u32x8& t, const uint64_t* ring, uint32_t sec, uint32_t rb0,
+                                                         uint32_t done, uint32_t len) {
+  const uint32_t* rq = reinterpret_cast<const uint32_t*>(ring);
+  const int j0 = int(sec * 64u - rb0);
+  const int a = j0 >> 3;  // floor
+  const uint32_t sh = 4u * uint32_t(j0 & 7);
+  uint32_t bad = 0, q_lo = rq[a & 31];
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    const uint32_t q_hi = rq[(a + w + 1) & 31];
+    const uint32_t qw = __funnelshift_r(q_lo, q_hi, sh);  // query symbols j0 + 8 w .. + 7
+    const int jw = j0 + 8 * w;
+    const uint32_t m = low_mask(4 * (int(len) - jw)) & ~low_mask(4 * (int(done) - jw));
+    bad |= (qw ^ t.v[w]) & m;
+    q_lo = q_hi;
+  }
+  return bad;
+}
 
 // ---- a lane's share of a 128-B amino block (4 lanes): matching rows of its 32-row slice and, in the
 // lane that holds it, the block-start count of the symbol ----

@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256) w_search_kernel(WideView ix, const uint64
         const uint64_t w = qs.w;
         if (ALPHA == 0) {
           ok = (w & (0xCCCCCCCCCCCCCCCCull >> (4 * (16 - k)))) == 0;
-          for (uint32_t j = 0; j < k; j++) idx |= ((w >> (4 * j)) & 3ull) << (2 * j);
+          idx = kmer_index(w, k);
         } else {
           uint64_t mult = 1;
           for (uint32_t j = 0; j < k; j++) {
@@ -281,8 +281,7 @@ __global__ void __launch_bounds__(256, 6)
           const uint64_t w = qs.w;
           if (k != 0 && len >= k && (w & (0xCCCCCCCCCCCCCCCCull >> (4 * (16 - k)))) == 0) {
             uint64_t idx = 0;
-#pragma unroll 1
-            for (uint32_t j = 0; j < k; j++) idx |= ((w >> (4 * j)) & 3ull) << (2 * j);
+            idx = kmer_index(w, k);
             AWRY_CHK(idx < ix.n_table);
             const ulonglong2 r = ix.table[idx];
             sp = r.x;

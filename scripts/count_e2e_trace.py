@@ -5,7 +5,7 @@ import numpy as np, torch
 from awry_b200 import FmIndex, fm_index as f
 from fixtures import pyfixture_gpu as fxg
 n, nq, L = 3_100_000_000, 10_000_000, 150
-os.environ.setdefault("AWRY_B200_FULL_SA", "0"); os.environ.setdefault("AWRY_B200_LEAN_SA", "0")
+os.environ.setdefault("AWRY_B200_LEAN_SA", "0")
 parts, _ = fxg.build_parts(0, n, 3, ratio=8, kmer_len=13)
 ix = FmIndex.from_parts(parts.alphabet, parts.ratio, parts.bwt_len, parts.kmer_len, parts.blocks, parts.prefix_sums, parts.sa_words)
 d = torch.empty(nq * L, dtype=torch.uint8, device="cuda"); fxg.gen_queries_device(0, n, 3, nq, L, 4, d.data_ptr())

@@ -20,14 +20,20 @@ cnt = torch.zeros(nq, dtype=torch.int64, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
 f.profile_enable(True)
 orc = po.OracleIndex.from_parts(parts.alphabet, parts.ratio, parts.bwt_len, parts.kmer_len, parts.blocks, parts.prefix_sums, parts.sa_words)
-for mut, what in ((0, "exact reads"), (100_000, "10 % of the reads with one substitution")):
+QUICK = os.environ.get("PROBE_QUICK") == "1"  # branching kernel only, exact reads only (ticket-size sweeps)
+for mut, what in ((0, "exact reads"), (100_000, "10 % of the reads with one substitution"))[:1 if QUICK else 2]:
     d = torch.empty(nq * L, dtype=torch.uint8, device="cuda")
     fxg.gen_queries_device(0, n, 3, nq, L, 4, d.data_ptr(), mut_ppm=mut)
     ref = None
-    for variant, bps, name in ((1, 0, "backward search only        "), (0, 0, "finish in the text, 6 blk/SM"),
-                               (0, 4, "finish in the text, 4 blk/SM"), (0, 8, "finish in the text, 8 blk/SM")):
+    for variant, lanes, bps, name in ((1, 0, 0, "backward search only                      "),
+                                      (0, 0, 0, "finish in the text, branching, 6 blk/SM   "),
+                                      (0, 0, 8, "finish in the text, branching, 8 blk/SM   "),
+                                      (0, 81, 0, "finish in the text, states, 1 slot, 8 blk "),
+                                      (0, 83, 0, "finish in the text, states, 1 slot, 6 blk "),
+                                      (0, 82, 0, "finish in the text, states, 2 slots, 5 blk"),
+                                      (0, 84, 0, "finish in the text, states, 2 slots, 4 blk"))[:3 if QUICK else 7]:
         f.set_count_variant(variant)
-        f.set_search_variant(0, 0, bps)
+        f.set_search_variant(lanes, 0, bps)
         for _ in range(3):
             ix.count_device(d.data_ptr(), off.data_ptr(), nq, cnt.data_ptr(), st)
         torch.cuda.synchronize()

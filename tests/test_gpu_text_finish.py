@@ -85,9 +85,13 @@ def test_counts_equal_backward_search_and_the_oracle(po, multi, multi_dev):
         plain = multi_dev.count_packed(qb, qo)
     finally:
         f.set_count_variant(0)
-    got = multi_dev.count_packed(qb, qo)
     assert np.array_equal(plain, want)
-    assert np.array_equal(got, want)
+    try:
+        for kernel in (0, 81, 82, 83, 84):                  # the branching kernel and the state-machine one (1 / 2 slots)
+            f.set_search_variant(kernel)
+            assert np.array_equal(multi_dev.count_packed(qb, qo), want), kernel
+    finally:
+        f.set_search_variant(0)
     crumbs, exc = f.host_pack_dna(qb)                       # the pre-packed entry point runs the same kernel
     assert np.array_equal(multi_dev.count_prepacked(crumbs, qo, exc), want)
 
