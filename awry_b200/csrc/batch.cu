@@ -362,6 +362,10 @@ void enqueue_search(const awry_index* ix, Replica& r, PackBalance& bal, Workspac
     v.avg_len = uint32_t(std::min<uint64_t>(nbytes / std::max<uint64_t>(1, nq), 1u << 30));
     v.b_lo = c.b0;
     v.b_hi = c.b1;
+    // locate: when pass 2 will be the gather from the unsampled array, queries finished in the text are stored as
+    // their text position (decided here, once, and remembered in the workspace for locate_chunk_walk)
+    v.locate_positions = mode == OUT_SP_CNT_U32 && locate_positions_ok(r.view, v);
+    ws->sp_cnt_positions = v.locate_positions;
     ws->gpu_probe_bytes = 0;
     const bool time_kernel = qs.pinned && !qs.crumbs && nbytes >= (8u << 20);  // PackBalance: what the GPU consumes
     if (time_kernel) {
@@ -565,8 +569,8 @@ uint64_t* locate_chunk_walk(Replica& r, Workspace* ws, uint64_t nq, uint64_t n_h
   if (n_hits == 0) return nullptr;
   IndexView view = r.view;
   const int lv = g_locate_variant.load(std::memory_order_relaxed);
-  if (lv != 0) view.full_sa = nullptr;      // 1, 2: walk
-  if (lv == 1) view.walk_blocks = nullptr;  // 1: to the file's row samples
+  if (lv != 0 && !ws->sp_cnt_positions) view.full_sa = nullptr;  // 1, 2: walk (unless pass 1 already wrote positions)
+  if (lv == 1) view.walk_blocks = nullptr;                        // 1: to the file's row samples
   const void* d_sp_cnt = ws->d_out;
   uint64_t* d_hits = nullptr;
   CU(cudaMallocAsync(reinterpret_cast<void**>(&d_hits), n_hits * 16 + 16, st));  // pool: no driver round trip
@@ -1265,6 +1269,8 @@ int awry_locate_device(const awry_index* ix, int replica, const uint8_t* d_qbyte
         v.avg_len = uint32_t(std::min<uint64_t>((ends[1] - ends[0]) / nq, 1u << 30));
         v.b_lo = ends[0];
         v.b_hi = ends[1];
+        v.locate_positions = locate_positions_ok(r.view, v);
+        ws->sp_cnt_positions = v.locate_positions;
         CU(launch_search(r.view, ws->d_qwords - 4 * (ends[0] >> sh), d_qoff, nq, OUT_SP_CNT_U32, ws->d_out, ws->d_defer, v, r.sm_count, st));
       }
       uint64_t n = 0;

@@ -140,6 +140,10 @@ inline SearchVariant current_variant() {
   v.finish_in_text = g_count_variant.load(std::memory_order_relaxed) == 0;
   return v;
 }
+// locate pass 1 may store text positions (CNT_AT_TEXT_POS) when pass 2 will be the gather from the unsampled array
+inline bool locate_positions_ok(const IndexView& view, const SearchVariant& v) {
+  return view.rtext && view.full_sa && v.finish_in_text && g_locate_variant.load(std::memory_order_relaxed) == 0;
+}
 inline void store_variant(int lanes, int tpb, int blocks_per_sm, int slots) {
   g_variant_bits.store(uint64_t(uint16_t(lanes + 1)) | (uint64_t(uint16_t(tpb)) << 16) | (uint64_t(uint16_t(blocks_per_sm)) << 32) |
                            (uint64_t(uint8_t(slots + 1)) << 48),
@@ -154,6 +158,8 @@ struct Workspace {
   cudaStream_t st = nullptr;
   cudaEvent_t done = nullptr;
   // pinned staging
+  bool sp_cnt_positions = false;  // the (sp, count) pairs in d_out may hold text positions (CNT_AT_TEXT_POS): pass 2
+                                  // must be the gather from the unsampled array
   uint8_t* h_qbytes = nullptr;
   size_t h_qbytes_cap = 0;
   uint64_t* h_qoff = nullptr;

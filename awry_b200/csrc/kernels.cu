@@ -1241,11 +1241,15 @@ __global__ void __launch_bounds__(TPB, MINB)
           }
           ok = !__any_sync(gmask, bad != 0u);
         }
-        left = 0;  // finished either way: one row (count 1) or
-        if (!ok) {  // empty
-          sp = 1;
-          ep = 0;
+        // finished either way -- one hit or none -- and stored here: the group draws a new query next iteration
+        if (sub == 0) {
+          if (MODE == OUT_COUNT_U64)
+            reinterpret_cast<uint64_t*>(out)[cur] = ok ? 1ull : 0ull;
+          else  // OUT_SP_CNT_U32 for a gather pass 2: the hit's text position itself
+            reinterpret_cast<uint2*>(out)[cur] = ok ? make_uint2(p - left, CNT_AT_TEXT_POS) : make_uint2(1u, 0u);
         }
+        cur = NONE;
+        left = 0;
       }
     }
   }
@@ -1652,6 +1656,9 @@ static cudaError_t launch_search_pair(const IndexView& ix, const uint64_t* d_qwo
     return 0;
   }();
   const int slots = v.slots >= 0 ? v.slots : slots_default;
+  // locate pass 1 for a gather pass 2: the same, the hit stored as its text position
+  if (MODE == OUT_SP_CNT_U32 && v.finish_in_text && v.locate_positions && ix.rtext != nullptr && ix.full_sa != nullptr)
+    return launch_search_pair_b<OUT_SP_CNT_U32, 6, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, br);
   // count mode with the text on the device: finish one-row intervals by comparing with the text (see the kernel)
   if (MODE == OUT_COUNT_U64 && v.finish_in_text && ix.rtext != nullptr && ix.full_sa != nullptr) {
     if (slots == 1) return launch_search_pairx_b<OUT_COUNT_U64, 8, 1, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, sm_count, s, v.avg_len, br);

@@ -18,6 +18,9 @@ inline uint64_t packed_words(int alphabet, uint64_t nq, uint64_t total_bytes) {
 inline int packed_unit_shift(int alphabet) { return alphabet == 0 ? 6 : 5; }
 
 enum SearchOut { OUT_COUNT_U64 = 0, OUT_RANGE_U64 = 1, OUT_SP_CNT_U32 = 2 };
+// OUT_SP_CNT_U32 with SearchVariant::locate_positions: count field of a query that was finished in the text -- it has ONE
+// hit and the first field is its text position, not a BWT row (a real count is at most bwt_len - 1 < 2^32 - 257)
+constexpr uint32_t CNT_AT_TEXT_POS = 0xffffffffu;
 
 struct SearchVariant {
   int lanes = 0;          // nucleotide: 1, 2, 4 lanes per query on the 1-step blocks; 8 = pair-index
@@ -28,6 +31,8 @@ struct SearchVariant {
                           // query slots per lane group; -1 = default (AWRY_B200_SLOTS, else the measured winner)
   bool finish_in_text = true;  // count mode, pair kernel: finish one-row intervals by comparing with the text
                                // (IndexView::rtext) instead of stepping on (awry_set_count_variant)
+  bool locate_positions = false;  // OUT_SP_CNT_U32, pair kernel: a query finished in the text is stored as (text position,
+                                  // CNT_AT_TEXT_POS) -- only for callers whose pass 2 is the gather from the unsampled array
   uint32_t avg_len = 0;   // mean query length of the batch (0 = unknown): sizes the tickets of the dynamic hand-out
   uint64_t b_lo = 0, b_hi = ~0ull;  // byte range of the batch's queries: offsets outside it are refused (see launch_pack)
 };

@@ -18,7 +18,9 @@ namespace awry {
 struct CountOf {
   const uint2* r;
   uint64_t nq;
-  __host__ __device__ uint64_t operator()(uint64_t i) const { return i < nq ? uint64_t(r[i].y) : 0ull; }
+  __host__ __device__ uint64_t operator()(uint64_t i) const {
+    return i < nq ? (r[i].y == CNT_AT_TEXT_POS ? 1ull : uint64_t(r[i].y)) : 0ull;
+  }
 };
 
 // exclusive scan of the per-query hit counts -> CSR offsets, d_hit_off[nq] = total
@@ -640,10 +642,12 @@ __global__ void __launch_bounds__(256)
       cnt = r.y;
       off = hit_off[q];
     }
+    const bool at_pos = cnt == CNT_AT_TEXT_POS;  // finished in the text by the search kernel: sp IS the position
+    if (at_pos) cnt = 1;
     uint32_t small = cnt < 8 ? cnt : 8;
     for (uint32_t i = 0; i < small; i++) {
-      AWRY_CHK(uint64_t(sp) + i < ix.n_full_sa);
-      uint64_t loc = __ldg(full + sp + i);
+      AWRY_CHK(at_pos || uint64_t(sp) + i < ix.n_full_sa);
+      uint64_t loc = at_pos ? uint64_t(sp) : uint64_t(__ldg(full + sp + i));
       if (MAP)
         map_location(ix, loc, out + SLOT * (off + i));
       else
@@ -702,11 +706,13 @@ __global__ void __launch_bounds__(256)
       off = hbase + local_off[q];
       off_out[q] = off;
     }
+    const bool at_pos = cnt == CNT_AT_TEXT_POS;  // finished in the text by the search kernel: sp IS the position
+    if (at_pos) cnt = 1;
     uint32_t small = cnt < 8 ? cnt : 8;
     for (uint32_t i = 0; i < small; i++) {
       uint64_t pr[2];
-      AWRY_CHK(uint64_t(sp) + i < ix.n_full_sa);
-      map_location(ix, __ldg(full + sp + i), pr);
+      AWRY_CHK(at_pos || uint64_t(sp) + i < ix.n_full_sa);
+      map_location(ix, at_pos ? uint64_t(sp) : uint64_t(__ldg(full + sp + i)), pr);
       if (off + i < capacity) out[off + i] = make_ulonglong2(pr[0], pr[1]);
     }
     uint32_t big = __ballot_sync(0xffffffffu, cnt > 8);

@@ -352,6 +352,8 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
           v.avg_len = uint32_t(std::min<uint64_t>(plan.seq_bytes / nq, 1u << 30));
           v.b_lo = 0;
           v.b_hi = plan.seq_bytes;
+          v.locate_positions = locate && locate_positions_ok(r.view, v);
+          ws->sp_cnt_positions = v.locate_positions;
           CU(launch_search(r.view, ws->d_qwords, d_qoff, nq, locate ? OUT_SP_CNT_U32 : OUT_COUNT_U64, ws->d_out, ws->d_defer,
                            v, r.sm_count, st));
         }

@@ -96,6 +96,47 @@ def test_counts_equal_backward_search_and_the_oracle(po, multi, multi_dev):
     assert np.array_equal(multi_dev.count_prepacked(crumbs, qo, exc), want)
 
 
+def test_locate_through_the_text_equals_the_oracle(po, multi, multi_dev):
+    """locate pass 1 stores a query finished in the text as its text position (CNT_AT_TEXT_POS) and pass 2 -- the
+    gather from the unsampled array -- passes it through: same CSR offsets and hits as the oracle, through the
+    owned-buffer call, the caller-buffer call (hits written by the gather kernel into pinned memory), the
+    pre-packed call, sorted output, and with the walks (locate variants 1 / 2: pass 1 then keeps rows)"""
+    import torch
+    from awry_b200 import fm_index as f
+    orc = oracle_from_parts(po, multi)
+    qb, qo = queries_of_every_kind(multi, 30_000, seed=5)
+    woff, whits, _ = orc.locate_batch(qb, qo)
+    soff, shits, _ = orc.locate_batch(qb, qo, sorted_hits=True)
+    assert (np.diff(woff.astype(np.int64)) == 1).sum() > 4_000
+
+    def pinned(shape):
+        return torch.zeros(shape, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+
+    for count_variant in (0, 1):
+        f.set_count_variant(count_variant)
+        try:
+            for lv in (0, 1, 2):
+                f.set_locate_variant(lv)
+                off, hits = multi_dev.locate_packed(qb, qo)
+                assert np.array_equal(off, woff) and np.array_equal(hits, whits), (count_variant, lv)
+            f.set_locate_variant(0)
+            off, hits = multi_dev.locate_packed(qb, qo, sorted_hits=True)
+            assert np.array_equal(off, soff) and np.array_equal(hits, shits)
+            hoff, hh = pinned(len(qo)), pinned((len(whits) + 3, 2))
+            pq, pqo = torch.from_numpy(qb).pin_memory().numpy(), pinned(len(qo))
+            pqo[:] = qo
+            n = multi_dev.locate_packed_into(pq, pqo, hoff, hh)
+            assert n == len(whits) and np.array_equal(hoff, woff) and np.array_equal(hh[:n], whits)
+            crumbs, exc = f.host_pack_dna(qb)
+            hoff[:] = 0
+            hh[:] = 0
+            n = multi_dev.locate_prepacked_into(crumbs, qo, exc, hoff, hh)
+            assert n == len(whits) and np.array_equal(hoff, woff) and np.array_equal(hh[:n], whits)
+        finally:
+            f.set_count_variant(0)
+            f.set_locate_variant(0)
+
+
 def test_every_length_and_every_mismatch_position(po, fx):
     """one read of every length 1 .. 330 from one place, exact and with the substitution walked over every
     position of a 300-symbol read: the comparison starts at every alignment of query words against text words"""
