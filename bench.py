@@ -55,6 +55,9 @@ def parse_args():
     ap.add_argument("--ref-reads-per-step", type=int, default=1_000_000)
     ap.add_argument("--locate-reads", type=int, default=1_000_000, help="cfg3: queries of the locate leg")
     ap.add_argument("--locate-len", type=int, default=50)
+    ap.add_argument("--count-variant", type=int, default=0, choices=[0, 1],
+                    help="0 = the library's default count path (one-row intervals finished in the text), 1 = backward "
+                         "search to the last symbol for the headline leg too (ncu captures of that kernel)")
     ap.add_argument("--no-locate", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -148,17 +151,23 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
 
 
-def traffic_from_profiles(kernel):
+def traffic_from_profiles(kernel, in_text=None):
     """DRAM bytes per launch of a kernel from the committed `ncu --set full` capture of this bench command
-    (profiles/kernel_traffic.json, written by scripts/ncu_summary.py), or None"""
+    (profiles/*_traffic.json, written by scripts/ncu_summary.py), or None.  `in_text`: the pair kernel exists
+    with (last template argument 1) and without (0, or absent in captures older than the argument) the
+    finish-in-the-text step."""
     import glob
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))):
         try:
             d = json.load(open(path))
         except Exception:
             continue
-        if str(d.get("kernel", "")).startswith(kernel) and d.get("dram_bytes_per_launch"):
-            return d
+        name = str(d.get("kernel", ""))
+        if not name.startswith(kernel) or not d.get("dram_bytes_per_launch"):
+            continue
+        if in_text is not None and name.rstrip().endswith(", 1>") != in_text:
+            continue
+        return d
     return None
 
 
@@ -628,6 +637,8 @@ def main():
         ix.count_device(d_q.data_ptr(), d_off.data_ptr(), nq, d_cnt.data_ptr(), stream)
 
     # ---- kernel-only figure: inputs resident in HBM, CUDA events on the launching stream
+    f.set_count_variant(a.count_variant)
+    in_text = a.count_variant == 0 and dev_bytes.get("text", 0) > 0   # the default path finishes one-row intervals in the text
     for _ in range(max(a.warmup, 3)):
         step_device()
     barrier()
@@ -655,6 +666,37 @@ def main():
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_max = float(t_ms.item())
     value = world * nq * a.steps / (ms_max * 1e-3)
+
+    # ---- the same leg with backward search to the last symbol (awry_set_count_variant(1)): the kernel the
+    # north star describes, one block read per two symbols of every read; same counts
+    lf_only = None
+    if in_text:
+        d_cnt_lf = torch.zeros(nq, dtype=torch.int64, device="cuda")
+        f.set_count_variant(1)
+        try:
+            for _ in range(3):
+                ix.count_device(d_q.data_ptr(), d_off.data_ptr(), nq, d_cnt_lf.data_ptr(), stream)
+            barrier()
+            f.profile_enable(True)
+            f.profile_reset()
+            l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0.record()
+            for _ in range(a.steps):
+                ix.count_device(d_q.data_ptr(), d_off.data_ptr(), nq, d_cnt_lf.data_ptr(), stream)
+            l1.record()
+            barrier()
+            prof_lf = f.profile_get()
+            f.profile_enable(False)
+        finally:
+            f.set_count_variant(0)
+        t_l = torch.tensor([l0.elapsed_time(l1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_l, op=dist.ReduceOp.MAX)
+        lf_only = {"value": world * nq * a.steps / (float(t_l.item()) * 1e-3), "unit": "reads/s",
+                   "ms_per_step": float(t_l.item()) / a.steps,
+                   "kernel_ms": prof_lf["search_ms"] / max(1, prof_lf["search_launches"]),
+                   "counts_equal_default_path": bool(torch.equal(d_cnt_lf, d_cnt))}
+        del d_cnt_lf
 
     # ---- end-to-end figure: C-ABI call with pinned HOST buffers, H2D + D2H inside the timed region
     e2e = e2e_packed = None
@@ -853,38 +895,57 @@ def main():
     peak, peak_src = measured_peak()
     alg_bytes_per_launch = nq * (L + 8 + 16 + ALG_BYTES_PER_BLOCK * touches_per_read)
     search_ms = prof["search_ms"] / max(1, prof["search_launches"])
-    tr = traffic_from_profiles("search_dna_pair_kernel")
     std_cfg = nq == 10_000_000 and L == 150 and a.kmer == 13 and a.text_len == 3_100_000_000
-    accesses = nq * (((L - a.kmer) + 1) // 2 + 1)          # pair steps (+ odd tail) + seed lookup
-    if tr and std_cfg:
-        traffic, traffic_src = float(tr["dram_bytes_per_launch"]), f"ncu --set full capture of this command ({tr.get('source')})"
-    else:
-        traffic, traffic_src = float(nq * ((((L - a.kmer) + 1) // 2) * 1.006 * 128 + 200)), "estimate: 128 B per block read + ~200 B per read"
-    achieved = traffic / (search_ms * 1e-3) / 1e9
-    gather = None
+    lf_accesses = nq * (((L - a.kmer) + 1) // 2 + 1)          # pair steps (+ odd tail) + seed lookup
+    g_reads = g_gbs = None
+    gather_err = None
     if rank == 0:
         try:   # the "random-access HBM roofline" of the north star: independent random 128-B reads
             # 4 lanes x LDG.256 per read, 4 in flight per lane group, 16 waves of blocks so the hardware
             # balances the SMs (a static split stops at 37.8 G reads/s: it ends with the slowest SM)
             g_reads, g_gbs = f.bench_random_gather(local_rank, 4 << 30, 128, 3164, 400_000_000, 2)
-            gather = {"granule_bytes": 128, "reads_per_s": g_reads, "gb_per_s": g_gbs,
-                      "kernel_block_reads_per_s": accesses / (search_ms * 1e-3),
-                      "frac_of_random_gather": accesses / (search_ms * 1e-3) / g_reads}
         except Exception as e:  # noqa: BLE001
-            gather = {"error": str(e)}
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": traffic_src,
+            gather_err = str(e)
+
+    def roofline_of(kernel_ms, text_path, share):
+        """physical roofline of one flavour of the count kernel: ncu DRAM bytes per launch / its mean launch time"""
+        tr = traffic_from_profiles("search_dna_pair_kernel", in_text=text_path)
+        if tr and std_cfg:
+            traffic, src = float(tr["dram_bytes_per_launch"]), f"ncu --set full capture of this command ({tr.get('source')})"
+        elif text_path:
+            traffic, src = float(nq * 940), "estimate: ~7.3 lines of 128 B per read (seed entry, 2-3 pair blocks, SA element, 1-2 lines of text, the read itself)"
+        else:
+            traffic, src = float(nq * ((((L - a.kmer) + 1) // 2) * 1.006 * 128 + 200)), "estimate: 128 B per block read + ~200 B per read"
+        achieved = traffic / (kernel_ms * 1e-3) / 1e9
+        lines = traffic / 128 if text_path else float(lf_accesses)
+        gather = {"error": gather_err} if g_reads is None else {
+            "granule_bytes": 128, "reads_per_s": g_reads, "gb_per_s": g_gbs,
+            "kernel_line_reads_per_s": lines / (kernel_ms * 1e-3),
+            "line_reads_counted_as": "DRAM bytes / 128" if text_path else "block reads issued: pair steps + seed lookup per read",
+            "frac_of_random_gather": lines / (kernel_ms * 1e-3) / g_reads}
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "traffic_source": src,
                 "traffic_check": "ok" if achieved <= 1.05 * peak else "FAILED: physical traffic above the stream peak",
                 "peak_source": peak_src,
-                "kernel": "search_dna_pair_kernel", "kernel_ms": search_ms,
-                "kernel_share_of_step": prof["search_ms"] / ms_total,
+                "kernel": "search_dna_pair_kernel<count, 256, 6, %s>" % ("finish in the text" if text_path else "backward search only"),
+                "kernel_ms": kernel_ms, "kernel_share_of_step": share,
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch,
-                "algorithmic_equivalent_gbs": alg_bytes_per_launch / (search_ms * 1e-3) / 1e9,
-                "lf_steps_per_s": nq * (L - a.kmer) / (search_ms * 1e-3), "random_gather_roofline": gather,
-                "note": "achieved / frac are physical DRAM traffic over the stream peak; algorithmic_equivalent_gbs counts "
-                        "the reference algorithm's bytes (104 B per LF step, SURVEY 8(d)) -- two LF steps ride on one "
-                        "128-B pair-block read, so it may exceed the peak; frac_of_random_gather compares block reads/s "
-                        "with the random 128-B gather probe of this run"}
+                "algorithmic_equivalent_gbs": alg_bytes_per_launch / (kernel_ms * 1e-3) / 1e9,
+                "lf_steps_per_s_equivalent": nq * (L - a.kmer) / (kernel_ms * 1e-3), "random_gather_roofline": gather}
+
+    roofline = roofline_of(search_ms, in_text, prof["search_ms"] / ms_total)
+    roofline["note"] = (
+        "achieved / frac are physical DRAM traffic over the stream peak.  The default count path stops stepping once a read's "
+        "interval is one row wide: it reads SA[row] and compares the rest of the read with the text (4 bits per symbol, on the "
+        "device) -- ~7 line reads per 150-bp read instead of ~70, identical counts; `lf_only` is the same leg with backward "
+        "search to the last symbol (the kernel the north star describes) and carries its own roofline.  "
+        "algorithmic_equivalent_gbs counts the reference algorithm's bytes (104 B per LF step, SURVEY 8(d)) over the kernel "
+        "time: not a fraction of anything") if in_text else (
+        "achieved / frac are physical DRAM traffic over the stream peak; algorithmic_equivalent_gbs counts the reference "
+        "algorithm's bytes (104 B per LF step, SURVEY 8(d)) -- two LF steps ride on one 128-B pair-block read, so it may exceed "
+        "the peak; frac_of_random_gather compares block reads/s with the random 128-B gather probe of this run")
+    if lf_only:
+        lf_only["roofline"] = roofline_of(lf_only["kernel_ms"], False, lf_only["kernel_ms"] / lf_only["ms_per_step"])
 
     # ---- BASELINE cfg4 / cfg5 as secondary legs (one GPU)
     cfg4 = cfg5 = None
@@ -939,7 +1000,10 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": config_of(a), "setup": {"setup_s": round(setup_s, 1), "fixture_build_s": phases.get("total"),
                                               "index_device_bytes": dev_bytes},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e_line, "clocks": clocks,
+            "count_path": ("backward search until the interval is one row wide, then SA[row] and a comparison of the rest of "
+                           "the read with the text on the device (bit-exact; `lf_only` = backward search to the last symbol)"
+                           if in_text else "backward search to the last symbol"),
+            "roofline": roofline, "lf_only": lf_only, "cpu_baseline": cpu_baseline, "e2e": e2e_line, "clocks": clocks,
             "gpu_launches": int(prof["launches"]), "parity_vs_oracle_on_sample": parity,
             "e2e_prepacked": (inproc or {}).get("prepacked") or e2e_packed,
             "e2e_per_process": e2e if world > 1 else None,

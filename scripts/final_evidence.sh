@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-end evidence in ONE gpurun call (one GPU): GPU tests, the default bench line (+ the reference arm's line),
-# `ncu --set full` of the dominant kernel and of the protein kernel, and the ncu launch list of a short bench run.
+# `ncu --set full` of the dominant kernel (both flavours: finish in the text / backward search only) and of the protein kernel, and the ncu launch list of a short bench run.
 # Each ncu pass runs only after the same program has exited 0 without ncu.  Outputs land in gpurun_out/<tag>_*;
 # scripts/ncu_summary.py turns them into profiles/.
 #   gpurun --timeout 900 -- 'bash scripts/final_evidence.sh r02'
@@ -18,6 +18,9 @@ cut -c1-300 gpurun_out/${T}_bench_reference.json
 timeout 150 ncu --set full --clock-control none --import-source on -k regex:search_dna_pair_kernel -s 3 -c 1 -f \
   -o gpurun_out/${T}_prof python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-locate --no-e2e --no-secondary \
   > gpurun_out/${T}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 150 ncu --set full --clock-control none --import-source on -k regex:search_dna_pair_kernel -s 3 -c 1 -f \
+  -o gpurun_out/${T}_prof_lf python bench.py --steps 1 --warmup 3 --count-variant 1 --no-cpu-baseline --no-locate --no-e2e --no-secondary \
+  > gpurun_out/${T}_ncu_full_lf.log 2>&1; echo "ncu full (backward search only) rc=$?"
 timeout 60 python scripts/cfg4_ncu_target.py > gpurun_out/${T}_cfg4_target.log 2>&1 && \
 timeout 150 ncu --set full --clock-control none --import-source on -k regex:search_amino_kernel -s 2 -c 1 -f \
   -o gpurun_out/${T}_prof_amino python scripts/cfg4_ncu_target.py > gpurun_out/${T}_ncu_amino.log 2>&1; echo "ncu amino rc=$?"
