@@ -1064,6 +1064,11 @@ __global__ void __launch_bounds__(TPB, MINB)
   uint32_t sp = 1, ep = 0, left = 0, len = 0, nwords = 0;
   uint32_t ubase = 0;  // word index of the query's packed symbols
   uint32_t wlim = 8;   // word index at which the ring slides by 8 words
+  // VFY: a query lives for ~8 loads, so the latency of the ticket atomic was 16 % of the warp-stall samples
+  // (profiles/r02p_search_text_full.md): the warp draws its NEXT ticket when it starts on the current one and
+  // looks at the result only when the pool runs dry (lane 0 holds it)
+  uint32_t ahead = 0;
+  if (VFY && lane == 0) ahead = atomicAdd(ticket, ticket_sz);
 
   // Every lane of the warp runs every iteration (the loop exit is a warp vote), so the rank
   // reduction can use full-mask shuffles; a group whose query ended refills in the same iteration.
@@ -1076,7 +1081,12 @@ __global__ void __launch_bounds__(TPB, MINB)
       uint32_t b = 0, got = 0;
       if (n_want > avail && more) {
         uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(ticket, ticket_sz);
+        if (VFY) {
+          t = ahead;
+          if (lane == 0 && t < nq32) ahead = atomicAdd(ticket, ticket_sz);
+        } else if (lane == 0) {
+          t = atomicAdd(ticket, ticket_sz);
+        }
         t = __shfl_sync(FULL, t, 0);
         b = t;
         got = t < nq32 ? (nq32 - t < ticket_sz ? nq32 - t : ticket_sz) : 0u;
@@ -1177,12 +1187,17 @@ __global__ void __launch_bounds__(TPB, MINB)
     // A pair step always starts on an EVEN symbol index (an odd start takes one single-symbol step
     // first), so both symbols are one byte of the ring: low nibble = symbol pos, high nibble = pos + 1.
     const uint32_t qb = reinterpret_cast<const uint8_t*>(ring)[(pos >> 1) & 127];
-    const bool two = left >= 2 && (pos & 1) == 0;
+    // VFY: a query takes two or three steps in all, so the single-symbol step an odd seed length asks for would
+    // be one of its ~8 dependent loads; there the two symbols are cut out of two ring bytes instead (the word
+    // behind the current one is always in the ring: it slides only when `pos` enters word wlim)
+    const bool two = VFY ? left >= 2 : (left >= 2 && (pos & 1) == 0);
     const uint32_t pa = sp - 1, pb = ep;
     uint32_t ra = 0, rb = 0, base = 0;
     if (active) {
       if (two) {
-        const uint32_t pair = ((qb & 3u) << 2) | (qb >> 4);
+        uint32_t q2 = qb;
+        if (VFY) q2 = ((qb | (uint32_t(reinterpret_cast<const uint8_t*>(ring)[((pos >> 1) + 1) & 127]) << 8)) >> (4 * (pos & 1))) & 0xffu;
+        const uint32_t pair = ((q2 & 3u) << 2) | (q2 >> 4);
         const uint32_t ba = __umulhi(pa, 0xAAAAAAABu) >> 6;  // / 96
         const uint32_t la = pa - ba * PAIR_ROWS_PER_BLOCK, lb = pb - ba * PAIR_ROWS_PER_BLOCK;
         AWRY_CHK(uint64_t(ba) * PAIR_BLOCK_UINT4 + 7 < ix.n_pair_u4);
@@ -1658,7 +1673,7 @@ static cudaError_t launch_search_pair(const IndexView& ix, const uint64_t* d_qwo
   const int slots = v.slots >= 0 ? v.slots : slots_default;
   // locate pass 1 for a gather pass 2: the same, the hit stored as its text position
   if (MODE == OUT_SP_CNT_U32 && v.finish_in_text && v.locate_positions && ix.rtext != nullptr && ix.full_sa != nullptr)
-    return launch_search_pair_b<OUT_SP_CNT_U32, 6, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, br);
+    return launch_search_pair_b<OUT_SP_CNT_U32, 5, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, br);
   // count mode with the text on the device: finish one-row intervals by comparing with the text (see the kernel)
   if (MODE == OUT_COUNT_U64 && v.finish_in_text && ix.rtext != nullptr && ix.full_sa != nullptr) {
     if (slots == 1) return launch_search_pairx_b<OUT_COUNT_U64, 8, 1, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, sm_count, s, v.avg_len, br);
@@ -1667,8 +1682,11 @@ static cudaError_t launch_search_pair(const IndexView& ix, const uint64_t* d_qwo
     if (slots == 4) return launch_search_pairx_b<OUT_COUNT_U64, 4, 2, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, sm_count, s, v.avg_len, br);
     switch (v.blocks_per_sm) {
       case 4: return launch_search_pair_b<OUT_COUNT_U64, 4, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, br);
+      // 5 x 256 threads/SM: 48 registers hold the comparison without spills (at 6 x 256 = 40 registers two values
+      // live in local memory and a launch takes 3.6 instead of 2.5 ms, profiles/r02_s8_text_finish_probe.log)
+      case 6: return launch_search_pair_b<OUT_COUNT_U64, 6, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, br);
       case 8: return launch_search_pair_b<OUT_COUNT_U64, 8, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, br);
-      default: return launch_search_pair_b<OUT_COUNT_U64, 6, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, br);
+      default: return launch_search_pair_b<OUT_COUNT_U64, 5, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, br);
     }
   }
   // the state-machine variant, kept selectable for A/B runs with its two best residencies (see the kernel)
