@@ -236,7 +236,7 @@ void enqueue_search(const awry_index* ix, Replica& r, PackBalance& bal, Workspac
   Workspace::grow_dev(ws->d_qoff, ws->d_qoff_cap, size_t(nq) + 1);
   Workspace::grow_dev(ws->d_qwords, ws->d_qwords_cap, size_t(packed_words(ix->alphabet, nq, nbytes)));
   Workspace::grow_dev(ws->d_out, ws->d_out_cap, size_t(nq) * out_elem);
-  Workspace::grow_dev(ws->d_defer, ws->d_defer_cap, size_t(nq) + 2);
+  Workspace::grow_dev(ws->d_defer, ws->d_defer_cap, defer_words(nq));
   const uint64_t* src_o = qs.qoff + c.q0;
   uint64_t* const d_words = ws->d_qwords - 4 * (c.b0 >> ush);
   ws->link_probe_bytes = 0;
@@ -1216,7 +1216,7 @@ int awry_count_device(const awry_index* ix, int replica, const uint8_t* d_qbytes
     const int sh = packed_unit_shift(ix->alphabet);
     uint64_t words = 4 * (nq + ((ends[1] >> sh) - (ends[0] >> sh)) + 2) + 32;
     uint64_t* d_qwords = nullptr;  // packed queries, then the deferred-query list
-    CU(cudaMallocAsync(reinterpret_cast<void**>(&d_qwords), words * 8 + (nq + 2) * 4, st));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&d_qwords), words * 8 + defer_words(nq) * 4, st));
     uint32_t* d_defer = reinterpret_cast<uint32_t*>(d_qwords + words);
     {
       ProfScope p(2, r.device, st);
@@ -1258,7 +1258,7 @@ int awry_locate_device(const awry_index* ix, int replica, const uint8_t* d_qbyte
       uint64_t words = 4 * (nq + ((ends[1] >> sh) - (ends[0] >> sh)) + 2) + 32;
       Workspace::grow_dev(ws->d_qwords, ws->d_qwords_cap, size_t(words));
       Workspace::grow_dev(ws->d_out, ws->d_out_cap, size_t(nq) * sp_cnt_bytes(r.view));
-      Workspace::grow_dev(ws->d_defer, ws->d_defer_cap, size_t(nq) + 2);
+      Workspace::grow_dev(ws->d_defer, ws->d_defer_cap, defer_words(nq));
       {
         ProfScope p(2, r.device, st);
         CU(launch_pack(ix->alphabet, d_qbytes, d_qoff, nq, ws->d_qwords - 4 * (ends[0] >> sh), ends[0], ends[1], r.d_async_flag, st));

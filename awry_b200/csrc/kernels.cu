@@ -1031,7 +1031,9 @@ __device__ __forceinline__ PairSlice pair_slice(const u32x8& x, uint32_t sub, ui
 // spells the rest of the query) or become empty (fm_index.rs:409-416 with update_range_with_symbol, :559-582).
 constexpr uint32_t VERIFY_MIN_LEFT = 8;
 
-template <int MODE, int TPB, int MINB, bool VFY = false>
+// LIST: the queries to run are the ones search_dna_wave_kernel left over (defer + nq + 2: count, ticket counter,
+// then the query numbers), handed out from that ticket counter.
+template <int MODE, int TPB, int MINB, bool VFY = false, bool LIST = false>
 __global__ void __launch_bounds__(TPB, MINB)
     search_dna_pair_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
                            const uint64_t* __restrict__ qoff, uint64_t nq, void* __restrict__ out,
@@ -1046,7 +1048,8 @@ __global__ void __launch_bounds__(TPB, MINB)
   const uint32_t gbase = (threadIdx.x & 31) - sub;
   const uint32_t gmask = 0xfu << gbase;
   uint64_t* const ring = s_q[threadIdx.x / LANES];
-  const uint32_t nq32 = uint32_t(nq);
+  const uint32_t* const rest = defer + nq + 2;
+  const uint32_t nq32 = LIST ? rest[0] : uint32_t(nq);
   // Queries are handed out dynamically from a counter behind the deferred list (defer[nq + 1]): with a
   // static stride every SM gets the same share and the kernel ends when the slowest SM does -- on B200 the
   // SMs do not all see the same random-access throughput (the gather probe's SMs are busy between 52 % and
@@ -1056,7 +1059,7 @@ __global__ void __launch_bounds__(TPB, MINB)
   // `ticket_sz` queries.  So the counter sees one atomic per warp-ticket however the 8 groups of the warp
   // drift apart (a per-group grab collapses once reads that end early dephase the groups: same-address
   // atomics retire at ~0.5 G/s), and at the end of the batch at most ticket_sz - 1 queries wait in a pool.
-  uint32_t* const ticket = defer + nq + 1;
+  uint32_t* const ticket = LIST ? defer + nq + 3 : defer + nq + 1;
   const uint32_t lane = threadIdx.x & 31;
   uint32_t pn = 0, pe = 0;  // the warp's pool of query numbers
   bool more = true;         // the counter has not run past nq yet
@@ -1109,7 +1112,7 @@ __global__ void __launch_bounds__(TPB, MINB)
       cur = NONE;
       left = 0;
       if (next_q != NONE) {
-        cur = next_q;
+        cur = LIST ? rest[2 + next_q] : next_q;
         uint64_t ov = qoff[cur + (sub & 1)];  // lanes 0/1 fetch both ends with one request
         uint64_t o0 = __shfl_sync(gmask, ov, gbase), o1 = __shfl_sync(gmask, ov, gbase + 1);
         len = checked_len(o0, o1, br);
@@ -1265,6 +1268,191 @@ __global__ void __launch_bounds__(TPB, MINB)
         }
         cur = NONE;
         left = 0;
+      }
+    }
+  }
+}
+
+// ---- nucleotide wave kernel (count / locate pass 1 with the text on the device) ----
+// With "finish in the text" a 150-bp read is a chain of ~8 dependent loads of seven kinds -- its offsets, its
+// packed words, its seed entry, two or three pair blocks, one suffix-array element, one or two lines of text --
+// and search_dna_pair_kernel<VFY>, whose lane groups refill one by one, spends its time with the 8 groups of a
+// warp in 8 different phases: every phase's load is issued alone, inside a branch the other groups wait behind
+// (13.7 of 32 lanes active per instruction, 19 warps per issue slot waiting on a load,
+// profiles/r02p_search_text_full.md).  Here a warp takes 8 queries at a time and walks them through the phases
+// TOGETHER: every phase is one straight piece of code whose 8 loads go out side by side, the votes are full-warp
+// ballots, and nothing is refilled in between -- the queries of a wave need the same few steps, so a wave ends
+// together.  Queries that do not fit the pattern are handed on instead of stalling their wave: more than
+// WAVE_MAX_STEPS steps with the interval still wider than one row (repeats), or more than 256 symbols -> the
+// `rest` list, searched afterwards by search_dna_pair_kernel<VFY, LIST>; an ambiguity symbol -> the scalar kernel.
+// Both block reads of an interval that straddles two blocks are issued before either is used.
+constexpr int WAVE_MAX_STEPS = 6;
+
+template <int MODE, int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB)
+    search_dna_wave_kernel(IndexView ix, const uint64_t* __restrict__ qwords, const uint64_t* __restrict__ qoff,
+                           uint64_t nq, void* __restrict__ out, uint32_t* __restrict__ defer, uint32_t ticket_sz,
+                           ByteRange br) {
+  constexpr uint32_t FULL = 0xffffffffu;
+  enum : uint32_t { W_NONE = 0, W_RUN = 1, W_EMPTY = 2 };  // no query (or handed on) / in progress / refused by the prepass
+  __shared__ uint64_t s_q[TPB / 4][16];
+  const uint32_t lane = threadIdx.x & 31, sub = lane & 3, gbase = lane - sub, gmask = 0xfu << gbase, grp = lane >> 2;
+  uint64_t* const ring = s_q[threadIdx.x >> 2];
+  const uint32_t nq32 = uint32_t(nq);
+  uint32_t* const ticket = defer + nq + 1;
+  uint32_t* const rest = defer + nq + 2;  // rest[0] = count, rest[2 ..] = query numbers
+  uint32_t pn = 0, pe = 0;                // the warp's pool of query numbers (identical in all lanes)
+  uint32_t ahead = 0;                     // the warp's NEXT ticket, drawn while the current one is worked on (lane 0)
+  if (lane == 0) ahead = atomicAdd(ticket, ticket_sz);
+  for (;;) {
+    if (pn == pe) {  // warp-uniform
+      uint32_t t = ahead;
+      if (lane == 0 && t < nq32) ahead = atomicAdd(ticket, ticket_sz);
+      t = __shfl_sync(FULL, t, 0);
+      if (t >= nq32) break;
+      pn = t;
+      pe = t + (nq32 - t < ticket_sz ? nq32 - t : ticket_sz);
+    }
+    const uint32_t q = pn + grp;
+    uint32_t st = q < pe ? W_RUN : W_NONE;
+    pn = pe - pn > 8u ? pn + 8u : pe;
+
+    // ---- offsets
+    uint64_t ov = 0;
+    if (st == W_RUN) ov = __ldg(qoff + q + (sub & 1));  // lanes 0/1 fetch both ends with one request
+    const uint64_t o0 = __shfl_sync(FULL, ov, gbase), o1 = __shfl_sync(FULL, ov, gbase + 1);
+    const uint32_t len = st == W_RUN ? checked_len(o0, o1, br) : 0u;
+    if (st == W_RUN && len == 0) st = W_EMPTY;
+    const uint32_t nwords = (len + 15) >> 4;
+    if (st == W_RUN && nwords > 16) {  // longer than the ring: the refilling kernel slides it
+      if (sub == 0) rest[2 + atomicAdd(rest, 1u)] = q;
+      st = W_NONE;
+    }
+    // ---- packed words -> ring; ambiguity symbols (code >= 4) are looked for here, once
+    uint32_t amb = 0;
+    __syncwarp();  // the previous wave's ring reads are done
+    if (st == W_RUN && 4 * sub < nwords) {
+      const uint32_t ubase = 4 * (q + uint32_t(o0 >> 6));
+      AWRY_CHK_QWORDS(ubase + 4 * sub, br, nq, 6);
+      const u32x8 t = ldg256(qwords + ubase + 4 * sub);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        ring[4 * sub + j] = uint64_t(t.v[2 * j]) | (uint64_t(t.v[2 * j + 1]) << 32);
+        if (4 * sub + j < nwords) amb |= (t.v[2 * j] | t.v[2 * j + 1]) & 0xCCCCCCCCu;
+      }
+    }
+    const uint32_t amb_groups = __ballot_sync(FULL, amb != 0);
+    __syncwarp();
+    if (st == W_RUN && (amb_groups & gmask) != 0) {  // the scalar kernel takes the whole query
+      if (sub == 0) defer[1 + atomicAdd(defer, 1u)] = q;
+      st = W_NONE;
+    }
+    // ---- seed
+    uint32_t sp = 1, ep = 0, left = 0;
+    if (st == W_RUN) {
+      const uint32_t k = ix.kmer_len;
+      const uint64_t w = ring[0];
+      if (k != 0 && len >= k) {  // k <= 16: inside word 0
+        const uint64_t idx = kmer_index(w, k);
+        AWRY_CHK(idx < ix.n_table);
+        const uint2 r = __ldg(ix.table + idx);
+        sp = r.x;
+        ep = r.y;
+        left = len - k;
+      } else {
+        const uint32_t c = uint32_t(w) & 15u;
+        sp = ix.c_lo[c];
+        ep = ix.c_hi[c];
+        left = len - 1;
+      }
+    }
+    // ---- steps, until every interval of the wave is one row wide (or empty, or its query is used up)
+#pragma unroll 1
+    for (int it = 0; it <= WAVE_MAX_STEPS; it++) {
+      const bool active = st == W_RUN && left != 0 && sp <= ep && !(sp == ep && left >= VERIFY_MIN_LEFT);
+      if (!__any_sync(FULL, active)) break;
+      if (it == WAVE_MAX_STEPS) {  // still wide: a repeat -- handed on, searched from its start by the refilling kernel
+        if (active) {
+          if (sub == 0) rest[2 + atomicAdd(rest, 1u)] = q;
+          st = W_NONE;
+        }
+        break;
+      }
+      const uint32_t pos = len - left;  // search-order index of the next symbol
+      const uint8_t* const rb8 = reinterpret_cast<const uint8_t*>(ring);
+      const uint32_t qb = rb8[(pos >> 1) & 127];
+      const bool two = left >= 2;
+      const uint32_t pa = sp - 1, pb = ep;
+      uint32_t ra = 0, rb = 0, base = 0;
+      if (active) {
+        if (two) {  // (the word behind the current one is in the ring: it holds the whole query)
+          const uint32_t q2 = ((qb | (uint32_t(rb8[((pos >> 1) + 1) & 127]) << 8)) >> (4 * (pos & 1))) & 0xffu;
+          const uint32_t pair = ((q2 & 3u) << 2) | (q2 >> 4);
+          const uint32_t ba = __umulhi(pa, 0xAAAAAAABu) >> 6, bb = __umulhi(pb, 0xAAAAAAABu) >> 6;  // / 96
+          AWRY_CHK(uint64_t(ba) * PAIR_BLOCK_UINT4 + 7 < ix.n_pair_u4 && uint64_t(bb) * PAIR_BLOCK_UINT4 + 7 < ix.n_pair_u4);
+          const u32x8 x = ldg256(ix.pair_blocks + size_t(ba) * PAIR_BLOCK_UINT4 + 2 * sub);
+          u32x8 y = x;
+          if (bb != ba) y = ldg256(ix.pair_blocks + size_t(bb) * PAIR_BLOCK_UINT4 + 2 * sub);
+          PairSlice s = pair_slice(x, sub, pair);
+          ra = __popc(s.match & low_mask(int(pa - ba * PAIR_ROWS_PER_BLOCK) + 1 - int(32 * sub))) + s.count;
+          if (bb != ba) s = pair_slice(y, sub, pair);
+          rb = __popc(s.match & low_mask(int(pb - bb * PAIR_ROWS_PER_BLOCK) + 1 - int(32 * sub))) + s.count;
+          base = ix.c2[pair];
+        } else {
+          const uint32_t c1 = (qb >> (4 * (pos & 1))) & 15u;
+          const uint32_t ba = pa >> 7, bb = pb >> 7;
+          LaneChunks<4> y;
+          AWRY_CHK(uint64_t(ba) * DNA_BLOCK_UINT4 + 3 < ix.n_blocks_u4 && uint64_t(bb) * DNA_BLOCK_UINT4 + 3 < ix.n_blocks_u4);
+          y.load(ix.blocks + size_t(ba) * DNA_BLOCK_UINT4, sub);
+          const uint32_t m0 = (c1 & 1) ? ~0u : 0u, m1 = (c1 & 2) ? ~0u : 0u;
+          ra = dna_partial_rank<4>(y, sub, pa & 127, c1, m0, m1);
+          if (bb != ba) y.load(ix.blocks + size_t(bb) * DNA_BLOCK_UINT4, sub);
+          rb = dna_partial_rank<4>(y, sub, pb & 127, c1, m0, m1);
+          base = ix.c_lo[c1];
+        }
+      }
+      ra += __shfl_xor_sync(FULL, ra, 1);
+      rb += __shfl_xor_sync(FULL, rb, 1);
+      ra += __shfl_xor_sync(FULL, ra, 2);
+      rb += __shfl_xor_sync(FULL, rb, 2);
+      if (active) {
+        sp = base + ra;
+        ep = base + rb - 1;
+        left -= two ? 2 : 1;
+      }
+    }
+    // ---- finish in the text: a one-row interval with symbols left (see search_dna_pair_kernel<VFY>)
+    const bool need = st == W_RUN && left != 0 && sp <= ep;  // (then sp == ep and left >= VERIFY_MIN_LEFT)
+    uint32_t p = 0;
+    if (need) {
+      AWRY_CHK(sp < ix.n_full_sa);
+      p = __ldg(ix.full_sa + sp);  // the matched suffix stands at text[p ..]
+    }
+    bool ok = need && p >= left;   // else the rest of the query would start before the text
+    uint32_t bad = 0;
+    if (ok) {
+      const uint32_t done = len - left;
+      const uint32_t rb0 = ix.bwt_len - p - done;  // reversed-text index of search-order symbol 0
+      const uint32_t s_first = (rb0 + done) >> 6, s_last = (rb0 + len - 1) >> 6;  // 32-B sectors = 64 symbols
+      for (uint32_t sec = s_first + sub; sec <= s_last; sec += 4) {
+        AWRY_CHK(uint64_t(sec) * 32 + 31 < ix.n_rtext);
+        const u32x8 t = ldg256(ix.rtext + size_t(sec) * 32);
+        bad |= text_sector_mismatch(t, ring, sec, rb0, done, len);
+      }
+    }
+    const uint32_t bad_groups = __ballot_sync(FULL, bad != 0);
+    ok = ok && (bad_groups & gmask) == 0;
+    // ---- results
+    if (sub == 0) {
+      if (st == W_EMPTY) {
+        store_result<MODE>(out, q, 1u, 0u);
+      } else if (st == W_RUN && !need) {
+        store_result<MODE>(out, q, sp, ep);
+      } else if (st == W_RUN) {  // one hit or none
+        if (MODE == OUT_COUNT_U64)
+          reinterpret_cast<uint64_t*>(out)[q] = ok ? 1ull : 0ull;
+        else  // OUT_SP_CNT_U32 for a gather pass 2: the hit's text position itself
+          reinterpret_cast<uint2*>(out)[q] = ok ? make_uint2(p - left, CNT_AT_TEXT_POS) : make_uint2(1u, 0u);
       }
     }
   }
@@ -1625,6 +1813,42 @@ static cudaError_t launch_search_pair_b(const IndexView& ix, const uint64_t* d_q
   return cudaGetLastError();
 }
 
+// the wave kernel, then the refilling kernel over the queries it handed on, then the scalar kernel over the
+// queries with ambiguity symbols (both lists are empty for a batch of clean sequencer reads)
+template <int MODE>
+static cudaError_t launch_search_wave(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff, uint64_t nq,
+                                      void* d_out, uint32_t* d_defer, int sm_count, cudaStream_t s, uint32_t avg_len,
+                                      ByteRange br) {
+  constexpr int TPB = 256, MINB = 5;
+  cudaError_t e = cudaMemsetAsync(d_defer + nq + 2, 0, 8, s);  // count of the rest list, its ticket counter
+  if (e != cudaSuccess) return e;
+  auto kern = search_dna_wave_kernel<MODE, TPB, MINB>;
+  auto kern_rest = search_dna_pair_kernel<MODE, TPB, MINB, true, true>;
+  int per_sm = 0, per_sm_rest = 0;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, 0)) != cudaSuccess) return e;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_rest, kern_rest, TPB, 0)) != cudaSuccess) return e;
+  const uint64_t need_blocks = (nq * 4 + TPB - 1) / TPB;
+  const unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * std::max(1, per_sm), need_blocks)));
+  const unsigned grid_rest = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * std::max(1, per_sm_rest), need_blocks)));
+  static const uint32_t ticket_env = [] {  // AWRY_B200_TICKET: fixed ticket size (experiments)
+    if (const char* e = getenv("AWRY_B200_TICKET")) return uint32_t(std::min(1024l, std::max(8l, strtol(e, nullptr, 10)))) & ~7u;
+    return 0u;
+  }();
+  // a ticket = 4 waves of 8 queries per warp; small batches get one wave per ticket so that every warp draws some
+  uint32_t ticket_sz = nq >= uint64_t(grid) * (TPB / 32) * 128 ? 32u : 8u;
+  if (ticket_env) ticket_sz = ticket_env;
+  e = launch_with_table_window(kern, grid, TPB, s, ix, ix, d_qwords, d_qoff, nq, d_out, d_defer, ticket_sz, br);
+  COUNT_LAUNCH();
+  if (e != cudaSuccess) return e;
+  uint32_t per_group = avg_len == 0 ? 2u : std::min(8u, std::max(1u, 200u / avg_len));
+  e = launch_with_table_window(kern_rest, grid_rest, TPB, s, ix, ix, d_qwords, d_qoff, nq, d_out, d_defer, 8u * per_group, br);
+  COUNT_LAUNCH();
+  if (e != cudaSuccess) return e;
+  search_scalar_kernel<0, MODE, true><<<unsigned(sm_count) * 2, 256, 0, s>>>(ix, d_qwords, d_qoff, nq, d_out, d_defer, br);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
 // the state-machine kernel: NS query slots per lane group, `per_sm` resident 256-thread blocks (register budget)
 template <int MODE, int MINB, int NS, bool VFY = false>
 static cudaError_t launch_search_pairx_b(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
@@ -1671,11 +1895,20 @@ static cudaError_t launch_search_pair(const IndexView& ix, const uint64_t* d_qwo
     return 0;
   }();
   const int slots = v.slots >= 0 ? v.slots : slots_default;
-  // locate pass 1 for a gather pass 2: the same, the hit stored as its text position
-  if (MODE == OUT_SP_CNT_U32 && v.finish_in_text && v.locate_positions && ix.rtext != nullptr && ix.full_sa != nullptr)
+  // With the text on the device one-row intervals are finished by comparing with it (see the kernels): count mode,
+  // and locate pass 1 for a gather pass 2 (the hit stored as its text position).  Default: the wave kernel; the
+  // refilling kernel with the same step (awry_set_search_variant(80), or a residency) and the state-machine one
+  // (81-84, count only) stay selectable.
+  const bool in_text = v.finish_in_text && ix.rtext != nullptr && ix.full_sa != nullptr &&
+                       (MODE == OUT_COUNT_U64 || (MODE == OUT_SP_CNT_U32 && v.locate_positions));
+  if (in_text && v.slots < 0 && slots_default == 0 && v.blocks_per_sm == 0) {
+    if (MODE == OUT_COUNT_U64) return launch_search_wave<OUT_COUNT_U64>(ix, d_qwords, d_qoff, nq, d_out, d_defer, sm_count, s, v.avg_len, br);
+    if (MODE == OUT_SP_CNT_U32) return launch_search_wave<OUT_SP_CNT_U32>(ix, d_qwords, d_qoff, nq, d_out, d_defer, sm_count, s, v.avg_len, br);
+  }
+  if (MODE == OUT_SP_CNT_U32 && in_text)
     return launch_search_pair_b<OUT_SP_CNT_U32, 5, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, 0, sm_count, s, v.avg_len, br);
   // count mode with the text on the device: finish one-row intervals by comparing with the text (see the kernel)
-  if (MODE == OUT_COUNT_U64 && v.finish_in_text && ix.rtext != nullptr && ix.full_sa != nullptr) {
+  if (MODE == OUT_COUNT_U64 && in_text) {
     if (slots == 1) return launch_search_pairx_b<OUT_COUNT_U64, 8, 1, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, sm_count, s, v.avg_len, br);
     if (slots == 2) return launch_search_pairx_b<OUT_COUNT_U64, 5, 2, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, sm_count, s, v.avg_len, br);
     if (slots == 3) return launch_search_pairx_b<OUT_COUNT_U64, 6, 1, true>(ix, d_qwords, d_qoff, nq, d_out, d_defer, sm_count, s, v.avg_len, br);

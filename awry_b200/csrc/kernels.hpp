@@ -121,8 +121,10 @@ cudaError_t launch_pack(int alphabet, const uint8_t* d_qbytes, const uint64_t* d
 cudaError_t launch_pack2(const uint32_t* d_crumbs, uint64_t base, const uint64_t* d_qoff, uint64_t nq, uint64_t* d_qwords,
                          const uint64_t* d_exc, uint64_t n_exc, uint64_t exc_base, uint64_t b_lo, uint64_t b_hi,
                          unsigned long long* d_first_bad, cudaStream_t s);
-// d_defer: nq + 2 u32 of scratch (count + list of queries the cooperative kernel hands to the scalar
-// one, then the ticket counter of the dynamic query hand-out)
+// d_defer: defer_words(nq) u32 of scratch -- [0] count and [1 .. nq] list of the queries the cooperative kernel hands to
+// the scalar kernel, [nq + 1] ticket counter; [nq + 2] count, [nq + 3] ticket counter and [nq + 4 ..] list of the queries
+// the wave kernel hands to the refilling kernel
+inline size_t defer_words(uint64_t nq) { return 2 * size_t(nq) + 8; }
 cudaError_t launch_search(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
                           uint64_t nq, SearchOut mode, void* d_out, uint32_t* d_defer,
                           const SearchVariant& v, int sm_count, cudaStream_t s);

@@ -339,7 +339,7 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
       if (nq) {
         Workspace::grow_dev(ws->d_qwords, ws->d_qwords_cap, size_t(packed_words(ix->alphabet, nq, plan.seq_bytes)));
         Workspace::grow_dev(ws->d_out, ws->d_out_cap, size_t(nq) * (locate ? sp_cnt_bytes(r.view) : 8));
-        Workspace::grow_dev(ws->d_defer, ws->d_defer_cap, size_t(nq) + 2);
+        Workspace::grow_dev(ws->d_defer, ws->d_defer_cap, defer_words(nq));
         CU(cudaMemsetAsync(ws->d_flag, 0xff, 8, st));
         {
           ProfScope p(2, r.device, st);

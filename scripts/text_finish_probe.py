@@ -26,12 +26,13 @@ for mut, what in ((0, "exact reads"), (100_000, "10 % of the reads with one subs
     fxg.gen_queries_device(0, n, 3, nq, L, 4, d.data_ptr(), mut_ppm=mut)
     ref = None
     for variant, lanes, bps, name in ((1, 0, 0, "backward search only                      "),
-                                      (0, 0, 0, "finish in the text, branching, 5 blk/SM   "),
+                                      (0, 0, 0, "finish in the text, wave kernel           "),
+                                      (0, 80, 0, "finish in the text, branching, 5 blk/SM   "),
                                       (0, 0, 6, "finish in the text, branching, 6 blk/SM   "),
                                       (0, 81, 0, "finish in the text, states, 1 slot, 8 blk "),
                                       (0, 83, 0, "finish in the text, states, 1 slot, 6 blk "),
                                       (0, 82, 0, "finish in the text, states, 2 slots, 5 blk"),
-                                      (0, 84, 0, "finish in the text, states, 2 slots, 4 blk"))[:3 if QUICK else 7]:
+                                      (0, 84, 0, "finish in the text, states, 2 slots, 4 blk"))[:4 if QUICK else 8]:
         f.set_count_variant(variant)
         f.set_search_variant(lanes, 0, bps)
         for _ in range(3):

@@ -87,7 +87,7 @@ def test_counts_equal_backward_search_and_the_oracle(po, multi, multi_dev):
         f.set_count_variant(0)
     assert np.array_equal(plain, want)
     try:
-        for kernel in (0, 81, 82, 83, 84):                  # the branching kernel and the state-machine one (1 / 2 slots)
+        for kernel in (0, 80, 81, 82, 83, 84):              # wave kernel, refilling kernel, state-machine kernel (1 / 2 slots)
             f.set_search_variant(kernel)
             assert np.array_equal(multi_dev.count_packed(qb, qo), want), kernel
     finally:
