@@ -909,7 +909,8 @@ def main():
 
     def roofline_of(kernel_ms, text_path, share):
         """physical roofline of one flavour of the count kernel: ncu DRAM bytes per launch / its mean launch time"""
-        tr = traffic_from_profiles("search_dna_pair_kernel", in_text=text_path)
+        tr = (traffic_from_profiles("search_dna_wave_kernel") if text_path
+              else traffic_from_profiles("search_dna_pair_kernel", in_text=False))
         if tr and std_cfg:
             traffic, src = float(tr["dram_bytes_per_launch"]), f"ncu --set full capture of this command ({tr.get('source')})"
         elif text_path:
@@ -927,7 +928,8 @@ def main():
                 "traffic": traffic, "traffic_source": src,
                 "traffic_check": "ok" if achieved <= 1.05 * peak else "FAILED: physical traffic above the stream peak",
                 "peak_source": peak_src,
-                "kernel": "search_dna_pair_kernel<count, 256, 6, %s>" % ("finish in the text" if text_path else "backward search only"),
+                "kernel": ("search_dna_wave_kernel<count, 256, 5> (+ the refilling and the scalar kernel over the queries it hands "
+                           "on: none in this batch)" if text_path else "search_dna_pair_kernel<count, 256, 6> (backward search only)"),
                 "kernel_ms": kernel_ms, "kernel_share_of_step": share,
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "algorithmic_equivalent_gbs": alg_bytes_per_launch / (kernel_ms * 1e-3) / 1e9,

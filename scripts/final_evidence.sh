@@ -15,7 +15,7 @@ cut -c1-300 gpurun_out/${T}_bench.json
 [ $rc -eq 0 ] || exit $rc
 timeout 200 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${T}_bench_reference.json 2> gpurun_out/${T}_bench_reference.err; echo "reference arm rc=$?"
 cut -c1-300 gpurun_out/${T}_bench_reference.json
-timeout 150 ncu --set full --clock-control none --import-source on -k regex:search_dna_pair_kernel -s 3 -c 1 -f \
+timeout 150 ncu --set full --clock-control none --import-source on -k regex:search_dna_wave_kernel -s 3 -c 1 -f \
   -o gpurun_out/${T}_prof python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-locate --no-e2e --no-secondary \
   > gpurun_out/${T}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 timeout 150 ncu --set full --clock-control none --import-source on -k regex:search_dna_pair_kernel -s 3 -c 1 -f \
@@ -27,4 +27,5 @@ timeout 150 ncu --set full --clock-control none --import-source on -k regex:sear
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv \
   --log-file gpurun_out/${T}_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-secondary \
   > gpurun_out/${T}_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+timeout 300 python scripts/text_finish_probe.py > gpurun_out/${T}_text_finish_probe.log 2>&1; echo "probe rc=$?"
 ls -la gpurun_out/${T}_*
