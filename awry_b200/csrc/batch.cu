@@ -464,8 +464,9 @@ void search_on_replica(const awry_index* ix, size_t ri, const QuerySource& qs, u
           may_pack = true;
         } else {
           // a chunk goes up as it is as soon as the raw share is behind plan: raw chunks sit early in the batch,
-          // where the host packs the following chunks while they cross the link (packing first and sending the
-          // raw ones at the end leaves the host idle behind them: 15.7 ms per 10 M reads against 12-13)
+          // where the host packs the following chunks while they cross the link, not at its end, where the host
+          // would idle behind them (measured effect: none on a host whose memory system is the limit -- 15.4-15.9 ms
+          // per 10 M reads for every share from 0.7 to 1.0, profiles/r02_s10_e2e_share_sweep.log)
           may_pack = !(double(bytes_total - bytes_packed) < (1.0 - plan.share) * double(bytes_total + (c.b1 - c.b0)));
         }
         bytes_total += c.b1 - c.b0;
