@@ -1240,8 +1240,10 @@ __global__ void __launch_bounds__(TPB, MINB)
       left -= two ? 2 : 1;
     }
     if (VFY) {
-      // the unconsumed symbols [len - left, len) must all be in the ring (always, for queries of <= 256 symbols)
-      if (active && sp == ep && left >= VERIFY_MIN_LEFT && nwords <= wlim + 8) {
+      // the unconsumed symbols [len - left, len) are compared out of the ring when it holds them all (always, for
+      // queries of <= 256 symbols), else out of the packed words in global memory
+      if (active && sp == ep && left >= VERIFY_MIN_LEFT) {
+        const bool in_ring = nwords <= wlim + 8;
         AWRY_CHK(sp < ix.n_full_sa);
         const uint32_t p = __ldg(ix.full_sa + sp);  // the matched suffix stands at text[p ..]
         bool ok = p >= left;                          // else the rest of the query would start before the text
@@ -1255,7 +1257,8 @@ __global__ void __launch_bounds__(TPB, MINB)
           for (uint32_t sec = s_first + sub; sec <= s_last; sec += 4) {
             AWRY_CHK(uint64_t(sec) * 32 + 31 < ix.n_rtext);
             const u32x8 t = ldg256(ix.rtext + size_t(sec) * 32);
-            bad |= text_sector_mismatch(t, ring, sec, rb0, done, len);
+            bad |= in_ring ? text_sector_mismatch<true>(t, ring, sec, rb0, done, len)
+                           : text_sector_mismatch<false>(t, qwords + ubase, sec, rb0, done, len);
           }
           ok = !__any_sync(gmask, bad != 0u);
         }
@@ -1823,7 +1826,7 @@ static cudaError_t launch_search_wave(const IndexView& ix, const uint64_t* d_qwo
   cudaError_t e = cudaMemsetAsync(d_defer + nq + 2, 0, 8, s);  // count of the rest list, its ticket counter
   if (e != cudaSuccess) return e;
   auto kern = search_dna_wave_kernel<MODE, TPB, MINB>;
-  auto kern_rest = search_dna_pair_kernel<MODE, TPB, MINB, true, true>;
+  auto kern_rest = search_dna_pair_kernel<MODE, TPB, 4, true, true>;  // (64 registers: the list-driven flavour spills at 48)
   int per_sm = 0, per_sm_rest = 0;
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, 0)) != cudaSuccess) return e;
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_rest, kern_rest, TPB, 0)) != cudaSuccess) return e;

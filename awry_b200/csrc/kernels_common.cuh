@@ -143,16 +143,21 @@ __device__ __forceinline__ uint32_t low_mask(int n) {
 // search-order symbol 0, so the sector's first symbol has search-order index j0 = 64 * sec - rb0 (negative for
 // the sector the window starts in); symbols [done, len) take part.  Returns non-zero on a mismatch.
 // The ring is read as 32 words of 8 symbols; words outside the loaded part are masked out, not avoided.
+// RING = false: the query is longer than the ring (256 symbols) and `ring` points at its packed words in global
+// memory instead (read through L2: the words were fetched when the query started).
+template <bool RING = true>
 __device__ __forceinline__ uint32_t text_sector_mismatch(const u32x8& t, const uint64_t* ring, uint32_t sec, uint32_t rb0,
                                                          uint32_t done, uint32_t len) {
   const uint32_t* rq = reinterpret_cast<const uint32_t*>(ring);
   const int j0 = int(sec * 64u - rb0);
   const int a = j0 >> 3;  // floor
   const uint32_t sh = 4u * uint32_t(j0 & 7);
-  uint32_t bad = 0, q_lo = rq[a & 31];
+  // (global memory: the words in front of the query belong to no symbol that takes part -- they are masked out --
+  // so word 0 stands in for them; behind the last query the buffer is padded by 32 words)
+  uint32_t bad = 0, q_lo = RING ? rq[a & 31] : __ldg(rq + (a < 0 ? 0 : a));
 #pragma unroll
   for (int w = 0; w < 8; w++) {
-    const uint32_t q_hi = rq[(a + w + 1) & 31];
+    const uint32_t q_hi = RING ? rq[(a + w + 1) & 31] : __ldg(rq + (a + w + 1 < 0 ? 0 : a + w + 1));
     const uint32_t qw = __funnelshift_r(q_lo, q_hi, sh);  // query symbols j0 + 8 w .. + 7
     const int jw = j0 + 8 * w;
     const uint32_t m = low_mask(4 * (int(len) - jw)) & ~low_mask(4 * (int(done) - jw));

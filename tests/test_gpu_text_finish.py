@@ -168,6 +168,39 @@ def test_every_length_and_every_mismatch_position(po, fx):
         ix.close()
 
 
+def test_long_reads_are_compared_out_of_global_memory(po, multi, multi_dev):
+    """reads longer than the 256-symbol ring (1-8 kbp): the wave kernel hands them to the refilling kernel, which
+    compares against the packed words in global memory; exact, with a substitution near either end, and hanging
+    over the start of the text"""
+    from awry_b200 import fm_index as f
+    orc = oracle_from_parts(po, multi)
+    r = np.random.default_rng(21)
+    t = bytes(multi.text)
+    qs = []
+    for i in range(1500):
+        ln = int(r.integers(257, 8000))
+        p = int(r.integers(0, len(t) - ln)) if i % 7 else 0
+        q = bytearray(t[p:p + ln])
+        if i % 3 == 1:
+            at = [int(r.integers(0, ln)), 0, ln - 1, int(r.integers(0, 20)), ln - 1 - int(r.integers(0, 300))][i % 5]
+            q[at] = ord("ACGT"[(b"ACGT".find(bytes([q[at]])) + 1) % 4]) if q[at] in b"ACGT" else ord("C")
+        if i % 11 == 0:
+            q = bytearray(bytes(r.choice(np.frombuffer(b"ACGT", np.uint8), 5)) + t[:ln])   # starts before the text
+        qs.append(bytes(q))
+    qb, qo = f.pack_queries(qs)
+    want, _ = orc.count_batch(qb, qo)
+    assert (want >= 1).sum() > 300 and (want == 0).sum() > 300
+    for kernel in (0, 80):
+        f.set_search_variant(kernel)
+        try:
+            assert np.array_equal(multi_dev.count_packed(qb, qo), want), kernel
+        finally:
+            f.set_search_variant(0)
+    woff, whits, _ = orc.locate_batch(qb, qo)
+    off, hits = multi_dev.locate_packed(qb, qo)
+    assert np.array_equal(off, woff) and np.array_equal(hits, whits)
+
+
 def test_without_the_text_the_kernel_steps_to_the_end(po, fx, monkeypatch):
     from awry_b200 import fm_index as f
     monkeypatch.setenv("AWRY_B200_TEXT", "0")
