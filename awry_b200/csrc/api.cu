@@ -314,14 +314,28 @@ void finish_replica0(awry_index* ix, Replica& r) {
   CU(cudaMemset(r.d_async_flag, 0xff, 8));
   keep_pool_memory(r.device);
 
-  // device seed table: k_dev = min(k_file, cap); the table only accelerates, results are those
-  // of the plain backward search either way
-  uint32_t cap = ix->alphabet == AWRY_NUCLEOTIDE ? 14 : 6;
+  // device seed table: the table only accelerates, results are those of the plain backward search either way, so
+  // its depth is the library's choice: the file's k (capped at 14), or deeper when the index is large enough to
+  // make use of it -- nucleotide: the deepest k <= 15 with 4^k <= rows / 2 whose table takes at most an eighth of
+  // the free memory (k = 15, 8.6 GB, at 3.1 G rows: a seeded interval is then ~3 rows wide and a wave of the count
+  // kernel needs one or two pair steps instead of three: 1.70 / 1.48 / 1.34 / 1.19 ms per 10 M x 150-bp reads
+  // with k = 13 / 14 / 15 / 16, profiles/r02_s11_seed_depth.log; k = 16 would be 34 GB).  AWRY_B200_KMER_DEV
+  // sets it (up to 16).
+  const bool dna = ix->alphabet == AWRY_NUCLEOTIDE;
+  uint32_t cap = dna ? 14 : 6;
   uint32_t k = std::min<uint32_t>(ix->kmer_len_file, cap);
+  const uint32_t k_file = k;
+  if (dna && !ix->wide && k > 0) {
+    uint32_t k_auto = 0;
+    while (k_auto < 15 && (1ull << (2 * (k_auto + 1))) <= ix->bwt_len / 2) k_auto++;
+    k = std::max(k, k_auto);
+  }
   size_t free_b = 0, total_b = 0;
   CU(cudaMemGetInfo(&free_b, &total_b));
-  if (const char* e = getenv("AWRY_B200_KMER_DEV")) k = std::min<uint32_t>(uint32_t(std::max(0l, strtol(e, nullptr, 10))), cap);  // experiments
+  if (const char* e = getenv("AWRY_B200_KMER_DEV")) k = std::min<uint32_t>(uint32_t(std::max(0l, strtol(e, nullptr, 10))), dna ? 16u : cap);  // experiments
   const size_t entry_bytes = ix->wide ? 16 : 8;
+  if (!getenv("AWRY_B200_KMER_DEV"))
+    while (k > k_file && table_entries(ix->alphabet, k) * entry_bytes > free_b / 8) k--;  // the deeper table is a luxury
   while (k > 0 && table_entries(ix->alphabet, k) * entry_bytes > free_b / 4) k--;
   ix->kmer_len_dev = k;
   set_view_constants(ix, r);
