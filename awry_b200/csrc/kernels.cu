@@ -357,8 +357,48 @@ __global__ void build_table_kernel(IndexView ix, uint2* __restrict__ table, uint
   table[idx] = sp <= ep ? make_uint2(sp, ep) : make_uint2(1u, 0u);
 }
 
+// Nucleotide tables deeper than 4^10 entries are built level by level: the entry of a j-mer is ONE LF step on the
+// entry of its first j - 1 symbols (the low digits of its index), so level j costs 4^j steps instead of j * 4^j
+// (k = 15: 1.4 G steps instead of 16 G; the two scratch levels take 4^(k-1) + 4^(k-2) entries).
+__global__ void __launch_bounds__(256)
+    extend_table_kernel(IndexView ix, const uint2* __restrict__ prev, uint2* __restrict__ next, uint64_t n_next, uint32_t j) {
+  const uint64_t idx = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (idx >= n_next) return;
+  const uint64_t n_prev = n_next >> 2;
+  const uint2 r = prev[idx & (n_prev - 1)];
+  uint32_t sp = r.x, ep = r.y;
+  if (sp <= ep) lf_update<0>(ix, sp, ep, uint32_t(idx >> (2 * (j - 1))));
+  next[idx] = sp <= ep ? make_uint2(sp, ep) : make_uint2(1u, 0u);
+}
+
 cudaError_t launch_build_table(const IndexView& ix, uint2* d_table, uint32_t k, cudaStream_t s) {
   uint64_t n = table_entries(int(ix.alphabet), k);
+  constexpr uint32_t K0 = 10;  // levels up to here: one thread per k-mer walks all of its steps
+  if (ix.alphabet == 0 && k > K0) {
+    uint2* scratch[2] = {nullptr, nullptr};
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&scratch[0]), (n >> 2) * sizeof(uint2));
+    if (e == cudaSuccess && k > K0 + 1) e = cudaMalloc(reinterpret_cast<void**>(&scratch[1]), (n >> 4) * sizeof(uint2));
+    if (e == cudaSuccess) {
+      // level j lands in scratch[(k - 1 - j) & 1], so level k - 1 is in scratch[0] (the large one) and k - 2 in scratch[1]
+      uint2* cur = scratch[(k - 1 - K0) & 1];
+      const uint64_t n0 = table_entries(0, K0);
+      build_table_kernel<0><<<unsigned((n0 + 255) / 256), 256, 0, s>>>(ix, cur, n0, K0);
+      COUNT_LAUNCH();
+      for (uint32_t j = K0 + 1; j <= k && e == cudaSuccess; j++) {
+        uint2* const dst = j == k ? d_table : scratch[(k - 1 - j) & 1];
+        const uint64_t nj = table_entries(0, j);
+        extend_table_kernel<<<unsigned((nj + 255) / 256), 256, 0, s>>>(ix, cur, dst, nj, j);
+        COUNT_LAUNCH();
+        e = cudaGetLastError();
+        cur = dst;
+      }
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    }
+    cudaFree(scratch[0]);
+    cudaFree(scratch[1]);
+    if (e == cudaSuccess) return e;
+    cudaGetLastError();  // scratch did not fit (or a launch failed): the one-pass kernel below needs none
+  }
   unsigned grid = unsigned((n + 255) / 256);
   if (ix.alphabet == 0)
     build_table_kernel<0><<<grid, 256, 0, s>>>(ix, d_table, n, k);
