@@ -325,9 +325,9 @@ void finish_replica0(awry_index* ix, Replica& r) {
   uint32_t cap = dna ? 14 : 6;
   uint32_t k = std::min<uint32_t>(ix->kmer_len_file, cap);
   const uint32_t k_file = k;
-  if (dna && !ix->wide && k > 0) {
+  if (!ix->wide && k > 0) {  // (protein: up to k = 6, 0.5 GB -- one block read less per peptide)
     uint32_t k_auto = 0;
-    while (k_auto < 15 && (1ull << (2 * (k_auto + 1))) <= ix->bwt_len / 2) k_auto++;
+    while (k_auto < (dna ? 15u : cap) && table_entries(ix->alphabet, k_auto + 1) <= ix->bwt_len / 2) k_auto++;
     k = std::max(k, k_auto);
   }
   size_t free_b = 0, total_b = 0;
