@@ -1,4 +1,5 @@
 // reads_api.cu -- host side of the streaming reads-file front-end (device side: reads.cu).
+#include <sys/mman.h>
 #include <zlib.h>
 
 #include "host.hpp"
@@ -15,8 +16,36 @@ namespace {
 // search / locate kernels as the *_device entry points.  A record cut by a chunk boundary is carried
 // into the next chunk by the host.
 
+// counts of a reads file: a malloc'd array that grows by doubling and is handed to the caller as it is (the
+// results of a chunk come back through the workspace's pinned buffer and are copied in after the chunk's wait)
+struct CountsBuf {
+  uint64_t* p = nullptr;
+  size_t n = 0, cap = 0;
+  CountsBuf() = default;
+  CountsBuf(const CountsBuf&) = delete;
+  CountsBuf& operator=(const CountsBuf&) = delete;
+  ~CountsBuf() { free(p); }
+  void resize(size_t want) {
+    if (want > cap) {
+      size_t c = std::max<size_t>(std::max<size_t>(want, cap * 2), 1u << 16);
+      void* q = realloc(p, c * 8);
+      if (!q) fail(AWRY_ERR_NOMEM, "out of host memory for %llu counts", (unsigned long long)c);
+      p = static_cast<uint64_t*>(q);
+      cap = c;
+    }
+    n = want;
+  }
+  uint64_t* data() { return p; }
+  uint64_t* release() {
+    uint64_t* r = p;
+    p = nullptr;
+    n = cap = 0;
+    return r;
+  }
+};
+
 struct ReadsOut {
-  std::vector<uint64_t> counts;
+  CountsBuf counts;
   std::vector<uint64_t> hit_off;  // locate: CSR, n_reads + 1
   awry_hit* hits = nullptr;       // locate: malloc'd
   uint64_t n_hits = 0, hits_cap = 0;
@@ -131,6 +160,12 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
   cudaStream_t st = ws->st;
   Workspace::ReadsScratch& rs = ws->rs;
 
+  // AWRY_B200_TRACE=1: where the wall time of the call goes (one line per call on stderr)
+  static const bool trace = getenv("AWRY_B200_TRACE") != nullptr;
+  using Clock = std::chrono::steady_clock;
+  double t_slot = 0, t_lines = 0, t_parse = 0, t_search = 0, t_pread = 0, t_ring = 0, t_copy_out = 0;  // seconds
+  auto since = [](Clock::time_point t0) { return std::chrono::duration<double>(Clock::now() - t0).count(); };
+  const auto t_call = Clock::now();
   // reader thread state
   std::mutex mu;
   std::condition_variable cv;
@@ -142,6 +177,13 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
   bool stop = false;
   std::string reader_err;
   std::thread reader;
+  // The hits array is sized for the whole segment when the first chunk is back; its pages are mapped by a helper
+  // thread (madvise(MADV_POPULATE_WRITE): contents untouched) while the pipeline runs, so that the copies into it do
+  // not take a page fault per 4 KiB (160 MB of hits: 75 ms of a 160 ms call).  Joined before the array moves.
+  std::thread populate;
+  auto populate_done = [&] {
+    if (populate.joinable()) populate.join();
+  };
 
   auto cleanup = [&] {
     {
@@ -150,6 +192,7 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
     }
     cv.notify_all();
     if (reader.joinable()) reader.join();
+    populate_done();
     if (rs.st_in) cudaStreamSynchronize(rs.st_in);
     cudaStreamSynchronize(st);
     r.release(ws);
@@ -189,10 +232,13 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
       for (int c = 0;; c++) {
         Slot& s = slots[c % NBUF];
         {
+          const auto t0 = Clock::now();
           std::unique_lock<std::mutex> lk(mu);
           cv.wait(lk, [&] { return stop || !s.filled; });
+          t_ring += since(t0);
           if (stop) return;
         }
+        const auto t_read = Clock::now();
         uint64_t n = gz ? 0 : std::min<uint64_t>(CHUNK, fsize - pos);
         bool gz_end = false;
         try {
@@ -221,6 +267,7 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
           return;
         }
         pos += n;
+        t_pread += since(t_read);
         const bool at_eof = gz ? gz_end : pos >= fsize;
         {
           std::lock_guard<std::mutex> lk(mu);
@@ -251,11 +298,13 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
       const int si = c % NBUF;
       Slot& s = slots[si];
       {
+        const auto t0 = Clock::now();
         std::unique_lock<std::mutex> lk(mu);
         if (blocking)
           cv.wait(lk, [&] { return s.filled; });
         else if (!s.filled)
           return false;
+        t_slot += since(t0);
       }
       if (!reader_err.empty()) fail(AWRY_ERR_IO, "%s", reader_err.c_str());
       uint8_t* base = h_buf[si] + CARRY - tail_len;
@@ -292,7 +341,9 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
       CU(cudaStreamWaitEvent(st, rs.ev_in[c & 1], 0));
       CU(reads_find_lines(d_raw, uint32_t(n), d_nl, d_small, d_temp, temp_bytes, st));
       CU(cudaMemcpyAsync(h_n_lines, d_small, 4, cudaMemcpyDeviceToHost, st));
+      auto t_sync = Clock::now();
       CU(cudaStreamSynchronize(st));
+      t_lines += since(t_sync);
       const uint32_t n_lines = *h_n_lines;
       if (size_t(n_lines) + 2 > cap_lines) {
         cudaFree(d_seq_len);
@@ -317,7 +368,9 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
       CU(reads_parse_lines(d_raw, uint32_t(n), d_nl, d_small, n_lines, fastq, eof ? 1 : 0, d_seq_len, d_is_hdr, d_seq_off,
                            d_hdr_rank, d_plan, d_qbytes, d_qoff, d_temp, temp_bytes, st));
       CU(cudaMemcpyAsync(h_plan, d_plan, sizeof(ReadsPlan), cudaMemcpyDeviceToHost, st));
+      t_sync = Clock::now();
       CU(cudaStreamSynchronize(st));
+      t_parse += since(t_sync);
       const ReadsPlan plan = *h_plan;
       const uint64_t nq = plan.n_records;
       tail_len = n - plan.consumed;
@@ -359,35 +412,71 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
         }
         CU(cudaMemcpyAsync(ws->h_flag, ws->d_flag, 8, cudaMemcpyDeviceToHost, st));
         if (!locate) {
+          if (out.counts.cap == 0 && plan.consumed) {  // first chunk: size the array for the whole segment
+            const double per_read = double(plan.consumed) / double(nq);
+            out.counts.resize(size_t(double(out.file_bytes) / per_read * 1.02) + nq + 1024);
+          }
           out.counts.resize(out.n_reads + nq);
-          CU(cudaMemcpyAsync(out.counts.data() + out.n_reads, ws->d_out, nq * 8, cudaMemcpyDeviceToHost, st));
+          Workspace::grow_host(ws->h_out, ws->h_out_cap, size_t(nq) * 8);
+          CU(cudaMemcpyAsync(ws->h_out, ws->d_out, nq * 8, cudaMemcpyDeviceToHost, st));
           g_prof.d2h += nq * 8;
+          t_sync = Clock::now();
           CU(cudaStreamSynchronize(st));
+          t_search += since(t_sync);
+          memcpy(out.counts.data() + out.n_reads, ws->h_out, nq * 8);
         } else {
           Workspace::grow_dev(ws->d_hit_off, ws->d_hit_off_cap, size_t(nq) + 1);
+          t_sync = Clock::now();
           uint64_t n_hits = locate_chunk_count(r, ws, nq, ws->d_hit_off, st);
+          t_search += since(t_sync);
+          // results come back through the workspace's pinned buffer (offsets, then hits) and are copied into the
+          // caller-bound arrays after the chunk's wait: a device-to-host copy into pageable memory would block this
+          // thread for the whole transfer.  The first chunk sizes both arrays for the whole segment.
+          const double seg_reads = plan.consumed ? double(out.file_bytes) / (double(plan.consumed) / double(nq)) * 1.02 + double(nq) : 0.0;
+          if (out.n_reads == 0 && seg_reads > 0) out.hit_off.reserve(size_t(seg_reads) + 1024);
           out.hit_off.resize(out.n_reads + nq + 1);
           uint64_t* dst_off = out.hit_off.data() + out.n_reads;
-          CU(cudaMemcpyAsync(dst_off, ws->d_hit_off, (nq + 1) * 8, cudaMemcpyDeviceToHost, st));
+          const size_t off_bytes = (size_t(nq) + 1) * 8;
+          Workspace::grow_host(ws->h_out, ws->h_out_cap, off_bytes + size_t(n_hits) * 16);
+          CU(cudaMemcpyAsync(ws->h_out, ws->d_hit_off, off_bytes, cudaMemcpyDeviceToHost, st));
           if (n_hits) {
             uint64_t* d_hits = locate_chunk_walk(r, ws, nq, n_hits, flags, ws->d_hit_off, st);
             if (out.n_hits + n_hits > out.hits_cap) {
               uint64_t cap = std::max<uint64_t>(out.n_hits + n_hits, out.hits_cap * 2);
+              if (out.hits_cap == 0 && seg_reads > 0)  // hits per read of the first chunk, over the whole segment
+                cap = std::max<uint64_t>(cap, uint64_t(seg_reads * (double(n_hits) / double(nq)) * 1.05) + 1024);
+              populate_done();
               void* np = realloc(out.hits, cap * sizeof(awry_hit));
               if (!np) {
                 cudaFreeAsync(d_hits, st);
                 fail(AWRY_ERR_NOMEM, "out of host memory for %llu hits", (unsigned long long)cap);
               }
+              const bool first_alloc = out.hits_cap == 0;
               out.hits = static_cast<awry_hit*>(np);
               out.hits_cap = cap;
+#ifdef MADV_POPULATE_WRITE
+              if (first_alloc && cap * sizeof(awry_hit) >= (32u << 20)) {
+                const uintptr_t lo = (reinterpret_cast<uintptr_t>(np) + 4095) & ~uintptr_t(4095);
+                const uintptr_t hi = (reinterpret_cast<uintptr_t>(np) + cap * sizeof(awry_hit)) & ~uintptr_t(4095);
+                if (hi > lo) populate = std::thread([lo, hi] { (void)madvise(reinterpret_cast<void*>(lo), hi - lo, MADV_POPULATE_WRITE); });
+              }
+#else
+              (void)first_alloc;
+#endif
             }
-            CU(cudaMemcpyAsync(out.hits + out.n_hits, d_hits, n_hits * 16, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(ws->h_out + off_bytes, d_hits, n_hits * 16, cudaMemcpyDeviceToHost, st));
             cudaFreeAsync(d_hits, st);
             g_prof.d2h += n_hits * 16;
           }
+          t_sync = Clock::now();
           CU(cudaStreamSynchronize(st));
+          t_search += since(t_sync);
+          const auto t_copy = Clock::now();
           g_prof.d2h += (nq + 1) * 8;
-          for (uint64_t i = 0; i <= nq; i++) dst_off[i] += out.n_hits;
+          if (n_hits) memcpy(out.hits + out.n_hits, ws->h_out + off_bytes, n_hits * 16);
+          const uint64_t* src_off = reinterpret_cast<const uint64_t*>(ws->h_out);
+          for (uint64_t i = 0; i <= nq; i++) dst_off[i] = src_off[i] + out.n_hits;
+          t_copy_out += since(t_copy);
           out.n_hits += n_hits;
         }
         if (*ws->h_flag != ~0ull && bad_read) *bad_read = out.n_reads + (*ws->h_flag >> 1);
@@ -410,6 +499,11 @@ void run_reads_file(const awry_index* ix, const char* path, bool locate, uint32_
     throw;
   }
   cleanup();
+  if (trace)
+    fprintf(stderr, "[trace] reads file, replica %zu: %.1f ms in all; main thread waited %.1f ms for the reader, %.1f ms for the "
+            "line split, %.1f ms for the record split, %.1f ms for search + results (+ %.1f ms copying hits out); reader "
+            "thread read for %.1f ms and waited %.1f ms for a free buffer\n", ri, since(t_call) * 1e3, t_slot * 1e3,
+            t_lines * 1e3, t_parse * 1e3, t_search * 1e3, t_copy_out * 1e3, t_pread * 1e3, t_ring * 1e3);
 }
 
 // ---- one reads file over SEVERAL replicas (plain files) ----
@@ -579,10 +673,8 @@ int awry_count_reads_file(const awry_index* ix, const char* path, uint64_t** cou
     *n_reads = 0;
     ReadsOut out;
     run_reads_file_multi(ix, path, false, 0, out);
-    uint64_t* buf = static_cast<uint64_t*>(malloc(std::max<size_t>(8, out.n_reads * 8)));
-    if (!buf) fail(AWRY_ERR_NOMEM, "out of host memory for %llu counts", (unsigned long long)out.n_reads);
-    if (out.n_reads) memcpy(buf, out.counts.data(), out.n_reads * 8);
-    *counts = buf;
+    out.counts.resize(std::max<size_t>(1, size_t(out.n_reads)));  // (never a null array, even for an empty file)
+    *counts = out.counts.release();
     *n_reads = out.n_reads;
   });
 }
