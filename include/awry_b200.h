@@ -301,19 +301,21 @@ int awry_bench_random_gather(int device, uint64_t footprint_bytes, uint32_t gran
                              uint64_t n_reads, int iters, double *reads_per_s, double *gb_per_s);
 
 /* Tuning knob for experiments: selects the search-kernel variant.  lanes_per_query: 1/2/4 =
- * that many lanes on the one-symbol blocks, 8 = the two-symbol (pair index) kernel, -1 = scalar
- * kernel, 0 = default (pair kernel when the pair index exists); 80 / 81 / 82 = the pair kernel with its
- * query start as a branch (80) or as states of 1 / 2 query slots per lane group (81 / 82).
- * blocks_per_sm caps residency. */
+ * that many lanes on the one-symbol blocks, 8 = the two-symbol (pair index) kernels, -1 = scalar
+ * kernel, 0 = default (pair index when it exists: the wave kernel where one-row intervals are finished in the
+ * text -- see awry_set_count_variant -- else the refilling kernel); 80 = the refilling pair kernel (lane groups
+ * draw a new query as soon as theirs ends), 81 / 82 (83 / 84: lower residency) = the same as a state machine
+ * with 1 / 2 query slots per lane group.  blocks_per_sm caps residency (and selects the refilling kernel). */
 int awry_set_search_variant(int lanes_per_query, int threads_per_block, int blocks_per_sm);
 
-/* Count, nucleotide.  Once backward search (fm_index.rs:402-438) has narrowed the interval to ONE row, the rest of
+/* Count and locate pass 1, nucleotide.  Once backward search (fm_index.rs:402-438) has narrowed the interval to ONE row, the rest of
  * the query can only keep that row or empty the interval, and which of the two is decided by the text in front
  * of the occurrence.  When the index holds the unsampled suffix array and the text (4 bits per symbol, read back
  * out of BWT + suffix array at load time: bwt_len / 2 bytes, AWRY_B200_TEXT=0 never), the count kernel looks the
  * row's position up and compares the remaining symbols with the text -- 2-3 memory requests instead of one per
- * two symbols; counts are identical.  variant 0 = do so when the arrays are present (default), 1 = backward
- * search to the last symbol. */
+ * two symbols; counts are identical.  Locate does the same when its pass 2 is the gather from the unsampled array:
+ * the hit of such a query is the text position itself.  variant 0 = do so when the arrays are present (default),
+ * 1 = backward search to the last symbol. */
 int awry_set_count_variant(int variant);
 
 /* Locate pass 2.  Three ways to turn a BWT row into a text position, identical results:
