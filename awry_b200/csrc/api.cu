@@ -82,7 +82,7 @@ void set_limits(awry_index* ix, Replica& r) {
   v.n_table = ix->wide ? 0 : (r.d_table ? table_entries(ix->alphabet, ix->kmer_len_dev) : 0);
   v.n_sa_words = ix->n_sa_words + 2;
   v.n_full_sa = r.d_full_sa ? ix->bwt_len : 0;
-  v.n_rtext = r.d_rtext ? rtext_bytes(ix->bwt_len) : 0;
+  v.n_rtext = r.d_rtext ? rtext_bytes(ix->alphabet, ix->bwt_len) : 0;
   v.n_walk_u4 = r.d_walk ? walk_block_count(ix->bwt_len) * WALK_BLOCK_UINT4 : 0;
   v.n_walk_rank = r.d_walk ? walk_block_count(ix->bwt_len) + 1 : 0;
   v.n_pos_samples = r.d_walk && ix->lean_ratio ? (ix->bwt_len + ix->lean_ratio - 1) / ix->lean_ratio : 0;
@@ -394,8 +394,9 @@ void finish_replica0(awry_index* ix, Replica& r) {
   // With it the count kernel finishes a query whose interval has narrowed to one row with one suffix-array read
   // and one or two lines of text instead of a block read per two symbols.  n / 2 bytes; AWRY_B200_TEXT=0 never.
   const char* tx = getenv("AWRY_B200_TEXT");
-  if (ix->alphabet == AWRY_NUCLEOTIDE && r.d_full_sa && r.d_pair && !(tx && tx[0] == '0') && !g_skip_accelerators) {
-    const size_t bytes = rtext_bytes(ix->bwt_len);
+  // Protein: the same with one byte per symbol (bwt_len bytes).
+  if (r.d_full_sa && (ix->alphabet != AWRY_NUCLEOTIDE || r.d_pair) && !(tx && tx[0] == '0') && !g_skip_accelerators) {
+    const size_t bytes = rtext_bytes(ix->alphabet, ix->bwt_len);
     CU(cudaMemGetInfo(&free_b, &total_b));
     if (bytes < free_b / 3) {
       CU(cudaMalloc(reinterpret_cast<void**>(&r.d_rtext), bytes));

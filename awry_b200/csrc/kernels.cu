@@ -1992,7 +1992,12 @@ static cudaError_t launch_search_pair(const IndexView& ix, const uint64_t* d_qwo
 // Same shape as the nucleotide pair kernel: the query (8-bit symbols) is staged in a 16-word
 // shared-memory ring with one aligned read, groups refill in-loop, the warp leaves by vote and
 // the rank reduction uses full-mask shuffles.  Slices 0/1 hold the planes of rows 0-31 / 32-63.
-template <int MODE, int TPB, int MINB>
+// VFY (count, and locate pass 1 for a gather pass 2; needs ix.full_sa and ix.rtext): as in the nucleotide kernels, a
+// one-row interval with at least AMINO_VERIFY_MIN_LEFT symbols left is finished by reading SA[row] and comparing
+// the rest of the query with the text (one byte per symbol) -- two dependent loads instead of `left`.
+constexpr uint32_t AMINO_VERIFY_MIN_LEFT = 3;
+
+template <int MODE, int TPB, int MINB, bool VFY = false>
 __global__ void __launch_bounds__(TPB, MINB)
     search_amino_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
                         const uint64_t* __restrict__ qoff, uint64_t nq, void* __restrict__ out,
@@ -2123,6 +2128,34 @@ __global__ void __launch_bounds__(TPB, MINB)
       ep = base + rb - 1;
       left--;
     }
+    if (VFY) {
+      // (the unconsumed symbols must all be in the ring: always, for queries of <= 128 symbols)
+      if (active && sp == ep && left >= AMINO_VERIFY_MIN_LEFT && ((len + 7) >> 3) <= wlim + 8) {
+        AWRY_CHK(sp < ix.n_full_sa);
+        const uint32_t p = __ldg(ix.full_sa + sp);  // the matched suffix stands at text[p ..]
+        bool ok = p >= left;                          // else the rest of the query would start before the text
+        if (ok) {
+          const uint32_t done = len - left;
+          const uint32_t rb0 = ix.bwt_len - p - done;  // reversed-text index of search-order symbol 0
+          const uint32_t s_first = (rb0 + done) >> 5, s_last = (rb0 + len - 1) >> 5;  // 32-B sectors = 32 symbols
+          uint32_t bad = 0;
+          for (uint32_t sec = s_first + sub; sec <= s_last; sec += 4) {
+            AWRY_CHK(uint64_t(sec) * 32 + 31 < ix.n_rtext);
+            const u32x8 t = ldg256(ix.rtext + size_t(sec) * 32);
+            bad |= text_sector_mismatch8(t, ring, sec, rb0, done, len);
+          }
+          ok = !__any_sync(gmask, bad != 0u);
+        }
+        if (sub == 0) {
+          if (MODE == OUT_COUNT_U64)
+            reinterpret_cast<uint64_t*>(out)[cur] = ok ? 1ull : 0ull;
+          else
+            reinterpret_cast<uint2*>(out)[cur] = ok ? make_uint2(p - left, CNT_AT_TEXT_POS) : make_uint2(1u, 0u);
+        }
+        cur = NONE;
+        left = 0;
+      }
+    }
   }
 }
 
@@ -2132,7 +2165,10 @@ static cudaError_t launch_search_amino(const IndexView& ix, const uint64_t* d_qw
                                        int sm_count, cudaStream_t s) {
   if (nq >= (1ull << 32) - (1u << 24)) return cudaErrorInvalidValue;  // 32-bit ticket counter
   constexpr int TPB = 256;
+  const bool in_text = v.finish_in_text && ix.rtext != nullptr && ix.full_sa != nullptr &&
+                       (MODE == OUT_COUNT_U64 || (MODE == OUT_SP_CNT_U32 && v.locate_positions));
   auto kern = search_amino_kernel<MODE, TPB, 6>;
+  if (in_text && MODE != OUT_RANGE_U64) kern = search_amino_kernel<MODE == OUT_RANGE_U64 ? OUT_COUNT_U64 : MODE, TPB, 6, true>;
   int per_sm = 0;
   cudaError_t e = cudaMemsetAsync(d_ticket, 0, 4, s);
   if (e != cudaSuccess) return e;

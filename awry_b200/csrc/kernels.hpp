@@ -96,8 +96,10 @@ cudaError_t build_pair_index(const IndexView& ix, uint4* d_pair_blocks, uint32_t
 cudaError_t launch_fill_offsets(uint64_t* d_qoff, uint64_t first, uint64_t len, uint64_t n, cudaStream_t s);
 cudaError_t build_full_sa(const IndexView& ix, uint32_t* d_full, int sm_count, cudaStream_t s);
 // The indexed text, reversed, 4 bits per symbol (IndexView::rtext, layout.cuh), from the blocks and ix.full_sa:
-// text[SA[row] - 1] = BWT[row].  d_rtext: rtext_bytes(bwt_len) bytes.
-inline size_t rtext_bytes(uint64_t bwt_len) { return ((size_t(bwt_len) + 1) / 2 + 127) / 128 * 128 + 128; }
+// text[SA[row] - 1] = BWT[row].  Protein: one byte per symbol (the reference symbol index).  d_rtext: rtext_bytes() bytes.
+inline size_t rtext_bytes(int alphabet, uint64_t bwt_len) {
+  return ((alphabet == 0 ? (size_t(bwt_len) + 1) / 2 : size_t(bwt_len)) + 127) / 128 * 128 + 128;
+}
 cudaError_t build_rtext(const IndexView& ix, uint8_t* d_rtext, cudaStream_t s);
 
 // The prepass latches the first query it refuses in *d_first_bad (atomicMin, ~0 = none) as

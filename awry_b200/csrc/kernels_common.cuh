@@ -167,6 +167,26 @@ __device__ __forceinline__ uint32_t text_sector_mismatch(const u32x8& t, const u
   return bad;
 }
 
+// protein: 8 bits per symbol, so a 32-byte sector holds 32 symbols, 4 per word, and the ring 128
+__device__ __forceinline__ uint32_t text_sector_mismatch8(const u32x8& t, const uint64_t* ring, uint32_t sec, uint32_t rb0,
+                                                          uint32_t done, uint32_t len) {
+  const uint32_t* rq = reinterpret_cast<const uint32_t*>(ring);
+  const int j0 = int(sec * 32u - rb0);
+  const int a = j0 >> 2;  // floor
+  const uint32_t sh = 8u * uint32_t(j0 & 3);
+  uint32_t bad = 0, q_lo = rq[a & 31];
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    const uint32_t q_hi = rq[(a + w + 1) & 31];
+    const uint32_t qw = __funnelshift_r(q_lo, q_hi, sh);  // query symbols j0 + 4 w .. + 3
+    const int jw = j0 + 4 * w;
+    const uint32_t m = low_mask(8 * (int(len) - jw)) & ~low_mask(8 * (int(done) - jw));
+    bad |= (qw ^ t.v[w]) & m;
+    q_lo = q_hi;
+  }
+  return bad;
+}
+
 // ---- a lane's share of a 128-B amino block (4 lanes): matching rows of its 32-row slice and, in the
 // lane that holds it, the block-start count of the symbol ----
 struct AminoSlice {

@@ -426,13 +426,32 @@ __global__ void __launch_bounds__(256) rtext_kernel(IndexView ix, uint32_t* __re
   }
 }
 
+// protein: one byte per symbol, so plain byte stores
+__global__ void __launch_bounds__(256) rtext_amino_kernel(IndexView ix, uint8_t* __restrict__ rtext) {
+  const uint64_t stride = gridDim.x * uint64_t(blockDim.x);
+  const uint32_t n = ix.bwt_len;
+  for (uint64_t r64 = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; r64 < n; r64 += stride) {
+    const uint32_t row = uint32_t(r64);
+    AWRY_CHK(row < ix.n_full_sa);
+    const uint32_t c = amino_symbol_at(ix, row);
+    const uint32_t p = __ldg(ix.full_sa + row);
+    const uint32_t i = p == 0 ? 0u : n - p;
+    AWRY_CHK(p < n && i < ix.n_rtext);
+    rtext[i] = uint8_t(c);
+  }
+}
+
 cudaError_t build_rtext(const IndexView& ix, uint8_t* d_rtext, cudaStream_t s) {
-  if (ix.full_sa == nullptr || ix.alphabet != 0 || ix.wide != nullptr) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(d_rtext, 0, rtext_bytes(ix.bwt_len), s);
+  if (ix.full_sa == nullptr || ix.wide != nullptr) return cudaErrorInvalidValue;
+  const size_t bytes = rtext_bytes(int(ix.alphabet), ix.bwt_len);
+  cudaError_t e = cudaMemsetAsync(d_rtext, 0, bytes, s);
   if (e != cudaSuccess) return e;
   IndexView v = ix;
-  v.n_rtext = rtext_bytes(ix.bwt_len);
+  v.n_rtext = bytes;
   const unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(1u << 20, (uint64_t(ix.bwt_len) + 255) / 256)));
+  if (ix.alphabet != 0)
+    rtext_amino_kernel<<<grid, 256, 0, s>>>(v, d_rtext);
+  else
   rtext_kernel<<<grid, 256, 0, s>>>(v, reinterpret_cast<uint32_t*>(d_rtext));
   COUNT_LAUNCH();
   return cudaGetLastError();

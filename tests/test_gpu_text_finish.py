@@ -201,6 +201,65 @@ def test_long_reads_are_compared_out_of_global_memory(po, multi, multi_dev):
     assert np.array_equal(off, woff) and np.array_equal(hits, whits)
 
 
+def test_protein_counts_and_hits_through_the_text(po, fx):
+    """the protein kernel finishes one-row intervals the same way (one byte per symbol): peptides of every
+    length 1 .. 200 (the ring holds 128 symbols), a substitution at every position of a 40-residue peptide,
+    peptides hanging over the start of the text and across record delimiters (X), X in the query; counts and
+    locate lists equal the oracle with the step on and off"""
+    from awry_b200 import fm_index as f
+    recs = [bytes(fx.gen_text(1, n, 40 + i)) for i, n in enumerate([60_000, 3, 90_000, 25])]
+    text, starts = fx.concat_records(recs, 1)
+    parts = fx.build_parts(text, 1, ratio=8, kmer_len=3, seq_starts=starts)
+    orc = oracle_from_parts(po, parts)
+    t = bytes(parts.text)
+    r = np.random.default_rng(8)
+    letters = b"ACDEFGHIKLMNPQRSTVWY"
+    qs = []
+    for base in (0, 1, 5, 31, 32, 33, 70_001, len(t) - 200):
+        for ln in range(1, 201):
+            qs.append(t[base:base + ln])
+            qs.append(t[len(t) - ln:])
+        pep = bytearray(t[base:base + 40])
+        for at in range(40):
+            q = bytearray(pep)
+            q[at] = letters[(letters.find(bytes([q[at]])) + 3) % 20] if q[at] in letters else ord("A")
+            qs.append(bytes(q))
+    for i in range(4000):
+        ln = int(r.integers(1, 60))
+        kind = i % 8
+        if kind == 0:
+            q = bytes(r.choice(np.frombuffer(letters, np.uint8), int(r.integers(1, 6)))) + t[:ln]       # before the text
+        elif kind == 1:
+            s0 = int(starts[int(r.integers(1, len(starts)))])
+            a = max(0, s0 - int(r.integers(1, 20)))
+            q = t[a:a + ln]                                                                       # across a delimiter (X)
+        else:
+            p0 = int(r.integers(0, len(t) - ln))
+            q = bytearray(t[p0:p0 + ln])
+            if kind == 2:
+                q[int(r.integers(0, ln))] = ord("X")
+            if kind == 3:
+                at = int(r.integers(0, ln))
+                q[at] = letters[(letters.find(bytes([q[at]])) + 1) % 20] if q[at] in letters else ord("C")
+            q = bytes(q)
+        qs.append(q)
+    qb, qo = f.pack_queries(qs)
+    want, _ = orc.count_batch(qb, qo)
+    woff, whits, _ = orc.locate_batch(qb, qo)
+    assert (want == 1).sum() > 2_000 and (want == 0).sum() > 500
+    ix = device_from_parts(parts)
+    try:
+        assert ix.device_bytes()["text"] > 0
+        for count_variant in (0, 1):
+            f.set_count_variant(count_variant)
+            assert np.array_equal(ix.count_packed(qb, qo), want), count_variant
+            off, hits = ix.locate_packed(qb, qo)
+            assert np.array_equal(off, woff) and np.array_equal(hits, whits), count_variant
+    finally:
+        f.set_count_variant(0)
+        ix.close()
+
+
 def test_without_the_text_the_kernel_steps_to_the_end(po, fx, monkeypatch):
     from awry_b200 import fm_index as f
     monkeypatch.setenv("AWRY_B200_TEXT", "0")
