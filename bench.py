@@ -179,7 +179,8 @@ def workload_name(a):
 def config_of(a):
     """identical in both arms (the driver compares them)"""
     return {"workload": workload_name(a), "reads_per_gpu_per_step": a.reads,
-            "l2": "inputs larger than L2 (1.5 GB reads, 4.1 GB pair blocks, 0.5 GB seed table per step)",
+            "l2": "inputs larger than L2 (1.5 GB of reads per step; 4.1 GB pair blocks, 8.6 GB seed table, 12.4 GB suffix array, "
+                  "1.55 GB text, all read at random)",
             "index": "replicated per GPU; ranks search disjoint batches; no collective on the data path"}
 
 
