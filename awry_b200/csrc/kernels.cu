@@ -1997,7 +1997,9 @@ static cudaError_t launch_search_pair(const IndexView& ix, const uint64_t* d_qwo
 // the rest of the query with the text (one byte per symbol) -- two dependent loads instead of `left`.
 constexpr uint32_t AMINO_VERIFY_MIN_LEFT = 3;
 
-template <int MODE, int TPB, int MINB, bool VFY = false>
+// LIST: the peptides to run are the ones search_amino_wave_kernel handed on; `ticket` is then the counter behind
+// their count (defer + nq + 3: the count sits one word in front of it, the numbers one word behind it).
+template <int MODE, int TPB, int MINB, bool VFY = false, bool LIST = false>
 __global__ void __launch_bounds__(TPB, MINB)
     search_amino_kernel(IndexView ix, const uint64_t* __restrict__ qwords,
                         const uint64_t* __restrict__ qoff, uint64_t nq, void* __restrict__ out,
@@ -2009,7 +2011,8 @@ __global__ void __launch_bounds__(TPB, MINB)
   const uint32_t gbase = (threadIdx.x & 31) - sub;
   const uint32_t gmask = 0xfu << gbase;
   uint64_t* const ring = s_q[threadIdx.x / LANES];
-  const uint32_t nq32 = uint32_t(nq);
+  const uint32_t* const rest = LIST ? ticket - 1 : ticket;  // (LIST only)
+  const uint32_t nq32 = LIST ? rest[0] : uint32_t(nq);
   uint32_t q = 0, q_end = 0;  // dynamic hand-out of ticket_sz queries at a time (see the pair kernel)
   bool more = true;
   uint32_t cur = NONE;
@@ -2030,7 +2033,8 @@ __global__ void __launch_bounds__(TPB, MINB)
         q_end = more ? (nq32 - t < ticket_sz ? nq32 : t + ticket_sz) : 0u;
       }
       if (q < q_end) {
-        cur = q++;
+        cur = LIST ? rest[2 + q] : q;
+        q++;
         uint64_t ov = qoff[cur + (sub & 1)];
         uint64_t o0 = __shfl_sync(gmask, ov, gbase), o1 = __shfl_sync(gmask, ov, gbase + 1);
         len = checked_len(o0, o1, br);
@@ -2159,6 +2163,177 @@ __global__ void __launch_bounds__(TPB, MINB)
   }
 }
 
+// ---- protein wave kernel: search_dna_wave_kernel's structure on the 64-row / 128-B protein blocks ----
+// A warp takes 8 peptides at a time through the phases together: offsets, packed symbols (8 bits each: the
+// 16-word ring holds 128), seed entry, one-symbol steps until every interval of the wave is one row wide (or
+// empty, or used up), SA element, text (one byte per symbol).  Peptides longer than the ring, or still wide after
+// AMINO_WAVE_MAX_STEPS steps, go to the `rest` list and are searched by search_amino_kernel<VFY, LIST>.
+constexpr int AMINO_WAVE_MAX_STEPS = 8;
+
+template <int MODE, int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB)
+    search_amino_wave_kernel(IndexView ix, const uint64_t* __restrict__ qwords, const uint64_t* __restrict__ qoff,
+                             uint64_t nq, void* __restrict__ out, uint32_t* __restrict__ defer, uint32_t ticket_sz,
+                             ByteRange br) {
+  constexpr uint32_t FULL = 0xffffffffu;
+  enum : uint32_t { W_NONE = 0, W_RUN = 1, W_EMPTY = 2 };
+  __shared__ uint64_t s_q[TPB / 4][16];
+  const uint32_t lane = threadIdx.x & 31, sub = lane & 3, gbase = lane - sub, gmask = 0xfu << gbase, grp = lane >> 2;
+  uint64_t* const ring = s_q[threadIdx.x >> 2];
+  const uint32_t nq32 = uint32_t(nq);
+  uint32_t* const ticket = defer + nq + 1;
+  uint32_t* const rest = defer + nq + 2;  // rest[0] = count, rest[2 ..] = query numbers
+  uint32_t pn = 0, pe = 0;
+  uint32_t ahead = 0;  // the warp's next ticket, drawn one ahead (lane 0)
+  if (lane == 0) ahead = atomicAdd(ticket, ticket_sz);
+  for (;;) {
+    if (pn == pe) {  // warp-uniform
+      uint32_t t = ahead;
+      if (lane == 0 && t < nq32) ahead = atomicAdd(ticket, ticket_sz);
+      t = __shfl_sync(FULL, t, 0);
+      if (t >= nq32) break;
+      pn = t;
+      pe = t + (nq32 - t < ticket_sz ? nq32 - t : ticket_sz);
+    }
+    const uint32_t q = pn + grp;
+    uint32_t st = q < pe ? W_RUN : W_NONE;
+    pn = pe - pn > 8u ? pn + 8u : pe;
+
+    // ---- offsets
+    uint64_t ov = 0;
+    if (st == W_RUN) ov = __ldg(qoff + q + (sub & 1));
+    const uint64_t o0 = __shfl_sync(FULL, ov, gbase), o1 = __shfl_sync(FULL, ov, gbase + 1);
+    const uint32_t len = st == W_RUN ? checked_len(o0, o1, br) : 0u;
+    if (st == W_RUN && len == 0) st = W_EMPTY;
+    const uint32_t nwords = (len + 7) >> 3;
+    if (st == W_RUN && nwords > 16) {  // longer than the ring
+      if (sub == 0) rest[2 + atomicAdd(rest, 1u)] = q;
+      st = W_NONE;
+    }
+    // ---- packed symbols -> ring
+    __syncwarp();  // the previous wave's ring reads are done
+    if (st == W_RUN && 4 * sub < nwords) {
+      const uint32_t ubase = 4 * (q + uint32_t(o0 >> 5));
+      AWRY_CHK_QWORDS(ubase + 4 * sub, br, nq, 5);
+      const u32x8 t = ldg256(qwords + ubase + 4 * sub);
+#pragma unroll
+      for (int j = 0; j < 4; j++) ring[4 * sub + j] = uint64_t(t.v[2 * j]) | (uint64_t(t.v[2 * j + 1]) << 32);
+    }
+    __syncwarp();
+    // ---- seed
+    uint32_t sp = 1, ep = 0, left = 0;
+    if (st == W_RUN) {
+      const uint32_t k = ix.kmer_len;
+      const uint64_t w = ring[0];
+      bool seeded = false;
+      if (k != 0 && len >= k) {  // k <= 8: inside word 0
+        uint64_t idx = 0, mult = 1;
+        bool ok = true;
+#pragma unroll 1
+        for (uint32_t j = 0; j < k; j++) {
+          const uint32_t c = uint32_t(w >> (8 * j)) & 0xffu;
+          ok &= (c != uint32_t(AMINO_X)) & (c != uint32_t(AMINO_SENTINEL));
+          idx += uint64_t(c == 21 ? 19 : c - 1) * mult;
+          mult *= 20;
+        }
+        if (ok) {
+          AWRY_CHK(idx < ix.n_table);
+          const uint2 r = __ldg(ix.table + idx);
+          sp = r.x;
+          ep = r.y;
+          left = len - k;
+          seeded = true;
+        }
+      }
+      if (!seeded) {
+        const uint32_t c = uint32_t(w) & 0xffu;
+        if (c != uint32_t(AMINO_SENTINEL) && c <= 21) {
+          sp = ix.c_lo[c];
+          ep = ix.c_hi[c];
+          left = len - 1;
+        }
+      }
+    }
+    // ---- steps
+#pragma unroll 1
+    for (int it = 0; it <= AMINO_WAVE_MAX_STEPS; it++) {
+      bool active = st == W_RUN && left != 0 && sp <= ep && !(sp == ep && left >= AMINO_VERIFY_MIN_LEFT);
+      if (!__any_sync(FULL, active)) break;
+      if (it == AMINO_WAVE_MAX_STEPS) {  // still wide: handed on
+        if (active) {
+          if (sub == 0) rest[2 + atomicAdd(rest, 1u)] = q;
+          st = W_NONE;
+        }
+        break;
+      }
+      const uint32_t pos = len - left;
+      const uint32_t c = uint32_t(ring[(pos >> 3) & 15] >> (8 * (pos & 7))) & 0xffu;
+      if (active && (c == uint32_t(AMINO_SENTINEL) || c > 21)) {  // rejected by the prepass; stay defined
+        sp = 1;
+        ep = 0;
+        active = false;
+      }
+      const uint32_t pa = sp - 1, pb = ep;
+      uint32_t ra = 0, rb = 0;
+      if (active) {
+        const uint32_t ba = pa >> 6, bb = pb >> 6;
+        AWRY_CHK(uint64_t(ba) * AMINO_BLOCK_UINT4 + 7 < ix.n_blocks_u4 && uint64_t(bb) * AMINO_BLOCK_UINT4 + 7 < ix.n_blocks_u4);
+        const u32x8 x = ldg256(ix.blocks + size_t(ba) * AMINO_BLOCK_UINT4 + 2 * sub);
+        u32x8 y = x;
+        if (bb != ba) y = ldg256(ix.blocks + size_t(bb) * AMINO_BLOCK_UINT4 + 2 * sub);  // both reads before either use
+        AminoSlice s = amino_slice(x, sub, c);
+        ra = __popc(s.match & low_mask(int(pa & 63) + 1 - int(32 * sub))) + s.count;
+        if (bb != ba) s = amino_slice(y, sub, c);
+        rb = __popc(s.match & low_mask(int(pb & 63) + 1 - int(32 * sub))) + s.count;
+      }
+      ra += __shfl_xor_sync(FULL, ra, 1);
+      rb += __shfl_xor_sync(FULL, rb, 1);
+      ra += __shfl_xor_sync(FULL, ra, 2);
+      rb += __shfl_xor_sync(FULL, rb, 2);
+      if (active) {
+        const uint32_t base = ix.c_lo[c];
+        sp = base + ra;
+        ep = base + rb - 1;
+        left--;
+      }
+    }
+    // ---- finish in the text
+    const bool need = st == W_RUN && left != 0 && sp <= ep;  // (then sp == ep and left >= AMINO_VERIFY_MIN_LEFT)
+    uint32_t p = 0;
+    if (need) {
+      AWRY_CHK(sp < ix.n_full_sa);
+      p = __ldg(ix.full_sa + sp);
+    }
+    bool ok = need && p >= left;
+    uint32_t bad = 0;
+    if (ok) {
+      const uint32_t done = len - left;
+      const uint32_t rb0 = ix.bwt_len - p - done;
+      const uint32_t s_first = (rb0 + done) >> 5, s_last = (rb0 + len - 1) >> 5;  // 32-B sectors = 32 symbols
+      for (uint32_t sec = s_first + sub; sec <= s_last; sec += 4) {
+        AWRY_CHK(uint64_t(sec) * 32 + 31 < ix.n_rtext);
+        const u32x8 t = ldg256(ix.rtext + size_t(sec) * 32);
+        bad |= text_sector_mismatch8(t, ring, sec, rb0, done, len);
+      }
+    }
+    const uint32_t bad_groups = __ballot_sync(FULL, bad != 0);
+    ok = ok && (bad_groups & gmask) == 0;
+    // ---- results
+    if (sub == 0) {
+      if (st == W_EMPTY) {
+        store_result<MODE>(out, q, 1u, 0u);
+      } else if (st == W_RUN && !need) {
+        store_result<MODE>(out, q, sp, ep);
+      } else if (st == W_RUN) {
+        if (MODE == OUT_COUNT_U64)
+          reinterpret_cast<uint64_t*>(out)[q] = ok ? 1ull : 0ull;
+        else
+          reinterpret_cast<uint2*>(out)[q] = ok ? make_uint2(p - left, CNT_AT_TEXT_POS) : make_uint2(1u, 0u);
+      }
+    }
+  }
+}
+
 template <int MODE>
 static cudaError_t launch_search_amino(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff,
                                        uint64_t nq, void* d_out, uint32_t* d_ticket, const SearchVariant& v,
@@ -2172,6 +2347,30 @@ static cudaError_t launch_search_amino(const IndexView& ix, const uint64_t* d_qw
   int per_sm = 0;
   cudaError_t e = cudaMemsetAsync(d_ticket, 0, 4, s);
   if (e != cudaSuccess) return e;
+  if (in_text && MODE != OUT_RANGE_U64 && v.slots < 0 && v.blocks_per_sm == 0) {
+    // default with the text on the device: the wave kernel, then the refilling kernel over what it handed on
+    // (awry_set_search_variant(80) keeps the refilling kernel for everything)
+    constexpr int M = MODE == OUT_RANGE_U64 ? OUT_COUNT_U64 : MODE;
+    uint32_t* const d_defer = d_ticket;
+    if ((e = cudaMemsetAsync(d_defer + nq + 1, 0, 12, s)) != cudaSuccess) return e;  // ticket, rest count, rest ticket
+    auto wave = search_amino_wave_kernel<M, TPB, 6>;
+    auto rest = search_amino_kernel<M, TPB, 6, true, true>;
+    int per_w = 0, per_r = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_w, wave, TPB, 0)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_r, rest, TPB, 0)) != cudaSuccess) return e;
+    const uint64_t need = (nq * 4 + TPB - 1) / TPB;
+    const unsigned grid_w = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * std::max(1, per_w), need)));
+    const unsigned grid_r = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(sm_count) * std::max(1, per_r), need)));
+    const uint32_t wave_ticket = nq >= uint64_t(grid_w) * (TPB / 32) * 128 ? 32u : 8u;
+    const ByteRange br{v.b_lo, v.b_hi};
+    e = launch_with_table_window(wave, grid_w, TPB, s, ix, ix, d_qwords, d_qoff, nq, d_out, d_defer, wave_ticket, br);
+    COUNT_LAUNCH();
+    if (e != cudaSuccess) return e;
+    e = launch_with_table_window(rest, grid_r, TPB, s, ix, ix, d_qwords, d_qoff, nq, d_out, d_defer + nq + 3,
+                                 ticket_size(v.avg_len), br);
+    COUNT_LAUNCH();
+    return e;
+  }
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, 0);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;

@@ -22,7 +22,7 @@ timeout 150 ncu --set full --clock-control none --import-source on -k regex:sear
   -o gpurun_out/${T}_prof_lf python bench.py --steps 1 --warmup 3 --count-variant 1 --no-cpu-baseline --no-locate --no-e2e --no-secondary \
   > gpurun_out/${T}_ncu_full_lf.log 2>&1; echo "ncu full (backward search only) rc=$?"
 timeout 60 python scripts/cfg4_ncu_target.py > gpurun_out/${T}_cfg4_target.log 2>&1 && \
-timeout 150 ncu --set full --clock-control none --import-source on -k regex:search_amino_kernel -s 2 -c 1 -f \
+timeout 150 ncu --set full --clock-control none --import-source on -k regex:search_amino_wave_kernel -s 2 -c 1 -f \
   -o gpurun_out/${T}_prof_amino python scripts/cfg4_ncu_target.py > gpurun_out/${T}_ncu_amino.log 2>&1; echo "ncu amino rc=$?"
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv \
   --log-file gpurun_out/${T}_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-secondary \

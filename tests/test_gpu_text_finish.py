@@ -252,11 +252,14 @@ def test_protein_counts_and_hits_through_the_text(po, fx):
         assert ix.device_bytes()["text"] > 0
         for count_variant in (0, 1):
             f.set_count_variant(count_variant)
-            assert np.array_equal(ix.count_packed(qb, qo), want), count_variant
-            off, hits = ix.locate_packed(qb, qo)
-            assert np.array_equal(off, woff) and np.array_equal(hits, whits), count_variant
+            for kernel in (0, 80):                          # wave kernel / refilling kernel
+                f.set_search_variant(kernel)
+                assert np.array_equal(ix.count_packed(qb, qo), want), (count_variant, kernel)
+                off, hits = ix.locate_packed(qb, qo)
+                assert np.array_equal(off, woff) and np.array_equal(hits, whits), (count_variant, kernel)
     finally:
         f.set_count_variant(0)
+        f.set_search_variant(0)
         ix.close()
 
 
