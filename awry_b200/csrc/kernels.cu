@@ -1870,6 +1870,8 @@ template <int MODE>
 static cudaError_t launch_search_wave(const IndexView& ix, const uint64_t* d_qwords, const uint64_t* d_qoff, uint64_t nq,
                                       void* d_out, uint32_t* d_defer, int sm_count, cudaStream_t s, uint32_t avg_len,
                                       ByteRange br) {
+  // 6 x 256 threads/SM (40 registers, 8-16 bytes of spill) beat 5 x 256 (47 registers, none): 1.70 against 1.80 ms
+  // per 10 M x 150-bp reads with a k = 13 seed table
   constexpr int TPB = 256, MINB = 6;
   cudaError_t e = cudaMemsetAsync(d_defer + nq + 2, 0, 8, s);  // count of the rest list, its ticket counter
   if (e != cudaSuccess) return e;
